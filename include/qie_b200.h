@@ -1,0 +1,202 @@
+/*
+ * qie_b200.h -- C ABI of libqie_b200.so, the B200-native (sm_100a) replacement for the
+ * decode/prefill forward of Rafae1130/qwen_inference_engine.
+ *
+ * Everything here is `extern "C"`, plain pointers / integers / sizes; no C++ or torch
+ * types cross the boundary.  Two levels, mirroring the two levels of the reference's
+ * header API; citations are relative to /root/reference/layers/:
+ *
+ *   (1) operator level  -- one entry point per reference __global__ / launch_* wrapper
+ *                          (include/layers_include.cuh:15-35, include/helpers.cuh:45-166).
+ *                          Device pointers in, device pointers out, explicit stream.
+ *   (2) driver level    -- what iengine's main() drives (include/iengine.cuh:51-55,
+ *                          include/utils.hh:90-105, include/tensor_parser.hh:47-52):
+ *                          checkpoint load, sequences, KV pages, prefill / decode.
+ *
+ * Error behaviour: every function returns 0 on success or a negative QIE_E* code;
+ * qie_last_error() returns a thread-local message.  Token ids are never used to carry
+ * errors (the reference returns token 0 on CUDA failure, src/qwen_main.cu:135,262).
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * QIE_ECUDA.
+ */
+#ifndef QIE_B200_H
+#define QIE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QIE_OK 0
+#define QIE_EINVAL (-1)   /* bad argument / unsupported shape */
+#define QIE_ECUDA (-2)    /* CUDA runtime or launch failure   */
+#define QIE_EIO (-3)      /* checkpoint file problem          */
+#define QIE_ENOMEM (-4)   /* device memory or KV pages exhausted */
+#define QIE_ESTATE (-5)   /* call not valid in the current sequence state */
+
+typedef void* qie_stream;      /* cudaStream_t */
+typedef uint16_t qie_bf16;     /* raw __nv_bfloat16 bits */
+
+const char* qie_last_error(void);
+/* ABI version; bumped on any signature change. */
+int qie_abi_version(void);
+
+/* ------------------------------------------------------------------------------------
+ * (1) operator level.  All pointers are DEVICE pointers unless named h_*.
+ * Argument order follows the reference wrapper each one replaces.
+ * ---------------------------------------------------------------------------------- */
+
+/* embedding_matrix_func, src/embedded_matrix.cu:5-17: out[t,:] = table[ids[t],:] */
+int qie_embedding(qie_bf16* out, const qie_bf16* table, const int* ids, size_t hidden, size_t n_tok,
+                  qie_stream st);
+
+/* launch_rms -> rmsNorm, helpers.cuh:45-49 / src/normalization.cu:5-26.
+ * y = bf16((x / sqrt(sum(x^2)/hidden + 1e-4)) * w), sum in the reference's sequential
+ * fp32 FFMA order. */
+int qie_rmsnorm(const qie_bf16* x, const qie_bf16* w, qie_bf16* y, size_t hidden, size_t n_tok, qie_stream st);
+
+/* launch_matmul / proj -> matrix_mul, helpers.cuh:81-106,132-138 / src/matrix_mul.cu:165.
+ * C[M,K] = A[M,N] * B[K,N]^T (B in HF [out,in] layout); N = inner dim, K = out columns,
+ * exactly the reference's argument meaning.  fp32 accumulation through m16n8k16 bf16
+ * tensor-core MMAs fed in the reference's chunk order, one bf16 rounding at the end. */
+int qie_matmul(const qie_bf16* A, const qie_bf16* B, qie_bf16* C, int M, int N, int K, qie_stream st);
+
+/* launch_qknorm -> qkNorm, helpers.cuh:140-142 / src/qk_norm.cu:43-80 (in place). */
+int qie_qknorm(qie_bf16* x, const qie_bf16* w, int head_dim, int n_tok, int row_dim, int n_heads, qie_stream st);
+
+/* launch_rope / launch_rope_single -> RoPE, helpers.cuh:51-55,143-147 / src/RoPE.cu:6-22.
+ * cos/sin: fp32 tables [context, head_dim/2]; token t uses row pos0 + t. In place. */
+int qie_rope(const float* cos_t, const float* sin_t, qie_bf16* x, int n_tok, int pos0, int head_dim, int row_dim,
+             int n_heads, qie_stream st);
+
+/* precompute_cos_sin, src/include.cpp:5-18 (host libm, fp32). HOST pointers. */
+int qie_precompute_cos_sin(float* h_cos, float* h_sin, int seq_len, int head_dim);
+
+/* launch_act -> activation (SiLU), launch_elem -> element_mul, launch_resadd ->
+ * residual_add; helpers.cuh:108-119. */
+int qie_silu(qie_bf16* x, size_t n, qie_stream st);
+int qie_elem_mul(const qie_bf16* a, const qie_bf16* b, qie_bf16* c, size_t n, qie_stream st);
+int qie_residual_add(qie_bf16* a, const qie_bf16* b, size_t n, qie_stream st);
+
+/* KV pool geometry used by the operator-level attention / store entry points.
+ * B200 layout (DESIGN.md "KV pool"): one allocation,
+ *   pool[page][layer][k|v][kv_head][slot][head_dim]   (bf16)
+ * replacing the reference's linked list of per-page cudaMallocs laid out
+ * [slot][layer][kv_dim] (include/iengine.cuh:42-48, src/include_cuda.cu:165-279). */
+typedef struct {
+  qie_bf16* pool;
+  int n_pages, page_size, n_layers, n_kv_heads, head_dim;
+} qie_kv_view;
+
+/* kv_copy_layer_to_cache_{prefill,decode}, src/include_cuda.cu:165-279: scatter rows of
+ * K,V ([n_tok, n_kv*hd]) of `layer` to positions pos[t] of the sequence whose page ids
+ * are block_table[slot[t]*max_pages + ...]. */
+int qie_kv_store(const qie_kv_view* kv, int layer, const qie_bf16* K, const qie_bf16* V, const int* pos,
+                 const int* slot, const int* block_table, int max_pages, int n_tok, qie_stream st);
+
+/* launch_attn -> selfattention, helpers.cuh:121-130 / src/self_attension.cu:10-149.
+ * Row t (query token) of Q attends to cache positions 0..pos[t] of its sequence
+ * (prefill: causal; decode: the whole cache).  Reference arithmetic order. */
+int qie_attention(const qie_kv_view* kv, int layer, const qie_bf16* Q, qie_bf16* out, const int* pos,
+                  const int* slot, const int* block_table, int max_pages, int n_tok, int n_q_heads,
+                  qie_stream st);
+
+/* sample_topk_bf16 -> topk_temperature_softmax_sampling_kernel_bf16,
+ * helpers.cuh:157-166 / src/logit_decode.cu:149-274. One row of `vocab` bf16 logits per
+ * sequence; same arg-max tie-break and XORWOW stream (subsequence 0) as the reference.
+ * out_tokens: device int[n_rows]. seeds: per-row seed = seed + row*seed_stride. */
+int qie_sample_topk(const qie_bf16* logits, int* out_tokens, int n_rows, size_t vocab, float temperature, int k,
+                    uint64_t seed, uint64_t seed_stride, qie_stream st);
+
+/* ------------------------------------------------------------------------------------
+ * (2) driver level
+ * ---------------------------------------------------------------------------------- */
+
+typedef struct {
+  int hidden, inter, layers, n_q, n_kv, head_dim, vocab, context;
+} qie_config;
+
+typedef struct {
+  int device;            /* CUDA device ordinal */
+  int page_size;         /* KV positions per page (reference main() uses 4, iengine.cu:334) */
+  int max_pages;         /* KV pool size in pages; 0 = size from kv_bytes */
+  size_t kv_bytes;       /* KV pool bytes if max_pages == 0; 0 = 1 GiB default */
+  int max_seqs;          /* concurrently live sequences */
+  int max_batch_tokens;  /* rows per forward (prefill chunk or decode batch) */
+  int context;           /* RoPE table rows; 0 = 32786 as the reference (utills.cu:14) */
+  int head_dim_hint;     /* used only if the checkpoint has no q_norm tensor */
+  int use_graph;         /* replay decode steps from a CUDA graph */
+  int tp_rank, tp_size;  /* tensor-parallel shard (1 = off) */
+} qie_engine_opts;
+
+void qie_engine_opts_default(qie_engine_opts* o);
+
+typedef struct qie_engine qie_engine;
+
+/* Synthetic checkpoint in the reference's on-disk format: weights.bin + the text
+ * meta_data.txt that operator<< emits (src/tensor_parser.cpp:19-28). HOST side only. */
+int qie_synth_checkpoint_write(const qie_config* cfg, uint64_t seed, const char* meta_path,
+                               const char* weights_path);
+
+/* build_indexed_tensors + load_all_weights_to_gpu_chunked + initialize_model_buffers,
+ * tensor_parser.cpp:132-165, iengine.cu:117-223, utills.cu:4-129: parse meta_data.txt,
+ * upload weights.bin as ONE device blob, derive the model shape from tensor shapes. */
+int qie_engine_create(const char* meta_path, const char* weights_path, const qie_engine_opts* opts,
+                      qie_engine** out);
+/* Same engine, weights generated on the device by the same counter hash (no file). */
+int qie_engine_create_synthetic(const qie_config* cfg, uint64_t seed, const qie_engine_opts* opts,
+                                qie_engine** out);
+void qie_engine_destroy(qie_engine* e);
+int qie_engine_get_config(const qie_engine* e, qie_config* out);
+/* device pointer into the weight blob for (short_name, layer), as assign_weight_pointer
+ * helpers.cuh:18-29; *n_elems receives the element count. NULL on miss. */
+const qie_bf16* qie_engine_weight(const qie_engine* e, const char* short_name, int layer, size_t* n_elems);
+int qie_engine_kv_view(const qie_engine* e, qie_kv_view* out);
+qie_stream qie_engine_stream(const qie_engine* e);
+
+/* sampling parameters applied by prefill/decode (defaults: top-k 1 = greedy).
+ * The reference hard-codes k=50, T=1.0 prefill / 0.7 decode, seed 1234(+step)
+ * (qwen_main.cu:241,381-388). per-step seed = seed + step when add_step != 0. */
+int qie_engine_set_sampling(qie_engine* e, int topk, float temperature_prefill, float temperature_decode,
+                            uint64_t seed, int add_step);
+
+/* create_new_sequence + create_page_list (iengine.cu:25-47,73-87). Returns a slot id. */
+int qie_seq_new(qie_engine* e, int* seq);
+/* free_page_list + destroy_model_buffers (iengine.cu:98-109, utills.cu:147-205). */
+int qie_seq_free(qie_engine* e, int seq);
+int qie_seq_len(const qie_engine* e, int seq);
+int qie_kv_pages_free(const qie_engine* e);
+
+/* llm() with state == prefill, qwen_main.cu:74-247. h_ids: HOST int32[n]. The sampled
+ * token is written to *h_token (HOST). */
+int qie_prefill(qie_engine* e, int seq, const int32_t* h_ids, int n, int32_t* h_token);
+/* llm() with state == decode, qwen_main.cu:250-404, for a batch of sequences:
+ * h_seqs[i] consumes h_tokens_in[i] and produces h_tokens_out[i]. HOST buffers; one H2D
+ * and one D2H per call. */
+int qie_decode_step(qie_engine* e, const int* h_seqs, const int32_t* h_tokens_in, int n, int32_t* h_tokens_out);
+/* Greedy/top-k multi-step decode that feeds sampled tokens back on the device:
+ * h_tokens_out is HOST int32[steps*n] (step-major). h_tokens_in is the first input. */
+int qie_decode_run(qie_engine* e, const int* h_seqs, const int32_t* h_tokens_in, int n, int steps,
+                   int32_t* h_tokens_out);
+
+/* Device-resident variant used for kernel-only timing: token ids stay on the device
+ * (the previous step's samples), no host copies, no synchronisation. */
+int qie_decode_step_device(qie_engine* e, const int* h_seqs, int n);
+int qie_sync(qie_engine* e);
+
+/* Parity hooks (the reference's dump_device_bf16, qwen_main.cu:42-61). When capture is
+ * on, every forward keeps per-layer activations; qie_capture_read copies one of them to
+ * HOST memory. Tags: input_norm q k v attn x_attn mlp_h x_out (layer >= 0), logits
+ * (layer = -1). Returns the element count or a negative error. */
+int qie_capture_enable(qie_engine* e, int on);
+long qie_capture_read(qie_engine* e, const char* tag, int layer, qie_bf16* h_out, size_t max_elems);
+
+/* launch statistics of the last forward: kernels launched by this library. */
+long qie_launch_count(const qie_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

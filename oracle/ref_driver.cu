@@ -1,0 +1,402 @@
+// ref_driver.cu -- TEST INFRASTRUCTURE ONLY (oracle/).  Thin extern "C" driver around
+// the reference's OWN kernels and launch wrappers, compiled from the sources where they
+// lie under /root/reference/layers (see oracle/Makefile; nothing of the reference is
+// copied into this repository).  It exists so that tests can compare libqie_b200's
+// results with the reference's on a B200 bit for bit, and so that bench.py --impl
+// reference can time the reference's CUDA path.
+//
+// Why a replay and not llm() itself: llm() (src/qwen_main.cu:64-417) hard-wires the
+// Qwen3-14B dimensions (literal 5120s) and prints/dumps per layer.
+// ref_forward_* below issues exactly llm()'s kernel sequence through the reference's
+// helpers.cuh wrappers with the dimensions taken from a struct instead, including the
+// cudaDeviceSynchronize() calls llm() makes in its decode branch.
+//
+// The only reference file that is not dimension-generic is src/self_attension.cu
+// ("/ 5" and "num_layers = 40" at :33,35,116,118); oracle/Makefile compiles a sed-patched
+// temporary copy in which those literals read two __device__ variables set through
+// qie_ref_set_attn_dims().
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <fcntl.h>
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "helpers.cuh"  // reference: launch_* wrappers (non-inline: include from ONE TU only)
+
+void precompute_cos_sin(float* cos_values, float* sin_values, int seq_len, int head_dim);
+extern "C" void qie_ref_set_attn_dims(int group, int layers);  // appended to the patched attention TU
+
+// Referenced only by the reference's main() (src/iengine.cu:226, compiled with
+// -Dmain=qie_ref_unused_main to get create_page_list & co.); never called from here.
+std::vector<tensor> parsed_tensors() { abort(); }
+std::unordered_map<std::string, std::vector<tensor>> build_indexed_tensors() { abort(); }
+void initialize_model_buffers(ModelBuffers&, int*, TensorTable&, std::ifstream&, size_t) { abort(); }
+int llm(batch_metadata*, std::unordered_map<std::string, std::vector<tensor>>, std::ifstream&, page_table*, int,
+        __nv_bfloat16*) {
+  abort();
+}
+
+namespace {
+struct Quiet {  // the reference prints from kv_copy_layer_to_cache_decode (include_cuda.cu:267) etc.
+  int saved = -1;
+  Quiet() {
+    fflush(stdout);
+    saved = dup(1);
+    int nul = open("/dev/null", O_WRONLY);
+    dup2(nul, 1);
+    close(nul);
+  }
+  ~Quiet() {
+    fflush(stdout);
+    std::cout.flush();
+    dup2(saved, 1);
+    close(saved);
+  }
+};
+int sync_check(const char* what) {
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    fprintf(stderr, "ref_driver: %s: %s\n", what, cudaGetErrorString(e));
+    return -1;
+  }
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+// ------------------------------------------------------------------ single operators
+int ref_embedding(__nv_bfloat16* out, __nv_bfloat16* table, int* ids, size_t hidden, size_t n_tok) {
+  int threads = 256, blocks = (int)((n_tok + threads - 1) / threads);  // utills.cu:51-54
+  embedding_matrix_func<<<blocks, threads>>>(out, table, ids, hidden, n_tok);
+  return sync_check("embedding");
+}
+int ref_rmsnorm(__nv_bfloat16* x, __nv_bfloat16* w, __nv_bfloat16* y, size_t hidden, size_t seqlen) {
+  launch_rms(x, w, y, hidden, seqlen);
+  return sync_check("rmsNorm");
+}
+int ref_matmul(__nv_bfloat16* A, __nv_bfloat16* B, __nv_bfloat16* C, int M, int N, int K) {
+  launch_matmul(A, B, C, M, N, K);
+  return sync_check("matrix_mul");
+}
+int ref_qknorm(__nv_bfloat16* X, __nv_bfloat16* w, int head_dim, int seqlen, int hidden, int nheads) {
+  launch_qknorm(X, w, head_dim, seqlen, hidden, nheads);
+  return sync_check("qkNorm");
+}
+int ref_rope(float* cos_d, float* sin_d, __nv_bfloat16* x, size_t seqlen, size_t head_dim, size_t hidden_dim,
+             size_t nheads) {
+  launch_rope(cos_d, sin_d, x, seqlen, head_dim, hidden_dim, nheads);
+  return sync_check("RoPE");
+}
+int ref_rope_single(float* cos_d, float* sin_d, __nv_bfloat16* x, size_t pos, size_t head_dim, int hidden_dim,
+                    int nheads) {
+  launch_rope_single(cos_d, sin_d, x, pos, head_dim, hidden_dim, nheads);
+  return sync_check("RoPE single");
+}
+int ref_act(__nv_bfloat16* x, size_t n) {
+  launch_act(x, n);
+  return sync_check("activation");
+}
+int ref_elem(__nv_bfloat16* a, __nv_bfloat16* b, __nv_bfloat16* out, int n) {
+  launch_elem(a, b, out, n);
+  return sync_check("element_mul");
+}
+int ref_resadd(__nv_bfloat16* x, __nv_bfloat16* y, size_t n) {
+  launch_resadd(x, y, n);
+  return sync_check("residual_add");
+}
+int ref_sample(__nv_bfloat16* logits, int vocab, float temperature, int topk, unsigned long long seed, int step) {
+  return sample_topk_bf16(logits, vocab, temperature, topk, seed, step);
+}
+void ref_precompute_cos_sin(float* c, float* s, int seq_len, int head_dim) {
+  precompute_cos_sin(c, s, seq_len, head_dim);
+}
+
+// ------------------------------------------------------------------ page list
+void* ref_pages_create(int n_pages, size_t elems_per_page) {
+  page_table* head = create_page_list(n_pages);
+  for (page_table* p = head; p; p = p->ptr_to_next_page) {
+    allocate_page_buffers(p, elems_per_page);
+    cudaMemset(p->k_page_ptr, 0, elems_per_page * 2);
+    cudaMemset(p->v_page_ptr, 0, elems_per_page * 2);
+  }
+  return head;
+}
+void ref_pages_free(void* h) {  // free_page_list() std::free()s managed memory (iengine.cu:104); do it properly
+  page_table* p = (page_table*)h;
+  while (p) {
+    page_table* nx = p->ptr_to_next_page;
+    if (p->k_page_ptr) cudaFree(p->k_page_ptr);
+    if (p->v_page_ptr) cudaFree(p->v_page_ptr);
+    cudaFree(p);
+    p = nx;
+  }
+}
+int ref_pages_count(void* h) {
+  int n = 0;
+  for (page_table* p = (page_table*)h; p; p = p->ptr_to_next_page) ++n;
+  return n;
+}
+// copy page `idx` K or V buffer to host (elems bf16)
+int ref_pages_read(void* h, int idx, int which, __nv_bfloat16* host, size_t elems) {
+  page_table* p = (page_table*)h;
+  for (int i = 0; i < idx && p; ++i) p = p->ptr_to_next_page;
+  if (!p) return -1;
+  cudaMemcpy(host, which ? p->v_page_ptr : p->k_page_ptr, elems * 2, cudaMemcpyDeviceToHost);
+  return 0;
+}
+
+int ref_pages_write(void* h, int idx, int which, const __nv_bfloat16* host, size_t elems) {
+  page_table* p = (page_table*)h;
+  for (int i = 0; i < idx && p; ++i) p = p->ptr_to_next_page;
+  if (!p) return -1;
+  cudaMemcpy(which ? p->v_page_ptr : p->k_page_ptr, host, elems * 2, cudaMemcpyHostToDevice);
+  return 0;
+}
+
+int ref_attn(__nv_bfloat16* Q, __nv_bfloat16* out, size_t mq, size_t mkv, size_t head_dim, size_t hidden,
+             size_t hidden_kv, int causal, size_t q_abs_base, int layer_id, void* pages, int page_size, int n_layers) {
+  qie_ref_set_attn_dims((int)((hidden / head_dim) / (hidden_kv / head_dim)), n_layers);
+  launch_attn(Q, out, mq, mkv, head_dim, hidden, hidden_kv, causal, q_abs_base, layer_id, (page_table*)pages,
+              page_size);
+  return sync_check("selfattention");
+}
+
+// ------------------------------------------------------------------ llm() replay
+struct ref_layer_w {
+  __nv_bfloat16 *in_ln, *q, *k, *v, *o, *q_norm, *k_norm, *post_ln, *up, *gate, *down;
+};
+struct ref_model_desc {
+  int hidden, inter, layers, n_q, n_kv, head_dim, vocab, context;
+  __nv_bfloat16 *embed, *norm, *lm_head;
+  const ref_layer_w* L;  // host array [layers] of DEVICE pointers
+};
+
+struct ref_seq {
+  ref_model_desc m;
+  std::vector<ref_layer_w> L;
+  ModelBuffers buf;  // the reference's own struct (include/utils.hh:14-88)
+  page_table* pages = nullptr;
+  int page_size = 4;
+  int cap_tok = 0;
+  int step = 0;
+  int* d_tok = nullptr;
+};
+
+static void seq_alloc(ref_seq* s, int n_tok) {
+  ModelBuffers& b = s->buf;
+  const ref_model_desc& m = s->m;
+  size_t H = m.hidden, Dq = (size_t)m.n_q * m.head_dim, Dkv = (size_t)m.n_kv * m.head_dim, I = m.inter;
+  auto A = [&](__nv_bfloat16*& p, size_t n) {
+    if (p) cudaFree(p);
+    cudaMalloc(&p, n * sizeof(__nv_bfloat16));
+  };
+  A(b.embeddings_out, n_tok * H);
+  A(b.rms_out, n_tok * H);
+  A(b.Q, n_tok * Dq);
+  A(b.K, n_tok * Dkv);
+  A(b.V, n_tok * Dkv);
+  A(b.atten_out, n_tok * Dq);
+  A(b.out_proj, n_tok * H);
+  A(b.MLP_UP, n_tok * I);
+  A(b.MLP_GATE, n_tok * I);
+  A(b.MLP_GATE_OUT, n_tok * I);
+  A(b.MLP_DOWN, n_tok * H);
+  if (b.d_token_ids) cudaFree(b.d_token_ids);
+  cudaMalloc(&b.d_token_ids, n_tok * sizeof(int));
+  s->cap_tok = n_tok;
+}
+
+void* ref_seq_create(const ref_model_desc* m, int page_size) {
+  ref_seq* s = new ref_seq();
+  s->m = *m;
+  s->L.assign(m->L, m->L + m->layers);
+  s->page_size = page_size;
+  ModelBuffers& b = s->buf;
+  memset(&b, 0, sizeof(b));
+  b.number_of_layers = m->layers;
+  b.head_dim = m->head_dim;
+  b.hidden_dim = m->hidden;
+  b.hidden_dim_kv = (size_t)m->n_kv * m->head_dim;
+  b.num_of_qheads = m->n_q;
+  b.num_of_kvheads = m->n_kv;
+  b.context_size = m->context;
+  b.vocab_size = m->vocab;
+  b.up_dim = m->inter;
+  b.embeddings_d = m->embed;
+  size_t tab = (size_t)m->context * (m->head_dim / 2) * sizeof(float);
+  b.cos_values_h = (float*)malloc(tab);
+  b.sin_values_h = (float*)malloc(tab);
+  precompute_cos_sin(b.cos_values_h, b.sin_values_h, m->context, m->head_dim);  // utills.cu:36-44
+  cudaMalloc(&b.cos_values_d, tab);
+  cudaMalloc(&b.sin_values_d, tab);
+  cudaMemcpy(b.cos_values_d, b.cos_values_h, tab, cudaMemcpyHostToDevice);
+  cudaMemcpy(b.sin_values_d, b.sin_values_h, tab, cudaMemcpyHostToDevice);
+  cudaMalloc(&b.last_x, m->hidden * sizeof(__nv_bfloat16));
+  cudaMalloc(&b.prefill_output_d, (size_t)m->vocab * sizeof(__nv_bfloat16));
+  cudaMalloc(&s->d_tok, sizeof(int));
+  qie_ref_set_attn_dims(m->n_q / m->n_kv, m->layers);
+  return s;
+}
+
+void ref_seq_destroy(void* h) {
+  ref_seq* s = (ref_seq*)h;
+  if (!s) return;
+  cudaDeviceSynchronize();
+  ModelBuffers& b = s->buf;
+  void* dev[] = {b.embeddings_out, b.rms_out, b.Q, b.K, b.V, b.atten_out, b.out_proj, b.MLP_UP, b.MLP_GATE,
+                 b.MLP_GATE_OUT, b.MLP_DOWN, b.d_token_ids, b.cos_values_d, b.sin_values_d, b.last_x,
+                 b.prefill_output_d, s->d_tok};
+  for (void* p : dev)
+    if (p) cudaFree(p);
+  free(b.cos_values_h);
+  free(b.sin_values_h);
+  ref_pages_free(s->pages);
+  delete s;
+}
+
+int ref_seq_len(void* h) { return (int)((ref_seq*)h)->buf.sequence_len; }
+void* ref_seq_pages(void* h) { return ((ref_seq*)h)->pages; }
+
+// read back an activation buffer of the last forward (n bf16 values)
+int ref_seq_read(void* h, const char* tag, __nv_bfloat16* host, size_t n) {
+  ref_seq* s = (ref_seq*)h;
+  ModelBuffers& b = s->buf;
+  __nv_bfloat16* p = nullptr;
+  if (!strcmp(tag, "logits")) p = b.prefill_output_d;
+  else if (!strcmp(tag, "x")) p = b.embeddings_out;
+  else if (!strcmp(tag, "q")) p = b.Q;
+  else if (!strcmp(tag, "attn")) p = b.atten_out;
+  else if (!strcmp(tag, "mlp_h")) p = b.MLP_GATE_OUT;
+  if (!p) return -1;
+  cudaMemcpy(host, p, n * 2, cudaMemcpyDeviceToHost);
+  return 0;
+}
+
+// per-layer tap: if tap != NULL it receives (tag, layer, device ptr, elems) after each stage
+typedef void (*ref_tap_fn)(void* user, const char* tag, int layer, const __nv_bfloat16* dev, size_t n);
+
+// the 18-kernel layer body shared by both branches (qwen_main.cu:77-222 / :271-365)
+static int layer_body(ref_seq* s, int i, int m_rows, bool decode, bool with_syncs, ref_tap_fn tap, void* user) {
+  ModelBuffers* b = &s->buf;
+  const ref_layer_w& w = s->L[i];
+  const int H = (int)b->hidden_dim, Dq = (int)(b->num_of_qheads * b->head_dim), Dkv = (int)b->hidden_dim_kv,
+            I = (int)b->up_dim;
+#define SYNC() \
+  if (with_syncs) cudaDeviceSynchronize()
+#define TAP(tag, ptr, n) \
+  if (tap) tap(user, tag, i, ptr, n)
+  launch_rms(b->embeddings_out, w.in_ln, b->rms_out, H, m_rows);
+  SYNC();
+  TAP("input_norm", b->rms_out, (size_t)m_rows * H);
+  launch_matmul(b->rms_out, w.q, b->Q, m_rows, H, Dq);
+  SYNC();
+  launch_matmul(b->rms_out, w.k, b->K, m_rows, H, Dkv);
+  launch_matmul(b->rms_out, w.v, b->V, m_rows, H, Dkv);
+  if (w.q_norm) launch_qknorm(b->Q, w.q_norm, (int)b->head_dim, m_rows, Dq, (int)b->num_of_qheads);
+  if (w.k_norm) launch_qknorm(b->K, w.k_norm, (int)b->head_dim, m_rows, Dkv, (int)b->num_of_kvheads);
+  if (!decode) {
+    launch_rope(b->cos_values_d, b->sin_values_d, b->Q, m_rows, b->head_dim, Dq, b->num_of_qheads);
+    launch_rope(b->cos_values_d, b->sin_values_d, b->K, m_rows, b->head_dim, Dkv, b->num_of_kvheads);
+    kv_copy_layer_to_cache_prefill(b, i, s->pages, s->page_size);
+  } else {
+    launch_rope_single(b->cos_values_d, b->sin_values_d, b->Q, b->sequence_len - 1, b->head_dim, Dq,
+                       (int)b->num_of_qheads);
+    SYNC();
+    launch_rope_single(b->cos_values_d, b->sin_values_d, b->K, b->sequence_len - 1, b->head_dim, Dkv,
+                       (int)b->num_of_kvheads);
+    SYNC();
+    kv_copy_layer_to_cache_decode(b, i, s->pages, s->page_size);
+    SYNC();
+  }
+  TAP("q", b->Q, (size_t)m_rows * Dq);
+  TAP("v", b->V, (size_t)m_rows * Dkv);
+  if (!decode)
+    launch_attn(b->Q, b->atten_out, m_rows, b->sequence_len, b->head_dim, Dq, Dkv, 1, 0, i, s->pages, s->page_size);
+  else
+    launch_attn(b->Q, b->atten_out, 1, b->sequence_len, b->head_dim, Dq, Dkv, 0, b->sequence_len - 1, i, s->pages,
+                s->page_size);
+  TAP("attn", b->atten_out, (size_t)m_rows * Dq);
+  launch_matmul(b->atten_out, w.o, b->out_proj, m_rows, Dq, H);
+  launch_resadd(b->embeddings_out, b->out_proj, (size_t)m_rows * H);
+  TAP("x_attn", b->embeddings_out, (size_t)m_rows * H);
+  launch_rms(b->embeddings_out, w.post_ln, b->rms_out, H, m_rows);
+  launch_matmul(b->rms_out, w.up, b->MLP_UP, m_rows, H, I);
+  launch_matmul(b->rms_out, w.gate, b->MLP_GATE, m_rows, H, I);
+  launch_act(b->MLP_GATE, (size_t)m_rows * I);
+  launch_elem(b->MLP_UP, b->MLP_GATE, b->MLP_GATE_OUT, m_rows * I);
+  TAP("mlp_h", b->MLP_GATE_OUT, (size_t)m_rows * I);
+  launch_matmul(b->MLP_GATE_OUT, w.down, b->MLP_DOWN, m_rows, I, H);
+  launch_resadd(b->embeddings_out, b->MLP_DOWN, (size_t)m_rows * H);
+  TAP("x_out", b->embeddings_out, (size_t)m_rows * H);
+#undef SYNC
+#undef TAP
+  return 0;
+}
+
+// prefill branch, qwen_main.cu:74-247 (+ the set-up main() does, iengine.cu:327-351)
+int ref_forward_prefill(void* h, const int* ids, int n_tok, int topk, float temperature, unsigned long long seed,
+                        ref_tap_fn tap, void* user) {
+  ref_seq* s = (ref_seq*)h;
+  Quiet q;
+  ModelBuffers* b = &s->buf;
+  seq_alloc(s, n_tok);
+  b->sequence_len = n_tok;
+  cudaMemcpy(b->d_token_ids, ids, n_tok * sizeof(int), cudaMemcpyHostToDevice);
+  int pages_required = ((n_tok + s->page_size - 1) / s->page_size) + 1;  // iengine.cu:338
+  size_t elems = (size_t)s->page_size * b->number_of_layers * b->hidden_dim_kv;
+  s->pages = (page_table*)ref_pages_create(pages_required, elems);
+  b->k_cache = s->pages->k_page_ptr;  // iengine.cu:359-360
+  b->v_cache = s->pages->v_page_ptr;
+  int threads = 256, blocks = (n_tok + threads - 1) / threads;
+  embedding_matrix_func<<<blocks, threads>>>(b->embeddings_out, b->embeddings_d, b->d_token_ids, b->hidden_dim,
+                                             b->sequence_len);
+  for (int i = 0; i < (int)b->number_of_layers; ++i) layer_body(s, i, n_tok, false, false, tap, user);
+  launch_rms(b->embeddings_out, s->m.norm, b->rms_out, b->hidden_dim, b->sequence_len);
+  copy_last_vocab_vec(b->rms_out, b->last_x, (int)b->hidden_dim, (int)b->sequence_len);
+  launch_matmul(b->last_x, s->m.lm_head, b->prefill_output_d, 1, (int)b->hidden_dim, (int)b->vocab_size);
+  if (sync_check("prefill")) return -1000000;
+  int tok = sample_topk_bf16(b->prefill_output_d, (int)b->vocab_size, temperature, topk, seed, 0);
+  s->step = 1;  // iengine.cu:419
+  return tok;
+}
+
+// decode branch, qwen_main.cu:250-404, one token
+int ref_forward_decode(void* h, int token, int topk, float temperature, unsigned long long seed, int with_syncs,
+                       ref_tap_fn tap, void* user) {
+  ref_seq* s = (ref_seq*)h;
+  Quiet q;
+  ModelBuffers* b = &s->buf;
+  int* d_token_ids_decode;
+  cudaMalloc((void**)&d_token_ids_decode, sizeof(int));  // :254 (per-call malloc is part of the reference)
+  cudaMemcpy(d_token_ids_decode, &token, sizeof(int), cudaMemcpyHostToDevice);
+  if (with_syncs) cudaDeviceSynchronize();
+  b->sequence_len = b->sequence_len + 1;
+  embedding_matrix_func<<<1, 1>>>(b->embeddings_out, b->embeddings_d, d_token_ids_decode, b->hidden_dim, 1);
+  if (with_syncs) cudaDeviceSynchronize();
+  for (int i = 0; i < (int)b->number_of_layers; ++i) layer_body(s, i, 1, true, with_syncs != 0, tap, user);
+  launch_rms(b->embeddings_out, s->m.norm, b->rms_out, b->hidden_dim, 1);
+  copy_first_token(b->rms_out, b->last_x, (int)b->hidden_dim);
+  launch_matmul(b->last_x, s->m.lm_head, b->prefill_output_d, 1, (int)b->hidden_dim, (int)b->vocab_size);
+  if (sync_check("decode")) return -1000000;
+  int* d_output_token;
+  cudaMalloc(&d_output_token, sizeof(int));  // :383
+  cudaDeviceSynchronize();
+  topk_temperature_softmax_sampling_kernel_bf16<<<1, 256>>>(b->prefill_output_d, d_output_token, temperature, topk,
+                                                            b->vocab_size, seed + s->step, 0);
+  cudaDeviceSynchronize();
+  int out = 0;
+  cudaMemcpy(&out, d_output_token, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaDeviceSynchronize();
+  cudaFree(d_output_token);
+  cudaFree(d_token_ids_decode);
+  s->step += 1;
+  return out;
+}
+
+}  // extern "C"

@@ -1,0 +1,736 @@
+// capi.cu -- the extern "C" boundary declared in include/qie_b200.h.
+#include <math.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "engine.h"
+
+using namespace qie;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+  return fail(QIE_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+#define CU(expr)                                        \
+  do {                                                  \
+    cudaError_t _e = (expr);                            \
+    if (_e != cudaSuccess) return cuda_fail(_e, #expr); \
+  } while (0)
+
+extern "C" {
+
+const char* qie_last_error(void) { return g_err; }
+int qie_abi_version(void) { return 1; }
+
+// ---------------------------------------------------------------- operator level
+int qie_embedding(qie_bf16* out, const qie_bf16* table, const int* ids, size_t hidden, size_t n_tok, qie_stream st) {
+  CU(launch_embedding((bf16*)out, (const bf16*)table, ids, hidden, n_tok, (cudaStream_t)st));
+  return QIE_OK;
+}
+int qie_rmsnorm(const qie_bf16* x, const qie_bf16* w, qie_bf16* y, size_t hidden, size_t n_tok, qie_stream st) {
+  if (hidden == 0 || hidden > 48 * 1024 / 4) return fail(QIE_EINVAL, "rmsnorm: hidden %zu unsupported", hidden);
+  CU(launch_rmsnorm_ref((const bf16*)x, (const bf16*)w, (bf16*)y, hidden, n_tok, hidden, (cudaStream_t)st));
+  return QIE_OK;
+}
+int qie_matmul(const qie_bf16* A, const qie_bf16* B, qie_bf16* C, int M, int N, int K, qie_stream st) {
+  // reference argument meaning (helpers.cuh:81): N = inner dim, K = output columns
+  if (M < 0 || N <= 0 || K <= 0 || (N & 7)) return fail(QIE_EINVAL, "matmul: need N %% 8 == 0 (got M=%d N=%d K=%d)", M, N, K);
+  int dev = 0, sms = 0;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  for (int r0 = 0; r0 < M; r0 += 64) {
+    GemmArgs g{};
+    g.A = (const bf16*)A + (size_t)r0 * N;
+    g.lda = N;
+    g.M = std::min(64, M - r0);
+    g.K = N;
+    g.nseg = 1;
+    g.epi = EPI_STORE;
+    g.seg[0] = GemmSeg{(const bf16*)B, nullptr, (bf16*)C + (size_t)r0 * K, K, K};
+    CU(launch_gemm_ref_order(g, sms, (cudaStream_t)st));
+  }
+  return QIE_OK;
+}
+int qie_qknorm(qie_bf16* x, const qie_bf16* w, int head_dim, int n_tok, int row_dim, int n_heads, qie_stream st) {
+  if (head_dim != 64 && head_dim != 128 && head_dim != 256) return fail(QIE_EINVAL, "head_dim %d unsupported", head_dim);
+  CU(launch_qknorm_ref((bf16*)x, (const bf16*)w, head_dim, n_tok, row_dim, n_heads, (cudaStream_t)st));
+  return QIE_OK;
+}
+int qie_rope(const float* cos_t, const float* sin_t, qie_bf16* x, int n_tok, int pos0, int head_dim, int row_dim,
+             int n_heads, qie_stream st) {
+  if (head_dim != 64 && head_dim != 128 && head_dim != 256) return fail(QIE_EINVAL, "head_dim %d unsupported", head_dim);
+  CU(launch_rope_ref(cos_t, sin_t, (bf16*)x, n_tok, nullptr, pos0, head_dim, row_dim, n_heads, (cudaStream_t)st));
+  return QIE_OK;
+}
+int qie_precompute_cos_sin(float* h_cos, float* h_sin, int seq_len, int head_dim) {
+  // src/include.cpp:5-18 -- float operands throughout, so powf / cosf / sinf
+  if (!h_cos || !h_sin || seq_len < 0 || head_dim <= 0) return fail(QIE_EINVAL, "precompute_cos_sin: bad args");
+  float base = 1000000;
+  int half = head_dim / 2;
+  for (int i = 0; i < half; i++) {
+    float exponent = 2 * ((float)i / (float)head_dim);
+    float theta = powf(base, -exponent);
+    for (int pos = 0; pos < seq_len; pos++) {
+      h_cos[(size_t)pos * half + i] = cosf(pos * theta);
+      h_sin[(size_t)pos * half + i] = sinf(pos * theta);
+    }
+  }
+  return QIE_OK;
+}
+int qie_silu(qie_bf16* x, size_t n, qie_stream st) {
+  CU(launch_silu((bf16*)x, n, (cudaStream_t)st));
+  return QIE_OK;
+}
+int qie_elem_mul(const qie_bf16* a, const qie_bf16* b, qie_bf16* c, size_t n, qie_stream st) {
+  CU(launch_elem_mul((const bf16*)a, (const bf16*)b, (bf16*)c, n, (cudaStream_t)st));
+  return QIE_OK;
+}
+int qie_residual_add(qie_bf16* a, const qie_bf16* b, size_t n, qie_stream st) {
+  CU(launch_residual_add((bf16*)a, (const bf16*)b, n, (cudaStream_t)st));
+  return QIE_OK;
+}
+
+static KvGeom geom_of(const qie_kv_view* v) {
+  KvGeom g{};
+  g.pool = (bf16*)v->pool;
+  g.n_pages = v->n_pages;
+  g.page_size = v->page_size;
+  g.n_layers = v->n_layers;
+  g.n_kv = v->n_kv_heads;
+  g.hd = v->head_dim;
+  return g;
+}
+int qie_kv_store(const qie_kv_view* kv, int layer, const qie_bf16* K, const qie_bf16* V, const int* pos,
+                 const int* slot, const int* block_table, int max_pages, int n_tok, qie_stream st) {
+  if (!kv || layer < 0 || layer >= kv->n_layers) return fail(QIE_EINVAL, "kv_store: bad layer");
+  CU(launch_kv_store(geom_of(kv), layer, (const bf16*)K, (const bf16*)V, pos, slot, block_table, max_pages, n_tok,
+                     (cudaStream_t)st));
+  return QIE_OK;
+}
+int qie_attention(const qie_kv_view* kv, int layer, const qie_bf16* Q, qie_bf16* out, const int* pos, const int* slot,
+                  const int* block_table, int max_pages, int n_tok, int n_q_heads, qie_stream st) {
+  if (!kv || layer < 0 || layer >= kv->n_layers) return fail(QIE_EINVAL, "attention: bad layer");
+  AttnArgs a{};
+  a.q = (const bf16*)Q;
+  a.out = (bf16*)out;
+  a.pos = pos;
+  a.slot = slot;
+  a.block_table = block_table;
+  a.max_pages = max_pages;
+  a.n_tok = n_tok;
+  a.n_q = n_q_heads;
+  a.layer = layer;
+  a.max_kv_len = max_pages * kv->page_size;
+  a.kv = geom_of(kv);
+  CU(launch_attention_ref(a, (cudaStream_t)st));
+  return QIE_OK;
+}
+int qie_sample_topk(const qie_bf16* logits, int* out_tokens, int n_rows, size_t vocab, float temperature, int k,
+                    uint64_t seed, uint64_t seed_stride, qie_stream st) {
+  CU(launch_sample_topk((const bf16*)logits, out_tokens, n_rows, vocab, temperature, k, seed, seed_stride, nullptr,
+                        (cudaStream_t)st));
+  return QIE_OK;
+}
+
+// ---------------------------------------------------------------- driver level
+void qie_engine_opts_default(qie_engine_opts* o) {
+  memset(o, 0, sizeof(*o));
+  o->device = 0;
+  o->page_size = 16;
+  o->max_pages = 0;
+  o->kv_bytes = 0;
+  o->max_seqs = 64;
+  o->max_batch_tokens = 256;
+  o->context = 0;
+  o->head_dim_hint = 0;
+  o->use_graph = 1;
+  o->tp_rank = 0;
+  o->tp_size = 1;
+}
+
+int qie_synth_checkpoint_write(const qie_config* cfg, uint64_t seed, const char* meta_path,
+                               const char* weights_path) {
+  if (!cfg || !meta_path || !weights_path) return fail(QIE_EINVAL, "synth: null argument");
+  Checkpoint ck = synth_layout(*cfg);
+  FILE* fm = fopen(meta_path, "w");
+  if (!fm) return fail(QIE_EIO, "cannot write %s", meta_path);
+  write_meta(ck, fm);
+  fclose(fm);
+  FILE* fw = fopen(weights_path, "wb");
+  if (!fw) return fail(QIE_EIO, "cannot write %s", weights_path);
+  std::vector<uint16_t> buf(1 << 20);
+  for (const TensorInfo& t : ck.tensors) {
+    size_t elems = (t.end - t.begin) / 2, g0 = t.begin / 2;
+    for (size_t e0 = 0; e0 < elems; e0 += buf.size()) {
+      size_t m = std::min(buf.size(), elems - e0);
+      for (size_t j = 0; j < m; ++j) buf[j] = synth_value(seed, g0 + e0 + j, t.kind);
+      if (fwrite(buf.data(), 2, m, fw) != m) {
+        fclose(fw);
+        return fail(QIE_EIO, "short write to %s", weights_path);
+      }
+    }
+  }
+  fclose(fw);
+  return QIE_OK;
+}
+
+static void engine_free(qie_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->opts.device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (auto& kvp : e->graphs)
+    if (kvp.second.exec) cudaGraphExecDestroy(kvp.second.exec);
+  for (auto& kvp : e->cap)
+    if (kvp.second.d) cudaFree(kvp.second.d);
+  void* dev[] = {e->blob, e->cos_d, e->sin_d, e->kv.pool, e->block_table_d, e->ids_d, e->pos_d, e->slot_d,
+                 e->sampled_d, e->rowstep_d, e->x, e->xn, e->q, e->k, e->v, e->att, e->h, e->logits};
+  for (void* p : dev)
+    if (p) cudaFree(p);
+  if (e->block_table_h) cudaFreeHost(e->block_table_h);
+  if (e->stage_h) cudaFreeHost(e->stage_h);
+  if (e->sampled_h) cudaFreeHost(e->sampled_h);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+static int engine_finish_setup(qie_engine* e) {
+  const qie_config& c = e->cfg;
+  const qie_engine_opts& o = e->opts;
+  if (c.head_dim != 64 && c.head_dim != 128 && c.head_dim != 256)
+    return fail(QIE_EINVAL, "head_dim %d unsupported (64/128/256)", c.head_dim);
+  if ((c.hidden & 7) || (c.inter & 7)) return fail(QIE_EINVAL, "hidden/inter must be multiples of 8");
+  // weight pointers (assign_weight_pointer, helpers.cuh:18-29)
+  auto ptr = [&](const char* sn, int layer) -> const bf16* {
+    const TensorInfo* t = e->ck.find(sn, layer);
+    return t ? reinterpret_cast<const bf16*>(reinterpret_cast<const char*>(e->blob) + t->begin) : nullptr;
+  };
+  e->L.resize(c.layers);
+  for (int l = 0; l < c.layers; ++l) {
+    LayerWeights& w = e->L[l];
+    w.in_ln = ptr("input_layernorm.weight", l);
+    w.q = ptr("self_attn.q_proj.weight", l);
+    w.k = ptr("self_attn.k_proj.weight", l);
+    w.v = ptr("self_attn.v_proj.weight", l);
+    w.o = ptr("self_attn.o_proj.weight", l);
+    w.q_norm = ptr("self_attn.q_norm.weight", l);  // data-driven: absent in Qwen2.5 checkpoints
+    w.k_norm = ptr("self_attn.k_norm.weight", l);
+    w.post_ln = ptr("post_attention_layernorm.weight", l);
+    w.up = ptr("mlp.up_proj.weight", l);
+    w.gate = ptr("mlp.gate_proj.weight", l);
+    w.down = ptr("mlp.down_proj.weight", l);
+    if (!w.in_ln || !w.q || !w.k || !w.v || !w.o || !w.post_ln || !w.up || !w.gate || !w.down)
+      return fail(QIE_EIO, "layer %d: missing tensor in checkpoint", l);
+  }
+  e->embed = ptr("embed_tokens.weight", -1);
+  e->final_norm = ptr("norm.weight", -1);
+  e->lm_head = ptr("logits", -1);
+  if (!e->embed || !e->final_norm || !e->lm_head) return fail(QIE_EIO, "missing embed/norm/lm_head tensor");
+
+  // RoPE tables on the host with libm, exactly as the reference (include.cpp:5-18)
+  {
+    size_t nel = (size_t)c.context * (c.head_dim / 2);
+    std::vector<float> hc(nel), hs(nel);
+    qie_precompute_cos_sin(hc.data(), hs.data(), c.context, c.head_dim);
+    CU(cudaMalloc(&e->cos_d, nel * sizeof(float)));
+    CU(cudaMalloc(&e->sin_d, nel * sizeof(float)));
+    CU(cudaMemcpy(e->cos_d, hc.data(), nel * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(e->sin_d, hs.data(), nel * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  // KV pool
+  e->kv.page_size = o.page_size;
+  e->kv.n_layers = c.layers;
+  e->kv.n_kv = c.n_kv;
+  e->kv.hd = c.head_dim;
+  size_t page_bytes = e->kv.page_stride() * sizeof(bf16);
+  int n_pages = o.max_pages;
+  if (n_pages <= 0) {
+    size_t bytes = o.kv_bytes ? o.kv_bytes : ((size_t)1 << 30);
+    n_pages = (int)std::max<size_t>(1, bytes / page_bytes);
+  }
+  e->kv.n_pages = n_pages;
+  CU(cudaMalloc(&e->kv.pool, (size_t)n_pages * page_bytes));
+  CU(cudaMemsetAsync(e->kv.pool, 0, (size_t)n_pages * page_bytes, e->stream));
+  e->free_pages.resize(n_pages);
+  for (int i = 0; i < n_pages; ++i) e->free_pages[i] = n_pages - 1 - i;  // pop_back hands out 0,1,2,...
+  e->seqs.assign(o.max_seqs, Sequence());
+  e->max_pages_per_seq = std::min(n_pages, (c.context + o.page_size - 1) / o.page_size);
+  size_t bt = (size_t)o.max_seqs * e->max_pages_per_seq;
+  CU(cudaMalloc(&e->block_table_d, bt * sizeof(int)));
+  CU(cudaMemsetAsync(e->block_table_d, 0, bt * sizeof(int), e->stream));
+  CU(cudaMallocHost(&e->block_table_h, bt * sizeof(int)));
+  memset(e->block_table_h, 0, bt * sizeof(int));
+  // row metadata + activations
+  const size_t R = o.max_batch_tokens;
+  const size_t H = c.hidden, Dq = (size_t)c.n_q * c.head_dim, Dkv = (size_t)c.n_kv * c.head_dim, I = c.inter;
+  CU(cudaMalloc(&e->ids_d, R * sizeof(int)));
+  CU(cudaMalloc(&e->pos_d, R * sizeof(int)));
+  CU(cudaMalloc(&e->slot_d, R * sizeof(int)));
+  CU(cudaMalloc(&e->sampled_d, R * sizeof(int)));
+  CU(cudaMalloc(&e->rowstep_d, R * sizeof(int)));
+  CU(cudaMallocHost(&e->stage_h, 4 * R * sizeof(int)));
+  e->sampled_h_cap = R;
+  CU(cudaMallocHost(&e->sampled_h, e->sampled_h_cap * sizeof(int)));
+  CU(cudaMalloc(&e->x, R * H * sizeof(bf16)));
+  CU(cudaMalloc(&e->xn, R * std::max(H, Dq) * sizeof(bf16)));
+  CU(cudaMalloc(&e->q, R * Dq * sizeof(bf16)));
+  CU(cudaMalloc(&e->k, R * Dkv * sizeof(bf16)));
+  CU(cudaMalloc(&e->v, R * Dkv * sizeof(bf16)));
+  CU(cudaMalloc(&e->att, R * Dq * sizeof(bf16)));
+  CU(cudaMalloc(&e->h, R * I * sizeof(bf16)));
+  e->logits_rows = std::min<int>((int)R, o.max_seqs);
+  CU(cudaMalloc(&e->logits, (size_t)e->logits_rows * c.vocab * sizeof(bf16)));
+  CU(cudaStreamSynchronize(e->stream));
+  return QIE_OK;
+}
+
+static int engine_begin(const qie_engine_opts* opts, qie_engine** out_e) {
+  qie_engine_opts o;
+  if (opts) o = *opts;
+  else qie_engine_opts_default(&o);
+  if (o.page_size <= 0) o.page_size = 16;
+  if (o.max_seqs <= 0) o.max_seqs = 64;
+  if (o.max_batch_tokens <= 0) o.max_batch_tokens = 256;
+  if (o.context <= 0) o.context = 32786;  // sic, utills.cu:14
+  if (o.tp_size <= 0) o.tp_size = 1;
+  if (o.tp_size != 1) return fail(QIE_EINVAL, "tensor parallel engine not built yet (tp_size must be 1)");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(QIE_ECUDA, "no CUDA device (%s); libqie_b200 has no CPU fallback", cudaGetErrorString(ce));
+  if (o.device < 0 || o.device >= ndev) return fail(QIE_EINVAL, "device %d out of range", o.device);
+  CU(cudaSetDevice(o.device));
+  qie_engine* e = new qie_engine();
+  e->opts = o;
+  cudaError_t r = cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, o.device);
+  if (r == cudaSuccess) r = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+  if (r != cudaSuccess) {
+    delete e;
+    return cuda_fail(r, "engine init");
+  }
+  *out_e = e;
+  return QIE_OK;
+}
+
+int qie_engine_create(const char* meta_path, const char* weights_path, const qie_engine_opts* opts,
+                      qie_engine** out) {
+  if (!meta_path || !weights_path || !out) return fail(QIE_EINVAL, "engine_create: null argument");
+  qie_engine* e = nullptr;
+  int rc = engine_begin(opts, &e);
+  if (rc) return rc;
+  std::string err;
+  if (!parse_meta(meta_path, &e->ck, &err) ||
+      !derive_config(e->ck, e->opts.head_dim_hint, e->opts.context, &e->cfg, &err)) {
+    engine_free(e);
+    return fail(QIE_EIO, "%s", err.c_str());
+  }
+  // weights.bin -> one device blob, streamed through two pinned buffers
+  // (load_all_weights_to_gpu_chunked, iengine.cu:117-223, used one pageable 2 GiB buffer)
+  FILE* f = fopen(weights_path, "rb");
+  if (!f) {
+    engine_free(e);
+    return fail(QIE_EIO, "cannot open %s", weights_path);
+  }
+  fseek(f, 0, SEEK_END);
+  size_t fsize = (size_t)ftell(f);
+  fseek(f, 0, SEEK_SET);
+  if (fsize < e->ck.total_bytes) {
+    fclose(f);
+    engine_free(e);
+    return fail(QIE_EIO, "%s is %zu bytes, meta_data needs %zu", weights_path, fsize, e->ck.total_bytes);
+  }
+  cudaError_t ce = cudaMalloc(&e->blob, e->ck.total_bytes);
+  if (ce != cudaSuccess) {
+    fclose(f);
+    engine_free(e);
+    return fail(QIE_ENOMEM, "cudaMalloc(%zu) for weights: %s", e->ck.total_bytes, cudaGetErrorString(ce));
+  }
+  const size_t CH = (size_t)64 << 20;
+  char* pin[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2];
+  for (int i = 0; i < 2; ++i) {
+    cudaMallocHost(&pin[i], CH);
+    cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+  }
+  size_t off = 0;
+  int b = 0;
+  bool ok = pin[0] && pin[1];
+  while (ok && off < e->ck.total_bytes) {
+    size_t m = std::min(CH, e->ck.total_bytes - off);
+    cudaEventSynchronize(ev[b]);
+    if (fread(pin[b], 1, m, f) != m) {
+      ok = false;
+      break;
+    }
+    cudaMemcpyAsync(reinterpret_cast<char*>(e->blob) + off, pin[b], m, cudaMemcpyHostToDevice, e->stream);
+    cudaEventRecord(ev[b], e->stream);
+    off += m;
+    b ^= 1;
+  }
+  cudaStreamSynchronize(e->stream);
+  for (int i = 0; i < 2; ++i) {
+    if (pin[i]) cudaFreeHost(pin[i]);
+    cudaEventDestroy(ev[i]);
+  }
+  fclose(f);
+  if (!ok) {
+    engine_free(e);
+    return fail(QIE_EIO, "read error on %s", weights_path);
+  }
+  rc = engine_finish_setup(e);
+  if (rc) {
+    engine_free(e);
+    return rc;
+  }
+  *out = e;
+  return QIE_OK;
+}
+
+int qie_engine_create_synthetic(const qie_config* cfg, uint64_t seed, const qie_engine_opts* opts,
+                                qie_engine** out) {
+  if (!cfg || !out) return fail(QIE_EINVAL, "engine_create_synthetic: null argument");
+  qie_engine* e = nullptr;
+  int rc = engine_begin(opts, &e);
+  if (rc) return rc;
+  e->ck = synth_layout(*cfg);
+  std::string err;
+  if (!derive_config(e->ck, cfg->head_dim, e->opts.context, &e->cfg, &err)) {
+    engine_free(e);
+    return fail(QIE_EINVAL, "%s", err.c_str());
+  }
+  cudaError_t ce = cudaMalloc(&e->blob, e->ck.total_bytes);
+  if (ce != cudaSuccess) {
+    engine_free(e);
+    return fail(QIE_ENOMEM, "cudaMalloc(%zu) for weights: %s", e->ck.total_bytes, cudaGetErrorString(ce));
+  }
+  for (const TensorInfo& t : e->ck.tensors) {
+    ce = launch_synth_fill(e->blob, t.begin / 2, (t.end - t.begin) / 2, seed, t.kind, e->stream);
+    if (ce != cudaSuccess) {
+      engine_free(e);
+      return cuda_fail(ce, "synth_fill");
+    }
+  }
+  rc = engine_finish_setup(e);
+  if (rc) {
+    engine_free(e);
+    return rc;
+  }
+  *out = e;
+  return QIE_OK;
+}
+
+void qie_engine_destroy(qie_engine* e) { engine_free(e); }
+
+int qie_engine_get_config(const qie_engine* e, qie_config* out) {
+  if (!e || !out) return fail(QIE_EINVAL, "null argument");
+  *out = e->cfg;
+  return QIE_OK;
+}
+
+const qie_bf16* qie_engine_weight(const qie_engine* e, const char* short_name, int layer, size_t* n_elems) {
+  if (!e || !short_name) return nullptr;
+  const TensorInfo* t = e->ck.find(short_name, layer);
+  if (!t) return nullptr;
+  if (n_elems) *n_elems = (t->end - t->begin) / 2;
+  return reinterpret_cast<const qie_bf16*>(reinterpret_cast<const char*>(e->blob) + t->begin);
+}
+
+int qie_engine_kv_view(const qie_engine* e, qie_kv_view* out) {
+  if (!e || !out) return fail(QIE_EINVAL, "null argument");
+  out->pool = (qie_bf16*)e->kv.pool;
+  out->n_pages = e->kv.n_pages;
+  out->page_size = e->kv.page_size;
+  out->n_layers = e->kv.n_layers;
+  out->n_kv_heads = e->kv.n_kv;
+  out->head_dim = e->kv.hd;
+  return QIE_OK;
+}
+
+qie_stream qie_engine_stream(const qie_engine* e) { return e ? (qie_stream)e->stream : nullptr; }
+
+int qie_engine_set_sampling(qie_engine* e, int topk, float temperature_prefill, float temperature_decode,
+                            uint64_t seed, int add_step) {
+  if (!e || topk < 1 || topk > 256) return fail(QIE_EINVAL, "set_sampling: topk must be in [1,256]");
+  cudaStreamSynchronize(e->stream);
+  for (auto& kvp : e->graphs)  // sampling parameters are baked into captured graphs
+    if (kvp.second.exec) cudaGraphExecDestroy(kvp.second.exec);
+  e->graphs.clear();
+  e->topk = topk;
+  e->temp_prefill = temperature_prefill;
+  e->temp_decode = temperature_decode;
+  e->seed = seed;
+  e->add_step = add_step;
+  return QIE_OK;
+}
+
+int qie_seq_new(qie_engine* e, int* seq) {
+  if (!e || !seq) return fail(QIE_EINVAL, "null argument");
+  for (int i = 0; i < (int)e->seqs.size(); ++i)
+    if (!e->seqs[i].live) {
+      e->seqs[i] = Sequence();
+      e->seqs[i].live = true;
+      *seq = i;
+      return QIE_OK;
+    }
+  return fail(QIE_ENOMEM, "all %zu sequence slots are live", e->seqs.size());
+}
+
+static int check_seq(const qie_engine* e, int seq) {
+  if (!e || seq < 0 || seq >= (int)e->seqs.size() || !e->seqs[seq].live) return fail(QIE_EINVAL, "bad sequence id %d", seq);
+  return QIE_OK;
+}
+
+int qie_seq_free(qie_engine* e, int seq) {
+  int rc = check_seq(e, seq);
+  if (rc) return rc;
+  cudaStreamSynchronize(e->stream);
+  for (int p : e->seqs[seq].pages) e->free_pages.push_back(p);
+  e->seqs[seq] = Sequence();
+  return QIE_OK;
+}
+
+int qie_seq_len(const qie_engine* e, int seq) {
+  int rc = check_seq(e, seq);
+  if (rc) return rc;
+  return e->seqs[seq].len;
+}
+
+int qie_kv_pages_free(const qie_engine* e) { return e ? (int)e->free_pages.size() : QIE_EINVAL; }
+
+// grow the page list of `seq` to hold new_len positions; returns 1 if the block table
+// row changed, 0 if not, negative on error.
+static int ensure_pages(qie_engine* e, int seq, int new_len) {
+  Sequence& s = e->seqs[seq];
+  if (new_len > e->cfg.context) return fail(QIE_EINVAL, "sequence %d would exceed the context (%d)", seq, e->cfg.context);
+  int need = (new_len + e->kv.page_size - 1) / e->kv.page_size;
+  if (need > e->max_pages_per_seq) return fail(QIE_ENOMEM, "sequence %d needs %d pages > max %d", seq, need, e->max_pages_per_seq);
+  int changed = 0;
+  while ((int)s.pages.size() < need) {
+    if (e->free_pages.empty()) return fail(QIE_ENOMEM, "KV pool exhausted (%d pages)", e->kv.n_pages);
+    int p = e->free_pages.back();
+    e->free_pages.pop_back();
+    e->block_table_h[(size_t)seq * e->max_pages_per_seq + s.pages.size()] = p;
+    s.pages.push_back(p);
+    changed = 1;
+  }
+  return changed;
+}
+
+static cudaError_t push_block_row(qie_engine* e, int seq) {
+  size_t off = (size_t)seq * e->max_pages_per_seq;
+  return cudaMemcpyAsync(e->block_table_d + off, e->block_table_h + off, e->max_pages_per_seq * sizeof(int),
+                         cudaMemcpyHostToDevice, e->stream);
+}
+
+int qie_prefill(qie_engine* e, int seq, const int32_t* h_ids, int n, int32_t* h_token) {
+  int rc = check_seq(e, seq);
+  if (rc) return rc;
+  if (!h_ids || n <= 0 || !h_token) return fail(QIE_EINVAL, "prefill: empty prompt or null buffers");
+  for (int i = 0; i < n; ++i)
+    if (h_ids[i] < 0 || h_ids[i] >= e->cfg.vocab) return fail(QIE_EINVAL, "prefill: token id %d out of range", h_ids[i]);
+  CU(cudaSetDevice(e->opts.device));
+  Sequence& s = e->seqs[seq];
+  rc = ensure_pages(e, seq, s.len + n);
+  if (rc < 0) return rc;
+  if (rc) CU(push_block_row(e, seq));
+  const int R = e->opts.max_batch_tokens;
+  e->launches = 0;
+  for (int c0 = 0; c0 < n; c0 += R) {
+    int m = std::min(R, n - c0);
+    bool last = c0 + m == n;
+    int* st = e->stage_h;
+    CU(cudaStreamSynchronize(e->stream));  // staging buffer reuse
+    for (int i = 0; i < m; ++i) {
+      st[i] = h_ids[c0 + i];
+      st[R + i] = s.len + c0 + i;
+      st[2 * R + i] = seq;
+      st[3 * R + i] = s.step;
+    }
+    CU(cudaMemcpyAsync(e->ids_d, st, m * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->pos_d, st + R, m * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CU(cudaMemcpyAsync(e->slot_d, st + 2 * R, m * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    // the sampled row is row 0 of the sampler -> its step lives in rowstep_d[0]
+    CU(cudaMemcpyAsync(e->rowstep_d, st + 3 * R, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CU(forward_rows(e, m, s.len + c0 + m, m - 1, last ? 1 : 0, e->temp_prefill, false));
+  }
+  CU(cudaMemcpyAsync(e->sampled_h, e->sampled_d, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  *h_token = e->sampled_h[0];
+  s.len += n;
+  s.step += 1;  // iengine.cu:419
+  return QIE_OK;
+}
+
+// one decode step for the batch already staged on the device (ids/pos/slot/rowstep)
+static int decode_launch(qie_engine* e, int n, int max_kv_len) {
+  const int bucket = ((max_kv_len + 127) / 128) * 128;
+  if (!e->opts.use_graph || e->capture) {
+    CU(forward_rows(e, n, bucket, 0, n, e->temp_decode, true));
+    return QIE_OK;
+  }
+  auto key = std::make_pair(n, bucket);
+  auto it = e->graphs.find(key);
+  if (it == e->graphs.end()) {
+    e->graphs.emplace(key, qie_engine::GraphEntry());
+    CU(forward_rows(e, n, bucket, 0, n, e->temp_decode, true));
+    return QIE_OK;
+  }
+  if (!it->second.exec) {
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    long before = e->launches;
+    cudaError_t fe = forward_rows(e, n, bucket, 0, n, e->temp_decode, true);
+    cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+    if (fe != cudaSuccess) return cuda_fail(fe, "forward (capture)");
+    if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
+    it->second.launches = e->launches - before;
+    e->launches = before;
+    CU(cudaGraphInstantiate(&it->second.exec, graph, 0));
+    cudaGraphDestroy(graph);
+  }
+  CU(cudaGraphLaunch(it->second.exec, e->stream));
+  e->launches += it->second.launches;  // the graph replays exactly these kernels
+  return QIE_OK;
+}
+
+static int decode_prepare(qie_engine* e, const int* h_seqs, int n, int* max_kv_len) {
+  if (!e || !h_seqs || n <= 0) return fail(QIE_EINVAL, "decode: empty batch");
+  if (n > e->opts.max_batch_tokens || n > e->logits_rows) return fail(QIE_EINVAL, "decode: batch %d exceeds max %d", n, e->logits_rows);
+  CU(cudaSetDevice(e->opts.device));
+  int mk = 0;
+  for (int i = 0; i < n; ++i) {
+    int rc = check_seq(e, h_seqs[i]);
+    if (rc) return rc;
+    Sequence& s = e->seqs[h_seqs[i]];
+    if (s.len == 0) return fail(QIE_ESTATE, "sequence %d has not been prefilled", h_seqs[i]);
+    rc = ensure_pages(e, h_seqs[i], s.len + 1);
+    if (rc < 0) return rc;
+    if (rc) CU(push_block_row(e, h_seqs[i]));
+    mk = std::max(mk, s.len + 1);
+  }
+  *max_kv_len = mk;
+  return QIE_OK;
+}
+
+static int decode_stage_inputs(qie_engine* e, const int* h_seqs, const int32_t* h_tokens_in, int n) {
+  const int R = e->opts.max_batch_tokens;
+  int* st = e->stage_h;
+  CU(cudaStreamSynchronize(e->stream));
+  for (int i = 0; i < n; ++i) {
+    if (h_tokens_in[i] < 0 || h_tokens_in[i] >= e->cfg.vocab) return fail(QIE_EINVAL, "decode: token id %d out of range", h_tokens_in[i]);
+    const Sequence& s = e->seqs[h_seqs[i]];
+    st[i] = h_tokens_in[i];
+    st[R + i] = s.len;  // position of the new token (sequence_len-1 after ++, qwen_main.cu:265,300)
+    st[2 * R + i] = h_seqs[i];
+    st[3 * R + i] = s.step;
+  }
+  CU(cudaMemcpyAsync(e->ids_d, st, n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(e->pos_d, st + R, n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(e->slot_d, st + 2 * R, n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  CU(cudaMemcpyAsync(e->rowstep_d, st + 3 * R, n * sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  return QIE_OK;
+}
+
+int qie_decode_step(qie_engine* e, const int* h_seqs, const int32_t* h_tokens_in, int n, int32_t* h_tokens_out) {
+  if (!h_tokens_in || !h_tokens_out) return fail(QIE_EINVAL, "decode: null buffers");
+  int mk = 0;
+  int rc = decode_prepare(e, h_seqs, n, &mk);
+  if (rc) return rc;
+  rc = decode_stage_inputs(e, h_seqs, h_tokens_in, n);
+  if (rc) return rc;
+  e->launches = 0;
+  rc = decode_launch(e, n, mk);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(e->sampled_h, e->sampled_d, n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  for (int i = 0; i < n; ++i) {
+    h_tokens_out[i] = e->sampled_h[i];
+    e->seqs[h_seqs[i]].len += 1;
+    e->seqs[h_seqs[i]].step += 1;
+  }
+  return QIE_OK;
+}
+
+int qie_decode_run(qie_engine* e, const int* h_seqs, const int32_t* h_tokens_in, int n, int steps,
+                   int32_t* h_tokens_out) {
+  if (!h_tokens_in || !h_tokens_out || steps <= 0) return fail(QIE_EINVAL, "decode_run: bad arguments");
+  if (!e) return fail(QIE_EINVAL, "null engine");
+  if ((size_t)n * steps > e->sampled_h_cap) {
+    CU(cudaStreamSynchronize(e->stream));
+    if (e->sampled_h) cudaFreeHost(e->sampled_h);
+    e->sampled_h = nullptr;
+    e->sampled_h_cap = (size_t)n * steps;
+    CU(cudaMallocHost(&e->sampled_h, e->sampled_h_cap * sizeof(int)));
+  }
+  e->launches = 0;
+  for (int s = 0; s < steps; ++s) {
+    int mk = 0;
+    int rc = decode_prepare(e, h_seqs, n, &mk);
+    if (rc) return rc;
+    if (s == 0) {
+      rc = decode_stage_inputs(e, h_seqs, h_tokens_in, n);
+      if (rc) return rc;
+    }
+    rc = decode_launch(e, n, mk);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(e->sampled_h + (size_t)s * n, e->sampled_d, n * sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    for (int i = 0; i < n; ++i) {
+      e->seqs[h_seqs[i]].len += 1;
+      e->seqs[h_seqs[i]].step += 1;
+    }
+  }
+  CU(cudaStreamSynchronize(e->stream));
+  memcpy(h_tokens_out, e->sampled_h, (size_t)n * steps * sizeof(int));
+  return QIE_OK;
+}
+
+int qie_decode_step_device(qie_engine* e, const int* h_seqs, int n) {
+  int mk = 0;
+  int rc = decode_prepare(e, h_seqs, n, &mk);
+  if (rc) return rc;
+  rc = decode_launch(e, n, mk);
+  if (rc) return rc;
+  for (int i = 0; i < n; ++i) {
+    e->seqs[h_seqs[i]].len += 1;
+    e->seqs[h_seqs[i]].step += 1;
+  }
+  return QIE_OK;
+}
+
+int qie_sync(qie_engine* e) {
+  if (!e) return fail(QIE_EINVAL, "null engine");
+  CU(cudaStreamSynchronize(e->stream));
+  return QIE_OK;
+}
+
+int qie_capture_enable(qie_engine* e, int on) {
+  if (!e) return fail(QIE_EINVAL, "null engine");
+  e->capture = on != 0;
+  return QIE_OK;
+}
+
+long qie_capture_read(qie_engine* e, const char* tag, int layer, qie_bf16* h_out, size_t max_elems) {
+  if (!e || !tag || !h_out) return fail(QIE_EINVAL, "null argument");
+  std::string key = std::string(tag) + "#" + std::to_string(layer);
+  auto it = e->cap.find(key);
+  if (it == e->cap.end() || !it->second.d) return fail(QIE_EINVAL, "no capture for %s", key.c_str());
+  size_t n = std::min(max_elems, it->second.elems);
+  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaMemcpy(h_out, it->second.d, n * sizeof(bf16), cudaMemcpyDeviceToHost));
+  return (long)it->second.elems;
+}
+
+long qie_launch_count(const qie_engine* e) { return e ? e->launches : 0; }
+
+}  // extern "C"

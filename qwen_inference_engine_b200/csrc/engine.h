@@ -1,0 +1,97 @@
+// engine.h -- host side of the forward: weights, KV page pool, sequences, batch
+// scheduler state, forward launch order.  Replaces llm() (src/qwen_main.cu:64-417),
+// ModelBuffers (include/utils.hh:14-88), batch_metadata / page_table
+// (include/iengine.cuh:23-48) and the page-list allocator (src/iengine.cu:72-109) of the
+// reference.  One engine per GPU; no global mutable state, so data-parallel replicas are
+// independent.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "checkpoint.h"
+#include "kernels.h"
+
+namespace qie {
+
+struct LayerWeights {
+  const bf16 *in_ln = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *o = nullptr, *q_norm = nullptr,
+             *k_norm = nullptr, *post_ln = nullptr, *up = nullptr, *gate = nullptr, *down = nullptr;
+};
+
+struct Sequence {
+  bool live = false;
+  int len = 0;   // positions held in the KV cache (ModelBuffers::sequence_len)
+  int step = 0;  // batch_metadata::step
+  std::vector<int> pages;
+};
+
+struct CaptureBuf {
+  bf16* d = nullptr;
+  size_t elems = 0, cap = 0;
+};
+
+}  // namespace qie
+
+struct qie_engine {
+  qie_config cfg{};
+  qie_engine_opts opts{};
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+
+  // weights: ONE device blob, tensors addressed as blob + begin (helpers.cuh:18-29)
+  qie::Checkpoint ck;
+  qie::bf16* blob = nullptr;
+  std::vector<qie::LayerWeights> L;
+  const qie::bf16 *embed = nullptr, *final_norm = nullptr, *lm_head = nullptr;
+  float *cos_d = nullptr, *sin_d = nullptr;
+
+  // KV pool + page allocator
+  qie::KvGeom kv{};
+  std::vector<int> free_pages;
+  std::vector<qie::Sequence> seqs;
+  int max_pages_per_seq = 0;
+  int* block_table_d = nullptr;
+  int* block_table_h = nullptr;  // pinned mirror
+
+  // per-forward row metadata (device) + pinned staging
+  int *ids_d = nullptr, *pos_d = nullptr, *slot_d = nullptr, *sampled_d = nullptr, *rowstep_d = nullptr;
+  int *stage_h = nullptr;    // pinned: ids | pos | slot | rowstep
+  int* sampled_h = nullptr;  // pinned
+  size_t sampled_h_cap = 0;
+
+  // activations [max_batch_tokens, *]
+  qie::bf16 *x = nullptr, *xn = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *att = nullptr, *h = nullptr,
+            *logits = nullptr;
+  int logits_rows = 0;
+
+  // sampling
+  int topk = 1;
+  float temp_prefill = 1.0f, temp_decode = 0.7f;
+  uint64_t seed = 1234;
+  int add_step = 1;
+
+  // capture (parity hooks)
+  bool capture = false;
+  std::map<std::string, qie::CaptureBuf> cap;
+
+  // CUDA graphs of the decode step keyed by (rows, kv bucket). A shape is run eagerly
+  // the first time it is seen (that also sets kernel attributes) and captured the second.
+  struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    long launches = 0;
+  };
+  std::map<std::pair<int, int>, GraphEntry> graphs;
+
+  long launches = 0;
+};
+
+namespace qie {
+// one forward over n_rows rows already described in ids_d/pos_d/slot_d; logits for rows
+// [out_row0, out_row0+n_out); samples into sampled_d[0..n_out). Returns cudaSuccess or the
+// first launch error. Counts launches into e->launches.
+cudaError_t forward_rows(qie_engine* e, int n_rows, int max_kv_len, int out_row0, int n_out, float temperature,
+                         bool advance);
+}  // namespace qie

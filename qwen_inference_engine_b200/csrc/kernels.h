@@ -1,0 +1,108 @@
+// kernels.h -- host-visible launch interface of the sm_100a kernels (internal header;
+// the public boundary is include/qie_b200.h).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace qie {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------- KV pool geometry
+// pool[page][layer][k|v][kv_head][slot][head_dim]
+struct KvGeom {
+  bf16* pool;
+  int n_pages, page_size, n_layers, n_kv, hd;
+  __host__ __device__ size_t head_stride() const { return (size_t)page_size * hd; }
+  __host__ __device__ size_t kv_stride() const { return (size_t)n_kv * page_size * hd; }
+  __host__ __device__ size_t layer_stride() const { return 2 * kv_stride(); }
+  __host__ __device__ size_t page_stride() const { return (size_t)n_layers * layer_stride(); }
+  __host__ __device__ bf16* chunk(int page, int layer, int kv, int head) const {
+    return pool + (size_t)page * page_stride() + (size_t)layer * layer_stride() + (size_t)kv * kv_stride() +
+           (size_t)head * head_stride();
+  }
+};
+
+// ---------------------------------------------------------------- reference-order GEMM
+enum { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_SILU_MUL = 2 };
+
+struct GemmSeg {
+  const bf16* W;   // [rows, K] row-major (HF [out,in])
+  const bf16* W2;  // second weight (up_proj) for EPI_SILU_MUL, else unused
+  bf16* out;       // [M, ld_out]
+  int rows;
+  int ld_out;
+};
+
+struct GemmArgs {
+  const bf16* A;  // [M, lda]
+  int lda, M, K;
+  int nseg, total_units, epi, dual, stages;
+  int unit_begin[4];
+  GemmSeg seg[3];
+};
+
+// Launch C = A * W^T for up to 3 weight segments sharing A (e.g. q,k,v). M <= 64.
+cudaError_t launch_gemm_ref_order(const GemmArgs& args, int num_sms, cudaStream_t st);
+
+// ---------------------------------------------------------------- row-wise ops
+cudaError_t launch_embedding(bf16* out, const bf16* table, const int* ids, size_t hidden, size_t n_tok,
+                             cudaStream_t st);
+cudaError_t launch_rmsnorm_ref(const bf16* x, const bf16* w, bf16* y, size_t hidden, size_t n_tok,
+                               size_t x_stride, cudaStream_t st);
+cudaError_t launch_qknorm_ref(bf16* x, const bf16* w, int hd, int n_tok, int row_dim, int n_heads, cudaStream_t st);
+cudaError_t launch_rope_ref(const float* cos_t, const float* sin_t, bf16* x, int n_tok, const int* pos, int pos0,
+                            int hd, int row_dim, int n_heads, cudaStream_t st);
+cudaError_t launch_silu(bf16* x, size_t n, cudaStream_t st);
+cudaError_t launch_elem_mul(const bf16* a, const bf16* b, bf16* c, size_t n, cudaStream_t st);
+cudaError_t launch_residual_add(bf16* a, const bf16* b, size_t n, cudaStream_t st);
+
+// fused q/k-norm + RoPE + KV store for one layer:
+//   q (in place) and k: per-head RMS norm (if the norm weights are non-null), RoPE at
+//   pos[t]; k (post-RoPE) and v (raw) are written to the KV pool.
+struct QkvPostArgs {
+  bf16* q;        // [n_tok, n_q*hd]   in place
+  const bf16* k;  // [n_tok, n_kv*hd]
+  const bf16* v;  // [n_tok, n_kv*hd]
+  const bf16* q_norm_w;
+  const bf16* k_norm_w;
+  const float* cos_t;
+  const float* sin_t;
+  const int* pos;          // [n_tok]
+  const int* slot;         // [n_tok] block-table row
+  const int* block_table;  // [*, max_pages]
+  int max_pages, n_tok, n_q, layer;
+  KvGeom kv;
+};
+cudaError_t launch_qkv_post(const QkvPostArgs& a, cudaStream_t st);
+
+cudaError_t launch_kv_store(const KvGeom& kv, int layer, const bf16* K, const bf16* V, const int* pos,
+                            const int* slot, const int* block_table, int max_pages, int n_tok, cudaStream_t st);
+
+// reference-order attention: row t attends to positions 0..pos[t] of its sequence.
+struct AttnArgs {
+  const bf16* q;  // [n_tok, n_q*hd]
+  bf16* out;      // [n_tok, n_q*hd]
+  const int* pos;
+  const int* slot;
+  const int* block_table;
+  int max_pages, n_tok, n_q, layer;
+  int max_kv_len;  // upper bound on pos[t]+1 (sizes shared memory)
+  KvGeom kv;
+};
+cudaError_t launch_attention_ref(const AttnArgs& a, cudaStream_t st);
+
+// sampling (reference tie-break + XORWOW)
+cudaError_t launch_sample_topk(const bf16* logits, int* out_tokens, int n_rows, size_t vocab, float temperature,
+                               int k, uint64_t seed, uint64_t seed_stride, const int* step_ptr, cudaStream_t st);
+
+// synthetic weights on the device (twin of the host generator)
+cudaError_t launch_synth_fill(bf16* blob, size_t elem_begin, size_t n_elems, uint64_t seed, int kind,
+                              cudaStream_t st);
+
+// step bookkeeping on the device: pos[i] += 1 ; ids <- sampled tokens
+cudaError_t launch_advance(int* pos, int* ids, const int* sampled, int n, int* step_ptr, cudaStream_t st);
+
+}  // namespace qie

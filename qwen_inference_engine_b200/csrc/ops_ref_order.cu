@@ -1,0 +1,622 @@
+// ops_ref_order.cu -- the non-GEMM operators of the forward, written so that every
+// floating-point result is produced by the same sequence of IEEE operations as the
+// reference kernel it replaces (citations relative to /root/reference/layers/), while
+// the work is spread over warps/blocks instead of one thread per token:
+//   rmsNorm        src/normalization.cu:5-26   sequential FFMA chain (kept: it IS the spec)
+//   qkNorm         src/qk_norm.cu:43-80        shared-memory tree  -> same tree in shuffles
+//   RoPE           src/RoPE.cu:6-22            fma(x0,c,-(x1*s)) , fma(c,x1,x0*s)
+//   selfattention  src/self_attension.cu:10-149
+//   sampling       src/logit_decode.cu:149-274
+// This file is compiled with -fmad=false; every fused multiply-add the reference's SASS
+// contains is spelled __fmaf_rn here, everything else is an explicit _rn intrinsic.
+#include <curand_kernel.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace qie {
+
+// ------------------------------------------------------------------ embedding
+__global__ void embedding_kernel(bf16* __restrict__ out, const bf16* __restrict__ table,
+                                 const int* __restrict__ ids, size_t hidden) {
+  const size_t t = blockIdx.x;
+  const bf16* src = table + (size_t)ids[t] * hidden;
+  bf16* dst = out + t * hidden;
+  if ((hidden & 7) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (size_t i = threadIdx.x; i < hidden / 8; i += blockDim.x) d4[i] = s4[i];
+  } else {
+    for (size_t i = threadIdx.x; i < hidden; i += blockDim.x) dst[i] = src[i];
+  }
+}
+
+cudaError_t launch_embedding(bf16* out, const bf16* table, const int* ids, size_t hidden, size_t n_tok,
+                             cudaStream_t st) {
+  if (n_tok == 0) return cudaSuccess;
+  embedding_kernel<<<(unsigned)n_tok, 128, 0, st>>>(out, table, ids, hidden);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ rmsNorm
+// One block per token.  The reference's sum is a strictly sequential fp32 FFMA chain
+// over the hidden dimension (one thread per token); fp32 addition is not associative, so
+// the chain order is part of the result.  Thread 0 walks the chain out of shared memory
+// (4-cycle dependent FFMA issue, loads hoisted), the block does the rest in parallel.
+__global__ void __launch_bounds__(128) rmsnorm_ref_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                           bf16* __restrict__ y, int hidden, size_t x_stride) {
+  extern __shared__ float xs[];
+  __shared__ float s_rms;
+  const bf16* xr = x + (size_t)blockIdx.x * x_stride;
+  bf16* yr = y + (size_t)blockIdx.x * hidden;
+  for (int i = threadIdx.x; i < hidden; i += blockDim.x) xs[i] = bf2f(xr[i]);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sum = 0.f;
+    int i = 0;
+    for (; i + 8 <= hidden; i += 8) {
+      float v0 = xs[i], v1 = xs[i + 1], v2 = xs[i + 2], v3 = xs[i + 3];
+      float v4 = xs[i + 4], v5 = xs[i + 5], v6 = xs[i + 6], v7 = xs[i + 7];
+      sum = __fmaf_rn(v0, v0, sum);
+      sum = __fmaf_rn(v1, v1, sum);
+      sum = __fmaf_rn(v2, v2, sum);
+      sum = __fmaf_rn(v3, v3, sum);
+      sum = __fmaf_rn(v4, v4, sum);
+      sum = __fmaf_rn(v5, v5, sum);
+      sum = __fmaf_rn(v6, v6, sum);
+      sum = __fmaf_rn(v7, v7, sum);
+    }
+    for (; i < hidden; ++i) sum = __fmaf_rn(xs[i], xs[i], sum);
+    s_rms = __fsqrt_rn(__fadd_rn(__fdiv_rn(sum, (float)hidden), 1e-04f));
+  }
+  __syncthreads();
+  const float rms = s_rms;
+  for (int i = threadIdx.x; i < hidden; i += blockDim.x)
+    yr[i] = f2bf(__fmul_rn(__fdiv_rn(xs[i], rms), bf2f(w[i])));
+}
+
+cudaError_t launch_rmsnorm_ref(const bf16* x, const bf16* w, bf16* y, size_t hidden, size_t n_tok, size_t x_stride,
+                               cudaStream_t st) {
+  if (n_tok == 0) return cudaSuccess;
+  rmsnorm_ref_kernel<<<(unsigned)n_tok, 128, hidden * sizeof(float), st>>>(x, w, y, (int)hidden, x_stride);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ per-head tree sum
+// Lane l holds, for p in [0,NP): elements t = 64p + 2l and 64p + 2l + 1 of a head of
+// hd = 64*NP values.  Reproduces  for (stride = hd/2; stride > 0; stride >>= 1)
+//   buf[t] += buf[t+stride]  (t < stride)   exactly; the result is valid in lane 0.
+template <int NP>
+__device__ __forceinline__ float head_tree_sum(float (&v)[NP][2]) {
+#pragma unroll
+  for (int s = NP / 2; s >= 1; s >>= 1)  // strides >= 64: partners live in the same lane
+#pragma unroll
+    for (int p = 0; p < s; ++p) {
+      v[p][0] = __fadd_rn(v[p][0], v[p + s][0]);
+      v[p][1] = __fadd_rn(v[p][1], v[p + s][1]);
+    }
+  float a = v[0][0], b = v[0][1];
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {  // strides 32,16,8,4,2
+    a = __fadd_rn(a, __shfl_down_sync(0xffffffffu, a, o));
+    b = __fadd_rn(b, __shfl_down_sync(0xffffffffu, b, o));
+  }
+  return __fadd_rn(a, b);  // stride 1
+}
+
+// q/k-norm of one head held in registers (in place, values become the bf16-rounded
+// results as floats): qk_norm.cu:46-78.
+template <int NP>
+__device__ __forceinline__ void head_norm(float (&x)[NP][2], const bf16* __restrict__ w, int lane) {
+  float sq[NP][2];
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    sq[p][0] = __fmul_rn(x[p][0], x[p][0]);
+    sq[p][1] = __fmul_rn(x[p][1], x[p][1]);
+  }
+  float tot = head_tree_sum<NP>(sq);
+  float rms = __fsqrt_rn(__fadd_rn(__fdiv_rn(tot, (float)(64 * NP)), 1e-04f));
+  rms = __shfl_sync(0xffffffffu, rms, 0);
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    uint32_t wp = *reinterpret_cast<const uint32_t*>(w + 64 * p + 2 * lane);
+    x[p][0] = bf2f(f2bf(__fmul_rn(__fdiv_rn(x[p][0], rms), lo2f(wp))));
+    x[p][1] = bf2f(f2bf(__fmul_rn(__fdiv_rn(x[p][1], rms), hi2f(wp))));
+  }
+}
+
+// RoPE of one head held in registers: RoPE.cu:15-18 (pair j = 32p + lane).
+template <int NP>
+__device__ __forceinline__ void head_rope(float (&x)[NP][2], const float* __restrict__ cos_row,
+                                          const float* __restrict__ sin_row, int lane) {
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    float c = cos_row[32 * p + lane], s = sin_row[32 * p + lane];
+    float x0 = x[p][0], x1 = x[p][1];
+    float v1 = __fmaf_rn(x0, c, -__fmul_rn(x1, s));
+    float v2 = __fmaf_rn(c, x1, __fmul_rn(x0, s));
+    x[p][0] = bf2f(f2bf(v1));
+    x[p][1] = bf2f(f2bf(v2));
+  }
+}
+
+template <int NP>
+__device__ __forceinline__ void head_load(float (&x)[NP][2], const bf16* __restrict__ src, int lane) {
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    uint32_t v = *reinterpret_cast<const uint32_t*>(src + 64 * p + 2 * lane);
+    x[p][0] = lo2f(v);
+    x[p][1] = hi2f(v);
+  }
+}
+template <int NP>
+__device__ __forceinline__ void head_store(const float (&x)[NP][2], bf16* __restrict__ dst, int lane) {
+#pragma unroll
+  for (int p = 0; p < NP; ++p)
+    *reinterpret_cast<uint32_t*>(dst + 64 * p + 2 * lane) = pack2(f2bf(x[p][0]), f2bf(x[p][1]));
+}
+
+// ---- operator-level qkNorm / RoPE (one warp per (token, head)) ----------------------
+template <int NP>
+__global__ void qknorm_ref_kernel(bf16* __restrict__ x, const bf16* __restrict__ w, int n_tok, int row_dim,
+                                  int n_heads) {
+  int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= n_tok * n_heads) return;
+  int tok = gw / n_heads, h = gw % n_heads;
+  bf16* p = x + (size_t)tok * row_dim + (size_t)h * 64 * NP;
+  float v[NP][2];
+  head_load<NP>(v, p, lane);
+  head_norm<NP>(v, w, lane);
+  head_store<NP>(v, p, lane);
+}
+
+template <int NP>
+__global__ void rope_ref_kernel(const float* __restrict__ cos_t, const float* __restrict__ sin_t,
+                                bf16* __restrict__ x, int n_tok, const int* __restrict__ pos, int pos0, int row_dim,
+                                int n_heads) {
+  int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= n_tok * n_heads) return;
+  int tok = gw / n_heads, h = gw % n_heads;
+  int ps = pos ? pos[tok] : pos0 + tok;
+  bf16* p = x + (size_t)tok * row_dim + (size_t)h * 64 * NP;
+  float v[NP][2];
+  head_load<NP>(v, p, lane);
+  head_rope<NP>(v, cos_t + (size_t)ps * 32 * NP, sin_t + (size_t)ps * 32 * NP, lane);
+  head_store<NP>(v, p, lane);
+}
+
+#define QIE_DISPATCH_HD(hd, CALL)                  \
+  switch (hd) {                                    \
+    case 64: { constexpr int NP = 1; CALL; break; }  \
+    case 128: { constexpr int NP = 2; CALL; break; } \
+    case 256: { constexpr int NP = 4; CALL; break; } \
+    default: return cudaErrorInvalidValue;         \
+  }
+
+cudaError_t launch_qknorm_ref(bf16* x, const bf16* w, int hd, int n_tok, int row_dim, int n_heads, cudaStream_t st) {
+  int warps = n_tok * n_heads;
+  if (warps == 0) return cudaSuccess;
+  int blocks = (warps + 3) / 4;
+  QIE_DISPATCH_HD(hd, (qknorm_ref_kernel<NP><<<blocks, 128, 0, st>>>(x, w, n_tok, row_dim, n_heads)));
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rope_ref(const float* cos_t, const float* sin_t, bf16* x, int n_tok, const int* pos, int pos0,
+                            int hd, int row_dim, int n_heads, cudaStream_t st) {
+  int warps = n_tok * n_heads;
+  if (warps == 0) return cudaSuccess;
+  int blocks = (warps + 3) / 4;
+  QIE_DISPATCH_HD(hd,
+                  (rope_ref_kernel<NP><<<blocks, 128, 0, st>>>(cos_t, sin_t, x, n_tok, pos, pos0, row_dim, n_heads)));
+  return cudaGetLastError();
+}
+
+// ---- fused q/k-norm + RoPE + KV store: replaces 2x qkNorm + 2x RoPE + the
+// cudaMemcpy2D scatter of kv_copy_layer_to_cache_* (include_cuda.cu:165-279) ------------
+template <int NP>
+__global__ void qkv_post_kernel(QkvPostArgs a) {
+  const int hd = 64 * NP;
+  const int heads = a.n_q + 2 * a.kv.n_kv;  // q heads, k heads, v heads
+  int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= a.n_tok * heads) return;
+  int tok = gw / heads, h = gw % heads;
+  int ps = a.pos[tok];
+  float v[NP][2];
+  if (h < a.n_q) {
+    bf16* p = a.q + (size_t)tok * a.n_q * hd + (size_t)h * hd;
+    head_load<NP>(v, p, lane);
+    if (a.q_norm_w) head_norm<NP>(v, a.q_norm_w, lane);
+    head_rope<NP>(v, a.cos_t + (size_t)ps * 32 * NP, a.sin_t + (size_t)ps * 32 * NP, lane);
+    head_store<NP>(v, p, lane);
+    return;
+  }
+  int page = a.block_table[(size_t)a.slot[tok] * a.max_pages + ps / a.kv.page_size];
+  int off = ps % a.kv.page_size;
+  if (h < a.n_q + a.kv.n_kv) {
+    int kh = h - a.n_q;
+    head_load<NP>(v, a.k + (size_t)tok * a.kv.n_kv * hd + (size_t)kh * hd, lane);
+    if (a.k_norm_w) head_norm<NP>(v, a.k_norm_w, lane);
+    head_rope<NP>(v, a.cos_t + (size_t)ps * 32 * NP, a.sin_t + (size_t)ps * 32 * NP, lane);
+    head_store<NP>(v, a.kv.chunk(page, a.layer, 0, kh) + (size_t)off * hd, lane);
+  } else {
+    int vh = h - a.n_q - a.kv.n_kv;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.v + (size_t)tok * a.kv.n_kv * hd + (size_t)vh * hd);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(a.kv.chunk(page, a.layer, 1, vh) + (size_t)off * hd);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) dst[32 * p + lane] = src[32 * p + lane];
+  }
+}
+
+cudaError_t launch_qkv_post(const QkvPostArgs& a, cudaStream_t st) {
+  int warps = a.n_tok * (a.n_q + 2 * a.kv.n_kv);
+  if (warps == 0) return cudaSuccess;
+  int blocks = (warps + 3) / 4;
+  QIE_DISPATCH_HD(a.kv.hd, (qkv_post_kernel<NP><<<blocks, 128, 0, st>>>(a)));
+  return cudaGetLastError();
+}
+
+// plain K/V scatter (operator-level twin of kv_copy_layer_to_cache_*)
+__global__ void kv_store_kernel(KvGeom kv, int layer, const bf16* __restrict__ K, const bf16* __restrict__ V,
+                                const int* __restrict__ pos, const int* __restrict__ slot,
+                                const int* __restrict__ block_table, int max_pages, int n_tok) {
+  int tok = blockIdx.x;
+  int ps = pos[tok];
+  int page = block_table[(size_t)slot[tok] * max_pages + ps / kv.page_size];
+  int off = ps % kv.page_size;
+  int dkv = kv.n_kv * kv.hd;
+  for (int i = threadIdx.x; i < dkv; i += blockDim.x) {
+    int h = i / kv.hd, d = i % kv.hd;
+    kv.chunk(page, layer, 0, h)[(size_t)off * kv.hd + d] = K[(size_t)tok * dkv + i];
+    kv.chunk(page, layer, 1, h)[(size_t)off * kv.hd + d] = V[(size_t)tok * dkv + i];
+  }
+}
+
+cudaError_t launch_kv_store(const KvGeom& kv, int layer, const bf16* K, const bf16* V, const int* pos,
+                            const int* slot, const int* block_table, int max_pages, int n_tok, cudaStream_t st) {
+  if (n_tok == 0) return cudaSuccess;
+  kv_store_kernel<<<n_tok, 128, 0, st>>>(kv, layer, K, V, pos, slot, block_table, max_pages, n_tok);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ elementwise
+__global__ void silu_kernel(bf16* x, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    float v = bf2f(x[i]);
+    float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-v)));
+    x[i] = f2bf(__fmul_rn(v, sg));
+  }
+}
+__global__ void elem_mul_kernel(const bf16* a, const bf16* b, bf16* c, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) c[i] = f2bf(__fmul_rn(bf2f(a[i]), bf2f(b[i])));
+}
+__global__ void residual_add_kernel(bf16* a, const bf16* b, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = f2bf(__fadd_rn(bf2f(a[i]), bf2f(b[i])));
+}
+cudaError_t launch_silu(bf16* x, size_t n, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  silu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_elem_mul(const bf16* a, const bf16* b, bf16* c, size_t n, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  elem_mul_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, b, c, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_residual_add(bf16* a, const bf16* b, size_t n, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  residual_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, b, n);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ attention
+// grid (q head, token); 256 threads.  Phase 1: one warp per kv position computes the
+// score with the reference's 2^k tree over head_dim.  Phase 2: max (order free), expf,
+// the reference's sequential sum, p = e/sum.  Phase 3: thread d accumulates
+// out[d] = fma(p[k], v[k][d], out[d]) for k ascending (self_attension.cu:112-137).
+// Positions > pos[t] contribute exact zeros in the reference (mask -1e9 -> expf = 0 ->
+// fma(0, v, o) = o), so stopping at pos[t] is bit-identical.
+template <int NP>
+__global__ void __launch_bounds__(256) attention_ref_kernel(AttnArgs a) {
+  constexpr int hd = 64 * NP;
+  extern __shared__ float sm[];
+  float* score = sm;                                                   // [kv_len]
+  int* pages = reinterpret_cast<int*>(sm + a.max_kv_len);              // [pages used]
+  __shared__ float s_red[8];
+  __shared__ float s_bcast;
+
+  const int h = blockIdx.x, tok = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv_len = a.pos[tok] + 1;
+  const int group = a.n_q / a.kv.n_kv;
+  const int kvh = h / group;
+  const int psz = a.kv.page_size;
+  const int n_pages = (kv_len + psz - 1) / psz;
+  const int* bt = a.block_table + (size_t)a.slot[tok] * a.max_pages;
+  for (int i = threadIdx.x; i < n_pages; i += blockDim.x) pages[i] = bt[i];
+
+  float q[NP][2];
+  head_load<NP>(q, a.q + (size_t)tok * a.n_q * hd + (size_t)h * hd, lane);
+  __syncthreads();
+
+  const float inv_den = __fsqrt_rn((float)hd);
+  for (int k = warp; k < kv_len; k += 8) {
+    const bf16* kp = a.kv.chunk(pages[k / psz], a.layer, 0, kvh) + (size_t)(k % psz) * hd;
+    float pr[NP][2];
+    head_load<NP>(pr, kp, lane);
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      pr[p][0] = __fmul_rn(q[p][0], pr[p][0]);
+      pr[p][1] = __fmul_rn(q[p][1], pr[p][1]);
+    }
+    float dot = head_tree_sum<NP>(pr);
+    if (lane == 0) score[k] = __fdiv_rn(dot, inv_den);
+  }
+  __syncthreads();
+
+  // max
+  float m = -1e9f;
+  for (int k = threadIdx.x; k < kv_len; k += blockDim.x) m = fmaxf(m, score[k]);
+  m = warp_max(m);
+  if (lane == 0) s_red[warp] = m;
+  __syncthreads();
+  m = s_red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, s_red[i]);
+  for (int k = threadIdx.x; k < kv_len; k += blockDim.x) score[k] = expf(__fsub_rn(score[k], m));
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float sum = 0.f;
+    int k = 0;
+    for (; k + 8 <= kv_len; k += 8) {
+      float e0 = score[k], e1 = score[k + 1], e2 = score[k + 2], e3 = score[k + 3];
+      float e4 = score[k + 4], e5 = score[k + 5], e6 = score[k + 6], e7 = score[k + 7];
+      sum = __fadd_rn(sum, e0);
+      sum = __fadd_rn(sum, e1);
+      sum = __fadd_rn(sum, e2);
+      sum = __fadd_rn(sum, e3);
+      sum = __fadd_rn(sum, e4);
+      sum = __fadd_rn(sum, e5);
+      sum = __fadd_rn(sum, e6);
+      sum = __fadd_rn(sum, e7);
+    }
+    for (; k < kv_len; ++k) sum = __fadd_rn(sum, score[k]);
+    s_bcast = sum;
+  }
+  __syncthreads();
+  const float sum = s_bcast;
+  for (int k = threadIdx.x; k < kv_len; k += blockDim.x) score[k] = __fdiv_rn(score[k], sum);
+  __syncthreads();
+
+  if (threadIdx.x < hd) {
+    const int d = threadIdx.x;
+    float o = 0.f;
+    int k = 0;
+    for (; k + 4 <= kv_len; k += 4) {
+      float v0 = bf2f(a.kv.chunk(pages[k / psz], a.layer, 1, kvh)[(size_t)(k % psz) * hd + d]);
+      float v1 = bf2f(a.kv.chunk(pages[(k + 1) / psz], a.layer, 1, kvh)[(size_t)((k + 1) % psz) * hd + d]);
+      float v2 = bf2f(a.kv.chunk(pages[(k + 2) / psz], a.layer, 1, kvh)[(size_t)((k + 2) % psz) * hd + d]);
+      float v3 = bf2f(a.kv.chunk(pages[(k + 3) / psz], a.layer, 1, kvh)[(size_t)((k + 3) % psz) * hd + d]);
+      o = __fmaf_rn(score[k], v0, o);
+      o = __fmaf_rn(score[k + 1], v1, o);
+      o = __fmaf_rn(score[k + 2], v2, o);
+      o = __fmaf_rn(score[k + 3], v3, o);
+    }
+    for (; k < kv_len; ++k)
+      o = __fmaf_rn(score[k], bf2f(a.kv.chunk(pages[k / psz], a.layer, 1, kvh)[(size_t)(k % psz) * hd + d]), o);
+    a.out[(size_t)tok * a.n_q * hd + (size_t)h * hd + d] = f2bf(o);
+  }
+}
+
+cudaError_t launch_attention_ref(const AttnArgs& a, cudaStream_t st) {
+  if (a.n_tok == 0) return cudaSuccess;
+  int max_pages_used = (a.max_kv_len + a.kv.page_size - 1) / a.kv.page_size;
+  size_t smem = (size_t)a.max_kv_len * sizeof(float) + (size_t)max_pages_used * sizeof(int);
+  dim3 grid(a.n_q, a.n_tok);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+#define QIE_ATTN(NPV)                                                                                         \
+  {                                                                                                           \
+    static bool set = false;                                                                                  \
+    if (!set) {                                                                                               \
+      cudaError_t e = cudaFuncSetAttribute(attention_ref_kernel<NPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           200 * 1024);                                                       \
+      if (e != cudaSuccess) return e;                                                                         \
+      set = true;                                                                                             \
+    }                                                                                                         \
+    attention_ref_kernel<NPV><<<grid, 256, smem, st>>>(a);                                                    \
+  }
+  switch (a.kv.hd) {
+    case 64: QIE_ATTN(1); break;
+    case 128: QIE_ATTN(2); break;
+    case 256: QIE_ATTN(4); break;
+    default: return cudaErrorInvalidValue;
+  }
+#undef QIE_ATTN
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ sampling
+// The reference runs ONE block of 256 threads and, for each of k rounds, a strided scan
+// + shared-memory arg-max whose tie-break is a function of (idx & 255):
+// value, then the larger bit-reversed low byte of idx, then the lower idx.  That is a
+// total order, so the scan can use any number of threads and still pick the same token.
+struct Cand {
+  float val;
+  int idx;
+};
+__device__ __forceinline__ bool cand_better(float va, int ia, float vb, int ib) {
+  if (ib < 0) return ia >= 0;
+  if (ia < 0) return false;
+  if (va > vb) return true;
+  if (va < vb) return false;
+  unsigned ra = __brev((unsigned)ia << 24), rb = __brev((unsigned)ib << 24);
+  if (ra != rb) return ra > rb;
+  return ia < ib;
+}
+
+__global__ void __launch_bounds__(1024) sample_topk_kernel(const bf16* __restrict__ logits, int* __restrict__ out,
+                                                            size_t vocab, float temperature, int k, uint64_t seed,
+                                                            uint64_t seed_stride, const int* __restrict__ step_ptr) {
+  __shared__ float topk_vals[256];
+  __shared__ int topk_idxs[256];
+  __shared__ Cand s_c[32];
+  const bf16* row = logits + (size_t)blockIdx.x * vocab;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (k <= 0) {
+    if (tid == 0) out[blockIdx.x] = -1;
+    return;
+  }
+  k = min(k, (int)min(vocab, (size_t)256));
+  if (!(temperature > 0.0f)) temperature = 1.0f;
+  if (tid < 256) {
+    topk_vals[tid] = -CUDART_INF_F;
+    topk_idxs[tid] = -1;
+  }
+  __syncthreads();
+  for (int sel = 0; sel < k; ++sel) {
+    float bv = -CUDART_INF_F;
+    int bi = -1;
+    for (size_t idx = tid; idx < vocab; idx += blockDim.x) {
+      float v = bf2f(row[idx]);
+      if (!(v > -CUDART_INF_F)) continue;  // -inf / NaN are never selected (v > local.val fails)
+      bool chosen = false;
+      for (int t = 0; t < sel; ++t)
+        if ((int)idx == topk_idxs[t]) {
+          chosen = true;
+          break;
+        }
+      if (!chosen && cand_better(v, (int)idx, bv, bi)) {
+        bv = v;
+        bi = (int)idx;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (cand_better(ov, oi, bv, bi)) {
+        bv = ov;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      s_c[warp].val = bv;
+      s_c[warp].idx = bi;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      bv = lane < (blockDim.x >> 5) ? s_c[lane].val : -CUDART_INF_F;
+      bi = lane < (blockDim.x >> 5) ? s_c[lane].idx : -1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (cand_better(ov, oi, bv, bi)) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      if (lane == 0) {
+        topk_vals[sel] = bi >= 0 ? bv : -CUDART_INF_F;
+        topk_idxs[sel] = bi;
+      }
+    }
+    __syncthreads();
+    if (topk_idxs[sel] == -1) break;
+  }
+  if (tid == 0) {
+    int actual_k = 0;
+    for (int i = 0; i < k; ++i) {
+      if (topk_idxs[i] != -1)
+        actual_k++;
+      else
+        break;
+    }
+    if (actual_k == 0) {
+      out[blockIdx.x] = -1;
+      return;
+    }
+    if (actual_k == 1) {  // softmax over one candidate is 1; u in (0,1] always selects it
+      out[blockIdx.x] = topk_idxs[0];
+      return;
+    }
+    float max_val = __fdiv_rn(topk_vals[0], temperature);
+    for (int i = 1; i < actual_k; ++i) {
+      float v = __fdiv_rn(topk_vals[i], temperature);
+      if (v > max_val) max_val = v;
+      topk_vals[i] = v;
+    }
+    topk_vals[0] = __fdiv_rn(topk_vals[0], temperature);
+    float sum = 0.0f;
+    for (int i = 0; i < actual_k; ++i) {
+      topk_vals[i] = expf(__fsub_rn(topk_vals[i], max_val));
+      sum = __fadd_rn(sum, topk_vals[i]);
+    }
+    curandState rng;
+    unsigned long long sd = seed + (unsigned long long)blockIdx.x * seed_stride + (step_ptr ? (unsigned)step_ptr[blockIdx.x] : 0u);
+    curand_init(sd, 0, 0, &rng);
+    float u = __fmul_rn(curand_uniform(&rng), sum);
+    float cum = 0.0f;
+    int picked = topk_idxs[actual_k - 1];
+    for (int i = 0; i < actual_k; ++i) {
+      cum = __fadd_rn(cum, topk_vals[i]);
+      if (u <= cum) {
+        picked = topk_idxs[i];
+        break;
+      }
+    }
+    out[blockIdx.x] = picked;
+  }
+}
+
+cudaError_t launch_sample_topk(const bf16* logits, int* out_tokens, int n_rows, size_t vocab, float temperature,
+                               int k, uint64_t seed, uint64_t seed_stride, const int* step_ptr, cudaStream_t st) {
+  if (n_rows == 0) return cudaSuccess;
+  sample_topk_kernel<<<n_rows, 1024, 0, st>>>(logits, out_tokens, vocab, temperature, k, seed, seed_stride, step_ptr);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ synthetic weights
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__global__ void synth_fill_kernel(bf16* blob, size_t elem_begin, size_t n, unsigned long long seed, int kind) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long g = elem_begin + i;
+  unsigned long long a = mix64(seed + (g + 1) * 0x9E3779B97F4A7C15ull);
+  unsigned long long b = mix64(a + 0x9E3779B97F4A7C15ull);
+  int sum = (int)((a & 0xffff) + ((a >> 16) & 0xffff) + ((a >> 32) & 0xffff) + (a >> 48) + (b & 0xffff) +
+                  ((b >> 16) & 0xffff) + ((b >> 32) & 0xffff) + (b >> 48));
+  float c = (float)(sum - 262140);
+  float v = kind == 0 ? __fmul_rn(c, 0.02f / 53509.92f) : __fadd_rn(1.0f, __fmul_rn(c, 0.05f / 53509.92f));
+  blob[g] = f2bf(v);
+}
+cudaError_t launch_synth_fill(bf16* blob, size_t elem_begin, size_t n_elems, uint64_t seed, int kind,
+                              cudaStream_t st) {
+  if (!n_elems) return cudaSuccess;
+  synth_fill_kernel<<<(unsigned)((n_elems + 255) / 256), 256, 0, st>>>(blob, elem_begin, n_elems, seed, kind);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ step bookkeeping
+__global__ void advance_kernel(int* pos, int* ids, const int* sampled, int n, int* step_ptr) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    pos[i] += 1;
+    ids[i] = sampled[i];
+    if (step_ptr) step_ptr[i] += 1;
+  }
+}
+cudaError_t launch_advance(int* pos, int* ids, const int* sampled, int n, int* step_ptr, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  advance_kernel<<<(n + 127) / 128, 128, 0, st>>>(pos, ids, sampled, n, step_ptr);
+  return cudaGetLastError();
+}
+
+}  // namespace qie

@@ -1,0 +1,184 @@
+"""Python mirror of the driver-level C ABI (include/qie_b200.h, section 2).
+
+Names follow the reference's host driver (/root/reference/layers/src/iengine.cu): an
+Engine owns the weight blob + KV pages (main(), iengine.cu:226-482), a sequence is what
+create_new_sequence() returns (iengine.cu:25-47), prefill()/decode_step() are llm() in
+its two states (src/qwen_main.cu:74-247 / 250-404).  All compute happens in
+libqie_b200.so; numpy arrays here are HOST buffers handed to the C ABI.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Config, EngineOpts, KvView, QieError, check  # noqa: F401
+
+# Qwen2.5 shape table. Operator semantics are the reference's (q/k-norm,
+# no bias, explicit lm_head, interleaved RoPE, eps 1e-4).
+ARCHS = {
+    "qwen2.5-0.5b": dict(hidden=896, inter=4864, layers=24, n_q=14, n_kv=2, head_dim=64, vocab=151936),
+    "qwen2.5-1.5b": dict(hidden=1536, inter=8960, layers=28, n_q=12, n_kv=2, head_dim=128, vocab=151936),
+    "qwen2.5-7b": dict(hidden=3584, inter=18944, layers=28, n_q=28, n_kv=4, head_dim=128, vocab=152064),
+    # small shapes for tests
+    "tiny": dict(hidden=128, inter=256, layers=2, n_q=4, n_kv=2, head_dim=64, vocab=512),
+    "small": dict(hidden=256, inter=640, layers=3, n_q=4, n_kv=2, head_dim=64, vocab=4096),
+    "small128": dict(hidden=256, inter=512, layers=2, n_q=2, n_kv=1, head_dim=128, vocab=2048),
+}
+REF_CONTEXT = 32786  # sic: /root/reference/layers/src/utills.cu:14
+
+
+def make_config(arch, context=REF_CONTEXT, **over):
+    d = dict(ARCHS[arch]) if isinstance(arch, str) else dict(arch)
+    d.update(over)
+    d.setdefault("context", context)
+    return Config(**d)
+
+
+def weight_bytes(cfg):
+    """bf16 bytes read per decode step (all layers + norms + lm_head), SURVEY 8d."""
+    H, I, L, hd = cfg.hidden, cfg.inter, cfg.layers, cfg.head_dim
+    Dq, Dkv = cfg.n_q * hd, cfg.n_kv * hd
+    return 2 * (L * (H * Dq + 2 * H * Dkv + Dq * H + 3 * H * I + 2 * H + 2 * hd) + H + cfg.vocab * H)
+
+
+def kv_bytes_per_pos(cfg):
+    return 2 * cfg.layers * cfg.n_kv * cfg.head_dim * 2
+
+
+def write_synthetic_checkpoint(cfg, seed, meta_path, weights_path):
+    check(_lib.lib().qie_synth_checkpoint_write(C.byref(cfg), seed, str(meta_path).encode(),
+                                                str(weights_path).encode()))
+
+
+def _i32(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+
+
+class Engine:
+    def __init__(self, meta_path=None, weights_path=None, *, synthetic=None, seed=1234, device=0,
+                 page_size=16, kv_bytes=0, max_pages=0, max_seqs=64, max_batch_tokens=256,
+                 context=REF_CONTEXT, use_graph=True, head_dim_hint=0):
+        L = _lib.lib()
+        o = EngineOpts()
+        L.qie_engine_opts_default(C.byref(o))
+        o.device, o.page_size, o.kv_bytes, o.max_pages = device, page_size, kv_bytes, max_pages
+        o.max_seqs, o.max_batch_tokens, o.context = max_seqs, max_batch_tokens, context
+        o.use_graph, o.head_dim_hint = int(use_graph), head_dim_hint
+        h = C.c_void_p()
+        if synthetic is not None:
+            cfg = synthetic if isinstance(synthetic, Config) else make_config(synthetic, context=context)
+            check(L.qie_engine_create_synthetic(C.byref(cfg), seed, C.byref(o), C.byref(h)))
+        else:
+            check(L.qie_engine_create(str(meta_path).encode(), str(weights_path).encode(), C.byref(o),
+                                      C.byref(h)))
+        self._h = h
+        self._L = L
+        cfg = Config()
+        check(L.qie_engine_get_config(h, C.byref(cfg)))
+        self.config = cfg
+
+    # -- lifecycle -------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.qie_engine_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration ---------------------------------------------------------
+    def set_sampling(self, topk=1, temperature_prefill=1.0, temperature_decode=0.7, seed=1234, add_step=True):
+        check(self._L.qie_engine_set_sampling(self._h, topk, temperature_prefill, temperature_decode, seed,
+                                              int(add_step)))
+
+    @property
+    def stream(self):
+        return self._L.qie_engine_stream(self._h)
+
+    def kv_view(self):
+        v = KvView()
+        check(self._L.qie_engine_kv_view(self._h, C.byref(v)))
+        return v
+
+    def weight_ptr(self, short_name, layer=-1):
+        n = C.c_size_t()
+        p = self._L.qie_engine_weight(self._h, short_name.encode(), layer, C.byref(n))
+        return p, n.value
+
+    # -- sequences -------------------------------------------------------------
+    def new_sequence(self):
+        s = C.c_int()
+        check(self._L.qie_seq_new(self._h, C.byref(s)))
+        return s.value
+
+    def free_sequence(self, seq):
+        check(self._L.qie_seq_free(self._h, seq))
+
+    def seq_len(self, seq):
+        return check(self._L.qie_seq_len(self._h, seq))
+
+    def pages_free(self):
+        return check(self._L.qie_kv_pages_free(self._h))
+
+    # -- forward ---------------------------------------------------------------
+    def prefill(self, seq, ids):
+        ids = _i32(ids)
+        tok = np.zeros(1, np.int32)
+        check(self._L.qie_prefill(self._h, seq, ids.ctypes.data, len(ids), tok.ctypes.data))
+        return int(tok[0])
+
+    def decode_step(self, seqs, tokens_in):
+        seqs, tokens_in = _i32(seqs), _i32(tokens_in)
+        out = np.zeros(len(seqs), np.int32)
+        check(self._L.qie_decode_step(self._h, seqs.ctypes.data, tokens_in.ctypes.data, len(seqs),
+                                      out.ctypes.data))
+        return out
+
+    def decode_run(self, seqs, tokens_in, steps):
+        seqs, tokens_in = _i32(seqs), _i32(tokens_in)
+        out = np.zeros((steps, len(seqs)), np.int32)
+        check(self._L.qie_decode_run(self._h, seqs.ctypes.data, tokens_in.ctypes.data, len(seqs), steps,
+                                     out.ctypes.data))
+        return out
+
+    def decode_step_device(self, seqs):
+        seqs = _i32(seqs)
+        check(self._L.qie_decode_step_device(self._h, seqs.ctypes.data, len(seqs)))
+
+    def sync(self):
+        check(self._L.qie_sync(self._h))
+
+    def launch_count(self):
+        return self._L.qie_launch_count(self._h)
+
+    # -- parity hooks ------------------------------------------------------------
+    def capture(self, on=True):
+        check(self._L.qie_capture_enable(self._h, int(on)))
+
+    def read_capture(self, tag, layer, max_elems=1 << 26):
+        probe = np.zeros(1, np.uint16)
+        n = check(self._L.qie_capture_read(self._h, tag.encode(), layer, probe.ctypes.data, 1))
+        out = np.zeros(n, np.uint16)
+        check(self._L.qie_capture_read(self._h, tag.encode(), layer, out.ctypes.data, n))
+        return out
+
+    def generate(self, ids, n_new):
+        """greedy/top-k generation of one sequence: prefill + n_new-1 decode steps."""
+        s = self.new_sequence()
+        try:
+            toks = [self.prefill(s, ids)]
+            if n_new > 1:
+                out = self.decode_run([s], [toks[0]], n_new - 1)
+                toks += [int(t) for t in out[:, 0]]
+            return toks
+        finally:
+            self.free_sequence(s)
