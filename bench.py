@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline metric on B200 (contract: see the task statement).
+
+Metric (BASELINE.json): decode tokens/s.  Workload at N=1 = BASELINE.json configs[1]:
+Qwen2.5-0.5B-arch bf16, batch 64 decode, 2048-token context, KV cache resident on one
+B200.  A "step" is one decode step of the whole batch (64 tokens).  N>1 (torchrun, one
+process per GPU) is data-parallel over independent sequences, no data-path collective:
+every rank runs the same per-GPU workload (weak scaling), value = tokens of all ranks /
+max-over-ranks device time.
+
+  value     : kernel-only rate -- token ids and KV already resident in HBM, steps replayed
+              from CUDA graphs, timed with CUDA events on the engine's stream.
+  e2e       : the same step through the C ABI entry point a host driver calls
+              (qie_decode_step: HOST token buffers in, HOST tokens out; the H2D/D2H copies
+              and the stream sync are inside the timed region).
+  roofline  : per-launch algorithmic bytes / live CUDA-event duration of the dominant
+              kernel class, against MEASURED_PEAKS.json.
+  cpu_baseline : the plain-C oracle (oracle/qie_oracle.c, "port") timed on the host cores
+              on a bounded sample.  bench.py is one of the places allowed to run oracle/.
+  --impl reference : the reference's own kernels (oracle/_ref, built from
+              /root/reference/layers/src) replaying llm()'s launch order on the GPU --
+              the reference has no CPU implementation; its only implementation is CUDA.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ARCH = "qwen2.5-0.5b"
+BATCH = 64
+CTX = 2048
+METRIC = "decode tokens/s (Qwen2.5-0.5B-arch bf16, batch 64, ctx 2048)"
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for i, n in enumerate(names):
+                    if r[5 + i].lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def cpu_baseline_port(cfg_name, sample_tokens=3, prompt_len=8):
+    """plain-C oracle (scalar port, row-parallel over all host cores) on a bounded sample:
+    one sequence, short prompt, `sample_tokens` decode tokens of the same architecture."""
+    import numpy as np
+
+    import qwen_inference_engine_b200 as q
+    from oracle.oracle import Oracle, OracleModel
+    cores = os.cpu_count() or 1
+    o = Oracle()
+    o.set_threads(cores)
+    cfg = q.make_config(cfg_name)
+    d = tempfile.mkdtemp(prefix="qie_bench_")
+    meta, wts = os.path.join(d, "meta_data.txt"), os.path.join(d, "weights.bin")
+    q.write_synthetic_checkpoint(cfg, 1234, meta, wts)
+    om = OracleModel(o, meta, wts)
+    s = om.new_seq()
+    tok = om.prefill(s, np.arange(1, prompt_len + 1, dtype=np.int32))
+    t0 = time.perf_counter()
+    for i in range(sample_tokens):
+        tok = om.decode(s, tok, seed=1234 + 1 + i)
+    dt = time.perf_counter() - t0
+    om.close()
+    try:
+        os.remove(wts)
+        os.remove(meta)
+        os.rmdir(d)
+    except OSError:
+        pass
+    return {"value": sample_tokens / dt, "unit": "tokens/s", "cores": cores, "kind": "port",
+            "sample": f"oracle/qie_oracle.c: {sample_tokens} greedy decode tokens of ONE {cfg_name} sequence after a "
+                      f"{prompt_len}-token prompt (context {prompt_len + 1}..{prompt_len + sample_tokens}), matmul rows over "
+                      f"{cores} pthreads; per-sequence rate (a batch of 64 is 64 such sequences one after another)"}
+
+
+def run_reference(args):
+    """the reference's own CUDA kernels (oracle/_ref) replaying llm()'s decode branch."""
+    rank, world, local = dist_env()
+    if rank != 0:
+        return 0
+    import torch
+
+    import qwen_inference_engine_b200 as q
+    from oracle.oracle import Ref, RefSeq
+    torch.cuda.set_device(0)
+    ref = Ref()
+    eng = q.Engine(synthetic=ARCH, seed=1234, kv_bytes=64 << 20, max_seqs=2, max_batch_tokens=16)  # weight blob only
+    desc = ref.model_desc(eng)
+    rs = RefSeq(ref, desc, page_size=4)  # the reference's main() uses page_size 4 (iengine.cu:334)
+    rs.fake_context(CTX)
+    tok = 785
+    for _ in range(args.warmup):
+        tok = rs.decode(tok)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        tok = rs.decode(tok)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    rs.close()
+    eng.close()
+    val = args.steps / dt
+    sample = (f"reference CUDA kernels (sm_100a build of /root/reference/layers/src, launch order + syncs of llm() "
+              f"decode) on ONE sequence at context {CTX}.. (KV pages pre-allocated, zero-filled), {args.steps} tokens; "
+              "the reference has no batching: a batch of 64 is 64 such calls, so tokens/s is the per-call rate")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "tokens/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic (seeded random-init weights; zero KV cache of the stated length)",
+            "config": {"workload": f"{ARCH} decode, batch {BATCH} (processed one sequence at a time), ctx {CTX}",
+                       "note": "rank 0 only; the reference is single-GPU, single-sequence"},
+            "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": 1, "kind": "reference", "sample": sample},
+            "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--ctx", type=int, default=CTX)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the batch-1 (configs[0]) side measurement")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        if args.steps > 4:
+            args.steps = 4  # each reference token at ctx 2048 takes seconds (page-list walks)
+        args.warmup = min(args.warmup, 1)
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+
+    import qwen_inference_engine_b200 as q
+
+    rank, world, local = dist_env()
+    use_dist = world > 1
+    torch.cuda.set_device(local)
+    if use_dist:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    B, ctx = args.batch, args.ctx
+    cfg = q.make_config(ARCH)
+    kvpp = q.kv_bytes_per_pos(cfg)
+    total_steps = 2 * (args.warmup + args.steps) + 8
+    kv_need = B * (ctx + total_steps + 64) * kvpp + (64 << 20)
+    eng = q.Engine(synthetic=ARCH, seed=1234, device=local, kv_bytes=kv_need, max_seqs=B + 1, max_batch_tokens=max(B, 64),
+                   page_size=16)
+    seqs = []
+    for i in range(B):
+        s = eng.new_sequence()
+        eng.fill_synthetic(s, ctx, seed=1000 + 17 * rank + i)
+        seqs.append(s)
+    rng = np.random.default_rng(1234 + rank)
+    tokens = rng.integers(0, cfg.vocab, size=B).astype(np.int32)
+
+    ext = torch.cuda.ExternalStream(eng.stream)
+
+    def barrier():
+        eng.sync()
+        torch.cuda.synchronize()
+        if use_dist:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- kernel-only leg (graph replay, ids resident on the device) ----------
+    cur = eng.decode_step(seqs, tokens)  # stages ids/pos on the device, first graph shape seen
+    for _ in range(args.warmup):
+        eng.decode_step_device(seqs)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    with torch.cuda.stream(ext):
+        e0.record()
+    for _ in range(args.steps):
+        eng.decode_step_device(seqs)
+        launches += eng.launch_count()
+    with torch.cuda.stream(ext):
+        e1.record()
+    eng.sync()
+    ms_kernel = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    barrier()
+
+    # ---------------- e2e leg (host buffers through the C ABI) ----------------------------
+    cur = eng.decode_step(seqs, tokens)
+    for _ in range(args.warmup):
+        cur = eng.decode_step(seqs, cur)
+    barrier()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(ext):
+        e0.record()
+    for _ in range(args.steps):
+        cur = eng.decode_step(seqs, cur)
+    with torch.cuda.stream(ext):
+        e1.record()
+    eng.sync()
+    ms_e2e = max(e0.elapsed_time(e1), 1000.0 * (time.perf_counter() - t0))
+    barrier()
+
+    # ---------------- per-kernel-class timing of one eager step (roofline leg) ------------
+    prof = eng.decode_step_profile(seqs, cur)
+    ctx_now = eng.seq_len(seqs[0])
+
+    if use_dist:
+        t = torch.tensor([ms_kernel, ms_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_kernel, ms_e2e = float(t[0]), float(t[1])
+
+    tokens_total = B * args.steps * world
+    value = tokens_total / (ms_kernel / 1000.0)
+    e2e_val = tokens_total / (ms_e2e / 1000.0)
+
+    # roofline of the dominant kernel class
+    peak, peak_src = measured_peaks()
+    H, I, hd = cfg.hidden, cfg.inter, cfg.head_dim
+    Dq, Dkv = cfg.n_q * hd, cfg.n_kv * hd
+    alg_bytes = {  # algorithmic bytes of ONE launch of each class (DESIGN.md "roofline arithmetic")
+        "attention": B * ctx_now * 2 * Dkv * 2 + 2 * B * Dq * 2,
+        "gemm_qkv": 2 * H * (Dq + 2 * Dkv) + B * 2 * (H + Dq + 2 * Dkv),
+        "gemm_o": 2 * Dq * H + B * 2 * (Dq + 2 * H),
+        "gemm_gateup": 2 * 2 * H * I + B * 2 * (H + I),
+        "gemm_down": 2 * H * I + B * 2 * (I + 2 * H),
+        "lm_head": 2 * cfg.vocab * H + B * 2 * (H + cfg.vocab),
+    }
+    step_ms_eager = sum(v[0] for v in prof.values())
+    dom = max(alg_bytes, key=lambda k: prof.get(k, (0, 0))[0])
+    dom_ms, dom_n = prof[dom]
+    dom_avg_s = (dom_ms / max(dom_n, 1)) / 1000.0
+    achieved = alg_bytes[dom] / dom_avg_s / 1e9 if dom_avg_s > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(dom)
+        except Exception:
+            traffic = None
+    step_bytes = q.weight_bytes(cfg) + B * ctx_now * kvpp + B * kvpp + B * 2 * H
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_launch": alg_bytes[dom], "avg_launch_us": dom_avg_s * 1e6,
+                "share_of_step": dom_ms / step_ms_eager if step_ms_eager else None,
+                "step": {"alg_bytes": step_bytes, "achieved_GBs": step_bytes / (ms_kernel / args.steps / 1000.0) / 1e9,
+                         "frac_of_peak": step_bytes / (ms_kernel / args.steps / 1000.0) / 1e9 / peak},
+                "by_kernel_ms": {k: round(v[0], 4) for k, v in prof.items()},
+                "by_kernel_launches": {k: v[1] for k, v in prof.items()}}
+
+    line = {"metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_kernel / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic: seeded random-init weights generated on the device; KV cache pre-filled with seeded "
+                    "random K/V (no real prefill); token ids fed back from the sampler",
+            "config": {"workload": f"{ARCH} decode, batch {B} per GPU, ctx {ctx} at the first timed step (+1 per step)",
+                       "parallelism": f"dp{world}", "page_size": 16, "sampling": "greedy (top-k 1, reference tie-break)",
+                       "numerics": "reference-order kernels (bit-identical to the reference's kernels per sequence)",
+                       "l2": f"working set per step {step_bytes / 1e9:.2f} GB >> 126 MB L2 (inputs larger than L2, no flush)"},
+            "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": int(4 * B), "d2h_bytes_per_step": int(4 * B),
+                    "ms_per_step": ms_e2e / args.steps,
+                    "api": "qie_decode_step (HOST int32 tokens in/out, pinned staging, one H2D + one D2H + stream sync per step)"},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+
+    if rank == 0 and world == 1 and not args.no_extra:
+        # configs[0] side measurement: batch 1, 32-token prompt, 128 greedy tokens (the parity case)
+        try:
+            ids = np.array([151643, 785, 50802, 1525, 3818] + list(range(100, 127)), np.int32)
+            s1 = eng.new_sequence()
+            t_first = eng.prefill(s1, ids)
+            eng.decode_run([s1], [t_first], 8)
+            eng.sync()
+            t0 = time.perf_counter()
+            out = eng.decode_run([s1], [int(t_first)], 120)
+            dt = time.perf_counter() - t0
+            b1_bytes = q.weight_bytes(cfg) + kvpp * (eng.seq_len(s1) - 60)
+            line["extra"] = {"batch1": {"workload": "configs[0]: batch 1, 32-token prompt, greedy decode (qie_decode_run, 120 tokens)",
+                                        "tokens_per_s": 120 / dt, "us_per_token": 1e6 * dt / 120,
+                                        "frac_of_hbm_peak": (b1_bytes * 120 / dt / 1e9) / peak}}
+            eng.free_sequence(s1)
+        except Exception as ex:  # the side measurement must never break the contract line
+            line["extra"] = {"batch1_error": str(ex)}
+    eng.close()
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline_port(ARCH)
+        except Exception as ex:
+            line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"failed: {ex}"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if use_dist:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -196,6 +196,16 @@ long qie_capture_read(qie_engine* e, const char* tag, int layer, qie_bf16* h_out
 /* launch statistics of the last forward: kernels launched by this library. */
 long qie_launch_count(const qie_engine* e);
 
+/* Measurement helpers (bench.py). qie_seq_fill_synthetic appends n_pos positions of seeded
+ * random K/V to a sequence WITHOUT running the model (stand-in for a long prefill when only
+ * decode is timed). qie_decode_step_profile runs one decode step eagerly with a CUDA event
+ * pair around every launch and returns, per kernel class, the summed device time (ms) and
+ * the launch count; class names come from qie_kernel_kind_name (NULL past the last). */
+int qie_seq_fill_synthetic(qie_engine* e, int seq, int n_pos, uint64_t seed);
+int qie_decode_step_profile(qie_engine* e, const int* h_seqs, const int32_t* h_tokens_in, int n, float* ms_by_kind,
+                            int* launches_by_kind, int n_kinds);
+const char* qie_kernel_kind_name(int kind);
+
 #ifdef __cplusplus
 }
 #endif

@@ -290,6 +290,7 @@ class Ref:
         L.ref_seq_pages.restype = vp
         L.ref_seq_pages.argtypes = [vp]
         L.ref_seq_read.argtypes = [vp, C.c_char_p, vp, sz]
+        L.ref_seq_fake_context.argtypes = [vp, i32]
         L.ref_forward_prefill.argtypes = [vp, vp, i32, i32, f32, u64, _TAP_FN, vp]
         L.ref_forward_decode.argtypes = [vp, i32, i32, f32, u64, i32, _TAP_FN, vp]
 
@@ -343,6 +344,10 @@ class RefSeq:
     def decode(self, token, topk=1, temperature=0.7, seed=1234, with_syncs=True, taps=None):
         return self.ref.L.ref_forward_decode(self.h, int(token), topk, temperature, seed, int(with_syncs),
                                              self._tap(taps), None)
+
+    def fake_context(self, n_ctx):
+        if self.ref.L.ref_seq_fake_context(self.h, n_ctx):
+            raise RuntimeError("ref_seq_fake_context failed")
 
     def read(self, tag, n):
         out = np.zeros(n, np.uint16)

@@ -366,6 +366,22 @@ int ref_forward_prefill(void* h, const int* ids, int n_tok, int topk, float temp
   return tok;
 }
 
+// bench only: give the sequence a cache of n_ctx (zero) positions without running the
+// O(T^2 * pages) reference prefill, so a decode step at a long context can be timed.
+int ref_seq_fake_context(void* h, int n_ctx) {
+  ref_seq* s = (ref_seq*)h;
+  ModelBuffers* b = &s->buf;
+  seq_alloc(s, 1);
+  int pages_required = ((n_ctx + s->page_size - 1) / s->page_size) + 1;
+  size_t elems = (size_t)s->page_size * b->number_of_layers * b->hidden_dim_kv;
+  s->pages = (page_table*)ref_pages_create(pages_required, elems);
+  b->k_cache = s->pages->k_page_ptr;
+  b->v_cache = s->pages->v_page_ptr;
+  b->sequence_len = n_ctx;
+  s->step = 1;
+  return sync_check("fake_context");
+}
+
 // decode branch, qwen_main.cu:250-404, one token
 int ref_forward_decode(void* h, int token, int topk, float temperature, unsigned long long seed, int with_syncs,
                        ref_tap_fn tap, void* user) {

@@ -97,6 +97,9 @@ def lib():
         "qie_capture_enable": (i32, [vp, i32]),
         "qie_capture_read": (C.c_long, [vp, C.c_char_p, i32, vp, sz]),
         "qie_launch_count": (C.c_long, [vp]),
+        "qie_seq_fill_synthetic": (i32, [vp, i32, i32, u64]),
+        "qie_decode_step_profile": (i32, [vp, vp, vp, i32, vp, vp, i32]),
+        "qie_kernel_kind_name": (C.c_char_p, [i32]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

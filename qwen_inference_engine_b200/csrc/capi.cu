@@ -699,6 +699,7 @@ int qie_decode_step_device(qie_engine* e, const int* h_seqs, int n) {
   int mk = 0;
   int rc = decode_prepare(e, h_seqs, n, &mk);
   if (rc) return rc;
+  e->launches = 0;
   rc = decode_launch(e, n, mk);
   if (rc) return rc;
   for (int i = 0; i < n; ++i) {
@@ -732,5 +733,66 @@ long qie_capture_read(qie_engine* e, const char* tag, int layer, qie_bf16* h_out
 }
 
 long qie_launch_count(const qie_engine* e) { return e ? e->launches : 0; }
+
+int qie_seq_fill_synthetic(qie_engine* e, int seq, int n_pos, uint64_t seed) {
+  int rc = check_seq(e, seq);
+  if (rc) return rc;
+  if (n_pos <= 0) return fail(QIE_EINVAL, "fill_synthetic: n_pos must be > 0");
+  CU(cudaSetDevice(e->opts.device));
+  Sequence& s = e->seqs[seq];
+  rc = ensure_pages(e, seq, s.len + n_pos);
+  if (rc < 0) return rc;
+  if (rc) CU(push_block_row(e, seq));
+  CU(launch_kv_fill(e->kv, e->block_table_d + (size_t)seq * e->max_pages_per_seq, s.len, n_pos,
+                    seed + 0x51ull * (uint64_t)seq, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  s.len += n_pos;
+  if (s.step == 0) s.step = 1;
+  return QIE_OK;
+}
+
+const char* qie_kernel_kind_name(int kind) {
+  static const char* names[KK_COUNT] = {"embedding", "rmsnorm", "gemm_qkv", "qkv_post", "attention", "gemm_o",
+                                        "gemm_gateup", "gemm_down", "lm_head", "sample", "advance"};
+  return kind >= 0 && kind < KK_COUNT ? names[kind] : nullptr;
+}
+
+int qie_decode_step_profile(qie_engine* e, const int* h_seqs, const int32_t* h_tokens_in, int n, float* ms_by_kind,
+                            int* launches_by_kind, int n_kinds) {
+  if (!h_tokens_in || !ms_by_kind || !launches_by_kind || n_kinds < KK_COUNT)
+    return fail(QIE_EINVAL, "decode_step_profile: need %d kinds", (int)KK_COUNT);
+  int mk = 0;
+  int rc = decode_prepare(e, h_seqs, n, &mk);
+  if (rc) return rc;
+  rc = decode_stage_inputs(e, h_seqs, h_tokens_in, n);
+  if (rc) return rc;
+  e->launches = 0;
+  e->prof.clear();
+  e->prof_on = true;
+  cudaError_t fe = forward_rows(e, n, ((mk + 127) / 128) * 128, 0, n, e->temp_decode, true);
+  e->prof_on = false;
+  cudaError_t se = cudaStreamSynchronize(e->stream);
+  for (int i = 0; i < n_kinds; ++i) {
+    ms_by_kind[i] = 0.f;
+    launches_by_kind[i] = 0;
+  }
+  for (auto& r : e->prof) {
+    float ms = 0.f;
+    if (fe == cudaSuccess && se == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      ms_by_kind[r.kind] += ms;
+      launches_by_kind[r.kind] += 1;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  e->prof.clear();
+  if (fe != cudaSuccess) return cuda_fail(fe, "forward (profile)");
+  if (se != cudaSuccess) return cuda_fail(se, "sync (profile)");
+  for (int i = 0; i < n; ++i) {
+    e->seqs[h_seqs[i]].len += 1;
+    e->seqs[h_seqs[i]].step += 1;
+  }
+  return QIE_OK;
+}
 
 }  // extern "C"

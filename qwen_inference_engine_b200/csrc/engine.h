@@ -86,9 +86,21 @@ struct qie_engine {
   std::map<std::pair<int, int>, GraphEntry> graphs;
 
   long launches = 0;
+
+  // per-kernel-class device timing of one eager step (bench.py roofline leg)
+  bool prof_on = false;
+  struct ProfRec {
+    int kind;
+    cudaEvent_t a, b;
+  };
+  std::vector<ProfRec> prof;
 };
 
 namespace qie {
+enum KernelKind {
+  KK_EMBED = 0, KK_RMSNORM, KK_GEMM_QKV, KK_QKV_POST, KK_ATTN, KK_GEMM_O, KK_GEMM_GATEUP, KK_GEMM_DOWN,
+  KK_LM_HEAD, KK_SAMPLE, KK_ADVANCE, KK_COUNT
+};
 // one forward over n_rows rows already described in ids_d/pos_d/slot_d; logits for rows
 // [out_row0, out_row0+n_out); samples into sampled_d[0..n_out). Returns cudaSuccess or the
 // first launch error. Counts launches into e->launches.

@@ -102,6 +102,9 @@ cudaError_t launch_sample_topk(const bf16* logits, int* out_tokens, int n_rows, 
 cudaError_t launch_synth_fill(bf16* blob, size_t elem_begin, size_t n_elems, uint64_t seed, int kind,
                               cudaStream_t st);
 
+cudaError_t launch_kv_fill(const KvGeom& kv, const int* block_row, int pos0, int n_pos, uint64_t seed,
+                           cudaStream_t st);
+
 // step bookkeeping on the device: pos[i] += 1 ; ids <- sampled tokens
 cudaError_t launch_advance(int* pos, int* ids, const int* sampled, int n, int* step_ptr, cudaStream_t st);
 

@@ -604,6 +604,36 @@ cudaError_t launch_synth_fill(bf16* blob, size_t elem_begin, size_t n_elems, uin
   return cudaGetLastError();
 }
 
+// fill positions [pos0, pos0+n_pos) of one sequence's KV pages (all layers, K and V) with
+// seeded N(0,1)-like values: bench-only stand-in for a long prefill
+__global__ void kv_fill_kernel(KvGeom kv, const int* __restrict__ block_row, int pos0, int n_pos,
+                               unsigned long long seed) {
+  const size_t per_pos = (size_t)kv.n_layers * 2 * kv.n_kv * kv.hd;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per_pos * n_pos) return;
+  int p = (int)(i / per_pos);
+  size_t r = i % per_pos;
+  int d = (int)(r % kv.hd);
+  r /= kv.hd;
+  int head = (int)(r % kv.n_kv);
+  r /= kv.n_kv;
+  int which = (int)(r % 2);
+  int layer = (int)(r / 2);
+  int pos = pos0 + p;
+  int page = block_row[pos / kv.page_size];
+  unsigned long long a = mix64(seed + (i + 1) * 0x9E3779B97F4A7C15ull);
+  int sum = (int)((a & 0xffff) + ((a >> 16) & 0xffff) + ((a >> 32) & 0xffff) + (a >> 48));
+  float v = __fmul_rn((float)(sum - 131070), 1.0f / 37837.0f);
+  kv.chunk(page, layer, which, head)[(size_t)(pos % kv.page_size) * kv.hd + d] = f2bf(v);
+}
+cudaError_t launch_kv_fill(const KvGeom& kv, const int* block_row, int pos0, int n_pos, uint64_t seed,
+                           cudaStream_t st) {
+  size_t n = (size_t)kv.n_layers * 2 * kv.n_kv * kv.hd * n_pos;
+  if (!n) return cudaSuccess;
+  kv_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kv, block_row, pos0, n_pos, seed);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ step bookkeeping
 __global__ void advance_kernel(int* pos, int* ids, const int* sampled, int n, int* step_ptr) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;

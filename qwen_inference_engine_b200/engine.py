@@ -157,6 +157,26 @@ class Engine:
     def sync(self):
         check(self._L.qie_sync(self._h))
 
+    def fill_synthetic(self, seq, n_pos, seed=99):
+        """append n_pos positions of seeded random K/V without running the model (bench only)"""
+        check(self._L.qie_seq_fill_synthetic(self._h, seq, n_pos, seed))
+
+    def decode_step_profile(self, seqs, tokens_in):
+        """one eager decode step with an event pair around every launch ->
+        {kernel class: (summed ms, launches)}"""
+        seqs, tokens_in = _i32(seqs), _i32(tokens_in)
+        ms = np.zeros(32, np.float32)
+        cnt = np.zeros(32, np.int32)
+        check(self._L.qie_decode_step_profile(self._h, seqs.ctypes.data, tokens_in.ctypes.data, len(seqs),
+                                              ms.ctypes.data, cnt.ctypes.data, 32))
+        out = {}
+        for i in range(32):
+            name = self._L.qie_kernel_kind_name(i)
+            if name is None:
+                break
+            out[name.decode()] = (float(ms[i]), int(cnt[i]))
+        return out
+
     def launch_count(self):
         return self._L.qie_launch_count(self._h)
 
