@@ -41,7 +41,7 @@ typedef uint16_t qie_bf16;     /* raw __nv_bfloat16 bits */
 
 const char* qie_last_error(void);
 /* ABI version; bumped on any signature change. */
-int qie_abi_version(void);
+int qie_abi_version(void); /* currently 2 */
 
 /* ------------------------------------------------------------------------------------
  * (1) operator level.  All pointers are DEVICE pointers unless named h_*.
@@ -110,6 +110,15 @@ int qie_attention(const qie_kv_view* kv, int layer, const qie_bf16* Q, qie_bf16*
 int qie_sample_topk(const qie_bf16* logits, int* out_tokens, int n_rows, size_t vocab, float temperature, int k,
                     uint64_t seed, uint64_t seed_stride, qie_stream st);
 
+/* FAST-numerics operators (same contracts as qie_matmul / qie_attention, results within
+ * the 1e-2 bf16 tolerance instead of bit-exact): tcgen05/TMEM/TMA GEMM with split-K, and
+ * split-KV flash-decoding (one query token per row; n_splits = 0 picks a default).
+ * Scratch space is allocated internally on first use. */
+int qie_matmul_fast(const qie_bf16* A, const qie_bf16* B, qie_bf16* C, int M, int N, int K, qie_stream st);
+int qie_attention_decode_fast(const qie_kv_view* kv, int layer, const qie_bf16* Q, qie_bf16* out, const int* pos,
+                              const int* slot, const int* block_table, int max_pages, int n_tok, int n_q_heads,
+                              int n_splits, qie_stream st);
+
 /* ------------------------------------------------------------------------------------
  * (2) driver level
  * ---------------------------------------------------------------------------------- */
@@ -129,7 +138,16 @@ typedef struct {
   int head_dim_hint;     /* used only if the checkpoint has no q_norm tensor */
   int use_graph;         /* replay decode steps from a CUDA graph */
   int tp_rank, tp_size;  /* tensor-parallel shard (1 = off) */
+  int numerics;          /* QIE_NUMERICS_REFERENCE_ORDER (default) or QIE_NUMERICS_FAST */
 } qie_engine_opts;
+
+/* REFERENCE_ORDER: every kernel reproduces the reference's fp32 operation order; results
+ * are bit-identical to the reference's kernels (greedy tokens, logits, activations).
+ * FAST: rows > 8 use the tcgen05/TMEM GEMM (+ split-K), decode attention is split-KV
+ * flash-decoding, RMSNorm reduces in parallel; results agree with the reference within
+ * the 1e-2 bf16 tolerance of BASELINE.json, not bit for bit. */
+#define QIE_NUMERICS_REFERENCE_ORDER 0
+#define QIE_NUMERICS_FAST 1
 
 void qie_engine_opts_default(qie_engine_opts* o);
 

@@ -31,7 +31,7 @@ class EngineOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("page_size", C.c_int), ("max_pages", C.c_int),
                 ("kv_bytes", C.c_size_t), ("max_seqs", C.c_int), ("max_batch_tokens", C.c_int),
                 ("context", C.c_int), ("head_dim_hint", C.c_int), ("use_graph", C.c_int),
-                ("tp_rank", C.c_int), ("tp_size", C.c_int)]
+                ("tp_rank", C.c_int), ("tp_size", C.c_int), ("numerics", C.c_int)]
 
 
 class KvView(C.Structure):
@@ -75,6 +75,8 @@ def lib():
         "qie_kv_store": (i32, [C.POINTER(KvView), i32, vp, vp, vp, vp, vp, i32, i32, vp]),
         "qie_attention": (i32, [C.POINTER(KvView), i32, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
         "qie_sample_topk": (i32, [vp, vp, i32, sz, f32, i32, u64, u64, vp]),
+        "qie_matmul_fast": (i32, [vp, vp, vp, i32, i32, i32, vp]),
+        "qie_attention_decode_fast": (i32, [C.POINTER(KvView), i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "qie_engine_opts_default": (None, [C.POINTER(EngineOpts)]),
         "qie_synth_checkpoint_write": (i32, [C.POINTER(Config), u64, C.c_char_p, C.c_char_p]),
         "qie_engine_create": (i32, [C.c_char_p, C.c_char_p, C.POINTER(EngineOpts), C.POINTER(vp)]),

@@ -32,7 +32,7 @@ static int cuda_fail(cudaError_t e, const char* what) {
 extern "C" {
 
 const char* qie_last_error(void) { return g_err; }
-int qie_abi_version(void) { return 1; }
+int qie_abi_version(void) { return 2; }
 
 // ---------------------------------------------------------------- operator level
 int qie_embedding(qie_bf16* out, const qie_bf16* table, const int* ids, size_t hidden, size_t n_tok, qie_stream st) {
@@ -144,6 +144,78 @@ int qie_sample_topk(const qie_bf16* logits, int* out_tokens, int n_rows, size_t 
   return QIE_OK;
 }
 
+static int scratch(void** p, size_t* cap, size_t need) {
+  if (*cap >= need) return QIE_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  CU(cudaMalloc(p, need));
+  *cap = need;
+  return QIE_OK;
+}
+
+int qie_matmul_fast(const qie_bf16* A, const qie_bf16* B, qie_bf16* C, int M, int N, int K, qie_stream st) {
+  if (M < 1 || N < 64 || (N % 8) || K < 1) return fail(QIE_EINVAL, "matmul_fast: need M>=1, N>=64, N%%8==0");
+  static thread_local void* ws = nullptr;
+  static thread_local size_t ws_cap = 0;
+  int dev = 0, sms = 0;
+  CU(cudaGetDevice(&dev));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int rc = scratch(&ws, &ws_cap, std::max<size_t>((size_t)32 << 20, (size_t)M * K * 4 * 4));
+  if (rc) return rc;
+  TensorMap2D wmap, xmap;
+  CU(make_tensor_map_2d(&wmap, (const bf16*)B, K, N, 128));
+  CU(make_tensor_map_2d(&xmap, (const bf16*)A, M, N, tc_token_tile(M)));
+  TcGemm t{};
+  t.w[0] = &wmap;
+  t.x = &xmap;
+  t.rows[0] = K;
+  t.nseg = 1;
+  t.M = M;
+  t.K = N;
+  t.epi = EPI_STORE;
+  t.out = (bf16*)C;
+  t.ld_out = K;
+  t.ws = (float*)ws;
+  t.ws_bytes = ws_cap;
+  t.max_splits = (int)std::max<size_t>(1, ws_cap / ((size_t)M * K * sizeof(float)));
+  CU(launch_gemm_tcgen05(t, sms, (cudaStream_t)st, nullptr));
+  return QIE_OK;
+}
+
+int qie_attention_decode_fast(const qie_kv_view* kv, int layer, const qie_bf16* Q, qie_bf16* out, const int* pos,
+                              const int* slot, const int* block_table, int max_pages, int n_tok, int n_q_heads,
+                              int n_splits, qie_stream st) {
+  if (!kv || layer < 0 || layer >= kv->n_layers) return fail(QIE_EINVAL, "attention_decode_fast: bad layer");
+  if (n_q_heads % kv->n_kv_heads || n_q_heads / kv->n_kv_heads > 16 || (kv->head_dim != 64 && kv->head_dim != 128))
+    return fail(QIE_EINVAL, "attention_decode_fast: need n_q/n_kv <= 16 and head_dim 64 or 128");
+  static thread_local void *wo = nullptr, *wml = nullptr;
+  static thread_local size_t wo_cap = 0, wml_cap = 0;
+  if (n_splits <= 0) n_splits = 4;
+  n_splits = std::min(n_splits, 64);
+  int rc = scratch(&wo, &wo_cap, (size_t)n_splits * n_tok * n_q_heads * kv->head_dim * 4);
+  if (rc) return rc;
+  rc = scratch(&wml, &wml_cap, (size_t)n_splits * n_tok * n_q_heads * 2 * 4);
+  if (rc) return rc;
+  FastAttnArgs a{};
+  a.q = (const bf16*)Q;
+  a.out = (bf16*)out;
+  a.pos = pos;
+  a.slot = slot;
+  a.block_table = block_table;
+  a.max_pages = max_pages;
+  a.n_tok = n_tok;
+  a.n_q = n_q_heads;
+  a.layer = layer;
+  a.n_splits = n_splits;
+  a.scale_log2 = 1.4426950408889634f / sqrtf((float)kv->head_dim);
+  a.ws_o = (float*)wo;
+  a.ws_ml = (float*)wml;
+  a.kv = geom_of(kv);
+  CU(launch_attention_decode_fast(a, (cudaStream_t)st));
+  return QIE_OK;
+}
+
 // ---------------------------------------------------------------- driver level
 void qie_engine_opts_default(qie_engine_opts* o) {
   memset(o, 0, sizeof(*o));
@@ -158,6 +230,7 @@ void qie_engine_opts_default(qie_engine_opts* o) {
   o->use_graph = 1;
   o->tp_rank = 0;
   o->tp_size = 1;
+  o->numerics = QIE_NUMERICS_REFERENCE_ORDER;
 }
 
 int qie_synth_checkpoint_write(const qie_config* cfg, uint64_t seed, const char* meta_path,
@@ -195,7 +268,8 @@ static void engine_free(qie_engine* e) {
   for (auto& kvp : e->cap)
     if (kvp.second.d) cudaFree(kvp.second.d);
   void* dev[] = {e->blob, e->cos_d, e->sin_d, e->kv.pool, e->block_table_d, e->ids_d, e->pos_d, e->slot_d,
-                 e->sampled_d, e->rowstep_d, e->x, e->xn, e->q, e->k, e->v, e->att, e->h, e->logits};
+                 e->sampled_d, e->rowstep_d, e->x, e->xn, e->q, e->k, e->v, e->att, e->h, e->logits, e->qkv,
+                 e->gemm_ws, e->attn_ws_o, e->attn_ws_ml};
   for (void* p : dev)
     if (p) cudaFree(p);
   if (e->block_table_h) cudaFreeHost(e->block_table_h);
@@ -291,6 +365,28 @@ static int engine_finish_setup(qie_engine* e) {
   CU(cudaMalloc(&e->h, R * I * sizeof(bf16)));
   e->logits_rows = std::min<int>((int)R, o.max_seqs);
   CU(cudaMalloc(&e->logits, (size_t)e->logits_rows * c.vocab * sizeof(bf16)));
+  if (o.numerics == QIE_NUMERICS_FAST) {
+    if (c.n_q / c.n_kv > 16 || c.head_dim > 128) return fail(QIE_EINVAL, "fast numerics: need n_q/n_kv <= 16 and head_dim <= 128");
+    if ((c.hidden % 64) || (c.inter % 64) || ((c.n_q * c.head_dim) % 64)) return fail(QIE_EINVAL, "fast numerics: inner dims must be multiples of 64");
+    e->wmaps.resize(c.layers);
+    for (int l = 0; l < c.layers; ++l) {
+      const LayerWeights& w = e->L[l];
+      qie_engine::LayerMaps& m = e->wmaps[l];
+      CU(make_tensor_map_2d(&m.q, w.q, (int)Dq, (int)H, 128));
+      CU(make_tensor_map_2d(&m.k, w.k, (int)Dkv, (int)H, 128));
+      CU(make_tensor_map_2d(&m.v, w.v, (int)Dkv, (int)H, 128));
+      CU(make_tensor_map_2d(&m.o, w.o, (int)H, (int)Dq, 128));
+      CU(make_tensor_map_2d(&m.gate, w.gate, (int)I, (int)H, 128));
+      CU(make_tensor_map_2d(&m.up, w.up, (int)I, (int)H, 128));
+      CU(make_tensor_map_2d(&m.down, w.down, (int)H, (int)I, 128));
+    }
+    CU(make_tensor_map_2d(&e->lm_head_map, e->lm_head, c.vocab, (int)H, 128));
+    CU(cudaMalloc(&e->qkv, R * (Dq + 2 * Dkv) * sizeof(bf16)));
+    e->gemm_ws_bytes = std::max<size_t>((size_t)64 << 20, R * 2 * I * sizeof(float) * 2);
+    CU(cudaMalloc(&e->gemm_ws, e->gemm_ws_bytes));
+    CU(cudaMalloc(&e->attn_ws_o, (size_t)e->attn_max_splits * R * Dq * sizeof(float)));
+    CU(cudaMalloc(&e->attn_ws_ml, (size_t)e->attn_max_splits * R * c.n_q * 2 * sizeof(float)));
+  }
   CU(cudaStreamSynchronize(e->stream));
   return QIE_OK;
 }

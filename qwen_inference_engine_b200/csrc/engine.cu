@@ -53,6 +53,46 @@ static cudaError_t gemm_rows(qie_engine* e, int kind, GemmArgs g, int n_rows, si
   return cudaSuccess;
 }
 
+// tcgen05 GEMM launch (fast numerics, rows > 8). x: [n, K] activations.
+static cudaError_t gemm_tc(qie_engine* e, int kind, const bf16* x, int n, int K, int nseg, const TensorMap2D* const* w,
+                           const int* rows, int epi, bf16* out, int ld_out) {
+  TensorMap2D xmap;
+  cudaError_t r = make_tensor_map_2d(&xmap, x, n, K, tc_token_tile(n));
+  if (r != cudaSuccess) return r;
+  TcGemm t{};
+  int cols = 0;
+  for (int i = 0; i < nseg; ++i) {
+    t.w[i] = w[i];
+    t.rows[i] = rows[i];
+    cols += rows[i];
+  }
+  t.x = &xmap;
+  t.nseg = nseg;
+  t.M = n;
+  t.K = K;
+  t.epi = epi;
+  t.out = out;
+  t.ld_out = ld_out;
+  t.ws = e->gemm_ws;
+  t.ws_bytes = e->gemm_ws_bytes;
+  t.max_splits = (int)std::max<size_t>(1, e->gemm_ws_bytes / ((size_t)n * cols * sizeof(float)));
+  int nl = 0;
+  qie_engine::ProfRec pr{kind, nullptr, nullptr};
+  if (e->prof_on) {
+    cudaEventCreate(&pr.a);
+    cudaEventCreate(&pr.b);
+    cudaEventRecord(pr.a, e->stream);
+  }
+  r = launch_gemm_tcgen05(t, e->num_sms, e->stream, &nl);
+  if (r != cudaSuccess) return r;
+  if (e->prof_on) {
+    cudaEventRecord(pr.b, e->stream);
+    e->prof.push_back(pr);
+  }
+  e->launches += nl;
+  return cudaSuccess;
+}
+
 // Launch order = llm()'s (qwen_main.cu:77-222 prefill / :271-365 decode): per layer
 // rms -> q,k,v -> q/k-norm -> RoPE -> KV store -> attention -> o (+residual) -> rms ->
 // up,gate -> SiLU*up -> down (+residual); then final norm -> lm_head -> sampling.
@@ -62,13 +102,24 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
   const qie_config& c = e->cfg;
   const int H = c.hidden, hd = c.head_dim, Dq = c.n_q * hd, Dkv = c.n_kv * hd, I = c.inter;
   cudaStream_t st = e->stream;
+  const bool fast = e->opts.numerics == QIE_NUMERICS_FAST;
+  const bool tc = fast && n > 8;                  // tcgen05 GEMMs
+  const bool fast_attn = fast && advance;         // decode rows: one token per sequence
+  auto rms = [&](const bf16* x, const bf16* w, bf16* y, int rows) {
+    return fast ? launch_rmsnorm_fast(x, w, y, H, rows, H, st) : launch_rmsnorm_ref(x, w, y, H, rows, H, st);
+  };
 
   QIE_TRY(KK_EMBED, launch_embedding(e->x, e->embed, e->ids_d, H, n, st));
   for (int l = 0; l < c.layers; ++l) {
     const LayerWeights& w = e->L[l];
-    QIE_TRY(KK_RMSNORM, launch_rmsnorm_ref(e->x, w.in_ln, e->xn, H, n, H, st));
+    QIE_TRY(KK_RMSNORM, rms(e->x, w.in_ln, e->xn, n));
     capture_copy(e, "input_norm", l, e->xn, (size_t)n * H);
-    {
+    if (tc) {
+      const TensorMap2D* wm[3] = {&e->wmaps[l].q, &e->wmaps[l].k, &e->wmaps[l].v};
+      const int rows[3] = {Dq, Dkv, Dkv};
+      cudaError_t r = gemm_tc(e, KK_GEMM_QKV, e->xn, n, H, 3, wm, rows, EPI_STORE, e->qkv, Dq + 2 * Dkv);
+      if (r != cudaSuccess) return r;
+    } else {
       GemmArgs g{};
       g.A = e->xn;
       g.lda = H;
@@ -84,8 +135,18 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
     {
       QkvPostArgs a{};
       a.q = e->q;
-      a.k = e->k;
-      a.v = e->v;
+      if (tc) {
+        a.q_in = e->qkv;
+        a.k = e->qkv + Dq;
+        a.v = e->qkv + Dq + Dkv;
+        a.q_in_stride = a.kv_stride = Dq + 2 * Dkv;
+      } else {
+        a.q_in = e->q;
+        a.k = e->k;
+        a.v = e->v;
+        a.q_in_stride = Dq;
+        a.kv_stride = Dkv;
+      }
       a.q_norm_w = w.q_norm;
       a.k_norm_w = w.k_norm;
       a.cos_t = e->cos_d;
@@ -101,8 +162,29 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
       QIE_TRY(KK_QKV_POST, launch_qkv_post(a, st));
     }
     capture_copy(e, "q", l, e->q, (size_t)n * Dq);
-    capture_copy(e, "v", l, e->v, (size_t)n * Dkv);
-    {
+    if (!tc) capture_copy(e, "v", l, e->v, (size_t)n * Dkv);
+    if (fast_attn) {
+      FastAttnArgs a{};
+      a.q = e->q;
+      a.out = e->att;
+      a.pos = e->pos_d;
+      a.slot = e->slot_d;
+      a.block_table = e->block_table_d;
+      a.max_pages = e->max_pages_per_seq;
+      a.n_tok = n;
+      a.n_q = c.n_q;
+      a.layer = l;
+      const int tiles = (max_kv_len + 63) / 64;
+      int ns = (4 * e->num_sms) / std::max(1, n * c.n_kv);
+      ns = std::max(1, std::min(ns, std::min(e->attn_max_splits, tiles)));
+      a.n_splits = ns;
+      a.scale_log2 = 1.4426950408889634f / sqrtf((float)hd);
+      a.ws_o = e->attn_ws_o;
+      a.ws_ml = e->attn_ws_ml;
+      a.kv = e->kv;
+      QIE_TRY(KK_ATTN, launch_attention_decode_fast(a, st));
+      if (ns > 1) ++e->launches;  // + combine kernel
+    } else {
       AttnArgs a{};
       a.q = e->q;
       a.out = e->att;
@@ -118,7 +200,12 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
       QIE_TRY(KK_ATTN, launch_attention_ref(a, st));
     }
     capture_copy(e, "attn", l, e->att, (size_t)n * Dq);
-    {
+    if (tc) {
+      const TensorMap2D* wm[1] = {&e->wmaps[l].o};
+      const int rows[1] = {H};
+      cudaError_t r = gemm_tc(e, KK_GEMM_O, e->att, n, Dq, 1, wm, rows, EPI_RESIDUAL, e->x, H);
+      if (r != cudaSuccess) return r;
+    } else {
       GemmArgs g{};
       g.A = e->att;
       g.lda = Dq;
@@ -130,8 +217,13 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
       if (r != cudaSuccess) return r;
     }
     capture_copy(e, "x_attn", l, e->x, (size_t)n * H);
-    QIE_TRY(KK_RMSNORM, launch_rmsnorm_ref(e->x, w.post_ln, e->xn, H, n, H, st));
-    {
+    QIE_TRY(KK_RMSNORM, rms(e->x, w.post_ln, e->xn, n));
+    if (tc) {
+      const TensorMap2D* wm[2] = {&e->wmaps[l].gate, &e->wmaps[l].up};
+      const int rows[2] = {I, I};
+      cudaError_t r = gemm_tc(e, KK_GEMM_GATEUP, e->xn, n, H, 2, wm, rows, EPI_SILU_MUL, e->h, I);
+      if (r != cudaSuccess) return r;
+    } else {
       GemmArgs g{};
       g.A = e->xn;
       g.lda = H;
@@ -143,7 +235,12 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
       if (r != cudaSuccess) return r;
     }
     capture_copy(e, "mlp_h", l, e->h, (size_t)n * I);
-    {
+    if (tc) {
+      const TensorMap2D* wm[1] = {&e->wmaps[l].down};
+      const int rows[1] = {H};
+      cudaError_t r = gemm_tc(e, KK_GEMM_DOWN, e->h, n, I, 1, wm, rows, EPI_RESIDUAL, e->x, H);
+      if (r != cudaSuccess) return r;
+    } else {
       GemmArgs g{};
       g.A = e->h;
       g.lda = I;
@@ -158,8 +255,13 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
   }
   if (n_out == 0) return cudaSuccess;  // non-final prefill chunk: only the KV cache is needed
   // final norm only on the rows that feed lm_head (qwen_main.cu:227-236, :367-372)
-  QIE_TRY(KK_RMSNORM, launch_rmsnorm_ref(e->x + (size_t)out_row0 * H, e->final_norm, e->xn, H, n_out, H, st));
-  {
+  QIE_TRY(KK_RMSNORM, rms(e->x + (size_t)out_row0 * H, e->final_norm, e->xn, n_out));
+  if (fast && n_out > 8) {
+    const TensorMap2D* wm[1] = {&e->lm_head_map};
+    const int rows[1] = {c.vocab};
+    cudaError_t r = gemm_tc(e, KK_LM_HEAD, e->xn, n_out, H, 1, wm, rows, EPI_STORE, e->logits, c.vocab);
+    if (r != cudaSuccess) return r;
+  } else {
     GemmArgs g{};
     g.A = e->xn;
     g.lda = H;

@@ -67,6 +67,18 @@ struct qie_engine {
             *logits = nullptr;
   int logits_rows = 0;
 
+  // fast numerics (opts.numerics == QIE_NUMERICS_FAST)
+  struct LayerMaps {
+    qie::TensorMap2D q, k, v, o, gate, up, down;
+  };
+  std::vector<LayerMaps> wmaps;  // TMA descriptors of the weight matrices (box 128 x 64)
+  qie::TensorMap2D lm_head_map;
+  qie::bf16* qkv = nullptr;      // fused [rows, Dq + 2*Dkv] projection output
+  float* gemm_ws = nullptr;      // split-K partials
+  size_t gemm_ws_bytes = 0;
+  float *attn_ws_o = nullptr, *attn_ws_ml = nullptr;
+  int attn_max_splits = 16;
+
   // sampling
   int topk = 1;
   float temp_prefill = 1.0f, temp_decode = 0.7f;

@@ -63,9 +63,11 @@ cudaError_t launch_residual_add(bf16* a, const bf16* b, size_t n, cudaStream_t s
 //   q (in place) and k: per-head RMS norm (if the norm weights are non-null), RoPE at
 //   pos[t]; k (post-RoPE) and v (raw) are written to the KV pool.
 struct QkvPostArgs {
-  bf16* q;        // [n_tok, n_q*hd]   in place
-  const bf16* k;  // [n_tok, n_kv*hd]
-  const bf16* v;  // [n_tok, n_kv*hd]
+  bf16* q;          // [n_tok, n_q*hd]  output (contiguous)
+  const bf16* q_in; // projection output rows (may alias q), row stride q_in_stride
+  const bf16* k;    // row stride kv_stride
+  const bf16* v;    // row stride kv_stride
+  int q_in_stride, kv_stride;
   const bf16* q_norm_w;
   const bf16* k_norm_w;
   const float* cos_t;
@@ -93,6 +95,43 @@ struct AttnArgs {
   KvGeom kv;
 };
 cudaError_t launch_attention_ref(const AttnArgs& a, cudaStream_t st);
+
+// split-KV flash-decoding (fast numerics): one query token per row, row b = sequence slot[b]
+struct FastAttnArgs {
+  const bf16* q;  // [n_tok, n_q*hd]
+  bf16* out;      // [n_tok, n_q*hd]
+  const int* pos;
+  const int* slot;
+  const int* block_table;
+  int max_pages, n_tok, n_q, layer, n_splits;
+  float scale_log2;  // log2(e) / sqrt(hd)
+  float* ws_o;       // [n_splits][n_tok][n_q][hd]
+  float* ws_ml;      // [n_splits][n_tok][n_q][2]
+  KvGeom kv;
+};
+cudaError_t launch_attention_decode_fast(const FastAttnArgs& a, cudaStream_t st);
+
+// tcgen05 GEMM (fast numerics, M > 8)
+struct TensorMap2D {
+  alignas(64) unsigned char opaque[128];  // CUtensorMap
+};
+cudaError_t make_tensor_map_2d(TensorMap2D* out, const bf16* base, int rows, int K, int box_rows);
+int tc_token_tile(int M);
+struct TcGemm {
+  const TensorMap2D* w[3];  // weight maps, box rows = 128
+  const TensorMap2D* x;     // activation map [M, K], box rows = tc_token_tile(M)
+  int rows[3];
+  int nseg, M, K, epi;
+  bf16* out;     // [M, ld_out]; EPI_SILU_MUL: segments are (gate, up), out has rows[0] columns
+  int ld_out;
+  float* ws;
+  size_t ws_bytes;
+  int max_splits;
+};
+cudaError_t launch_gemm_tcgen05(const TcGemm& t, int num_sms, cudaStream_t st, int* launches);
+
+cudaError_t launch_rmsnorm_fast(const bf16* x, const bf16* w, bf16* y, size_t hidden, size_t n_tok, size_t x_stride,
+                                cudaStream_t st);
 
 // sampling (reference tie-break + XORWOW)
 cudaError_t launch_sample_topk(const bf16* logits, int* out_tokens, int n_rows, size_t vocab, float temperature,

@@ -83,6 +83,40 @@ cudaError_t launch_rmsnorm_ref(const bf16* x, const bf16* w, bf16* y, size_t hid
   return cudaGetLastError();
 }
 
+// fast-numerics variant: the sum of squares is reduced in parallel (warp shuffles), so it
+// differs from the reference's sequential chain in the last fp32 bits.
+__global__ void __launch_bounds__(256) rmsnorm_fast_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                            bf16* __restrict__ y, int hidden, size_t x_stride) {
+  __shared__ float s_part[8];
+  const bf16* xr = x + (size_t)blockIdx.x * x_stride;
+  bf16* yr = y + (size_t)blockIdx.x * hidden;
+  float sum = 0.f;
+  for (int i = threadIdx.x * 2; i < hidden; i += 512) {
+    uint32_t v = *reinterpret_cast<const uint32_t*>(xr + i);
+    float a = lo2f(v), b = hi2f(v);
+    sum += a * a + b * b;
+  }
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += s_part[i];
+  const float rms = __fsqrt_rn(__fadd_rn(__fdiv_rn(tot, (float)hidden), 1e-04f));
+  for (int i = threadIdx.x * 2; i < hidden; i += 512) {
+    uint32_t v = *reinterpret_cast<const uint32_t*>(xr + i), wv = *reinterpret_cast<const uint32_t*>(w + i);
+    *reinterpret_cast<uint32_t*>(yr + i) = pack2(f2bf(__fmul_rn(__fdiv_rn(lo2f(v), rms), lo2f(wv))),
+                                                 f2bf(__fmul_rn(__fdiv_rn(hi2f(v), rms), hi2f(wv))));
+  }
+}
+cudaError_t launch_rmsnorm_fast(const bf16* x, const bf16* w, bf16* y, size_t hidden, size_t n_tok, size_t x_stride,
+                                cudaStream_t st) {
+  if (n_tok == 0) return cudaSuccess;
+  if (hidden & 1) return cudaErrorInvalidValue;
+  rmsnorm_fast_kernel<<<(unsigned)n_tok, 256, 0, st>>>(x, w, y, (int)hidden, x_stride);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ per-head tree sum
 // Lane l holds, for p in [0,NP): elements t = 64p + 2l and 64p + 2l + 1 of a head of
 // hd = 64*NP values.  Reproduces  for (stride = hd/2; stride > 0; stride >>= 1)
@@ -225,7 +259,7 @@ __global__ void qkv_post_kernel(QkvPostArgs a) {
   float v[NP][2];
   if (h < a.n_q) {
     bf16* p = a.q + (size_t)tok * a.n_q * hd + (size_t)h * hd;
-    head_load<NP>(v, p, lane);
+    head_load<NP>(v, a.q_in + (size_t)tok * a.q_in_stride + (size_t)h * hd, lane);
     if (a.q_norm_w) head_norm<NP>(v, a.q_norm_w, lane);
     head_rope<NP>(v, a.cos_t + (size_t)ps * 32 * NP, a.sin_t + (size_t)ps * 32 * NP, lane);
     head_store<NP>(v, p, lane);
@@ -235,13 +269,13 @@ __global__ void qkv_post_kernel(QkvPostArgs a) {
   int off = ps % a.kv.page_size;
   if (h < a.n_q + a.kv.n_kv) {
     int kh = h - a.n_q;
-    head_load<NP>(v, a.k + (size_t)tok * a.kv.n_kv * hd + (size_t)kh * hd, lane);
+    head_load<NP>(v, a.k + (size_t)tok * a.kv_stride + (size_t)kh * hd, lane);
     if (a.k_norm_w) head_norm<NP>(v, a.k_norm_w, lane);
     head_rope<NP>(v, a.cos_t + (size_t)ps * 32 * NP, a.sin_t + (size_t)ps * 32 * NP, lane);
     head_store<NP>(v, a.kv.chunk(page, a.layer, 0, kh) + (size_t)off * hd, lane);
   } else {
     int vh = h - a.n_q - a.kv.n_kv;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.v + (size_t)tok * a.kv.n_kv * hd + (size_t)vh * hd);
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.v + (size_t)tok * a.kv_stride + (size_t)vh * hd);
     uint32_t* dst = reinterpret_cast<uint32_t*>(a.kv.chunk(page, a.layer, 1, vh) + (size_t)off * hd);
 #pragma unroll
     for (int p = 0; p < NP; ++p) dst[32 * p + lane] = src[32 * p + lane];

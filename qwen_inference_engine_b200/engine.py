@@ -57,13 +57,15 @@ def _i32(a):
 class Engine:
     def __init__(self, meta_path=None, weights_path=None, *, synthetic=None, seed=1234, device=0,
                  page_size=16, kv_bytes=0, max_pages=0, max_seqs=64, max_batch_tokens=256,
-                 context=REF_CONTEXT, use_graph=True, head_dim_hint=0):
+                 context=REF_CONTEXT, use_graph=True, head_dim_hint=0, numerics="reference_order"):
         L = _lib.lib()
         o = EngineOpts()
         L.qie_engine_opts_default(C.byref(o))
         o.device, o.page_size, o.kv_bytes, o.max_pages = device, page_size, kv_bytes, max_pages
         o.max_seqs, o.max_batch_tokens, o.context = max_seqs, max_batch_tokens, context
         o.use_graph, o.head_dim_hint = int(use_graph), head_dim_hint
+        o.numerics = {"reference_order": 0, "fast": 1}[numerics]
+        self.numerics = numerics
         h = C.c_void_p()
         if synthetic is not None:
             cfg = synthetic if isinstance(synthetic, Config) else make_config(synthetic, context=context)

@@ -105,3 +105,16 @@ def sample_topk_bf16(logits_d, vocab, temperature, topk, seed, step=0):
     check(_lib.lib().qie_sample_topk(_p(logits_d), _p(out), rows, vocab, float(temperature), topk, seed + step, 0,
                                      _st()))
     return out.cpu().numpy()
+
+
+# ---- fast-numerics operators (tolerance parity, see include/qie_b200.h) ---------------------
+def launch_matmul_fast(A, B, Cout, M, N, K):
+    """tcgen05/TMEM/TMA GEMM: same contract as launch_matmul, results within 1e-2 (bf16)."""
+    check(_lib.lib().qie_matmul_fast(_p(A), _p(B), _p(Cout), M, N, K, _st()))
+
+
+def launch_attn_decode_fast(Q, out, pool, layer, pos, slot, n_q_heads, n_splits=0):
+    """split-KV flash-decoding: one query token per row."""
+    check(_lib.lib().qie_attention_decode_fast(C.byref(pool.view), layer, _p(Q), _p(out), _p(pos), _p(slot),
+                                               _p(pool.block_table), pool.max_pages, pos.numel(), n_q_heads,
+                                               n_splits, _st()))
