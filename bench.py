@@ -191,6 +191,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--ctx", type=int, default=CTX)
+    ap.add_argument("--numerics", default="fast", choices=["fast", "reference_order"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the batch-1 (configs[0]) side measurement")
     args = ap.parse_args()
@@ -220,7 +221,7 @@ def main():
     total_steps = 2 * (args.warmup + args.steps) + 8
     kv_need = B * (ctx + total_steps + 64) * kvpp + (64 << 20)
     eng = q.Engine(synthetic=ARCH, seed=1234, device=local, kv_bytes=kv_need, max_seqs=B + 1, max_batch_tokens=max(B, 64),
-                   page_size=16)
+                   page_size=16, numerics=args.numerics)
     seqs = []
     for i in range(B):
         s = eng.new_sequence()
@@ -329,7 +330,9 @@ def main():
                     "random K/V (no real prefill); token ids fed back from the sampler",
             "config": {"workload": f"{ARCH} decode, batch {B} per GPU, ctx {ctx} at the first timed step (+1 per step)",
                        "parallelism": f"dp{world}", "page_size": 16, "sampling": "greedy (top-k 1, reference tie-break)",
-                       "numerics": "reference-order kernels (bit-identical to the reference's kernels per sequence)",
+                       "numerics": ("fast: tcgen05 GEMM + split-K, flash-decoding, parallel RMSNorm (1e-2 bf16 tolerance vs the reference)"
+                                    if args.numerics == "fast" else
+                                    "reference-order kernels (bit-identical to the reference's kernels per sequence)"),
                        "l2": f"working set per step {step_bytes / 1e9:.2f} GB >> 126 MB L2 (inputs larger than L2, no flush)"},
             "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": int(4 * B), "d2h_bytes_per_step": int(4 * B),
                     "ms_per_step": ms_e2e / args.steps,

@@ -33,6 +33,12 @@ def rel_err(a_u16, b_u16):
     return float(np.max(np.abs(a - b)) / (np.max(np.abs(b)) + 1e-30))
 
 
+def rel_l2(a_u16, b_u16):
+    """||a-b||_2 / ||b||_2 over bf16 arrays: the tensor-level 'relative error in bf16'."""
+    a, b = bf16_to_f32(a_u16).astype(np.float64), bf16_to_f32(b_u16).astype(np.float64)
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-30))
+
+
 def ulp_diff(a_u16, b_u16):
     """max distance in bf16 ulps (monotone integer mapping of the bit patterns)."""
     def key(u):
