@@ -21,6 +21,7 @@
 //   splits: partial (max, sum, unnormalised O) per split -> attn_combine_kernel
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.h"
 
 namespace qie {
 
@@ -43,6 +44,8 @@ __device__ __forceinline__ uint32_t swz(int r, int ch) {
 
 template <int HD>
 __global__ void __launch_bounds__(128) attn_decode_fast_kernel(FastAttnArgs a) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(128) unsigned char smem[];
   using SM = FastAttnSmem<HD>;
   constexpr int CH = HD / 8;   // 16-byte chunks per row
@@ -239,6 +242,8 @@ __global__ void __launch_bounds__(128) attn_decode_fast_kernel(FastAttnArgs a) {
 
 // out[b,h,:] = sum_s O_s 2^(m_s-M) / sum_s l_s 2^(m_s-M)
 __global__ void attn_combine_kernel(FastAttnArgs a, int hd) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y, h = blockIdx.x, d = threadIdx.x;
   float M = -INFINITY;
   for (int s = 0; s < a.n_splits; ++s) M = fmaxf(M, a.ws_ml[(((size_t)s * a.n_tok + b) * a.n_q + h) * 2]);
@@ -264,11 +269,11 @@ static cudaError_t launch_hd(const FastAttnArgs& a, cudaStream_t st) {
     set = true;
   }
   dim3 grid(a.n_splits, a.kv.n_kv, a.n_tok);
-  attn_decode_fast_kernel<HD><<<grid, 128, smem, st>>>(a);
+  (void)launch_k(attn_decode_fast_kernel<HD>, dim3(grid), dim3(128), smem, st, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (a.n_splits > 1) {
-    attn_combine_kernel<<<dim3(a.n_q, a.n_tok), HD, 0, st>>>(a, HD);
+    (void)launch_k(attn_combine_kernel, dim3(dim3(a.n_q, a.n_tok)), dim3(HD), 0, st, a, HD);
     e = cudaGetLastError();
   }
   return e;

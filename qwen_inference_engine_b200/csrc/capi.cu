@@ -158,6 +158,11 @@ int qie_matmul_fast(const qie_bf16* A, const qie_bf16* B, qie_bf16* C, int M, in
   if (M < 1 || N < 64 || (N % 8) || K < 1) return fail(QIE_EINVAL, "matmul_fast: need M>=1, N>=64, N%%8==0");
   static thread_local void* ws = nullptr;
   static thread_local size_t ws_cap = 0;
+  static thread_local int* counters = nullptr;
+  if (!counters) {
+    CU(cudaMalloc(&counters, 8192 * sizeof(int)));
+    CU(cudaMemset(counters, 0, 8192 * sizeof(int)));
+  }
   int dev = 0, sms = 0;
   CU(cudaGetDevice(&dev));
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -179,6 +184,9 @@ int qie_matmul_fast(const qie_bf16* A, const qie_bf16* B, qie_bf16* C, int M, in
   t.ws = (float*)ws;
   t.ws_bytes = ws_cap;
   t.max_splits = (int)std::max<size_t>(1, ws_cap / ((size_t)M * K * sizeof(float)));
+  t.counters = counters;
+  t.n_counters = 8192;
+  t.w_static = 0;  // B may have been written by the caller's previous kernel
   CU(launch_gemm_tcgen05(t, sms, (cudaStream_t)st, nullptr));
   return QIE_OK;
 }
@@ -269,7 +277,7 @@ static void engine_free(qie_engine* e) {
     if (kvp.second.d) cudaFree(kvp.second.d);
   void* dev[] = {e->blob, e->cos_d, e->sin_d, e->kv.pool, e->block_table_d, e->ids_d, e->pos_d, e->slot_d,
                  e->sampled_d, e->rowstep_d, e->x, e->xn, e->q, e->k, e->v, e->att, e->h, e->logits, e->qkv,
-                 e->gemm_ws, e->attn_ws_o, e->attn_ws_ml};
+                 e->gemm_ws, e->attn_ws_o, e->attn_ws_ml, e->gemm_counters};
   for (void* p : dev)
     if (p) cudaFree(p);
   if (e->block_table_h) cudaFreeHost(e->block_table_h);
@@ -384,6 +392,8 @@ static int engine_finish_setup(qie_engine* e) {
     CU(cudaMalloc(&e->qkv, R * (Dq + 2 * Dkv) * sizeof(bf16)));
     e->gemm_ws_bytes = std::max<size_t>((size_t)64 << 20, R * 2 * I * sizeof(float) * 2);
     CU(cudaMalloc(&e->gemm_ws, e->gemm_ws_bytes));
+    CU(cudaMalloc(&e->gemm_counters, 8192 * sizeof(int)));
+    CU(cudaMemsetAsync(e->gemm_counters, 0, 8192 * sizeof(int), e->stream));
     CU(cudaMalloc(&e->attn_ws_o, (size_t)e->attn_max_splits * R * Dq * sizeof(float)));
     CU(cudaMalloc(&e->attn_ws_ml, (size_t)e->attn_max_splits * R * c.n_q * 2 * sizeof(float)));
   }

@@ -1,6 +1,8 @@
 // engine.cu -- forward launch order + engine lifecycle. See engine.h.
 #include "engine.h"
 
+#include "launch.h"
+
 #include <math.h>
 
 #include <algorithm>
@@ -8,6 +10,11 @@
 #include <cstring>
 
 namespace qie {
+
+bool g_use_pdl = [] {
+  const char* v = getenv("QIE_PDL");
+  return !(v && v[0] == '0');
+}();
 
 // launch + count + (optionally) bracket with events for the per-kernel-class timing
 #define QIE_TRY(kind, expr)                                    \
@@ -76,6 +83,9 @@ static cudaError_t gemm_tc(qie_engine* e, int kind, const bf16* x, int n, int K,
   t.ws = e->gemm_ws;
   t.ws_bytes = e->gemm_ws_bytes;
   t.max_splits = (int)std::max<size_t>(1, e->gemm_ws_bytes / ((size_t)n * cols * sizeof(float)));
+  t.counters = e->gemm_counters;
+  t.n_counters = 8192;
+  t.w_static = 1;
   int nl = 0;
   qie_engine::ProfRec pr{kind, nullptr, nullptr};
   if (e->prof_on) {

@@ -74,6 +74,7 @@ struct qie_engine {
   std::vector<LayerMaps> wmaps;  // TMA descriptors of the weight matrices (box 128 x 64)
   qie::TensorMap2D lm_head_map;
   qie::bf16* qkv = nullptr;      // fused [rows, Dq + 2*Dkv] projection output
+  int* gemm_counters = nullptr;  // fused split-K reduction tickets (self-resetting)
   float* gemm_ws = nullptr;      // split-K partials
   size_t gemm_ws_bytes = 0;
   float *attn_ws_o = nullptr, *attn_ws_ml = nullptr;

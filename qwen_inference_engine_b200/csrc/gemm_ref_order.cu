@@ -17,6 +17,7 @@
 // The rounding points are the reference's (SURVEY.md 8a list R3, R8, R9).
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.h"
 
 namespace qie {
 
@@ -53,6 +54,8 @@ __device__ __forceinline__ float silu_ref(float x) {
 // zeros), so no zero rows have to exist in shared memory.
 template <int MT>
 __global__ void __launch_bounds__(256) gemm_ref_order_kernel(GemmArgs g) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ __align__(128) unsigned char smem[];
   const int nw = blockDim.x >> 5;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -221,7 +224,7 @@ static cudaError_t launch_mt(const GemmArgs& g, int nw, size_t smem, cudaStream_
     attr_set = true;
   }
   int grid = (g.total_units + nw - 1) / nw;
-  gemm_ref_order_kernel<MT><<<grid, nw * 32, smem, st>>>(g);
+  (void)launch_k(gemm_ref_order_kernel<MT>, dim3(grid), dim3(nw * 32), smem, st, g);
   return cudaGetLastError();
 }
 

@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.h"
 
 namespace qie {
 
@@ -109,6 +110,11 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+__device__ __forceinline__ float silu_ref_f(float x) {
+  float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
+  return __fmul_rn(x, sg);
+}
+
 struct TcSeg {
   int rows;      // weight rows of this segment
   int col0;      // first output column of this segment in the [*, ld] output / workspace
@@ -121,7 +127,11 @@ struct TcArgs {
   TcSeg seg[3];
   float* ws;           // [splits][M][ld] fp32 partials (splits > 1 or epilogue needs finalize)
   bf16* direct_out;    // splits == 1 && plain store: bf16 [M][ld]
-  int tok0;            // first token of this token tile (prefill: grid.z tiles over tokens)
+  // fused split-K reduction: the LAST CTA to finish a tile group sums the partials in split
+  // order and applies the epilogue (no separate finalize launch)
+  int* counters;       // [token_tiles * groups], zero-initialised once, self-resetting (atomicInc wraps)
+  int fuse, groups, expected, epi, n_out, ld_out, w_static;
+  bf16* out;
 };
 
 template <int BN>
@@ -129,6 +139,7 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
                                                             const __grid_constant__ CUtensorMap map_w1,
                                                             const __grid_constant__ CUtensorMap map_w2,
                                                             const __grid_constant__ CUtensorMap map_x, TcArgs g) {
+  pdl_trigger();  // let the next kernel's CTAs get scheduled; they wait in their own pdl_wait()
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr int A_BYTES = BM * BK * 2;  // 16 KiB
   constexpr int B_BYTES = BN * BK * 2;
@@ -173,7 +184,17 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
+      // Weights never depend on the previous kernel: start streaming them BEFORE waiting for
+      // it (programmatic dependent launch), so HBM stays busy across the kernel boundary.
+      const int pre = g.w_static ? min(nkb, TC_STAGES) : 0;
+      for (int i = 0; i < pre; ++i) {
+        mbar_expect_tx(full_bar(i), STAGE_BYTES);
+        tma_load_2d(smem0 + i * STAGE_BYTES, map_w, full_bar(i), (kb0 + i) * BK, row0);
+      }
+      pdl_wait();  // activations are produced by the previous kernel
+      for (int i = 0; i < pre; ++i)
+        tma_load_2d(smem0 + i * STAGE_BYTES + A_BYTES, &map_x, full_bar(i), (kb0 + i) * BK, tok_base);
+      for (int i = pre; i < nkb; ++i) {
         const int s = i % TC_STAGES;
         const uint32_t ph = (i / TC_STAGES) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
@@ -203,6 +224,7 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
     }
   } else {
     // epilogue warps 2..5 -> TMEM lane quarter (warp % 4)
+    pdl_wait();  // ws / out may still be read by the previous kernel
     const int qd = warp & 3;
     const int w_row = row0 + qd * 32 + lane;  // weight row inside the segment
     const bool row_ok = w_row < g.seg[si].rows;
@@ -233,6 +255,46 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
         }
       }
     }
+    if (g.fuse) {
+      // ---- fused split-K reduction + epilogue by the last CTA of this tile group
+      __shared__ int s_last;
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int dual = g.epi == EPI_SILU_MUL;
+      const int grp = ttile * g.groups + (dual ? tile % g.groups : tile);
+      if (threadIdx.x == 64) {
+        const unsigned old = atomicInc(reinterpret_cast<unsigned*>(g.counters) + grp, (unsigned)g.expected - 1u);
+        s_last = old == (unsigned)g.expected - 1u;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (s_last) {
+        __threadfence();
+        // output column handled by this thread (dual: gate column c, up column n_out + c)
+        const int seg_row = row0 + qd * 32 + lane;
+        const int c = dual ? seg_row : col;
+        const bool ok = seg_row < g.seg[si].rows;
+        const int t_end = min(g.M, tok_base + BN);
+        if (ok) {
+          for (int tok = tok_base; tok < t_end; ++tok) {
+            float acc = 0.f, acc2 = 0.f;
+            for (int sp = 0; sp < g.splits; ++sp) {
+              const float* pw = g.ws + ((size_t)sp * g.M + tok) * g.ld;
+              acc += __ldcg(pw + c);
+              if (dual) acc2 += __ldcg(pw + g.n_out + c);
+            }
+            bf16* dst = g.out + (size_t)tok * g.ld_out + c;
+            if (g.epi == EPI_STORE) {
+              *dst = f2bf(acc);
+            } else if (g.epi == EPI_RESIDUAL) {
+              *dst = f2bf(__fadd_rn(bf2f(*dst), bf2f(f2bf(acc))));
+            } else {
+              const float gt = bf2f(f2bf(acc)), up = bf2f(f2bf(acc2));
+              *dst = f2bf(__fmul_rn(up, bf2f(f2bf(silu_ref_f(gt)))));
+            }
+          }
+        }
+      }
+    }
     tc_fence_before();
   }
   __syncthreads();
@@ -243,13 +305,11 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
 }
 
 // ------------------------------------------------------------------ split-K sum + epilogue
-__device__ __forceinline__ float silu_ref_f(float x) {
-  float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
-  return __fmul_rn(x, sg);
-}
 // ws: [splits][M][ld]; EPI_SILU_MUL: columns [0,n) = gate, [n,2n) = up, out has n columns
 __global__ void gemm_finalize_kernel(const float* __restrict__ ws, bf16* __restrict__ out, int M, int ld, int n_out,
                                      int ld_out, int splits, int epi) {
+  pdl_wait();
+  pdl_trigger();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)M * n_out) return;
   const int tok = (int)(i / n_out), c = (int)(i % n_out);
@@ -315,7 +375,7 @@ static cudaError_t launch_bn(const TcGemm& t, const TcArgs& g, int token_tiles, 
   const CUtensorMap* w0 = reinterpret_cast<const CUtensorMap*>(t.w[0]);
   const CUtensorMap* w1 = reinterpret_cast<const CUtensorMap*>(t.w[t.nseg > 1 ? 1 : 0]);
   const CUtensorMap* w2 = reinterpret_cast<const CUtensorMap*>(t.w[t.nseg > 2 ? 2 : 0]);
-  gemm_tcgen05_kernel<BN><<<grid, 192, smem, st>>>(*w0, *w1, *w2, *reinterpret_cast<const CUtensorMap*>(t.x), g);
+  (void)launch_k(gemm_tcgen05_kernel<BN>, dim3(grid), dim3(192), smem, st, *w0, *w1, *w2, *reinterpret_cast<const CUtensorMap*>(t.x), g);
   return cudaGetLastError();
 }
 
@@ -346,6 +406,7 @@ cudaError_t launch_gemm_tcgen05(const TcGemm& t, int num_sms, cudaStream_t st, i
     splits = (num_sms + tiles * token_tiles - 1) / (tiles * token_tiles);
     splits = std::min(splits, std::max(1, g.kb_total / 2));
     splits = std::min(splits, t.max_splits);
+    splits = std::min(splits, 8);  // the last CTA of a tile sums the partials: keep that tail short
   }
   g.kb_per_split = (g.kb_total + splits - 1) / splits;
   splits = (g.kb_total + g.kb_per_split - 1) / g.kb_per_split;
@@ -353,6 +414,20 @@ cudaError_t launch_gemm_tcgen05(const TcGemm& t, int num_sms, cudaStream_t st, i
   const bool direct = splits == 1 && t.epi == EPI_STORE;
   g.direct_out = direct ? t.out : nullptr;
   g.ws = t.ws;
+  const bool dual = t.epi == EPI_SILU_MUL;
+  const int n_out_cols = dual ? cols / 2 : cols;
+  // fused finalize needs whole tiles per group (dual: gate tile i pairs with up tile i)
+  const bool can_fuse = !direct && t.counters && (!dual || (t.nseg == 2 && t.rows[0] == t.rows[1] && t.rows[0] % BM == 0));
+  g.fuse = can_fuse ? 1 : 0;
+  g.groups = dual ? tiles / 2 : tiles;
+  g.expected = dual ? 2 * splits : splits;
+  g.counters = t.counters;
+  g.epi = t.epi;
+  g.n_out = n_out_cols;
+  g.ld_out = t.ld_out;
+  g.out = t.out;
+  g.w_static = t.w_static;
+  if (can_fuse && (size_t)g.groups * token_tiles > (size_t)t.n_counters) return cudaErrorInvalidValue;
   if (!direct && (size_t)splits * t.M * cols * sizeof(float) > t.ws_bytes) return cudaErrorMemoryAllocation;
   cudaError_t e;
   switch (BN) {
@@ -364,10 +439,10 @@ cudaError_t launch_gemm_tcgen05(const TcGemm& t, int num_sms, cudaStream_t st, i
   }
   if (e != cudaSuccess) return e;
   if (launches) *launches = 1;
-  if (!direct) {
+  if (!direct && !can_fuse) {
     const int n_out = t.epi == EPI_SILU_MUL ? cols / 2 : cols;
     const size_t n = (size_t)t.M * n_out;
-    gemm_finalize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(t.ws, t.out, t.M, cols, n_out, t.ld_out, splits,
+    (void)launch_k(gemm_finalize_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, t.ws, t.out, t.M, cols, n_out, t.ld_out, splits,
                                                                       t.epi);
     e = cudaGetLastError();
     if (launches) *launches = 2;

@@ -127,6 +127,9 @@ struct TcGemm {
   float* ws;
   size_t ws_bytes;
   int max_splits;
+  int* counters;   // zero-initialised ints for the fused split-K reduction (nullptr: separate finalize kernel)
+  int n_counters;
+  int w_static;    // weights are not produced by a preceding kernel: prefetch them before the PDL wait
 };
 cudaError_t launch_gemm_tcgen05(const TcGemm& t, int num_sms, cudaStream_t st, int* launches);
 

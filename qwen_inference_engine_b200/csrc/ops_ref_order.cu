@@ -14,12 +14,15 @@
 
 #include "common.cuh"
 #include "kernels.h"
+#include "launch.h"
 
 namespace qie {
 
 // ------------------------------------------------------------------ embedding
 __global__ void embedding_kernel(bf16* __restrict__ out, const bf16* __restrict__ table,
                                  const int* __restrict__ ids, size_t hidden) {
+  pdl_wait();
+  pdl_trigger();
   const size_t t = blockIdx.x;
   const bf16* src = table + (size_t)ids[t] * hidden;
   bf16* dst = out + t * hidden;
@@ -35,7 +38,7 @@ __global__ void embedding_kernel(bf16* __restrict__ out, const bf16* __restrict_
 cudaError_t launch_embedding(bf16* out, const bf16* table, const int* ids, size_t hidden, size_t n_tok,
                              cudaStream_t st) {
   if (n_tok == 0) return cudaSuccess;
-  embedding_kernel<<<(unsigned)n_tok, 128, 0, st>>>(out, table, ids, hidden);
+  (void)launch_k(embedding_kernel, dim3((unsigned)n_tok), dim3(128), 0, st, out, table, ids, hidden);
   return cudaGetLastError();
 }
 
@@ -46,6 +49,8 @@ cudaError_t launch_embedding(bf16* out, const bf16* table, const int* ids, size_
 // (4-cycle dependent FFMA issue, loads hoisted), the block does the rest in parallel.
 __global__ void __launch_bounds__(128) rmsnorm_ref_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                            bf16* __restrict__ y, int hidden, size_t x_stride) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float xs[];
   __shared__ float s_rms;
   const bf16* xr = x + (size_t)blockIdx.x * x_stride;
@@ -79,7 +84,7 @@ __global__ void __launch_bounds__(128) rmsnorm_ref_kernel(const bf16* __restrict
 cudaError_t launch_rmsnorm_ref(const bf16* x, const bf16* w, bf16* y, size_t hidden, size_t n_tok, size_t x_stride,
                                cudaStream_t st) {
   if (n_tok == 0) return cudaSuccess;
-  rmsnorm_ref_kernel<<<(unsigned)n_tok, 128, hidden * sizeof(float), st>>>(x, w, y, (int)hidden, x_stride);
+  (void)launch_k(rmsnorm_ref_kernel, dim3((unsigned)n_tok), dim3(128), hidden * sizeof(float), st, x, w, y, (int)hidden, x_stride);
   return cudaGetLastError();
 }
 
@@ -87,6 +92,8 @@ cudaError_t launch_rmsnorm_ref(const bf16* x, const bf16* w, bf16* y, size_t hid
 // differs from the reference's sequential chain in the last fp32 bits.
 __global__ void __launch_bounds__(256) rmsnorm_fast_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                             bf16* __restrict__ y, int hidden, size_t x_stride) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_part[8];
   const bf16* xr = x + (size_t)blockIdx.x * x_stride;
   bf16* yr = y + (size_t)blockIdx.x * hidden;
@@ -113,7 +120,7 @@ cudaError_t launch_rmsnorm_fast(const bf16* x, const bf16* w, bf16* y, size_t hi
                                 cudaStream_t st) {
   if (n_tok == 0) return cudaSuccess;
   if (hidden & 1) return cudaErrorInvalidValue;
-  rmsnorm_fast_kernel<<<(unsigned)n_tok, 256, 0, st>>>(x, w, y, (int)hidden, x_stride);
+  (void)launch_k(rmsnorm_fast_kernel, dim3((unsigned)n_tok), dim3(256), 0, st, x, w, y, (int)hidden, x_stride);
   return cudaGetLastError();
 }
 
@@ -195,6 +202,8 @@ __device__ __forceinline__ void head_store(const float (&x)[NP][2], bf16* __rest
 template <int NP>
 __global__ void qknorm_ref_kernel(bf16* __restrict__ x, const bf16* __restrict__ w, int n_tok, int row_dim,
                                   int n_heads) {
+  pdl_wait();
+  pdl_trigger();
   int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= n_tok * n_heads) return;
   int tok = gw / n_heads, h = gw % n_heads;
@@ -209,6 +218,8 @@ template <int NP>
 __global__ void rope_ref_kernel(const float* __restrict__ cos_t, const float* __restrict__ sin_t,
                                 bf16* __restrict__ x, int n_tok, const int* __restrict__ pos, int pos0, int row_dim,
                                 int n_heads) {
+  pdl_wait();
+  pdl_trigger();
   int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (gw >= n_tok * n_heads) return;
   int tok = gw / n_heads, h = gw % n_heads;
@@ -232,7 +243,7 @@ cudaError_t launch_qknorm_ref(bf16* x, const bf16* w, int hd, int n_tok, int row
   int warps = n_tok * n_heads;
   if (warps == 0) return cudaSuccess;
   int blocks = (warps + 3) / 4;
-  QIE_DISPATCH_HD(hd, (qknorm_ref_kernel<NP><<<blocks, 128, 0, st>>>(x, w, n_tok, row_dim, n_heads)));
+  QIE_DISPATCH_HD(hd, ((void)launch_k(qknorm_ref_kernel<NP>, dim3(blocks), dim3(128), 0, st, x, w, n_tok, row_dim, n_heads)));
   return cudaGetLastError();
 }
 
@@ -242,7 +253,7 @@ cudaError_t launch_rope_ref(const float* cos_t, const float* sin_t, bf16* x, int
   if (warps == 0) return cudaSuccess;
   int blocks = (warps + 3) / 4;
   QIE_DISPATCH_HD(hd,
-                  (rope_ref_kernel<NP><<<blocks, 128, 0, st>>>(cos_t, sin_t, x, n_tok, pos, pos0, row_dim, n_heads)));
+                  ((void)launch_k(rope_ref_kernel<NP>, dim3(blocks), dim3(128), 0, st, cos_t, sin_t, x, n_tok, pos, pos0, row_dim, n_heads)));
   return cudaGetLastError();
 }
 
@@ -250,6 +261,8 @@ cudaError_t launch_rope_ref(const float* cos_t, const float* sin_t, bf16* x, int
 // cudaMemcpy2D scatter of kv_copy_layer_to_cache_* (include_cuda.cu:165-279) ------------
 template <int NP>
 __global__ void qkv_post_kernel(QkvPostArgs a) {
+  pdl_wait();
+  pdl_trigger();
   const int hd = 64 * NP;
   const int heads = a.n_q + 2 * a.kv.n_kv;  // q heads, k heads, v heads
   int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -286,7 +299,7 @@ cudaError_t launch_qkv_post(const QkvPostArgs& a, cudaStream_t st) {
   int warps = a.n_tok * (a.n_q + 2 * a.kv.n_kv);
   if (warps == 0) return cudaSuccess;
   int blocks = (warps + 3) / 4;
-  QIE_DISPATCH_HD(a.kv.hd, (qkv_post_kernel<NP><<<blocks, 128, 0, st>>>(a)));
+  QIE_DISPATCH_HD(a.kv.hd, ((void)launch_k(qkv_post_kernel<NP>, dim3(blocks), dim3(128), 0, st, a)));
   return cudaGetLastError();
 }
 
@@ -294,6 +307,8 @@ cudaError_t launch_qkv_post(const QkvPostArgs& a, cudaStream_t st) {
 __global__ void kv_store_kernel(KvGeom kv, int layer, const bf16* __restrict__ K, const bf16* __restrict__ V,
                                 const int* __restrict__ pos, const int* __restrict__ slot,
                                 const int* __restrict__ block_table, int max_pages, int n_tok) {
+  pdl_wait();
+  pdl_trigger();
   int tok = blockIdx.x;
   int ps = pos[tok];
   int page = block_table[(size_t)slot[tok] * max_pages + ps / kv.page_size];
@@ -309,12 +324,14 @@ __global__ void kv_store_kernel(KvGeom kv, int layer, const bf16* __restrict__ K
 cudaError_t launch_kv_store(const KvGeom& kv, int layer, const bf16* K, const bf16* V, const int* pos,
                             const int* slot, const int* block_table, int max_pages, int n_tok, cudaStream_t st) {
   if (n_tok == 0) return cudaSuccess;
-  kv_store_kernel<<<n_tok, 128, 0, st>>>(kv, layer, K, V, pos, slot, block_table, max_pages, n_tok);
+  (void)launch_k(kv_store_kernel, dim3(n_tok), dim3(128), 0, st, kv, layer, K, V, pos, slot, block_table, max_pages, n_tok);
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ elementwise
 __global__ void silu_kernel(bf16* x, size_t n) {
+  pdl_wait();
+  pdl_trigger();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     float v = bf2f(x[i]);
@@ -323,26 +340,30 @@ __global__ void silu_kernel(bf16* x, size_t n) {
   }
 }
 __global__ void elem_mul_kernel(const bf16* a, const bf16* b, bf16* c, size_t n) {
+  pdl_wait();
+  pdl_trigger();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) c[i] = f2bf(__fmul_rn(bf2f(a[i]), bf2f(b[i])));
 }
 __global__ void residual_add_kernel(bf16* a, const bf16* b, size_t n) {
+  pdl_wait();
+  pdl_trigger();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = f2bf(__fadd_rn(bf2f(a[i]), bf2f(b[i])));
 }
 cudaError_t launch_silu(bf16* x, size_t n, cudaStream_t st) {
   if (!n) return cudaSuccess;
-  silu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n);
+  (void)launch_k(silu_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x, n);
   return cudaGetLastError();
 }
 cudaError_t launch_elem_mul(const bf16* a, const bf16* b, bf16* c, size_t n, cudaStream_t st) {
   if (!n) return cudaSuccess;
-  elem_mul_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, b, c, n);
+  (void)launch_k(elem_mul_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, a, b, c, n);
   return cudaGetLastError();
 }
 cudaError_t launch_residual_add(bf16* a, const bf16* b, size_t n, cudaStream_t st) {
   if (!n) return cudaSuccess;
-  residual_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, b, n);
+  (void)launch_k(residual_add_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, a, b, n);
   return cudaGetLastError();
 }
 
@@ -355,6 +376,8 @@ cudaError_t launch_residual_add(bf16* a, const bf16* b, size_t n, cudaStream_t s
 // fma(0, v, o) = o), so stopping at pos[t] is bit-identical.
 template <int NP>
 __global__ void __launch_bounds__(256) attention_ref_kernel(AttnArgs a) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int hd = 64 * NP;
   extern __shared__ float sm[];
   float* score = sm;                                                   // [kv_len]
@@ -460,7 +483,7 @@ cudaError_t launch_attention_ref(const AttnArgs& a, cudaStream_t st) {
       if (e != cudaSuccess) return e;                                                                         \
       set = true;                                                                                             \
     }                                                                                                         \
-    attention_ref_kernel<NPV><<<grid, 256, smem, st>>>(a);                                                    \
+    (void)launch_k(attention_ref_kernel<NPV>, dim3(grid), dim3(256), smem, st, a);                                                    \
   }
   switch (a.kv.hd) {
     case 64: QIE_ATTN(1); break;
@@ -494,6 +517,8 @@ __device__ __forceinline__ bool cand_better(float va, int ia, float vb, int ib) 
 __global__ void __launch_bounds__(1024) sample_topk_kernel(const bf16* __restrict__ logits, int* __restrict__ out,
                                                             size_t vocab, float temperature, int k, uint64_t seed,
                                                             uint64_t seed_stride, const int* __restrict__ step_ptr) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float topk_vals[256];
   __shared__ int topk_idxs[256];
   __shared__ Cand s_c[32];
@@ -609,7 +634,7 @@ __global__ void __launch_bounds__(1024) sample_topk_kernel(const bf16* __restric
 cudaError_t launch_sample_topk(const bf16* logits, int* out_tokens, int n_rows, size_t vocab, float temperature,
                                int k, uint64_t seed, uint64_t seed_stride, const int* step_ptr, cudaStream_t st) {
   if (n_rows == 0) return cudaSuccess;
-  sample_topk_kernel<<<n_rows, 1024, 0, st>>>(logits, out_tokens, vocab, temperature, k, seed, seed_stride, step_ptr);
+  (void)launch_k(sample_topk_kernel, dim3(n_rows), dim3(1024), 0, st, logits, out_tokens, vocab, temperature, k, seed, seed_stride, step_ptr);
   return cudaGetLastError();
 }
 
@@ -620,6 +645,8 @@ __device__ __forceinline__ unsigned long long mix64(unsigned long long z) {
   return z ^ (z >> 31);
 }
 __global__ void synth_fill_kernel(bf16* blob, size_t elem_begin, size_t n, unsigned long long seed, int kind) {
+  pdl_wait();
+  pdl_trigger();
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   unsigned long long g = elem_begin + i;
@@ -634,7 +661,7 @@ __global__ void synth_fill_kernel(bf16* blob, size_t elem_begin, size_t n, unsig
 cudaError_t launch_synth_fill(bf16* blob, size_t elem_begin, size_t n_elems, uint64_t seed, int kind,
                               cudaStream_t st) {
   if (!n_elems) return cudaSuccess;
-  synth_fill_kernel<<<(unsigned)((n_elems + 255) / 256), 256, 0, st>>>(blob, elem_begin, n_elems, seed, kind);
+  (void)launch_k(synth_fill_kernel, dim3((unsigned)((n_elems + 255) / 256)), dim3(256), 0, st, blob, elem_begin, n_elems, seed, kind);
   return cudaGetLastError();
 }
 
@@ -642,6 +669,8 @@ cudaError_t launch_synth_fill(bf16* blob, size_t elem_begin, size_t n_elems, uin
 // seeded N(0,1)-like values: bench-only stand-in for a long prefill
 __global__ void kv_fill_kernel(KvGeom kv, const int* __restrict__ block_row, int pos0, int n_pos,
                                unsigned long long seed) {
+  pdl_wait();
+  pdl_trigger();
   const size_t per_pos = (size_t)kv.n_layers * 2 * kv.n_kv * kv.hd;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= per_pos * n_pos) return;
@@ -664,12 +693,14 @@ cudaError_t launch_kv_fill(const KvGeom& kv, const int* block_row, int pos0, int
                            cudaStream_t st) {
   size_t n = (size_t)kv.n_layers * 2 * kv.n_kv * kv.hd * n_pos;
   if (!n) return cudaSuccess;
-  kv_fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(kv, block_row, pos0, n_pos, seed);
+  (void)launch_k(kv_fill_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, kv, block_row, pos0, n_pos, seed);
   return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ step bookkeeping
 __global__ void advance_kernel(int* pos, int* ids, const int* sampled, int n, int* step_ptr) {
+  pdl_wait();
+  pdl_trigger();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     pos[i] += 1;
@@ -679,7 +710,7 @@ __global__ void advance_kernel(int* pos, int* ids, const int* sampled, int n, in
 }
 cudaError_t launch_advance(int* pos, int* ids, const int* sampled, int n, int* step_ptr, cudaStream_t st) {
   if (!n) return cudaSuccess;
-  advance_kernel<<<(n + 127) / 128, 128, 0, st>>>(pos, ids, sampled, n, step_ptr);
+  (void)launch_k(advance_kernel, dim3((n + 127) / 128), dim3(128), 0, st, pos, ids, sampled, n, step_ptr);
   return cudaGetLastError();
 }
 
