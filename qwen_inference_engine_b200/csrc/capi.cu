@@ -384,8 +384,8 @@ static int engine_finish_setup(qie_engine* e) {
       CU(make_tensor_map_2d(&m.k, w.k, (int)Dkv, (int)H, 128));
       CU(make_tensor_map_2d(&m.v, w.v, (int)Dkv, (int)H, 128));
       CU(make_tensor_map_2d(&m.o, w.o, (int)H, (int)Dq, 128));
-      CU(make_tensor_map_2d(&m.gate, w.gate, (int)I, (int)H, 128));
-      CU(make_tensor_map_2d(&m.up, w.up, (int)I, (int)H, 128));
+      CU(make_tensor_map_2d(&m.gate, w.gate, (int)I, (int)H, 64));  // dual tile: 64 gate + 64 up rows
+      CU(make_tensor_map_2d(&m.up, w.up, (int)I, (int)H, 64));
       CU(make_tensor_map_2d(&m.down, w.down, (int)H, (int)I, 128));
     }
     CU(make_tensor_map_2d(&e->lm_head_map, e->lm_head, c.vocab, (int)H, 128));

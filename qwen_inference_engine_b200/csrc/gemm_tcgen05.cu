@@ -8,15 +8,22 @@
 // Swap-AB: the weight tile is the UMMA "A" operand (M = 128 weight rows = 128 TMEM lanes),
 // the activations are the "B" operand (N = BN tokens, 16..256), both K-major, 128-byte
 // swizzle, BLOCK_K = 64 bf16.  D[w_row, token] lives in TMEM: lane = weight row, column =
-// token.  Decode is HBM-bound on the weights, so the grid is (weight tiles x split-K) to
-// put >= one CTA on every SM; each CTA streams its [128 x Kslice] weight slab exactly once
-// through a 6-stage TMA/mbarrier ring.
-//   warp 0 : TMA producer (one elected lane)
+// token.  Decode is HBM-bound on the weights: each CTA streams its [128 x Kslice] weight
+// slab exactly once through a TMA/mbarrier ring.
+//   warp 0 : TMA producer (one elected lane); weight tiles are requested BEFORE the PDL
+//            wait on the previous kernel, activation tiles after it
 //   warp 1 : TMEM alloc/dealloc + MMA issuer (one elected lane, tcgen05.mma / commit)
-//   warps 2-5 : epilogue, TMEM -> registers (tcgen05.ld 32x32b) -> global
-// Split-K partials go to an fp32 workspace [split][token][Nout]; gemm_finalize_kernel sums
-// them in split order and applies the epilogue (store / residual / SiLU*up) with the
-// reference's rounding points (R3, R8, R9 of SURVEY.md 8a).
+//   warps 2-5 : epilogue, TMEM -> registers (tcgen05.ld 32x32b) -> ...
+// Split-K without a workspace: the S K-slices of one output tile are the S CTAs of a
+// thread-block CLUSTER (grid.y = cluster dim).  Each CTA parks its fp32 partial tile in its
+// own shared memory, the cluster synchronises, and CTA r sums rows [r*128/S, (r+1)*128/S)
+// of all S partials through distributed shared memory (ld.shared::cluster) in rank order
+// -- deterministic -- and applies the epilogue.  No partials in HBM/L2, no second launch.
+// Epilogues keep the reference's rounding points (R3, R8, R9 of SURVEY.md 8a):
+//   EPI_STORE     C = bf16(acc)
+//   EPI_RESIDUAL  x = bf16(float(x) + float(bf16(acc)))
+//   EPI_SILU_MUL  h = bf16(bf16(up) * bf16(silu(bf16(gate))));  the CTA's 128-lane tile is
+//                 64 gate rows (lanes 0-63) + the same 64 up rows (lanes 64-127)
 #include <cuda.h>
 
 #include <algorithm>
@@ -27,11 +34,11 @@
 
 namespace qie {
 
-static constexpr int BM = 128;     // weight rows per CTA (UMMA M)
-static constexpr int BK = 64;      // k elements per stage (128 B rows, SWIZZLE_128B)
+static constexpr int BM = 128;  // weight rows per CTA (UMMA M)
+static constexpr int BK = 64;   // k elements per stage (128 B rows, SWIZZLE_128B)
 template <int BN>
 struct TcCfg {
-  static constexpr int STAGES = BN <= 128 ? 6 : 4;  // 6 x (16+16) KiB = 192 KiB at BN=128; 4 x 48 KiB at BN=256
+  static constexpr int STAGES = BN <= 128 ? 6 : 4;  // 6 x (16+16) KiB at BN=128; 4 x 48 KiB at BN=256
 };
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -91,6 +98,17 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float ld_dsmem_f32(uint32_t local_addr, uint32_t cta_rank) {
+  uint32_t remote;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(cta_rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(remote) : "memory");
+  return v;
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 // start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) =
@@ -116,22 +134,17 @@ __device__ __forceinline__ float silu_ref_f(float x) {
 }
 
 struct TcSeg {
-  int rows;      // weight rows of this segment
-  int col0;      // first output column of this segment in the [*, ld] output / workspace
-  int tile0;     // first tile index
+  int rows;   // weight rows of this segment
+  int col0;   // first output column of this segment
+  int tile0;  // first tile index
 };
 
 struct TcArgs {
-  int M, K, ld;        // tokens, inner dim, total output columns (sum of segment rows)
+  int M, K;
   int nseg, n_tiles, splits, kb_per_split, kb_total;
+  int epi, dual, w_static, ld_out;
   TcSeg seg[3];
-  float* ws;           // [splits][M][ld] fp32 partials (splits > 1 or epilogue needs finalize)
-  bf16* direct_out;    // splits == 1 && plain store: bf16 [M][ld]
-  // fused split-K reduction: the LAST CTA to finish a tile group sums the partials in split
-  // order and applies the epilogue (no separate finalize launch)
-  int* counters;       // [token_tiles * groups], zero-initialised once, self-resetting (atomicInc wraps)
-  int fuse, groups, expected, epi, n_out, ld_out, w_static;
-  bf16* out;
+  bf16* out;  // [M, ld_out]
 };
 
 template <int BN>
@@ -146,7 +159,9 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
   constexpr int TC_STAGES = TcCfg<BN>::STAGES;
-  // 1024-byte alignment for SWIZZLE_128B
+  static_assert(TC_STAGES * STAGE_BYTES >= BN * BM * 4, "reduction tile must fit in the pipeline ring");
+  // 1024-byte alignment for SWIZZLE_128B (same offset in every CTA of a cluster: the dynamic
+  // shared window starts at the same address in all CTAs of a kernel)
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem0 + TC_STAGES * STAGE_BYTES;  // full[S], empty[S], tmem_full, slot
   auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -158,8 +173,11 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
   const int tile = blockIdx.x, split = blockIdx.y, ttile = blockIdx.z;
   int si = 0;
   while (si + 1 < g.nseg && tile >= g.seg[si + 1].tile0) ++si;
-  const CUtensorMap* map_w = si == 0 ? &map_w0 : (si == 1 ? &map_w1 : &map_w2);
-  const int row0 = (tile - g.seg[si].tile0) * BM;  // first weight row of this tile inside its segment
+  // dual (gate/up): one tile = 64 gate rows + the same 64 up rows; segment 0 = gate map, 1 = up map
+  const CUtensorMap* map_w = g.dual ? &map_w0 : (si == 0 ? &map_w0 : (si == 1 ? &map_w1 : &map_w2));
+  const int row0 = g.dual ? tile * (BM / 2) : (tile - g.seg[si].tile0) * BM;
+  const int seg_rows = g.seg[si].rows;
+  const int col0 = g.dual ? 0 : g.seg[si].col0;
   const int kb0 = split * g.kb_per_split;
   const int kb1 = min(g.kb_total, kb0 + g.kb_per_split);
   const int nkb = max(0, kb1 - kb0);
@@ -167,6 +185,7 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map_w) : "memory");
+    if (g.dual) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     for (int s = 0; s < TC_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
@@ -182,6 +201,16 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(slot));
 
+  auto load_w = [&](int i, int s) {
+    const uint32_t sa = smem0 + s * STAGE_BYTES;
+    if (g.dual) {  // two 64-row boxes: gate rows -> lanes 0-63, up rows -> lanes 64-127
+      tma_load_2d(sa, &map_w0, full_bar(s), (kb0 + i) * BK, row0);
+      tma_load_2d(sa + A_BYTES / 2, &map_w1, full_bar(s), (kb0 + i) * BK, row0);
+    } else {
+      tma_load_2d(sa, map_w, full_bar(s), (kb0 + i) * BK, row0);
+    }
+  };
+
   if (warp == 0) {
     if (lane == 0) {
       // Weights never depend on the previous kernel: start streaming them BEFORE waiting for
@@ -189,7 +218,7 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
       const int pre = g.w_static ? min(nkb, TC_STAGES) : 0;
       for (int i = 0; i < pre; ++i) {
         mbar_expect_tx(full_bar(i), STAGE_BYTES);
-        tma_load_2d(smem0 + i * STAGE_BYTES, map_w, full_bar(i), (kb0 + i) * BK, row0);
+        load_w(i, i);
       }
       pdl_wait();  // activations are produced by the previous kernel
       for (int i = 0; i < pre; ++i)
@@ -199,9 +228,8 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
         const uint32_t ph = (i / TC_STAGES) & 1;
         mbar_wait(empty_bar(s), ph ^ 1);
         mbar_expect_tx(full_bar(s), STAGE_BYTES);
-        const uint32_t sa = smem0 + s * STAGE_BYTES, sb = sa + A_BYTES;
-        tma_load_2d(sa, map_w, full_bar(s), (kb0 + i) * BK, row0);
-        tma_load_2d(sb, &map_x, full_bar(s), (kb0 + i) * BK, tok_base);
+        load_w(i, s);
+        tma_load_2d(smem0 + s * STAGE_BYTES + A_BYTES, &map_x, full_bar(s), (kb0 + i) * BK, tok_base);
       }
     }
   } else if (warp == 1) {
@@ -220,19 +248,24 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
         }
         umma_commit(empty_bar(s));  // frees the smem stage once the MMAs have read it
       }
-      umma_commit(tmem_full_bar);   // accumulator complete
+      umma_commit(tmem_full_bar);  // accumulator complete
     }
-  } else {
-    // epilogue warps 2..5 -> TMEM lane quarter (warp % 4)
-    pdl_wait();  // ws / out may still be read by the previous kernel
-    const int qd = warp & 3;
-    const int w_row = row0 + qd * 32 + lane;  // weight row inside the segment
-    const bool row_ok = w_row < g.seg[si].rows;
-    const int col = g.seg[si].col0 + w_row;
+  }
+
+  // ================= epilogue =================
+  // red[token][lane] fp32 (conflict-free: a warp writes 32 consecutive floats per token);
+  // it reuses the pipeline ring, which is idle once tmem_full has fired.
+  const uint32_t red = smem0;
+  const bool epi_warp = warp >= 2;
+  const int qd = warp & 3;  // TMEM lane quarter of this epilogue warp
+  const bool via_smem = g.splits > 1 || g.dual;
+  if (epi_warp) {
+    pdl_wait();  // `out` may still be read (residual) by the previous kernel
     if (nkb > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
+    const int lane_row = qd * 32 + lane;  // TMEM lane = row inside the 128-row tile
 #pragma unroll
     for (int c0 = 0; c0 < BN; c0 += 16) {
       uint32_t r[16];
@@ -242,54 +275,24 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
 #pragma unroll
         for (int j = 0; j < 16; ++j) r[j] = 0u;
       }
-      if (row_ok) {
+      if (via_smem) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int tok = tok_base + c0 + j;
-          if (tok < g.M) {
-            if (g.direct_out)
-              g.direct_out[(size_t)tok * g.ld + col] = f2bf(__uint_as_float(r[j]));
-            else
-              g.ws[((size_t)split * g.M + tok) * g.ld + col] = __uint_as_float(r[j]);
-          }
-        }
-      }
-    }
-    if (g.fuse) {
-      // ---- fused split-K reduction + epilogue by the last CTA of this tile group
-      __shared__ int s_last;
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int dual = g.epi == EPI_SILU_MUL;
-      const int grp = ttile * g.groups + (dual ? tile % g.groups : tile);
-      if (threadIdx.x == 64) {
-        const unsigned old = atomicInc(reinterpret_cast<unsigned*>(g.counters) + grp, (unsigned)g.expected - 1u);
-        s_last = old == (unsigned)g.expected - 1u;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (s_last) {
-        __threadfence();
-        // output column handled by this thread (dual: gate column c, up column n_out + c)
-        const int seg_row = row0 + qd * 32 + lane;
-        const int c = dual ? seg_row : col;
-        const bool ok = seg_row < g.seg[si].rows;
-        const int t_end = min(g.M, tok_base + BN);
-        if (ok) {
-          for (int tok = tok_base; tok < t_end; ++tok) {
-            float acc = 0.f, acc2 = 0.f;
-            for (int sp = 0; sp < g.splits; ++sp) {
-              const float* pw = g.ws + ((size_t)sp * g.M + tok) * g.ld;
-              acc += __ldcg(pw + c);
-              if (dual) acc2 += __ldcg(pw + g.n_out + c);
-            }
-            bf16* dst = g.out + (size_t)tok * g.ld_out + c;
-            if (g.epi == EPI_STORE) {
-              *dst = f2bf(acc);
-            } else if (g.epi == EPI_RESIDUAL) {
-              *dst = f2bf(__fadd_rn(bf2f(*dst), bf2f(f2bf(acc))));
-            } else {
-              const float gt = bf2f(f2bf(acc)), up = bf2f(f2bf(acc2));
-              *dst = f2bf(__fmul_rn(up, bf2f(f2bf(silu_ref_f(gt)))));
+        for (int j = 0; j < 16; ++j)
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(red + (uint32_t)((c0 + j) * BM + lane_row) * 4u), "r"(r[j]) : "memory");
+      } else {
+        // no split, single accumulator: epilogue straight from registers
+        const int w_row = row0 + lane_row;
+        if (w_row < seg_rows) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int tok = tok_base + c0 + j;
+            if (tok < g.M) {
+              bf16* dst = g.out + (size_t)tok * g.ld_out + col0 + w_row;
+              const float v = __uint_as_float(r[j]);
+              if (g.epi == EPI_RESIDUAL)
+                *dst = f2bf(__fadd_rn(bf2f(*dst), bf2f(f2bf(v))));
+              else
+                *dst = f2bf(v);
             }
           }
         }
@@ -297,36 +300,53 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
     }
     tc_fence_before();
   }
+  if (via_smem) {
+    // all partial tiles of the cluster are parked in shared memory
+    if (g.splits > 1) cluster_sync_all();
+    else __syncthreads();
+    if (epi_warp) {
+      const int t = threadIdx.x - 64;  // 0..127
+      const int S = g.splits;
+      const int tile_rows = g.dual ? BM / 2 : BM;          // output rows produced by this tile
+      const int rows_per = (tile_rows + S - 1) / S;        // rows reduced by this CTA
+      const int rbeg = split * rows_per;
+      const int rcnt = max(0, min(rows_per, tile_rows - rbeg));
+      const int n_tok = min(BN, g.M - tok_base);
+      for (int o = t; o < rcnt * n_tok; o += 128) {
+        const int tok = o / rcnt, rr = rbeg + o % rcnt;
+        float acc = 0.f, acc2 = 0.f;
+        const uint32_t a1 = red + (uint32_t)(tok * BM + rr) * 4u;
+        const uint32_t a2 = a1 + (uint32_t)(BM / 2) * 4u;  // dual: the up half of the tile
+        if (S > 1) {
+          for (int sp = 0; sp < S; ++sp) {
+            acc += ld_dsmem_f32(a1, sp);
+            if (g.dual) acc2 += ld_dsmem_f32(a2, sp);
+          }
+        } else {
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(acc) : "r"(a1) : "memory");
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(acc2) : "r"(a2) : "memory");
+        }
+        const int w_row = row0 + rr;
+        if (w_row < seg_rows) {
+          bf16* dst = g.out + (size_t)(tok_base + tok) * g.ld_out + col0 + w_row;
+          if (g.epi == EPI_STORE) {
+            *dst = f2bf(acc);
+          } else if (g.epi == EPI_RESIDUAL) {
+            *dst = f2bf(__fadd_rn(bf2f(*dst), bf2f(f2bf(acc))));
+          } else {
+            const float gt = bf2f(f2bf(acc)), up = bf2f(f2bf(acc2));
+            *dst = f2bf(__fmul_rn(up, bf2f(f2bf(silu_ref_f(gt)))));
+          }
+        }
+      }
+    }
+    // nobody may exit (and release its shared memory) while a peer still reads it
+    if (g.splits > 1) cluster_sync_all();
+  }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
-  }
-}
-
-// ------------------------------------------------------------------ split-K sum + epilogue
-// ws: [splits][M][ld]; EPI_SILU_MUL: columns [0,n) = gate, [n,2n) = up, out has n columns
-__global__ void gemm_finalize_kernel(const float* __restrict__ ws, bf16* __restrict__ out, int M, int ld, int n_out,
-                                     int ld_out, int splits, int epi) {
-  pdl_wait();
-  pdl_trigger();
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (size_t)M * n_out) return;
-  const int tok = (int)(i / n_out), c = (int)(i % n_out);
-  float acc = 0.f, acc2 = 0.f;
-  for (int s = 0; s < splits; ++s) {
-    const float* p = ws + ((size_t)s * M + tok) * ld;
-    acc += p[c];
-    if (epi == EPI_SILU_MUL) acc2 += p[n_out + c];
-  }
-  bf16* dst = out + (size_t)tok * ld_out + c;
-  if (epi == EPI_STORE) {
-    *dst = f2bf(acc);
-  } else if (epi == EPI_RESIDUAL) {
-    *dst = f2bf(__fadd_rn(bf2f(*dst), bf2f(f2bf(acc))));
-  } else {
-    const float gt = bf2f(f2bf(acc)), up = bf2f(f2bf(acc2));
-    *dst = f2bf(__fmul_rn(up, bf2f(f2bf(silu_ref_f(gt)))));
   }
 }
 
@@ -369,14 +389,35 @@ static cudaError_t launch_bn(const TcGemm& t, const TcArgs& g, int token_tiles, 
   if (!set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
     set = true;
   }
-  dim3 grid(g.n_tiles, g.splits, token_tiles);
   const CUtensorMap* w0 = reinterpret_cast<const CUtensorMap*>(t.w[0]);
   const CUtensorMap* w1 = reinterpret_cast<const CUtensorMap*>(t.w[t.nseg > 1 ? 1 : 0]);
   const CUtensorMap* w2 = reinterpret_cast<const CUtensorMap*>(t.w[t.nseg > 2 ? 2 : 0]);
-  (void)launch_k(gemm_tcgen05_kernel<BN>, dim3(grid), dim3(192), smem, st, *w0, *w1, *w2, *reinterpret_cast<const CUtensorMap*>(t.x), g);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(g.n_tiles, g.splits, token_tiles);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  if (g.splits > 1) {
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = 1;
+    at[na].val.clusterDim.y = g.splits;
+    at[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (g_use_pdl) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  return cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN>, *w0, *w1, *w2, *reinterpret_cast<const CUtensorMap*>(t.x), g);
 }
 
 int tc_token_tile(int M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256; }
@@ -387,48 +428,47 @@ cudaError_t launch_gemm_tcgen05(const TcGemm& t, int num_sms, cudaStream_t st, i
   g.M = t.M;
   g.K = t.K;
   g.nseg = t.nseg;
+  g.epi = t.epi;
+  g.dual = t.epi == EPI_SILU_MUL;
+  g.w_static = t.w_static;
+  g.ld_out = t.ld_out;
+  g.out = t.out;
   int tiles = 0, cols = 0;
-  for (int i = 0; i < t.nseg; ++i) {
-    g.seg[i].rows = t.rows[i];
-    g.seg[i].col0 = cols;
-    g.seg[i].tile0 = tiles;
-    tiles += (t.rows[i] + BM - 1) / BM;
-    cols += t.rows[i];
+  if (g.dual) {
+    // segments = (gate, up) with equal row counts; the weight maps must have 64-row boxes
+    if (t.nseg != 2 || t.rows[0] != t.rows[1]) return cudaErrorInvalidValue;
+    g.seg[0].rows = t.rows[0];
+    g.seg[0].col0 = 0;
+    g.seg[0].tile0 = 0;
+    g.nseg = 1;
+    tiles = (t.rows[0] + BM / 2 - 1) / (BM / 2);
+    cols = t.rows[0];
+  } else {
+    for (int i = 0; i < t.nseg; ++i) {
+      g.seg[i].rows = t.rows[i];
+      g.seg[i].col0 = cols;
+      g.seg[i].tile0 = tiles;
+      tiles += (t.rows[i] + BM - 1) / BM;
+      cols += t.rows[i];
+    }
   }
+  (void)cols;
   g.n_tiles = tiles;
-  g.ld = cols;
   g.kb_total = (t.K + BK - 1) / BK;
   const int BN = tc_token_tile(t.M);
   const int token_tiles = (t.M + BN - 1) / BN;
-  // split-K so that >= ~1 CTA lands on every SM; every split keeps >= 2 k-blocks
+  // split-K (= cluster size along grid.y) so that roughly one CTA lands on every SM; every
+  // slice keeps >= 2 k-blocks; cluster size <= 8 (the portable maximum)
   int splits = 1;
-  if (tiles * token_tiles < num_sms) {
-    splits = (num_sms + tiles * token_tiles - 1) / (tiles * token_tiles);
+  const int ctas = tiles * token_tiles;
+  if (ctas * 2 <= num_sms) {
+    splits = num_sms / ctas;
     splits = std::min(splits, std::max(1, g.kb_total / 2));
-    splits = std::min(splits, t.max_splits);
-    splits = std::min(splits, 8);  // the last CTA of a tile sums the partials: keep that tail short
+    splits = std::min(splits, std::min(8, std::max(1, t.max_splits)));  // portable cluster size
   }
   g.kb_per_split = (g.kb_total + splits - 1) / splits;
   splits = (g.kb_total + g.kb_per_split - 1) / g.kb_per_split;
   g.splits = splits;
-  const bool direct = splits == 1 && t.epi == EPI_STORE;
-  g.direct_out = direct ? t.out : nullptr;
-  g.ws = t.ws;
-  const bool dual = t.epi == EPI_SILU_MUL;
-  const int n_out_cols = dual ? cols / 2 : cols;
-  // fused finalize needs whole tiles per group (dual: gate tile i pairs with up tile i)
-  const bool can_fuse = !direct && t.counters && (!dual || (t.nseg == 2 && t.rows[0] == t.rows[1] && t.rows[0] % BM == 0));
-  g.fuse = can_fuse ? 1 : 0;
-  g.groups = dual ? tiles / 2 : tiles;
-  g.expected = dual ? 2 * splits : splits;
-  g.counters = t.counters;
-  g.epi = t.epi;
-  g.n_out = n_out_cols;
-  g.ld_out = t.ld_out;
-  g.out = t.out;
-  g.w_static = t.w_static;
-  if (can_fuse && (size_t)g.groups * token_tiles > (size_t)t.n_counters) return cudaErrorInvalidValue;
-  if (!direct && (size_t)splits * t.M * cols * sizeof(float) > t.ws_bytes) return cudaErrorMemoryAllocation;
   cudaError_t e;
   switch (BN) {
     case 16: e = launch_bn<16>(t, g, token_tiles, st); break;
@@ -437,16 +477,7 @@ cudaError_t launch_gemm_tcgen05(const TcGemm& t, int num_sms, cudaStream_t st, i
     case 128: e = launch_bn<128>(t, g, token_tiles, st); break;
     default: e = launch_bn<256>(t, g, token_tiles, st); break;
   }
-  if (e != cudaSuccess) return e;
   if (launches) *launches = 1;
-  if (!direct && !can_fuse) {
-    const int n_out = t.epi == EPI_SILU_MUL ? cols / 2 : cols;
-    const size_t n = (size_t)t.M * n_out;
-    (void)launch_k(gemm_finalize_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, t.ws, t.out, t.M, cols, n_out, t.ld_out, splits,
-                                                                      t.epi);
-    e = cudaGetLastError();
-    if (launches) *launches = 2;
-  }
   return e;
 }
 
