@@ -14,7 +14,7 @@
 //   GQA   : the G = n_q/n_kv query heads that share a kv head are the M rows (padded to
 //           16) of one m16n8k16 bf16 MMA, so K/V are loaded once for all of them
 //   KV    : page chunks [slot][hd] are contiguous in pool[page][layer][k|v][head][slot][hd];
-//           16-byte cp.async into a 4-stage XOR-swizzled ring, ldmatrix (K) /
+//           16-byte cp.async into a 3-stage XOR-swizzled ring, ldmatrix (K) /
 //           ldmatrix.trans (V) conflict-free
 //   softmax: online (running max / sum in fp32, exp2f with the scale folded in), P rounded
 //           to bf16 for the PV MMA (as FlashAttention does)
@@ -26,14 +26,16 @@
 namespace qie {
 
 static constexpr int TILE = 64;    // kv positions per pipeline stage
-static constexpr int STAGES = 4;
+static constexpr int STAGES = 3;   // 3 x 16 KiB (hd 64): 4 CTAs / SM
 
 template <int HD>
 struct FastAttnSmem {
   static constexpr int ROW_BYTES = HD * 2;
   static constexpr int TILE_BYTES = TILE * ROW_BYTES;       // one of K or V
   static constexpr int STAGE_BYTES = 2 * TILE_BYTES;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES;
+  static constexpr int RING = STAGES * STAGE_BYTES;
+  static constexpr int MAX_PAGES = 512;                     // page ids of this CTA's kv range, cached
+  static constexpr int TOTAL = RING + MAX_PAGES * 4;
 };
 
 // swizzled byte offset of 16-byte chunk `ch` of row `r` (rows are HD*2 bytes)
@@ -67,6 +69,12 @@ __global__ void __launch_bounds__(128) attn_decode_fast_kernel(FastAttnArgs a) {
   const int n_tiles = max(0, t_end - t_begin);
 
   const uint32_t sbase = smem_u32(smem);
+  // page ids of [t_begin*TILE, t_end*TILE) cached in shared memory (one global read each)
+  int* s_pages = reinterpret_cast<int*>(smem + SM::RING);
+  const int page0 = (t_begin * TILE) / psz;
+  const int n_pg = n_tiles > 0 ? min(SM::MAX_PAGES, (min(kv_len, t_end * TILE) - 1) / psz - page0 + 1) : 0;
+  for (int i = threadIdx.x; i < n_pg; i += 128) s_pages[i] = bt[page0 + i];
+  __syncthreads();
 
   // ---- Q fragments: rows = the G query heads of this kv head (rows >= G are zero)
   uint32_t qf[KC][4];
@@ -90,7 +98,8 @@ __global__ void __launch_bounds__(128) attn_decode_fast_kernel(FastAttnArgs a) {
       const int r = i / CH, ch = i % CH;
       int p = p0 + r;
       if (p >= kv_len) p = kv_len - 1;  // clamp: masked below
-      const int page = bt[p / psz];
+      const int pi = p / psz - page0;
+      const int page = pi < SM::MAX_PAGES ? s_pages[pi] : bt[p / psz];
       const size_t off = (size_t)(p % psz) * HD + ch * 8;
       cp_async16(kb + swz<HD>(r, ch), a.kv.chunk(page, a.layer, 0, kvh) + off);
       cp_async16(vb + swz<HD>(r, ch), a.kv.chunk(page, a.layer, 1, kvh) + off);
@@ -262,7 +271,7 @@ template <int HD>
 static cudaError_t launch_hd(const FastAttnArgs& a, cudaStream_t st) {
   static bool set = false;
   constexpr int smem = FastAttnSmem<HD>::TOTAL;
-  static_assert(smem >= 4 * 16 * HD * 4 + 4 * 16 * 2 * 4, "merge scratch must fit in the KV ring");
+  static_assert(FastAttnSmem<HD>::RING >= 4 * 16 * HD * 4 + 4 * 16 * 2 * 4, "merge scratch must fit in the KV ring");
   if (!set) {
     cudaError_t e = cudaFuncSetAttribute(attn_decode_fast_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
