@@ -158,6 +158,12 @@ typedef struct qie_engine qie_engine;
 int qie_synth_checkpoint_write(const qie_config* cfg, uint64_t seed, const char* meta_path,
                                const char* weights_path);
 
+/* HOST only (no GPU needed): parse meta_data.txt as build_indexed_tensors would index it
+ * (tensor_parser.cpp:132-165) and derive the model shape from the tensor shapes.
+ * head_dim_hint is used only when the checkpoint has no q_norm tensor. */
+int qie_checkpoint_inspect(const char* meta_path, int head_dim_hint, qie_config* cfg_out, size_t* total_bytes,
+                           int* n_tensors);
+
 /* build_indexed_tensors + load_all_weights_to_gpu_chunked + initialize_model_buffers,
  * tensor_parser.cpp:132-165, iengine.cu:117-223, utills.cu:4-129: parse meta_data.txt,
  * upload weights.bin as ONE device blob, derive the model shape from tensor shapes. */

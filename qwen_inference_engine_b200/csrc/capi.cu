@@ -267,6 +267,18 @@ int qie_synth_checkpoint_write(const qie_config* cfg, uint64_t seed, const char*
   return QIE_OK;
 }
 
+int qie_checkpoint_inspect(const char* meta_path, int head_dim_hint, qie_config* cfg_out, size_t* total_bytes,
+                           int* n_tensors) {
+  if (!meta_path || !cfg_out) return fail(QIE_EINVAL, "checkpoint_inspect: null argument");
+  Checkpoint ck;
+  std::string err;
+  if (!parse_meta(meta_path, &ck, &err)) return fail(QIE_EIO, "%s", err.c_str());
+  if (!derive_config(ck, head_dim_hint, 32786, cfg_out, &err)) return fail(QIE_EIO, "%s", err.c_str());
+  if (total_bytes) *total_bytes = ck.total_bytes;
+  if (n_tensors) *n_tensors = (int)ck.tensors.size();
+  return QIE_OK;
+}
+
 static void engine_free(qie_engine* e) {
   if (!e) return;
   cudaSetDevice(e->opts.device);

@@ -50,6 +50,14 @@ def write_synthetic_checkpoint(cfg, seed, meta_path, weights_path):
                                                 str(weights_path).encode()))
 
 
+def inspect_checkpoint(meta_path, head_dim_hint=0):
+    """host-only: (Config, total weight bytes, tensor count) of a meta_data.txt"""
+    cfg, tot, n = Config(), C.c_size_t(), C.c_int()
+    check(_lib.lib().qie_checkpoint_inspect(str(meta_path).encode(), head_dim_hint, C.byref(cfg), C.byref(tot),
+                                            C.byref(n)))
+    return cfg, tot.value, n.value
+
+
 def _i32(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
 

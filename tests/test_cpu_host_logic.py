@@ -1,0 +1,161 @@
+"""not-gpu: C-ABI surface, checkpoint format, synthetic-weight twins, host-side logic."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import qwen_inference_engine_b200 as q
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = q.lib()
+    names = q.declared_symbols()
+    assert len(names) >= 40
+    missing = [s for s in names if not hasattr(lib, s)]
+    assert not missing
+    out = subprocess.check_output(["nm", "-D", "--defined-only", q.LIB_PATH], text=True)
+    exported = set(re.findall(r" T (qie_\w+)", out))
+    assert set(names) <= exported
+    assert lib.qie_abi_version() == 2
+
+
+def test_header_cites_reference_interfaces():
+    src = open(os.path.join(ROOT, "include", "qie_b200.h")).read()
+    for cite in ("helpers.cuh:45-49", "matrix_mul.cu:165", "self_attension.cu:10-149", "logit_decode.cu:149-274",
+                 "qwen_main.cu:74-247", "qwen_main.cu:250-404", "tensor_parser.cpp:19-28", "iengine.cu:25-47"):
+        assert cite in src, cite
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(q.QieError) as ei:
+        q.Engine(synthetic="tiny")
+    assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "qwen_inference_engine_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or f == "Makefile":
+                txt = open(os.path.join(dirpath, f)).read()
+                # no import, include, dlopen or symbol of the checker anywhere in the product
+                assert not re.search(r"(^|\n)\s*(from|import)\s+oracle", txt), f
+                assert not re.search(r"#include\s+[\"<][^\n]*oracle", txt), f
+                for needle in ("libqie_oracle", "libqie_ref", "orc_", "ref_driver", "qie_oracle"):
+                    assert needle not in txt, (f, needle)
+    r = subprocess.run(["ldd", q.LIB_PATH], capture_output=True, text=True)
+    assert "oracle" not in r.stdout and "qie_ref" not in r.stdout
+
+
+def _np_synth(seed, g, kind):
+    """numpy twin of qie::synth_value / orc_synth_value / synth_fill_kernel"""
+    def mix(z):
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        return z ^ (z >> np.uint64(31))
+    with np.errstate(over="ignore"):
+        g = g.astype(np.uint64)
+        a = mix(np.uint64(seed) + (g + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15))
+        b = mix(a + np.uint64(0x9E3779B97F4A7C15))
+        m = np.uint64(0xFFFF)
+        s = sum(((x >> np.uint64(sh)) & m) for x in (a, b) for sh in (0, 16, 32, 48)).astype(np.int64)
+    c = (s - 262140).astype(np.float32)
+    k02 = np.float32(0.02) / np.float32(53509.92)
+    k05 = np.float32(0.05) / np.float32(53509.92)
+    v = c * k02 if kind == 0 else np.float32(1.0) + c * k05
+    u = v.astype(np.float32).view(np.uint32).astype(np.uint64)
+    return ((u + 0x7FFF + ((u >> 16) & 1)) >> 16).astype(np.uint16)
+
+
+def test_synthetic_checkpoint_twins(oracle, tmp_path):
+    """product generator == oracle generator == numpy twin, byte for byte; the meta text is the
+    reference's operator<< format; the loader parses it back to the same shape."""
+    cfg = q.make_config("tiny", context=64)
+    mp, wp = tmp_path / "meta_p.txt", tmp_path / "w_p.bin"
+    mo, wo = tmp_path / "meta_o.txt", tmp_path / "w_o.bin"
+    q.write_synthetic_checkpoint(cfg, 99, mp, wp)
+    oracle.synth_write(cfg, 99, mo, wo)
+    assert open(mp).read() == open(mo).read()
+    blob = np.fromfile(wp, np.uint16)
+    assert np.array_equal(blob, np.fromfile(wo, np.uint16))
+    txt = open(mp).read()
+    assert txt.startswith("Tensor: lm_head.weight\n  layer: -1\n  short_name: logits\n  shape: [ 512 128 ]\n  offsets: [ 0, 131072 ]\n\n")
+    # numpy twin over every tensor
+    for m in re.finditer(r"Tensor: (\S+)\n  layer: (-?\d+)\n  short_name: (\S+)\n  shape: \[ ([\d ]+)\]\n  offsets: \[ (\d+), (\d+) \]", txt):
+        b, e = int(m.group(5)), int(m.group(6))
+        kind = 1 if "norm" in m.group(3) else 0
+        g = np.arange(b // 2, e // 2)
+        assert np.array_equal(blob[b // 2:e // 2], _np_synth(99, g, kind)), m.group(1)
+    c2, total, n = q.inspect_checkpoint(mp)
+    want = cfg.as_dict()
+    want["context"] = 32786
+    assert c2.as_dict() == want and total == blob.nbytes and n == 3 + 11 * cfg.layers
+    w = (blob.astype(np.uint32) << 16).view(np.float32)
+    assert abs(w[:65536].std() - 0.02) < 2e-3
+
+
+def test_meta_parser_errors(tmp_path):
+    bad = tmp_path / "bad.txt"
+    bad.write_text("Tensor: model.embed_tokens.weight\n  layer: -1\n  short_name: embed_tokens.weight\n  shape: [ 4 4 ]\n  offsets: [ 0, 30 ]\n\n")
+    with pytest.raises(q.QieError) as ei:
+        q.inspect_checkpoint(bad)
+    assert ei.value.code == -3 and "byte range" in str(ei.value)
+    with pytest.raises(q.QieError):
+        q.inspect_checkpoint(tmp_path / "missing.txt")
+    # a checkpoint without an explicit lm_head (tied embeddings) is refused loudly
+    cfg = q.make_config("tiny")
+    m, w = tmp_path / "m.txt", tmp_path / "w.bin"
+    q.write_synthetic_checkpoint(cfg, 1, m, w)
+    txt = open(m).read()
+    first = txt.index("Tensor: model.embed_tokens.weight")
+    (tmp_path / "nolm.txt").write_text(txt[first:])
+    with pytest.raises(q.QieError) as ei:
+        q.inspect_checkpoint(tmp_path / "nolm.txt")
+    assert "lm_head" in str(ei.value)
+
+
+def test_reference_meta_data_parses_when_present():
+    ref_meta = "/root/reference/model_files/meta_data.txt"
+    if not os.path.exists(ref_meta):
+        pytest.skip("reference tree not present (GPU box)")
+    cfg, total, n = q.inspect_checkpoint(ref_meta)
+    assert (cfg.hidden, cfg.inter, cfg.layers, cfg.n_q, cfg.n_kv, cfg.head_dim, cfg.vocab) == (5120, 17408, 40, 40, 8, 128, 151936)
+    assert total == 29536614400  # weights.bin bytes of Qwen3-14B
+
+
+def test_rope_tables_host_function(oracle):
+    c = np.zeros((40, 32), np.float32)
+    s = np.zeros((40, 32), np.float32)
+    assert q.lib().qie_precompute_cos_sin(c.ctypes.data, s.ctypes.data, 40, 64) == 0
+    oc, osn = oracle.cos_sin(40, 64)
+    assert np.array_equal(c, oc) and np.array_equal(s, osn)
+    assert c[0].tolist() == [1.0] * 32 and abs(c[1, 0] - np.cos(1.0)) < 1e-6
+
+
+def test_tiebreak_closed_form_equals_block_reduction(oracle):
+    rng = np.random.default_rng(3)
+    from util import f32_to_bf16
+    for vocab in (1, 7, 255, 256, 257, 1000, 5000):
+        for levels in (1, 2, 5):
+            lg = f32_to_bf16(rng.choice(np.arange(levels, dtype=np.float32), size=vocab))
+            assert oracle.sample_topk(lg, 1.0, 1, 1234) == oracle.argmax_tiebreak(lg)
+    lg = f32_to_bf16(np.zeros(600, np.float32))  # all tied: residue class 255 wins, lowest index in it
+    assert oracle.argmax_tiebreak(lg) == 255
+
+
+def test_shape_table_and_roofline_bytes():
+    c = q.make_config("qwen2.5-0.5b")
+    assert q.weight_bytes(c) == 988016384 and q.kv_bytes_per_pos(c) == 12288
+    assert q.weight_bytes(q.make_config("qwen2.5-1.5b")) == 3087328256
+    assert q.weight_bytes(q.make_config("qwen2.5-7b")) == 14140994560
