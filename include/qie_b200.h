@@ -169,6 +169,11 @@ int qie_checkpoint_inspect(const char* meta_path, int head_dim_hint, qie_config*
  * upload weights.bin as ONE device blob, derive the model shape from tensor shapes. */
 int qie_engine_create(const char* meta_path, const char* weights_path, const qie_engine_opts* opts,
                       qie_engine** out);
+/* Same engine over a weight blob that is ALREADY on the device (the reference's main()
+ * uploads weights.bin itself, iengine.cu:117-223, and hands g_gpu_weights_buffer to llm()).
+ * The blob is borrowed, never freed by the engine. */
+int qie_engine_create_from_blob(const char* meta_path, void* device_blob, const qie_engine_opts* opts,
+                                qie_engine** out);
 /* Same engine, weights generated on the device by the same counter hash (no file). */
 int qie_engine_create_synthetic(const qie_config* cfg, uint64_t seed, const qie_engine_opts* opts,
                                 qie_engine** out);

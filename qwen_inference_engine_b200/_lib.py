@@ -81,6 +81,7 @@ def lib():
         "qie_synth_checkpoint_write": (i32, [C.POINTER(Config), u64, C.c_char_p, C.c_char_p]),
         "qie_checkpoint_inspect": (i32, [C.c_char_p, i32, C.POINTER(Config), C.POINTER(sz), C.POINTER(i32)]),
         "qie_engine_create": (i32, [C.c_char_p, C.c_char_p, C.POINTER(EngineOpts), C.POINTER(vp)]),
+        "qie_engine_create_from_blob": (i32, [C.c_char_p, vp, C.POINTER(EngineOpts), C.POINTER(vp)]),
         "qie_engine_create_synthetic": (i32, [C.POINTER(Config), u64, C.POINTER(EngineOpts), C.POINTER(vp)]),
         "qie_engine_destroy": (None, [vp]),
         "qie_engine_get_config": (i32, [vp, C.POINTER(Config)]),

@@ -287,6 +287,7 @@ static void engine_free(qie_engine* e) {
     if (kvp.second.exec) cudaGraphExecDestroy(kvp.second.exec);
   for (auto& kvp : e->cap)
     if (kvp.second.d) cudaFree(kvp.second.d);
+  if (!e->blob_owned) e->blob = nullptr;
   void* dev[] = {e->blob, e->cos_d, e->sin_d, e->kv.pool, e->block_table_d, e->ids_d, e->pos_d, e->slot_d,
                  e->sampled_d, e->rowstep_d, e->x, e->xn, e->q, e->k, e->v, e->att, e->h, e->logits, e->qkv,
                  e->gemm_ws, e->attn_ws_o, e->attn_ws_ml, e->gemm_counters};
@@ -506,6 +507,29 @@ int qie_engine_create(const char* meta_path, const char* weights_path, const qie
     engine_free(e);
     return fail(QIE_EIO, "read error on %s", weights_path);
   }
+  rc = engine_finish_setup(e);
+  if (rc) {
+    engine_free(e);
+    return rc;
+  }
+  *out = e;
+  return QIE_OK;
+}
+
+int qie_engine_create_from_blob(const char* meta_path, void* device_blob, const qie_engine_opts* opts,
+                                qie_engine** out) {
+  if (!meta_path || !device_blob || !out) return fail(QIE_EINVAL, "engine_create_from_blob: null argument");
+  qie_engine* e = nullptr;
+  int rc = engine_begin(opts, &e);
+  if (rc) return rc;
+  std::string err;
+  if (!parse_meta(meta_path, &e->ck, &err) ||
+      !derive_config(e->ck, e->opts.head_dim_hint, e->opts.context, &e->cfg, &err)) {
+    engine_free(e);
+    return fail(QIE_EIO, "%s", err.c_str());
+  }
+  e->blob = (bf16*)device_blob;
+  e->blob_owned = false;
   rc = engine_finish_setup(e);
   if (rc) {
     engine_free(e);

@@ -1,0 +1,186 @@
+// compat_layers.cpp -- implementation of include/layers/iengine_compat.hh: the reference's
+// host API names on top of the C ABI.  Host code only; every computation goes through
+// libqie_b200's kernels.
+#include "../../include/layers/iengine_compat.hh"
+
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <map>
+#include <mutex>
+
+#include "checkpoint.h"
+
+static const char* meta_path() {
+  const char* p = getenv("QIE_META");
+  return p ? p : "../model_files/meta_data.txt";  // tensor_parser.cpp:34
+}
+
+std::ostream& operator<<(std::ostream& os, const tensor& t) {  // tensor_parser.cpp:19-28
+  os << "Tensor: " << t.tensor_name << "\n";
+  os << "  layer: " << t.layer_index << "\n";
+  os << "  short_name: " << t.short_name << "\n";
+  os << "  shape: [ ";
+  for (auto s : t.shape) os << s << " ";
+  os << "]\n";
+  os << "  offsets: [ " << t.data_offsets[0] << ", " << t.data_offsets[1] << " ]\n";
+  return os;
+}
+
+std::vector<tensor> parsed_tensors() {
+  qie::Checkpoint ck;
+  std::string err;
+  std::vector<tensor> out;
+  if (!qie::parse_meta(meta_path(), &ck, &err)) {
+    std::cerr << "parsed_tensors: " << err << "\n";
+    return out;
+  }
+  for (const qie::TensorInfo& ti : ck.tensors) {
+    tensor t;
+    t.tensor_name = ti.name;
+    t.short_name = ti.short_name;
+    t.layer_index = ti.layer;
+    t.shape = ti.shape;
+    t.data_offsets = {ti.begin, ti.end};
+    out.push_back(t);
+  }
+  return out;
+}
+
+TensorTable build_indexed_tensors() {  // tensor_parser.cpp:132-165
+  TensorTable indexed;
+  for (auto& t : parsed_tensors()) {
+    size_t slot = t.layer_index >= 0 ? (size_t)t.layer_index : 0;
+    auto& v = indexed[t.short_name];
+    if (v.size() <= slot) v.resize(slot + 1);
+    v[slot] = t;
+  }
+  return indexed;
+}
+
+void precompute_cos_sin(float* c, float* s, int seq_len, int head_dim) { qie_precompute_cos_sin(c, s, seq_len, head_dim); }
+
+// ---- page list: host bookkeeping only (KV memory is the engine's pool) -----------------
+page_table* create_page_list(int pages_required) {
+  page_table* head = nullptr;
+  page_table** cur = &head;
+  for (int i = 0; i < pages_required; ++i) {
+    *cur = new page_table();
+    (*cur)->k_page_ptr = nullptr;
+    (*cur)->v_page_ptr = nullptr;
+    (*cur)->page_allocated = 0;
+    (*cur)->ptr_to_next_page = nullptr;
+    cur = &((*cur)->ptr_to_next_page);
+  }
+  return head;
+}
+void allocate_page_buffers(page_table* node, size_t) {
+  if (node) node->page_allocated = 1;  // pages are taken from the pool when positions are written
+}
+void free_page_list(page_table* head) {
+  while (head) {
+    page_table* next = head->ptr_to_next_page;
+    delete head;
+    head = next;
+  }
+}
+
+// ---- engine binding ---------------------------------------------------------------------
+static std::mutex g_mu;
+static std::map<void*, qie_engine*> g_engines;
+
+extern "C" int qie_engine_create_from_blob(const char* meta_path, void* device_blob, const qie_engine_opts* opts,
+                                           qie_engine** out);
+
+qie_engine* qie_compat_engine(__nv_bfloat16* blob) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_engines.find(blob);
+  if (it != g_engines.end()) return it->second;
+  qie_engine_opts o;
+  qie_engine_opts_default(&o);
+  o.page_size = 16;
+  qie_engine* e = nullptr;
+  if (qie_engine_create_from_blob(meta_path(), blob, &o, &e) != QIE_OK) {
+    fprintf(stderr, "qie compat: %s\n", qie_last_error());
+    return nullptr;
+  }
+  // the reference hard-codes top-k 50, T = 1.0 (prefill) / 0.7 (decode), seed 1234 + step
+  qie_engine_set_sampling(e, 50, 1.0f, 0.7f, 1234, 1);
+  g_engines[blob] = e;
+  return e;
+}
+
+void initialize_model_buffers(ModelBuffers& buf, int* h_token_ids, TensorTable& tensors, std::ifstream&, size_t n) {
+  buf.sequence_len = n;
+  buf.h_token_ids.assign(h_token_ids, h_token_ids + n);
+  auto dim = [&](const char* name, int i) -> size_t {
+    auto it = tensors.find(name);
+    return it == tensors.end() || it->second.empty() || (int)it->second[0].shape.size() <= i ? 0 : it->second[0].shape[i];
+  };
+  buf.hidden_dim = dim("embed_tokens.weight", 1);
+  buf.vocab_size = dim("logits", 0);
+  buf.up_dim = dim("mlp.up_proj.weight", 0);
+  buf.head_dim = dim("self_attn.q_norm.weight", 0);
+  buf.hidden_dim_kv = dim("self_attn.k_proj.weight", 0);
+  buf.num_of_qheads = buf.head_dim ? dim("self_attn.q_proj.weight", 0) / buf.head_dim : 0;
+  buf.num_of_kvheads = buf.head_dim ? buf.hidden_dim_kv / buf.head_dim : 0;
+  buf.number_of_layers = tensors.count("input_layernorm.weight") ? tensors["input_layernorm.weight"].size() : 0;
+  buf.context_size = CONTEXT_SIZE;
+}
+void destroy_model_buffers(ModelBuffers& buf) { buf.h_token_ids.clear(); }
+
+int llm(batch_metadata* seq, TensorTable, std::ifstream&, page_table*, int, __nv_bfloat16* blob) {
+  qie_engine* e = qie_compat_engine(blob);
+  if (!e || !seq || !seq->buffer) return QIE_EINVAL;
+  ModelBuffers* b = seq->buffer;
+  if (b->qie_seq < 0 && qie_seq_new(e, &b->qie_seq) != QIE_OK) return QIE_ENOMEM;
+  int32_t tok = 0;
+  int rc;
+  if (seq->state == prefill) {
+    rc = qie_prefill(e, b->qie_seq, b->h_token_ids.data(), (int)b->h_token_ids.size(), &tok);
+  } else {
+    int32_t in = seq->generated_token;
+    rc = qie_decode_step(e, &b->qie_seq, &in, 1, &tok);
+    b->sequence_len += 1;  // qwen_main.cu:265
+  }
+  if (rc != QIE_OK) {
+    fprintf(stderr, "llm: %s\n", qie_last_error());
+    return rc;  // negative: never a token id
+  }
+  return tok;
+}
+
+// ---- operator wrappers (default stream) --------------------------------------------------
+#define QB(p) reinterpret_cast<qie_bf16*>(p)
+void launch_rms(__nv_bfloat16* x, __nv_bfloat16* w, __nv_bfloat16* y, size_t hidden, size_t seqlen) {
+  qie_rmsnorm(QB(x), QB(w), QB(y), hidden, seqlen, nullptr);
+}
+void launch_rope(float* c, float* s, __nv_bfloat16* x, size_t seqlen, size_t hd, size_t hidden, size_t nheads) {
+  qie_rope(c, s, QB(x), (int)seqlen, 0, (int)hd, (int)hidden, (int)nheads, nullptr);
+}
+void launch_rope_single(float* c, float* s, __nv_bfloat16* x, size_t pos, size_t hd, int hidden, int nheads) {
+  qie_rope(c, s, QB(x), 1, (int)pos, (int)hd, hidden, nheads, nullptr);
+}
+void launch_matmul(__nv_bfloat16* A, __nv_bfloat16* B, __nv_bfloat16* C, int M, int N, int K) {
+  qie_matmul(QB(A), QB(B), QB(C), M, N, K, nullptr);
+}
+void launch_elem(__nv_bfloat16* a, __nv_bfloat16* b, __nv_bfloat16* out, int n) { qie_elem_mul(QB(a), QB(b), QB(out), n, nullptr); }
+void launch_act(__nv_bfloat16* x, size_t n) { qie_silu(QB(x), n, nullptr); }
+void launch_resadd(__nv_bfloat16* x, __nv_bfloat16* y, size_t n) { qie_residual_add(QB(x), QB(y), n, nullptr); }
+void launch_qknorm(__nv_bfloat16* X, __nv_bfloat16* w, int hd, int seqlen, int hidden, int nheads) {
+  qie_qknorm(QB(X), QB(w), hd, seqlen, hidden, nheads, nullptr);
+}
+void proj(const tensor& t, std::ifstream&, __nv_bfloat16*, __nv_bfloat16* w_d, size_t, __nv_bfloat16* x, __nv_bfloat16* y,
+          int m, int n, int k, __nv_bfloat16* blob) {
+  assign_weight_pointer(t, w_d, blob);
+  launch_matmul(x, w_d, y, m, n, k);
+}
+int sample_topk_bf16(__nv_bfloat16* logits_d, int vocab, float temperature, int topk, unsigned long long seed, int step) {
+  int* d_tok = nullptr;
+  int h_tok = -1;
+  if (cudaMalloc(&d_tok, sizeof(int)) != cudaSuccess) return QIE_ECUDA;
+  int rc = qie_sample_topk(QB(logits_d), d_tok, 1, (size_t)vocab, temperature, topk, seed + (unsigned long long)step, 0, nullptr);
+  cudaMemcpy(&h_tok, d_tok, sizeof(int), cudaMemcpyDeviceToHost);
+  cudaFree(d_tok);
+  return rc == QIE_OK ? h_tok : rc;
+}

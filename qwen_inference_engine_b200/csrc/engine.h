@@ -44,6 +44,7 @@ struct qie_engine {
   // weights: ONE device blob, tensors addressed as blob + begin (helpers.cuh:18-29)
   qie::Checkpoint ck;
   qie::bf16* blob = nullptr;
+  bool blob_owned = true;
   std::vector<qie::LayerWeights> L;
   const qie::bf16 *embed = nullptr, *final_norm = nullptr, *lm_head = nullptr;
   float *cos_d = nullptr, *sin_d = nullptr;
