@@ -41,7 +41,7 @@ typedef uint16_t qie_bf16;     /* raw __nv_bfloat16 bits */
 
 const char* qie_last_error(void);
 /* ABI version; bumped on any signature change. */
-int qie_abi_version(void); /* currently 2 */
+int qie_abi_version(void); /* currently 3 */
 
 /* ------------------------------------------------------------------------------------
  * (1) operator level.  All pointers are DEVICE pointers unless named h_*.
@@ -234,6 +234,21 @@ int qie_seq_fill_synthetic(qie_engine* e, int seq, int n_pos, uint64_t seed);
 int qie_decode_step_profile(qie_engine* e, const int* h_seqs, const int32_t* h_tokens_in, int n, float* ms_by_kind,
                             int* launches_by_kind, int n_kinds);
 const char* qie_kernel_kind_name(int kind);
+
+/* Persistent decode kernel (decode_mega.cu): reference-order decode steps of <= 8 rows run
+ * as ONE cooperative launch.  qie_engine_set_int keys: "mega" (0/1, default 1 unless
+ * QIE_MEGA=0), "mega_layers_run" (debug: stop after N layers, 0 = whole step), "mega_prof"
+ * (0/1: record a device timestamp at every phase boundary).  qie_decode_uses_mega tells
+ * whether a step of n rows at this KV length would take that path.
+ * qie_mega_prof_read copies the timestamps (ns, globaltimer) of the last profiled step to
+ * HOST memory: [0] start, then 5 per layer (after QKV, attention, O, gate/up, down), then
+ * after lm_head and after sampling; returns the number of values.
+ * qie_engine_read_activation copies an activation buffer of the last forward to HOST
+ * memory (names: x qkv att h logits sampled kv); returns the byte count copied. */
+int qie_engine_set_int(qie_engine* e, const char* key, long value);
+int qie_decode_uses_mega(const qie_engine* e, int n_rows, int kv_len);
+long qie_mega_prof_read(qie_engine* e, uint64_t* h_out, size_t max_values);
+long qie_engine_read_activation(qie_engine* e, const char* name, void* h_out, size_t max_bytes);
 
 #ifdef __cplusplus
 }

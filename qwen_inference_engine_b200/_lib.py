@@ -104,6 +104,10 @@ def lib():
         "qie_seq_fill_synthetic": (i32, [vp, i32, i32, u64]),
         "qie_decode_step_profile": (i32, [vp, vp, vp, i32, vp, vp, i32]),
         "qie_kernel_kind_name": (C.c_char_p, [i32]),
+        "qie_engine_set_int": (i32, [vp, C.c_char_p, C.c_long]),
+        "qie_decode_uses_mega": (i32, [vp, i32, i32]),
+        "qie_mega_prof_read": (C.c_long, [vp, vp, sz]),
+        "qie_engine_read_activation": (C.c_long, [vp, C.c_char_p, vp, sz]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

@@ -32,7 +32,7 @@ static int cuda_fail(cudaError_t e, const char* what) {
 extern "C" {
 
 const char* qie_last_error(void) { return g_err; }
-int qie_abi_version(void) { return 2; }
+int qie_abi_version(void) { return 3; }
 
 // ---------------------------------------------------------------- operator level
 int qie_embedding(qie_bf16* out, const qie_bf16* table, const int* ids, size_t hidden, size_t n_tok, qie_stream st) {
@@ -290,7 +290,8 @@ static void engine_free(qie_engine* e) {
   if (!e->blob_owned) e->blob = nullptr;
   void* dev[] = {e->blob, e->cos_d, e->sin_d, e->kv.pool, e->block_table_d, e->ids_d, e->pos_d, e->slot_d,
                  e->sampled_d, e->rowstep_d, e->x, e->xn, e->q, e->k, e->v, e->att, e->h, e->logits, e->qkv,
-                 e->gemm_ws, e->attn_ws_o, e->attn_ws_ml, e->gemm_counters};
+                 e->gemm_ws, e->attn_ws_o, e->attn_ws_ml, e->gemm_counters, e->mega_layers_d, e->mega_cand_d,
+                 e->mega_bar_d, e->mega_prof_d};
   for (void* p : dev)
     if (p) cudaFree(p);
   if (e->block_table_h) cudaFreeHost(e->block_table_h);
@@ -386,6 +387,28 @@ static int engine_finish_setup(qie_engine* e) {
   CU(cudaMalloc(&e->h, R * I * sizeof(bf16)));
   e->logits_rows = std::min<int>((int)R, o.max_seqs);
   CU(cudaMalloc(&e->logits, (size_t)e->logits_rows * c.vocab * sizeof(bf16)));
+  CU(cudaMalloc(&e->qkv, R * (Dq + 2 * Dkv) * sizeof(bf16)));
+  {
+    const char* mv = getenv("QIE_MEGA");
+    e->use_mega = !(mv && mv[0] == '0');
+    std::vector<MegaLayer> ml(c.layers);
+    bool aligned = true;
+    for (int l = 0; l < c.layers; ++l) {
+      const LayerWeights& w = e->L[l];
+      ml[l] = MegaLayer{w.in_ln, w.q, w.k, w.v, w.o, w.q_norm, w.k_norm, w.post_ln, w.gate, w.up, w.down};
+      const void* ps[] = {w.in_ln, w.q, w.k, w.v, w.o, w.post_ln, w.gate, w.up, w.down, w.q_norm, w.k_norm};
+      for (const void* p : ps) aligned = aligned && (((uintptr_t)p & 15) == 0);
+    }
+    aligned = aligned && (((uintptr_t)e->lm_head & 15) == 0) && (((uintptr_t)e->embed & 15) == 0) &&
+              (((uintptr_t)e->final_norm & 15) == 0) && (c.vocab % 2 == 0);
+    if (aligned) {  // TMA bulk copies need 16-byte aligned weight rows; otherwise the per-operator path is used
+      CU(cudaMalloc(&e->mega_layers_d, c.layers * sizeof(MegaLayer)));
+      CU(cudaMemcpy(e->mega_layers_d, ml.data(), c.layers * sizeof(MegaLayer), cudaMemcpyHostToDevice));
+      CU(cudaMalloc(&e->mega_cand_d, (size_t)e->num_sms * 8 * sizeof(MegaCand)));
+      CU(cudaMalloc(&e->mega_bar_d, 64));
+      CU(cudaMalloc(&e->mega_prof_d, (size_t)decode_mega_prof_slots(c.layers) * sizeof(unsigned long long)));
+    }
+  }
   if (o.numerics == QIE_NUMERICS_FAST) {
     if (c.n_q / c.n_kv > 16 || c.head_dim > 128) return fail(QIE_EINVAL, "fast numerics: need n_q/n_kv <= 16 and head_dim <= 128");
     if ((c.hidden % 64) || (c.inter % 64) || ((c.n_q * c.head_dim) % 64)) return fail(QIE_EINVAL, "fast numerics: inner dims must be multiples of 64");
@@ -402,7 +425,6 @@ static int engine_finish_setup(qie_engine* e) {
       CU(make_tensor_map_2d(&m.down, w.down, (int)H, (int)I, 128));
     }
     CU(make_tensor_map_2d(&e->lm_head_map, e->lm_head, c.vocab, (int)H, 128));
-    CU(cudaMalloc(&e->qkv, R * (Dq + 2 * Dkv) * sizeof(bf16)));
     e->gemm_ws_bytes = std::max<size_t>((size_t)64 << 20, R * 2 * I * sizeof(float) * 2);
     CU(cudaMalloc(&e->gemm_ws, e->gemm_ws_bytes));
     CU(cudaMalloc(&e->gemm_counters, 8192 * sizeof(int)));
@@ -715,24 +737,29 @@ int qie_prefill(qie_engine* e, int seq, const int32_t* h_ids, int n, int32_t* h_
 }
 
 // one decode step for the batch already staged on the device (ids/pos/slot/rowstep)
+static cudaError_t decode_forward(qie_engine* e, int n, int bucket) {
+  if (decode_uses_mega(e, n, bucket)) return forward_decode_mega(e, n, bucket, e->temp_decode);
+  return forward_rows(e, n, bucket, 0, n, e->temp_decode, true);
+}
+
 static int decode_launch(qie_engine* e, int n, int max_kv_len) {
   const int bucket = ((max_kv_len + 127) / 128) * 128;
   if (!e->opts.use_graph || e->capture) {
-    CU(forward_rows(e, n, bucket, 0, n, e->temp_decode, true));
+    CU(decode_forward(e, n, bucket));
     return QIE_OK;
   }
   auto key = std::make_pair(n, bucket);
   auto it = e->graphs.find(key);
   if (it == e->graphs.end()) {
     e->graphs.emplace(key, qie_engine::GraphEntry());
-    CU(forward_rows(e, n, bucket, 0, n, e->temp_decode, true));
+    CU(decode_forward(e, n, bucket));
     return QIE_OK;
   }
   if (!it->second.exec) {
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
     long before = e->launches;
-    cudaError_t fe = forward_rows(e, n, bucket, 0, n, e->temp_decode, true);
+    cudaError_t fe = decode_forward(e, n, bucket);
     cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
     if (fe != cudaSuccess) return cuda_fail(fe, "forward (capture)");
     if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
@@ -891,6 +918,57 @@ int qie_seq_fill_synthetic(qie_engine* e, int seq, int n_pos, uint64_t seed) {
   s.len += n_pos;
   if (s.step == 0) s.step = 1;
   return QIE_OK;
+}
+
+int qie_engine_set_int(qie_engine* e, const char* key, long value) {
+  if (!e || !key) return fail(QIE_EINVAL, "null argument");
+  std::string k(key);
+  if (k == "mega") e->use_mega = value != 0;
+  else if (k == "mega_layers_run") e->mega_layers_run = (int)value;
+  else if (k == "mega_prof") e->mega_prof_on = value != 0;
+  else return fail(QIE_EINVAL, "unknown option %s", key);
+  // captured graphs bake these choices in
+  CU(cudaStreamSynchronize(e->stream));
+  for (auto& kvp : e->graphs)
+    if (kvp.second.exec) cudaGraphExecDestroy(kvp.second.exec);
+  e->graphs.clear();
+  return QIE_OK;
+}
+
+int qie_decode_uses_mega(const qie_engine* e, int n_rows, int kv_len) {
+  if (!e) return 0;
+  return decode_uses_mega(e, n_rows, ((kv_len + 127) / 128) * 128) ? 1 : 0;
+}
+
+long qie_mega_prof_read(qie_engine* e, uint64_t* h_out, size_t max_values) {
+  if (!e || !h_out) return fail(QIE_EINVAL, "null argument");
+  if (!e->mega_prof_d) return fail(QIE_ESTATE, "persistent decode kernel not available for this checkpoint");
+  size_t n = std::min<size_t>(max_values, (size_t)5 * e->cfg.layers + 3);
+  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaMemcpy(h_out, e->mega_prof_d, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return (long)n;
+}
+
+long qie_engine_read_activation(qie_engine* e, const char* name, void* h_out, size_t max_bytes) {
+  if (!e || !name || !h_out) return fail(QIE_EINVAL, "null argument");
+  const qie_config& c = e->cfg;
+  const size_t R = e->opts.max_batch_tokens;
+  const size_t Dq = (size_t)c.n_q * c.head_dim, Dkv = (size_t)c.n_kv * c.head_dim;
+  std::string k(name);
+  const void* src = nullptr;
+  size_t bytes = 0;
+  if (k == "x") src = e->x, bytes = R * c.hidden * 2;
+  else if (k == "qkv") src = e->qkv, bytes = R * (Dq + 2 * Dkv) * 2;
+  else if (k == "att") src = e->att, bytes = R * Dq * 2;
+  else if (k == "h") src = e->h, bytes = R * c.inter * 2;
+  else if (k == "logits") src = e->logits, bytes = (size_t)e->logits_rows * c.vocab * 2;
+  else if (k == "sampled") src = e->sampled_d, bytes = R * sizeof(int);
+  else if (k == "kv") src = e->kv.pool, bytes = (size_t)e->kv.n_pages * e->kv.page_stride() * 2;
+  else return fail(QIE_EINVAL, "unknown activation %s", name);
+  bytes = std::min(bytes, max_bytes);
+  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaMemcpy(h_out, src, bytes, cudaMemcpyDeviceToHost));
+  return (long)bytes;
 }
 
 const char* qie_kernel_kind_name(int kind) {

@@ -289,4 +289,60 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
   return cudaSuccess;
 }
 
+
+bool decode_uses_mega(const qie_engine* e, int n, int max_kv_len) {
+  if (!e->use_mega || e->opts.numerics != QIE_NUMERICS_REFERENCE_ORDER || e->capture || !e->mega_layers_d) return false;
+  const qie_config& c = e->cfg;
+  return n <= decode_mega_max_rows(c.hidden, c.inter, c.n_q, c.n_kv, c.head_dim, max_kv_len);
+}
+
+cudaError_t forward_decode_mega(qie_engine* e, int n, int max_kv_len, float temperature) {
+  const qie_config& c = e->cfg;
+  MegaArgs a{};
+  a.H = c.hidden;
+  a.I = c.inter;
+  a.L = c.layers;
+  a.n_q = c.n_q;
+  a.n_kv = c.n_kv;
+  a.hd = c.head_dim;
+  a.V = c.vocab;
+  a.layers = e->mega_layers_d;
+  a.embed = e->embed;
+  a.final_norm = e->final_norm;
+  a.lm_head = e->lm_head;
+  a.cos_t = e->cos_d;
+  a.sin_t = e->sin_d;
+  a.B = n;
+  a.ids = e->ids_d;
+  a.pos = e->pos_d;
+  a.slot = e->slot_d;
+  a.block_table = e->block_table_d;
+  a.max_pages = e->max_pages_per_seq;
+  a.max_kv_len = max_kv_len;
+  a.rowstep = e->rowstep_d;
+  a.kv = e->kv;
+  a.x = e->x;
+  a.qkv = e->qkv;
+  a.att = e->att;
+  a.h = e->h;
+  a.logits = e->logits;
+  a.cand = e->mega_cand_d;
+  a.sampled = e->sampled_d;
+  a.bar = e->mega_bar_d;
+  a.prof = e->mega_prof_on ? e->mega_prof_d : nullptr;
+  a.greedy = e->topk == 1;
+  a.advance = 1;
+  a.n_layers_run = e->mega_layers_run;
+  cudaError_t r = launch_decode_mega(a, e->num_sms, e->stream);
+  if (r != cudaSuccess) return r;
+  ++e->launches;
+  if (!a.greedy && e->mega_layers_run <= 0) {
+    // top-k > 1: the sampler is the reference's k-round scan + XORWOW draw (logit_decode.cu:149-274)
+    QIE_TRY(KK_SAMPLE, launch_sample_topk(e->logits, e->sampled_d, n, c.vocab, temperature, e->topk, e->seed, 0,
+                                          e->add_step ? e->rowstep_d : nullptr, e->stream));
+    QIE_TRY(KK_ADVANCE, launch_advance(e->pos_d, e->ids_d, e->sampled_d, n, e->rowstep_d, e->stream));
+  }
+  return cudaSuccess;
+}
+
 }  // namespace qie

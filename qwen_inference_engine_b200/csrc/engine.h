@@ -81,6 +81,15 @@ struct qie_engine {
   float *attn_ws_o = nullptr, *attn_ws_ml = nullptr;
   int attn_max_splits = 16;
 
+  // persistent decode kernel (decode_mega.cu): reference-order decode steps of <= 8 rows
+  bool use_mega = true;              // QIE_MEGA=0 disables
+  qie::MegaLayer* mega_layers_d = nullptr;
+  qie::MegaCand* mega_cand_d = nullptr;
+  unsigned* mega_bar_d = nullptr;
+  unsigned long long* mega_prof_d = nullptr;  // phase timestamps of the last profiled step
+  bool mega_prof_on = false;
+  int mega_layers_run = 0;           // debug: run only this many layers (no lm_head)
+
   // sampling
   int topk = 1;
   float temp_prefill = 1.0f, temp_decode = 0.7f;
@@ -120,4 +129,8 @@ enum KernelKind {
 // first launch error. Counts launches into e->launches.
 cudaError_t forward_rows(qie_engine* e, int n_rows, int max_kv_len, int out_row0, int n_out, float temperature,
                          bool advance);
+// true if a decode step of n rows / this kv bucket runs through the persistent kernel
+bool decode_uses_mega(const qie_engine* e, int n_rows, int max_kv_len);
+// one decode step (rows described in ids_d/pos_d/slot_d) through the persistent kernel
+cudaError_t forward_decode_mega(qie_engine* e, int n_rows, int max_kv_len, float temperature);
 }  // namespace qie

@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "launch.h"
+#include "ref_math.cuh"
 
 namespace qie {
 
@@ -39,12 +40,6 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {
 #undef QIE_W
     default: asm volatile("cp.async.wait_group 0;\n" ::: "memory"); break;
   }
-}
-
-__device__ __forceinline__ float silu_ref(float x) {
-  // SiLU.cu:6-8,19-20:  y = x * (1 / (1 + expf(-x)))
-  float sg = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-x)));
-  return __fmul_rn(x, sg);
 }
 
 // One warp = one unit = 8 consecutive weight rows over the full K.

@@ -150,4 +150,42 @@ cudaError_t launch_kv_fill(const KvGeom& kv, const int* block_row, int pos0, int
 // step bookkeeping on the device: pos[i] += 1 ; ids <- sampled tokens
 cudaError_t launch_advance(int* pos, int* ids, const int* sampled, int n, int* step_ptr, cudaStream_t st);
 
+// ---------------------------------------------------------------- persistent decode step
+// decode_mega.cu: ONE cooperative launch runs a whole decode step (all layers, lm_head,
+// greedy arg-max, bookkeeping) for up to 8 sequences in reference-order arithmetic.
+struct MegaLayer {
+  const bf16 *in_ln, *q, *k, *v, *o, *q_norm, *k_norm, *post_ln, *gate, *up, *down;
+};
+struct MegaCand {
+  float val;
+  int idx;
+};
+struct MegaArgs {
+  int H, I, L, n_q, n_kv, hd, V;
+  const MegaLayer* layers;  // device array [L]
+  const bf16 *embed, *final_norm, *lm_head;
+  const float *cos_t, *sin_t;
+  int B;  // decode rows, one token per sequence
+  int* ids;
+  int* pos;
+  const int* slot;
+  const int* block_table;
+  int max_pages, max_kv_len;
+  int* rowstep;
+  KvGeom kv;
+  bf16 *x, *qkv, *att, *h, *logits;  // [B, H] [B, Dq+2Dkv] [B, Dq] [B, I] [B, V]
+  MegaCand* cand;                    // [grid, B] per-CTA arg-max candidates
+  int* sampled;                      // [B]
+  unsigned* bar;                     // grid barrier counter, zeroed by the launcher
+  unsigned long long* prof;          // optional: globaltimer at every phase boundary (CTA 0)
+  int greedy, advance;
+  int n_layers_run;                  // debug: stop after this many layers (0 = all, then lm_head)
+  // geometry, filled by the launcher
+  int KC, n_slots, slot_bytes, act_bytes;
+};
+// max rows the persistent kernel accepts for this model shape (0 = shape unsupported)
+int decode_mega_max_rows(int H, int I, int n_q, int n_kv, int hd, int max_kv_len);
+int decode_mega_prof_slots(int L);
+cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st);
+
 }  // namespace qie

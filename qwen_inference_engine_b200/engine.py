@@ -187,6 +187,24 @@ class Engine:
             out[name.decode()] = (float(ms[i]), int(cnt[i]))
         return out
 
+    # -- persistent decode kernel ---------------------------------------------------
+    def set_int(self, key, value):
+        check(self._L.qie_engine_set_int(self._h, key.encode(), int(value)))
+
+    def uses_mega(self, n_rows, kv_len):
+        return bool(self._L.qie_decode_uses_mega(self._h, n_rows, kv_len))
+
+    def mega_prof(self):
+        """device timestamps (ns) of the last profiled persistent-kernel step"""
+        out = np.zeros(5 * self.config.layers + 3, np.uint64)
+        n = check(self._L.qie_mega_prof_read(self._h, out.ctypes.data, len(out)))
+        return out[:n]
+
+    def read_activation(self, name, n_elems, dtype=np.uint16):
+        out = np.zeros(n_elems, dtype)
+        check(self._L.qie_engine_read_activation(self._h, name.encode(), out.ctypes.data, out.nbytes))
+        return out
+
     def launch_count(self):
         return self._L.qie_launch_count(self._h)
 

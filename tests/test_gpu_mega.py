@@ -1,0 +1,117 @@
+"""-m gpu: the persistent decode kernel (csrc/decode_mega.cu) against the per-operator
+reference-order path of the same library -- which tests/test_gpu_e2e_vs_reference.py pins
+bit for bit to the reference's own kernels -- and directly against those kernels.
+Everything here is bit-exact: activations, logits, KV cache, tokens."""
+import numpy as np
+import pytest
+
+from util import prompt_ids
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def qie():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import qwen_inference_engine_b200 as q
+    return q
+
+
+def _kv_snapshot(eng):
+    """the whole KV pool as raw bf16 bits"""
+    v = eng.kv_view()
+    n = v.n_pages * v.page_size * v.n_layers * 2 * v.n_kv_heads * v.head_dim
+    return eng.read_activation("kv", n)
+
+
+def _run(eng, n_seq, n_prompt, n_steps, use_mega):
+    eng.set_int("mega", int(use_mega))
+    seqs, toks = [], []
+    for i in range(n_seq):
+        s = eng.new_sequence()
+        seqs.append(s)
+        toks.append(eng.prefill(s, prompt_ids(n_prompt + i, eng.config.vocab, seed=11 + i)))
+    hist, logits = [], []
+    cur = np.asarray(toks, np.int32)
+    for _ in range(n_steps):
+        cur = eng.decode_step(seqs, cur)
+        hist.append(cur.copy())
+        logits.append(eng.read_activation("logits", n_seq * eng.config.vocab))
+    kv = _kv_snapshot(eng)
+    for s in seqs:
+        eng.free_sequence(s)
+    return np.stack(hist), logits, kv
+
+
+@pytest.mark.parametrize("arch,n_seq,n_prompt,n_steps", [
+    ("tiny", 1, 3, 20), ("small", 1, 9, 40), ("small", 3, 5, 24), ("small128", 2, 7, 20), ("small", 8, 4, 12),
+])
+def test_mega_equals_per_operator_path(qie, arch, n_seq, n_prompt, n_steps):
+    eng = qie.Engine(synthetic=arch, seed=1234, context=512, max_batch_tokens=64, use_graph=False)
+    assert eng.uses_mega(n_seq, n_prompt + n_seq + n_steps)
+    want_t, want_l, want_kv = _run(eng, n_seq, n_prompt, n_steps, use_mega=False)
+    got_t, got_l, got_kv = _run(eng, n_seq, n_prompt, n_steps, use_mega=True)
+    for i in range(n_steps):
+        assert np.array_equal(got_l[i], want_l[i]), f"logits differ at step {i}"
+    assert np.array_equal(got_t, want_t)
+    assert np.array_equal(got_kv, want_kv)
+    eng.close()
+
+
+@pytest.mark.parametrize("n_layers", [1, 2])
+def test_mega_layer_activations(qie, n_layers):
+    """debug hook: stop after n layers and compare the residual stream / MLP activations."""
+    eng = qie.Engine(synthetic="small", seed=1234, context=512, max_batch_tokens=64, use_graph=False)
+    cfg = eng.config
+    outs = {}
+    for mode in (0, 1):
+        eng.set_int("mega", mode)
+        s = eng.new_sequence()
+        t = eng.prefill(s, prompt_ids(6, cfg.vocab))
+        if mode:
+            eng.set_int("mega_layers_run", n_layers)
+            eng.decode_step([s], [t])
+            eng.set_int("mega_layers_run", 0)
+            outs[mode] = {k: eng.read_activation(k, n) for k, n in
+                          (("x", cfg.hidden), ("h", cfg.inter), ("att", cfg.n_q * cfg.head_dim))}
+        else:
+            eng.capture(True)
+            eng.decode_step([s], [t])
+            outs[mode] = {"x": eng.read_capture("x_out", n_layers - 1)[:cfg.hidden],
+                          "h": eng.read_capture("mlp_h", n_layers - 1)[:cfg.inter],
+                          "att": eng.read_capture("attn", n_layers - 1)[:cfg.n_q * cfg.head_dim]}
+            eng.capture(False)
+        eng.free_sequence(s)
+    for k in ("att", "h", "x"):
+        assert np.array_equal(outs[1][k], outs[0][k]), k
+    eng.close()
+
+
+def test_mega_graph_replay_and_topk(qie):
+    """CUDA-graph replay of the cooperative launch; top-k 50 sampling falls back to the
+    reference sampler behind the persistent kernel (same XORWOW stream)."""
+    eng = qie.Engine(synthetic="small", seed=1234, context=512, max_batch_tokens=64, use_graph=True)
+    ids = prompt_ids(12, eng.config.vocab)
+    eng.set_int("mega", 0)
+    want = eng.generate(ids, 48)
+    eng.set_int("mega", 1)
+    assert eng.generate(ids, 48) == want
+    eng.set_sampling(topk=50, temperature_prefill=1.0, temperature_decode=0.7, seed=1234, add_step=True)
+    got = eng.generate(ids, 32)
+    eng.set_int("mega", 0)
+    assert eng.generate(ids, 32) == got
+    eng.close()
+
+
+def test_mega_config1_vs_reference_kernels(qie, ref):
+    """BASELINE configs[0] through the persistent kernel: 128 greedy tokens identical to the
+    reference's own kernels."""
+    from test_gpu_e2e_vs_reference import _ref_generate
+    eng = qie.Engine(synthetic="qwen2.5-0.5b", seed=1234, max_batch_tokens=64, kv_bytes=256 << 20)
+    ids = prompt_ids(32, eng.config.vocab)
+    assert eng.uses_mega(1, 160)
+    want, _, _ = _ref_generate(ref, eng, ids, 128)
+    assert eng.generate(ids, 128) == want
+    eng.close()

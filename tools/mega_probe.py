@@ -1,0 +1,52 @@
+"""persistent decode kernel probe: tokens/s at batch B and the per-phase time breakdown."""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import qwen_inference_engine_b200 as q  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--arch", default="qwen2.5-0.5b")
+ap.add_argument("--batch", type=int, default=1)
+ap.add_argument("--ctx", type=int, default=32)
+ap.add_argument("--steps", type=int, default=128)
+ap.add_argument("--mega", type=int, default=1)
+ap.add_argument("--graph", type=int, default=1)
+a = ap.parse_args()
+cfg = q.make_config(a.arch)
+eng = q.Engine(synthetic=a.arch, kv_bytes=a.batch * (a.ctx + a.steps + 256) * q.kv_bytes_per_pos(cfg) + (64 << 20),
+               max_seqs=a.batch + 1, max_batch_tokens=max(a.batch, 64), use_graph=bool(a.graph))
+eng.set_int("mega", a.mega)
+seqs = []
+for i in range(a.batch):
+    s = eng.new_sequence()
+    eng.fill_synthetic(s, a.ctx, seed=i)
+    seqs.append(s)
+tok = np.arange(a.batch, dtype=np.int32) + 5
+print("uses_mega", eng.uses_mega(a.batch, a.ctx + a.steps))
+out = eng.decode_run(seqs, tok, 8)  # warm-up (+ graph capture)
+eng.sync()
+t0 = time.perf_counter()
+out = eng.decode_run(seqs, out[-1], a.steps)
+eng.sync()
+dt = time.perf_counter() - t0
+wb = q.weight_bytes(cfg)
+print(f"batch {a.batch} ctx {a.ctx}: {a.steps} steps in {dt*1e3:.2f} ms -> {dt/a.steps*1e6:.1f} us/step, "
+      f"{a.batch*a.steps/dt:.1f} tok/s, weights-only HBM {wb/(dt/a.steps)/1e9:.0f} GB/s")
+print("tokens", out[-1][:4])
+if a.mega and eng.uses_mega(a.batch, a.ctx + a.steps + 16):
+    eng.set_int("mega_prof", 1)
+    eng.decode_run(seqs, out[-1], 3)
+    ts = eng.mega_prof().astype(np.int64)
+    L = cfg.layers
+    d = np.diff(ts)
+    per = d[:5 * L].reshape(L, 5)
+    names = ["rms+qkv", "attention", "o", "rms+gateup", "down"]
+    print("phase us (mean over layers):", {n: round(float(per[:, i].mean()) / 1e3, 2) for i, n in enumerate(names)})
+    print("layers total us", round(float(per.sum()) / 1e3, 1), "lm_head us", round(float(d[5 * L]) / 1e3, 1),
+          "sample us", round(float(d[5 * L + 1]) / 1e3, 1), "whole us", round(float(ts[-1] - ts[0]) / 1e3, 1))
+eng.close()
