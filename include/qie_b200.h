@@ -241,8 +241,10 @@ const char* qie_kernel_kind_name(int kind);
  * (0/1: record a device timestamp at every phase boundary).  qie_decode_uses_mega tells
  * whether a step of n rows at this KV length would take that path.
  * qie_mega_prof_read copies the timestamps (ns, globaltimer) of the last profiled step to
- * HOST memory: [0] start, then 5 per layer (after QKV, attention, O, gate/up, down), then
- * after lm_head and after sampling; returns the number of values.
+ * HOST memory: [0] start, then 16 per layer (QKV: rows loaded, normed, GEMM done, barrier;
+ * attention: done, barrier; O: loaded, GEMM, barrier; gate/up: loaded, normed, GEMM, barrier;
+ * down: loaded, GEMM, barrier), then lm_head (loaded, normed, GEMM, barrier) and sampling;
+ * returns the number of values (16*layers + 6).
  * qie_engine_read_activation copies an activation buffer of the last forward to HOST
  * memory (names: x qkv att h logits sampled kv); returns the byte count copied. */
 int qie_engine_set_int(qie_engine* e, const char* key, long value);

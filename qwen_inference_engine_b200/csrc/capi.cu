@@ -404,7 +404,7 @@ static int engine_finish_setup(qie_engine* e) {
     if (aligned) {  // TMA bulk copies need 16-byte aligned weight rows; otherwise the per-operator path is used
       CU(cudaMalloc(&e->mega_layers_d, c.layers * sizeof(MegaLayer)));
       CU(cudaMemcpy(e->mega_layers_d, ml.data(), c.layers * sizeof(MegaLayer), cudaMemcpyHostToDevice));
-      CU(cudaMalloc(&e->mega_cand_d, (size_t)e->num_sms * 8 * sizeof(MegaCand)));
+      CU(cudaMalloc(&e->mega_cand_d, (size_t)e->num_sms * 64 * sizeof(MegaCand)));
       CU(cudaMalloc(&e->mega_bar_d, 64));
       CU(cudaMalloc(&e->mega_prof_d, (size_t)decode_mega_prof_slots(c.layers) * sizeof(unsigned long long)));
     }
@@ -943,7 +943,7 @@ int qie_decode_uses_mega(const qie_engine* e, int n_rows, int kv_len) {
 long qie_mega_prof_read(qie_engine* e, uint64_t* h_out, size_t max_values) {
   if (!e || !h_out) return fail(QIE_EINVAL, "null argument");
   if (!e->mega_prof_d) return fail(QIE_ESTATE, "persistent decode kernel not available for this checkpoint");
-  size_t n = std::min<size_t>(max_values, (size_t)5 * e->cfg.layers + 3);
+  size_t n = std::min<size_t>(max_values, (size_t)16 * e->cfg.layers + 6);
   CU(cudaStreamSynchronize(e->stream));
   CU(cudaMemcpy(h_out, e->mega_prof_d, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return (long)n;

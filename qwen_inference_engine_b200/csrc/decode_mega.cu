@@ -25,6 +25,7 @@
 // (+residual); then final norm + lm_head with the greedy arg-max (reference tie-break,
 // logit_decode.cu:15-33,182-223) folded into the epilogue, and the step bookkeeping.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -37,9 +38,14 @@ constexpr int NW = 8;                         // consumer warps
 constexpr int NTC = NW * 32;                  // consumer threads
 constexpr int MEGA_THREADS = NTC + 32;        // + producer warp
 constexpr int MAX_SLOTS = 32;
-constexpr int MAX_ROWS = 8;                   // rows per launch (A fragments by predicated LDS)
-constexpr int OFF_FULL = 0, OFF_EMPTY = 256, OFF_RMS = 512, OFF_CAND = 1024;
-constexpr int HDR_BYTES = OFF_CAND + NW * MAX_ROWS * 8;  // 1536
+constexpr int VT = 128;                       // cached positions per V tile in shared memory
+constexpr int MAX_ROWS = 64;                  // rows (sequences) per launch
+constexpr int MAX_LAYERS = 64;
+// shared-memory header
+constexpr int OFF_FULL = 0, OFF_EMPTY = 256, OFF_ISSUED = 512, OFF_RMS = 768, OFF_CAND = 1024;
+constexpr int OFF_LAYERS = OFF_CAND + NW * MAX_ROWS * 8;                 // MegaLayer[MAX_LAYERS]
+constexpr int OFF_WNORM = OFF_LAYERS + MAX_LAYERS * (int)sizeof(MegaLayer);  // 2 x [H] bf16 norm weights
+static_assert(sizeof(MegaLayer) == 88, "MegaLayer layout");
 
 enum { PH_QKV = 0, PH_O = 1, PH_GATEUP = 2, PH_DOWN = 3, PH_LMHEAD = 4 };
 
@@ -77,24 +83,33 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ uint32_t lds32_volatile(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts32_volatile(uint32_t addr, uint32_t v) {
+  asm volatile("st.volatile.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long globaltimer() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
 
-// grid barrier for the consumer warps of all CTAs (cooperative launch: all CTAs resident)
+// Grid barrier for the consumer warps of all CTAs (cooperative launch: all CTAs resident).
+// bar.sync orders the CTA's writes before thread 0's release; the release/acquire pair on
+// the counter publishes them device-wide.  Readers fetch activations with ld.cg /
+// cp.async.cg (L2), never through L1.
 __device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& epoch) {
   bar_consumers();
   if (threadIdx.x == 0) {
     epoch += gridDim.x;
-    __threadfence();
-    atomicAdd(ctr, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
     unsigned v;
     do {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
     } while (v < epoch);
-    __threadfence();
   }
   bar_consumers();
 }
@@ -108,7 +123,7 @@ struct Phase {
   int nseg, K, dual, units, kind;
 };
 
-__device__ __forceinline__ void make_phase(const MegaArgs& a, int idx, Phase& p) {
+__device__ __forceinline__ void make_phase(const MegaArgs& a, const unsigned char* smem, int idx, Phase& p) {
   const int hd = a.hd, Dq = a.n_q * hd, Dkv = a.n_kv * hd;
   p.W2 = nullptr;
   p.dual = 0;
@@ -119,7 +134,7 @@ __device__ __forceinline__ void make_phase(const MegaArgs& a, int idx, Phase& p)
     p.rows[0] = a.V;
     p.K = a.H;
   } else {
-    const MegaLayer& w = a.layers[idx >> 2];
+    const MegaLayer& w = reinterpret_cast<const MegaLayer*>(smem + OFF_LAYERS)[idx >> 2];
     p.kind = idx & 3;
     switch (p.kind) {
       case PH_QKV:
@@ -155,20 +170,21 @@ __device__ __forceinline__ int units_of_cta(int units, int cta, int grid) {
 // ---------------------------------------------------------------- producer
 // Walks every GEMM phase of the step in order; per phase the units of this CTA in rounds of
 // NW (one unit per consumer warp), chunk-major inside a round so the warps advance together.
-__device__ void producer_loop(const MegaArgs& a, uint32_t smem_base, int n_phases) {
+// `issued` (shared memory) tells consumers that job j's mbarrier phase has been armed: a
+// consumer that is a whole ring lap ahead must not test the parity of an older phase.
+__device__ void producer_loop(const MegaArgs& a, const unsigned char* smem, uint32_t smem_base, int n_phases) {
   const int lane = threadIdx.x & 31;
   const int S = a.n_slots, KC = a.KC, RS = (KC + 8) * 2;
-  const uint32_t ring = smem_base + HDR_BYTES + a.act_bytes;
+  const uint32_t ring = smem_base + a.off_ring;
   uint32_t job = 0;
   for (int ph = 0; ph < n_phases; ++ph) {
     Phase p;
-    make_phase(a, ph, p);
+    make_phase(a, smem, ph, p);
     const int n_c = units_of_cta(p.units, blockIdx.x, gridDim.x);
     const int nch = (p.K + KC - 1) / KC;
     const int nrows = p.dual ? 16 : 8;
     for (int r0 = 0; r0 < n_c; r0 += NW) {
       const int nact = min(NW, n_c - r0);
-      // this lane's source row for each unit slot of the round is recomputed per job (cheap)
       for (int ch = 0; ch < nch; ++ch) {
         const int k0 = ch * KC;
         const int klen = min(KC, p.K - k0);
@@ -182,6 +198,8 @@ __device__ void producer_loop(const MegaArgs& a, uint32_t smem_base, int n_phase
           if (lane == 0) {
             mbar_wait(empty, par ^ 1);
             mbar_expect_tx(full, (uint32_t)(nrows * klen * 2));
+            __threadfence_block();
+            sts32_volatile(smem_base + OFF_ISSUED, job + 1);
           }
           __syncwarp();
           if (lane < nrows) {
@@ -202,12 +220,19 @@ struct Best {
   int i;
 };
 
-// One warp accumulates its unit (8 weight rows, or 8 gate + 8 up rows) over one chunk.
-template <bool DUAL>
-__device__ __forceinline__ void mma_chunk(float (&acc)[4], float (&acc2)[4], uint32_t slot_addr, uint32_t a_addr,
-                                          int RS, int nk16, bool row_valid, int lane) {
+// One warp accumulates its unit (8 weight rows, or 8 gate + 8 up rows) over one chunk for
+// all token tiles.  MT == 0: up to 8 tokens, A fragments by predicated 32-bit LDS (rows
+// 8..15 of the MMA tile are register zeros).  MT >= 1: 16*MT token rows by ldmatrix.
+template <int MT, bool DUAL>
+__device__ __forceinline__ void mma_chunk(float (&acc)[MT == 0 ? 1 : MT][4], float (&acc2)[MT == 0 ? 1 : MT][4],
+                                          uint32_t slot_addr, uint32_t a_addr, int AS, int RS, int nk16, int B,
+                                          int lane) {
+  constexpr int MTT = MT == 0 ? 1 : MT;
   // ldmatrix source rows: lanes 0-7 rows 0-7 @k, 8-15 rows 0-7 @k+8 (x2); DUAL adds rows 8-15 (up)
   const uint32_t baddr = slot_addr + (lane & 7) * RS + ((lane >> 3) & 1) * 16 + (DUAL ? ((lane >> 4) & 1) * 8 * RS : 0);
+  const bool row_valid = (lane >> 2) < B;
+  const uint32_t a0 = MT == 0 ? a_addr + (lane >> 2) * AS + (lane & 3) * 4
+                              : a_addr + ((lane & 7) + ((lane >> 3) & 1) * 8) * AS + (lane >> 4) * 16;
 #pragma unroll 4
   for (int j = 0; j < nk16; ++j) {
     uint32_t b0, b1, b2 = 0, b3 = 0;
@@ -215,64 +240,115 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[4], float (&acc2)[4], uin
       ldmatrix_x4(b0, b1, b2, b3, baddr + j * 32);
     else
       ldmatrix_x2(b0, b1, baddr + j * 32);
-    uint32_t af[4] = {0u, 0u, 0u, 0u};
-    if (row_valid) {
-      af[0] = lds32(a_addr + j * 32);
-      af[2] = lds32(a_addr + j * 32 + 16);
+#pragma unroll
+    for (int m = 0; m < MTT; ++m) {
+      uint32_t af[4] = {0u, 0u, 0u, 0u};
+      if (MT == 0) {
+        if (row_valid) {
+          af[0] = lds32(a0 + j * 32);
+          af[2] = lds32(a0 + j * 32 + 16);
+        }
+      } else {
+        ldmatrix_x4(af[0], af[1], af[2], af[3], a0 + m * 16 * AS + j * 32);
+      }
+      mma_bf16_16816(acc[m], af, b0, b1);
+      if (DUAL) mma_bf16_16816(acc2[m], af, b2, b3);
     }
-    mma_bf16_16816(acc, af, b0, b1);
-    if (DUAL) mma_bf16_16816(acc2, af, b2, b3);
   }
 }
 
-__device__ void gemm_phase(const MegaArgs& a, const Phase& p, unsigned char* smem, uint32_t smem_base, uint32_t& job_base,
-                           Best& best) {
+// a_src == nullptr: the A operand [B, K] is resident in the activation region (row stride
+// (K+8)*2).  Otherwise it is streamed from global memory (row stride K) in KC-wide chunks
+// through two buffers of the activation region, all consumer threads copying.
+template <int MT>
+__device__ void gemm_phase(const MegaArgs& a, const Phase& p, uint32_t smem_base, uint32_t& job_base,
+                           const bf16* a_src, Best (&best)[MT == 0 ? 1 : MT][2]) {
+  constexpr int MTT = MT == 0 ? 1 : MT;
+  constexpr int BPAD = MT == 0 ? 8 : 16 * MT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = a.n_slots, KC = a.KC, RS = (KC + 8) * 2;
-  const uint32_t ring = smem_base + HDR_BYTES + a.act_bytes;
-  const int AS = (p.K + 8) * 2;  // activation row stride in shared memory (bytes)
+  const uint32_t ring = smem_base + a.off_ring, act = smem_base + a.off_act;
+  const bool stream = a_src != nullptr;
+  const int AS = stream ? RS : (p.K + 8) * 2;  // activation row stride in shared memory (bytes)
   const int g = lane >> 2, c = lane & 3;
-  const bool row_valid = g < a.B;
-  const uint32_t a_row = smem_base + HDR_BYTES + g * AS + c * 4;
   const int n_c = units_of_cta(p.units, blockIdx.x, gridDim.x);
   const int nch = (p.K + KC - 1) / KC;
   const int Dq = a.n_q * a.hd, Dkv = a.n_kv * a.hd;
 
+  auto a_chunk_load = [&](int ch) {  // stream mode: rows [0,B) x [ch*KC, +klen) -> buffer ch&1
+    const int k0 = ch * KC, klen = min(KC, p.K - k0), per = klen >> 3;
+    const uint32_t dst = act + (ch & 1) * (BPAD * RS);
+    for (int i = threadIdx.x; i < a.B * per; i += NTC) {
+      const int b = i / per, cc = i - b * per;
+      cp_async16(dst + b * RS + cc * 16, a_src + (size_t)b * p.K + k0 + cc * 8);
+    }
+    cp_async_commit();
+  };
+
   for (int r0 = 0; r0 < n_c; r0 += NW) {
     const int nact = min(NW, n_c - r0);
-    if (warp >= nact) break;
-    const int u = blockIdx.x + (r0 + warp) * gridDim.x;
-    int seg = 0;
-    while (seg + 1 < p.nseg && u >= p.ubeg[seg + 1]) ++seg;
-    const int row0 = (u - p.ubeg[seg]) << 3;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool has = warp < nact;
+    if (!stream && !has) break;  // resident A: idle warps need not take part
+    int seg = 0, row0 = 0;
+    if (has) {
+      const int u = blockIdx.x + (r0 + warp) * gridDim.x;
+      while (seg + 1 < p.nseg && u >= p.ubeg[seg + 1]) ++seg;
+      row0 = (u - p.ubeg[seg]) << 3;
+    }
+    float acc[MTT][4], acc2[MTT][4];
+#pragma unroll
+    for (int m = 0; m < MTT; ++m)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[m][i] = acc2[m][i] = 0.f;
+    if (stream) a_chunk_load(0);
     for (int ch = 0; ch < nch; ++ch) {
-      const uint32_t job = job_base + (uint32_t)(r0 * nch + ch * nact + warp);
-      const uint32_t slot = job % S, par = (job / S) & 1;
       const int k0 = ch * KC;
       const int klen = min(KC, p.K - k0);
-      mbar_wait(smem_base + OFF_FULL + slot * 8, par);
-      if (p.dual)
-        mma_chunk<true>(acc, acc2, ring + slot * a.slot_bytes, a_row + k0 * 2, RS, klen >> 4, row_valid, lane);
-      else
-        mma_chunk<false>(acc, acc2, ring + slot * a.slot_bytes, a_row + k0 * 2, RS, klen >> 4, row_valid, lane);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_base + OFF_EMPTY + slot * 8);
+      if (stream) {
+        if (ch + 1 < nch) {
+          a_chunk_load(ch + 1);
+          cp_async_wait<1>();
+        } else {
+          cp_async_wait<0>();
+        }
+        bar_consumers();
+      }
+      if (has) {
+        const uint32_t job = job_base + (uint32_t)(r0 * nch + ch * nact + warp);
+        const uint32_t slot = job % S, par = (job / S) & 1;
+        while (lds32_volatile(smem_base + OFF_ISSUED) <= job) {
+        }
+        mbar_wait(smem_base + OFF_FULL + slot * 8, par);
+        const uint32_t a_addr = stream ? act + (ch & 1) * (BPAD * RS) : act + k0 * 2;
+        if (p.dual)
+          mma_chunk<MT, true>(acc, acc2, ring + slot * a.slot_bytes, a_addr, AS, RS, klen >> 4, a.B, lane);
+        else
+          mma_chunk<MT, false>(acc, acc2, ring + slot * a.slot_bytes, a_addr, AS, RS, klen >> 4, a.B, lane);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_base + OFF_EMPTY + slot * 8);
+      }
+      if (stream) bar_consumers();  // the buffer is refilled two chunks later
     }
-    // epilogue: c0,c1 -> (token g, n = row0 + 2c + {0,1}); tokens 8..15 do not exist here
-    if (row_valid) {
-      const int n = row0 + c * 2;
-      if (n < p.rows[seg]) {  // rows are multiples of 2 everywhere (checked by the launcher)
-        const float v0 = acc[0], v1 = acc[1];
+    if (!has) continue;
+    // epilogue: c0,c1 -> (token 16m + g, n = row0 + 2c + {0,1}); c2,c3 -> token 16m + g + 8
+    const int n = row0 + c * 2;
+    if (n >= p.rows[seg]) continue;  // rows are even everywhere (checked by the launcher)
+#pragma unroll
+    for (int m = 0; m < MTT; ++m)
+#pragma unroll
+      for (int hr = 0; hr < (MT == 0 ? 1 : 2); ++hr) {
+        const int tok = m * 16 + g + hr * 8;
+        if (tok >= a.B) continue;
+        const float v0 = acc[m][hr * 2], v1 = acc[m][hr * 2 + 1];
         switch (p.kind) {
           case PH_QKV: {
             const int col = (seg == 0 ? 0 : (seg == 1 ? Dq : Dq + Dkv)) + n;
-            *reinterpret_cast<uint32_t*>(a.qkv + (size_t)g * (Dq + 2 * Dkv) + col) = pack2(f2bf(v0), f2bf(v1));
+            *reinterpret_cast<uint32_t*>(a.qkv + (size_t)tok * (Dq + 2 * Dkv) + col) = pack2(f2bf(v0), f2bf(v1));
             break;
           }
           case PH_O:
           case PH_DOWN: {
-            uint32_t* dst = reinterpret_cast<uint32_t*>(a.x + (size_t)g * a.H + n);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(a.x + (size_t)tok * a.H + n);
             const uint32_t old = __ldcg(dst);
             const float y0 = bf2f(f2bf(v0)), y1 = bf2f(f2bf(v1));
             *dst = pack2(f2bf(__fadd_rn(lo2f(old), y0)), f2bf(__fadd_rn(hi2f(old), y1)));
@@ -280,29 +356,29 @@ __device__ void gemm_phase(const MegaArgs& a, const Phase& p, unsigned char* sme
           }
           case PH_GATEUP: {
             const float g0 = bf2f(f2bf(v0)), g1 = bf2f(f2bf(v1));
-            const float u0 = bf2f(f2bf(acc2[0])), u1 = bf2f(f2bf(acc2[1]));
+            const float u0 = bf2f(f2bf(acc2[m][hr * 2])), u1 = bf2f(f2bf(acc2[m][hr * 2 + 1]));
             const float s0 = bf2f(f2bf(silu_ref(g0))), s1 = bf2f(f2bf(silu_ref(g1)));
-            *reinterpret_cast<uint32_t*>(a.h + (size_t)g * a.I + n) =
+            *reinterpret_cast<uint32_t*>(a.h + (size_t)tok * a.I + n) =
                 pack2(f2bf(__fmul_rn(u0, s0)), f2bf(__fmul_rn(u1, s1)));
             break;
           }
           default: {  // PH_LMHEAD
             const bf16 l0 = f2bf(v0), l1 = f2bf(v1);
-            *reinterpret_cast<uint32_t*>(a.logits + (size_t)g * a.V + n) = pack2(l0, l1);
+            *reinterpret_cast<uint32_t*>(a.logits + (size_t)tok * a.V + n) = pack2(l0, l1);
             const float f0 = bf2f(l0), f1 = bf2f(l1);
-            if (f0 > -CUDART_INF_F && cand_better(f0, n, best.v, best.i)) {
-              best.v = f0;
-              best.i = n;
+            Best& bb = best[m][hr];
+            if (f0 > -CUDART_INF_F && cand_better(f0, n, bb.v, bb.i)) {
+              bb.v = f0;
+              bb.i = n;
             }
-            if (f1 > -CUDART_INF_F && cand_better(f1, n + 1, best.v, best.i)) {
-              best.v = f1;
-              best.i = n + 1;
+            if (f1 > -CUDART_INF_F && cand_better(f1, n + 1, bb.v, bb.i)) {
+              bb.v = f1;
+              bb.i = n + 1;
             }
             break;
           }
         }
       }
-    }
   }
   job_base += (uint32_t)(n_c * nch);
 }
@@ -321,15 +397,24 @@ __device__ __forceinline__ void load_rows(uint32_t act, int B, int K, RowPtr row
   bar_consumers();
 }
 
+// norm weight [H] -> shared memory buffer `which` (completes with the next cp.async wait)
+__device__ __forceinline__ void prefetch_norm_w(const MegaArgs& a, uint32_t smem_base, int which, const bf16* w) {
+  const uint32_t dst = smem_base + OFF_WNORM + which * a.H * 2;
+  for (int i = threadIdx.x; i < (a.H >> 3); i += NTC) cp_async16(dst + i * 16, w + i * 8);
+  cp_async_commit();
+}
+
 // RMSNorm of the rows in the activation region, in place (normalization.cu:5-26): the sum
 // of squares is the reference's sequential FFMA chain, one thread per row.
-__device__ void rmsnorm_rows(unsigned char* smem, int B, int H, const bf16* __restrict__ w) {
+__device__ void rmsnorm_rows(const MegaArgs& a, unsigned char* smem, int B, int H, int which) {
   const int AS = (H + 8) * 2;
-  unsigned char* act = smem + HDR_BYTES;
+  unsigned char* act = smem + a.off_act;
+  const bf16* w = reinterpret_cast<const bf16*>(smem + OFF_WNORM + which * H * 2);
   float* rms_s = reinterpret_cast<float*>(smem + OFF_RMS);
   if (threadIdx.x < B) {
     const uint4* row = reinterpret_cast<const uint4*>(act + threadIdx.x * AS);
     float sum = 0.f;
+#pragma unroll 2
     for (int i = 0; i < (H >> 3); ++i) {
       const uint4 v = row[i];
       float f;
@@ -409,13 +494,16 @@ __device__ void attention_phase(const MegaArgs& a, int layer, unsigned char* sme
   const int ntask = per_head ? a.B * a.n_q : a.B * a.n_kv;
   const int tmax = (a.max_kv_len + 3) & ~3;
   const int psz = a.kv.page_size;
-  const MegaLayer& w = a.layers[layer];
+  const MegaLayer& w = reinterpret_cast<const MegaLayer*>(smem + OFF_LAYERS)[layer];
 
-  float* q_s = reinterpret_cast<float*>(smem + HDR_BYTES);          // [hs][HD] fp32
+  float* q_s = reinterpret_cast<float*>(smem + a.off_act);          // [hs][HD] fp32
   bf16* knew = reinterpret_cast<bf16*>(q_s + hs * HD);              // [HD] bf16 (16-byte aligned)
   bf16* vnew = knew + HD;
   float* score = reinterpret_cast<float*>(vnew + HD);               // [hs][tmax]
   int* pages = reinterpret_cast<int*>(score + hs * tmax);
+  const int n_pages_max = a.max_kv_len / psz + 1;
+  unsigned char* vbuf = reinterpret_cast<unsigned char*>(pages) + ((n_pages_max * 4 + 15) & ~15);  // [2][VT][HD] bf16
+  const uint32_t vbuf_u32 = smem_u32(vbuf);
 
   for (int task = blockIdx.x; task < ntask; task += gridDim.x) {
     int b, kvh, h0;
@@ -433,6 +521,17 @@ __device__ void attention_phase(const MegaArgs& a, int layer, unsigned char* sme
     const int n_pages = ps / psz + 1;
     const int* bt = a.block_table + (size_t)a.slot[b] * a.max_pages;
     for (int i = threadIdx.x; i < n_pages; i += NTC) pages[i] = bt[i];
+    auto v_tile_load = [&](int it) {  // cached positions [it*VT, min(ps, it*VT+VT)) of V -> vbuf[it&1]
+      const int t0 = it * VT, tn = min(VT, ps - t0);
+      const uint32_t dst = vbuf_u32 + (it & 1) * (VT * HD * 2);
+      for (int idx = threadIdx.x; idx < tn * (HD / 8); idx += NTC) {
+        const int r = idx / (HD / 8), cc = idx - r * (HD / 8);
+        const int k = t0 + r;
+        cp_async16(dst + r * (HD * 2) + cc * 16, a.kv.chunk(bt[k / psz], layer, 1, kvh) + (size_t)(k % psz) * HD + cc * 8);
+      }
+      cp_async_commit();
+    };
+    v_tile_load(0);  // overlaps q/k-norm, scores and softmax
     const bf16* row = a.qkv + (size_t)b * QKV;
     const float* cos_row = a.cos_t + (size_t)ps * 32 * NP;
     const float* sin_row = a.sin_t + (size_t)ps * 32 * NP;
@@ -479,7 +578,7 @@ __device__ void attention_phase(const MegaArgs& a, int layer, unsigned char* sme
     }
     bar_consumers();
 
-    // softmax + PV: one warp per head (self_attension.cu:94-137)
+    // softmax: one warp per head (self_attension.cu:94-107)
     for (int i = warp; i < hs; i += NW) {
       float* s = score + i * tmax;
       float m = -1e9f;
@@ -501,51 +600,83 @@ __device__ void attention_phase(const MegaArgs& a, int layer, unsigned char* sme
       }
       sum = __shfl_sync(0xffffffffu, sum, 0);
       for (int k = lane; k <= ps; k += 32) s[k] = __fdiv_rn(s[k], sum);
-      __syncwarp();
-      float o[NP][2];
+    }
+    // PV (self_attension.cu:112-137): V streams through shared memory in tiles of VT cached
+    // positions (all consumer threads copy, double buffered); warp i keeps the sequential
+    // fma chain of head i, lane l owning dims 2l, 2l+1 (+64p).
+    float o[2][NP][2];  // heads i = warp and warp + NW of the task (hs <= 2*NW)
 #pragma unroll
-      for (int p = 0; p < NP; ++p) o[p][0] = o[p][1] = 0.f;
-      int k = 0;
-      for (; k + 4 <= ps; k += 4) {  // cached positions 0..ps-1 from the pool
-        uint32_t vv[4][NP];
+    for (int q2 = 0; q2 < 2; ++q2)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const bf16* vp = a.kv.chunk(pages[(k + j) / psz], layer, 1, kvh) + (size_t)((k + j) % psz) * HD;
-#pragma unroll
-          for (int p = 0; p < NP; ++p) vv[j][p] = *reinterpret_cast<const uint32_t*>(vp + 64 * p + 2 * lane);
-        }
-        const float4 pr = *reinterpret_cast<const float4*>(s + k);
-        const float prj[4] = {pr.x, pr.y, pr.z, pr.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int p = 0; p < NP; ++p) {
-            o[p][0] = __fmaf_rn(prj[j], lo2f(vv[j][p]), o[p][0]);
-            o[p][1] = __fmaf_rn(prj[j], hi2f(vv[j][p]), o[p][1]);
-          }
+      for (int p = 0; p < NP; ++p) o[q2][p][0] = o[q2][p][1] = 0.f;
+    const int nt = (ps + VT - 1) / VT;
+    for (int it = 0; it < nt; ++it) {
+      if (it + 1 < nt) {
+        v_tile_load(it + 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
       }
-      for (; k <= ps; ++k) {
-        const bf16* vp = (k == ps) ? vnew : a.kv.chunk(pages[k / psz], layer, 1, kvh) + (size_t)(k % psz) * HD;
-        const float pk = s[k];
+      bar_consumers();
+      const unsigned char* vb = vbuf + (it & 1) * (VT * HD * 2);
+      const int t0 = it * VT, tn = min(VT, ps - t0);
+#pragma unroll
+      for (int q2 = 0; q2 < 2; ++q2) {
+        const int i = warp + q2 * NW;
+        if (i < hs) {
+          const float* s = score + i * tmax + t0;
+          int k = 0;
+          for (; k + 4 <= tn; k += 4) {
+            const float4 pr = *reinterpret_cast<const float4*>(s + k);
+            const float prj[4] = {pr.x, pr.y, pr.z, pr.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int p = 0; p < NP; ++p) {
+                const uint32_t vv = *reinterpret_cast<const uint32_t*>(vb + (k + j) * (HD * 2) + (64 * p + 2 * lane) * 2);
+                o[q2][p][0] = __fmaf_rn(prj[j], lo2f(vv), o[q2][p][0]);
+                o[q2][p][1] = __fmaf_rn(prj[j], hi2f(vv), o[q2][p][1]);
+              }
+          }
+          for (; k < tn; ++k) {
+            const float pk = s[k];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+              const uint32_t vv = *reinterpret_cast<const uint32_t*>(vb + k * (HD * 2) + (64 * p + 2 * lane) * 2);
+              o[q2][p][0] = __fmaf_rn(pk, lo2f(vv), o[q2][p][0]);
+              o[q2][p][1] = __fmaf_rn(pk, hi2f(vv), o[q2][p][1]);
+            }
+          }
+        }
+      }
+      bar_consumers();  // the buffer is refilled two tiles later
+    }
+    __syncwarp();
+#pragma unroll
+    for (int q2 = 0; q2 < 2; ++q2) {
+      const int i = warp + q2 * NW;
+      if (i < hs) {
+        const float pk = score[i * tmax + ps];  // the new position: V from this step's projection
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
-          const uint32_t vv = *reinterpret_cast<const uint32_t*>(vp + 64 * p + 2 * lane);
-          o[p][0] = __fmaf_rn(pk, lo2f(vv), o[p][0]);
-          o[p][1] = __fmaf_rn(pk, hi2f(vv), o[p][1]);
+          const uint32_t vv = *reinterpret_cast<const uint32_t*>(vnew + 64 * p + 2 * lane);
+          o[q2][p][0] = __fmaf_rn(pk, lo2f(vv), o[q2][p][0]);
+          o[q2][p][1] = __fmaf_rn(pk, hi2f(vv), o[q2][p][1]);
         }
+        head_store<NP>(o[q2], a.att + (size_t)b * Dq + (size_t)(h0 + i) * HD, lane);
       }
-      head_store<NP>(o, a.att + (size_t)b * Dq + (size_t)(h0 + i) * HD, lane);
     }
     bar_consumers();  // shared memory is reused by the next task / phase
   }
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int NP>
+template <int NP, int MT>
 __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __grid_constant__ MegaArgs a) {
+  constexpr int MTT = MT == 0 ? 1 : MT;
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t smem_base = smem_u32(smem);
-  const int warp = threadIdx.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = a.n_layers_run > 0 ? min(a.n_layers_run, a.L) : a.L;
   const bool with_head = a.n_layers_run <= 0;
 
@@ -554,17 +685,24 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
       mbar_init(smem_base + OFF_FULL + s * 8, 1);
       mbar_init(smem_base + OFF_EMPTY + s * 8, 1);
     }
+    *reinterpret_cast<volatile uint32_t*>(smem + OFF_ISSUED) = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  {  // layer table -> shared memory (pointer chasing through global memory costs ~1 us per phase)
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.layers);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem + OFF_LAYERS);
+    for (int i = threadIdx.x; i < a.L * (int)(sizeof(MegaLayer) / 4); i += MEGA_THREADS) dst[i] = src[i];
   }
   __syncthreads();
 
   if (warp == NW) {  // producer warp
-    producer_loop(a, smem_base, with_head ? 4 * a.L + 1 : 4 * L);
+    producer_loop(a, smem, smem_base, with_head ? 4 * a.L + 1 : 4 * L);
     return;
   }
 
   // ---- consumers
+  const MegaLayer* layers = reinterpret_cast<const MegaLayer*>(smem + OFF_LAYERS);
   unsigned epoch = 0;
   uint32_t job_base = 0;
   int prof_i = 0;
@@ -572,10 +710,14 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
     if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[prof_i] = globaltimer();
     ++prof_i;
   };
-  const uint32_t act = smem_base + HDR_BYTES;
+  const uint32_t act = smem_base + a.off_act;
   const int H = a.H, Dq = a.n_q * a.hd;
-  Best best{-CUDART_INF_F, -1};
+  Best best[MTT][2];
+#pragma unroll
+  for (int m = 0; m < MTT; ++m) best[m][0] = best[m][1] = Best{-CUDART_INF_F, -1};
+  Phase p;
 
+  prefetch_norm_w(a, smem_base, 0, layers[0].in_ln);
   // embedding rows (embedded_matrix.cu:5-17): x[b] = E[ids[b]]; layer 0 reads E directly
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
     const uint4* src = reinterpret_cast<const uint4*>(a.embed + (size_t)a.ids[b] * H);
@@ -584,42 +726,56 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
   }
   stamp();
   for (int l = 0; l < L; ++l) {
-    const MegaLayer& w = a.layers[l];
-    Phase p;
     // ---- QKV
+    prefetch_norm_w(a, smem_base, 1, layers[l].post_ln);
     if (l == 0)
       load_rows(act, a.B, H, [&](int b) { return a.embed + (size_t)a.ids[b] * H; });
     else
       load_rows(act, a.B, H, [&](int b) { return a.x + (size_t)b * H; });
-    rmsnorm_rows(smem, a.B, H, w.in_ln);
-    make_phase(a, 4 * l + PH_QKV, p);
-    gemm_phase(a, p, smem, smem_base, job_base, best);
+    stamp();
+    rmsnorm_rows(a, smem, a.B, H, 0);
+    stamp();
+    make_phase(a, smem, 4 * l + PH_QKV, p);
+    gemm_phase<MT>(a, p, smem_base, job_base, nullptr, best);
+    stamp();
     grid_sync(a.bar, epoch);
     stamp();
     // ---- attention
-    if (NP == 1)
-      attention_phase<1>(a, l, smem);
-    else
-      attention_phase<NP>(a, l, smem);
+    attention_phase<NP>(a, l, smem);
+    stamp();
     grid_sync(a.bar, epoch);
     stamp();
     // ---- O + residual
     load_rows(act, a.B, Dq, [&](int b) { return a.att + (size_t)b * Dq; });
-    make_phase(a, 4 * l + PH_O, p);
-    gemm_phase(a, p, smem, smem_base, job_base, best);
+    stamp();
+    make_phase(a, smem, 4 * l + PH_O, p);
+    gemm_phase<MT>(a, p, smem_base, job_base, nullptr, best);
+    stamp();
     grid_sync(a.bar, epoch);
     stamp();
     // ---- gate/up + SiLU*up
+    prefetch_norm_w(a, smem_base, 0, l + 1 < a.L ? layers[l + 1].in_ln : a.final_norm);
     load_rows(act, a.B, H, [&](int b) { return a.x + (size_t)b * H; });
-    rmsnorm_rows(smem, a.B, H, w.post_ln);
-    make_phase(a, 4 * l + PH_GATEUP, p);
-    gemm_phase(a, p, smem, smem_base, job_base, best);
+    stamp();
+    rmsnorm_rows(a, smem, a.B, H, 1);
+    stamp();
+    make_phase(a, smem, 4 * l + PH_GATEUP, p);
+    gemm_phase<MT>(a, p, smem_base, job_base, nullptr, best);
+    stamp();
     grid_sync(a.bar, epoch);
     stamp();
     // ---- down + residual
-    load_rows(act, a.B, a.I, [&](int b) { return a.h + (size_t)b * a.I; });
-    make_phase(a, 4 * l + PH_DOWN, p);
-    gemm_phase(a, p, smem, smem_base, job_base, best);
+    if (a.stream_down) {
+      stamp();
+      make_phase(a, smem, 4 * l + PH_DOWN, p);
+      gemm_phase<MT>(a, p, smem_base, job_base, a.h, best);
+    } else {
+      load_rows(act, a.B, a.I, [&](int b) { return a.h + (size_t)b * a.I; });
+      stamp();
+      make_phase(a, smem, 4 * l + PH_DOWN, p);
+      gemm_phase<MT>(a, p, smem_base, job_base, nullptr, best);
+    }
+    stamp();
     grid_sync(a.bar, epoch);
     stamp();
   }
@@ -627,24 +783,32 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
 
   // ---- final norm + lm_head (+ greedy arg-max candidates)
   {
-    Phase p;
     load_rows(act, a.B, H, [&](int b) { return a.x + (size_t)b * H; });
-    rmsnorm_rows(smem, a.B, H, a.final_norm);
-    make_phase(a, 4 * a.L, p);
-    gemm_phase(a, p, smem, smem_base, job_base, best);
-    // candidates: lanes (g, c) of a warp hold token g; reduce over c, then over warps
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int o = 1; o <= 2; o <<= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, best.v, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, best.i, o);
-      if (cand_better(ov, oi, best.v, best.i)) {
-        best.v = ov;
-        best.i = oi;
-      }
-    }
+    stamp();
+    rmsnorm_rows(a, smem, a.B, H, 0);
+    stamp();
+    make_phase(a, smem, 4 * a.L, p);
+    gemm_phase<MT>(a, p, smem_base, job_base, nullptr, best);
+    stamp();
+    // candidates: lanes (g, c) of a warp hold tokens 16m + g (+8); reduce over c, then over warps
     MegaCand* cs = reinterpret_cast<MegaCand*>(smem + OFF_CAND);
-    if ((lane & 3) == 0 && (lane >> 2) < MAX_ROWS) cs[warp * MAX_ROWS + (lane >> 2)] = MegaCand{best.v, best.i};
+#pragma unroll
+    for (int m = 0; m < MTT; ++m)
+#pragma unroll
+      for (int hr = 0; hr < (MT == 0 ? 1 : 2); ++hr) {
+        Best bb = best[m][hr];
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bb.v, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bb.i, o);
+          if (cand_better(ov, oi, bb.v, bb.i)) {
+            bb.v = ov;
+            bb.i = oi;
+          }
+        }
+        const int tok = m * 16 + (lane >> 2) + hr * 8;
+        if ((lane & 3) == 0 && tok < MAX_ROWS) cs[warp * MAX_ROWS + tok] = MegaCand{bb.v, bb.i};
+      }
     bar_consumers();
     if (threadIdx.x < a.B) {
       float bv = cs[threadIdx.x].val;
@@ -663,7 +827,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
   }
   // ---- arg-max over the CTAs' candidates + step bookkeeping (advance_kernel)
   if (a.greedy && warp == 0) {
-    const int lane = threadIdx.x & 31;
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
       float bv = -CUDART_INF_F;
       int bi = -1;
@@ -699,25 +862,37 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
 }
 
 struct Geom {
-  int KC, slot_bytes, act_bytes, n_slots;
+  int KC, slot_bytes, act_bytes, n_slots, off_act, off_ring, mt, stream_down;
   size_t smem;
 };
 
-bool mega_geometry(int H, int I, int n_q, int n_kv, int hd, int B, int max_kv_len, int grid, Geom* g) {
+bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int grid, Geom* g) {
   const int Dq = n_q * hd;
-  if ((H % 32) || (I % 32) || (Dq % 32) || (hd != 64 && hd != 128 && hd != 256)) return false;
-  if (B < 1 || B > MAX_ROWS || n_q % n_kv) return false;
+  if ((H % 32) || (I % 32) || (Dq % 32) || (hd != 64 && hd != 128)) return false;
+  if (B < 1 || B > MAX_ROWS || n_q % n_kv || n_q / n_kv > 2 * NW || L > MAX_LAYERS) return false;
   const int nch = (H + 511) / 512;
   int KC = ((H + nch - 1) / nch + 31) & ~31;
-  const int Kmax = std::max(H, std::max(I, Dq));
-  int act = B * (Kmax + 8) * 2;
+  if (const char* kv = getenv("QIE_MEGA_KC")) {  // tuning knob: k elements per weight tile
+    const int v = atoi(kv);
+    if (v >= 32 && v <= 4096 && v % 32 == 0) KC = v;
+  }
+  const int mt = B <= 8 ? 0 : (B <= 16 ? 1 : (B <= 32 ? 2 : 4));
+  const int bpad = mt == 0 ? 8 : 16 * mt;
+  const int rows_a = mt == 0 ? B : bpad;  // rows the A fragments may touch
+  const int res_h = rows_a * (std::max(H, Dq) + 8) * 2;
+  const int res_i = rows_a * (I + 8) * 2;
+  const int strm = 2 * bpad * (KC + 8) * 2;
+  const int stream_down = res_i > 48 * 1024;
+  int act = std::max(res_h, stream_down ? strm : res_i);
   const int hs = (B * n_q <= grid) ? 1 : n_q / n_kv;
   const int tmax = (max_kv_len + 3) & ~3;
-  const int attn = hs * hd * 4 + 2 * hd * 2 + hs * tmax * 4 + (max_kv_len / 1 + 16) * 4;  // pages: <= one per position
+  const int attn = hs * hd * 4 + 2 * hd * 2 + hs * tmax * 4 + (max_kv_len + 32) * 4 /* pages: <= one per position */ +
+                   2 * VT * hd * 2;
   act = std::max(act, attn);
   act = (act + 127) & ~127;
+  const int off_act = (OFF_WNORM + 2 * H * 2 + 127) & ~127;
   const int slot = 16 * (KC + 8) * 2;
-  const int budget = 227 * 1024 - HDR_BYTES - act;
+  const int budget = 227 * 1024 - off_act - act;
   int S = budget / slot;
   if (S > MAX_SLOTS) S = MAX_SLOTS;
   if (S < 3) return false;
@@ -725,35 +900,52 @@ bool mega_geometry(int H, int I, int n_q, int n_kv, int hd, int B, int max_kv_le
   g->slot_bytes = slot;
   g->act_bytes = act;
   g->n_slots = S;
-  g->smem = (size_t)HDR_BYTES + act + (size_t)S * slot;
+  g->off_act = off_act;
+  g->off_ring = off_act + act;
+  g->mt = mt;
+  g->stream_down = stream_down;
+  g->smem = (size_t)off_act + act + (size_t)S * slot;
   return true;
 }
 
 }  // namespace
 
-int decode_mega_max_rows(int H, int I, int n_q, int n_kv, int hd, int max_kv_len) {
+int decode_mega_max_rows(int H, int I, int L, int n_q, int n_kv, int hd, int max_kv_len) {
   Geom g;
   int best = 0;
   for (int B = 1; B <= MAX_ROWS; ++B)
-    if (mega_geometry(H, I, n_q, n_kv, hd, B, max_kv_len, 148, &g)) best = B;
+    if (mega_geometry(H, I, L, n_q, n_kv, hd, B, max_kv_len, 148, &g)) best = B;
   return best;
 }
 
-int decode_mega_prof_slots(int L) { return 5 * L + 4; }
+bool decode_mega_supports(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int num_sms) {
+  Geom g;
+  return mega_geometry(H, I, L, n_q, n_kv, hd, B, max_kv_len, num_sms, &g);
+}
+
+int decode_mega_prof_slots(int L) { return 16 * L + 8; }
+
+template <int NP>
+static void (*pick_kernel(int mt))(MegaArgs) {
+  switch (mt) {
+    case 0: return decode_mega_kernel<NP, 0>;
+    case 1: return decode_mega_kernel<NP, 1>;
+    case 2: return decode_mega_kernel<NP, 2>;
+    default: return decode_mega_kernel<NP, 4>;
+  }
+}
 
 cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st) {
   Geom g;
-  if (!mega_geometry(a.H, a.I, a.n_q, a.n_kv, a.hd, a.B, a.max_kv_len, num_sms, &g)) return cudaErrorInvalidValue;
+  if (!mega_geometry(a.H, a.I, a.L, a.n_q, a.n_kv, a.hd, a.B, a.max_kv_len, num_sms, &g)) return cudaErrorInvalidValue;
   a.KC = g.KC;
   a.slot_bytes = g.slot_bytes;
   a.act_bytes = g.act_bytes;
   a.n_slots = g.n_slots;
-  void (*kern)(MegaArgs) = nullptr;
-  switch (a.hd) {
-    case 64: kern = decode_mega_kernel<1>; break;
-    case 128: kern = decode_mega_kernel<2>; break;
-    default: kern = decode_mega_kernel<4>; break;
-  }
+  a.off_act = g.off_act;
+  a.off_ring = g.off_ring;
+  a.stream_down = g.stream_down;
+  void (*kern)(MegaArgs) = a.hd == 64 ? pick_kernel<1>(g.mt) : pick_kernel<2>(g.mt);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(a.bar, 0, sizeof(unsigned), st);

@@ -293,7 +293,7 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
 bool decode_uses_mega(const qie_engine* e, int n, int max_kv_len) {
   if (!e->use_mega || e->opts.numerics != QIE_NUMERICS_REFERENCE_ORDER || e->capture || !e->mega_layers_d) return false;
   const qie_config& c = e->cfg;
-  return n <= decode_mega_max_rows(c.hidden, c.inter, c.n_q, c.n_kv, c.head_dim, max_kv_len);
+  return decode_mega_supports(c.hidden, c.inter, c.layers, c.n_q, c.n_kv, c.head_dim, n, max_kv_len, e->num_sms);
 }
 
 cudaError_t forward_decode_mega(qie_engine* e, int n, int max_kv_len, float temperature) {

@@ -152,7 +152,7 @@ cudaError_t launch_advance(int* pos, int* ids, const int* sampled, int n, int* s
 
 // ---------------------------------------------------------------- persistent decode step
 // decode_mega.cu: ONE cooperative launch runs a whole decode step (all layers, lm_head,
-// greedy arg-max, bookkeeping) for up to 8 sequences in reference-order arithmetic.
+// greedy arg-max, bookkeeping) for up to 64 sequences in reference-order arithmetic.
 struct MegaLayer {
   const bf16 *in_ln, *q, *k, *v, *o, *q_norm, *k_norm, *post_ln, *gate, *up, *down;
 };
@@ -181,10 +181,11 @@ struct MegaArgs {
   int greedy, advance;
   int n_layers_run;                  // debug: stop after this many layers (0 = all, then lm_head)
   // geometry, filled by the launcher
-  int KC, n_slots, slot_bytes, act_bytes;
+  int KC, n_slots, slot_bytes, act_bytes, off_act, off_ring, stream_down;
 };
 // max rows the persistent kernel accepts for this model shape (0 = shape unsupported)
-int decode_mega_max_rows(int H, int I, int n_q, int n_kv, int hd, int max_kv_len);
+int decode_mega_max_rows(int H, int I, int L, int n_q, int n_kv, int hd, int max_kv_len);
+bool decode_mega_supports(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int num_sms);
 int decode_mega_prof_slots(int L);
 cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st);
 

@@ -196,7 +196,7 @@ class Engine:
 
     def mega_prof(self):
         """device timestamps (ns) of the last profiled persistent-kernel step"""
-        out = np.zeros(5 * self.config.layers + 3, np.uint64)
+        out = np.zeros(16 * self.config.layers + 6, np.uint64)
         n = check(self._L.qie_mega_prof_read(self._h, out.ctypes.data, len(out)))
         return out[:n]
 

@@ -26,7 +26,9 @@ def _kv_snapshot(eng):
     return eng.read_activation("kv", n)
 
 
-def _run(eng, n_seq, n_prompt, n_steps, use_mega):
+def _run(qie, arch, n_seq, n_prompt, n_steps, use_mega):
+    eng = qie.Engine(synthetic=arch, seed=1234, context=512, max_batch_tokens=64, use_graph=False, kv_bytes=32 << 20)
+    assert eng.uses_mega(n_seq, n_prompt + n_seq + n_steps)
     eng.set_int("mega", int(use_mega))
     seqs, toks = [], []
     for i in range(n_seq):
@@ -40,24 +42,21 @@ def _run(eng, n_seq, n_prompt, n_steps, use_mega):
         hist.append(cur.copy())
         logits.append(eng.read_activation("logits", n_seq * eng.config.vocab))
     kv = _kv_snapshot(eng)
-    for s in seqs:
-        eng.free_sequence(s)
+    eng.close()
     return np.stack(hist), logits, kv
 
 
 @pytest.mark.parametrize("arch,n_seq,n_prompt,n_steps", [
     ("tiny", 1, 3, 20), ("small", 1, 9, 40), ("small", 3, 5, 24), ("small128", 2, 7, 20), ("small", 8, 4, 12),
+    ("small", 16, 4, 10), ("small", 40, 3, 8), ("small128", 33, 3, 6), ("tiny", 64, 2, 6),
 ])
 def test_mega_equals_per_operator_path(qie, arch, n_seq, n_prompt, n_steps):
-    eng = qie.Engine(synthetic=arch, seed=1234, context=512, max_batch_tokens=64, use_graph=False)
-    assert eng.uses_mega(n_seq, n_prompt + n_seq + n_steps)
-    want_t, want_l, want_kv = _run(eng, n_seq, n_prompt, n_steps, use_mega=False)
-    got_t, got_l, got_kv = _run(eng, n_seq, n_prompt, n_steps, use_mega=True)
+    want_t, want_l, want_kv = _run(qie, arch, n_seq, n_prompt, n_steps, use_mega=False)
+    got_t, got_l, got_kv = _run(qie, arch, n_seq, n_prompt, n_steps, use_mega=True)
     for i in range(n_steps):
         assert np.array_equal(got_l[i], want_l[i]), f"logits differ at step {i}"
     assert np.array_equal(got_t, want_t)
     assert np.array_equal(got_kv, want_kv)
-    eng.close()
 
 
 @pytest.mark.parametrize("n_layers", [1, 2])
@@ -87,6 +86,32 @@ def test_mega_layer_activations(qie, n_layers):
     for k in ("att", "h", "x"):
         assert np.array_equal(outs[1][k], outs[0][k]), k
     eng.close()
+
+
+def test_mega_qwen05b_batch64_long_context(qie):
+    """BASELINE configs[1] shape: 0.5B-arch, 64 sequences, synthetic KV of 300..363 positions
+    (several V tiles, ragged lengths) -- tokens and logits equal the per-operator path."""
+    cfg = qie.make_config("qwen2.5-0.5b")
+    res = {}
+    for mode in (0, 1):
+        eng = qie.Engine(synthetic="qwen2.5-0.5b", seed=1234, max_seqs=65, max_batch_tokens=64, use_graph=False,
+                         kv_bytes=64 * 512 * qie.kv_bytes_per_pos(cfg) + (64 << 20))
+        eng.set_int("mega", mode)
+        seqs = []
+        for i in range(64):
+            s = eng.new_sequence()
+            eng.fill_synthetic(s, 300 + i, seed=i)
+            seqs.append(s)
+        assert eng.uses_mega(64, 400) == bool(mode)
+        tok = (np.arange(64, dtype=np.int32) * 977 + 5) % cfg.vocab
+        hist = []
+        for _ in range(3):
+            tok = eng.decode_step(seqs, tok)
+            hist.append(tok.copy())
+        res[mode] = (np.stack(hist), eng.read_activation("logits", 64 * cfg.vocab))
+        eng.close()
+    assert np.array_equal(res[1][1], res[0][1])
+    assert np.array_equal(res[1][0], res[0][0])
 
 
 def test_mega_graph_replay_and_topk(qie):

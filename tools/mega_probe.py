@@ -44,9 +44,11 @@ if a.mega and eng.uses_mega(a.batch, a.ctx + a.steps + 16):
     ts = eng.mega_prof().astype(np.int64)
     L = cfg.layers
     d = np.diff(ts)
-    per = d[:5 * L].reshape(L, 5)
-    names = ["rms+qkv", "attention", "o", "rms+gateup", "down"]
-    print("phase us (mean over layers):", {n: round(float(per[:, i].mean()) / 1e3, 2) for i, n in enumerate(names)})
-    print("layers total us", round(float(per.sum()) / 1e3, 1), "lm_head us", round(float(d[5 * L]) / 1e3, 1),
-          "sample us", round(float(d[5 * L + 1]) / 1e3, 1), "whole us", round(float(ts[-1] - ts[0]) / 1e3, 1))
+    per = d[:16 * L].reshape(L, 16)
+    names = ["qkv.load", "qkv.norm", "qkv.gemm", "qkv.bar", "att.run", "att.bar", "o.load", "o.gemm", "o.bar",
+             "gu.load", "gu.norm", "gu.gemm", "gu.bar", "dn.load", "dn.gemm", "dn.bar"]
+    print("phase us (mean over layers, CTA 0):", {n: round(float(per[1:, i].mean()) / 1e3, 2) for i, n in enumerate(names)})
+    hn = ["head.load", "head.norm", "head.gemm", "head.bar", "sample"]
+    print("layers total us", round(float(per.sum()) / 1e3, 1), {n: round(float(d[16 * L + i]) / 1e3, 1) for i, n in enumerate(hn)},
+          "whole us", round(float(ts[-1] - ts[0]) / 1e3, 1))
 eng.close()
