@@ -244,7 +244,10 @@ const char* qie_kernel_kind_name(int kind);
  * HOST memory: [0] start, then 16 per layer (QKV: rows loaded, normed, GEMM done, barrier;
  * attention: done, barrier; O: loaded, GEMM, barrier; gate/up: loaded, normed, GEMM, barrier;
  * down: loaded, GEMM, barrier), then lm_head (loaded, normed, GEMM, barrier) and sampling;
- * returns the number of values (16*layers + 6).
+ * the buffer holds 16*layers + 8 slots of globaltimer ns followed by as many SM cycle-counter
+ * values taken at the same points (16*layers + 6 of each are used), then 10 cycle counters:
+ * per GEMM phase kind (qkv, o, gate/up, down, lm_head) the cycles warp 0 of CTA 0 waited for
+ * weights and spent in its MMA loop; returns the values copied.
  * qie_engine_read_activation copies an activation buffer of the last forward to HOST
  * memory (names: x qkv att h logits sampled kv); returns the byte count copied. */
 int qie_engine_set_int(qie_engine* e, const char* key, long value);

@@ -34,7 +34,7 @@
 namespace qie {
 namespace {
 
-constexpr int NW = 8;                         // consumer warps
+constexpr int NW = 7;                         // consumer warps (7 + the producer warp = 256 threads: 255 registers per thread)
 constexpr int NTC = NW * 32;                  // consumer threads
 constexpr int MEGA_THREADS = NTC + 32;        // + producer warp
 constexpr int MAX_SLOTS = 32;
@@ -42,7 +42,7 @@ constexpr int VT = 128;                       // cached positions per V tile in 
 constexpr int MAX_ROWS = 64;                  // rows (sequences) per launch
 constexpr int MAX_LAYERS = 64;
 // shared-memory header
-constexpr int OFF_FULL = 0, OFF_EMPTY = 256, OFF_ISSUED = 512, OFF_RMS = 768, OFF_CAND = 1024;
+constexpr int OFF_FULL = 0, OFF_EMPTY = 256, OFF_ISSUED = 512, OFF_DBG = 528, OFF_RMS = 768, OFF_CAND = 1024;  // OFF_DBG: 10 x u64 cycle counters
 constexpr int OFF_LAYERS = OFF_CAND + NW * MAX_ROWS * 8;                 // MegaLayer[MAX_LAYERS]
 constexpr int OFF_WNORM = OFF_LAYERS + MAX_LAYERS * (int)sizeof(MegaLayer);  // 2 x [H] bf16 norm weights
 static_assert(sizeof(MegaLayer) == 88, "MegaLayer layout");
@@ -59,23 +59,31 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t addr) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
+constexpr long long SPIN_LIMIT = 4000000000ll;  // ~2 s of SM clocks: trap instead of hanging the GPU
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "MB_WAIT_%=:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra MB_DONE_%=;\n"
-      "bra MB_WAIT_%=;\n"
-      "MB_DONE_%=:\n"
-      "}\n" ::"r"(addr),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
       : "memory");
+  return ok != 0;
 }
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(mbar)
-               : "memory");
+__device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
+  if (mbar_try(addr, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(addr, parity))
+    if (clock64() - t0 > SPIN_LIMIT) __trap();
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* map, uint32_t mbar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(mbar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(NTC) : "memory"); }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
@@ -107,50 +115,54 @@ __device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& epoch) {
     epoch += gridDim.x;
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
     unsigned v;
+    const long long t0 = clock64();
     do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (clock64() - t0 > SPIN_LIMIT) __trap();
     } while (v < epoch);
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
   }
   bar_consumers();
 }
 
 // ---------------------------------------------------------------- GEMM phase description
 struct Phase {
-  const bf16* W[3];
-  const bf16* W2;
+  const TensorMap2D* W[3];  // weight tensor maps (3-D view, box = 8 rows x KC)
+  const TensorMap2D* W2;
   int rows[3];
   int ubeg[4];
   int nseg, K, dual, units, kind;
+  int n_c, nch;  // units of THIS CTA, chunks per unit (host-precomputed tables: no integer division here)
 };
 
-__device__ __forceinline__ void make_phase(const MegaArgs& a, const unsigned char* smem, int idx, Phase& p) {
+__device__ __forceinline__ void make_phase(const MegaArgs& a, int idx, Phase& p) {
   const int hd = a.hd, Dq = a.n_q * hd, Dkv = a.n_kv * hd;
   p.W2 = nullptr;
   p.dual = 0;
   p.nseg = 1;
   if (idx >= 4 * a.L) {
     p.kind = PH_LMHEAD;
-    p.W[0] = a.lm_head;
+    p.W[0] = a.wmaps + 7 * a.L;
     p.rows[0] = a.V;
     p.K = a.H;
   } else {
-    const MegaLayer& w = reinterpret_cast<const MegaLayer*>(smem + OFF_LAYERS)[idx >> 2];
+    const TensorMap2D* m = a.wmaps + 7 * (idx >> 2);
     p.kind = idx & 3;
     switch (p.kind) {
       case PH_QKV:
         p.nseg = 3;
-        p.W[0] = w.q; p.W[1] = w.k; p.W[2] = w.v;
+        p.W[0] = m; p.W[1] = m + 1; p.W[2] = m + 2;
         p.rows[0] = Dq; p.rows[1] = Dkv; p.rows[2] = Dkv;
         p.K = a.H;
         break;
       case PH_O:
-        p.W[0] = w.o; p.rows[0] = a.H; p.K = Dq;
+        p.W[0] = m + 3; p.rows[0] = a.H; p.K = Dq;
         break;
       case PH_GATEUP:
-        p.W[0] = w.gate; p.W2 = w.up; p.rows[0] = a.I; p.K = a.H; p.dual = 1;
+        p.W[0] = m + 4; p.W2 = m + 5; p.rows[0] = a.I; p.K = a.H; p.dual = 1;
         break;
       default:
-        p.W[0] = w.down; p.rows[0] = a.H; p.K = a.I;
+        p.W[0] = m + 6; p.rows[0] = a.H; p.K = a.I;
         break;
     }
   }
@@ -161,52 +173,69 @@ __device__ __forceinline__ void make_phase(const MegaArgs& a, const unsigned cha
   }
   p.ubeg[p.nseg] = u;
   p.units = u;
+  p.n_c = a.ph_q[p.kind] + ((int)blockIdx.x < a.ph_r[p.kind] ? 1 : 0);
+  p.nch = a.ph_nch[p.kind];
 }
 
-__device__ __forceinline__ int units_of_cta(int units, int cta, int grid) {
-  return cta < units ? (units - cta + grid - 1) / grid : 0;
-}
+struct RingPos {  // position of a job in the weight ring, advanced without divisions
+  uint32_t job, slot, par;
+  __device__ __forceinline__ void advance(uint32_t jobs, uint32_t dslot, uint32_t dpar, uint32_t S) {  // dslot = jobs % S
+    job += jobs;
+    slot += dslot;
+    par ^= dpar;
+    if (slot >= S) {
+      slot -= S;
+      par ^= 1;
+    }
+  }
+  __device__ __forceinline__ void step(uint32_t d, uint32_t S) {  // small d (< a few S)
+    job += d;
+    slot += d;
+    while (slot >= S) {
+      slot -= S;
+      par ^= 1;
+    }
+  }
+};
 
 // ---------------------------------------------------------------- producer
-// Walks every GEMM phase of the step in order; per phase the units of this CTA in rounds of
-// NW (one unit per consumer warp), chunk-major inside a round so the warps advance together.
+// One elected thread walks every GEMM phase of the step in order; per phase the units of this
+// CTA in rounds of NW (one unit per consumer warp), chunk-major inside a round so the warps
+// advance together.  A job = ONE TMA request (two for gate+up): a box of 8 weight rows x KC
+// k-elements lands in the slot as [k-block][row][64] with the 128-byte swizzle.
 // `issued` (shared memory) tells consumers that job j's mbarrier phase has been armed: a
 // consumer that is a whole ring lap ahead must not test the parity of an older phase.
-__device__ void producer_loop(const MegaArgs& a, const unsigned char* smem, uint32_t smem_base, int n_phases) {
-  const int lane = threadIdx.x & 31;
-  const int S = a.n_slots, KC = a.KC, RS = (KC + 8) * 2;
+__device__ __forceinline__ void producer_loop(const MegaArgs& a, uint32_t smem_base, int n_phases) {
+  if ((threadIdx.x & 31) != 0) return;
+  const uint32_t S = a.n_slots;
+  const int KC = a.KC;
   const uint32_t ring = smem_base + a.off_ring;
-  uint32_t job = 0;
+  const uint32_t box_bytes = (uint32_t)(8 * KC * 2);
+  uint32_t job = 0, slot = 0, par = 0;
   for (int ph = 0; ph < n_phases; ++ph) {
     Phase p;
-    make_phase(a, smem, ph, p);
-    const int n_c = units_of_cta(p.units, blockIdx.x, gridDim.x);
-    const int nch = (p.K + KC - 1) / KC;
-    const int nrows = p.dual ? 16 : 8;
+    make_phase(a, ph, p);
+    const int n_c = p.n_c, nch = p.nch;
     for (int r0 = 0; r0 < n_c; r0 += NW) {
       const int nact = min(NW, n_c - r0);
       for (int ch = 0; ch < nch; ++ch) {
-        const int k0 = ch * KC;
-        const int klen = min(KC, p.K - k0);
-        for (int s = 0; s < nact; ++s, ++job) {
+        for (int s = 0; s < nact; ++s) {
           const int u = blockIdx.x + (r0 + s) * gridDim.x;
           int seg = 0;
           while (seg + 1 < p.nseg && u >= p.ubeg[seg + 1]) ++seg;
           const int row0 = (u - p.ubeg[seg]) << 3;
-          const uint32_t slot = job % S, par = (job / S) & 1;
           const uint32_t full = smem_base + OFF_FULL + slot * 8, empty = smem_base + OFF_EMPTY + slot * 8;
-          if (lane == 0) {
-            mbar_wait(empty, par ^ 1);
-            mbar_expect_tx(full, (uint32_t)(nrows * klen * 2));
-            __threadfence_block();
-            sts32_volatile(smem_base + OFF_ISSUED, job + 1);
-          }
-          __syncwarp();
-          if (lane < nrows) {
-            const bf16* Wm = (lane < 8) ? p.W[seg] : p.W2;
-            int gr = row0 + (lane & 7);
-            if (gr >= p.rows[seg]) gr = p.rows[seg] - 1;  // duplicate rows are never stored
-            bulk_g2s(ring + slot * a.slot_bytes + lane * RS, Wm + (size_t)gr * p.K + k0, (uint32_t)(klen * 2), full);
+          mbar_wait(empty, par ^ 1);
+          mbar_expect_tx(full, p.dual ? 2 * box_bytes : box_bytes);  // out-of-range rows / k-blocks are zero-filled
+          __threadfence_block();
+          sts32_volatile(smem_base + OFF_ISSUED, job + 1);
+          const uint32_t dst = ring + slot * a.slot_bytes;
+          tma_load_3d(dst, p.W[seg], full, 0, row0, ch * (KC / 64));
+          if (p.dual) tma_load_3d(dst + box_bytes, p.W2, full, 0, row0, ch * (KC / 64));
+          ++job;
+          if (++slot == S) {
+            slot = 0;
+            par ^= 1;
           }
         }
       }
@@ -223,36 +252,88 @@ struct Best {
 // One warp accumulates its unit (8 weight rows, or 8 gate + 8 up rows) over one chunk for
 // all token tiles.  MT == 0: up to 8 tokens, A fragments by predicated 32-bit LDS (rows
 // 8..15 of the MMA tile are register zeros).  MT >= 1: 16*MT token rows by ldmatrix.
+// The accumulation is a dependent HMMA chain per output tile (k ascending: the reference's
+// order); measured on B200 the dependent HMMA.16816 latency is 20.7 cycles and the issue
+// interval 8 cycles per SM sub-partition (tools/ubench/hmma_lat.cu), so the fragment loads
+// (LDSM/LDS, ~33 cycles) are software-pipelined one group of k-steps ahead in registers and
+// never sit on the chain.
+template <int MT, bool DUAL>
+struct Frags {
+  static constexpr int MTT = MT == 0 ? 1 : MT;
+  static constexpr int GS = MT <= 1 ? 4 : (MT == 2 ? 2 : 1);  // k16 steps per group
+  uint32_t b[GS][DUAL ? 4 : 2];
+  uint32_t a[GS][MTT][4];  // MT == 0: [1] and [3] (token rows 8..15) stay zero
+};
+
 template <int MT, bool DUAL>
 __device__ __forceinline__ void mma_chunk(float (&acc)[MT == 0 ? 1 : MT][4], float (&acc2)[MT == 0 ? 1 : MT][4],
-                                          uint32_t slot_addr, uint32_t a_addr, int AS, int RS, int nk16, int B,
+                                          uint32_t slot_addr, uint32_t a_addr, int AS, int up_off, int nk16, int B,
                                           int lane) {
-  constexpr int MTT = MT == 0 ? 1 : MT;
-  // ldmatrix source rows: lanes 0-7 rows 0-7 @k, 8-15 rows 0-7 @k+8 (x2); DUAL adds rows 8-15 (up)
-  const uint32_t baddr = slot_addr + (lane & 7) * RS + ((lane >> 3) & 1) * 16 + (DUAL ? ((lane >> 4) & 1) * 8 * RS : 0);
+  using F = Frags<MT, DUAL>;
+  constexpr int MTT = F::MTT, GS = F::GS;
+  // weight tile: [k-block of 64][row 0-7][64] bf16, 16-byte chunk c of row r stored at c ^ r;
+  // ldmatrix lanes 0-7 -> rows @k, 8-15 -> rows @k+8 (x2); DUAL: lanes 16-31 -> the up tile
+  const int br = lane & 7, bh = (lane >> 3) & 1;
+  const uint32_t brow = slot_addr + br * 128 + (DUAL ? ((lane >> 4) & 1) * up_off : 0);
+  uint32_t boff[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) boff[s] = (uint32_t)((((s << 1) + bh) ^ br) << 4);
   const bool row_valid = (lane >> 2) < B;
   const uint32_t a0 = MT == 0 ? a_addr + (lane >> 2) * AS + (lane & 3) * 4
                               : a_addr + ((lane & 7) + ((lane >> 3) & 1) * 8) * AS + (lane >> 4) * 16;
-#pragma unroll 4
-  for (int j = 0; j < nk16; ++j) {
-    uint32_t b0, b1, b2 = 0, b3 = 0;
-    if (DUAL)
-      ldmatrix_x4(b0, b1, b2, b3, baddr + j * 32);
-    else
-      ldmatrix_x2(b0, b1, baddr + j * 32);
+  auto load = [&](F& f, int j0) {
 #pragma unroll
-    for (int m = 0; m < MTT; ++m) {
-      uint32_t af[4] = {0u, 0u, 0u, 0u};
-      if (MT == 0) {
-        if (row_valid) {
-          af[0] = lds32(a0 + j * 32);
-          af[2] = lds32(a0 + j * 32 + 16);
+    for (int s = 0; s < GS; ++s) {
+      const int j = j0 + s;
+      const uint32_t baddr = brow + (uint32_t)(j >> 2) * 1024u + boff[(GS == 4) ? s : (j & 3)];
+      if (DUAL)
+        ldmatrix_x4(f.b[s][0], f.b[s][1], f.b[s][2], f.b[s][3], baddr);
+      else
+        ldmatrix_x2(f.b[s][0], f.b[s][1], baddr);
+#pragma unroll
+      for (int m = 0; m < MTT; ++m) {
+        if (MT == 0) {
+          if (row_valid) {  // invalid token rows keep the zeros they were initialised with
+            f.a[s][m][0] = lds32(a0 + j * 32);
+            f.a[s][m][2] = lds32(a0 + j * 32 + 16);
+          }
+        } else {
+          ldmatrix_x4(f.a[s][m][0], f.a[s][m][1], f.a[s][m][2], f.a[s][m][3], a0 + m * 16 * AS + j * 32);
         }
-      } else {
-        ldmatrix_x4(af[0], af[1], af[2], af[3], a0 + m * 16 * AS + j * 32);
       }
-      mma_bf16_16816(acc[m], af, b0, b1);
-      if (DUAL) mma_bf16_16816(acc2[m], af, b2, b3);
+    }
+  };
+  auto compute = [&](const F& f) {
+#pragma unroll
+    for (int s = 0; s < GS; ++s)
+#pragma unroll
+      for (int m = 0; m < MTT; ++m) {
+        mma_bf16_16816(acc[m], f.a[s][m], f.b[s][0], f.b[s][1]);
+        if (DUAL) mma_bf16_16816(acc2[m], f.a[s][m], f.b[s][2], f.b[s][3]);
+      }
+  };
+  F f0, f1;
+  if (MT == 0) {
+    // Token rows 8..15 of the MMA tile are zero.  The zeros are made opaque to the compiler so
+    // that each {a0, 0, a2, 0} operand quad stays allocated across the loop: with literal zeros
+    // ptxas re-creates the quad every k-step on top of a just-written accumulator, which puts
+    // HMMA -> MOV -> LDS -> HMMA (~60 cycles) on the dependent chain instead of 20.7.
+#pragma unroll
+    for (int s = 0; s < GS; ++s)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        asm volatile("mov.u32 %0, 0;" : "=r"(f0.a[s][0][i]));
+        asm volatile("mov.u32 %0, 0;" : "=r"(f1.a[s][0][i]));
+      }
+  }
+  load(f0, 0);  // nk16 is a multiple of 4 (chunks are whole 64-wide k blocks), GS divides 4
+  for (int j0 = 0; j0 < nk16; j0 += 2 * GS) {
+    const bool more1 = j0 + GS < nk16;
+    if (more1) load(f1, j0 + GS);
+    compute(f0);
+    if (more1) {
+      if (j0 + 2 * GS < nk16) load(f0, j0 + 2 * GS);
+      compute(f1);
     }
   }
 }
@@ -261,19 +342,21 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[MT == 0 ? 1 : MT][4], flo
 // (K+8)*2).  Otherwise it is streamed from global memory (row stride K) in KC-wide chunks
 // through two buffers of the activation region, all consumer threads copying.
 template <int MT>
-__device__ void gemm_phase(const MegaArgs& a, const Phase& p, uint32_t smem_base, uint32_t& job_base,
-                           const bf16* a_src, Best (&best)[MT == 0 ? 1 : MT][2]) {
+__device__ __forceinline__ void gemm_phase(const MegaArgs& a, const Phase& p, uint32_t smem_base, RingPos& base,
+                                           const bf16* a_src, Best (&best)[MT == 0 ? 1 : MT][2],
+                                           unsigned char* dbg_smem) {
   constexpr int MTT = MT == 0 ? 1 : MT;
   constexpr int BPAD = MT == 0 ? 8 : 16 * MT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int S = a.n_slots, KC = a.KC, RS = (KC + 8) * 2;
+  const uint32_t S = a.n_slots;
+  const int KC = a.KC, RS = (KC + 8) * 2;  // RS: row stride of a streamed A chunk
   const uint32_t ring = smem_base + a.off_ring, act = smem_base + a.off_act;
   const bool stream = a_src != nullptr;
   const int AS = stream ? RS : (p.K + 8) * 2;  // activation row stride in shared memory (bytes)
   const int g = lane >> 2, c = lane & 3;
-  const int n_c = units_of_cta(p.units, blockIdx.x, gridDim.x);
-  const int nch = (p.K + KC - 1) / KC;
+  const int n_c = p.n_c, nch = p.nch;
   const int Dq = a.n_q * a.hd, Dkv = a.n_kv * a.hd;
+  RingPos rnd = base;  // first job of the current round
 
   auto a_chunk_load = [&](int ch) {  // stream mode: rows [0,B) x [ch*KC, +klen) -> buffer ch&1
     const int k0 = ch * KC, klen = min(KC, p.K - k0), per = klen >> 3;
@@ -285,7 +368,7 @@ __device__ void gemm_phase(const MegaArgs& a, const Phase& p, uint32_t smem_base
     cp_async_commit();
   };
 
-  for (int r0 = 0; r0 < n_c; r0 += NW) {
+  for (int r0 = 0; r0 < n_c; r0 += NW, rnd.advance(NW * nch, a.ph_round_slot[p.kind], a.ph_round_par[p.kind], S)) {
     const int nact = min(NW, n_c - r0);
     const bool has = warp < nact;
     if (!stream && !has) break;  // resident A: idle warps need not take part
@@ -301,6 +384,9 @@ __device__ void gemm_phase(const MegaArgs& a, const Phase& p, uint32_t smem_base
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[m][i] = acc2[m][i] = 0.f;
     if (stream) a_chunk_load(0);
+    // ring position of this warp's first job of the round; consecutive chunks are nact jobs apart
+    RingPos me = rnd;
+    me.step(warp, S);
     for (int ch = 0; ch < nch; ++ch) {
       const int k0 = ch * KC;
       const int klen = min(KC, p.K - k0);
@@ -314,18 +400,28 @@ __device__ void gemm_phase(const MegaArgs& a, const Phase& p, uint32_t smem_base
         bar_consumers();
       }
       if (has) {
-        const uint32_t job = job_base + (uint32_t)(r0 * nch + ch * nact + warp);
-        const uint32_t slot = job % S, par = (job / S) & 1;
-        while (lds32_volatile(smem_base + OFF_ISSUED) <= job) {
+        const long long tw0 = clock64();
+        if (lds32_volatile(smem_base + OFF_ISSUED) <= me.job) {
+          const long long t0 = clock64();
+          while (lds32_volatile(smem_base + OFF_ISSUED) <= me.job)
+            if (clock64() - t0 > SPIN_LIMIT) __trap();
         }
-        mbar_wait(smem_base + OFF_FULL + slot * 8, par);
+        const uint32_t slot = me.slot;
+        mbar_wait(smem_base + OFF_FULL + slot * 8, me.par);
+        const long long tw1 = clock64();
         const uint32_t a_addr = stream ? act + (ch & 1) * (BPAD * RS) : act + k0 * 2;
         if (p.dual)
-          mma_chunk<MT, true>(acc, acc2, ring + slot * a.slot_bytes, a_addr, AS, RS, klen >> 4, a.B, lane);
+          mma_chunk<MT, true>(acc, acc2, ring + slot * a.slot_bytes, a_addr, AS, 8 * KC * 2, klen >> 4, a.B, lane);
         else
-          mma_chunk<MT, false>(acc, acc2, ring + slot * a.slot_bytes, a_addr, AS, RS, klen >> 4, a.B, lane);
+          mma_chunk<MT, false>(acc, acc2, ring + slot * a.slot_bytes, a_addr, AS, 0, klen >> 4, a.B, lane);
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_base + OFF_EMPTY + slot * 8);
+        if (a.prof && threadIdx.x == 0 && blockIdx.x == 0) {  // profiling: cycles this warp waited for weights / spent in the MMA loop
+          unsigned long long* dbg = reinterpret_cast<unsigned long long*>(dbg_smem);
+          dbg[p.kind * 2] += (unsigned long long)(tw1 - tw0);
+          dbg[p.kind * 2 + 1] += (unsigned long long)(clock64() - tw1);
+        }
+        me.step(nact, S);
       }
       if (stream) bar_consumers();  // the buffer is refilled two chunks later
     }
@@ -380,7 +476,8 @@ __device__ void gemm_phase(const MegaArgs& a, const Phase& p, uint32_t smem_base
         }
       }
   }
-  job_base += (uint32_t)(n_c * nch);
+  const int cls = (int)blockIdx.x < a.ph_r[p.kind] ? 1 : 0;
+  base.advance((uint32_t)(n_c * nch), a.ph_adv_slot[p.kind][cls], a.ph_adv_par[p.kind][cls], S);
 }
 
 // ---------------------------------------------------------------- consumer: activations
@@ -406,7 +503,7 @@ __device__ __forceinline__ void prefetch_norm_w(const MegaArgs& a, uint32_t smem
 
 // RMSNorm of the rows in the activation region, in place (normalization.cu:5-26): the sum
 // of squares is the reference's sequential FFMA chain, one thread per row.
-__device__ void rmsnorm_rows(const MegaArgs& a, unsigned char* smem, int B, int H, int which) {
+__device__ __forceinline__ void rmsnorm_rows(const MegaArgs& a, unsigned char* smem, int B, int H, int which) {
   const int AS = (H + 8) * 2;
   unsigned char* act = smem + a.off_act;
   const bf16* w = reinterpret_cast<const bf16*>(smem + OFF_WNORM + which * H * 2);
@@ -414,18 +511,30 @@ __device__ void rmsnorm_rows(const MegaArgs& a, unsigned char* smem, int B, int 
   if (threadIdx.x < B) {
     const uint4* row = reinterpret_cast<const uint4*>(act + threadIdx.x * AS);
     float sum = 0.f;
-#pragma unroll 2
-    for (int i = 0; i < (H >> 3); ++i) {
-      const uint4 v = row[i];
-      float f;
-      f = lo2f(v.x); sum = __fmaf_rn(f, f, sum);
-      f = hi2f(v.x); sum = __fmaf_rn(f, f, sum);
-      f = lo2f(v.y); sum = __fmaf_rn(f, f, sum);
-      f = hi2f(v.y); sum = __fmaf_rn(f, f, sum);
-      f = lo2f(v.z); sum = __fmaf_rn(f, f, sum);
-      f = hi2f(v.z); sum = __fmaf_rn(f, f, sum);
-      f = lo2f(v.w); sum = __fmaf_rn(f, f, sum);
-      f = hi2f(v.w); sum = __fmaf_rn(f, f, sum);
+    const int nv = H >> 3;
+    // the FFMA chain is 4 cycles per element; keep the next 4 vectors in flight so the
+    // shared-memory latency never sits on the chain
+    uint4 cur[4], nxt[4];  // H % 32 == 0 (launcher) -> nv % 4 == 0
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cur[j] = row[j];
+    for (int i = 0; i < nv; i += 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) nxt[j] = row[min(i + 4 + j, nv - 1)];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 v = cur[j];
+        float f;
+        f = lo2f(v.x); sum = __fmaf_rn(f, f, sum);
+        f = hi2f(v.x); sum = __fmaf_rn(f, f, sum);
+        f = lo2f(v.y); sum = __fmaf_rn(f, f, sum);
+        f = hi2f(v.y); sum = __fmaf_rn(f, f, sum);
+        f = lo2f(v.z); sum = __fmaf_rn(f, f, sum);
+        f = hi2f(v.z); sum = __fmaf_rn(f, f, sum);
+        f = lo2f(v.w); sum = __fmaf_rn(f, f, sum);
+        f = hi2f(v.w); sum = __fmaf_rn(f, f, sum);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
     }
     rms_s[threadIdx.x] = __fsqrt_rn(__fadd_rn(__fdiv_rn(sum, (float)H), 1e-04f));
   }
@@ -484,7 +593,7 @@ __device__ __forceinline__ void head_load_cg(float (&x)[NP][2], const bf16* src,
 // query group sharing the K/V stream.  q/k-norm + RoPE + the KV store of the new position
 // are done here (replaces 2x qkNorm, 2x RoPE, kv_copy_layer_to_cache_decode).
 template <int NP>
-__device__ void attention_phase(const MegaArgs& a, int layer, unsigned char* smem) {
+__device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, unsigned char* smem) {
   constexpr int HD = 64 * NP;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Gq = a.n_q / a.n_kv;
@@ -686,6 +795,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
       mbar_init(smem_base + OFF_EMPTY + s * 8, 1);
     }
     *reinterpret_cast<volatile uint32_t*>(smem + OFF_ISSUED) = 0u;
+    for (int i = 0; i < 10; ++i) reinterpret_cast<unsigned long long*>(smem + OFF_DBG)[i] = 0ull;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -697,17 +807,20 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
   __syncthreads();
 
   if (warp == NW) {  // producer warp
-    producer_loop(a, smem, smem_base, with_head ? 4 * a.L + 1 : 4 * L);
+    producer_loop(a, smem_base, with_head ? 4 * a.L + 1 : 4 * L);
     return;
   }
 
   // ---- consumers
   const MegaLayer* layers = reinterpret_cast<const MegaLayer*>(smem + OFF_LAYERS);
   unsigned epoch = 0;
-  uint32_t job_base = 0;
+  RingPos ring_pos{0u, 0u, 0u};
   int prof_i = 0;
   auto stamp = [&]() {
-    if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[prof_i] = globaltimer();
+    if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {
+      a.prof[prof_i] = globaltimer();
+      a.prof[a.prof_stride + prof_i] = (unsigned long long)clock64();
+    }
     ++prof_i;
   };
   const uint32_t act = smem_base + a.off_act;
@@ -715,7 +828,6 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
   Best best[MTT][2];
 #pragma unroll
   for (int m = 0; m < MTT; ++m) best[m][0] = best[m][1] = Best{-CUDART_INF_F, -1};
-  Phase p;
 
   prefetch_norm_w(a, smem_base, 0, layers[0].in_ln);
   // embedding rows (embedded_matrix.cu:5-17): x[b] = E[ids[b]]; layer 0 reads E directly
@@ -725,106 +837,83 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
     for (int i = threadIdx.x; i < (H >> 3); i += NTC) dst[i] = src[i];
   }
   stamp();
-  for (int l = 0; l < L; ++l) {
-    // ---- QKV
-    prefetch_norm_w(a, smem_base, 1, layers[l].post_ln);
-    if (l == 0)
-      load_rows(act, a.B, H, [&](int b) { return a.embed + (size_t)a.ids[b] * H; });
-    else
-      load_rows(act, a.B, H, [&](int b) { return a.x + (size_t)b * H; });
-    stamp();
-    rmsnorm_rows(a, smem, a.B, H, 0);
-    stamp();
-    make_phase(a, smem, 4 * l + PH_QKV, p);
-    gemm_phase<MT>(a, p, smem_base, job_base, nullptr, best);
-    stamp();
-    grid_sync(a.bar, epoch);
-    stamp();
-    // ---- attention
-    attention_phase<NP>(a, l, smem);
-    stamp();
-    grid_sync(a.bar, epoch);
-    stamp();
-    // ---- O + residual
-    load_rows(act, a.B, Dq, [&](int b) { return a.att + (size_t)b * Dq; });
-    stamp();
-    make_phase(a, smem, 4 * l + PH_O, p);
-    gemm_phase<MT>(a, p, smem_base, job_base, nullptr, best);
-    stamp();
-    grid_sync(a.bar, epoch);
-    stamp();
-    // ---- gate/up + SiLU*up
-    prefetch_norm_w(a, smem_base, 0, l + 1 < a.L ? layers[l + 1].in_ln : a.final_norm);
-    load_rows(act, a.B, H, [&](int b) { return a.x + (size_t)b * H; });
-    stamp();
-    rmsnorm_rows(a, smem, a.B, H, 1);
-    stamp();
-    make_phase(a, smem, 4 * l + PH_GATEUP, p);
-    gemm_phase<MT>(a, p, smem_base, job_base, nullptr, best);
-    stamp();
-    grid_sync(a.bar, epoch);
-    stamp();
-    // ---- down + residual
-    if (a.stream_down) {
+  // One loop over the GEMM phases (4 per layer, then lm_head) with a single inlined copy of
+  // every stage, so kernel arguments stay in the constant bank and the code stays small.
+  const int n_idx = with_head ? 4 * a.L + 1 : 4 * L;
+  for (int idx = 0; idx < n_idx; ++idx) {
+    const int kind = idx < 4 * a.L ? (idx & 3) : PH_LMHEAD;
+    const int l = idx >> 2;
+    const bf16* a_src = nullptr;
+    if (kind == PH_O) {
+      // ---- attention, then O + residual
+      attention_phase<NP>(a, l, smem);
       stamp();
-      make_phase(a, smem, 4 * l + PH_DOWN, p);
-      gemm_phase<MT>(a, p, smem_base, job_base, a.h, best);
+      grid_sync(a.bar, epoch);
+      stamp();
+      load_rows(act, a.B, Dq, [&](int b) { return a.att + (size_t)b * Dq; });
+      stamp();
+    } else if (kind == PH_DOWN) {
+      // ---- down + residual
+      if (a.stream_down)
+        a_src = a.h;
+      else
+        load_rows(act, a.B, a.I, [&](int b) { return a.h + (size_t)b * a.I; });
+      stamp();
     } else {
-      load_rows(act, a.B, a.I, [&](int b) { return a.h + (size_t)b * a.I; });
+      // ---- QKV / gate+up / lm_head: RMSNorm of the residual stream in front
+      const int which = kind == PH_GATEUP ? 1 : 0;
+      if (kind == PH_QKV)
+        prefetch_norm_w(a, smem_base, 1, layers[l].post_ln);
+      else if (kind == PH_GATEUP)
+        prefetch_norm_w(a, smem_base, 0, l + 1 < a.L ? layers[l + 1].in_ln : a.final_norm);
+      const bool from_embed = idx == 0;
+      load_rows(act, a.B, H, [&](int b) { return from_embed ? a.embed + (size_t)a.ids[b] * H : a.x + (size_t)b * H; });
       stamp();
-      make_phase(a, smem, 4 * l + PH_DOWN, p);
-      gemm_phase<MT>(a, p, smem_base, job_base, nullptr, best);
+      rmsnorm_rows(a, smem, a.B, H, which);
+      stamp();
     }
+    Phase p;
+    make_phase(a, idx, p);
+    gemm_phase<MT>(a, p, smem_base, ring_pos, a_src, best, smem + OFF_DBG);
     stamp();
+    if (kind == PH_LMHEAD) {
+      // candidates: lanes (g, c) of a warp hold tokens 16m + g (+8); reduce over c, then over warps
+      MegaCand* cs = reinterpret_cast<MegaCand*>(smem + OFF_CAND);
+#pragma unroll
+      for (int m = 0; m < MTT; ++m)
+#pragma unroll
+        for (int hr = 0; hr < (MT == 0 ? 1 : 2); ++hr) {
+          Best bb = best[m][hr];
+#pragma unroll
+          for (int o = 1; o <= 2; o <<= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, bb.v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bb.i, o);
+            if (cand_better(ov, oi, bb.v, bb.i)) {
+              bb.v = ov;
+              bb.i = oi;
+            }
+          }
+          const int tok = m * 16 + (lane >> 2) + hr * 8;
+          if ((lane & 3) == 0 && tok < MAX_ROWS) cs[warp * MAX_ROWS + tok] = MegaCand{bb.v, bb.i};
+        }
+      bar_consumers();
+      if (threadIdx.x < a.B) {
+        float bv = cs[threadIdx.x].val;
+        int bi = cs[threadIdx.x].idx;
+        for (int wv = 1; wv < NW; ++wv) {
+          const MegaCand o = cs[wv * MAX_ROWS + threadIdx.x];
+          if (cand_better(o.val, o.idx, bv, bi)) {
+            bv = o.val;
+            bi = o.idx;
+          }
+        }
+        a.cand[(size_t)blockIdx.x * a.B + threadIdx.x] = MegaCand{bv, bi};
+      }
+    }
     grid_sync(a.bar, epoch);
     stamp();
   }
   if (!with_head) return;
-
-  // ---- final norm + lm_head (+ greedy arg-max candidates)
-  {
-    load_rows(act, a.B, H, [&](int b) { return a.x + (size_t)b * H; });
-    stamp();
-    rmsnorm_rows(a, smem, a.B, H, 0);
-    stamp();
-    make_phase(a, smem, 4 * a.L, p);
-    gemm_phase<MT>(a, p, smem_base, job_base, nullptr, best);
-    stamp();
-    // candidates: lanes (g, c) of a warp hold tokens 16m + g (+8); reduce over c, then over warps
-    MegaCand* cs = reinterpret_cast<MegaCand*>(smem + OFF_CAND);
-#pragma unroll
-    for (int m = 0; m < MTT; ++m)
-#pragma unroll
-      for (int hr = 0; hr < (MT == 0 ? 1 : 2); ++hr) {
-        Best bb = best[m][hr];
-#pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, bb.v, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, bb.i, o);
-          if (cand_better(ov, oi, bb.v, bb.i)) {
-            bb.v = ov;
-            bb.i = oi;
-          }
-        }
-        const int tok = m * 16 + (lane >> 2) + hr * 8;
-        if ((lane & 3) == 0 && tok < MAX_ROWS) cs[warp * MAX_ROWS + tok] = MegaCand{bb.v, bb.i};
-      }
-    bar_consumers();
-    if (threadIdx.x < a.B) {
-      float bv = cs[threadIdx.x].val;
-      int bi = cs[threadIdx.x].idx;
-      for (int wv = 1; wv < NW; ++wv) {
-        const MegaCand o = cs[wv * MAX_ROWS + threadIdx.x];
-        if (cand_better(o.val, o.idx, bv, bi)) {
-          bv = o.val;
-          bi = o.idx;
-        }
-      }
-      a.cand[(size_t)blockIdx.x * a.B + threadIdx.x] = MegaCand{bv, bi};
-    }
-    grid_sync(a.bar, epoch);
-    stamp();
-  }
   // ---- arg-max over the CTAs' candidates + step bookkeeping (advance_kernel)
   if (a.greedy && warp == 0) {
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
@@ -859,6 +948,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
     }
   }
   stamp();
+  if (a.prof && blockIdx.x == 0 && threadIdx.x == 0)
+    for (int i = 0; i < 10; ++i) a.prof[2 * a.prof_stride + i] = reinterpret_cast<unsigned long long*>(smem + OFF_DBG)[i];
 }
 
 struct Geom {
@@ -866,16 +957,20 @@ struct Geom {
   size_t smem;
 };
 
-bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int grid, Geom* g) {
-  const int Dq = n_q * hd;
-  if ((H % 32) || (I % 32) || (Dq % 32) || (hd != 64 && hd != 128)) return false;
-  if (B < 1 || B > MAX_ROWS || n_q % n_kv || n_q / n_kv > 2 * NW || L > MAX_LAYERS) return false;
+int kc_for(int H) {
   const int nch = (H + 511) / 512;
-  int KC = ((H + nch - 1) / nch + 31) & ~31;
+  int KC = ((H + nch - 1) / nch + 63) & ~63;
   if (const char* kv = getenv("QIE_MEGA_KC")) {  // tuning knob: k elements per weight tile
     const int v = atoi(kv);
-    if (v >= 32 && v <= 4096 && v % 32 == 0) KC = v;
+    if (v >= 64 && v <= 4096 && v % 64 == 0) KC = v;
   }
+  return KC;
+}
+
+bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int grid, int KC, Geom* g) {
+  const int Dq = n_q * hd;
+  if ((H % 64) || (I % 64) || (Dq % 64) || (hd != 64 && hd != 128) || KC < 64 || (KC % 64)) return false;
+  if (B < 1 || B > MAX_ROWS || n_q % n_kv || n_q / n_kv > 2 * NW || L > MAX_LAYERS) return false;
   const int mt = B <= 8 ? 0 : (B <= 16 ? 1 : (B <= 32 ? 2 : 4));
   const int bpad = mt == 0 ? 8 : 16 * mt;
   const int rows_a = mt == 0 ? B : bpad;  // rows the A fragments may touch
@@ -889,41 +984,35 @@ bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int ma
   const int attn = hs * hd * 4 + 2 * hd * 2 + hs * tmax * 4 + (max_kv_len + 32) * 4 /* pages: <= one per position */ +
                    2 * VT * hd * 2;
   act = std::max(act, attn);
-  act = (act + 127) & ~127;
   const int off_act = (OFF_WNORM + 2 * H * 2 + 127) & ~127;
-  const int slot = 16 * (KC + 8) * 2;
-  const int budget = 227 * 1024 - off_act - act;
+  const int off_ring = (off_act + act + 1023) & ~1023;  // swizzled TMA tiles: 1024-byte aligned slots
+  const int slot = 16 * KC * 2;                          // gate + up boxes of 8 rows x KC
+  const int budget = 227 * 1024 - off_ring;
   int S = budget / slot;
   if (S > MAX_SLOTS) S = MAX_SLOTS;
   if (S < 3) return false;
   g->KC = KC;
   g->slot_bytes = slot;
-  g->act_bytes = act;
+  g->act_bytes = off_ring - off_act;
   g->n_slots = S;
   g->off_act = off_act;
-  g->off_ring = off_act + act;
+  g->off_ring = off_ring;
   g->mt = mt;
   g->stream_down = stream_down;
-  g->smem = (size_t)off_act + act + (size_t)S * slot;
+  g->smem = (size_t)off_ring + (size_t)S * slot;
   return true;
 }
 
 }  // namespace
 
-int decode_mega_max_rows(int H, int I, int L, int n_q, int n_kv, int hd, int max_kv_len) {
+int decode_mega_kc(int H) { return kc_for(H); }
+
+bool decode_mega_supports(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int num_sms, int KC) {
   Geom g;
-  int best = 0;
-  for (int B = 1; B <= MAX_ROWS; ++B)
-    if (mega_geometry(H, I, L, n_q, n_kv, hd, B, max_kv_len, 148, &g)) best = B;
-  return best;
+  return mega_geometry(H, I, L, n_q, n_kv, hd, B, max_kv_len, num_sms, KC, &g);
 }
 
-bool decode_mega_supports(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int num_sms) {
-  Geom g;
-  return mega_geometry(H, I, L, n_q, n_kv, hd, B, max_kv_len, num_sms, &g);
-}
-
-int decode_mega_prof_slots(int L) { return 16 * L + 8; }
+int decode_mega_prof_slots(int L) { return 2 * (16 * L + 8) + 10; }
 
 template <int NP>
 static void (*pick_kernel(int mt))(MegaArgs) {
@@ -937,14 +1026,32 @@ static void (*pick_kernel(int mt))(MegaArgs) {
 
 cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st) {
   Geom g;
-  if (!mega_geometry(a.H, a.I, a.L, a.n_q, a.n_kv, a.hd, a.B, a.max_kv_len, num_sms, &g)) return cudaErrorInvalidValue;
-  a.KC = g.KC;
+  if (!mega_geometry(a.H, a.I, a.L, a.n_q, a.n_kv, a.hd, a.B, a.max_kv_len, num_sms, a.KC, &g)) return cudaErrorInvalidValue;
   a.slot_bytes = g.slot_bytes;
   a.act_bytes = g.act_bytes;
   a.n_slots = g.n_slots;
   a.off_act = g.off_act;
   a.off_ring = g.off_ring;
   a.stream_down = g.stream_down;
+  {  // per phase kind: units of a CTA (q, +1 for the first r CTAs), chunks, and ring advances modulo the slot count
+    const int Dq = a.n_q * a.hd, Dkv = a.n_kv * a.hd;
+    const int units[5] = {(Dq + 7) / 8 + 2 * ((Dkv + 7) / 8), (a.H + 7) / 8, (a.I + 7) / 8, (a.H + 7) / 8, (a.V + 7) / 8};
+    const int Ks[5] = {a.H, Dq, a.H, a.I, a.H};
+    const int S = g.n_slots;
+    for (int k = 0; k < 5; ++k) {
+      a.ph_q[k] = units[k] / num_sms;
+      a.ph_r[k] = units[k] % num_sms;
+      a.ph_nch[k] = (Ks[k] + a.KC - 1) / a.KC;
+      for (int cls = 0; cls < 2; ++cls) {
+        const int jobs = (a.ph_q[k] + cls) * a.ph_nch[k];
+        a.ph_adv_slot[k][cls] = jobs % S;
+        a.ph_adv_par[k][cls] = (jobs / S) & 1;
+      }
+      const int rj = NW * a.ph_nch[k];
+      a.ph_round_slot[k] = rj % S;
+      a.ph_round_par[k] = (rj / S) & 1;
+    }
+  }
   void (*kern)(MegaArgs) = a.hd == 64 ? pick_kernel<1>(g.mt) : pick_kernel<2>(g.mt);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return e;

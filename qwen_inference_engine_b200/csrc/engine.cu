@@ -293,7 +293,7 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
 bool decode_uses_mega(const qie_engine* e, int n, int max_kv_len) {
   if (!e->use_mega || e->opts.numerics != QIE_NUMERICS_REFERENCE_ORDER || e->capture || !e->mega_layers_d) return false;
   const qie_config& c = e->cfg;
-  return decode_mega_supports(c.hidden, c.inter, c.layers, c.n_q, c.n_kv, c.head_dim, n, max_kv_len, e->num_sms);
+  return decode_mega_supports(c.hidden, c.inter, c.layers, c.n_q, c.n_kv, c.head_dim, n, max_kv_len, e->num_sms, e->mega_kc);
 }
 
 cudaError_t forward_decode_mega(qie_engine* e, int n, int max_kv_len, float temperature) {
@@ -307,6 +307,8 @@ cudaError_t forward_decode_mega(qie_engine* e, int n, int max_kv_len, float temp
   a.hd = c.head_dim;
   a.V = c.vocab;
   a.layers = e->mega_layers_d;
+  a.wmaps = e->mega_wmaps_d;
+  a.KC = e->mega_kc;
   a.embed = e->embed;
   a.final_norm = e->final_norm;
   a.lm_head = e->lm_head;
@@ -330,6 +332,7 @@ cudaError_t forward_decode_mega(qie_engine* e, int n, int max_kv_len, float temp
   a.sampled = e->sampled_d;
   a.bar = e->mega_bar_d;
   a.prof = e->mega_prof_on ? e->mega_prof_d : nullptr;
+  a.prof_stride = 16 * c.layers + 8;
   a.greedy = e->topk == 1;
   a.advance = 1;
   a.n_layers_run = e->mega_layers_run;

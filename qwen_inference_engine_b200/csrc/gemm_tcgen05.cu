@@ -381,6 +381,23 @@ cudaError_t make_tensor_map_2d(TensorMap2D* out, const bf16* base, int rows, int
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// Weight matrix [rows, K] viewed as a 3-D tensor {64 k-elements, rows, K/64 k-blocks} so that
+// ONE TMA request moves a box of 8 rows x kc k-elements (8 x kc x 2 bytes) into shared
+// memory as [k-block][row][64] with the 128-byte swizzle (decode_mega.cu weight ring).
+cudaError_t make_tensor_map_w3d(TensorMap2D* out, const bf16* base, int rows, int K, int kc) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return cudaErrorNotSupported;
+  if ((K % 64) || (kc % 64) || kc / 64 > 256) return cudaErrorInvalidValue;
+  cuuint64_t dims[3] = {64, (cuuint64_t)rows, (cuuint64_t)(K / 64)};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, 128};
+  cuuint32_t box[3] = {64, 8, (cuuint32_t)(kc / 64)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 template <int BN>
 static cudaError_t launch_bn(const TcGemm& t, const TcArgs& g, int token_tiles, cudaStream_t st) {
   constexpr int STAGE_BYTES = BM * BK * 2 + BN * BK * 2;

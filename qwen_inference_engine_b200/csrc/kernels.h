@@ -116,6 +116,7 @@ struct TensorMap2D {
   alignas(64) unsigned char opaque[128];  // CUtensorMap
 };
 cudaError_t make_tensor_map_2d(TensorMap2D* out, const bf16* base, int rows, int K, int box_rows);
+cudaError_t make_tensor_map_w3d(TensorMap2D* out, const bf16* base, int rows, int K, int kc);
 int tc_token_tile(int M);
 struct TcGemm {
   const TensorMap2D* w[3];  // weight maps, box rows = 128
@@ -163,6 +164,7 @@ struct MegaCand {
 struct MegaArgs {
   int H, I, L, n_q, n_kv, hd, V;
   const MegaLayer* layers;  // device array [L]
+  const TensorMap2D* wmaps; // device array [7*L + 1]: q k v o gate up down per layer, then lm_head (make_tensor_map_w3d)
   const bf16 *embed, *final_norm, *lm_head;
   const float *cos_t, *sin_t;
   int B;  // decode rows, one token per sequence
@@ -177,15 +179,18 @@ struct MegaArgs {
   MegaCand* cand;                    // [grid, B] per-CTA arg-max candidates
   int* sampled;                      // [B]
   unsigned* bar;                     // grid barrier counter, zeroed by the launcher
-  unsigned long long* prof;          // optional: globaltimer at every phase boundary (CTA 0)
+  unsigned long long* prof;          // optional: globaltimer at every phase boundary (CTA 0), then clock64 at +prof_stride
+  int prof_stride;
   int greedy, advance;
   int n_layers_run;                  // debug: stop after this many layers (0 = all, then lm_head)
-  // geometry, filled by the launcher
-  int KC, n_slots, slot_bytes, act_bytes, off_act, off_ring, stream_down;
+  int KC;  // k elements per weight tile = box depth of wmaps (decode_mega_kc at engine setup)
+  // geometry, filled by the launcher (ph_*: per GEMM phase kind qkv/o/gate+up/down/lm_head)
+  int ph_q[5], ph_r[5], ph_nch[5], ph_adv_slot[5][2], ph_adv_par[5][2], ph_round_slot[5], ph_round_par[5];
+  int n_slots, slot_bytes, act_bytes, off_act, off_ring, stream_down;
 };
 // max rows the persistent kernel accepts for this model shape (0 = shape unsupported)
-int decode_mega_max_rows(int H, int I, int L, int n_q, int n_kv, int hd, int max_kv_len);
-bool decode_mega_supports(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int num_sms);
+int decode_mega_kc(int H);  // k elements per weight tile (box depth of the weight tensor maps)
+bool decode_mega_supports(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int num_sms, int KC);
 int decode_mega_prof_slots(int L);
 cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st);
 

@@ -196,9 +196,11 @@ class Engine:
 
     def mega_prof(self):
         """device timestamps (ns) of the last profiled persistent-kernel step"""
-        out = np.zeros(16 * self.config.layers + 6, np.uint64)
-        n = check(self._L.qie_mega_prof_read(self._h, out.ctypes.data, len(out)))
-        return out[:n]
+        n = 16 * self.config.layers + 8
+        out = np.zeros(2 * n + 10, np.uint64)
+        check(self._L.qie_mega_prof_read(self._h, out.ctypes.data, len(out)))
+        self.mega_gemm_cycles = out[2 * n:]  # per GEMM phase kind: (cycles waiting for weights, cycles in the MMA loop)
+        return out[:n - 2], out[n:2 * n - 2]  # (ns, SM cycles) at the 16*layers + 6 stamp points
 
     def read_activation(self, name, n_elems, dtype=np.uint16):
         out = np.zeros(n_elems, dtype)

@@ -41,8 +41,12 @@ print("tokens", out[-1][:4])
 if a.mega and eng.uses_mega(a.batch, a.ctx + a.steps + 16):
     eng.set_int("mega_prof", 1)
     eng.decode_run(seqs, out[-1], 3)
-    ts = eng.mega_prof().astype(np.int64)
+    ts, cyc = eng.mega_prof()
+    ts, cyc = ts.astype(np.int64), cyc.astype(np.int64)
+    print("SM clock during the step: %.0f MHz" % ((cyc[-1] - cyc[0]) / max(1, ts[-1] - ts[0]) * 1e3))
     L = cfg.layers
+    gc = eng.mega_gemm_cycles.astype(np.int64).reshape(5, 2)
+    print("CTA0 warp0 cycles (wait for weights, MMA loop) per step:", {k: (int(gc[i, 0]), int(gc[i, 1])) for i, k in enumerate(["qkv", "o", "gateup", "down", "lm_head"])})
     d = np.diff(ts)
     per = d[:16 * L].reshape(L, 16)
     names = ["qkv.load", "qkv.norm", "qkv.gemm", "qkv.bar", "att.run", "att.bar", "o.load", "o.gemm", "o.bar",
