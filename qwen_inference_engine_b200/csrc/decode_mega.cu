@@ -42,7 +42,7 @@ constexpr int VT = 128;                       // cached positions per V tile in 
 constexpr int MAX_ROWS = 64;                  // rows (sequences) per launch
 constexpr int MAX_LAYERS = 64;
 // shared-memory header
-constexpr int OFF_FULL = 0, OFF_EMPTY = 256, OFF_ISSUED = 512, OFF_DBG = 528, OFF_RMS = 768, OFF_CAND = 1024;  // OFF_DBG: 10 x u64 cycle counters
+constexpr int OFF_FULL = 0, OFF_EMPTY = 256, OFF_ISSUED = 512, OFF_DBG = 528, OFF_REL = 640, OFF_RMS = 768, OFF_CAND = 1024;  // OFF_DBG: 10 x u64 cycle counters; OFF_REL: u32 per slot
 constexpr int OFF_LAYERS = OFF_CAND + NW * MAX_ROWS * 8;                 // MegaLayer[MAX_LAYERS]
 constexpr int OFF_WNORM = OFF_LAYERS + MAX_LAYERS * (int)sizeof(MegaLayer);  // 2 x [H] bf16 norm weights
 static_assert(sizeof(MegaLayer) == 88, "MegaLayer layout");
@@ -132,7 +132,7 @@ struct Phase {
   int rows[3];
   int ubeg[4];
   int nseg, K, dual, units, kind;
-  int n_c, nch;  // units of THIS CTA, chunks per unit (host-precomputed tables: no integer division here)
+  int n_c, nch, nu;  // units of THIS CTA, chunks per unit, units per round (host-precomputed tables)
 };
 
 __device__ __forceinline__ void make_phase(const MegaArgs& a, int idx, Phase& p) {
@@ -175,6 +175,7 @@ __device__ __forceinline__ void make_phase(const MegaArgs& a, int idx, Phase& p)
   p.units = u;
   p.n_c = a.ph_q[p.kind] + ((int)blockIdx.x < a.ph_r[p.kind] ? 1 : 0);
   p.nch = a.ph_nch[p.kind];
+  p.nu = a.ph_nu[p.kind];
 }
 
 struct RingPos {  // position of a job in the weight ring, advanced without divisions
@@ -216,8 +217,8 @@ __device__ __forceinline__ void producer_loop(const MegaArgs& a, uint32_t smem_b
     Phase p;
     make_phase(a, ph, p);
     const int n_c = p.n_c, nch = p.nch;
-    for (int r0 = 0; r0 < n_c; r0 += NW) {
-      const int nact = min(NW, n_c - r0);
+    for (int r0 = 0; r0 < n_c; r0 += p.nu) {
+      const int nact = min(p.nu, n_c - r0);
       for (int ch = 0; ch < nch; ++ch) {
         for (int s = 0; s < nact; ++s) {
           const int u = blockIdx.x + (r0 + s) * gridDim.x;
@@ -257,7 +258,7 @@ struct Best {
 // interval 8 cycles per SM sub-partition (tools/ubench/hmma_lat.cu), so the fragment loads
 // (LDSM/LDS, ~33 cycles) are software-pipelined one group of k-steps ahead in registers and
 // never sit on the chain.
-template <int MT, bool DUAL>
+template <int MT, bool DUAL>  // MT here = token tiles handled by ONE warp (0: the <= 8 token path)
 struct Frags {
   static constexpr int MTT = MT == 0 ? 1 : MT;
   static constexpr int GS = MT <= 1 ? 4 : (MT == 2 ? 2 : 1);  // k16 steps per group
@@ -341,13 +342,20 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[MT == 0 ? 1 : MT][4], flo
 // a_src == nullptr: the A operand [B, K] is resident in the activation region (row stride
 // (K+8)*2).  Otherwise it is streamed from global memory (row stride K) in KC-wide chunks
 // through two buffers of the activation region, all consumer threads copying.
-template <int MT>
-__device__ __forceinline__ void gemm_phase(const MegaArgs& a, const Phase& p, uint32_t smem_base, RingPos& base,
+// TW = token tiles per warp: TW == MT -> one warp per unit (all tiles); TW < MT -> the MT/TW warps
+// of a unit share its weight tile, each with its own token tiles (phases with one unit per
+// CTA: more dependent HMMA chains run side by side instead of back to back in one warp).
+template <int MT, int TW>
+__device__ __forceinline__ void gemm_inner(const MegaArgs& a, const Phase& p, uint32_t smem_base, RingPos& base,
                                            const bf16* a_src, Best (&best)[MT == 0 ? 1 : MT][2],
                                            unsigned char* dbg_smem) {
   constexpr int MTT = MT == 0 ? 1 : MT;
+  constexpr int TWW = TW == 0 ? 1 : TW;
+  constexpr int MS = MTT / TWW;   // warps per unit
+  constexpr int NU = NW / MS;     // units per round
   constexpr int BPAD = MT == 0 ? 8 : 16 * MT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int us = warp / MS, m0 = (warp % MS) * TWW;  // unit slot in the round, first token tile of this warp
   const uint32_t S = a.n_slots;
   const int KC = a.KC, RS = (KC + 8) * 2;  // RS: row stride of a streamed A chunk
   const uint32_t ring = smem_base + a.off_ring, act = smem_base + a.off_act;
@@ -368,25 +376,25 @@ __device__ __forceinline__ void gemm_phase(const MegaArgs& a, const Phase& p, ui
     cp_async_commit();
   };
 
-  for (int r0 = 0; r0 < n_c; r0 += NW, rnd.advance(NW * nch, a.ph_round_slot[p.kind], a.ph_round_par[p.kind], S)) {
-    const int nact = min(NW, n_c - r0);
-    const bool has = warp < nact;
+  for (int r0 = 0; r0 < n_c; r0 += NU, rnd.advance(NU * nch, a.ph_round_slot[p.kind], a.ph_round_par[p.kind], S)) {
+    const int nact = min(NU, n_c - r0);
+    const bool has = us < nact;
     if (!stream && !has) break;  // resident A: idle warps need not take part
     int seg = 0, row0 = 0;
     if (has) {
-      const int u = blockIdx.x + (r0 + warp) * gridDim.x;
+      const int u = blockIdx.x + (r0 + us) * gridDim.x;
       while (seg + 1 < p.nseg && u >= p.ubeg[seg + 1]) ++seg;
       row0 = (u - p.ubeg[seg]) << 3;
     }
-    float acc[MTT][4], acc2[MTT][4];
+    float acc[TWW][4], acc2[TWW][4];
 #pragma unroll
-    for (int m = 0; m < MTT; ++m)
+    for (int m = 0; m < TWW; ++m)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[m][i] = acc2[m][i] = 0.f;
     if (stream) a_chunk_load(0);
     // ring position of this warp's first job of the round; consecutive chunks are nact jobs apart
     RingPos me = rnd;
-    me.step(warp, S);
+    me.step(us, S);
     for (int ch = 0; ch < nch; ++ch) {
       const int k0 = ch * KC;
       const int klen = min(KC, p.K - k0);
@@ -409,13 +417,23 @@ __device__ __forceinline__ void gemm_phase(const MegaArgs& a, const Phase& p, ui
         const uint32_t slot = me.slot;
         mbar_wait(smem_base + OFF_FULL + slot * 8, me.par);
         const long long tw1 = clock64();
-        const uint32_t a_addr = stream ? act + (ch & 1) * (BPAD * RS) : act + k0 * 2;
+        const uint32_t a_addr = (stream ? act + (ch & 1) * (BPAD * RS) : act + k0 * 2) + m0 * 16 * AS;
         if (p.dual)
-          mma_chunk<MT, true>(acc, acc2, ring + slot * a.slot_bytes, a_addr, AS, 8 * KC * 2, klen >> 4, a.B, lane);
+          mma_chunk<TW, true>(acc, acc2, ring + slot * a.slot_bytes, a_addr, AS, 8 * KC * 2, klen >> 4, a.B, lane);
         else
-          mma_chunk<MT, false>(acc, acc2, ring + slot * a.slot_bytes, a_addr, AS, 0, klen >> 4, a.B, lane);
+          mma_chunk<TW, false>(acc, acc2, ring + slot * a.slot_bytes, a_addr, AS, 0, klen >> 4, a.B, lane);
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_base + OFF_EMPTY + slot * 8);
+        if (lane == 0) {
+          if (MS == 1) {
+            mbar_arrive(smem_base + OFF_EMPTY + slot * 8);
+          } else {  // the last of the MS warps sharing the tile releases the slot
+            uint32_t* rel = reinterpret_cast<uint32_t*>(dbg_smem - OFF_DBG + OFF_REL) + slot;
+            if (atomicAdd(rel, 1u) == (uint32_t)(MS - 1)) {
+              *rel = 0u;
+              mbar_arrive(smem_base + OFF_EMPTY + slot * 8);
+            }
+          }
+        }
         if (a.prof && threadIdx.x == 0 && blockIdx.x == 0) {  // profiling: cycles this warp waited for weights / spent in the MMA loop
           unsigned long long* dbg = reinterpret_cast<unsigned long long*>(dbg_smem);
           dbg[p.kind * 2] += (unsigned long long)(tw1 - tw0);
@@ -430,10 +448,10 @@ __device__ __forceinline__ void gemm_phase(const MegaArgs& a, const Phase& p, ui
     const int n = row0 + c * 2;
     if (n >= p.rows[seg]) continue;  // rows are even everywhere (checked by the launcher)
 #pragma unroll
-    for (int m = 0; m < MTT; ++m)
+    for (int m = 0; m < TWW; ++m)
 #pragma unroll
       for (int hr = 0; hr < (MT == 0 ? 1 : 2); ++hr) {
-        const int tok = m * 16 + g + hr * 8;
+        const int tok = (m0 + m) * 16 + g + hr * 8;
         if (tok >= a.B) continue;
         const float v0 = acc[m][hr * 2], v1 = acc[m][hr * 2 + 1];
         switch (p.kind) {
@@ -462,7 +480,7 @@ __device__ __forceinline__ void gemm_phase(const MegaArgs& a, const Phase& p, ui
             const bf16 l0 = f2bf(v0), l1 = f2bf(v1);
             *reinterpret_cast<uint32_t*>(a.logits + (size_t)tok * a.V + n) = pack2(l0, l1);
             const float f0 = bf2f(l0), f1 = bf2f(l1);
-            Best& bb = best[m][hr];
+            Best& bb = best[TW == MT ? m : 0][hr];  // lm_head never splits tiles (128 units per CTA)
             if (f0 > -CUDART_INF_F && cand_better(f0, n, bb.v, bb.i)) {
               bb.v = f0;
               bb.i = n;
@@ -478,6 +496,16 @@ __device__ __forceinline__ void gemm_phase(const MegaArgs& a, const Phase& p, ui
   }
   const int cls = (int)blockIdx.x < a.ph_r[p.kind] ? 1 : 0;
   base.advance((uint32_t)(n_c * nch), a.ph_adv_slot[p.kind][cls], a.ph_adv_par[p.kind][cls], S);
+}
+
+template <int MT>
+__device__ __forceinline__ void gemm_phase(const MegaArgs& a, const Phase& p, uint32_t smem_base, RingPos& base,
+                                           const bf16* a_src, Best (&best)[MT == 0 ? 1 : MT][2],
+                                           unsigned char* dbg_smem) {
+  if (MT >= 2 && p.nu != NW)
+    gemm_inner<MT, 1>(a, p, smem_base, base, a_src, best, dbg_smem);  // one token tile per warp
+  else
+    gemm_inner<MT, MT>(a, p, smem_base, base, a_src, best, dbg_smem);
 }
 
 // ---------------------------------------------------------------- consumer: activations
@@ -796,6 +824,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
     }
     *reinterpret_cast<volatile uint32_t*>(smem + OFF_ISSUED) = 0u;
     for (int i = 0; i < 10; ++i) reinterpret_cast<unsigned long long*>(smem + OFF_DBG)[i] = 0ull;
+    for (int i = 0; i < MAX_SLOTS; ++i) reinterpret_cast<uint32_t*>(smem + OFF_REL)[i] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -867,10 +896,27 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
       else if (kind == PH_GATEUP)
         prefetch_norm_w(a, smem_base, 0, l + 1 < a.L ? layers[l + 1].in_ln : a.final_norm);
       const bool from_embed = idx == 0;
-      load_rows(act, a.B, H, [&](int b) { return from_embed ? a.embed + (size_t)a.ids[b] * H : a.x + (size_t)b * H; });
-      stamp();
-      rmsnorm_rows(a, smem, a.B, H, which);
-      stamp();
+      if (a.dist_norm) {
+        // many rows: every CTA would repeat the whole batch's normalisation (IEEE divisions), so
+        // CTA b normalises row b once, publishes it, and everybody copies the result
+        const int b = blockIdx.x;
+        if (b < a.B) {  // B <= gridDim.x (launcher)
+          load_rows(act, 1, H, [&](int) { return from_embed ? a.embed + (size_t)a.ids[b] * H : a.x + (size_t)b * H; });
+          rmsnorm_rows(a, smem, 1, H, which);
+          const uint4* src = reinterpret_cast<const uint4*>(smem + a.off_act);
+          uint4* dst = reinterpret_cast<uint4*>(a.xn + (size_t)b * H);
+          for (int i = threadIdx.x; i < (H >> 3); i += NTC) dst[i] = src[i];
+        }
+        grid_sync(a.bar, epoch);
+        stamp();
+        load_rows(act, a.B, H, [&](int r) { return a.xn + (size_t)r * H; });
+        stamp();
+      } else {
+        load_rows(act, a.B, H, [&](int b) { return from_embed ? a.embed + (size_t)a.ids[b] * H : a.x + (size_t)b * H; });
+        stamp();
+        rmsnorm_rows(a, smem, a.B, H, which);
+        stamp();
+      }
     }
     Phase p;
     make_phase(a, idx, p);
@@ -1033,6 +1079,7 @@ cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st) {
   a.off_act = g.off_act;
   a.off_ring = g.off_ring;
   a.stream_down = g.stream_down;
+  a.dist_norm = a.B > 16 && a.B <= num_sms && a.xn != nullptr;
   {  // per phase kind: units of a CTA (q, +1 for the first r CTAs), chunks, and ring advances modulo the slot count
     const int Dq = a.n_q * a.hd, Dkv = a.n_kv * a.hd;
     const int units[5] = {(Dq + 7) / 8 + 2 * ((Dkv + 7) / 8), (a.H + 7) / 8, (a.I + 7) / 8, (a.H + 7) / 8, (a.V + 7) / 8};
@@ -1047,7 +1094,11 @@ cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st) {
         a.ph_adv_slot[k][cls] = jobs % S;
         a.ph_adv_par[k][cls] = (jobs / S) & 1;
       }
-      const int rj = NW * a.ph_nch[k];
+      // phases with at most one unit per CTA spread the token tiles of that unit over MT warps
+      const int mtt = g.mt == 0 ? 1 : g.mt;
+      const bool split = mtt >= 2 && units[k] <= num_sms && k != 4;
+      a.ph_nu[k] = split ? NW / mtt : NW;
+      const int rj = a.ph_nu[k] * a.ph_nch[k];
       a.ph_round_slot[k] = rj % S;
       a.ph_round_par[k] = (rj / S) & 1;
     }

@@ -324,6 +324,7 @@ cudaError_t forward_decode_mega(qie_engine* e, int n, int max_kv_len, float temp
   a.rowstep = e->rowstep_d;
   a.kv = e->kv;
   a.x = e->x;
+  a.xn = e->xn;
   a.qkv = e->qkv;
   a.att = e->att;
   a.h = e->h;

@@ -176,6 +176,8 @@ struct MegaArgs {
   int* rowstep;
   KvGeom kv;
   bf16 *x, *qkv, *att, *h, *logits;  // [B, H] [B, Dq+2Dkv] [B, Dq] [B, I] [B, V]
+  bf16* xn;                          // [B, H] normalised rows (batches > 16: one CTA per row)
+  int dist_norm;
   MegaCand* cand;                    // [grid, B] per-CTA arg-max candidates
   int* sampled;                      // [B]
   unsigned* bar;                     // grid barrier counter, zeroed by the launcher
@@ -185,6 +187,7 @@ struct MegaArgs {
   int n_layers_run;                  // debug: stop after this many layers (0 = all, then lm_head)
   int KC;  // k elements per weight tile = box depth of wmaps (decode_mega_kc at engine setup)
   // geometry, filled by the launcher (ph_*: per GEMM phase kind qkv/o/gate+up/down/lm_head)
+  int ph_nu[5];  // units per round (NW, or NW / token tiles when the tiles of a unit are spread over warps)
   int ph_q[5], ph_r[5], ph_nch[5], ph_adv_slot[5][2], ph_adv_par[5][2], ph_round_slot[5], ph_round_par[5];
   int n_slots, slot_bytes, act_bytes, off_act, off_ring, stream_down;
 };
