@@ -964,7 +964,7 @@ long qie_mega_prof_read(qie_engine* e, uint64_t* h_out, size_t max_values) {
   if (!e || !h_out) return fail(QIE_EINVAL, "null argument");
   if (!e->mega_prof_d) return fail(QIE_ESTATE, "persistent decode kernel not available for this checkpoint");
   // layout: [16L+8] globaltimer ns, then [16L+8] SM clock counter values of the same points
-  size_t n = std::min<size_t>(max_values, (size_t)2 * (16 * e->cfg.layers + 8) + 10);
+  size_t n = std::min<size_t>(max_values, (size_t)2 * (16 * e->cfg.layers + 8) + 16);
   CU(cudaStreamSynchronize(e->stream));
   CU(cudaMemcpy(h_out, e->mega_prof_d, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   return (long)n;

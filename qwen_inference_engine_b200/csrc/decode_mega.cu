@@ -42,7 +42,7 @@ constexpr int VT = 128;                       // cached positions per V tile in 
 constexpr int MAX_ROWS = 64;                  // rows (sequences) per launch
 constexpr int MAX_LAYERS = 64;
 // shared-memory header
-constexpr int OFF_FULL = 0, OFF_EMPTY = 256, OFF_ISSUED = 512, OFF_DBG = 528, OFF_REL = 640, OFF_RMS = 768, OFF_CAND = 1024;  // OFF_DBG: 10 x u64 cycle counters; OFF_REL: u32 per slot
+constexpr int OFF_FULL = 0, OFF_EMPTY = 256, OFF_ISSUED = 512, OFF_DBG = 528, OFF_REL = 768, OFF_RMS = 1024, OFF_CAND = 1280;  // OFF_DBG: 16 x u64 cycle counters; OFF_REL: u32 per slot
 constexpr int OFF_LAYERS = OFF_CAND + NW * MAX_ROWS * 8;                 // MegaLayer[MAX_LAYERS]
 constexpr int OFF_WNORM = OFF_LAYERS + MAX_LAYERS * (int)sizeof(MegaLayer);  // 2 x [H] bf16 norm weights
 static_assert(sizeof(MegaLayer) == 88, "MegaLayer layout");
@@ -631,6 +631,7 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
   const int ntask = per_head ? a.B * a.n_q : a.B * a.n_kv;
   const int tmax = (a.max_kv_len + 3) & ~3;
   const int psz = a.kv.page_size;
+  const int psz_shift = (psz & (psz - 1)) == 0 ? __ffs(psz) - 1 : -1;
   const MegaLayer& w = reinterpret_cast<const MegaLayer*>(smem + OFF_LAYERS)[layer];
 
   float* q_s = reinterpret_cast<float*>(smem + a.off_act);          // [hs][HD] fp32
@@ -642,7 +643,17 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
   unsigned char* vbuf = reinterpret_cast<unsigned char*>(pages) + ((n_pages_max * 4 + 15) & ~15);  // [2][VT][HD] bf16
   const uint32_t vbuf_u32 = smem_u32(vbuf);
 
+  unsigned long long* dbg = reinterpret_cast<unsigned long long*>(smem + OFF_DBG);
+  const bool timed = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
   for (int task = blockIdx.x; task < ntask; task += gridDim.x) {
+    long long tq = timed ? clock64() : 0;
+    auto lap = [&](int slot) {
+      if (timed) {
+        const long long t = clock64();
+        dbg[slot] += (unsigned long long)(t - tq);
+        tq = t;
+      }
+    };
     int b, kvh, h0;
     if (per_head) {
       b = task / a.n_q;
@@ -661,10 +672,13 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
     auto v_tile_load = [&](int it) {  // cached positions [it*VT, min(ps, it*VT+VT)) of V -> vbuf[it&1]
       const int t0 = it * VT, tn = min(VT, ps - t0);
       const uint32_t dst = vbuf_u32 + (it & 1) * (VT * HD * 2);
+      const int* pg = it == 0 ? bt : pages;  // tile 0 is issued while pages[] is still being filled
       for (int idx = threadIdx.x; idx < tn * (HD / 8); idx += NTC) {
         const int r = idx / (HD / 8), cc = idx - r * (HD / 8);
         const int k = t0 + r;
-        cp_async16(dst + r * (HD * 2) + cc * 16, a.kv.chunk(bt[k / psz], layer, 1, kvh) + (size_t)(k % psz) * HD + cc * 8);
+        const int pi = psz_shift >= 0 ? (k >> psz_shift) : k / psz;
+        const int po = k - pi * psz;
+        cp_async16(dst + r * (HD * 2) + cc * 16, a.kv.chunk(pg[pi], layer, 1, kvh) + (size_t)po * HD + cc * 8);
       }
       cp_async_commit();
     };
@@ -695,13 +709,15 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
       }
     }
     bar_consumers();
+    lap(10);
 
     // scores: one thread per cache position, all heads of the task
     const float den = __fsqrt_rn((float)HD);
     for (int k = threadIdx.x; k <= ps; k += NTC) {
       const uint4* kp = (k == ps) ? reinterpret_cast<const uint4*>(knew)
-                                  : reinterpret_cast<const uint4*>(a.kv.chunk(pages[k / psz], layer, 0, kvh) +
-                                                                   (size_t)(k % psz) * HD);
+                                  : reinterpret_cast<const uint4*>(
+                                        a.kv.chunk(pages[psz_shift >= 0 ? (k >> psz_shift) : k / psz], layer, 0, kvh) +
+                                        (size_t)(psz_shift >= 0 ? (k & (psz - 1)) : k % psz) * HD);
       uint32_t kr[HD / 2];
 #pragma unroll
       for (int i = 0; i < HD / 8; ++i) {
@@ -714,6 +730,7 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
       for (int i = 0; i < hs; ++i) score[i * tmax + k] = __fdiv_rn(dot_tree<HD>(q_s + i * HD, kr), den);
     }
     bar_consumers();
+    lap(11);
 
     // softmax: one warp per head (self_attension.cu:94-107)
     for (int i = warp; i < hs; i += NW) {
@@ -724,20 +741,34 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
       for (int k = lane; k <= ps; k += 32) s[k] = expf(__fsub_rn(s[k], m));
       __syncwarp();
       float sum = 0.f;
-      if (lane == 0) {
-        int k = 0;
-        for (; k + 4 <= ps + 1; k += 4) {
-          const float4 e = *reinterpret_cast<const float4*>(s + k);
-          sum = __fadd_rn(sum, e.x);
-          sum = __fadd_rn(sum, e.y);
-          sum = __fadd_rn(sum, e.z);
-          sum = __fadd_rn(sum, e.w);
+      if (lane == 0) {  // the reference's sequential sum: keep 8 values in flight ahead of the FADD chain
+        const int n = ps + 1, n8 = n & ~7;
+        float4 c0, c1, n0, n1;
+        if (n8) {
+          c0 = *reinterpret_cast<const float4*>(s);
+          c1 = *reinterpret_cast<const float4*>(s + 4);
         }
-        for (; k <= ps; ++k) sum = __fadd_rn(sum, s[k]);
+        for (int k = 0; k < n8; k += 8) {
+          const int kn = k + 8 < n8 ? k + 8 : k;
+          n0 = *reinterpret_cast<const float4*>(s + kn);
+          n1 = *reinterpret_cast<const float4*>(s + kn + 4);
+          sum = __fadd_rn(sum, c0.x);
+          sum = __fadd_rn(sum, c0.y);
+          sum = __fadd_rn(sum, c0.z);
+          sum = __fadd_rn(sum, c0.w);
+          sum = __fadd_rn(sum, c1.x);
+          sum = __fadd_rn(sum, c1.y);
+          sum = __fadd_rn(sum, c1.z);
+          sum = __fadd_rn(sum, c1.w);
+          c0 = n0;
+          c1 = n1;
+        }
+        for (int k = n8; k < n; ++k) sum = __fadd_rn(sum, s[k]);
       }
       sum = __shfl_sync(0xffffffffu, sum, 0);
       for (int k = lane; k <= ps; k += 32) s[k] = __fdiv_rn(s[k], sum);
     }
+    lap(12);
     // PV (self_attension.cu:112-137): V streams through shared memory in tiles of VT cached
     // positions (all consumer threads copy, double buffered); warp i keeps the sequential
     // fma chain of head i, lane l owning dims 2l, 2l+1 (+64p).
@@ -804,6 +835,7 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
       }
     }
     bar_consumers();  // shared memory is reused by the next task / phase
+    lap(13);
   }
 }
 
@@ -823,7 +855,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
       mbar_init(smem_base + OFF_EMPTY + s * 8, 1);
     }
     *reinterpret_cast<volatile uint32_t*>(smem + OFF_ISSUED) = 0u;
-    for (int i = 0; i < 10; ++i) reinterpret_cast<unsigned long long*>(smem + OFF_DBG)[i] = 0ull;
+    for (int i = 0; i < 16; ++i) reinterpret_cast<unsigned long long*>(smem + OFF_DBG)[i] = 0ull;
     for (int i = 0; i < MAX_SLOTS; ++i) reinterpret_cast<uint32_t*>(smem + OFF_REL)[i] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -995,7 +1027,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
   }
   stamp();
   if (a.prof && blockIdx.x == 0 && threadIdx.x == 0)
-    for (int i = 0; i < 10; ++i) a.prof[2 * a.prof_stride + i] = reinterpret_cast<unsigned long long*>(smem + OFF_DBG)[i];
+    for (int i = 0; i < 16; ++i) a.prof[2 * a.prof_stride + i] = reinterpret_cast<unsigned long long*>(smem + OFF_DBG)[i];
 }
 
 struct Geom {
@@ -1058,7 +1090,7 @@ bool decode_mega_supports(int H, int I, int L, int n_q, int n_kv, int hd, int B,
   return mega_geometry(H, I, L, n_q, n_kv, hd, B, max_kv_len, num_sms, KC, &g);
 }
 
-int decode_mega_prof_slots(int L) { return 2 * (16 * L + 8) + 10; }
+int decode_mega_prof_slots(int L) { return 2 * (16 * L + 8) + 16; }
 
 template <int NP>
 static void (*pick_kernel(int mt))(MegaArgs) {

@@ -197,9 +197,10 @@ class Engine:
     def mega_prof(self):
         """device timestamps (ns) of the last profiled persistent-kernel step"""
         n = 16 * self.config.layers + 8
-        out = np.zeros(2 * n + 10, np.uint64)
+        out = np.zeros(2 * n + 16, np.uint64)
         check(self._L.qie_mega_prof_read(self._h, out.ctypes.data, len(out)))
-        self.mega_gemm_cycles = out[2 * n:]  # per GEMM phase kind: (cycles waiting for weights, cycles in the MMA loop)
+        self.mega_gemm_cycles = out[2 * n:2 * n + 10]  # per GEMM phase kind: (cycles waiting for weights, cycles in the MMA loop)
+        self.mega_attn_cycles = out[2 * n + 10:2 * n + 14]  # attention of CTA 0: setup, scores, softmax, PV
         return out[:n - 2], out[n:2 * n - 2]  # (ns, SM cycles) at the 16*layers + 6 stamp points
 
     def read_activation(self, name, n_elems, dtype=np.uint16):

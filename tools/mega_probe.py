@@ -47,6 +47,7 @@ if a.mega and eng.uses_mega(a.batch, a.ctx + a.steps + 16):
     L = cfg.layers
     gc = eng.mega_gemm_cycles.astype(np.int64).reshape(5, 2)
     print("CTA0 warp0 cycles (wait for weights, MMA loop) per step:", {k: (int(gc[i, 0]), int(gc[i, 1])) for i, k in enumerate(["qkv", "o", "gateup", "down", "lm_head"])})
+    print("CTA0 attention cycles per step (setup, scores, softmax, PV):", [int(x) for x in eng.mega_attn_cycles])
     d = np.diff(ts)
     per = d[:16 * L].reshape(L, 16)
     names = ["qkv.load", "qkv.norm", "qkv.gemm", "qkv.bar", "att.run", "att.bar", "o.load", "o.gemm", "o.bar",
