@@ -291,7 +291,7 @@ static void engine_free(qie_engine* e) {
   void* dev[] = {e->blob, e->cos_d, e->sin_d, e->kv.pool, e->block_table_d, e->ids_d, e->pos_d, e->slot_d,
                  e->sampled_d, e->rowstep_d, e->x, e->xn, e->q, e->k, e->v, e->att, e->h, e->logits, e->qkv,
                  e->gemm_ws, e->attn_ws_o, e->attn_ws_ml, e->gemm_counters, e->mega_layers_d, e->mega_cand_d,
-                 e->mega_bar_d, e->mega_prof_d, e->mega_wmaps_d};
+                 e->mega_bar_d, e->mega_prof_d, e->mega_wmaps_d[0], e->mega_wmaps_d[1]};
   for (void* p : dev)
     if (p) cudaFree(p);
   if (e->block_table_h) cudaFreeHost(e->block_table_h);
@@ -404,24 +404,27 @@ static int engine_finish_setup(qie_engine* e) {
     const size_t Hs = c.hidden;
     aligned = aligned && (Hs % 64 == 0) && (I % 64 == 0) && (Dq % 64 == 0);
     if (aligned) {  // TMA needs 16-byte aligned weight rows and 64-wide k blocks; otherwise the per-operator path is used
-      e->mega_kc = decode_mega_kc(c.hidden);
-      std::vector<TensorMap2D> maps((size_t)7 * c.layers + 1);
-      bool ok = true;
-      for (int l = 0; l < c.layers && ok; ++l) {
-        const LayerWeights& w = e->L[l];
-        TensorMap2D* m = &maps[(size_t)7 * l];
-        ok = ok && make_tensor_map_w3d(m + 0, w.q, (int)Dq, (int)H, e->mega_kc) == cudaSuccess;
-        ok = ok && make_tensor_map_w3d(m + 1, w.k, (int)Dkv, (int)H, e->mega_kc) == cudaSuccess;
-        ok = ok && make_tensor_map_w3d(m + 2, w.v, (int)Dkv, (int)H, e->mega_kc) == cudaSuccess;
-        ok = ok && make_tensor_map_w3d(m + 3, w.o, (int)H, (int)Dq, e->mega_kc) == cudaSuccess;
-        ok = ok && make_tensor_map_w3d(m + 4, w.gate, (int)I, (int)H, e->mega_kc) == cudaSuccess;
-        ok = ok && make_tensor_map_w3d(m + 5, w.up, (int)I, (int)H, e->mega_kc) == cudaSuccess;
-        ok = ok && make_tensor_map_w3d(m + 6, w.down, (int)H, (int)I, e->mega_kc) == cudaSuccess;
+      for (int ts = 0; ts < 2; ++ts) {
+        e->mega_kc[ts] = decode_mega_kc(c.hidden, ts);
+        std::vector<TensorMap2D> maps((size_t)7 * c.layers + 1);
+        bool ok = true;
+        const int kc = e->mega_kc[ts];
+        for (int l = 0; l < c.layers && ok; ++l) {
+          const LayerWeights& w = e->L[l];
+          TensorMap2D* m = &maps[(size_t)7 * l];
+          ok = ok && make_tensor_map_w3d(m + 0, w.q, (int)Dq, (int)H, kc) == cudaSuccess;
+          ok = ok && make_tensor_map_w3d(m + 1, w.k, (int)Dkv, (int)H, kc) == cudaSuccess;
+          ok = ok && make_tensor_map_w3d(m + 2, w.v, (int)Dkv, (int)H, kc) == cudaSuccess;
+          ok = ok && make_tensor_map_w3d(m + 3, w.o, (int)H, (int)Dq, kc) == cudaSuccess;
+          ok = ok && make_tensor_map_w3d(m + 4, w.gate, (int)I, (int)H, kc) == cudaSuccess;
+          ok = ok && make_tensor_map_w3d(m + 5, w.up, (int)I, (int)H, kc) == cudaSuccess;
+          ok = ok && make_tensor_map_w3d(m + 6, w.down, (int)H, (int)I, kc) == cudaSuccess;
+        }
+        ok = ok && make_tensor_map_w3d(&maps[(size_t)7 * c.layers], e->lm_head, c.vocab, (int)H, kc) == cudaSuccess;
+        if (!ok) return fail(QIE_ECUDA, "cuTensorMapEncodeTiled failed for the weight views");
+        CU(cudaMalloc(&e->mega_wmaps_d[ts], maps.size() * sizeof(TensorMap2D)));
+        CU(cudaMemcpy(e->mega_wmaps_d[ts], maps.data(), maps.size() * sizeof(TensorMap2D), cudaMemcpyHostToDevice));
       }
-      ok = ok && make_tensor_map_w3d(&maps[(size_t)7 * c.layers], e->lm_head, c.vocab, (int)H, e->mega_kc) == cudaSuccess;
-      if (!ok) return fail(QIE_ECUDA, "cuTensorMapEncodeTiled failed for the weight views");
-      CU(cudaMalloc(&e->mega_wmaps_d, maps.size() * sizeof(TensorMap2D)));
-      CU(cudaMemcpy(e->mega_wmaps_d, maps.data(), maps.size() * sizeof(TensorMap2D), cudaMemcpyHostToDevice));
       CU(cudaMalloc(&e->mega_layers_d, c.layers * sizeof(MegaLayer)));
       CU(cudaMemcpy(e->mega_layers_d, ml.data(), c.layers * sizeof(MegaLayer), cudaMemcpyHostToDevice));
       CU(cudaMalloc(&e->mega_cand_d, (size_t)e->num_sms * 64 * sizeof(MegaCand)));

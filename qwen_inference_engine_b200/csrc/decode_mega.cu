@@ -1035,8 +1035,9 @@ struct Geom {
   size_t smem;
 };
 
-int kc_for(int H) {
-  const int nch = (H + 511) / 512;
+int kc_for(int H, int big) {
+  const int lim = big ? 1024 : 512;  // small batches: fewer, larger weight tiles
+  const int nch = (H + lim - 1) / lim;
   int KC = ((H + nch - 1) / nch + 63) & ~63;
   if (const char* kv = getenv("QIE_MEGA_KC")) {  // tuning knob: k elements per weight tile
     const int v = atoi(kv);
@@ -1083,7 +1084,7 @@ bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int ma
 
 }  // namespace
 
-int decode_mega_kc(int H) { return kc_for(H); }
+int decode_mega_kc(int H, int big) { return kc_for(H, big); }
 
 bool decode_mega_supports(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int num_sms, int KC) {
   Geom g;

@@ -290,10 +290,20 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
 }
 
 
+// weight-tile set: larger tiles for small batches when the ring still holds enough of them
+static int mega_tile_set(const qie_engine* e, int n, int max_kv_len) {
+  const qie_config& c = e->cfg;
+  if (n <= 8 && e->mega_kc[1] > e->mega_kc[0] &&
+      decode_mega_supports(c.hidden, c.inter, c.layers, c.n_q, c.n_kv, c.head_dim, n, max_kv_len, e->num_sms, e->mega_kc[1]))
+    return 1;
+  return 0;
+}
+
 bool decode_uses_mega(const qie_engine* e, int n, int max_kv_len) {
   if (!e->use_mega || e->opts.numerics != QIE_NUMERICS_REFERENCE_ORDER || e->capture || !e->mega_layers_d) return false;
   const qie_config& c = e->cfg;
-  return decode_mega_supports(c.hidden, c.inter, c.layers, c.n_q, c.n_kv, c.head_dim, n, max_kv_len, e->num_sms, e->mega_kc);
+  return decode_mega_supports(c.hidden, c.inter, c.layers, c.n_q, c.n_kv, c.head_dim, n, max_kv_len, e->num_sms,
+                              e->mega_kc[mega_tile_set(e, n, max_kv_len)]);
 }
 
 cudaError_t forward_decode_mega(qie_engine* e, int n, int max_kv_len, float temperature) {
@@ -307,8 +317,9 @@ cudaError_t forward_decode_mega(qie_engine* e, int n, int max_kv_len, float temp
   a.hd = c.head_dim;
   a.V = c.vocab;
   a.layers = e->mega_layers_d;
-  a.wmaps = e->mega_wmaps_d;
-  a.KC = e->mega_kc;
+  const int tset = mega_tile_set(e, n, max_kv_len);
+  a.wmaps = e->mega_wmaps_d[tset];
+  a.KC = e->mega_kc[tset];
   a.embed = e->embed;
   a.final_norm = e->final_norm;
   a.lm_head = e->lm_head;

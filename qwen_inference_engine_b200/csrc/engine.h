@@ -84,8 +84,9 @@ struct qie_engine {
   // persistent decode kernel (decode_mega.cu): reference-order decode steps of <= 8 rows
   bool use_mega = true;              // QIE_MEGA=0 disables
   qie::MegaLayer* mega_layers_d = nullptr;
-  qie::TensorMap2D* mega_wmaps_d = nullptr;  // 7 per layer + lm_head, 3-D weight views (box 8 rows x mega_kc)
-  int mega_kc = 0;
+  // 7 per layer + lm_head 3-D weight views (box 8 rows x mega_kc[s]); set 1 (larger tiles) serves batches <= 8
+  qie::TensorMap2D* mega_wmaps_d[2] = {nullptr, nullptr};
+  int mega_kc[2] = {0, 0};
   qie::MegaCand* mega_cand_d = nullptr;
   unsigned* mega_bar_d = nullptr;
   unsigned long long* mega_prof_d = nullptr;  // phase timestamps of the last profiled step

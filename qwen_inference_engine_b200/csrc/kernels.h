@@ -192,7 +192,7 @@ struct MegaArgs {
   int n_slots, slot_bytes, act_bytes, off_act, off_ring, stream_down;
 };
 // max rows the persistent kernel accepts for this model shape (0 = shape unsupported)
-int decode_mega_kc(int H);  // k elements per weight tile (box depth of the weight tensor maps)
+int decode_mega_kc(int H, int big);  // k elements per weight tile (box depth of the weight tensor maps); big: batches <= 8
 bool decode_mega_supports(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int num_sms, int KC);
 int decode_mega_prof_slots(int L);
 cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st);
