@@ -408,7 +408,8 @@ __device__ __forceinline__ void gemm_inner(const MegaArgs& a, const Phase& p, ui
         bar_consumers();
       }
       if (has) {
-        const long long tw0 = clock64();
+        const bool timed = a.prof != nullptr && threadIdx.x == 0 && blockIdx.x == 0;
+        const long long tw0 = timed ? clock64() : 0;
         if (lds32_volatile(smem_base + OFF_ISSUED) <= me.job) {
           const long long t0 = clock64();
           while (lds32_volatile(smem_base + OFF_ISSUED) <= me.job)
@@ -416,7 +417,7 @@ __device__ __forceinline__ void gemm_inner(const MegaArgs& a, const Phase& p, ui
         }
         const uint32_t slot = me.slot;
         mbar_wait(smem_base + OFF_FULL + slot * 8, me.par);
-        const long long tw1 = clock64();
+        const long long tw1 = timed ? clock64() : 0;
         const uint32_t a_addr = (stream ? act + (ch & 1) * (BPAD * RS) : act + k0 * 2) + m0 * 16 * AS;
         if (p.dual)
           mma_chunk<TW, true>(acc, acc2, ring + slot * a.slot_bytes, a_addr, AS, 8 * KC * 2, klen >> 4, a.B, lane);
@@ -434,7 +435,7 @@ __device__ __forceinline__ void gemm_inner(const MegaArgs& a, const Phase& p, ui
             }
           }
         }
-        if (a.prof && threadIdx.x == 0 && blockIdx.x == 0) {  // profiling: cycles this warp waited for weights / spent in the MMA loop
+        if (timed) {  // profiling: cycles this warp waited for weights / spent in the MMA loop
           unsigned long long* dbg = reinterpret_cast<unsigned long long*>(dbg_smem);
           dbg[p.kind * 2] += (unsigned long long)(tw1 - tw0);
           dbg[p.kind * 2 + 1] += (unsigned long long)(clock64() - tw1);
