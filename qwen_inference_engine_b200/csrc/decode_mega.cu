@@ -608,6 +608,26 @@ __device__ __forceinline__ float dot_tree(const float* __restrict__ q, const uin
   return d[0];
 }
 
+// the same tree over a K row that was widened to fp32 once (shared by all heads of the task),
+// evaluated with packed fp32x2 instructions (sm_100 FMUL2 / FADD2: two IEEE fp32 operations per
+// instruction, each lane bit-identical to the scalar op).  kf[j] = {k[2j], k[2j+1]}.
+template <int HD>
+__device__ __forceinline__ float dot_tree_f(const float* __restrict__ q, const float2 (&kf)[HD / 2]) {
+  float2 d[HD / 4];
+#pragma unroll
+  for (int j = 0; j < HD / 4; j += 2) {  // stride HD/2: d[j] = p[2j..2j+1] + p[2j+HD/2..]
+    const float4 qa = *reinterpret_cast<const float4*>(q + 2 * j);
+    const float4 qb = *reinterpret_cast<const float4*>(q + 2 * j + HD / 2);
+    d[j] = __fadd2_rn(__fmul2_rn(make_float2(qa.x, qa.y), kf[j]), __fmul2_rn(make_float2(qb.x, qb.y), kf[j + HD / 4]));
+    d[j + 1] = __fadd2_rn(__fmul2_rn(make_float2(qa.z, qa.w), kf[j + 1]), __fmul2_rn(make_float2(qb.z, qb.w), kf[j + 1 + HD / 4]));
+  }
+#pragma unroll
+  for (int s = HD / 8; s >= 1; s >>= 1)  // strides HD/4 ... 2 elements
+#pragma unroll
+    for (int j = 0; j < s; ++j) d[j] = __fadd2_rn(d[j], d[j + s]);
+  return __fadd_rn(d[0].x, d[0].y);  // stride 1
+}
+
 template <int NP>
 __device__ __forceinline__ void head_load_cg(float (&x)[NP][2], const bf16* src, int lane) {
 #pragma unroll
@@ -719,16 +739,20 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
                                   : reinterpret_cast<const uint4*>(
                                         a.kv.chunk(pages[psz_shift >= 0 ? (k >> psz_shift) : k / psz], layer, 0, kvh) +
                                         (size_t)(psz_shift >= 0 ? (k & (psz - 1)) : k % psz) * HD);
-      uint32_t kr[HD / 2];
+      float2 kf[HD / 2];
 #pragma unroll
       for (int i = 0; i < HD / 8; ++i) {
         const uint4 t = kp[i];
-        kr[4 * i] = t.x;
-        kr[4 * i + 1] = t.y;
-        kr[4 * i + 2] = t.z;
-        kr[4 * i + 3] = t.w;
+        kf[4 * i] = make_float2(lo2f(t.x), hi2f(t.x));
+        kf[4 * i + 1] = make_float2(lo2f(t.y), hi2f(t.y));
+        kf[4 * i + 2] = make_float2(lo2f(t.z), hi2f(t.z));
+        kf[4 * i + 3] = make_float2(lo2f(t.w), hi2f(t.w));
       }
-      for (int i = 0; i < hs; ++i) score[i * tmax + k] = __fdiv_rn(dot_tree<HD>(q_s + i * HD, kr), den);
+      // dot / sqrtf(hd): for hd = 64 the divisor is exactly 8, and x / 8 == x * 0.125 bit for bit
+      for (int i = 0; i < hs; ++i) {
+        const float dot = dot_tree_f<HD>(q_s + i * HD, kf);
+        score[i * tmax + k] = HD == 64 ? __fmul_rn(dot, 0.125f) : __fdiv_rn(dot, den);
+      }
     }
     bar_consumers();
     lap(11);
