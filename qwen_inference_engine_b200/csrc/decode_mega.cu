@@ -641,9 +641,14 @@ __device__ __forceinline__ void head_load_cg(float (&x)[NP][2], const bf16* src,
 // Tasks: (row, q head) while they fit one wave of CTAs, else (row, kv head) with the whole
 // query group sharing the K/V stream.  q/k-norm + RoPE + the KV store of the new position
 // are done here (replaces 2x qkNorm, 2x RoPE, kv_copy_layer_to_cache_decode).
+// stage 0 (before the grid barrier that publishes this layer's q/k/v): everything of the CTA's
+// first task that does not depend on them -- position, page ids, the first KSTG cached K rows,
+// V tile 0, norm weights and the RoPE row -- is requested into shared memory, so that the
+// dependent part after the barrier (stage 1) starts from on-chip data.
 template <int NP>
-__device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, unsigned char* smem) {
+__device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, unsigned char* smem, int stage) {
   constexpr int HD = 64 * NP;
+  constexpr int KROW = HD * 2 + 16;  // staged K rows are padded: conflict-free 16-byte reads, one row per thread
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Gq = a.n_q / a.n_kv;
   const int Dq = a.n_q * HD, Dkv = a.n_kv * HD, QKV = Dq + 2 * Dkv;
@@ -655,7 +660,8 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
   const int psz_shift = (psz & (psz - 1)) == 0 ? __ffs(psz) - 1 : -1;
   const MegaLayer& w = reinterpret_cast<const MegaLayer*>(smem + OFF_LAYERS)[layer];
 
-  float* q_s = reinterpret_cast<float*>(smem + a.off_act);          // [hs][HD] fp32
+  // staged mode: stage 0 runs next to the QKV GEMM, so the attention areas start behind its activation rows
+  float* q_s = reinterpret_cast<float*>(smem + a.off_act + a.attn_off);  // [hs][HD] fp32
   bf16* knew = reinterpret_cast<bf16*>(q_s + hs * HD);              // [HD] bf16 (16-byte aligned)
   bf16* vnew = knew + HD;
   float* score = reinterpret_cast<float*>(vnew + HD);               // [hs][tmax]
@@ -663,6 +669,53 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
   const int n_pages_max = a.max_kv_len / psz + 1;
   unsigned char* vbuf = reinterpret_cast<unsigned char*>(pages) + ((n_pages_max * 4 + 15) & ~15);  // [2][VT][HD] bf16
   const uint32_t vbuf_u32 = smem_u32(vbuf);
+  // stage-0 area (per-head tasks only): staged K rows, q/k norm weights, RoPE row, position
+  unsigned char* kst = vbuf + 2 * VT * HD * 2;                       // [kstg][KROW]
+  const int kstg = a.attn_kstg;
+  bf16* wq_s = reinterpret_cast<bf16*>(kst + kstg * KROW);           // [HD]
+  bf16* wk_s = wq_s + HD;
+  float* cos_s = reinterpret_cast<float*>(wk_s + HD);                // [HD/2]
+  float* sin_s = cos_s + HD / 2;
+  int* pre = reinterpret_cast<int*>(sin_s + HD / 2);                 // [0] = position of the staged task
+  const bool staged_mode = kstg > 0;
+
+  if (stage == 0) {
+    // executed by warps 1.. only (warp 0 owns the CTA's QKV unit and goes straight to its MMA chain)
+    if (!staged_mode || (int)blockIdx.x >= ntask || warp == 0) return;
+    const int tid = threadIdx.x - 32;
+    constexpr int NT0 = NTC - 32;
+    const int task = blockIdx.x;
+    const int b = task / a.n_q, h0 = task - b * a.n_q, kvh = h0 / Gq;  // staged mode = one q head per task
+    const int ps = a.pos[b];
+    const int* bt = a.block_table + (size_t)a.slot[b] * a.max_pages;
+    const int n_pages = ps / psz + 1;
+    for (int i = tid; i < n_pages; i += NT0) pages[i] = bt[i];
+    if (tid == 0) pre[0] = ps;
+    const int nk = min(ps, kstg);
+    const uint32_t kst_u32 = smem_u32(kst);
+    for (int idx = tid; idx < nk * (HD / 8); idx += NT0) {
+      const int r = idx / (HD / 8), cc = idx - r * (HD / 8);
+      const int pi = psz_shift >= 0 ? (r >> psz_shift) : r / psz;
+      cp_async16(kst_u32 + r * KROW + cc * 16, a.kv.chunk(bt[pi], layer, 0, kvh) + (size_t)(r - pi * psz) * HD + cc * 8);
+    }
+    if (tid < HD / 8) {
+      if (w.q_norm) cp_async16(smem_u32(wq_s) + tid * 16, w.q_norm + tid * 8);
+      if (w.k_norm) cp_async16(smem_u32(wk_s) + tid * 16, w.k_norm + tid * 8);
+      cp_async16(smem_u32(cos_s) + tid * 16, a.cos_t + (size_t)ps * 32 * NP + tid * 4);
+      cp_async16(smem_u32(sin_s) + tid * 16, a.sin_t + (size_t)ps * 32 * NP + tid * 4);
+    }
+    cp_async_commit();
+    {  // V tile 0 (page ids straight from the block table: pages[] is still being written)
+      const int tn = min(VT, ps);
+      for (int idx = tid; idx < tn * (HD / 8); idx += NT0) {
+        const int r = idx / (HD / 8), cc = idx - r * (HD / 8);
+        const int pi = psz_shift >= 0 ? (r >> psz_shift) : r / psz;
+        cp_async16(vbuf_u32 + r * (HD * 2) + cc * 16, a.kv.chunk(bt[pi], layer, 1, kvh) + (size_t)(r - pi * psz) * HD + cc * 8);
+      }
+      cp_async_commit();
+    }
+    return;
+  }
 
   unsigned long long* dbg = reinterpret_cast<unsigned long long*>(smem + OFF_DBG);
   const bool timed = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
@@ -686,10 +739,14 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
       h0 = kvh * Gq;
     }
     const bool writer = !per_head || (h0 == kvh * Gq);
-    const int ps = a.pos[b];
+    const bool staged = staged_mode && task == (int)blockIdx.x;  // stage 0 ran for this task
+    const int ps = staged ? pre[0] : a.pos[b];
     const int n_pages = ps / psz + 1;
-    const int* bt = a.block_table + (size_t)a.slot[b] * a.max_pages;
-    for (int i = threadIdx.x; i < n_pages; i += NTC) pages[i] = bt[i];
+    const int* bt = nullptr;
+    if (!staged) {
+      bt = a.block_table + (size_t)a.slot[b] * a.max_pages;
+      for (int i = threadIdx.x; i < n_pages; i += NTC) pages[i] = bt[i];
+    }
     auto v_tile_load = [&](int it) {  // cached positions [it*VT, min(ps, it*VT+VT)) of V -> vbuf[it&1]
       const int t0 = it * VT, tn = min(VT, ps - t0);
       const uint32_t dst = vbuf_u32 + (it & 1) * (VT * HD * 2);
@@ -703,23 +760,29 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
       }
       cp_async_commit();
     };
-    v_tile_load(0);  // overlaps q/k-norm, scores and softmax
+    if (staged)
+      cp_async_wait<1>();  // staged K rows / weights / RoPE row have landed (V tile 0 may still be in flight)
+    else
+      v_tile_load(0);  // overlaps q/k-norm, scores and softmax
     const bf16* row = a.qkv + (size_t)b * QKV;
-    const float* cos_row = a.cos_t + (size_t)ps * 32 * NP;
-    const float* sin_row = a.sin_t + (size_t)ps * 32 * NP;
-    const int new_page = bt[ps / psz], new_off = ps % psz;
+    const float* cos_row = staged ? cos_s : a.cos_t + (size_t)ps * 32 * NP;
+    const float* sin_row = staged ? sin_s : a.sin_t + (size_t)ps * 32 * NP;
+    const bf16* wqn = staged ? wq_s : w.q_norm;
+    const bf16* wkn = staged ? wk_s : w.k_norm;
+    const int new_page = staged ? pages[ps / psz] : bt[ps / psz], new_off = ps % psz;
+    if (staged) bar_consumers();  // cp.async data of other threads (weights, RoPE row) is visible after this
     for (int r = warp; r < hs + 2; r += NW) {
       float v[NP][2];
       if (r < hs) {
         head_load_cg<NP>(v, row + (size_t)(h0 + r) * HD, lane);
-        if (w.q_norm) head_norm<NP>(v, w.q_norm, lane);
+        if (w.q_norm) head_norm<NP>(v, wqn, lane);
         head_rope<NP>(v, cos_row, sin_row, lane);
 #pragma unroll
         for (int p = 0; p < NP; ++p)
           *reinterpret_cast<float2*>(q_s + r * HD + 64 * p + 2 * lane) = make_float2(v[p][0], v[p][1]);
       } else if (r == hs) {
         head_load_cg<NP>(v, row + Dq + (size_t)kvh * HD, lane);
-        if (w.k_norm) head_norm<NP>(v, w.k_norm, lane);
+        if (w.k_norm) head_norm<NP>(v, wkn, lane);
         head_rope<NP>(v, cos_row, sin_row, lane);
         head_store<NP>(v, knew, lane);
         if (writer) head_store<NP>(v, a.kv.chunk(new_page, layer, 0, kvh) + (size_t)new_off * HD, lane);
@@ -736,6 +799,7 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
     const float den = __fsqrt_rn((float)HD);
     for (int k = threadIdx.x; k <= ps; k += NTC) {
       const uint4* kp = (k == ps) ? reinterpret_cast<const uint4*>(knew)
+                        : (staged && k < kstg) ? reinterpret_cast<const uint4*>(kst + k * KROW)
                                   : reinterpret_cast<const uint4*>(
                                         a.kv.chunk(pages[psz_shift >= 0 ? (k >> psz_shift) : k / psz], layer, 0, kvh) +
                                         (size_t)(psz_shift >= 0 ? (k & (psz - 1)) : k % psz) * HD);
@@ -932,7 +996,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
     const bf16* a_src = nullptr;
     if (kind == PH_O) {
       // ---- attention, then O + residual
-      attention_phase<NP>(a, l, smem);
+      attention_phase<NP>(a, l, smem, 1);
       stamp();
       grid_sync(a.bar, epoch);
       stamp();
@@ -977,6 +1041,8 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
     }
     Phase p;
     make_phase(a, idx, p);
+    if (kind == PH_QKV && a.attn_kstg > 0)
+      attention_phase<NP>(a, l, smem, 0);  // warps 1..: request what attention needs that does not depend on q/k/v
     gemm_phase<MT>(a, p, smem_base, ring_pos, a_src, best, smem + OFF_DBG);
     stamp();
     if (kind == PH_LMHEAD) {
@@ -1056,7 +1122,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
 }
 
 struct Geom {
-  int KC, slot_bytes, act_bytes, n_slots, off_act, off_ring, mt, stream_down;
+  int KC, slot_bytes, act_bytes, n_slots, off_act, off_ring, mt, stream_down, kstg, attn_off;
   size_t smem;
 };
 
@@ -1085,9 +1151,11 @@ bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int ma
   int act = std::max(res_h, stream_down ? strm : res_i);
   const int hs = (B * n_q <= grid) ? 1 : n_q / n_kv;
   const int tmax = (max_kv_len + 3) & ~3;
+  const int kstg = hs == 1 ? std::min(256, (max_kv_len + 15) & ~15) : 0;  // K rows staged before the barrier
   const int attn = hs * hd * 4 + 2 * hd * 2 + hs * tmax * 4 + (max_kv_len + 32) * 4 /* pages: <= one per position */ +
-                   2 * VT * hd * 2;
-  act = std::max(act, attn);
+                   2 * VT * hd * 2 + kstg * (hd * 2 + 16) + 2 * hd * 2 + hd * 4 + 64;
+  const int attn_off = kstg > 0 ? ((res_h + 127) & ~127) : 0;  // staged attention areas live behind the resident rows
+  act = std::max(act, attn + attn_off);
   const int off_act = (OFF_WNORM + 2 * H * 2 + 127) & ~127;
   const int off_ring = (off_act + act + 1023) & ~1023;  // swizzled TMA tiles: 1024-byte aligned slots
   const int slot = 16 * KC * 2;                          // gate + up boxes of 8 rows x KC
@@ -1103,6 +1171,8 @@ bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int ma
   g->off_ring = off_ring;
   g->mt = mt;
   g->stream_down = stream_down;
+  g->kstg = kstg;
+  g->attn_off = attn_off;
   g->smem = (size_t)off_ring + (size_t)S * slot;
   return true;
 }
@@ -1137,6 +1207,8 @@ cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st) {
   a.off_act = g.off_act;
   a.off_ring = g.off_ring;
   a.stream_down = g.stream_down;
+  a.attn_kstg = g.kstg;
+  a.attn_off = g.attn_off;
   a.dist_norm = a.B > 16 && a.B <= num_sms && a.xn != nullptr;
   {  // per phase kind: units of a CTA (q, +1 for the first r CTAs), chunks, and ring advances modulo the slot count
     const int Dq = a.n_q * a.hd, Dkv = a.n_kv * a.hd;

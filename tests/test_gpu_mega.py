@@ -88,6 +88,17 @@ def test_mega_layer_activations(qie, n_layers):
     eng.close()
 
 
+@pytest.mark.parametrize("arch,n_seq", [("qwen2.5-1.5b", 3), ("qwen2.5-7b", 1)])
+def test_mega_larger_architectures(qie, arch, n_seq):
+    """BASELINE configs[2] / [4] shapes (head_dim 128, 28 layers): the persistent kernel equals the
+    per-operator path on the 1.5B and 7B architectures too."""
+    want_t, want_l, _ = _run(qie, arch, n_seq, 5, 4, use_mega=False)
+    got_t, got_l, _ = _run(qie, arch, n_seq, 5, 4, use_mega=True)
+    for i in range(4):
+        assert np.array_equal(got_l[i], want_l[i]), f"logits differ at step {i}"
+    assert np.array_equal(got_t, want_t)
+
+
 def test_mega_qwen05b_batch64_long_context(qie):
     """BASELINE configs[1] shape: 0.5B-arch, 64 sequences, synthetic KV of 300..363 positions
     (several V tiles, ragged lengths) -- tokens and logits equal the per-operator path."""
