@@ -391,6 +391,10 @@ __device__ __forceinline__ void gemm_inner(const MegaArgs& a, const Phase& p, ui
     for (int m = 0; m < TWW; ++m)
 #pragma unroll
       for (int i = 0; i < 4; ++i) acc[m][i] = acc2[m][i] = 0.f;
+    // <= 8 rows: the residual value of the epilogue is requested before the MMA chain, not after it
+    uint32_t res_old = 0u;
+    if (MT == 0 && has && (p.kind == PH_O || p.kind == PH_DOWN) && g < a.B && row0 + c * 2 < p.rows[seg])
+      res_old = __ldcg(reinterpret_cast<const uint32_t*>(a.x + (size_t)g * a.H + row0 + c * 2));
     if (stream) a_chunk_load(0);
     // ring position of this warp's first job of the round; consecutive chunks are nact jobs apart
     RingPos me = rnd;
@@ -464,7 +468,7 @@ __device__ __forceinline__ void gemm_inner(const MegaArgs& a, const Phase& p, ui
           case PH_O:
           case PH_DOWN: {
             uint32_t* dst = reinterpret_cast<uint32_t*>(a.x + (size_t)tok * a.H + n);
-            const uint32_t old = __ldcg(dst);
+            const uint32_t old = MT == 0 ? res_old : __ldcg(dst);
             const float y0 = bf2f(f2bf(v0)), y1 = bf2f(f2bf(v1));
             *dst = pack2(f2bf(__fadd_rn(lo2f(old), y0)), f2bf(__fadd_rn(hi2f(old), y1)));
             break;
