@@ -342,6 +342,50 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[MT == 0 ? 1 : MT][4], flo
 // a_src == nullptr: the A operand [B, K] is resident in the activation region (row stride
 // (K+8)*2).  Otherwise it is streamed from global memory (row stride K) in KC-wide chunks
 // through two buffers of the activation region, all consumer threads copying.
+// One output pair (token tok, columns n, n+1) of a GEMM phase: the reference's rounding points
+// (R3, R8, R9 of SURVEY 8a) and, for lm_head, the running arg-max candidate of this lane.
+template <int MT>
+__device__ __forceinline__ void epilogue_store(const MegaArgs& a, const Phase& p, int seg, int tok, int n, float v0, float v1,
+                                               float w0, float w1, uint32_t res_old, Best& bb) {
+  const int Dq = a.n_q * a.hd, Dkv = a.n_kv * a.hd;
+  switch (p.kind) {
+    case PH_QKV: {
+      const int col = (seg == 0 ? 0 : (seg == 1 ? Dq : Dq + Dkv)) + n;
+      *reinterpret_cast<uint32_t*>(a.qkv + (size_t)tok * (Dq + 2 * Dkv) + col) = pack2(f2bf(v0), f2bf(v1));
+      break;
+    }
+    case PH_O:
+    case PH_DOWN: {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(a.x + (size_t)tok * a.H + n);
+      const uint32_t old = MT == 0 ? res_old : __ldcg(dst);
+      const float y0 = bf2f(f2bf(v0)), y1 = bf2f(f2bf(v1));
+      *dst = pack2(f2bf(__fadd_rn(lo2f(old), y0)), f2bf(__fadd_rn(hi2f(old), y1)));
+      break;
+    }
+    case PH_GATEUP: {
+      const float g0 = bf2f(f2bf(v0)), g1 = bf2f(f2bf(v1));
+      const float u0 = bf2f(f2bf(w0)), u1 = bf2f(f2bf(w1));
+      const float s0 = bf2f(f2bf(silu_ref(g0))), s1 = bf2f(f2bf(silu_ref(g1)));
+      *reinterpret_cast<uint32_t*>(a.h + (size_t)tok * a.I + n) = pack2(f2bf(__fmul_rn(u0, s0)), f2bf(__fmul_rn(u1, s1)));
+      break;
+    }
+    default: {  // PH_LMHEAD
+      const bf16 l0 = f2bf(v0), l1 = f2bf(v1);
+      *reinterpret_cast<uint32_t*>(a.logits + (size_t)tok * a.V + n) = pack2(l0, l1);
+      const float f0 = bf2f(l0), f1 = bf2f(l1);
+      if (f0 > -CUDART_INF_F && cand_better(f0, n, bb.v, bb.i)) {
+        bb.v = f0;
+        bb.i = n;
+      }
+      if (f1 > -CUDART_INF_F && cand_better(f1, n + 1, bb.v, bb.i)) {
+        bb.v = f1;
+        bb.i = n + 1;
+      }
+      break;
+    }
+  }
+}
+
 // TW = token tiles per warp: TW == MT -> one warp per unit (all tiles); TW < MT -> the MT/TW warps
 // of a unit share its weight tile, each with its own token tiles (phases with one unit per
 // CTA: more dependent HMMA chains run side by side instead of back to back in one warp).
@@ -363,7 +407,6 @@ __device__ __forceinline__ void gemm_inner(const MegaArgs& a, const Phase& p, ui
   const int AS = stream ? RS : (p.K + 8) * 2;  // activation row stride in shared memory (bytes)
   const int g = lane >> 2, c = lane & 3;
   const int n_c = p.n_c, nch = p.nch;
-  const int Dq = a.n_q * a.hd, Dkv = a.n_kv * a.hd;
   RingPos rnd = base;  // first job of the current round
 
   auto a_chunk_load = [&](int ch) {  // stream mode: rows [0,B) x [ch*KC, +klen) -> buffer ch&1
@@ -458,45 +501,8 @@ __device__ __forceinline__ void gemm_inner(const MegaArgs& a, const Phase& p, ui
       for (int hr = 0; hr < (MT == 0 ? 1 : 2); ++hr) {
         const int tok = (m0 + m) * 16 + g + hr * 8;
         if (tok >= a.B) continue;
-        const float v0 = acc[m][hr * 2], v1 = acc[m][hr * 2 + 1];
-        switch (p.kind) {
-          case PH_QKV: {
-            const int col = (seg == 0 ? 0 : (seg == 1 ? Dq : Dq + Dkv)) + n;
-            *reinterpret_cast<uint32_t*>(a.qkv + (size_t)tok * (Dq + 2 * Dkv) + col) = pack2(f2bf(v0), f2bf(v1));
-            break;
-          }
-          case PH_O:
-          case PH_DOWN: {
-            uint32_t* dst = reinterpret_cast<uint32_t*>(a.x + (size_t)tok * a.H + n);
-            const uint32_t old = MT == 0 ? res_old : __ldcg(dst);
-            const float y0 = bf2f(f2bf(v0)), y1 = bf2f(f2bf(v1));
-            *dst = pack2(f2bf(__fadd_rn(lo2f(old), y0)), f2bf(__fadd_rn(hi2f(old), y1)));
-            break;
-          }
-          case PH_GATEUP: {
-            const float g0 = bf2f(f2bf(v0)), g1 = bf2f(f2bf(v1));
-            const float u0 = bf2f(f2bf(acc2[m][hr * 2])), u1 = bf2f(f2bf(acc2[m][hr * 2 + 1]));
-            const float s0 = bf2f(f2bf(silu_ref(g0))), s1 = bf2f(f2bf(silu_ref(g1)));
-            *reinterpret_cast<uint32_t*>(a.h + (size_t)tok * a.I + n) =
-                pack2(f2bf(__fmul_rn(u0, s0)), f2bf(__fmul_rn(u1, s1)));
-            break;
-          }
-          default: {  // PH_LMHEAD
-            const bf16 l0 = f2bf(v0), l1 = f2bf(v1);
-            *reinterpret_cast<uint32_t*>(a.logits + (size_t)tok * a.V + n) = pack2(l0, l1);
-            const float f0 = bf2f(l0), f1 = bf2f(l1);
-            Best& bb = best[TW == MT ? m : 0][hr];  // lm_head never splits tiles (128 units per CTA)
-            if (f0 > -CUDART_INF_F && cand_better(f0, n, bb.v, bb.i)) {
-              bb.v = f0;
-              bb.i = n;
-            }
-            if (f1 > -CUDART_INF_F && cand_better(f1, n + 1, bb.v, bb.i)) {
-              bb.v = f1;
-              bb.i = n + 1;
-            }
-            break;
-          }
-        }
+        epilogue_store<MT>(a, p, seg, tok, n, acc[m][hr * 2], acc[m][hr * 2 + 1], acc2[m][hr * 2], acc2[m][hr * 2 + 1],
+                           res_old, best[TW == MT ? m : 0][hr]);
       }
   }
   const int cls = (int)blockIdx.x < a.ph_r[p.kind] ? 1 : 0;
@@ -570,6 +576,139 @@ __device__ __forceinline__ void rmsnorm_rows(const MegaArgs& a, unsigned char* s
       for (int j = 0; j < 4; ++j) cur[j] = nxt[j];
     }
     rms_s[threadIdx.x] = __fsqrt_rn(__fadd_rn(__fdiv_rn(sum, (float)H), 1e-04f));
+  }
+  bar_consumers();
+  const int per = H >> 3;
+  for (int i = threadIdx.x; i < B * per; i += NTC) {
+    const int b = i / per, cc = i - b * per;
+    uint4* p = reinterpret_cast<uint4*>(act + b * AS + cc * 16);
+    const uint4 v = *p;
+    const uint4 wv = *reinterpret_cast<const uint4*>(w + cc * 8);
+    const float rms = rms_s[b];
+    uint4 o;
+    o.x = pack2(f2bf(__fmul_rn(__fdiv_rn(lo2f(v.x), rms), lo2f(wv.x))), f2bf(__fmul_rn(__fdiv_rn(hi2f(v.x), rms), hi2f(wv.x))));
+    o.y = pack2(f2bf(__fmul_rn(__fdiv_rn(lo2f(v.y), rms), lo2f(wv.y))), f2bf(__fmul_rn(__fdiv_rn(hi2f(v.y), rms), hi2f(wv.y))));
+    o.z = pack2(f2bf(__fmul_rn(__fdiv_rn(lo2f(v.z), rms), lo2f(wv.z))), f2bf(__fmul_rn(__fdiv_rn(hi2f(v.z), rms), hi2f(wv.z))));
+    o.w = pack2(f2bf(__fmul_rn(__fdiv_rn(lo2f(v.w), rms), lo2f(wv.w))), f2bf(__fmul_rn(__fdiv_rn(hi2f(v.w), rms), hi2f(wv.w))));
+    *p = o;
+  }
+  bar_consumers();
+}
+
+// FAST numerics (tolerance, not bit-exact), <= 8 rows: every unit is shared by ALL consumer
+// warps -- warp w takes the 64-wide k-groups g with g % NW == w of every weight tile -- so the
+// dependent HMMA chain per warp is 1/NW of the reference's; partial sums meet in shared memory
+// (fixed order, deterministic).  Units run in rounds of <= FAST_U so one reduction serves several.
+constexpr int FAST_U = 4;
+__device__ __forceinline__ void gemm_phase_fast(const MegaArgs& a, const Phase& p, uint32_t smem_base, RingPos& base,
+                                                Best (&best)[1][2], unsigned char* smem) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t S = a.n_slots;
+  const int KC = a.KC;
+  const uint32_t ring = smem_base + a.off_ring, act = smem_base + a.off_act;
+  const int AS = (p.K + 8) * 2;
+  const int g = lane >> 2, c = lane & 3;
+  const int n_c = p.n_c, nch = p.nch, U = p.nu;
+  float* red = reinterpret_cast<float*>(smem + a.off_red);  // [FAST_U][NW][32][8]
+  RingPos me = base;
+  for (int r0 = 0; r0 < n_c; r0 += U) {
+    const int nact = min(U, n_c - r0);
+    float acc[FAST_U][1][4], acc2[FAST_U][1][4];
+#pragma unroll
+    for (int u = 0; u < FAST_U; ++u)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc[u][0][i] = acc2[u][0][i] = 0.f;
+    for (int ch = 0; ch < nch; ++ch) {
+      const int k0 = ch * KC;
+      const int ngr = min(KC, p.K - k0) >> 6;
+#pragma unroll
+      for (int u = 0; u < FAST_U; ++u) {
+        if (u < nact) {
+          if (lds32_volatile(smem_base + OFF_ISSUED) <= me.job) {
+            const long long t0 = clock64();
+            while (lds32_volatile(smem_base + OFF_ISSUED) <= me.job)
+              if (clock64() - t0 > SPIN_LIMIT) __trap();
+          }
+          mbar_wait(smem_base + OFF_FULL + me.slot * 8, me.par);
+          const uint32_t slot_addr = ring + me.slot * a.slot_bytes;
+          for (int gi = warp; gi < ngr; gi += NW) {
+            if (p.dual)
+              mma_chunk<0, true>(acc[u], acc2[u], slot_addr + gi * 1024, act + (k0 + gi * 64) * 2, AS, 8 * KC * 2, 4, a.B, lane);
+            else
+              mma_chunk<0, false>(acc[u], acc2[u], slot_addr + gi * 1024, act + (k0 + gi * 64) * 2, AS, 0, 4, a.B, lane);
+          }
+          __syncwarp();
+          if (lane == 0) {  // the last warp through releases the slot
+            uint32_t* rel = reinterpret_cast<uint32_t*>(smem + OFF_REL) + me.slot;
+            if (atomicAdd(rel, 1u) == (uint32_t)(NW - 1)) {
+              *rel = 0u;
+              mbar_arrive(smem_base + OFF_EMPTY + me.slot * 8);
+            }
+          }
+          me.step(1, S);
+        }
+      }
+    }
+    // partial sums -> shared memory; warp u finishes unit u of the round
+#pragma unroll
+    for (int u = 0; u < FAST_U; ++u) {
+      if (u < nact) {
+        float4* dst = reinterpret_cast<float4*>(red + ((size_t)(u * NW + warp) * 32 + lane) * 8);
+        dst[0] = make_float4(acc[u][0][0], acc[u][0][1], acc[u][0][2], acc[u][0][3]);
+        dst[1] = make_float4(acc2[u][0][0], acc2[u][0][1], acc2[u][0][2], acc2[u][0][3]);
+      }
+    }
+    bar_consumers();
+    if (warp < nact) {
+      float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
+      for (int w = 0; w < NW; ++w) {
+        const float4* src = reinterpret_cast<const float4*>(red + ((size_t)(warp * NW + w) * 32 + lane) * 8);
+        const float4 x = src[0], y = src[1];
+        s0 += x.x;
+        s1 += x.y;
+        t0 += y.x;
+        t1 += y.y;
+      }
+      const int u = blockIdx.x + (r0 + warp) * gridDim.x;
+      int seg = 0;
+      while (seg + 1 < p.nseg && u >= p.ubeg[seg + 1]) ++seg;
+      const int row0 = (u - p.ubeg[seg]) << 3;
+      const int n = row0 + c * 2;
+      if (g < a.B && n < p.rows[seg]) {
+        uint32_t res_old = 0u;
+        if (p.kind == PH_O || p.kind == PH_DOWN) res_old = __ldcg(reinterpret_cast<const uint32_t*>(a.x + (size_t)g * a.H + n));
+        epilogue_store<0>(a, p, seg, g, n, s0, s1, t0, t1, res_old, best[0][0]);
+      }
+    }
+    bar_consumers();  // red[] is rewritten by the next round
+  }
+  base = me;
+}
+
+// FAST numerics RMSNorm: the sum of squares is reduced in parallel (one warp per row)
+__device__ __forceinline__ void rmsnorm_rows_fast(const MegaArgs& a, unsigned char* smem, int B, int H, int which) {
+  const int AS = (H + 8) * 2;
+  unsigned char* act = smem + a.off_act;
+  const bf16* w = reinterpret_cast<const bf16*>(smem + OFF_WNORM + which * H * 2);
+  float* rms_s = reinterpret_cast<float*>(smem + OFF_RMS);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int b = warp; b < B; b += NW) {
+    const uint4* row = reinterpret_cast<const uint4*>(act + b * AS);
+    float sum = 0.f;
+    for (int i = lane; i < (H >> 3); i += 32) {
+      const uint4 v = row[i];
+      float f;
+      f = lo2f(v.x); sum += f * f;
+      f = hi2f(v.x); sum += f * f;
+      f = lo2f(v.y); sum += f * f;
+      f = hi2f(v.y); sum += f * f;
+      f = lo2f(v.z); sum += f * f;
+      f = hi2f(v.z); sum += f * f;
+      f = lo2f(v.w); sum += f * f;
+      f = hi2f(v.w); sum += f * f;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) rms_s[b] = __fsqrt_rn(__fadd_rn(__fdiv_rn(sum, (float)H), 1e-04f));
   }
   bar_consumers();
   const int per = H >> 3;
@@ -933,7 +1072,7 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
 }
 
 // ---------------------------------------------------------------- the kernel
-template <int NP, int MT>
+template <int NP, int MT, bool FAST>
 __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __grid_constant__ MegaArgs a) {
   constexpr int MTT = MT == 0 ? 1 : MT;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -1039,7 +1178,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
       } else {
         load_rows(act, a.B, H, [&](int b) { return from_embed ? a.embed + (size_t)a.ids[b] * H : a.x + (size_t)b * H; });
         stamp();
-        rmsnorm_rows(a, smem, a.B, H, which);
+        if (FAST)
+          rmsnorm_rows_fast(a, smem, a.B, H, which);
+        else
+          rmsnorm_rows(a, smem, a.B, H, which);
         stamp();
       }
     }
@@ -1047,7 +1189,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
     make_phase(a, idx, p);
     if (kind == PH_QKV && a.attn_kstg > 0)
       attention_phase<NP>(a, l, smem, 0);  // warps 1..: request what attention needs that does not depend on q/k/v
-    gemm_phase<MT>(a, p, smem_base, ring_pos, a_src, best, smem + OFF_DBG);
+    bool done = false;
+    if constexpr (FAST) {  // fast numerics: K of every unit split over the warps of the CTA
+      gemm_phase_fast(a, p, smem_base, ring_pos, best, smem);
+      done = true;
+    }
+    if (!done) gemm_phase<MT>(a, p, smem_base, ring_pos, a_src, best, smem + OFF_DBG);
     stamp();
     if (kind == PH_LMHEAD) {
       // candidates: lanes (g, c) of a warp hold tokens 16m + g (+8); reduce over c, then over warps
@@ -1126,7 +1273,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
 }
 
 struct Geom {
-  int KC, slot_bytes, act_bytes, n_slots, off_act, off_ring, mt, stream_down, kstg, attn_off;
+  int KC, slot_bytes, act_bytes, n_slots, off_act, off_ring, mt, stream_down, kstg, attn_off, off_red;
   size_t smem;
 };
 
@@ -1141,7 +1288,7 @@ int kc_for(int H, int big) {
   return KC;
 }
 
-bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int grid, int KC, Geom* g) {
+bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int grid, int KC, int fast, Geom* g) {
   const int Dq = n_q * hd;
   if ((H % 64) || (I % 64) || (Dq % 64) || (hd != 64 && hd != 128) || KC < 64 || (KC % 64)) return false;
   if (B < 1 || B > MAX_ROWS || n_q % n_kv || n_q / n_kv > 2 * NW || L > MAX_LAYERS) return false;
@@ -1151,7 +1298,8 @@ bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int ma
   const int res_h = rows_a * (std::max(H, Dq) + 8) * 2;
   const int res_i = rows_a * (I + 8) * 2;
   const int strm = 2 * bpad * (KC + 8) * 2;
-  const int stream_down = res_i > 48 * 1024;
+  if (fast && B > 8) return false;
+  const int stream_down = !fast && res_i > 48 * 1024;  // fast numerics keeps [B, I] resident (<= 8 rows)
   int act = std::max(res_h, stream_down ? strm : res_i);
   const int hs = (B * n_q <= grid) ? 1 : n_q / n_kv;
   const int tmax = (max_kv_len + 3) & ~3;
@@ -1161,7 +1309,9 @@ bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int ma
   const int attn_off = kstg > 0 ? ((res_h + 127) & ~127) : 0;  // staged attention areas live behind the resident rows
   act = std::max(act, attn + attn_off);
   const int off_act = (OFF_WNORM + 2 * H * 2 + 127) & ~127;
-  const int off_ring = (off_act + act + 1023) & ~1023;  // swizzled TMA tiles: 1024-byte aligned slots
+  const int off_red = off_act + ((act + 127) & ~127);     // fast numerics: split-K partial sums [FAST_U][NW][32][8] fp32
+  const int red = fast ? FAST_U * NW * 32 * 8 * 4 : 0;
+  const int off_ring = (off_red + red + 1023) & ~1023;  // swizzled TMA tiles: 1024-byte aligned slots
   const int slot = 16 * KC * 2;                          // gate + up boxes of 8 rows x KC
   const int budget = 227 * 1024 - off_ring;
   int S = budget / slot;
@@ -1177,6 +1327,7 @@ bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int ma
   g->stream_down = stream_down;
   g->kstg = kstg;
   g->attn_off = attn_off;
+  g->off_red = off_red;
   g->smem = (size_t)off_ring + (size_t)S * slot;
   return true;
 }
@@ -1185,26 +1336,27 @@ bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int ma
 
 int decode_mega_kc(int H, int big) { return kc_for(H, big); }
 
-bool decode_mega_supports(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int num_sms, int KC) {
+bool decode_mega_supports(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int num_sms, int KC, int fast) {
   Geom g;
-  return mega_geometry(H, I, L, n_q, n_kv, hd, B, max_kv_len, num_sms, KC, &g);
+  return mega_geometry(H, I, L, n_q, n_kv, hd, B, max_kv_len, num_sms, KC, fast, &g);
 }
 
 int decode_mega_prof_slots(int L) { return 2 * (16 * L + 8) + 16; }
 
 template <int NP>
-static void (*pick_kernel(int mt))(MegaArgs) {
+static void (*pick_kernel(int mt, bool fast))(MegaArgs) {
+  if (fast) return decode_mega_kernel<NP, 0, true>;  // fast numerics: <= 8 rows only
   switch (mt) {
-    case 0: return decode_mega_kernel<NP, 0>;
-    case 1: return decode_mega_kernel<NP, 1>;
-    case 2: return decode_mega_kernel<NP, 2>;
-    default: return decode_mega_kernel<NP, 4>;
+    case 0: return decode_mega_kernel<NP, 0, false>;
+    case 1: return decode_mega_kernel<NP, 1, false>;
+    case 2: return decode_mega_kernel<NP, 2, false>;
+    default: return decode_mega_kernel<NP, 4, false>;
   }
 }
 
 cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st) {
   Geom g;
-  if (!mega_geometry(a.H, a.I, a.L, a.n_q, a.n_kv, a.hd, a.B, a.max_kv_len, num_sms, a.KC, &g)) return cudaErrorInvalidValue;
+  if (!mega_geometry(a.H, a.I, a.L, a.n_q, a.n_kv, a.hd, a.B, a.max_kv_len, num_sms, a.KC, a.fast, &g)) return cudaErrorInvalidValue;
   a.slot_bytes = g.slot_bytes;
   a.act_bytes = g.act_bytes;
   a.n_slots = g.n_slots;
@@ -1213,6 +1365,7 @@ cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st) {
   a.stream_down = g.stream_down;
   a.attn_kstg = g.kstg;
   a.attn_off = g.attn_off;
+  a.off_red = g.off_red;
   a.dist_norm = a.B > 16 && a.B <= num_sms && a.xn != nullptr;
   {  // per phase kind: units of a CTA (q, +1 for the first r CTAs), chunks, and ring advances modulo the slot count
     const int Dq = a.n_q * a.hd, Dkv = a.n_kv * a.hd;
@@ -1232,12 +1385,14 @@ cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st) {
       const int mtt = g.mt == 0 ? 1 : g.mt;
       const bool split = mtt >= 2 && units[k] <= num_sms && k != 4;
       a.ph_nu[k] = split ? NW / mtt : NW;
+      if (a.fast)  // split-K rounds of <= FAST_U units
+        a.ph_nu[k] = std::max(1, std::min(FAST_U, (units[k] + num_sms - 1) / num_sms));
       const int rj = a.ph_nu[k] * a.ph_nch[k];
       a.ph_round_slot[k] = rj % S;
       a.ph_round_par[k] = (rj / S) & 1;
     }
   }
-  void (*kern)(MegaArgs) = a.hd == 64 ? pick_kernel<1>(g.mt) : pick_kernel<2>(g.mt);
+  void (*kern)(MegaArgs) = a.hd == 64 ? pick_kernel<1>(g.mt, a.fast != 0) : pick_kernel<2>(g.mt, a.fast != 0);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(a.bar, 0, sizeof(unsigned), st);

@@ -293,17 +293,19 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
 // weight-tile set: larger tiles for small batches when the ring still holds enough of them
 static int mega_tile_set(const qie_engine* e, int n, int max_kv_len) {
   const qie_config& c = e->cfg;
+  const int fast = e->opts.numerics == QIE_NUMERICS_FAST;
   if (n <= 8 && e->mega_kc[1] > e->mega_kc[0] &&
-      decode_mega_supports(c.hidden, c.inter, c.layers, c.n_q, c.n_kv, c.head_dim, n, max_kv_len, e->num_sms, e->mega_kc[1]))
+      decode_mega_supports(c.hidden, c.inter, c.layers, c.n_q, c.n_kv, c.head_dim, n, max_kv_len, e->num_sms, e->mega_kc[1], fast))
     return 1;
   return 0;
 }
 
 bool decode_uses_mega(const qie_engine* e, int n, int max_kv_len) {
-  if (!e->use_mega || e->opts.numerics != QIE_NUMERICS_REFERENCE_ORDER || e->capture || !e->mega_layers_d) return false;
+  if (!e->use_mega || e->capture || !e->mega_layers_d) return false;
   const qie_config& c = e->cfg;
+  const int fast = e->opts.numerics == QIE_NUMERICS_FAST;  // fast numerics: persistent kernel for <= 8 rows
   return decode_mega_supports(c.hidden, c.inter, c.layers, c.n_q, c.n_kv, c.head_dim, n, max_kv_len, e->num_sms,
-                              e->mega_kc[mega_tile_set(e, n, max_kv_len)]);
+                              e->mega_kc[mega_tile_set(e, n, max_kv_len)], fast);
 }
 
 cudaError_t forward_decode_mega(qie_engine* e, int n, int max_kv_len, float temperature) {
@@ -346,6 +348,7 @@ cudaError_t forward_decode_mega(qie_engine* e, int n, int max_kv_len, float temp
   a.prof = e->mega_prof_on ? e->mega_prof_d : nullptr;
   a.prof_stride = 16 * c.layers + 8;
   a.greedy = e->topk == 1;
+  a.fast = e->opts.numerics == QIE_NUMERICS_FAST ? 1 : 0;
   a.advance = 1;
   a.n_layers_run = e->mega_layers_run;
   cudaError_t r = launch_decode_mega(a, e->num_sms, e->stream);
