@@ -352,7 +352,17 @@ cudaError_t forward_decode_mega(qie_engine* e, int n, int max_kv_len, float temp
   a.advance = 1;
   a.n_layers_run = e->mega_layers_run;
   cudaError_t r = launch_decode_mega(a, e->num_sms, e->stream);
-  if (r != cudaSuccess) return r;
+  if (r != cudaSuccess) {
+    // e.g. the cooperative launch cannot be co-scheduled (SMs taken by another context): this
+    // engine falls back to the per-operator GPU launches for good (still no CPU path).  A shape
+    // is always run eagerly before it is captured into a graph, so this never happens mid-capture.
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(e->stream, &cs);
+    if (cs != cudaStreamCaptureStatusNone) return r;
+    (void)cudaGetLastError();
+    e->use_mega = false;
+    return forward_rows(e, n, max_kv_len, 0, n, temperature, true);
+  }
   ++e->launches;
   if (!a.greedy && e->mega_layers_run <= 0) {
     // top-k > 1: the sampler is the reference's k-round scan + XORWOW draw (logit_decode.cu:149-274)
