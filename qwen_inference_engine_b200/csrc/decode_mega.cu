@@ -133,6 +133,7 @@ struct Phase {
   int ubeg[4];
   int nseg, K, dual, units, kind;
   int n_c, nch, nu;  // units of THIS CTA, chunks per unit, units per round (host-precomputed tables)
+  int upr, row2;     // weight rows per unit (8, or 16 for lm_head pairs), row offset of the second tile of a dual unit
 };
 
 __device__ __forceinline__ void make_phase(const MegaArgs& a, int idx, Phase& p) {
@@ -141,8 +142,12 @@ __device__ __forceinline__ void make_phase(const MegaArgs& a, int idx, Phase& p)
   p.dual = 0;
   p.nseg = 1;
   if (idx >= 4 * a.L) {
+    // lm_head: a unit is a PAIR of 8-row tiles (rows r..r+7 and r+8..r+15) accumulated side by side
+    // like gate/up: two independent HMMA chains per warp and each activation fragment feeds both
     p.kind = PH_LMHEAD;
     p.W[0] = a.wmaps + 7 * a.L;
+    p.W2 = p.W[0];
+    p.dual = 1;
     p.rows[0] = a.V;
     p.K = a.H;
   } else {
@@ -166,10 +171,12 @@ __device__ __forceinline__ void make_phase(const MegaArgs& a, int idx, Phase& p)
         break;
     }
   }
+  p.upr = p.kind == PH_LMHEAD ? 16 : 8;
+  p.row2 = p.kind == PH_LMHEAD ? 8 : 0;
   int u = 0;
   for (int s = 0; s < p.nseg; ++s) {
     p.ubeg[s] = u;
-    u += (p.rows[s] + 7) >> 3;
+    u += (p.rows[s] + p.upr - 1) / p.upr;
   }
   p.ubeg[p.nseg] = u;
   p.units = u;
@@ -224,7 +231,7 @@ __device__ __forceinline__ void producer_loop(const MegaArgs& a, uint32_t smem_b
           const int u = blockIdx.x + (r0 + s) * gridDim.x;
           int seg = 0;
           while (seg + 1 < p.nseg && u >= p.ubeg[seg + 1]) ++seg;
-          const int row0 = (u - p.ubeg[seg]) << 3;
+          const int row0 = (u - p.ubeg[seg]) * p.upr;
           const uint32_t full = smem_base + OFF_FULL + slot * 8, empty = smem_base + OFF_EMPTY + slot * 8;
           mbar_wait(empty, par ^ 1);
           mbar_expect_tx(full, p.dual ? 2 * box_bytes : box_bytes);  // out-of-range rows / k-blocks are zero-filled
@@ -232,7 +239,7 @@ __device__ __forceinline__ void producer_loop(const MegaArgs& a, uint32_t smem_b
           sts32_volatile(smem_base + OFF_ISSUED, job + 1);
           const uint32_t dst = ring + slot * a.slot_bytes;
           tma_load_3d(dst, p.W[seg], full, 0, row0, ch * (KC / 64));
-          if (p.dual) tma_load_3d(dst + box_bytes, p.W2, full, 0, row0, ch * (KC / 64));
+          if (p.dual) tma_load_3d(dst + box_bytes, p.W2, full, 0, row0 + p.row2, ch * (KC / 64));
           ++job;
           if (++slot == S) {
             slot = 0;
@@ -427,7 +434,7 @@ __device__ __forceinline__ void gemm_inner(const MegaArgs& a, const Phase& p, ui
     if (has) {
       const int u = blockIdx.x + (r0 + us) * gridDim.x;
       while (seg + 1 < p.nseg && u >= p.ubeg[seg + 1]) ++seg;
-      row0 = (u - p.ubeg[seg]) << 3;
+      row0 = (u - p.ubeg[seg]) * p.upr;
     }
     float acc[TWW][4], acc2[TWW][4];
 #pragma unroll
@@ -503,6 +510,9 @@ __device__ __forceinline__ void gemm_inner(const MegaArgs& a, const Phase& p, ui
         if (tok >= a.B) continue;
         epilogue_store<MT>(a, p, seg, tok, n, acc[m][hr * 2], acc[m][hr * 2 + 1], acc2[m][hr * 2], acc2[m][hr * 2 + 1],
                            res_old, best[TW == MT ? m : 0][hr]);
+        if (p.kind == PH_LMHEAD && n + 8 < p.rows[seg])  // second tile of the pair
+          epilogue_store<MT>(a, p, seg, tok, n + 8, acc2[m][hr * 2], acc2[m][hr * 2 + 1], 0.f, 0.f, 0u,
+                             best[TW == MT ? m : 0][hr]);
       }
   }
   const int cls = (int)blockIdx.x < a.ph_r[p.kind] ? 1 : 0;
@@ -672,12 +682,13 @@ __device__ __forceinline__ void gemm_phase_fast(const MegaArgs& a, const Phase& 
       const int u = blockIdx.x + (r0 + warp) * gridDim.x;
       int seg = 0;
       while (seg + 1 < p.nseg && u >= p.ubeg[seg + 1]) ++seg;
-      const int row0 = (u - p.ubeg[seg]) << 3;
+      const int row0 = (u - p.ubeg[seg]) * p.upr;
       const int n = row0 + c * 2;
       if (g < a.B && n < p.rows[seg]) {
         uint32_t res_old = 0u;
         if (p.kind == PH_O || p.kind == PH_DOWN) res_old = __ldcg(reinterpret_cast<const uint32_t*>(a.x + (size_t)g * a.H + n));
         epilogue_store<0>(a, p, seg, g, n, s0, s1, t0, t1, res_old, best[0][0]);
+        if (p.kind == PH_LMHEAD && n + 8 < p.rows[seg]) epilogue_store<0>(a, p, seg, g, n + 8, t0, t1, 0.f, 0.f, 0u, best[0][0]);
       }
     }
     bar_consumers();  // red[] is rewritten by the next round
@@ -1369,7 +1380,7 @@ cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st) {
   a.dist_norm = a.B > 16 && a.B <= num_sms && a.xn != nullptr;
   {  // per phase kind: units of a CTA (q, +1 for the first r CTAs), chunks, and ring advances modulo the slot count
     const int Dq = a.n_q * a.hd, Dkv = a.n_kv * a.hd;
-    const int units[5] = {(Dq + 7) / 8 + 2 * ((Dkv + 7) / 8), (a.H + 7) / 8, (a.I + 7) / 8, (a.H + 7) / 8, (a.V + 7) / 8};
+    const int units[5] = {(Dq + 7) / 8 + 2 * ((Dkv + 7) / 8), (a.H + 7) / 8, (a.I + 7) / 8, (a.H + 7) / 8, (a.V + 15) / 16};
     const int Ks[5] = {a.H, Dq, a.H, a.I, a.H};
     const int S = g.n_slots;
     for (int k = 0; k < 5; ++k) {
