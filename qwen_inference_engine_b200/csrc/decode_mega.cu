@@ -349,11 +349,26 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[MT == 0 ? 1 : MT][4], flo
 // a_src == nullptr: the A operand [B, K] is resident in the activation region (row stride
 // (K+8)*2).  Otherwise it is streamed from global memory (row stride K) in KC-wide chunks
 // through two buffers of the activation region, all consumer threads copying.
+// lm_head output pair: bf16 logits (R10) + the running arg-max candidate of this lane
+__device__ __forceinline__ void lm_store(const MegaArgs& a, int tok, int n, float v0, float v1, Best& bb) {
+  const bf16 l0 = f2bf(v0), l1 = f2bf(v1);
+  *reinterpret_cast<uint32_t*>(a.logits + (size_t)tok * a.V + n) = pack2(l0, l1);
+  const float f0 = bf2f(l0), f1 = bf2f(l1);
+  if (f0 > -CUDART_INF_F && cand_better(f0, n, bb.v, bb.i)) {
+    bb.v = f0;
+    bb.i = n;
+  }
+  if (f1 > -CUDART_INF_F && cand_better(f1, n + 1, bb.v, bb.i)) {
+    bb.v = f1;
+    bb.i = n + 1;
+  }
+}
+
 // One output pair (token tok, columns n, n+1) of a GEMM phase: the reference's rounding points
-// (R3, R8, R9 of SURVEY 8a) and, for lm_head, the running arg-max candidate of this lane.
+// (R3, R8, R9 of SURVEY 8a).
 template <int MT>
 __device__ __forceinline__ void epilogue_store(const MegaArgs& a, const Phase& p, int seg, int tok, int n, float v0, float v1,
-                                               float w0, float w1, uint32_t res_old, Best& bb) {
+                                               float w0, float w1, uint32_t res_old) {
   const int Dq = a.n_q * a.hd, Dkv = a.n_kv * a.hd;
   switch (p.kind) {
     case PH_QKV: {
@@ -376,20 +391,8 @@ __device__ __forceinline__ void epilogue_store(const MegaArgs& a, const Phase& p
       *reinterpret_cast<uint32_t*>(a.h + (size_t)tok * a.I + n) = pack2(f2bf(__fmul_rn(u0, s0)), f2bf(__fmul_rn(u1, s1)));
       break;
     }
-    default: {  // PH_LMHEAD
-      const bf16 l0 = f2bf(v0), l1 = f2bf(v1);
-      *reinterpret_cast<uint32_t*>(a.logits + (size_t)tok * a.V + n) = pack2(l0, l1);
-      const float f0 = bf2f(l0), f1 = bf2f(l1);
-      if (f0 > -CUDART_INF_F && cand_better(f0, n, bb.v, bb.i)) {
-        bb.v = f0;
-        bb.i = n;
-      }
-      if (f1 > -CUDART_INF_F && cand_better(f1, n + 1, bb.v, bb.i)) {
-        bb.v = f1;
-        bb.i = n + 1;
-      }
+    default:
       break;
-    }
   }
 }
 
@@ -508,11 +511,13 @@ __device__ __forceinline__ void gemm_inner(const MegaArgs& a, const Phase& p, ui
       for (int hr = 0; hr < (MT == 0 ? 1 : 2); ++hr) {
         const int tok = (m0 + m) * 16 + g + hr * 8;
         if (tok >= a.B) continue;
-        epilogue_store<MT>(a, p, seg, tok, n, acc[m][hr * 2], acc[m][hr * 2 + 1], acc2[m][hr * 2], acc2[m][hr * 2 + 1],
-                           res_old, best[TW == MT ? m : 0][hr]);
-        if (p.kind == PH_LMHEAD && n + 8 < p.rows[seg])  // second tile of the pair
-          epilogue_store<MT>(a, p, seg, tok, n + 8, acc2[m][hr * 2], acc2[m][hr * 2 + 1], 0.f, 0.f, 0u,
-                             best[TW == MT ? m : 0][hr]);
+        if (p.kind == PH_LMHEAD) {  // both tiles of the pair
+          lm_store(a, tok, n, acc[m][hr * 2], acc[m][hr * 2 + 1], best[TW == MT ? m : 0][hr]);
+          if (n + 8 < p.rows[seg]) lm_store(a, tok, n + 8, acc2[m][hr * 2], acc2[m][hr * 2 + 1], best[TW == MT ? m : 0][hr]);
+        } else {
+          epilogue_store<MT>(a, p, seg, tok, n, acc[m][hr * 2], acc[m][hr * 2 + 1], acc2[m][hr * 2], acc2[m][hr * 2 + 1],
+                             res_old);
+        }
       }
   }
   const int cls = (int)blockIdx.x < a.ph_r[p.kind] ? 1 : 0;
@@ -687,8 +692,12 @@ __device__ __forceinline__ void gemm_phase_fast(const MegaArgs& a, const Phase& 
       if (g < a.B && n < p.rows[seg]) {
         uint32_t res_old = 0u;
         if (p.kind == PH_O || p.kind == PH_DOWN) res_old = __ldcg(reinterpret_cast<const uint32_t*>(a.x + (size_t)g * a.H + n));
-        epilogue_store<0>(a, p, seg, g, n, s0, s1, t0, t1, res_old, best[0][0]);
-        if (p.kind == PH_LMHEAD && n + 8 < p.rows[seg]) epilogue_store<0>(a, p, seg, g, n + 8, t0, t1, 0.f, 0.f, 0u, best[0][0]);
+        if (p.kind == PH_LMHEAD) {
+          lm_store(a, g, n, s0, s1, best[0][0]);
+          if (n + 8 < p.rows[seg]) lm_store(a, g, n + 8, t0, t1, best[0][0]);
+        } else {
+          epilogue_store<0>(a, p, seg, g, n, s0, s1, t0, t1, res_old);
+        }
       }
     }
     bar_consumers();  // red[] is rewritten by the next round
