@@ -119,6 +119,14 @@ int qie_attention_decode_fast(const qie_kv_view* kv, int layer, const qie_bf16* 
                               const int* slot, const int* block_table, int max_pages, int n_tok, int n_q_heads,
                               int n_splits, qie_stream st);
 
+/* FAST-numerics causal attention for PREFILL rows (same contract as qie_attention with the
+ * restriction that the n_tok rows are consecutive positions pos[0]+t of ONE sequence
+ * slot[0], which is what llm()'s prefill branch produces, qwen_main.cu:160-176):
+ * FlashAttention-2 style tiling on mma.sync, K/V streamed from the paged pool. */
+int qie_attention_prefill_fast(const qie_kv_view* kv, int layer, const qie_bf16* Q, qie_bf16* out, const int* pos,
+                               const int* slot, const int* block_table, int max_pages, int n_tok, int n_q_heads,
+                               qie_stream st);
+
 /* ------------------------------------------------------------------------------------
  * (2) driver level
  * ---------------------------------------------------------------------------------- */
@@ -178,6 +186,23 @@ int qie_engine_create_from_blob(const char* meta_path, void* device_blob, const 
 int qie_engine_create_synthetic(const qie_config* cfg, uint64_t seed, const qie_engine_opts* opts,
                                 qie_engine** out);
 void qie_engine_destroy(qie_engine* e);
+
+/* Tensor parallelism (BASELINE configs[4]; the reference is single-GPU): one
+ * process per GPU, every rank creates the engine with the same checkpoint and
+ * opts.tp_rank / opts.tp_size, then all ranks call qie_engine_tp_connect with the 128-byte
+ * id that rank 0 obtained from qie_tp_unique_id (carried between the processes by the
+ * caller: torch.distributed broadcast, a file, MPI ...).  Attention heads, the MLP
+ * intermediate dimension and the vocabulary are sharded; o_proj / down_proj partial sums
+ * are all-reduced with NCCL over NVLink; greedy sampling merges per-rank candidates in the
+ * reference's tie-break order, every rank returns the same tokens.  Prefill/decode calls
+ * are collective: all ranks must make the same calls in the same order. */
+/* HOST only: what rank tp_rank of tp_size owns. out8 = {n_q, n_kv, inter, vocab} local sizes
+ * then {q_row0, kv_row0, inter0, vocab0}: first q_proj / k,v_proj output row (= o_proj input
+ * column), first gate/up row (= down_proj input column), first lm_head row.  Vocabulary
+ * shards start at multiples of 256 (the sampler's tie-break key is idx mod 256). */
+int qie_tp_plan(const qie_config* cfg, int tp_rank, int tp_size, int* out8);
+int qie_tp_unique_id(void* out128);
+int qie_engine_tp_connect(qie_engine* e, const void* id128);
 int qie_engine_get_config(const qie_engine* e, qie_config* out);
 /* device pointer into the weight blob for (short_name, layer), as assign_weight_pointer
  * helpers.cuh:18-29; *n_elems receives the element count. NULL on miss. */

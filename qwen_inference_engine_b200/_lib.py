@@ -76,6 +76,7 @@ def lib():
         "qie_attention": (i32, [C.POINTER(KvView), i32, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
         "qie_sample_topk": (i32, [vp, vp, i32, sz, f32, i32, u64, u64, vp]),
         "qie_matmul_fast": (i32, [vp, vp, vp, i32, i32, i32, vp]),
+        "qie_attention_prefill_fast": (i32, [C.POINTER(KvView), i32, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
         "qie_attention_decode_fast": (i32, [C.POINTER(KvView), i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "qie_engine_opts_default": (None, [C.POINTER(EngineOpts)]),
         "qie_synth_checkpoint_write": (i32, [C.POINTER(Config), u64, C.c_char_p, C.c_char_p]),
@@ -84,6 +85,9 @@ def lib():
         "qie_engine_create_from_blob": (i32, [C.c_char_p, vp, C.POINTER(EngineOpts), C.POINTER(vp)]),
         "qie_engine_create_synthetic": (i32, [C.POINTER(Config), u64, C.POINTER(EngineOpts), C.POINTER(vp)]),
         "qie_engine_destroy": (None, [vp]),
+        "qie_tp_plan": (i32, [C.POINTER(Config), i32, i32, ip]),
+        "qie_tp_unique_id": (i32, [vp]),
+        "qie_engine_tp_connect": (i32, [vp, vp]),
         "qie_engine_get_config": (i32, [vp, C.POINTER(Config)]),
         "qie_engine_weight": (vp, [vp, C.c_char_p, i32, C.POINTER(sz)]),
         "qie_engine_kv_view": (i32, [vp, C.POINTER(KvView)]),

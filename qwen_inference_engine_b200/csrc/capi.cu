@@ -224,6 +224,29 @@ int qie_attention_decode_fast(const qie_kv_view* kv, int layer, const qie_bf16* 
   return QIE_OK;
 }
 
+int qie_attention_prefill_fast(const qie_kv_view* kv, int layer, const qie_bf16* Q, qie_bf16* out, const int* pos,
+                               const int* slot, const int* block_table, int max_pages, int n_tok, int n_q_heads,
+                               qie_stream st) {
+  if (!kv || layer < 0 || layer >= kv->n_layers) return fail(QIE_EINVAL, "attention_prefill_fast: bad layer");
+  if (n_q_heads % kv->n_kv_heads || (kv->head_dim != 64 && kv->head_dim != 128))
+    return fail(QIE_EINVAL, "attention_prefill_fast: need n_q %% n_kv == 0 and head_dim 64 or 128");
+  FastAttnArgs a{};
+  a.q = (const bf16*)Q;
+  a.out = (bf16*)out;
+  a.pos = pos;
+  a.slot = slot;
+  a.block_table = block_table;
+  a.max_pages = max_pages;
+  a.n_tok = n_tok;
+  a.n_q = n_q_heads;
+  a.layer = layer;
+  a.n_splits = 1;
+  a.scale_log2 = 1.4426950408889634f / sqrtf((float)kv->head_dim);
+  a.kv = geom_of(kv);
+  CU(launch_attention_prefill_fast(a, (cudaStream_t)st));
+  return QIE_OK;
+}
+
 // ---------------------------------------------------------------- driver level
 void qie_engine_opts_default(qie_engine_opts* o) {
   memset(o, 0, sizeof(*o));
@@ -291,7 +314,8 @@ static void engine_free(qie_engine* e) {
   void* dev[] = {e->blob, e->cos_d, e->sin_d, e->kv.pool, e->block_table_d, e->ids_d, e->pos_d, e->slot_d,
                  e->sampled_d, e->rowstep_d, e->x, e->xn, e->q, e->k, e->v, e->att, e->h, e->logits, e->qkv,
                  e->gemm_ws, e->attn_ws_o, e->attn_ws_ml, e->gemm_counters, e->mega_layers_d, e->mega_cand_d,
-                 e->mega_bar_d, e->mega_prof_d, e->mega_wmaps_d[0], e->mega_wmaps_d[1]};
+                 e->mega_bar_d, e->mega_prof_d, e->mega_wmaps_d[0], e->mega_wmaps_d[1], e->tp_buf, e->tp_cand};
+  tp_comm_destroy(&e->tp);
   for (void* p : dev)
     if (p) cudaFree(p);
   if (e->block_table_h) cudaFreeHost(e->block_table_h);
@@ -349,6 +373,13 @@ static int engine_finish_setup(qie_engine* e) {
   e->kv.n_layers = c.layers;
   e->kv.n_kv = c.n_kv;
   e->kv.hd = c.head_dim;
+  if (o.tp_size > 1) {  // tensor parallel: this rank caches only its own kv heads
+    if (!tp_plan(c, o.tp_rank, o.tp_size, &e->plan))
+      return fail(QIE_EINVAL, "tp_size %d does not divide heads (%d q / %d kv) / intermediate %d", o.tp_size, c.n_q, c.n_kv, c.inter);
+    e->tp.rank = o.tp_rank;
+    e->tp.size = o.tp_size;  // comm stays null until qie_engine_tp_connect
+    e->kv.n_kv = e->plan.n_kv;
+  }
   size_t page_bytes = e->kv.page_stride() * sizeof(bf16);
   int n_pages = o.max_pages;
   if (n_pages <= 0) {
@@ -388,6 +419,10 @@ static int engine_finish_setup(qie_engine* e) {
   e->logits_rows = std::min<int>((int)R, o.max_seqs);
   CU(cudaMalloc(&e->logits, (size_t)e->logits_rows * c.vocab * sizeof(bf16)));
   CU(cudaMalloc(&e->qkv, R * (Dq + 2 * Dkv) * sizeof(bf16)));
+  if (o.tp_size > 1) {
+    CU(cudaMalloc(&e->tp_buf, R * H * sizeof(bf16)));
+    CU(cudaMalloc(&e->tp_cand, (size_t)(1 + o.tp_size) * R * sizeof(TpCand)));
+  }
   {
     const char* mv = getenv("QIE_MEGA");
     e->use_mega = !(mv && mv[0] == '0');
@@ -468,7 +503,7 @@ static int engine_begin(const qie_engine_opts* opts, qie_engine** out_e) {
   if (o.max_batch_tokens <= 0) o.max_batch_tokens = 256;
   if (o.context <= 0) o.context = 32786;  // sic, utills.cu:14
   if (o.tp_size <= 0) o.tp_size = 1;
-  if (o.tp_size != 1) return fail(QIE_EINVAL, "tensor parallel engine not built yet (tp_size must be 1)");
+  if (o.tp_rank < 0 || o.tp_rank >= o.tp_size) return fail(QIE_EINVAL, "tp_rank %d outside [0, %d)", o.tp_rank, o.tp_size);
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0)
@@ -618,6 +653,33 @@ int qie_engine_create_synthetic(const qie_config* cfg, uint64_t seed, const qie_
 }
 
 void qie_engine_destroy(qie_engine* e) { engine_free(e); }
+
+int qie_tp_plan(const qie_config* cfg, int tp_rank, int tp_size, int* out8) {
+  if (!cfg || !out8) return fail(QIE_EINVAL, "null argument");
+  TpPlan p;
+  if (!tp_plan(*cfg, tp_rank, tp_size, &p))
+    return fail(QIE_EINVAL, "tp_size %d does not divide heads (%d q / %d kv) / intermediate %d", tp_size, cfg->n_q, cfg->n_kv, cfg->inter);
+  const int v[8] = {p.n_q, p.n_kv, p.inter, p.vocab, p.q_row0, p.kv_row0, p.inter0, p.vocab0};
+  memcpy(out8, v, sizeof(v));
+  return QIE_OK;
+}
+
+int qie_tp_unique_id(void* out128) {
+  if (!out128) return fail(QIE_EINVAL, "null argument");
+  char err[256];
+  if (tp_unique_id(out128, err, sizeof(err))) return fail(QIE_ECUDA, "%s", err);
+  return QIE_OK;
+}
+
+int qie_engine_tp_connect(qie_engine* e, const void* id128) {
+  if (!e || !id128) return fail(QIE_EINVAL, "null argument");
+  if (e->opts.tp_size <= 1) return fail(QIE_ESTATE, "engine was created with tp_size 1");
+  if (e->tp.comm) return fail(QIE_ESTATE, "tensor-parallel communicator already connected");
+  CU(cudaSetDevice(e->opts.device));
+  char err[256];
+  if (tp_comm_init(&e->tp, id128, e->opts.tp_rank, e->opts.tp_size, err, sizeof(err))) return fail(QIE_ECUDA, "%s", err);
+  return QIE_OK;
+}
 
 int qie_engine_get_config(const qie_engine* e, qie_config* out) {
   if (!e || !out) return fail(QIE_EINVAL, "null argument");

@@ -109,12 +109,14 @@ static cudaError_t gemm_tc(qie_engine* e, int kind, const bf16* x, int n, int K,
 // 18 kernels + 2-4 memcpys per layer in the reference become 8 launches here.
 cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int n_out, float temperature,
                          bool advance) {
+  if (e->tp.size > 1) return forward_rows_tp(e, n, max_kv_len, out_row0, n_out, temperature, advance);
   const qie_config& c = e->cfg;
   const int H = c.hidden, hd = c.head_dim, Dq = c.n_q * hd, Dkv = c.n_kv * hd, I = c.inter;
   cudaStream_t st = e->stream;
   const bool fast = e->opts.numerics == QIE_NUMERICS_FAST;
   const bool tc = fast && n > 8;                  // tcgen05 GEMMs
   const bool fast_attn = fast && advance;         // decode rows: one token per sequence
+  const bool fast_prefill = fast && !advance;     // prefill rows: consecutive positions of one sequence
   auto rms = [&](const bf16* x, const bf16* w, bf16* y, int rows) {
     return fast ? launch_rmsnorm_fast(x, w, y, H, rows, H, st) : launch_rmsnorm_ref(x, w, y, H, rows, H, st);
   };
@@ -194,6 +196,21 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
       a.kv = e->kv;
       QIE_TRY(KK_ATTN, launch_attention_decode_fast(a, st));
       if (ns > 1) ++e->launches;  // + combine kernel
+    } else if (fast_prefill) {
+      FastAttnArgs a{};
+      a.q = e->q;
+      a.out = e->att;
+      a.pos = e->pos_d;
+      a.slot = e->slot_d;
+      a.block_table = e->block_table_d;
+      a.max_pages = e->max_pages_per_seq;
+      a.n_tok = n;
+      a.n_q = c.n_q;
+      a.layer = l;
+      a.n_splits = 1;
+      a.scale_log2 = 1.4426950408889634f / sqrtf((float)hd);
+      a.kv = e->kv;
+      QIE_TRY(KK_ATTN, launch_attention_prefill_fast(a, st));
     } else {
       AttnArgs a{};
       a.q = e->q;
@@ -300,8 +317,147 @@ static int mega_tile_set(const qie_engine* e, int n, int max_kv_len) {
   return 0;
 }
 
+// Tensor-parallel forward (BASELINE configs[4]: 7B-arch over 2/4 GPUs).  Every rank holds the full
+// weight blob and works on its shard by pointer arithmetic: q/k/v/gate/up/lm_head by output rows,
+// o_proj/down_proj by input columns (row stride = the full width).  The two row-parallel GEMMs
+// produce bf16 partial sums that are summed over ranks with ncclAllReduce (NVLink) before the
+// residual add; the greedy token is the best of the ranks' local arg-max candidates in the
+// reference's tie-break order.  Norms, residual stream and sampling state are replicated.
+cudaError_t forward_rows_tp(qie_engine* e, int n, int max_kv_len, int out_row0, int n_out, float temperature,
+                            bool advance) {
+  const qie_config& c = e->cfg;
+  const TpPlan& pl = e->plan;
+  const int H = c.hidden, hd = c.head_dim, Dq = c.n_q * hd, I = c.inter;
+  const int Dq_l = pl.n_q * hd, Dkv_l = pl.n_kv * hd, I_l = pl.inter, V_l = pl.vocab;
+  cudaStream_t st = e->stream;
+  if (!e->tp.comm) return cudaErrorNotReady;
+  if (e->topk != 1) return cudaErrorNotSupported;  // top-k sampling over a sharded vocabulary is not built
+  (void)temperature;
+
+  QIE_TRY(KK_EMBED, launch_embedding(e->x, e->embed, e->ids_d, H, n, st));
+  for (int l = 0; l < c.layers; ++l) {
+    const LayerWeights& w = e->L[l];
+    QIE_TRY(KK_RMSNORM, launch_rmsnorm_ref(e->x, w.in_ln, e->xn, H, n, H, st));
+    {
+      GemmArgs g{};
+      g.A = e->xn;
+      g.lda = H;
+      g.K = H;
+      g.nseg = 3;
+      g.epi = EPI_STORE;
+      g.seg[0] = GemmSeg{w.q + (size_t)pl.q_row0 * H, nullptr, e->q, Dq_l, Dq_l, 0};
+      g.seg[1] = GemmSeg{w.k + (size_t)pl.kv_row0 * H, nullptr, e->k, Dkv_l, Dkv_l, 0};
+      g.seg[2] = GemmSeg{w.v + (size_t)pl.kv_row0 * H, nullptr, e->v, Dkv_l, Dkv_l, 0};
+      cudaError_t r = gemm_rows(e, KK_GEMM_QKV, g, n, H);
+      if (r != cudaSuccess) return r;
+    }
+    {
+      QkvPostArgs a{};
+      a.q = e->q;
+      a.q_in = e->q;
+      a.k = e->k;
+      a.v = e->v;
+      a.q_in_stride = Dq_l;
+      a.kv_stride = Dkv_l;
+      a.q_norm_w = w.q_norm;
+      a.k_norm_w = w.k_norm;
+      a.cos_t = e->cos_d;
+      a.sin_t = e->sin_d;
+      a.pos = e->pos_d;
+      a.slot = e->slot_d;
+      a.block_table = e->block_table_d;
+      a.max_pages = e->max_pages_per_seq;
+      a.n_tok = n;
+      a.n_q = pl.n_q;
+      a.layer = l;
+      a.kv = e->kv;  // local kv heads
+      QIE_TRY(KK_QKV_POST, launch_qkv_post(a, st));
+    }
+    {
+      AttnArgs a{};
+      a.q = e->q;
+      a.out = e->att;
+      a.pos = e->pos_d;
+      a.slot = e->slot_d;
+      a.block_table = e->block_table_d;
+      a.max_pages = e->max_pages_per_seq;
+      a.n_tok = n;
+      a.n_q = pl.n_q;
+      a.layer = l;
+      a.max_kv_len = max_kv_len;
+      a.kv = e->kv;
+      QIE_TRY(KK_ATTN, launch_attention_ref(a, st));
+    }
+    {  // o_proj over the local head columns -> partial sums -> all-reduce -> residual
+      GemmArgs g{};
+      g.A = e->att;
+      g.lda = Dq_l;
+      g.K = Dq_l;
+      g.nseg = 1;
+      g.epi = EPI_STORE;
+      g.seg[0] = GemmSeg{w.o + pl.q_row0, nullptr, e->tp_buf, H, H, Dq};
+      cudaError_t r = gemm_rows(e, KK_GEMM_O, g, n, Dq_l);
+      if (r != cudaSuccess) return r;
+      r = tp_allreduce_bf16(&e->tp, e->tp_buf, (size_t)n * H, st);
+      if (r != cudaSuccess) return r;
+      QIE_TRY(KK_GEMM_O, launch_residual_add(e->x, e->tp_buf, (size_t)n * H, st));
+    }
+    QIE_TRY(KK_RMSNORM, launch_rmsnorm_ref(e->x, w.post_ln, e->xn, H, n, H, st));
+    {
+      GemmArgs g{};
+      g.A = e->xn;
+      g.lda = H;
+      g.K = H;
+      g.nseg = 1;
+      g.epi = EPI_SILU_MUL;
+      g.seg[0] = GemmSeg{w.gate + (size_t)pl.inter0 * H, w.up + (size_t)pl.inter0 * H, e->h, I_l, I_l, 0};
+      cudaError_t r = gemm_rows(e, KK_GEMM_GATEUP, g, n, H);
+      if (r != cudaSuccess) return r;
+    }
+    {  // down_proj over the local intermediate columns -> all-reduce -> residual
+      GemmArgs g{};
+      g.A = e->h;
+      g.lda = I_l;
+      g.K = I_l;
+      g.nseg = 1;
+      g.epi = EPI_STORE;
+      g.seg[0] = GemmSeg{w.down + pl.inter0, nullptr, e->tp_buf, H, H, I};
+      cudaError_t r = gemm_rows(e, KK_GEMM_DOWN, g, n, I_l);
+      if (r != cudaSuccess) return r;
+      r = tp_allreduce_bf16(&e->tp, e->tp_buf, (size_t)n * H, st);
+      if (r != cudaSuccess) return r;
+      QIE_TRY(KK_GEMM_DOWN, launch_residual_add(e->x, e->tp_buf, (size_t)n * H, st));
+    }
+  }
+  if (n_out == 0) return cudaSuccess;
+  QIE_TRY(KK_RMSNORM, launch_rmsnorm_ref(e->x + (size_t)out_row0 * H, e->final_norm, e->xn, H, n_out, H, st));
+  {
+    GemmArgs g{};
+    g.A = e->xn;
+    g.lda = H;
+    g.K = H;
+    g.nseg = 1;
+    g.epi = EPI_STORE;
+    g.seg[0] = GemmSeg{e->lm_head + (size_t)pl.vocab0 * H, nullptr, e->logits, V_l, V_l, 0};
+    cudaError_t r = gemm_rows(e, KK_LM_HEAD, g, n_out, H);
+    if (r != cudaSuccess) return r;
+  }
+  // local arg-max (reference tie-break; vocab/tp is a multiple of 256, so the low byte of the index is
+  // the same locally and globally), then the best candidate over the ranks
+  QIE_TRY(KK_SAMPLE, launch_sample_topk(e->logits, e->sampled_d, n_out, V_l, 1.0f, 1, e->seed, 0, nullptr, st));
+  const int R = e->opts.max_batch_tokens;
+  QIE_TRY(KK_SAMPLE, launch_tp_cand_make(e->logits, e->sampled_d, e->tp_cand, n_out, V_l, pl.vocab0, st));
+  {
+    cudaError_t r = tp_allgather(&e->tp, e->tp_cand, e->tp_cand + R, (size_t)n_out * sizeof(TpCand), st);
+    if (r != cudaSuccess) return r;
+  }
+  QIE_TRY(KK_SAMPLE, launch_tp_cand_merge(e->tp_cand + R, e->tp.size, n_out, e->sampled_d, st));
+  if (advance) QIE_TRY(KK_ADVANCE, launch_advance(e->pos_d, e->ids_d, e->sampled_d, n_out, e->rowstep_d, st));
+  return cudaSuccess;
+}
+
 bool decode_uses_mega(const qie_engine* e, int n, int max_kv_len) {
-  if (!e->use_mega || e->capture || !e->mega_layers_d) return false;
+  if (!e->use_mega || e->capture || !e->mega_layers_d || e->tp.size > 1) return false;
   const qie_config& c = e->cfg;
   const int fast = e->opts.numerics == QIE_NUMERICS_FAST;  // fast numerics: persistent kernel for <= 8 rows
   return decode_mega_supports(c.hidden, c.inter, c.layers, c.n_q, c.n_kv, c.head_dim, n, max_kv_len, e->num_sms,

@@ -13,6 +13,7 @@
 
 #include "checkpoint.h"
 #include "kernels.h"
+#include "tp_nccl.h"
 
 namespace qie {
 
@@ -93,6 +94,12 @@ struct qie_engine {
   bool mega_prof_on = false;
   int mega_layers_run = 0;           // debug: run only this many layers (no lm_head)
 
+  // tensor parallel (opts.tp_size > 1): heads / intermediate / vocabulary sharded, NCCL all-reduce
+  qie::TpComm tp;
+  qie::TpPlan plan{};
+  qie::bf16* tp_buf = nullptr;        // [max_batch_tokens, hidden] partial sums of o_proj / down_proj
+  qie::TpCand* tp_cand = nullptr;     // [1 + tp_size][max rows] local + gathered arg-max candidates
+
   // sampling
   int topk = 1;
   float temp_prefill = 1.0f, temp_decode = 0.7f;
@@ -132,6 +139,9 @@ enum KernelKind {
 // first launch error. Counts launches into e->launches.
 cudaError_t forward_rows(qie_engine* e, int n_rows, int max_kv_len, int out_row0, int n_out, float temperature,
                          bool advance);
+// tensor-parallel forward (per-operator launches, reference-order kernels on the local shard)
+cudaError_t forward_rows_tp(qie_engine* e, int n_rows, int max_kv_len, int out_row0, int n_out, float temperature,
+                            bool advance);
 // true if a decode step of n rows / this kv bucket runs through the persistent kernel
 bool decode_uses_mega(const qie_engine* e, int n_rows, int max_kv_len);
 // one decode step (rows described in ids_d/pos_d/slot_d) through the persistent kernel

@@ -107,9 +107,10 @@ __global__ void __launch_bounds__(256) gemm_ref_order_kernel(GemmArgs g) {
         bool ok = k < K;
         int gr = row0 + r;
         if (gr >= S.rows) gr = S.rows - 1;  // clamp: duplicates are never stored
-        cp_async16_zfill(wb + r * 128 + ((col ^ r) << 4), S.W + (size_t)gr * K + (ok ? k : 0), ok);
+        const size_t ldw = S.ldw ? (size_t)S.ldw : (size_t)K;  // weight row stride (tensor-parallel column slices)
+        cp_async16_zfill(wb + r * 128 + ((col ^ r) << 4), S.W + (size_t)gr * ldw + (ok ? k : 0), ok);
         if (g.dual)
-          cp_async16_zfill(wb + 1024 + r * 128 + ((col ^ r) << 4), S.W2 + (size_t)gr * K + (ok ? k : 0), ok);
+          cp_async16_zfill(wb + 1024 + r * 128 + ((col ^ r) << 4), S.W2 + (size_t)gr * ldw + (ok ? k : 0), ok);
       }
     }
   };

@@ -34,6 +34,7 @@ struct GemmSeg {
   bf16* out;       // [M, ld_out]
   int rows;
   int ld_out;
+  int ldw;  // weight row stride in elements; 0 = K (a column slice of a wider matrix has ldw > K)
 };
 
 struct GemmArgs {
@@ -110,6 +111,9 @@ struct FastAttnArgs {
   KvGeom kv;
 };
 cudaError_t launch_attention_decode_fast(const FastAttnArgs& a, cudaStream_t st);
+// causal tiled attention for prefill rows (attn_prefill_fast.cu): rows are consecutive positions
+// pos[0]+t of one sequence (slot[0]); n_splits / ws_* unused
+cudaError_t launch_attention_prefill_fast(const FastAttnArgs& a, cudaStream_t st);
 
 // tcgen05 GEMM (fast numerics, M > 8)
 struct TensorMap2D {
@@ -147,6 +151,16 @@ cudaError_t launch_synth_fill(bf16* blob, size_t elem_begin, size_t n_elems, uin
 
 cudaError_t launch_kv_fill(const KvGeom& kv, const int* block_row, int pos0, int n_pos, uint64_t seed,
                            cudaStream_t st);
+
+// tensor-parallel greedy arg-max: cand[i] = (logit of the locally sampled index, global index)
+struct TpCand {
+  float val;
+  int idx;
+};
+cudaError_t launch_tp_cand_make(const bf16* logits_local, const int* sampled_local, TpCand* cand, int n_rows, size_t vocab_local,
+                                int vocab_offset, cudaStream_t st);
+// pick, per row, the best of tp candidates [tp][n_rows] in the reference's tie-break order
+cudaError_t launch_tp_cand_merge(const TpCand* all, int tp, int n_rows, int* out_tokens, cudaStream_t st);
 
 // step bookkeeping on the device: pos[i] += 1 ; ids <- sampled tokens
 cudaError_t launch_advance(int* pos, int* ids, const int* sampled, int n, int* step_ptr, cudaStream_t st);

@@ -610,6 +610,48 @@ cudaError_t launch_kv_fill(const KvGeom& kv, const int* block_row, int pos0, int
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ tensor-parallel arg-max merge
+__global__ void tp_cand_make_kernel(const bf16* __restrict__ logits, const int* __restrict__ sampled, TpCand* cand, int n,
+                                    size_t vocab_local, int vocab_offset) {
+  pdl_wait();
+  pdl_trigger();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int li = sampled[i];
+  TpCand c;
+  c.val = li >= 0 ? bf2f(logits[(size_t)i * vocab_local + li]) : -CUDART_INF_F;
+  c.idx = li >= 0 ? li + vocab_offset : -1;
+  cand[i] = c;
+}
+__global__ void tp_cand_merge_kernel(const TpCand* __restrict__ all, int tp, int n, int* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float bv = -CUDART_INF_F;
+  int bi = -1;
+  for (int r = 0; r < tp; ++r) {
+    const TpCand c = all[(size_t)r * n + i];
+    if (cand_better(c.val, c.idx, bv, bi)) {
+      bv = c.val;
+      bi = c.idx;
+    }
+  }
+  out[i] = bi;
+}
+cudaError_t launch_tp_cand_make(const bf16* logits_local, const int* sampled_local, TpCand* cand, int n_rows, size_t vocab_local,
+                                int vocab_offset, cudaStream_t st) {
+  if (!n_rows) return cudaSuccess;
+  (void)launch_k(tp_cand_make_kernel, dim3((n_rows + 127) / 128), dim3(128), 0, st, logits_local, sampled_local, cand, n_rows,
+                 vocab_local, vocab_offset);
+  return cudaGetLastError();
+}
+cudaError_t launch_tp_cand_merge(const TpCand* all, int tp, int n_rows, int* out_tokens, cudaStream_t st) {
+  if (!n_rows) return cudaSuccess;
+  (void)launch_k(tp_cand_merge_kernel, dim3((n_rows + 127) / 128), dim3(128), 0, st, all, tp, n_rows, out_tokens);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ step bookkeeping
 __global__ void advance_kernel(int* pos, int* ids, const int* sampled, int n, int* step_ptr) {
   pdl_wait();

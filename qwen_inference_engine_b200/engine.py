@@ -58,6 +58,14 @@ def inspect_checkpoint(meta_path, head_dim_hint=0):
     return cfg, tot.value, n.value
 
 
+def tp_plan(cfg, tp_rank, tp_size):
+    """host-only: the shard of rank tp_rank (see qie_tp_plan in include/qie_b200.h)"""
+    out = (C.c_int * 8)()
+    check(_lib.lib().qie_tp_plan(C.byref(cfg), tp_rank, tp_size, out))
+    keys = ("n_q", "n_kv", "inter", "vocab", "q_row0", "kv_row0", "inter0", "vocab0")
+    return dict(zip(keys, list(out)))
+
+
 def _i32(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
 
@@ -65,7 +73,8 @@ def _i32(a):
 class Engine:
     def __init__(self, meta_path=None, weights_path=None, *, synthetic=None, seed=1234, device=0,
                  page_size=16, kv_bytes=0, max_pages=0, max_seqs=64, max_batch_tokens=256,
-                 context=REF_CONTEXT, use_graph=True, head_dim_hint=0, numerics="reference_order"):
+                 context=REF_CONTEXT, use_graph=True, head_dim_hint=0, numerics="reference_order",
+                 tp_rank=0, tp_size=1):
         L = _lib.lib()
         o = EngineOpts()
         L.qie_engine_opts_default(C.byref(o))
@@ -73,6 +82,7 @@ class Engine:
         o.max_seqs, o.max_batch_tokens, o.context = max_seqs, max_batch_tokens, context
         o.use_graph, o.head_dim_hint = int(use_graph), head_dim_hint
         o.numerics = {"reference_order": 0, "fast": 1}[numerics]
+        o.tp_rank, o.tp_size = tp_rank, tp_size
         self.numerics = numerics
         h = C.c_void_p()
         if synthetic is not None:
@@ -104,6 +114,18 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    # -- tensor parallel (one process per GPU) ---------------------------
+    @staticmethod
+    def tp_unique_id():
+        """128-byte NCCL id; rank 0 creates it and ships it to the other ranks."""
+        buf = C.create_string_buffer(128)
+        check(_lib.lib().qie_tp_unique_id(buf))
+        return buf.raw
+
+    def tp_connect(self, id128):
+        assert len(id128) == 128
+        check(self._L.qie_engine_tp_connect(self._h, C.create_string_buffer(bytes(id128), 128)))
 
     # -- configuration ---------------------------------------------------------
     def set_sampling(self, topk=1, temperature_prefill=1.0, temperature_decode=0.7, seed=1234, add_step=True):

@@ -118,3 +118,10 @@ def launch_attn_decode_fast(Q, out, pool, layer, pos, slot, n_q_heads, n_splits=
     check(_lib.lib().qie_attention_decode_fast(C.byref(pool.view), layer, _p(Q), _p(out), _p(pos), _p(slot),
                                                _p(pool.block_table), pool.max_pages, pos.numel(), n_q_heads,
                                                n_splits, _st()))
+
+
+def launch_attn_prefill_fast(Q, out, pool, layer, pos, slot, n_q_heads):
+    """causal tiled attention for prefill rows: consecutive positions pos[0]+t of one sequence."""
+    check(_lib.lib().qie_attention_prefill_fast(C.byref(pool.view), layer, _p(Q), _p(out), _p(pos), _p(slot),
+                                                _p(pool.block_table), pool.max_pages, pos.numel(), n_q_heads,
+                                                _st()))

@@ -85,6 +85,55 @@ def test_flash_decoding_vs_reference_order_attention(layers, hd, n_q, n_kv, B, t
     assert rel_err(got, want) < TOL_BF16
 
 
+@pytest.mark.parametrize("hd,n_q,n_kv,prefix,T", [(64, 14, 2, 0, 64), (64, 14, 2, 0, 1), (64, 14, 2, 0, 200), (64, 14, 2, 37, 91),
+                                                   (128, 12, 2, 0, 257), (128, 28, 4, 130, 70), (64, 4, 4, 15, 17),
+                                                   (128, 2, 1, 64, 128)])
+def test_prefill_attention_vs_reference_order_attention(layers, hd, n_q, n_kv, prefix, T):
+    """prefill chunk of T rows at positions prefix..prefix+T-1 of sequence 1 (sequence 0 holds other
+    data); the cache already contains the prefix (chunked prefill) and the chunk's own K/V."""
+    rng = np.random.default_rng(hd * 3 + n_q + prefix + T)
+    Dq, Dkv = n_q * hd, n_kv * hd
+    n_layers, layer, ps = 2, 1, 16
+    total = prefix + T
+    pool = layers.KvPool(n_pages=2 * ((total + ps - 1) // ps + 1), page_size=ps, n_layers=n_layers, n_kv_heads=n_kv,
+                         head_dim=hd, max_seqs=2)
+    for b, n in ((0, 9), (1, total)):
+        K, V = rand_bf16(rng, (n, Dkv), 1.0), rand_bf16(rng, (n, Dkv), 1.0)
+        pos = torch.arange(n, dtype=torch.int32, device="cuda")
+        pool.store(layer, to_dev(K), to_dev(V), pos, torch.full((n,), b, dtype=torch.int32, device="cuda"))
+    Q = to_dev(rand_bf16(rng, (T, Dq), 1.0))
+    pos = torch.arange(prefix, total, dtype=torch.int32, device="cuda")
+    slot = torch.full((T,), 1, dtype=torch.int32, device="cuda")
+    o_ref = torch.zeros_like(Q)
+    o_new = torch.full_like(Q, float("nan"))
+    layers.launch_attn(Q, o_ref, pool, layer, pos, slot, n_q)  # reference-order kernel (bit-exact vs reference)
+    layers.launch_attn_prefill_fast(Q, o_new, pool, layer, pos, slot, n_q)
+    torch.cuda.synchronize()
+    got, want = to_host(o_new), to_host(o_ref)
+    assert not np.isnan(bf16_to_f32(got)).any()
+    assert rel_err(got, want) < TOL_BF16
+
+
+def test_fast_prefill_engine_long_prompt():
+    """whole prefill, 300-token prompt in chunks of 128 rows (tcgen05 GEMMs + tiled causal attention):
+    logits and per-layer activations of the last chunk within tolerance of the reference-order engine."""
+    import qwen_inference_engine_b200 as q
+    kw = dict(synthetic="small128", seed=3, context=1024, max_batch_tokens=128, max_seqs=4)
+    e_ref = q.Engine(numerics="reference_order", **kw)
+    e_fast = q.Engine(numerics="fast", **kw)
+    ids = prompt_ids(300, e_ref.config.vocab, seed=11)
+    for eng in (e_ref, e_fast):
+        eng.capture(True)
+    ta, tb = e_ref.prefill(e_ref.new_sequence(), ids), e_fast.prefill(e_fast.new_sequence(), ids)
+    assert close(e_fast.read_capture("logits", -1), e_ref.read_capture("logits", -1))
+    for l in range(e_ref.config.layers):
+        for tag in ("attn", "x_out"):
+            assert close(e_fast.read_capture(tag, l), e_ref.read_capture(tag, l)), (tag, l)
+    print("fast prefill token", tb, "reference-order token", ta)
+    e_ref.close()
+    e_fast.close()
+
+
 def test_fast_engine_vs_reference_order_engine():
     """whole forward, batch 16 decode: FAST numerics vs REFERENCE_ORDER numerics on the same
     weights: logits within tolerance at every step; token agreement reported."""
