@@ -456,6 +456,46 @@ def main():
         except Exception as ex:  # the side measurement must never break the contract line
             line.setdefault("extra", {})["batch1_error"] = str(ex)
     eng.close()
+    if rank == 0 and world == 1 and not args.no_extra:
+        # configs[2] side measurement: Qwen2.5-1.5B-arch prefill of 4096 tokens (tcgen05 GEMMs + tiled causal
+        # attention, fast numerics), through qie_prefill with HOST ids in / HOST token out
+        try:
+            cfg15 = q.make_config("qwen2.5-1.5b", context=8192)
+            T = 4096
+            engp = q.Engine(synthetic=cfg15, seed=1234, device=local, max_seqs=2, max_batch_tokens=T, kv_bytes=2 << 30,
+                            context=8192, numerics="fast")
+            idsp = np.random.default_rng(5).integers(0, cfg15.vocab, size=T, dtype=np.int32)
+            extp = torch.cuda.ExternalStream(engp.stream)
+            tms = []
+            for r_ in range(4):
+                sp = engp.new_sequence()
+                torch.cuda.synchronize()
+                with torch.cuda.stream(extp):
+                    e0.record()
+                engp.prefill(sp, idsp)
+                with torch.cuda.stream(extp):
+                    e1.record()
+                torch.cuda.synchronize()
+                if r_ > 0:
+                    tms.append(e0.elapsed_time(e1))
+                engp.free_sequence(sp)
+            msp = float(np.median(tms))
+            H_, I_, L_, hd_ = cfg15.hidden, cfg15.inter, cfg15.layers, cfg15.head_dim
+            Dq_, Dkv_ = cfg15.n_q * hd_, cfg15.n_kv * hd_
+            flop = 2 * T * L_ * (H_ * Dq_ + 2 * H_ * Dkv_ + Dq_ * H_ + 3 * H_ * I_) + 2 * cfg15.vocab * H_ \
+                + L_ * cfg15.n_q * 4 * hd_ * T * T / 2
+            try:
+                tpeak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+            except Exception:
+                tpeak = 1377.7
+            line.setdefault("extra", {})["prefill_1p5b_4096"] = {
+                "workload": "configs[2]: qwen2.5-1.5b prefill of 4096 tokens in one forward (fast numerics: tcgen05/TMEM/TMA "
+                            "GEMMs, FlashAttention-2 style causal attention on mma.sync), qie_prefill end to end",
+                "ms": msp, "tokens_per_s": T / (msp / 1e3), "alg_tflop": flop / 1e12,
+                "achieved_tflops": flop / 1e12 / (msp / 1e3), "frac_of_tensor_peak": flop / 1e12 / (msp / 1e3) / tpeak}
+            engp.close()
+        except Exception as ex:
+            line.setdefault("extra", {})["prefill_error"] = str(ex)
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:

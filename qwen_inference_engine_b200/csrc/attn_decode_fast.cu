@@ -16,8 +16,8 @@
 //   KV    : page chunks [slot][hd] are contiguous in pool[page][layer][k|v][head][slot][hd];
 //           16-byte cp.async into a 3-stage XOR-swizzled ring, ldmatrix (K) /
 //           ldmatrix.trans (V) conflict-free
-//   softmax: online (running max / sum in fp32, exp2f with the scale folded in), P rounded
-//           to bf16 for the PV MMA (as FlashAttention does)
+//   softmax: online (running max / sum in fp32, exp2f with the scale folded in), P split into
+//           bf16 hi + lo parts for the PV MMA (two MMAs, 16 mantissa bits)
 //   splits: partial (max, sum, unnormalised O) per split -> attn_combine_kernel
 #include "common.cuh"
 #include "kernels.h"
@@ -163,19 +163,25 @@ __global__ void __launch_bounds__(128) attn_decode_fast_kernel(FastAttnArgs a) {
         m_run[h] = m_new;
       }
       float rs[2] = {0.f, 0.f};
-      uint32_t pf[4];
+      uint32_t pf[4], pl[4];
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const float p0 = exp2f(sc[j][0] - m_run[0]), p1 = exp2f(sc[j][1] - m_run[0]);
         const float p2 = exp2f(sc[j][2] - m_run[1]), p3 = exp2f(sc[j][3] - m_run[1]);
         rs[0] += p0 + p1;
         rs[1] += p2 + p3;
-        pf[2 * j] = pack2(f2bf(p0), f2bf(p1));      // a0 (j=0) / a2 (j=1): row g
-        pf[2 * j + 1] = pack2(f2bf(p2), f2bf(p3));  // a1 / a3: row g+8
+        // P = hi + lo in bf16 (16 mantissa bits): the PV product keeps fp32-like weights at the
+        // price of a second MMA, which is free in a kernel that waits for HBM
+        const bf16 h0 = f2bf(p0), h1 = f2bf(p1), h2 = f2bf(p2), h3 = f2bf(p3);
+        pf[2 * j] = pack2(h0, h1);      // a0 (j=0) / a2 (j=1): row g
+        pf[2 * j + 1] = pack2(h2, h3);  // a1 / a3: row g+8
+        pl[2 * j] = pack2(f2bf(p0 - bf2f(h0)), f2bf(p1 - bf2f(h1)));
+        pl[2 * j + 1] = pack2(f2bf(p2 - bf2f(h2)), f2bf(p3 - bf2f(h3)));
       }
       l_run[0] = l_run[0] * corr[0] + rs[0];
       l_run[1] = l_run[1] * corr[1] + rs[1];
       const uint32_t pa[4] = {pf[0], pf[1], pf[2], pf[3]};
+      const uint32_t pb[4] = {pl[0], pl[1], pl[2], pl[3]};
       // ---- O = O*corr + P V
 #pragma unroll
       for (int j = 0; j < NT; j += 2) {
@@ -193,6 +199,8 @@ __global__ void __launch_bounds__(128) attn_decode_fast_kernel(FastAttnArgs a) {
         ldmatrix_x4_trans(v0, v1, v2, v3, vb + swz<HD>(r, ch));
         mma_bf16_16816(o[j], pa, v0, v1);
         mma_bf16_16816(o[j + 1], pa, v2, v3);
+        mma_bf16_16816(o[j], pb, v0, v1);
+        mma_bf16_16816(o[j + 1], pb, v2, v3);
       }
     }
   }

@@ -17,8 +17,8 @@
 //   KV    : 64-position tiles, page chunks [slot][hd] contiguous in the pool, 16-byte cp.async
 //           into a 2-stage XOR-swizzled ring; ldmatrix (K) / ldmatrix.trans (V)
 //   math  : S = Q K^T and O += P V on mma.sync m16n8k16 bf16 (fp32 accumulate), online
-//           softmax in fp32 with exp2f and the 1/sqrt(hd) scale folded in, P rounded to bf16
-//           for the PV product; the causal mask is applied only on tiles that cross the diagonal
+//           softmax in fp32 with exp2f and the 1/sqrt(hd) scale folded in, P split into bf16 hi + lo
+//           parts for the PV product (the kernel is bound by ldmatrix traffic, not by the MMAs); the causal mask is applied only on tiles that cross the diagonal
 #include "common.cuh"
 #include "kernels.h"
 #include "launch.h"
@@ -173,15 +173,18 @@ __global__ void __launch_bounds__(128) attn_prefill_fast_kernel(FastAttnArgs a) 
         msafe[hh] = m_new;
       }
       float rs[2] = {0.f, 0.f};
-      uint32_t pa[SN / 2][4];
+      uint32_t pa[SN / 2][4], pb[SN / 2][4];  // P = hi + lo in bf16 (16 mantissa bits)
 #pragma unroll
       for (int j = 0; j < SN; ++j) {
         const float p0v = exp2f(sc[j][0] - msafe[0]), p1v = exp2f(sc[j][1] - msafe[0]);
         const float p2v = exp2f(sc[j][2] - msafe[1]), p3v = exp2f(sc[j][3] - msafe[1]);
         rs[0] += p0v + p1v;
         rs[1] += p2v + p3v;
-        pa[j >> 1][(j & 1) * 2] = pack2(f2bf(p0v), f2bf(p1v));      // a0 / a2: row g
-        pa[j >> 1][(j & 1) * 2 + 1] = pack2(f2bf(p2v), f2bf(p3v));  // a1 / a3: row g+8
+        const bf16 h0 = f2bf(p0v), h1 = f2bf(p1v), h2 = f2bf(p2v), h3 = f2bf(p3v);
+        pa[j >> 1][(j & 1) * 2] = pack2(h0, h1);      // a0 / a2: row g
+        pa[j >> 1][(j & 1) * 2 + 1] = pack2(h2, h3);  // a1 / a3: row g+8
+        pb[j >> 1][(j & 1) * 2] = pack2(f2bf(p0v - bf2f(h0)), f2bf(p1v - bf2f(h1)));
+        pb[j >> 1][(j & 1) * 2 + 1] = pack2(f2bf(p2v - bf2f(h2)), f2bf(p3v - bf2f(h3)));
       }
       l_run[0] = l_run[0] * corr[0] + rs[0];
       l_run[1] = l_run[1] * corr[1] + rs[1];
@@ -203,6 +206,8 @@ __global__ void __launch_bounds__(128) attn_prefill_fast_kernel(FastAttnArgs a) 
           ldmatrix_x4_trans(v0, v1, v2, v3, vb + pf_swz<HD>(r, ch));
           mma_bf16_16816(o[j], pa[kk], v0, v1);
           mma_bf16_16816(o[j + 1], pa[kk], v2, v3);
+          mma_bf16_16816(o[j], pb[kk], v0, v1);
+          mma_bf16_16816(o[j + 1], pb[kk], v2, v3);
         }
       }
     }

@@ -420,7 +420,7 @@ static int engine_finish_setup(qie_engine* e) {
   CU(cudaMalloc(&e->logits, (size_t)e->logits_rows * c.vocab * sizeof(bf16)));
   CU(cudaMalloc(&e->qkv, R * (Dq + 2 * Dkv) * sizeof(bf16)));
   if (o.tp_size > 1) {
-    CU(cudaMalloc(&e->tp_buf, R * H * sizeof(bf16)));
+    CU(cudaMalloc(&e->tp_buf, R * H * sizeof(float)));
     CU(cudaMalloc(&e->tp_cand, (size_t)(1 + o.tp_size) * R * sizeof(TpCand)));
   }
   {

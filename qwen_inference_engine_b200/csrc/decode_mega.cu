@@ -801,6 +801,43 @@ __device__ __forceinline__ void head_load_cg(float (&x)[NP][2], const bf16* src,
   }
 }
 
+// Cached K/V of a layer do not depend on anything computed in this step (only the new position does,
+// and that one travels through shared memory), so the chunks of this CTA's attention task(s) are
+// requested into L2 long before the attention phase reads them: one cp.async.bulk.prefetch per
+// (page, K|V) chunk, issued while the down_proj / QKV phases keep the SMs busy and HBM idle.  The
+// scores loop and the V tile loader then see L2 latency instead of DRAM latency.
+template <int NP>
+__device__ __forceinline__ void attention_prefetch_l2(const MegaArgs& a, int layer) {
+  constexpr int HD = 64 * NP;
+  const int Gq = a.n_q / a.n_kv;
+  const bool per_head = a.B * a.n_q <= (int)gridDim.x;
+  const int ntask = per_head ? a.B * a.n_q : a.B * a.n_kv;
+  const int psz = a.kv.page_size;
+  const uint32_t bytes = (uint32_t)psz * HD * 2;
+  if (bytes & 15) return;
+  for (int task = blockIdx.x; task < ntask; task += gridDim.x) {
+    int b, kvh;
+    if (per_head) {
+      b = task / a.n_q;
+      const int h0 = task - b * a.n_q;
+      kvh = h0 / Gq;
+      if (h0 != kvh * Gq) continue;  // one request per kv head
+    } else {
+      b = task / a.n_kv;
+      kvh = task - b * a.n_kv;
+    }
+    const int ps = a.pos[b];
+    if (ps <= a.attn_kstg) continue;  // short contexts are staged through cp.async next to the QKV GEMM
+    const int n_pages = (ps + psz - 1) / psz;
+    const int* bt = a.block_table + (size_t)a.slot[b] * a.max_pages;
+    for (int i = threadIdx.x; i < 2 * n_pages; i += NTC) {  // K chunks first: the scores loop reads them first
+      const int kv = i >= n_pages ? 1 : 0, pi = kv ? i - n_pages : i;
+      const bf16* src = a.kv.chunk(bt[pi], layer, kv, kvh);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+    }
+  }
+}
+
 // Tasks: (row, q head) while they fit one wave of CTAs, else (row, kv head) with the whole
 // query group sharing the K/V stream.  q/k-norm + RoPE + the KV store of the new position
 // are done here (replaces 2x qkNorm, 2x RoPE, kv_copy_layer_to_cache_decode).
@@ -1149,6 +1186,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
     uint4* dst = reinterpret_cast<uint4*>(a.x + (size_t)b * H);
     for (int i = threadIdx.x; i < (H >> 3); i += NTC) dst[i] = src[i];
   }
+  if (a.kv_l2_prefetch) attention_prefetch_l2<NP>(a, 0);
   stamp();
   // One loop over the GEMM phases (4 per layer, then lm_head) with a single inlined copy of
   // every stage, so kernel arguments stay in the constant bank and the code stays small.
@@ -1167,6 +1205,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
       stamp();
     } else if (kind == PH_DOWN) {
       // ---- down + residual
+      if (a.kv_l2_prefetch && l + 1 < L) attention_prefetch_l2<NP>(a, l + 1);
       if (a.stream_down)
         a_src = a.h;
       else

@@ -54,7 +54,8 @@ static cudaError_t gemm_rows(qie_engine* e, int kind, GemmArgs g, int n_rows, si
     GemmArgs c = g;
     c.A = g.A + (size_t)r0 * a_stride;
     c.M = std::min(64, n_rows - r0);
-    for (int s = 0; s < g.nseg; ++s) c.seg[s].out = g.seg[s].out + (size_t)r0 * g.seg[s].ld_out;
+    for (int s = 0; s < g.nseg; ++s)  // EPI_STORE_F32: `out` is a float*, twice the bf16 stride
+      c.seg[s].out = g.seg[s].out + (size_t)r0 * g.seg[s].ld_out * (g.epi == EPI_STORE_F32 ? 2 : 1);
     QIE_TRY(kind, launch_gemm_ref_order(c, e->num_sms, e->stream));
   }
   return cudaSuccess;
@@ -320,7 +321,8 @@ static int mega_tile_set(const qie_engine* e, int n, int max_kv_len) {
 // Tensor-parallel forward (BASELINE configs[4]: 7B-arch over 2/4 GPUs).  Every rank holds the full
 // weight blob and works on its shard by pointer arithmetic: q/k/v/gate/up/lm_head by output rows,
 // o_proj/down_proj by input columns (row stride = the full width).  The two row-parallel GEMMs
-// produce bf16 partial sums that are summed over ranks with ncclAllReduce (NVLink) before the
+// produce fp32 partial sums (the HMMA accumulators, not yet rounded) that are summed over ranks with
+// ncclAllReduce (NVLink) and rounded to bf16 ONCE, like the unsharded projection output, before the
 // residual add; the greedy token is the best of the ranks' local arg-max candidates in the
 // reference's tie-break order.  Norms, residual stream and sampling state are replicated.
 cudaError_t forward_rows_tp(qie_engine* e, int n, int max_kv_len, int out_row0, int n_out, float temperature,
@@ -394,13 +396,13 @@ cudaError_t forward_rows_tp(qie_engine* e, int n, int max_kv_len, int out_row0, 
       g.lda = Dq_l;
       g.K = Dq_l;
       g.nseg = 1;
-      g.epi = EPI_STORE;
-      g.seg[0] = GemmSeg{w.o + pl.q_row0, nullptr, e->tp_buf, H, H, Dq};
+      g.epi = EPI_STORE_F32;
+      g.seg[0] = GemmSeg{w.o + pl.q_row0, nullptr, reinterpret_cast<bf16*>(e->tp_buf), H, H, Dq};
       cudaError_t r = gemm_rows(e, KK_GEMM_O, g, n, Dq_l);
       if (r != cudaSuccess) return r;
-      r = tp_allreduce_bf16(&e->tp, e->tp_buf, (size_t)n * H, st);
+      r = tp_allreduce_f32(&e->tp, e->tp_buf, (size_t)n * H, st);
       if (r != cudaSuccess) return r;
-      QIE_TRY(KK_GEMM_O, launch_residual_add(e->x, e->tp_buf, (size_t)n * H, st));
+      QIE_TRY(KK_GEMM_O, launch_residual_add_f32(e->x, e->tp_buf, (size_t)n * H, st));
     }
     QIE_TRY(KK_RMSNORM, launch_rmsnorm_ref(e->x, w.post_ln, e->xn, H, n, H, st));
     {
@@ -420,13 +422,13 @@ cudaError_t forward_rows_tp(qie_engine* e, int n, int max_kv_len, int out_row0, 
       g.lda = I_l;
       g.K = I_l;
       g.nseg = 1;
-      g.epi = EPI_STORE;
-      g.seg[0] = GemmSeg{w.down + pl.inter0, nullptr, e->tp_buf, H, H, I};
+      g.epi = EPI_STORE_F32;
+      g.seg[0] = GemmSeg{w.down + pl.inter0, nullptr, reinterpret_cast<bf16*>(e->tp_buf), H, H, I};
       cudaError_t r = gemm_rows(e, KK_GEMM_DOWN, g, n, I_l);
       if (r != cudaSuccess) return r;
-      r = tp_allreduce_bf16(&e->tp, e->tp_buf, (size_t)n * H, st);
+      r = tp_allreduce_f32(&e->tp, e->tp_buf, (size_t)n * H, st);
       if (r != cudaSuccess) return r;
-      QIE_TRY(KK_GEMM_DOWN, launch_residual_add(e->x, e->tp_buf, (size_t)n * H, st));
+      QIE_TRY(KK_GEMM_DOWN, launch_residual_add_f32(e->x, e->tp_buf, (size_t)n * H, st));
     }
   }
   if (n_out == 0) return cudaSuccess;
@@ -505,6 +507,12 @@ cudaError_t forward_decode_mega(qie_engine* e, int n, int max_kv_len, float temp
   a.prof_stride = 16 * c.layers + 8;
   a.greedy = e->topk == 1;
   a.fast = e->opts.numerics == QIE_NUMERICS_FAST ? 1 : 0;
+  {
+    // measured on B200 (batch 64 / ctx 2048): no gain -- the attention phase is bound by shared-memory
+    // broadcast loads and FP32 issue, not by DRAM latency -- so the prefetch stays opt-in (QIE_MEGA_KVPF=1)
+    static const bool pf = [] { const char* v = getenv("QIE_MEGA_KVPF"); return v && v[0] == '1'; }();
+    a.kv_l2_prefetch = pf ? 1 : 0;
+  }
   a.advance = 1;
   a.n_layers_run = e->mega_layers_run;
   cudaError_t r = launch_decode_mega(a, e->num_sms, e->stream);

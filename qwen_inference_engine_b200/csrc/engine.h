@@ -97,7 +97,7 @@ struct qie_engine {
   // tensor parallel (opts.tp_size > 1): heads / intermediate / vocabulary sharded, NCCL all-reduce
   qie::TpComm tp;
   qie::TpPlan plan{};
-  qie::bf16* tp_buf = nullptr;        // [max_batch_tokens, hidden] partial sums of o_proj / down_proj
+  float* tp_buf = nullptr;            // [max_batch_tokens, hidden] fp32 partial sums of o_proj / down_proj
   qie::TpCand* tp_cand = nullptr;     // [1 + tp_size][max rows] local + gathered arg-max candidates
 
   // sampling

@@ -196,6 +196,8 @@ __global__ void __launch_bounds__(256) gemm_ref_order_kernel(GemmArgs g) {
         bf16* dst = S.out + (size_t)tok * S.ld_out + n;
         if (g.epi == EPI_STORE) {
           *dst = f2bf(v);
+        } else if (g.epi == EPI_STORE_F32) {
+          reinterpret_cast<float*>(S.out)[(size_t)tok * S.ld_out + n] = v;
         } else if (g.epi == EPI_RESIDUAL) {
           float y = bf2f(f2bf(v));
           *dst = f2bf(__fadd_rn(bf2f(*dst), y));

@@ -26,7 +26,7 @@ struct KvGeom {
 };
 
 // ---------------------------------------------------------------- reference-order GEMM
-enum { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_SILU_MUL = 2 };
+enum { EPI_STORE = 0, EPI_RESIDUAL = 1, EPI_SILU_MUL = 2, EPI_STORE_F32 = 3 };  // F32: `out` is really float* (tensor-parallel partial sums)
 
 struct GemmSeg {
   const bf16* W;   // [rows, K] row-major (HF [out,in])
@@ -159,6 +159,9 @@ struct TpCand {
 };
 cudaError_t launch_tp_cand_make(const bf16* logits_local, const int* sampled_local, TpCand* cand, int n_rows, size_t vocab_local,
                                 int vocab_offset, cudaStream_t st);
+// x[i] = bf16(float(x[i]) + float(bf16(y[i]))): the reference's residual_add (residual_add.cu:7) applied to the fp32
+// sum of the ranks' partial projections, rounded to bf16 once like the unsharded projection output
+cudaError_t launch_residual_add_f32(bf16* x, const float* y, size_t n, cudaStream_t st);
 // pick, per row, the best of tp candidates [tp][n_rows] in the reference's tie-break order
 cudaError_t launch_tp_cand_merge(const TpCand* all, int tp, int n_rows, int* out_tokens, cudaStream_t st);
 
@@ -199,6 +202,7 @@ struct MegaArgs {
   int prof_stride;
   int greedy, advance;
   int fast;                          // 1: fast (tolerance) numerics, <= 8 rows: split-K over the warps, parallel RMSNorm
+  int kv_l2_prefetch;                // 1: request the next layer's cached K/V into L2 one phase group ahead of its attention
   int n_layers_run;                  // debug: stop after this many layers (0 = all, then lm_head)
   int KC;  // k elements per weight tile = box depth of wmaps (decode_mega_kc at engine setup)
   // geometry, filled by the launcher (ph_*: per GEMM phase kind qkv/o/gate+up/down/lm_head)

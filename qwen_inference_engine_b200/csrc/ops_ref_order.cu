@@ -639,6 +639,17 @@ __global__ void tp_cand_merge_kernel(const TpCand* __restrict__ all, int tp, int
   }
   out[i] = bi;
 }
+__global__ void residual_add_f32_kernel(bf16* __restrict__ x, const float* __restrict__ y, size_t n) {
+  pdl_wait();
+  pdl_trigger();
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = f2bf(__fadd_rn(bf2f(x[i]), bf2f(f2bf(y[i]))));
+}
+cudaError_t launch_residual_add_f32(bf16* x, const float* y, size_t n, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  (void)launch_k(residual_add_f32_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x, y, n);
+  return cudaGetLastError();
+}
 cudaError_t launch_tp_cand_make(const bf16* logits_local, const int* sampled_local, TpCand* cand, int n_rows, size_t vocab_local,
                                 int vocab_offset, cudaStream_t st) {
   if (!n_rows) return cudaSuccess;

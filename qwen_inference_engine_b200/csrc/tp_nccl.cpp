@@ -75,7 +75,7 @@ const Nccl* nccl() {
   return &g_nccl;
 }
 // ncclDataType_t / ncclRedOp_t values of the NCCL 2.x ABI
-constexpr int kNcclInt8 = 0, kNcclBfloat16 = 9, kNcclSum = 0;
+constexpr int kNcclInt8 = 0, kNcclFloat32 = 7, kNcclBfloat16 = 9, kNcclSum = 0;
 }  // namespace
 
 int tp_unique_id(void* out128, char* err, size_t errlen) {
@@ -123,6 +123,12 @@ cudaError_t tp_allreduce_bf16(TpComm* t, void* buf, size_t nelem, cudaStream_t s
   const Nccl* n = nccl();
   if (!n || !t->comm) return cudaErrorNotReady;
   return n->all_reduce(buf, buf, nelem, kNcclBfloat16, kNcclSum, t->comm, st) == 0 ? cudaSuccess : cudaErrorUnknown;
+}
+
+cudaError_t tp_allreduce_f32(TpComm* t, float* buf, size_t nelem, cudaStream_t st) {
+  const Nccl* n = nccl();
+  if (!n || !t->comm) return cudaErrorNotReady;
+  return n->all_reduce(buf, buf, nelem, kNcclFloat32, kNcclSum, t->comm, st) == 0 ? cudaSuccess : cudaErrorUnknown;
 }
 
 cudaError_t tp_allgather(TpComm* t, const void* send, void* recv, size_t bytes, cudaStream_t st) {

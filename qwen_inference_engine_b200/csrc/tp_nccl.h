@@ -26,8 +26,9 @@ struct TpComm {
 int tp_unique_id(void* out128, char* err, size_t errlen);
 int tp_comm_init(TpComm* t, const void* id128, int rank, int size, char* err, size_t errlen);
 void tp_comm_destroy(TpComm* t);
-// in-place sum over ranks of n bf16 elements; all-gather of `bytes` bytes per rank
+// in-place sum over ranks of n bf16 / fp32 elements; all-gather of `bytes` bytes per rank
 cudaError_t tp_allreduce_bf16(TpComm* t, void* buf, size_t n, cudaStream_t st);
+cudaError_t tp_allreduce_f32(TpComm* t, float* buf, size_t n, cudaStream_t st);
 cudaError_t tp_allgather(TpComm* t, const void* send, void* recv, size_t bytes, cudaStream_t st);
 
 }  // namespace qie

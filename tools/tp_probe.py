@@ -38,7 +38,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cfg = q.make_config(a.arch, context=4096)
-    eng = q.Engine(synthetic=cfg, seed=1234, device=local, max_seqs=max(a.batch, 1), max_batch_tokens=max(a.batch, 64),
+    eng = q.Engine(synthetic=cfg, seed=1234, device=local, max_seqs=a.batch + 1, max_batch_tokens=max(a.batch, 64),
                    kv_bytes=2 << 30, context=4096, use_graph=bool(a.graph), tp_rank=rank, tp_size=world)
     if world > 1:
         idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
@@ -88,6 +88,15 @@ def main():
     wb = q.weight_bytes(cfg)
     res["weight_bytes_per_gpu"] = wb // world
     res["hbm_GBs_per_gpu"] = wb / world / (ms / a.steps / 1e3) / 1e9
+    prefill_logits = None
+    if a.check:
+        # collective: one more prefill on every rank so that rank 0 can compare the logits of a
+        # single forward (2 * layers all-reduces, no KV history) with the tp_size 1 engine
+        plan0 = q.tp_plan(cfg, rank, world)
+        last_logits = eng.read_activation("logits", a.batch * plan0["vocab"]).copy()
+        s2 = eng.new_sequence()
+        eng.prefill(s2, prompts[0])
+        prefill_logits = eng.read_activation("logits", plan0["vocab"]).copy()
     if a.check and rank == 0:
         ref = q.Engine(synthetic=cfg, seed=1234, device=local, max_seqs=max(a.batch, 1),
                        max_batch_tokens=max(a.batch, 64), kv_bytes=2 << 30, context=4096, use_graph=False)
@@ -95,12 +104,16 @@ def main():
         agree, total = 0, 0
         plan = q.tp_plan(cfg, rank, world)
         v0, vl = plan["vocab0"], plan["vocab"]
-        mine = eng.read_activation("logits", a.batch * vl).astype(np.uint32).reshape(a.batch, vl)
-        mine = (mine << 16).view(np.float32)
+        mine = (last_logits.astype(np.uint32).reshape(a.batch, vl) << 16).view(np.float32)
+        pl = (prefill_logits.astype(np.uint32) << 16).view(np.float32)
         rel = []
         for b in range(a.batch):
             s = ref.new_sequence()
             t1 = ref.prefill(s, prompts[b])
+            if b == 0:
+                full = ref.read_activation("logits", cfg.vocab).astype(np.uint32)
+                full = (full << 16).view(np.float32)[v0:v0 + vl]
+                res["check_prefill_logits_rel_l2"] = float(np.linalg.norm(full - pl) / np.linalg.norm(full))
             n_cmp = all_toks.shape[0]
             # teacher-forced on the TP engine's tokens: compare the next-token choice step by step
             seq_ok = int(t1 == all_toks[0, b])
