@@ -28,7 +28,7 @@ namespace qie {
 static constexpr int PF_QT = 64;     // query rows per CTA
 static constexpr int PF_KT = 64;     // kv positions per pipeline stage
 static constexpr int PF_STAGES = 2;
-static constexpr int PF_MAX_PAGES = 2048;  // page ids cached in shared memory
+static constexpr int PF_MAX_PAGES = 1024;  // page ids cached in shared memory
 
 template <int HD>
 struct PrefillAttnSmem {
@@ -37,7 +37,10 @@ struct PrefillAttnSmem {
   static constexpr int TILE_BYTES = PF_KT * ROW_BYTES;
   static constexpr int STAGE_BYTES = 2 * TILE_BYTES;
   static constexpr int RING = PF_STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = Q_BYTES + RING + PF_MAX_PAGES * 4;
+  // the Q tile is only needed until its fragments sit in registers: it borrows the K area of
+  // stage 1 (same size), so a CTA needs 64 KiB + page ids at hd 128 and three CTAs fit on an SM
+  static constexpr int TOTAL = RING + PF_MAX_PAGES * 4;
+  static_assert(Q_BYTES == TILE_BYTES, "Q tile aliases one K tile");
 };
 
 template <int HD>
@@ -46,7 +49,7 @@ __device__ __forceinline__ uint32_t pf_swz(int r, int ch) {
 }
 
 template <int HD>
-__global__ void __launch_bounds__(128) attn_prefill_fast_kernel(FastAttnArgs a) {
+__global__ void __launch_bounds__(128, 3) attn_prefill_fast_kernel(FastAttnArgs a) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ __align__(128) unsigned char smem[];
@@ -71,9 +74,9 @@ __global__ void __launch_bounds__(128) attn_prefill_fast_kernel(FastAttnArgs a) 
   const int n_tiles = (kv_len + PF_KT - 1) / PF_KT;
   const int Dq = a.n_q * HD;
 
-  const uint32_t sq = smem_u32(smem);
-  const uint32_t sring = sq + SM::Q_BYTES;
-  int* s_pages = reinterpret_cast<int*>(smem + SM::Q_BYTES + SM::RING);
+  const uint32_t sring = smem_u32(smem);
+  const uint32_t sq = sring + SM::STAGE_BYTES;  // K area of stage 1
+  int* s_pages = reinterpret_cast<int*>(smem + SM::RING);
   const int n_pg = min(PF_MAX_PAGES, (kv_len - 1) / psz + 1);
   for (int i = threadIdx.x; i < n_pg; i += 128) s_pages[i] = bt[i];
 
@@ -112,12 +115,16 @@ __global__ void __launch_bounds__(128) attn_prefill_fast_kernel(FastAttnArgs a) 
 #pragma unroll
     for (int kc = 0; kc < KC; ++kc) ldmatrix_x4(qf[kc][0], qf[kc][1], qf[kc][2], qf[kc][3], sq + pf_swz<HD>(r, 2 * kc + (lane >> 4)));
   }
+  __syncthreads();  // stage 1 is free for K/V tile 1 from here on
 
   float o[NT][4];
 #pragma unroll
   for (int j = 0; j < NT; ++j) o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
   const float sl2 = a.scale_log2;
+  // P = hi + lo (bf16) for short contexts, where few positions average the rounding error of P;
+  // beyond 1024 positions the single bf16 term is below the output's own bf16 rounding
+  const bool two_term = kv_len <= 1024;
   // last visible position of rows g and g+8 of this warp
   const int lim0 = pos_first + warp * 16 + g, lim1 = lim0 + 8;
   const int warp_last = pos_first + min(warp * 16 + 15, n_rows - 1);  // beyond this nothing is visible to the warp
@@ -206,8 +213,10 @@ __global__ void __launch_bounds__(128) attn_prefill_fast_kernel(FastAttnArgs a) 
           ldmatrix_x4_trans(v0, v1, v2, v3, vb + pf_swz<HD>(r, ch));
           mma_bf16_16816(o[j], pa[kk], v0, v1);
           mma_bf16_16816(o[j + 1], pa[kk], v2, v3);
-          mma_bf16_16816(o[j], pb[kk], v0, v1);
-          mma_bf16_16816(o[j + 1], pb[kk], v2, v3);
+          if (two_term) {
+            mma_bf16_16816(o[j], pb[kk], v0, v1);
+            mma_bf16_16816(o[j + 1], pb[kk], v2, v3);
+          }
         }
       }
     }

@@ -463,7 +463,7 @@ static int engine_finish_setup(qie_engine* e) {
       CU(cudaMalloc(&e->mega_layers_d, c.layers * sizeof(MegaLayer)));
       CU(cudaMemcpy(e->mega_layers_d, ml.data(), c.layers * sizeof(MegaLayer), cudaMemcpyHostToDevice));
       CU(cudaMalloc(&e->mega_cand_d, (size_t)e->num_sms * 64 * sizeof(MegaCand)));
-      CU(cudaMalloc(&e->mega_bar_d, 64));
+      CU(cudaMalloc(&e->mega_bar_d, 4096));  // grid-barrier counters (8 shards on separate lines)
       CU(cudaMalloc(&e->mega_prof_d, (size_t)decode_mega_prof_slots(c.layers) * sizeof(unsigned long long)));
     }
   }

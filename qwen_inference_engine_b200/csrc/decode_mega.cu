@@ -109,6 +109,9 @@ __device__ __forceinline__ unsigned long long globaltimer() {
 // bar.sync orders the CTA's writes before thread 0's release; the release/acquire pair on
 // the counter publishes them device-wide.  Readers fetch activations with ld.cg /
 // cp.async.cg (L2), never through L1.
+// Measured alternatives (B200, batch 1 and 64): arrivals sharded over 8 counters on separate
+// lines -> same step time (the wait is the slowest CTA of the phase, not the atomics); one flag
+// word per CTA polled by 148 threads of every CTA -> 2x slower barriers (hot lines).
 __device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& epoch) {
   bar_consumers();
   if (threadIdx.x == 0) {
@@ -997,20 +1000,48 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
 
     // scores: one thread per cache position, all heads of the task
     const float den = __fsqrt_rn((float)HD);
-    for (int k = threadIdx.x; k <= ps; k += NTC) {
-      const uint4* kp = (k == ps) ? reinterpret_cast<const uint4*>(knew)
-                        : (staged && k < kstg) ? reinterpret_cast<const uint4*>(kst + k * KROW)
-                                  : reinterpret_cast<const uint4*>(
-                                        a.kv.chunk(pages[psz_shift >= 0 ? (k >> psz_shift) : k / psz], layer, 0, kvh) +
-                                        (size_t)(psz_shift >= 0 ? (k & (psz - 1)) : k % psz) * HD);
-      float2 kf[HD / 2];
+    auto k_row = [&](int k) -> const uint4* {
+      return (k == ps) ? reinterpret_cast<const uint4*>(knew)
+             : (staged && k < kstg) ? reinterpret_cast<const uint4*>(kst + k * KROW)
+                       : reinterpret_cast<const uint4*>(
+                             a.kv.chunk(pages[psz_shift >= 0 ? (k >> psz_shift) : k / psz], layer, 0, kvh) +
+                             (size_t)(psz_shift >= 0 ? (k & (psz - 1)) : k % psz) * HD);
+    };
+    // hd 64: the thread's NEXT K row is requested (8 x 16 bytes in registers) before the current
+    // row's product trees run, so the L2/DRAM latency of the row overlaps ~600 FP instructions
+    constexpr bool PREFETCH_K = NP == 1;
+    uint4 raw[HD / 8];
+    if (PREFETCH_K && (int)threadIdx.x <= ps) {
+      const uint4* kp = k_row(threadIdx.x);
 #pragma unroll
-      for (int i = 0; i < HD / 8; ++i) {
-        const uint4 t = kp[i];
-        kf[4 * i] = make_float2(lo2f(t.x), hi2f(t.x));
-        kf[4 * i + 1] = make_float2(lo2f(t.y), hi2f(t.y));
-        kf[4 * i + 2] = make_float2(lo2f(t.z), hi2f(t.z));
-        kf[4 * i + 3] = make_float2(lo2f(t.w), hi2f(t.w));
+      for (int i = 0; i < HD / 8; ++i) raw[i] = kp[i];
+    }
+    for (int k = threadIdx.x; k <= ps; k += NTC) {
+      float2 kf[HD / 2];
+      if (PREFETCH_K) {
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i) {
+          const uint4 t = raw[i];
+          kf[4 * i] = make_float2(lo2f(t.x), hi2f(t.x));
+          kf[4 * i + 1] = make_float2(lo2f(t.y), hi2f(t.y));
+          kf[4 * i + 2] = make_float2(lo2f(t.z), hi2f(t.z));
+          kf[4 * i + 3] = make_float2(lo2f(t.w), hi2f(t.w));
+        }
+        if (k + NTC <= ps) {
+          const uint4* kn = k_row(k + NTC);
+#pragma unroll
+          for (int i = 0; i < HD / 8; ++i) raw[i] = kn[i];
+        }
+      } else {
+        const uint4* kp = k_row(k);
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i) {
+          const uint4 t = kp[i];
+          kf[4 * i] = make_float2(lo2f(t.x), hi2f(t.x));
+          kf[4 * i + 1] = make_float2(lo2f(t.y), hi2f(t.y));
+          kf[4 * i + 2] = make_float2(lo2f(t.z), hi2f(t.z));
+          kf[4 * i + 3] = make_float2(lo2f(t.w), hi2f(t.w));
+        }
       }
       // dot / sqrtf(hd): for hd = 64 the divisor is exactly 8, and x / 8 == x * 0.125 bit for bit
       for (int i = 0; i < hs; ++i) {
@@ -1083,17 +1114,40 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
         if (i < hs) {
           const float* s = score + i * tmax + t0;
           int k = 0;
-          for (; k + 4 <= tn; k += 4) {
-            const float4 pr = *reinterpret_cast<const float4*>(s + k);
-            const float prj[4] = {pr.x, pr.y, pr.z, pr.w};
+          if (tn >= 4) {
+            // groups of 4 positions, the next group's probabilities and V words requested before the
+            // current group's FFMA chain runs (same ascending order: the chain is the spec, its
+            // operands just arrive earlier)
+            const unsigned char* vl = vb + 4 * lane;
+            float4 pr = *reinterpret_cast<const float4*>(s);
+            uint32_t vv[4][NP];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
-              for (int p = 0; p < NP; ++p) {
-                const uint32_t vv = *reinterpret_cast<const uint32_t*>(vb + (k + j) * (HD * 2) + (64 * p + 2 * lane) * 2);
-                o[q2][p][0] = __fmaf_rn(prj[j], lo2f(vv), o[q2][p][0]);
-                o[q2][p][1] = __fmaf_rn(prj[j], hi2f(vv), o[q2][p][1]);
-              }
+              for (int p = 0; p < NP; ++p) vv[j][p] = *reinterpret_cast<const uint32_t*>(vl + j * (HD * 2) + 128 * p);
+            for (; k + 4 <= tn; k += 4) {
+              const bool more = k + 8 <= tn;
+              const int kn = more ? k + 4 : k;
+              const float4 prn = *reinterpret_cast<const float4*>(s + kn);
+              uint32_t vn[4][NP];
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int p = 0; p < NP; ++p) vn[j][p] = *reinterpret_cast<const uint32_t*>(vl + (kn + j) * (HD * 2) + 128 * p);
+              const float prj[4] = {pr.x, pr.y, pr.z, pr.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int p = 0; p < NP; ++p) {
+                  o[q2][p][0] = __fmaf_rn(prj[j], lo2f(vv[j][p]), o[q2][p][0]);
+                  o[q2][p][1] = __fmaf_rn(prj[j], hi2f(vv[j][p]), o[q2][p][1]);
+                }
+              pr = prn;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int p = 0; p < NP; ++p) vv[j][p] = vn[j][p];
+            }
           }
           for (; k < tn; ++k) {
             const float pk = s[k];

@@ -143,6 +143,7 @@ struct TcArgs {
   int M, K;
   int nseg, n_tiles, splits, kb_per_split, kb_total;
   int epi, dual, w_static, ld_out;
+  int staged;  // splits == 1 and 8-element aligned outputs: epilogue through a bf16 tile in shared memory, 16-byte global accesses
   TcSeg seg[3];
   bf16* out;  // [M, ld_out]
 };
@@ -253,6 +254,108 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
   }
 
   // ================= epilogue =================
+  if (g.staged) {
+    // No split-K (prefill / large batches): lane = weight row, column = token, but the output is
+    // [token][weight row] -- per-lane 2-byte global accesses would serialise (and the residual's
+    // read-modify-write would expose one DRAM round trip per token).  The tile is transposed
+    // through shared memory as bf16 [token][128 rows] (the pipeline ring is idle by now), then
+    // written -- or read-modified-written -- with independent 16-byte accesses, a 256-byte
+    // contiguous run per token.  Rounding points are the reference's (R3 / R8 / R9).
+    constexpr uint32_t PITCH = BM * 2;
+    const uint32_t stg = smem0;
+    if (warp >= 2) {
+      const int qd = warp & 3;
+      pdl_wait();  // `out` may still be read (residual) by the previous kernel
+      if (nkb > 0) {
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+      }
+      const int lane_row = qd * 32 + lane;
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[16];
+        if (nkb > 0) {
+          tmem_ld16(tmem_base + ((uint32_t)(qd * 32) << 16) + c0, r);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) r[j] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const unsigned short hb = __bfloat16_as_ushort(f2bf(__uint_as_float(r[j])));
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg + (uint32_t)(c0 + j) * PITCH + (uint32_t)lane_row * 2u), "h"(hb) : "memory");
+        }
+      }
+      tc_fence_before();
+      asm volatile("bar.sync 2, 128;" ::: "memory");  // the four epilogue warps
+      const int t = threadIdx.x - 64;
+      const int n_tok = min(BN, g.M - tok_base);
+      auto lds128 = [](uint32_t addr) {
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+        return v;
+      };
+      if (!g.dual) {
+        const int total = n_tok * (BM / 8);
+        for (int c = t; c < total; c += 4 * 128) {
+          uint4 y[4], x[4];
+          bf16* dst[4];
+          bool ok[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int cc = c + u * 128;
+            const int tok = cc >> 4, part = cc & 15;
+            const int w_row = row0 + part * 8;
+            ok[u] = cc < total && w_row < seg_rows;
+            dst[u] = g.out + (size_t)(tok_base + tok) * g.ld_out + col0 + w_row;
+            if (ok[u]) {
+              y[u] = lds128(stg + (uint32_t)tok * PITCH + (uint32_t)part * 16u);
+              if (g.epi == EPI_RESIDUAL) x[u] = *reinterpret_cast<const uint4*>(dst[u]);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (!ok[u]) continue;
+            if (g.epi == EPI_RESIDUAL) {
+              const uint32_t xs[4] = {x[u].x, x[u].y, x[u].z, x[u].w}, ys[4] = {y[u].x, y[u].y, y[u].z, y[u].w};
+              uint32_t o4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                o4[e] = pack2(f2bf(__fadd_rn(lo2f(xs[e]), lo2f(ys[e]))), f2bf(__fadd_rn(hi2f(xs[e]), hi2f(ys[e]))));
+              *reinterpret_cast<uint4*>(dst[u]) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+            } else {
+              *reinterpret_cast<uint4*>(dst[u]) = y[u];
+            }
+          }
+        }
+      } else {
+        // gate rows sit in lanes 0-63, the matching up rows in lanes 64-127
+        const int total = n_tok * (BM / 16);
+        for (int c = t; c < total; c += 128) {
+          const int tok = c >> 3, part = c & 7;
+          const int w_row = row0 + part * 8;
+          if (w_row >= seg_rows) continue;
+          const uint4 gt = lds128(stg + (uint32_t)tok * PITCH + (uint32_t)part * 16u);
+          const uint4 up = lds128(stg + (uint32_t)tok * PITCH + (uint32_t)(BM / 2) * 2u + (uint32_t)part * 16u);
+          const uint32_t gs[4] = {gt.x, gt.y, gt.z, gt.w}, us[4] = {up.x, up.y, up.z, up.w};
+          uint32_t o4[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a0 = __fmul_rn(lo2f(us[e]), bf2f(f2bf(silu_ref_f(lo2f(gs[e])))));
+            const float a1 = __fmul_rn(hi2f(us[e]), bf2f(f2bf(silu_ref_f(hi2f(gs[e])))));
+            o4[e] = pack2(f2bf(a0), f2bf(a1));
+          }
+          *reinterpret_cast<uint4*>(g.out + (size_t)(tok_base + tok) * g.ld_out + w_row) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        }
+      }
+    }
+    __syncthreads();
+    if (warp == 1) {
+      tc_fence_after();
+      tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+    return;
+  }
   // red[token][lane] fp32 (conflict-free: a warp writes 32 consecutive floats per token);
   // it reuses the pipeline ring, which is idle once tmem_full has fired.
   const uint32_t red = smem0;
@@ -486,6 +589,11 @@ cudaError_t launch_gemm_tcgen05(const TcGemm& t, int num_sms, cudaStream_t st, i
   g.kb_per_split = (g.kb_total + splits - 1) / splits;
   splits = (g.kb_total + g.kb_per_split - 1) / g.kb_per_split;
   g.splits = splits;
+  {
+    bool vec = (t.ld_out % 8 == 0) && ((reinterpret_cast<uintptr_t>(t.out) & 15) == 0);
+    for (int i = 0; i < t.nseg; ++i) vec = vec && (t.rows[i] % 8 == 0);
+    g.staged = splits == 1 && vec;
+  }
   cudaError_t e;
   switch (BN) {
     case 16: e = launch_bn<16>(t, g, token_tiles, st); break;
