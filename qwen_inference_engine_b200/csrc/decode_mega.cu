@@ -1007,41 +1007,18 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
                              a.kv.chunk(pages[psz_shift >= 0 ? (k >> psz_shift) : k / psz], layer, 0, kvh) +
                              (size_t)(psz_shift >= 0 ? (k & (psz - 1)) : k % psz) * HD);
     };
-    // hd 64: the thread's NEXT K row is requested (8 x 16 bytes in registers) before the current
-    // row's product trees run, so the L2/DRAM latency of the row overlaps ~600 FP instructions
-    constexpr bool PREFETCH_K = NP == 1;
-    uint4 raw[HD / 8];
-    if (PREFETCH_K && (int)threadIdx.x <= ps) {
-      const uint4* kp = k_row(threadIdx.x);
-#pragma unroll
-      for (int i = 0; i < HD / 8; ++i) raw[i] = kp[i];
-    }
+    // (measured: requesting the thread's next K row into registers ahead of the product trees does not
+    // shorten this loop -- it is bound by the broadcast loads of q and FP32 issue -- and costs spills)
     for (int k = threadIdx.x; k <= ps; k += NTC) {
+      const uint4* kp = k_row(k);
       float2 kf[HD / 2];
-      if (PREFETCH_K) {
 #pragma unroll
-        for (int i = 0; i < HD / 8; ++i) {
-          const uint4 t = raw[i];
-          kf[4 * i] = make_float2(lo2f(t.x), hi2f(t.x));
-          kf[4 * i + 1] = make_float2(lo2f(t.y), hi2f(t.y));
-          kf[4 * i + 2] = make_float2(lo2f(t.z), hi2f(t.z));
-          kf[4 * i + 3] = make_float2(lo2f(t.w), hi2f(t.w));
-        }
-        if (k + NTC <= ps) {
-          const uint4* kn = k_row(k + NTC);
-#pragma unroll
-          for (int i = 0; i < HD / 8; ++i) raw[i] = kn[i];
-        }
-      } else {
-        const uint4* kp = k_row(k);
-#pragma unroll
-        for (int i = 0; i < HD / 8; ++i) {
-          const uint4 t = kp[i];
-          kf[4 * i] = make_float2(lo2f(t.x), hi2f(t.x));
-          kf[4 * i + 1] = make_float2(lo2f(t.y), hi2f(t.y));
-          kf[4 * i + 2] = make_float2(lo2f(t.z), hi2f(t.z));
-          kf[4 * i + 3] = make_float2(lo2f(t.w), hi2f(t.w));
-        }
+      for (int i = 0; i < HD / 8; ++i) {
+        const uint4 t = kp[i];
+        kf[4 * i] = make_float2(lo2f(t.x), hi2f(t.x));
+        kf[4 * i + 1] = make_float2(lo2f(t.y), hi2f(t.y));
+        kf[4 * i + 2] = make_float2(lo2f(t.z), hi2f(t.z));
+        kf[4 * i + 3] = make_float2(lo2f(t.w), hi2f(t.w));
       }
       // dot / sqrtf(hd): for hd = 64 the divisor is exactly 8, and x / 8 == x * 0.125 bit for bit
       for (int i = 0; i < hs; ++i) {
