@@ -314,7 +314,10 @@ static void engine_free(qie_engine* e) {
   void* dev[] = {e->blob, e->cos_d, e->sin_d, e->kv.pool, e->block_table_d, e->ids_d, e->pos_d, e->slot_d,
                  e->sampled_d, e->rowstep_d, e->x, e->xn, e->q, e->k, e->v, e->att, e->h, e->logits, e->qkv,
                  e->gemm_ws, e->attn_ws_o, e->attn_ws_ml, e->gemm_counters, e->mega_layers_d, e->mega_cand_d,
-                 e->mega_bar_d, e->mega_prof_d, e->mega_wmaps_d[0], e->mega_wmaps_d[1], e->tp_buf, e->tp_cand};
+                 e->mega_bar_d, e->mega_prof_d, e->mega_wmaps_d[0], e->mega_wmaps_d[1], e->tp_buf, e->tp_cand, e->tp_xbuf, e->x2,
+                 e->mega_wmaps_tp_d[0], e->mega_wmaps_tp_d[1]};
+  for (int r = 0; r < MEGA_MAX_TP; ++r)
+    if (e->tp_peer_xbuf[r] && e->tp_peer_xbuf[r] != e->tp_xbuf) cudaIpcCloseMemHandle(e->tp_peer_xbuf[r]);
   tp_comm_destroy(&e->tp);
   for (void* p : dev)
     if (p) cudaFree(p);
@@ -422,6 +425,12 @@ static int engine_finish_setup(qie_engine* e) {
   if (o.tp_size > 1) {
     CU(cudaMalloc(&e->tp_buf, R * H * sizeof(float)));
     CU(cudaMalloc(&e->tp_cand, (size_t)(1 + o.tp_size) * R * sizeof(TpCand)));
+    if (o.tp_size <= MEGA_MAX_TP) {
+      const size_t xb = 256 + (size_t)2 * o.tp_size * MEGA_TP_ROWS * H * sizeof(float);
+      CU(cudaMalloc(&e->tp_xbuf, xb));
+      CU(cudaMemsetAsync(e->tp_xbuf, 0, xb, e->stream));
+      CU(cudaMalloc(&e->x2, R * H * sizeof(bf16)));
+    }
   }
   {
     const char* mv = getenv("QIE_MEGA");
@@ -459,6 +468,32 @@ static int engine_finish_setup(qie_engine* e) {
         if (!ok) return fail(QIE_ECUDA, "cuTensorMapEncodeTiled failed for the weight views");
         CU(cudaMalloc(&e->mega_wmaps_d[ts], maps.size() * sizeof(TensorMap2D)));
         CU(cudaMemcpy(e->mega_wmaps_d[ts], maps.data(), maps.size() * sizeof(TensorMap2D), cudaMemcpyHostToDevice));
+      }
+      if (o.tp_size > 1 && o.tp_size <= MEGA_MAX_TP && (e->plan.inter % 64 == 0) && ((e->plan.n_q * c.head_dim) % 64 == 0)) {
+        // this rank's shard as tensor-map views of the full blob: row slices for q/k/v/gate/up/lm_head, column
+        // slices (row stride = full width) for o_proj/down_proj
+        const TpPlan& pl = e->plan;
+        const int Dq_l = pl.n_q * c.head_dim, Dkv_l = pl.n_kv * c.head_dim;
+        for (int ts = 0; ts < 2; ++ts) {
+          std::vector<TensorMap2D> maps((size_t)7 * c.layers + 1);
+          bool ok = true;
+          const int kc = e->mega_kc[ts];
+          for (int l = 0; l < c.layers && ok; ++l) {
+            const LayerWeights& w = e->L[l];
+            TensorMap2D* m = &maps[(size_t)7 * l];
+            ok = ok && make_tensor_map_w3d(m + 0, w.q + (size_t)pl.q_row0 * H, Dq_l, (int)H, kc) == cudaSuccess;
+            ok = ok && make_tensor_map_w3d(m + 1, w.k + (size_t)pl.kv_row0 * H, Dkv_l, (int)H, kc) == cudaSuccess;
+            ok = ok && make_tensor_map_w3d(m + 2, w.v + (size_t)pl.kv_row0 * H, Dkv_l, (int)H, kc) == cudaSuccess;
+            ok = ok && make_tensor_map_w3d(m + 3, w.o + pl.q_row0, (int)H, Dq_l, kc, (int)Dq) == cudaSuccess;
+            ok = ok && make_tensor_map_w3d(m + 4, w.gate + (size_t)pl.inter0 * H, pl.inter, (int)H, kc) == cudaSuccess;
+            ok = ok && make_tensor_map_w3d(m + 5, w.up + (size_t)pl.inter0 * H, pl.inter, (int)H, kc) == cudaSuccess;
+            ok = ok && make_tensor_map_w3d(m + 6, w.down + pl.inter0, (int)H, pl.inter, kc, (int)I) == cudaSuccess;
+          }
+          ok = ok && make_tensor_map_w3d(&maps[(size_t)7 * c.layers], e->lm_head + (size_t)pl.vocab0 * H, pl.vocab, (int)H, kc) == cudaSuccess;
+          if (!ok) return fail(QIE_ECUDA, "cuTensorMapEncodeTiled failed for the tensor-parallel weight views");
+          CU(cudaMalloc(&e->mega_wmaps_tp_d[ts], maps.size() * sizeof(TensorMap2D)));
+          CU(cudaMemcpy(e->mega_wmaps_tp_d[ts], maps.data(), maps.size() * sizeof(TensorMap2D), cudaMemcpyHostToDevice));
+        }
       }
       CU(cudaMalloc(&e->mega_layers_d, c.layers * sizeof(MegaLayer)));
       CU(cudaMemcpy(e->mega_layers_d, ml.data(), c.layers * sizeof(MegaLayer), cudaMemcpyHostToDevice));
@@ -678,6 +713,57 @@ int qie_engine_tp_connect(qie_engine* e, const void* id128) {
   CU(cudaSetDevice(e->opts.device));
   char err[256];
   if (tp_comm_init(&e->tp, id128, e->opts.tp_rank, e->opts.tp_size, err, sizeof(err))) return fail(QIE_ECUDA, "%s", err);
+  // Peer mappings of the persistent kernel's exchange buffers: every rank exports its buffer with CUDA IPC, the
+  // 64-byte handles are all-gathered over the communicator that was just created, every rank opens its peers'.
+  // If any step fails the engine stays on the per-operator tensor-parallel path (NCCL all-reduce per projection).
+  const char* off = getenv("QIE_TP_MEGA");
+  if (e->tp_xbuf && e->mega_wmaps_tp_d[0] && !(off && off[0] == '0')) {
+    const int tp = e->opts.tp_size, me = e->opts.tp_rank;
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof(mine));
+    const bool ok = cudaIpcGetMemHandle(&mine, e->tp_xbuf) == cudaSuccess;
+    if (!ok) (void)cudaGetLastError();
+    // the all-gather is collective: every rank takes part even if its own export failed
+    struct Rec { cudaIpcMemHandle_t h; int ok; int pad[15]; };
+    static_assert(sizeof(Rec) == 128, "handle record");
+    std::vector<Rec> recs(tp + 1);
+    memset(recs.data(), 0, recs.size() * sizeof(Rec));
+    recs[0].h = mine;
+    recs[0].ok = ok ? 1 : 0;
+    Rec* rd = nullptr;
+    CU(cudaMalloc(&rd, (size_t)(tp + 1) * sizeof(Rec)));
+    CU(cudaMemcpyAsync(rd, recs.data(), sizeof(Rec), cudaMemcpyHostToDevice, e->stream));
+    CU(tp_allgather(&e->tp, rd, rd + 1, sizeof(Rec), e->stream));
+    CU(cudaMemcpyAsync(recs.data() + 1, rd + 1, (size_t)tp * sizeof(Rec), cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    cudaFree(rd);
+    bool all_ok = true;
+    for (int r = 0; r < tp; ++r) all_ok = all_ok && recs[1 + r].ok == 1;
+    if (all_ok) {
+      for (int r = 0; r < tp && all_ok; ++r) {
+        if (r == me) {
+          e->tp_peer_xbuf[r] = e->tp_xbuf;
+        } else if (cudaIpcOpenMemHandle(&e->tp_peer_xbuf[r], recs[1 + r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          (void)cudaGetLastError();
+          e->tp_peer_xbuf[r] = nullptr;
+          all_ok = false;
+        }
+      }
+    }
+    // agree on the outcome: one rank on the persistent kernel and one on NCCL would dead-lock
+    int* flag_d = nullptr;
+    CU(cudaMalloc(&flag_d, (size_t)(tp + 1) * 128));
+    int mine_ok = all_ok ? 1 : 0;
+    CU(cudaMemcpyAsync(flag_d, &mine_ok, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+    CU(tp_allgather(&e->tp, flag_d, flag_d + 32, 128, e->stream));
+    std::vector<int> flags((size_t)tp * 32);
+    CU(cudaMemcpyAsync(flags.data(), flag_d + 32, (size_t)tp * 128, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    cudaFree(flag_d);
+    bool everyone = true;
+    for (int r = 0; r < tp; ++r) everyone = everyone && flags[(size_t)r * 32] == 1;
+    e->tp_mega_ready = everyone;
+  }
   return QIE_OK;
 }
 

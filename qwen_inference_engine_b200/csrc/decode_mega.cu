@@ -128,6 +128,61 @@ __device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& epoch) {
   bar_consumers();
 }
 
+// Tensor-parallel exchange point (behind o_proj and down_proj): local grid barrier, then CTA 0 tells every
+// peer "this rank has finished exchange number xepoch" with a system-scope release store into the peer's flag
+// word, and every CTA waits until all peers have said the same.  Each CTA's thread 0 fences at system scope
+// before it arrives at the local barrier, so the CTA's peer stores are ordered before CTA 0's flag.
+__device__ __forceinline__ void tp_exchange_sync(const MegaArgs& a, unsigned& epoch, unsigned xepoch) {
+  bar_consumers();
+  if (threadIdx.x == 0) {
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    epoch += gridDim.x;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(a.bar) : "memory");
+    unsigned v;
+    long long t0 = clock64();
+    do {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.bar) : "memory");
+      if (clock64() - t0 > SPIN_LIMIT) __trap();
+    } while (v < epoch);
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    if (blockIdx.x == 0)
+      for (int r = 0; r < a.tp_size; ++r)
+        if (r != a.tp_rank)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.tp_flag[r] + a.tp_rank), "r"(xepoch) : "memory");
+    for (int r = 0; r < a.tp_size; ++r) {
+      if (r == a.tp_rank) continue;
+      t0 = clock64();
+      do {
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.tp_flag[a.tp_rank] + r) : "memory");
+        if (clock64() - t0 > 4 * SPIN_LIMIT) __trap();  // the peer may still be launching its kernel
+      } while ((int)(v - xepoch) < 0);
+    }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+  }
+  bar_consumers();
+}
+
+// Residual rows after an exchange: x_new = bf16(x + bf16(sum over ranks of the fp32 partial sums)), ranks in
+// ascending order on every rank (identical bits everywhere), written into the activation region (layout of
+// load_rows) by every CTA and into the other residual buffer by CTA 0.
+__device__ __forceinline__ void load_rows_tp(const MegaArgs& a, uint32_t act, int B, int H, const bf16* x_cur, bf16* x_next, int xpar) {
+  const int AS = (H + 8) * 2, hp = H >> 1;
+  for (int i = threadIdx.x; i < B * hp; i += NTC) {
+    const int b = i / hp, n = (i - b * hp) * 2;
+    const uint32_t old = __ldcg(reinterpret_cast<const uint32_t*>(x_cur + (size_t)b * H + n));
+    float2 sum = __ldcg(reinterpret_cast<const float2*>(a.tp_part[a.tp_rank] + (((size_t)xpar * a.tp_size) * MEGA_TP_ROWS + b) * H + n));
+    for (int r = 1; r < a.tp_size; ++r) {
+      const float2 pr = __ldcg(reinterpret_cast<const float2*>(a.tp_part[a.tp_rank] + (((size_t)xpar * a.tp_size + r) * MEGA_TP_ROWS + b) * H + n));
+      sum.x = __fadd_rn(sum.x, pr.x);
+      sum.y = __fadd_rn(sum.y, pr.y);
+    }
+    const uint32_t nw = pack2(f2bf(__fadd_rn(lo2f(old), bf2f(f2bf(sum.x)))), f2bf(__fadd_rn(hi2f(old), bf2f(f2bf(sum.y)))));
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(act + b * AS + n * 2), "r"(nw) : "memory");
+    if (blockIdx.x == 0) *reinterpret_cast<uint32_t*>(x_next + (size_t)b * H + n) = nw;
+  }
+  bar_consumers();
+}
+
 // ---------------------------------------------------------------- GEMM phase description
 struct Phase {
   const TensorMap2D* W[3];  // weight tensor maps (3-D view, box = 8 rows x KC)
@@ -137,6 +192,7 @@ struct Phase {
   int nseg, K, dual, units, kind;
   int n_c, nch, nu;  // units of THIS CTA, chunks per unit, units per round (host-precomputed tables)
   int upr, row2;     // weight rows per unit (8, or 16 for lm_head pairs), row offset of the second tile of a dual unit
+  int xpar;          // tensor parallel: which half of the exchange buffer this phase's partial sums go to
 };
 
 __device__ __forceinline__ void make_phase(const MegaArgs& a, int idx, Phase& p) {
@@ -144,6 +200,7 @@ __device__ __forceinline__ void make_phase(const MegaArgs& a, int idx, Phase& p)
   p.W2 = nullptr;
   p.dual = 0;
   p.nseg = 1;
+  p.xpar = 0;
   if (idx >= 4 * a.L) {
     // lm_head: a unit is a PAIR of 8-row tiles (rows r..r+7 and r+8..r+15) accumulated side by side
     // like gate/up: two independent HMMA chains per warp and each activation fragment feeds both
@@ -381,6 +438,11 @@ __device__ __forceinline__ void epilogue_store(const MegaArgs& a, const Phase& p
     }
     case PH_O:
     case PH_DOWN: {
+      if (a.tp_size > 1) {  // fp32 partial sums of this rank -> every rank's exchange buffer (peer stores over NVLink)
+        const size_t off = (((size_t)p.xpar * a.tp_size + a.tp_rank) * MEGA_TP_ROWS + tok) * a.H + n;
+        for (int r = 0; r < a.tp_size; ++r) *reinterpret_cast<float2*>(a.tp_part[r] + off) = make_float2(v0, v1);
+        break;
+      }
       uint32_t* dst = reinterpret_cast<uint32_t*>(a.x + (size_t)tok * a.H + n);
       const uint32_t old = MT == 0 ? res_old : __ldcg(dst);
       const float y0 = bf2f(f2bf(v0)), y1 = bf2f(f2bf(v1));
@@ -1206,6 +1268,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
   };
   const uint32_t act = smem_base + a.off_act;
   const int H = a.H, Dq = a.n_q * a.hd;
+  // tensor parallel: exchanges done in this launch, residual ping-pong, generation base of the flag words
+  const bool tp = a.tp_size > 1;
+  unsigned xch = 0;
+  const unsigned xbase = tp ? __ldcg(a.tp_epoch) : 0u;
+  const bf16* x_cur = a.x;
+  bf16* x_next = a.x2;
   Best best[MTT][2];
 #pragma unroll
   for (int m = 0; m < MTT; ++m) best[m][0] = best[m][1] = Best{-CUDART_INF_F, -1};
@@ -1266,7 +1334,14 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
         load_rows(act, a.B, H, [&](int r) { return a.xn + (size_t)r * H; });
         stamp();
       } else {
-        load_rows(act, a.B, H, [&](int b) { return from_embed ? a.embed + (size_t)a.ids[b] * H : a.x + (size_t)b * H; });
+        if (tp && !from_embed) {
+          load_rows_tp(a, act, a.B, H, x_cur, x_next, (int)((xch - 1) & 1));
+          const bf16* t = x_cur;
+          x_cur = x_next;
+          x_next = const_cast<bf16*>(t);
+        } else {
+          load_rows(act, a.B, H, [&](int b) { return from_embed ? a.embed + (size_t)a.ids[b] * H : a.x + (size_t)b * H; });
+        }
         stamp();
         if (FAST)
           rmsnorm_rows_fast(a, smem, a.B, H, which);
@@ -1277,6 +1352,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
     }
     Phase p;
     make_phase(a, idx, p);
+    p.xpar = (int)(xch & 1);
     if (kind == PH_QKV && a.attn_kstg > 0)
       attention_phase<NP>(a, l, smem, 0);  // warps 1..: request what attention needs that does not depend on q/k/v
     bool done = false;
@@ -1320,9 +1396,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
         a.cand[(size_t)blockIdx.x * a.B + threadIdx.x] = MegaCand{bv, bi};
       }
     }
-    grid_sync(a.bar, epoch);
+    if (tp && (kind == PH_O || kind == PH_DOWN)) {
+      ++xch;
+      tp_exchange_sync(a, epoch, xbase + xch);
+    } else {
+      grid_sync(a.bar, epoch);
+    }
     stamp();
   }
+  if (tp && blockIdx.x == 0 && threadIdx.x == 0) *a.tp_epoch = xbase + xch;  // every CTA read it before its first barrier
   if (!with_head) return;
   // ---- arg-max over the CTAs' candidates + step bookkeeping (advance_kernel)
   if (a.greedy && warp == 0) {

@@ -311,9 +311,11 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
 // weight-tile set: larger tiles for small batches when the ring still holds enough of them
 static int mega_tile_set(const qie_engine* e, int n, int max_kv_len) {
   const qie_config& c = e->cfg;
-  const int fast = e->opts.numerics == QIE_NUMERICS_FAST;
+  const bool tp = e->tp.size > 1;
+  const int fast = !tp && e->opts.numerics == QIE_NUMERICS_FAST;
+  const int I = tp ? e->plan.inter : c.inter, nq = tp ? e->plan.n_q : c.n_q, nkv = tp ? e->plan.n_kv : c.n_kv;
   if (n <= 8 && e->mega_kc[1] > e->mega_kc[0] &&
-      decode_mega_supports(c.hidden, c.inter, c.layers, c.n_q, c.n_kv, c.head_dim, n, max_kv_len, e->num_sms, e->mega_kc[1], fast))
+      decode_mega_supports(c.hidden, I, c.layers, nq, nkv, c.head_dim, n, max_kv_len, e->num_sms, e->mega_kc[1], fast))
     return 1;
   return 0;
 }
@@ -459,8 +461,16 @@ cudaError_t forward_rows_tp(qie_engine* e, int n, int max_kv_len, int out_row0, 
 }
 
 bool decode_uses_mega(const qie_engine* e, int n, int max_kv_len) {
-  if (!e->use_mega || e->capture || !e->mega_layers_d || e->tp.size > 1) return false;
+  if (!e->use_mega || e->capture || !e->mega_layers_d) return false;
   const qie_config& c = e->cfg;
+  if (e->tp.size > 1) {
+    // tensor parallel: the persistent kernel runs this rank's shard and exchanges partial sums over NVLink peer
+    // mappings (<= MEGA_TP_ROWS rows, greedy sampling, reference-order numerics)
+    if (!e->tp_mega_ready || n > MEGA_TP_ROWS || e->topk != 1) return false;
+    const TpPlan& pl = e->plan;
+    return decode_mega_supports(c.hidden, pl.inter, c.layers, pl.n_q, pl.n_kv, c.head_dim, n, max_kv_len, e->num_sms,
+                                e->mega_kc[mega_tile_set(e, n, max_kv_len)], 0);
+  }
   const int fast = e->opts.numerics == QIE_NUMERICS_FAST;  // fast numerics: persistent kernel for <= 8 rows
   return decode_mega_supports(c.hidden, c.inter, c.layers, c.n_q, c.n_kv, c.head_dim, n, max_kv_len, e->num_sms,
                               e->mega_kc[mega_tile_set(e, n, max_kv_len)], fast);
@@ -515,7 +525,41 @@ cudaError_t forward_decode_mega(qie_engine* e, int n, int max_kv_len, float temp
   }
   a.advance = 1;
   a.n_layers_run = e->mega_layers_run;
+  const bool tp = e->tp.size > 1;
+  if (tp) {
+    // this rank's shard: local heads / intermediate slice / vocabulary range, weight views of the shard
+    const TpPlan& pl = e->plan;
+    a.I = pl.inter;
+    a.n_q = pl.n_q;
+    a.n_kv = pl.n_kv;
+    a.V = pl.vocab;
+    a.wmaps = e->mega_wmaps_tp_d[tset];
+    a.lm_head = e->lm_head + (size_t)pl.vocab0 * c.hidden;
+    a.greedy = 0;  // local logits only; the arg-max over ranks follows the kernel
+    a.fast = 0;
+    a.tp_size = e->tp.size;
+    a.tp_rank = e->tp.rank;
+    for (int r = 0; r < e->tp.size; ++r) {
+      a.tp_flag[r] = reinterpret_cast<unsigned*>(e->tp_peer_xbuf[r]);
+      a.tp_part[r] = reinterpret_cast<float*>(reinterpret_cast<char*>(e->tp_peer_xbuf[r]) + 256);
+    }
+    a.tp_epoch = reinterpret_cast<unsigned*>(e->tp_xbuf) + 32;  // word 32 of the flag block: local generation base
+    a.x2 = e->x2;
+  }
   cudaError_t r = launch_decode_mega(a, e->num_sms, e->stream);
+  if (tp) {
+    if (r != cudaSuccess) return r;  // the ranks must stay on the same path: no silent fallback here
+    ++e->launches;
+    const TpPlan& pl = e->plan;
+    const int R = e->opts.max_batch_tokens;
+    QIE_TRY(KK_SAMPLE, launch_sample_topk(e->logits, e->sampled_d, n, pl.vocab, 1.0f, 1, e->seed, 0, nullptr, e->stream));
+    QIE_TRY(KK_SAMPLE, launch_tp_cand_make(e->logits, e->sampled_d, e->tp_cand, n, pl.vocab, pl.vocab0, e->stream));
+    r = tp_allgather(&e->tp, e->tp_cand, e->tp_cand + R, (size_t)n * sizeof(TpCand), e->stream);
+    if (r != cudaSuccess) return r;
+    QIE_TRY(KK_SAMPLE, launch_tp_cand_merge(e->tp_cand + R, e->tp.size, n, e->sampled_d, e->stream));
+    QIE_TRY(KK_ADVANCE, launch_advance(e->pos_d, e->ids_d, e->sampled_d, n, e->rowstep_d, e->stream));
+    return cudaSuccess;
+  }
   if (r != cudaSuccess) {
     // e.g. the cooperative launch cannot be co-scheduled (SMs taken by another context): this
     // engine falls back to the per-operator GPU launches for good (still no CPU path).  A shape

@@ -120,7 +120,7 @@ struct TensorMap2D {
   alignas(64) unsigned char opaque[128];  // CUtensorMap
 };
 cudaError_t make_tensor_map_2d(TensorMap2D* out, const bf16* base, int rows, int K, int box_rows);
-cudaError_t make_tensor_map_w3d(TensorMap2D* out, const bf16* base, int rows, int K, int kc);
+cudaError_t make_tensor_map_w3d(TensorMap2D* out, const bf16* base, int rows, int K, int kc, int ld = 0);  // ld: row stride in elements (0 = K)
 int tc_token_tile(int M);
 struct TcGemm {
   const TensorMap2D* w[3];  // weight maps, box rows = 128
@@ -171,6 +171,8 @@ cudaError_t launch_advance(int* pos, int* ids, const int* sampled, int n, int* s
 // ---------------------------------------------------------------- persistent decode step
 // decode_mega.cu: ONE cooperative launch runs a whole decode step (all layers, lm_head,
 // greedy arg-max, bookkeeping) for up to 64 sequences in reference-order arithmetic.
+constexpr int MEGA_MAX_TP = 4;
+constexpr int MEGA_TP_ROWS = 16;
 struct MegaLayer {
   const bf16 *in_ln, *q, *k, *v, *o, *q_norm, *k_norm, *post_ln, *gate, *up, *down;
 };
@@ -204,6 +206,15 @@ struct MegaArgs {
   int fast;                          // 1: fast (tolerance) numerics, <= 8 rows: split-K over the warps, parallel RMSNorm
   int kv_l2_prefetch;                // 1: request the next layer's cached K/V into L2 one phase group ahead of its attention
   int n_layers_run;                  // debug: stop after this many layers (0 = all, then lm_head)
+  // tensor parallel inside the kernel (tp_size > 1, <= 16 rows): n_q / n_kv / I / V and the weight maps describe
+  // THIS rank's shard; o_proj / down_proj accumulators are written as fp32 partial sums into every rank's
+  // exchange buffer over NVLink peer mappings, a cross-GPU flag barrier replaces the grid barrier behind those two
+  // phases, and the next phase's row load adds the partial sums in rank order (one bf16 rounding, like tp_size 1)
+  int tp_size, tp_rank;
+  float* tp_part[MEGA_MAX_TP];       // rank r's exchange buffer [2][tp_size][MEGA_TP_ROWS][H] (peer-mapped for r != tp_rank)
+  unsigned* tp_flag[MEGA_MAX_TP];    // rank r's flag words: flag[s] = number of exchanges rank s has completed
+  unsigned* tp_epoch;                // local: exchanges completed before this launch (kept on the device: graph replay)
+  bf16* x2;                          // ping-pong partner of x for the residual stream
   int KC;  // k elements per weight tile = box depth of wmaps (decode_mega_kc at engine setup)
   // geometry, filled by the launcher (ph_*: per GEMM phase kind qkv/o/gate+up/down/lm_head)
   int ph_nu[5];  // units per round (NW, or NW / token tiles when the tiles of a unit are spread over warps)
