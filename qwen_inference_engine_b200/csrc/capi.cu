@@ -426,7 +426,7 @@ static int engine_finish_setup(qie_engine* e) {
     CU(cudaMalloc(&e->tp_buf, R * H * sizeof(float)));
     CU(cudaMalloc(&e->tp_cand, (size_t)(1 + o.tp_size) * R * sizeof(TpCand)));
     if (o.tp_size <= MEGA_MAX_TP) {
-      const size_t xb = 256 + (size_t)2 * o.tp_size * MEGA_TP_ROWS * H * sizeof(float);
+      const size_t xb = MEGA_TP_HEADER + (size_t)2 * o.tp_size * MEGA_TP_ROWS * H * sizeof(float);
       CU(cudaMalloc(&e->tp_xbuf, xb));
       CU(cudaMemsetAsync(e->tp_xbuf, 0, xb, e->stream));
       CU(cudaMalloc(&e->x2, R * H * sizeof(bf16)));

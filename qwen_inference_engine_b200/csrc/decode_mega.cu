@@ -1404,8 +1404,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
     }
     stamp();
   }
-  if (tp && blockIdx.x == 0 && threadIdx.x == 0) *a.tp_epoch = xbase + xch;  // every CTA read it before its first barrier
-  if (!with_head) return;
+  if (!with_head) {
+    if (tp && blockIdx.x == 0 && threadIdx.x == 0) *a.tp_epoch = xbase + xch;  // every CTA read it before its first barrier
+    return;
+  }
   // ---- arg-max over the CTAs' candidates + step bookkeeping (advance_kernel)
   if (a.greedy && warp == 0) {
     for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
@@ -1430,14 +1432,49 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
         }
       }
       if (lane == 0) {
-        a.sampled[b] = bi;
-        if (a.advance) {
-          a.pos[b] += 1;
-          a.ids[b] = bi;
-          if (a.rowstep) a.rowstep[b] += 1;
+        if (tp) {
+          // this rank's best of its vocabulary range (the low byte of the index, the tie-break key, is the same
+          // in the shard and in the full row: shards start at multiples of 256) -> every rank's candidate table
+          const MegaCand mine{bv, bi >= 0 ? bi + a.tp_vocab0 : -1};
+          for (int r = 0; r < a.tp_size; ++r) a.tp_cand[r][a.tp_rank * MEGA_TP_ROWS + b] = mine;
+        } else {
+          a.sampled[b] = bi;
+          if (a.advance) {
+            a.pos[b] += 1;
+            a.ids[b] = bi;
+            if (a.rowstep) a.rowstep[b] += 1;
+          }
         }
       }
     }
+  }
+  if (tp) {
+    if (a.greedy) {
+      ++xch;
+      tp_exchange_sync(a, epoch, xbase + xch);
+      if (threadIdx.x == 0) {
+        for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
+          float bv = -CUDART_INF_F;
+          int bi = -1;
+          for (int r = 0; r < a.tp_size; ++r) {  // rank order; cand_better is a total order, so every rank picks the same token
+            const MegaCand* cp = a.tp_cand[a.tp_rank] + r * MEGA_TP_ROWS + b;
+            const float ov = __ldcg(&cp->val);
+            const int oi = __ldcg(&cp->idx);
+            if (cand_better(ov, oi, bv, bi)) {
+              bv = ov;
+              bi = oi;
+            }
+          }
+          a.sampled[b] = bi;
+          if (a.advance) {
+            a.pos[b] += 1;
+            a.ids[b] = bi;
+            if (a.rowstep) a.rowstep[b] += 1;
+          }
+        }
+      }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.tp_epoch = xbase + xch;  // every CTA read it before its first barrier
   }
   stamp();
   if (a.prof && blockIdx.x == 0 && threadIdx.x == 0)

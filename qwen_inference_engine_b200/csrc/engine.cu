@@ -535,29 +535,26 @@ cudaError_t forward_decode_mega(qie_engine* e, int n, int max_kv_len, float temp
     a.V = pl.vocab;
     a.wmaps = e->mega_wmaps_tp_d[tset];
     a.lm_head = e->lm_head + (size_t)pl.vocab0 * c.hidden;
-    a.greedy = 0;  // local logits only; the arg-max over ranks follows the kernel
+    a.greedy = 1;  // decode_uses_mega admits tensor parallel only with top-k 1
     a.fast = 0;
     a.tp_size = e->tp.size;
     a.tp_rank = e->tp.rank;
+    a.tp_vocab0 = pl.vocab0;
     for (int r = 0; r < e->tp.size; ++r) {
-      a.tp_flag[r] = reinterpret_cast<unsigned*>(e->tp_peer_xbuf[r]);
-      a.tp_part[r] = reinterpret_cast<float*>(reinterpret_cast<char*>(e->tp_peer_xbuf[r]) + 256);
+      char* base = reinterpret_cast<char*>(e->tp_peer_xbuf[r]);
+      a.tp_flag[r] = reinterpret_cast<unsigned*>(base);
+      a.tp_cand[r] = reinterpret_cast<MegaCand*>(base + 256);
+      a.tp_part[r] = reinterpret_cast<float*>(base + MEGA_TP_HEADER);
     }
-    a.tp_epoch = reinterpret_cast<unsigned*>(e->tp_xbuf) + 32;  // word 32 of the flag block: local generation base
+    a.tp_epoch = reinterpret_cast<unsigned*>(e->tp_xbuf) + 32;  // byte 128 of the header: local generation base
     a.x2 = e->x2;
   }
   cudaError_t r = launch_decode_mega(a, e->num_sms, e->stream);
   if (tp) {
-    if (r != cudaSuccess) return r;  // the ranks must stay on the same path: no silent fallback here
-    ++e->launches;
-    const TpPlan& pl = e->plan;
-    const int R = e->opts.max_batch_tokens;
-    QIE_TRY(KK_SAMPLE, launch_sample_topk(e->logits, e->sampled_d, n, pl.vocab, 1.0f, 1, e->seed, 0, nullptr, e->stream));
-    QIE_TRY(KK_SAMPLE, launch_tp_cand_make(e->logits, e->sampled_d, e->tp_cand, n, pl.vocab, pl.vocab0, e->stream));
-    r = tp_allgather(&e->tp, e->tp_cand, e->tp_cand + R, (size_t)n * sizeof(TpCand), e->stream);
+    // the ranks must stay on the same path: no silent fallback here.  The step is ONE launch per rank: the
+    // arg-max over the ranks' vocabulary ranges and the step bookkeeping happen inside the kernel.
     if (r != cudaSuccess) return r;
-    QIE_TRY(KK_SAMPLE, launch_tp_cand_merge(e->tp_cand + R, e->tp.size, n, e->sampled_d, e->stream));
-    QIE_TRY(KK_ADVANCE, launch_advance(e->pos_d, e->ids_d, e->sampled_d, n, e->rowstep_d, e->stream));
+    ++e->launches;
     return cudaSuccess;
   }
   if (r != cudaSuccess) {

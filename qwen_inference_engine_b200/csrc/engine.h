@@ -99,7 +99,7 @@ struct qie_engine {
   qie::TpPlan plan{};
   float* tp_buf = nullptr;            // [max_batch_tokens, hidden] fp32 partial sums of o_proj / down_proj
   qie::TpCand* tp_cand = nullptr;     // [1 + tp_size][max rows] local + gathered arg-max candidates
-  // exchange buffer of the persistent kernel: [256 B flags + epoch][2][tp][MEGA_TP_ROWS][hidden] fp32, exported
+  // exchange buffer of the persistent kernel: [MEGA_TP_HEADER: flags, generation, candidates][2][tp][MEGA_TP_ROWS][hidden] fp32, exported
   // to the peers through CUDA IPC (handles travel over the NCCL communicator in qie_engine_tp_connect)
   void* tp_xbuf = nullptr;
   void* tp_peer_xbuf[qie::MEGA_MAX_TP] = {nullptr, nullptr, nullptr, nullptr};  // [rank] mapped base (own entry = tp_xbuf)

@@ -173,6 +173,7 @@ cudaError_t launch_advance(int* pos, int* ids, const int* sampled, int n, int* s
 // greedy arg-max, bookkeeping) for up to 64 sequences in reference-order arithmetic.
 constexpr int MEGA_MAX_TP = 4;
 constexpr int MEGA_TP_ROWS = 16;
+constexpr int MEGA_TP_HEADER = 1024;  // bytes in front of the partial sums: flag words, generation word (byte 128), candidate table (byte 256)
 struct MegaLayer {
   const bf16 *in_ln, *q, *k, *v, *o, *q_norm, *k_norm, *post_ln, *gate, *up, *down;
 };
@@ -214,6 +215,8 @@ struct MegaArgs {
   float* tp_part[MEGA_MAX_TP];       // rank r's exchange buffer [2][tp_size][MEGA_TP_ROWS][H] (peer-mapped for r != tp_rank)
   unsigned* tp_flag[MEGA_MAX_TP];    // rank r's flag words: flag[s] = number of exchanges rank s has completed
   unsigned* tp_epoch;                // local: exchanges completed before this launch (kept on the device: graph replay)
+  MegaCand* tp_cand[MEGA_MAX_TP];    // rank r's candidate table [tp_size][MEGA_TP_ROWS]: best (logit, token) of every rank's vocabulary range
+  int tp_vocab0;                     // first vocabulary row of this rank
   bf16* x2;                          // ping-pong partner of x for the residual stream
   int KC;  // k elements per weight tile = box depth of wmaps (decode_mega_kc at engine setup)
   // geometry, filled by the launcher (ph_*: per GEMM phase kind qkv/o/gate+up/down/lm_head)

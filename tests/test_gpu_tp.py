@@ -41,6 +41,8 @@ def test_tp2_matches_single_gpu(arch, batch):
     line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
     res = json.loads(line)
     assert res["tp"] == 2 and res["ranks_agree"]
+    if os.environ.get("QIE_TP_MEGA", "1") != "0":
+        assert res["persistent_kernel"]  # decode steps ran as one launch per rank with the exchange over peer memory
     print(res)
     if arch == "small":
         assert res["check_prefill_logits_rel_l2"] < 1e-2  # BASELINE.json: 1e-2 relative error in bf16

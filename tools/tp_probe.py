@@ -84,7 +84,9 @@ def main():
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         same = bool(ok.item())
     res = {"arch": a.arch, "tp": world, "batch": a.batch, "steps": a.steps, "ms_per_step": ms / a.steps,
-           "tokens_per_s": a.batch * a.steps / (ms / 1e3), "ranks_agree": same}
+           "tokens_per_s": a.batch * a.steps / (ms / 1e3), "ranks_agree": same,
+           "persistent_kernel": bool(eng.uses_mega(a.batch, a.prompt + a.warmup + a.steps + 2)),
+           "launches_last_call": int(eng.launch_count())}
     wb = q.weight_bytes(cfg)
     res["weight_bytes_per_gpu"] = wb // world
     res["hbm_GBs_per_gpu"] = wb / world / (ms / a.steps / 1e3) / 1e9
