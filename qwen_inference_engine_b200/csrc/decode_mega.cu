@@ -166,21 +166,65 @@ __device__ __forceinline__ void tp_exchange_sync(const MegaArgs& a, unsigned& ep
 // ascending order on every rank (identical bits everywhere), written into the activation region (layout of
 // load_rows) by every CTA and into the other residual buffer by CTA 0.
 __device__ __forceinline__ void load_rows_tp(const MegaArgs& a, uint32_t act, int B, int H, const bf16* x_cur, bf16* x_next, int xpar) {
-  const int AS = (H + 8) * 2, hp = H >> 1;
-  for (int i = threadIdx.x; i < B * hp; i += NTC) {
-    const int b = i / hp, n = (i - b * hp) * 2;
-    const uint32_t old = __ldcg(reinterpret_cast<const uint32_t*>(x_cur + (size_t)b * H + n));
-    float2 sum = __ldcg(reinterpret_cast<const float2*>(a.tp_part[a.tp_rank] + (((size_t)xpar * a.tp_size) * MEGA_TP_ROWS + b) * H + n));
+  const int AS = (H + 8) * 2, hv = H >> 3;  // 8 elements per thread and step: one 16-byte x load, 2 x 16 bytes per rank
+  const float* part = a.tp_part[a.tp_rank] + (size_t)xpar * a.tp_size * MEGA_TP_ROWS * H;
+  const size_t rstride = (size_t)MEGA_TP_ROWS * H;
+#pragma unroll 2
+  for (int i = threadIdx.x; i < B * hv; i += NTC) {
+    const int b = i / hv, n = (i - b * hv) * 8;
+    const size_t e = (size_t)b * H + n;
+    const uint4 old = __ldcg(reinterpret_cast<const uint4*>(x_cur + e));
+    float4 s0 = __ldcg(reinterpret_cast<const float4*>(part + e));
+    float4 s1 = __ldcg(reinterpret_cast<const float4*>(part + e + 4));
     for (int r = 1; r < a.tp_size; ++r) {
-      const float2 pr = __ldcg(reinterpret_cast<const float2*>(a.tp_part[a.tp_rank] + (((size_t)xpar * a.tp_size + r) * MEGA_TP_ROWS + b) * H + n));
-      sum.x = __fadd_rn(sum.x, pr.x);
-      sum.y = __fadd_rn(sum.y, pr.y);
+      const float4 p0 = __ldcg(reinterpret_cast<const float4*>(part + r * rstride + e));
+      const float4 p1 = __ldcg(reinterpret_cast<const float4*>(part + r * rstride + e + 4));
+      s0.x = __fadd_rn(s0.x, p0.x); s0.y = __fadd_rn(s0.y, p0.y); s0.z = __fadd_rn(s0.z, p0.z); s0.w = __fadd_rn(s0.w, p0.w);
+      s1.x = __fadd_rn(s1.x, p1.x); s1.y = __fadd_rn(s1.y, p1.y); s1.z = __fadd_rn(s1.z, p1.z); s1.w = __fadd_rn(s1.w, p1.w);
     }
-    const uint32_t nw = pack2(f2bf(__fadd_rn(lo2f(old), bf2f(f2bf(sum.x)))), f2bf(__fadd_rn(hi2f(old), bf2f(f2bf(sum.y)))));
-    asm volatile("st.shared.b32 [%0], %1;" ::"r"(act + b * AS + n * 2), "r"(nw) : "memory");
-    if (blockIdx.x == 0) *reinterpret_cast<uint32_t*>(x_next + (size_t)b * H + n) = nw;
+    auto add2 = [](uint32_t o, float y0, float y1) {
+      return pack2(f2bf(__fadd_rn(lo2f(o), bf2f(f2bf(y0)))), f2bf(__fadd_rn(hi2f(o), bf2f(f2bf(y1)))));
+    };
+    uint4 nw;
+    nw.x = add2(old.x, s0.x, s0.y);
+    nw.y = add2(old.y, s0.z, s0.w);
+    nw.z = add2(old.z, s1.x, s1.y);
+    nw.w = add2(old.w, s1.z, s1.w);
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(act + b * AS + n * 2), "r"(nw.x), "r"(nw.y), "r"(nw.z), "r"(nw.w) : "memory");
+    if (blockIdx.x == 0) *reinterpret_cast<uint4*>(x_next + e) = nw;
   }
   bar_consumers();
+}
+
+// The same sum for more than a few rows: every CTA reading every rank's fp32 partial sums of the whole batch
+// costs (2 + 4 tp) bytes per element and CTA of L2 traffic, so the rows are combined ONCE -- item i by CTA
+// i mod grid -- into the other residual buffer, followed by a grid barrier and a plain bf16 row load.
+__device__ __forceinline__ void combine_rows_tp(const MegaArgs& a, int B, int H, const bf16* x_cur, bf16* x_next, int xpar) {
+  const int hv = H >> 3;
+  const float* part = a.tp_part[a.tp_rank] + (size_t)xpar * a.tp_size * MEGA_TP_ROWS * H;
+  const size_t rstride = (size_t)MEGA_TP_ROWS * H;
+  for (int i = blockIdx.x + threadIdx.x * gridDim.x; i < B * hv; i += NTC * gridDim.x) {
+    const int b = i / hv, n = (i - b * hv) * 8;
+    const size_t e = (size_t)b * H + n;
+    const uint4 old = __ldcg(reinterpret_cast<const uint4*>(x_cur + e));
+    float4 s0 = __ldcg(reinterpret_cast<const float4*>(part + e));
+    float4 s1 = __ldcg(reinterpret_cast<const float4*>(part + e + 4));
+    for (int r = 1; r < a.tp_size; ++r) {
+      const float4 p0 = __ldcg(reinterpret_cast<const float4*>(part + r * rstride + e));
+      const float4 p1 = __ldcg(reinterpret_cast<const float4*>(part + r * rstride + e + 4));
+      s0.x = __fadd_rn(s0.x, p0.x); s0.y = __fadd_rn(s0.y, p0.y); s0.z = __fadd_rn(s0.z, p0.z); s0.w = __fadd_rn(s0.w, p0.w);
+      s1.x = __fadd_rn(s1.x, p1.x); s1.y = __fadd_rn(s1.y, p1.y); s1.z = __fadd_rn(s1.z, p1.z); s1.w = __fadd_rn(s1.w, p1.w);
+    }
+    auto add2 = [](uint32_t o, float y0, float y1) {
+      return pack2(f2bf(__fadd_rn(lo2f(o), bf2f(f2bf(y0)))), f2bf(__fadd_rn(hi2f(o), bf2f(f2bf(y1)))));
+    };
+    uint4 nw;
+    nw.x = add2(old.x, s0.x, s0.y);
+    nw.y = add2(old.y, s0.z, s0.w);
+    nw.z = add2(old.z, s1.x, s1.y);
+    nw.w = add2(old.w, s1.z, s1.w);
+    *reinterpret_cast<uint4*>(x_next + e) = nw;
+  }
 }
 
 // ---------------------------------------------------------------- GEMM phase description
@@ -1335,7 +1379,14 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
         stamp();
       } else {
         if (tp && !from_embed) {
-          load_rows_tp(a, act, a.B, H, x_cur, x_next, (int)((xch - 1) & 1));
+          if (a.B > 4) {
+            combine_rows_tp(a, a.B, H, x_cur, x_next, (int)((xch - 1) & 1));
+            grid_sync(a.bar, epoch);
+            const bf16* xs = x_next;
+            load_rows(act, a.B, H, [&](int b) { return xs + (size_t)b * H; });
+          } else {
+            load_rows_tp(a, act, a.B, H, x_cur, x_next, (int)((xch - 1) & 1));
+          }
           const bf16* t = x_cur;
           x_cur = x_next;
           x_next = const_cast<bf16*>(t);
@@ -1512,19 +1563,25 @@ bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int ma
   int act = std::max(res_h, stream_down ? strm : res_i);
   const int hs = (B * n_q <= grid) ? 1 : n_q / n_kv;
   const int tmax = (max_kv_len + 3) & ~3;
-  const int kstg = hs == 1 ? std::min(256, (max_kv_len + 15) & ~15) : 0;  // K rows staged before the barrier
-  const int attn = hs * hd * 4 + 2 * hd * 2 + hs * tmax * 4 + (max_kv_len + 32) * 4 /* pages: <= one per position */ +
-                   2 * VT * hd * 2 + kstg * (hd * 2 + 16) + 2 * hd * 2 + hd * 4 + 64;
-  const int attn_off = kstg > 0 ? ((res_h + 127) & ~127) : 0;  // staged attention areas live behind the resident rows
-  act = std::max(act, attn + attn_off);
+  const int act_gemm = act;
   const int off_act = (OFF_WNORM + 2 * H * 2 + 127) & ~127;
-  const int off_red = off_act + ((act + 127) & ~127);     // fast numerics: split-K partial sums [FAST_U][NW][32][8] fp32
   const int red = fast ? FAST_U * NW * 32 * 8 * 4 : 0;
-  const int off_ring = (off_red + red + 1023) & ~1023;  // swizzled TMA tiles: 1024-byte aligned slots
   const int slot = 16 * KC * 2;                          // gate + up boxes of 8 rows x KC
-  const int budget = 227 * 1024 - off_ring;
-  int S = budget / slot;
-  if (S > MAX_SLOTS) S = MAX_SLOTS;
+  int kstg = hs == 1 ? std::min(256, (max_kv_len + 15) & ~15) : 0;  // K rows staged before the barrier
+  int attn_off = 0, off_red = 0, off_ring = 0, S = 0;
+  for (;;) {
+    const int attn = hs * hd * 4 + 2 * hd * 2 + hs * tmax * 4 + (max_kv_len + 32) * 4 /* pages: <= one per position */ +
+                     2 * VT * hd * 2 + kstg * (hd * 2 + 16) + 2 * hd * 2 + hd * 4 + 64;
+    attn_off = kstg > 0 ? ((res_h + 127) & ~127) : 0;  // staged attention areas live behind the resident rows
+    act = std::max(act_gemm, attn + attn_off);
+    off_red = off_act + ((act + 127) & ~127);     // fast numerics: split-K partial sums [FAST_U][NW][32][8] fp32
+    off_ring = (off_red + red + 1023) & ~1023;    // swizzled TMA tiles: 1024-byte aligned slots
+    const int budget = 227 * 1024 - off_ring;
+    S = budget / slot;
+    if (S > MAX_SLOTS) S = MAX_SLOTS;
+    if (S >= 3 || kstg == 0) break;
+    kstg = 0;  // the staged layout (K rows + attention areas behind the resident rows) does not fit: per-head tasks without stage 0
+  }
   if (S < 3) return false;
   g->KC = KC;
   g->slot_bytes = slot;
