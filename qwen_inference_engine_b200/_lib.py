@@ -9,7 +9,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqie_b200.so")
+LIB_PATH = os.environ.get("QIE_B200_LIB") or os.path.join(_HERE, "libqie_b200.so")  # override: A/B builds of the library
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "qie_b200.h")
 
 

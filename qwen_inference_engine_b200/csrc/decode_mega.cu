@@ -31,6 +31,10 @@
 #include "kernels.h"
 #include "ref_math.cuh"
 
+#ifndef QIE_PV_PIPE
+#define QIE_PV_PIPE 1  // PV loop: request the next group's operands before the current FFMA chain (A/B knob)
+#endif
+
 namespace qie {
 namespace {
 
@@ -1197,6 +1201,7 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
         if (i < hs) {
           const float* s = score + i * tmax + t0;
           int k = 0;
+#if QIE_PV_PIPE
           if (tn >= 4) {
             // groups of 4 positions, the next group's probabilities and V words requested before the
             // current group's FFMA chain runs (same ascending order: the chain is the spec, its
@@ -1232,6 +1237,20 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
                 for (int p = 0; p < NP; ++p) vv[j][p] = vn[j][p];
             }
           }
+#else
+          for (; k + 4 <= tn; k += 4) {
+            const float4 pr = *reinterpret_cast<const float4*>(s + k);
+            const float prj[4] = {pr.x, pr.y, pr.z, pr.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int p = 0; p < NP; ++p) {
+                const uint32_t vv = *reinterpret_cast<const uint32_t*>(vb + (k + j) * (HD * 2) + (64 * p + 2 * lane) * 2);
+                o[q2][p][0] = __fmaf_rn(prj[j], lo2f(vv), o[q2][p][0]);
+                o[q2][p][1] = __fmaf_rn(prj[j], hi2f(vv), o[q2][p][1]);
+              }
+          }
+#endif
           for (; k < tn; ++k) {
             const float pk = s[k];
 #pragma unroll

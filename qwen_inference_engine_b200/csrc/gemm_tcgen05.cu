@@ -27,6 +27,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -47,6 +48,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_local(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // bounded wait: a protocol bug must trap (loud failure), never hang the GPU
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
@@ -453,6 +457,217 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------ persistent variant (prefill)
+// Same tiles, same math, for launches without split-K and >= 129 tokens (BN = 256): ONE CTA per SM walks the
+// output tiles (weight tile fastest, so neighbouring CTAs share a token tile in L2), the accumulator is double
+// buffered in TMEM (2 x 256 columns), and the epilogue of tile j (TMEM -> bf16 staging tile in shared memory ->
+// 16-byte global accesses) runs on warps 2-5 while warps 0/1 already stream and multiply tile j+1.  ncu on the
+// one-tile-per-CTA kernel showed the tensor pipe 32-47 % active at K = 1536: per tile ~2.5 us of prologue and
+// ~8 us of epilogue sat next to a ~7-9 us mainloop (profiles/r01c_ncu_full_prefill_kernels.csv).
+static constexpr int PBN = 256;
+static constexpr int P_STAGES = 3;
+static constexpr int P_STAGE_BYTES = BM * BK * 2 + PBN * BK * 2;  // 48 KiB
+static constexpr int P_STAGING = PBN * BM * 2;                      // bf16 [256 tokens][128 rows] = 64 KiB
+
+__global__ void __launch_bounds__(192) gemm_tcgen05_persist_kernel(const __grid_constant__ CUtensorMap map_w0,
+                                                                   const __grid_constant__ CUtensorMap map_w1,
+                                                                   const __grid_constant__ CUtensorMap map_w2,
+                                                                   const __grid_constant__ CUtensorMap map_x, TcArgs g,
+                                                                   int token_tiles) {
+  pdl_trigger();
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int A_BYTES = BM * BK * 2;
+  constexpr uint32_t TMEM_COLS = 512;  // two accumulators
+  const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stg = smem0 + P_STAGES * P_STAGE_BYTES;
+  const uint32_t bars = stg + P_STAGING;  // full[S], empty[S], tmem_full[2], tmem_empty[2], slot
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (P_STAGES + s); };
+  auto tfull_bar = [&](int b) { return bars + 8u * (2 * P_STAGES + b); };
+  auto tempty_bar = [&](int b) { return bars + 8u * (2 * P_STAGES + 2 + b); };
+  const uint32_t slot = bars + 8u * (2 * P_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = g.n_tiles * token_tiles;
+  const int nkb = g.kb_total;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w2) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    for (int s = 0; s < P_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tfull_bar(b), 1);
+      mbar_init(tempty_bar(b), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(slot));
+
+  // tile -> (weight tile, token tile, segment) ; dual: one tile = 64 gate rows + the same 64 up rows
+  auto tile_geom = [&](int t, int& tile, int& ttile, int& si, int& row0) {
+    tile = t % g.n_tiles;
+    ttile = t / g.n_tiles;
+    si = 0;
+    while (si + 1 < g.nseg && tile >= g.seg[si + 1].tile0) ++si;
+    row0 = g.dual ? tile * (BM / 2) : (tile - g.seg[si].tile0) * BM;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      pdl_wait();  // activations come from the previous kernel (these launches run for 30-300 us: no early weight prefetch)
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        int tile, ttile, si, row0;
+        tile_geom(t, tile, ttile, si, row0);
+        const CUtensorMap* map_w = g.dual ? &map_w0 : (si == 0 ? &map_w0 : (si == 1 ? &map_w1 : &map_w2));
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % P_STAGES;
+          const uint32_t ph = (it / P_STAGES) & 1;
+          mbar_wait(empty_bar(s), ph ^ 1);
+          mbar_expect_tx(full_bar(s), P_STAGE_BYTES);
+          const uint32_t sa = smem0 + s * P_STAGE_BYTES;
+          if (g.dual) {
+            tma_load_2d(sa, &map_w0, full_bar(s), kb * BK, row0);
+            tma_load_2d(sa + A_BYTES / 2, &map_w1, full_bar(s), kb * BK, row0);
+          } else {
+            tma_load_2d(sa, map_w, full_bar(s), kb * BK, row0);
+          }
+          tma_load_2d(sa + A_BYTES, &map_x, full_bar(s), kb * BK, ttile * PBN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, PBN);
+      uint32_t it = 0;
+      int j = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+        const int buf = j & 1;
+        mbar_wait(tempty_bar(buf), (((uint32_t)j >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)buf * PBN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % P_STAGES;
+          const uint32_t ph = (it / P_STAGES) & 1;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t sa = smem0 + s * P_STAGE_BYTES, sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) umma_bf16(acc, make_desc(sa + k * 32), make_desc(sb + k * 32), idesc, (kb | k) != 0);
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(buf));
+      }
+    }
+  } else {
+    // ---- epilogue warps 2-5
+    constexpr uint32_t PITCH = BM * 2;
+    const int qd = warp & 3;
+    const int lane_row = qd * 32 + lane;
+    const int tq = threadIdx.x - 64;
+    auto lds128 = [](uint32_t addr) {
+      uint4 v;
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+      return v;
+    };
+    pdl_wait();  // `out` may still be read (residual) by the previous kernel
+    int j = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+      int tile, ttile, si, row0;
+      tile_geom(t, tile, ttile, si, row0);
+      const int seg_rows = g.seg[si].rows;
+      const int col0 = g.dual ? 0 : g.seg[si].col0;
+      const int tok_base = ttile * PBN;
+      const int buf = j & 1;
+      mbar_wait(tfull_bar(buf), ((uint32_t)j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)buf * PBN + ((uint32_t)(qd * 32) << 16);
+#pragma unroll 4
+      for (int c0 = 0; c0 < PBN; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(acc + c0, r);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const unsigned short hb = __bfloat16_as_ushort(f2bf(__uint_as_float(r[q])));
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg + (uint32_t)(c0 + q) * PITCH + (uint32_t)lane_row * 2u), "h"(hb) : "memory");
+        }
+      }
+      tc_fence_before();
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      if (tq == 0) mbar_arrive_local(tempty_bar(buf));  // the MMA warp may overwrite this accumulator (tile j+2)
+      const int n_tok = min(PBN, g.M - tok_base);
+      if (!g.dual) {
+        const int totalc = n_tok * (BM / 8);
+        for (int c = tq; c < totalc; c += 8 * 128) {
+          uint4 y[8], x[8];
+          bf16* dst[8];
+          bool ok[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int cc = c + u * 128;
+            const int tok = cc >> 4, part = cc & 15;
+            const int w_row = row0 + part * 8;
+            ok[u] = cc < totalc && w_row < seg_rows;
+            dst[u] = g.out + (size_t)(tok_base + tok) * g.ld_out + col0 + w_row;
+            if (ok[u]) {
+              if (g.epi == EPI_RESIDUAL) x[u] = *reinterpret_cast<const uint4*>(dst[u]);
+              y[u] = lds128(stg + (uint32_t)tok * PITCH + (uint32_t)part * 16u);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            if (!ok[u]) continue;
+            if (g.epi == EPI_RESIDUAL) {
+              const uint32_t xs[4] = {x[u].x, x[u].y, x[u].z, x[u].w}, ys[4] = {y[u].x, y[u].y, y[u].z, y[u].w};
+              uint32_t o4[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                o4[e] = pack2(f2bf(__fadd_rn(lo2f(xs[e]), lo2f(ys[e]))), f2bf(__fadd_rn(hi2f(xs[e]), hi2f(ys[e]))));
+              *reinterpret_cast<uint4*>(dst[u]) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+            } else {
+              *reinterpret_cast<uint4*>(dst[u]) = y[u];
+            }
+          }
+        }
+      } else {
+        const int totalc = n_tok * (BM / 16);
+        for (int c = tq; c < totalc; c += 128) {
+          const int tok = c >> 3, part = c & 7;
+          const int w_row = row0 + part * 8;
+          if (w_row >= seg_rows) continue;
+          const uint4 gt = lds128(stg + (uint32_t)tok * PITCH + (uint32_t)part * 16u);
+          const uint4 up = lds128(stg + (uint32_t)tok * PITCH + (uint32_t)(BM / 2) * 2u + (uint32_t)part * 16u);
+          const uint32_t gs[4] = {gt.x, gt.y, gt.z, gt.w}, us[4] = {up.x, up.y, up.z, up.w};
+          uint32_t o4[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a0 = __fmul_rn(lo2f(us[e]), bf2f(f2bf(silu_ref_f(lo2f(gs[e])))));
+            const float a1 = __fmul_rn(hi2f(us[e]), bf2f(f2bf(silu_ref_f(hi2f(gs[e])))));
+            o4[e] = pack2(f2bf(a0), f2bf(a1));
+          }
+          *reinterpret_cast<uint4*>(g.out + (size_t)(tok_base + tok) * g.ld_out + w_row) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+        }
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");  // the staging tile is rewritten by the next tile
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -596,6 +811,32 @@ cudaError_t launch_gemm_tcgen05(const TcGemm& t, int num_sms, cudaStream_t st, i
     g.staged = splits == 1 && vec;
   }
   cudaError_t e;
+  static const bool persist_on = [] { const char* v = getenv("QIE_TC_PERSIST"); return !(v && v[0] == '0'); }();
+  if (persist_on && g.staged && BN == PBN && tiles * token_tiles > num_sms / 2) {
+    // prefill-sized launches: persistent tile loop, epilogue overlapped with the next tile's mainloop
+    constexpr size_t smem = (size_t)P_STAGES * P_STAGE_BYTES + P_STAGING + 1024 /*align*/ + 256 /*barriers*/;
+    static bool set = false;
+    if (!set) {
+      e = cudaFuncSetAttribute(gemm_tcgen05_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      set = true;
+    }
+    const CUtensorMap* w0 = reinterpret_cast<const CUtensorMap*>(t.w[0]);
+    const CUtensorMap* w1 = reinterpret_cast<const CUtensorMap*>(t.w[t.nseg > 1 ? 1 : 0]);
+    const CUtensorMap* w2 = reinterpret_cast<const CUtensorMap*>(t.w[t.nseg > 2 ? 2 : 0]);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(std::min(num_sms, tiles * token_tiles));
+    cfg.blockDim = dim3(192);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = g_use_pdl ? 1 : 0;
+    if (launches) *launches = 1;
+    return cudaLaunchKernelEx(&cfg, gemm_tcgen05_persist_kernel, *w0, *w1, *w2, *reinterpret_cast<const CUtensorMap*>(t.x), g, token_tiles);
+  }
   switch (BN) {
     case 16: e = launch_bn<16>(t, g, token_tiles, st); break;
     case 32: e = launch_bn<32>(t, g, token_tiles, st); break;

@@ -34,7 +34,7 @@ def p(t):
 @pytest.mark.parametrize("M,N,K", [(64, 896, 896), (64, 896, 128), (64, 896, 4864), (64, 4864, 896), (9, 896, 1152),
                                    (16, 1536, 256), (17, 128, 384), (32, 896, 9728), (33, 256, 640), (128, 896, 896),
                                    (130, 512, 264), (256, 1536, 1536), (300, 896, 896), (64, 896, 15104), (40, 64, 128),
-                                   (64, 3584, 3584)])
+                                   (64, 3584, 3584), (600, 1536, 8960), (1000, 512, 2568)])
 def test_tcgen05_gemm_vs_reference_kernel(layers, ref, M, N, K):
     """C[M,K] = A[M,N] @ B[K,N]^T : tcgen05 path vs the reference's wmma kernel."""
     rng = np.random.default_rng(M * 7919 + N * 13 + K)
@@ -129,6 +129,29 @@ def test_fast_prefill_engine_long_prompt():
     for l in range(e_ref.config.layers):
         for tag in ("attn", "x_out"):
             assert close(e_fast.read_capture(tag, l), e_ref.read_capture(tag, l)), (tag, l)
+    print("fast prefill token", tb, "reference-order token", ta)
+    e_ref.close()
+    e_fast.close()
+
+
+def test_fast_prefill_persistent_gemm_whole_prompt():
+    """3000-token prompt in ONE forward on a 2-layer model with the 0.5B layer shape: every projection is
+    large enough for the persistent tcgen05 GEMM (tile loop, double-buffered TMEM accumulator, overlapped
+    store / residual / SiLU*up epilogues); logits and layer outputs against the reference-order engine."""
+    import qwen_inference_engine_b200 as q
+    cfg = q.make_config(dict(q.ARCHS["qwen2.5-0.5b"], layers=2, vocab=8192), context=4096)
+    kw = dict(synthetic=cfg, seed=9, context=4096, max_batch_tokens=3072, max_seqs=2, kv_bytes=256 << 20)
+    e_ref = q.Engine(numerics="reference_order", **kw)
+    e_fast = q.Engine(numerics="fast", **kw)
+    ids = prompt_ids(3000, cfg.vocab, seed=17)
+    for eng in (e_ref, e_fast):
+        eng.capture(True)
+    ta, tb = e_ref.prefill(e_ref.new_sequence(), ids), e_fast.prefill(e_fast.new_sequence(), ids)
+    assert close(e_fast.read_capture("logits", -1), e_ref.read_capture("logits", -1))
+    for l in range(cfg.layers):
+        for tag in ("attn", "x_attn", "mlp_h", "x_out"):
+            a, b = e_fast.read_capture(tag, l), e_ref.read_capture(tag, l)
+            assert close(a, b), (tag, l, rel_l2(a, b), rel_err(a, b))
     print("fast prefill token", tb, "reference-order token", ta)
     e_ref.close()
     e_fast.close()
