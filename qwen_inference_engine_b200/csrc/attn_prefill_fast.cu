@@ -89,18 +89,29 @@ __global__ void __launch_bounds__(128, 3) attn_prefill_fast_kernel(FastAttnArgs 
   cp_async_commit();
   __syncthreads();  // s_pages visible
 
+  // Every thread copies the same 16-byte chunk column `lch` of rows lr0, lr0 + RPP, ... of every tile, so the
+  // address arithmetic per request is one page lookup and one multiply-add (the generic i / CH, i % CH, p / psz,
+  // p % psz form cost as many instructions per tile as the softmax).
+  constexpr int RPP = 128 / CH;  // rows covered by one pass of the CTA
+  const int lch = threadIdx.x % CH, lr0 = threadIdx.x / CH;
+  const int psz_shift = (psz & (psz - 1)) == 0 ? __ffs(psz) - 1 : -1;
+  const size_t v_off = a.kv.kv_stride();  // V chunk of a (page, layer, head) sits kv_stride elements behind its K chunk
+  const bf16* kv_base = a.kv.chunk(0, a.layer, 0, kvh) + lch * 8;
+  const size_t page_stride = a.kv.page_stride();
   auto load_tile = [&](int tile, int buf) {
     const uint32_t kb = sring + buf * SM::STAGE_BYTES, vb = kb + SM::TILE_BYTES;
     const int p0 = tile * PF_KT;
-    for (int i = threadIdx.x; i < PF_KT * CH; i += 128) {
-      const int r = i / CH, ch = i % CH;
-      int p = p0 + r;
-      if (p >= kv_len) p = kv_len - 1;  // clamp: masked below
-      const int pi = p / psz;
+#pragma unroll
+    for (int k = 0; k < PF_KT / RPP; ++k) {
+      const int r = lr0 + k * RPP;
+      const int p = min(p0 + r, kv_len - 1);  // clamp: masked below
+      const int pi = psz_shift >= 0 ? (p >> psz_shift) : p / psz;
+      const int po = p - pi * psz;
       const int page = pi < PF_MAX_PAGES ? s_pages[pi] : bt[pi];
-      const size_t off = (size_t)(p % psz) * HD + ch * 8;
-      cp_async16(kb + pf_swz<HD>(r, ch), a.kv.chunk(page, a.layer, 0, kvh) + off);
-      cp_async16(vb + pf_swz<HD>(r, ch), a.kv.chunk(page, a.layer, 1, kvh) + off);
+      const bf16* src = kv_base + (size_t)page * page_stride + (size_t)po * HD;
+      const uint32_t so = pf_swz<HD>(r, lch);
+      cp_async16(kb + so, src);
+      cp_async16(vb + so, src + v_off);
     }
   };
   load_tile(0, 0);
@@ -153,54 +164,61 @@ __global__ void __launch_bounds__(128, 3) attn_prefill_fast_kernel(FastAttnArgs 
           mma_bf16_16816(sc[2 * np + 1], qf[kc], k2, k3);
         }
       }
-      // ---- scale (+ causal mask on tiles that cross the diagonal), online softmax
+      // ---- causal mask on tiles that cross the diagonal, online softmax on the raw scores: the
+      // 1/sqrt(hd) * log2(e) factor rides in the FFMA in front of exp2 (p = 2^(s*c - m*c))
       const bool need_mask = p0 + PF_KT - 1 > pos_first + warp * 16;
       float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
       for (int j = 0; j < SN; ++j)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          float v = sc[j][e] * sl2;
+          float v = sc[j][e];
           if (need_mask) {
             const int p = p0 + 8 * j + 2 * c + (e & 1);
             if (p > ((e >> 1) ? lim1 : lim0)) v = -INFINITY;
+            sc[j][e] = v;
           }
-          sc[j][e] = v;
           mx[e >> 1] = fmaxf(mx[e >> 1], v);
         }
-      float corr[2], msafe[2];
+      float corr[2], nms[2];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 1));
         mx[hh] = fmaxf(mx[hh], __shfl_xor_sync(0xffffffffu, mx[hh], 2));
         const float m_new = fmaxf(m_run[hh], mx[hh]);
         // every row sees position 0 in tile 0, so m_new is finite from the first tile on
-        corr[hh] = exp2f(m_run[hh] - m_new);
+        corr[hh] = exp2f((m_run[hh] - m_new) * sl2);  // m_run = -inf -> 0
         m_run[hh] = m_new;
-        msafe[hh] = m_new;
+        nms[hh] = -m_new * sl2;
       }
       float rs[2] = {0.f, 0.f};
       uint32_t pa[SN / 2][4], pb[SN / 2][4];  // P = hi + lo in bf16 (16 mantissa bits)
 #pragma unroll
       for (int j = 0; j < SN; ++j) {
-        const float p0v = exp2f(sc[j][0] - msafe[0]), p1v = exp2f(sc[j][1] - msafe[0]);
-        const float p2v = exp2f(sc[j][2] - msafe[1]), p3v = exp2f(sc[j][3] - msafe[1]);
+        const float p0v = exp2f(fmaf(sc[j][0], sl2, nms[0])), p1v = exp2f(fmaf(sc[j][1], sl2, nms[0]));
+        const float p2v = exp2f(fmaf(sc[j][2], sl2, nms[1])), p3v = exp2f(fmaf(sc[j][3], sl2, nms[1]));
         rs[0] += p0v + p1v;
         rs[1] += p2v + p3v;
         const bf16 h0 = f2bf(p0v), h1 = f2bf(p1v), h2 = f2bf(p2v), h3 = f2bf(p3v);
         pa[j >> 1][(j & 1) * 2] = pack2(h0, h1);      // a0 / a2: row g
         pa[j >> 1][(j & 1) * 2 + 1] = pack2(h2, h3);  // a1 / a3: row g+8
-        pb[j >> 1][(j & 1) * 2] = pack2(f2bf(p0v - bf2f(h0)), f2bf(p1v - bf2f(h1)));
-        pb[j >> 1][(j & 1) * 2 + 1] = pack2(f2bf(p2v - bf2f(h2)), f2bf(p3v - bf2f(h3)));
+        if (two_term) {
+          pb[j >> 1][(j & 1) * 2] = pack2(f2bf(p0v - bf2f(h0)), f2bf(p1v - bf2f(h1)));
+          pb[j >> 1][(j & 1) * 2 + 1] = pack2(f2bf(p2v - bf2f(h2)), f2bf(p3v - bf2f(h3)));
+        }
       }
       l_run[0] = l_run[0] * corr[0] + rs[0];
       l_run[1] = l_run[1] * corr[1] + rs[1];
+      // the accumulator is rescaled only when some row of the warp saw a new maximum (rare once the
+      // context is long)
+      if (__any_sync(0xffffffffu, corr[0] != 1.f || corr[1] != 1.f)) {
 #pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        o[j][0] *= corr[0];
-        o[j][1] *= corr[0];
-        o[j][2] *= corr[1];
-        o[j][3] *= corr[1];
+        for (int j = 0; j < NT; ++j) {
+          o[j][0] *= corr[0];
+          o[j][1] *= corr[0];
+          o[j][2] *= corr[1];
+          o[j][3] *= corr[1];
+        }
       }
       // ---- O += P V
 #pragma unroll
