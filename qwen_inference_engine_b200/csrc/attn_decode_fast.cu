@@ -90,19 +90,29 @@ __global__ void __launch_bounds__(128) attn_decode_fast_kernel(FastAttnArgs a) {
     }
   }
 
+  // every thread copies the same 16-byte chunk column of rows lr0, lr0 + RPP, ... of each tile: one page lookup
+  // and one multiply-add per request instead of the generic i / CH, i % CH, p / psz, p % psz arithmetic
+  constexpr int RPP = 128 / CH;
+  const int lch = threadIdx.x % CH, lr0 = threadIdx.x / CH;
+  const int psz_shift = (psz & (psz - 1)) == 0 ? __ffs(psz) - 1 : -1;
+  const size_t v_off = a.kv.kv_stride();
+  const size_t page_stride = a.kv.page_stride();
+  const bf16* kv_base = a.kv.chunk(0, a.layer, 0, kvh) + lch * 8;
   auto load_tile = [&](int tile, int buf) {
     const uint32_t kb = sbase + buf * SM::STAGE_BYTES, vb = kb + SM::TILE_BYTES;
     const int p0 = tile * TILE;
-    // TILE rows x CH chunks for K and for V
-    for (int i = threadIdx.x; i < TILE * CH; i += 128) {
-      const int r = i / CH, ch = i % CH;
-      int p = p0 + r;
-      if (p >= kv_len) p = kv_len - 1;  // clamp: masked below
-      const int pi = p / psz - page0;
-      const int page = pi < SM::MAX_PAGES ? s_pages[pi] : bt[p / psz];
-      const size_t off = (size_t)(p % psz) * HD + ch * 8;
-      cp_async16(kb + swz<HD>(r, ch), a.kv.chunk(page, a.layer, 0, kvh) + off);
-      cp_async16(vb + swz<HD>(r, ch), a.kv.chunk(page, a.layer, 1, kvh) + off);
+#pragma unroll
+    for (int k = 0; k < TILE / RPP; ++k) {
+      const int r = lr0 + k * RPP;
+      const int p = min(p0 + r, kv_len - 1);  // clamp: masked below
+      const int pg = psz_shift >= 0 ? (p >> psz_shift) : p / psz;
+      const int po = p - pg * psz;
+      const int pi = pg - page0;
+      const int page = pi < SM::MAX_PAGES ? s_pages[pi] : bt[pg];
+      const bf16* src = kv_base + (size_t)page * page_stride + (size_t)po * HD;
+      const uint32_t so = swz<HD>(r, lch);
+      cp_async16(kb + so, src);
+      cp_async16(vb + so, src + v_off);
     }
   };
 

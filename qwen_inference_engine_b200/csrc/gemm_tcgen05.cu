@@ -419,30 +419,66 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
       const int rbeg = split * rows_per;
       const int rcnt = max(0, min(rows_per, tile_rows - rbeg));
       const int n_tok = min(BN, g.M - tok_base);
-      for (int o = t; o < rcnt * n_tok; o += 128) {
-        const int tok = o / rcnt, rr = rbeg + o % rcnt;
-        float acc = 0.f, acc2 = 0.f;
-        const uint32_t a1 = red + (uint32_t)(tok * BM + rr) * 4u;
-        const uint32_t a2 = a1 + (uint32_t)(BM / 2) * 4u;  // dual: the up half of the tile
-        if (S > 1) {
-          for (int sp = 0; sp < S; ++sp) {
-            acc += ld_dsmem_f32(a1, sp);
-            if (g.dual) acc2 += ld_dsmem_f32(a2, sp);
+      // Two outputs per thread and step, every load of the step requested before the first use: the S
+      // distributed-shared-memory reads of an output (and the residual's old value) are independent, but
+      // interleaved with their additions they went out one DSMEM round trip at a time.
+      constexpr int MAXS = 8;  // portable cluster size
+      uint32_t rb[MAXS];
+#pragma unroll
+      for (int sp = 0; sp < MAXS; ++sp) {
+        rb[sp] = red;
+        if (S > 1 && sp < S) asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb[sp]) : "r"(red), "r"(sp));
+      }
+      const int total = rcnt * n_tok;
+      for (int o0 = t; o0 < total; o0 += 2 * 128) {
+        float v[2][MAXS], v2[2][MAXS];
+        bf16* dst[2];
+        bf16 old[2];
+        bool ok[2], in_rows[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int o = o0 + u * 128;
+          ok[u] = o < total;
+          const int oo = ok[u] ? o : 0;
+          const int tok = oo / rcnt, rr = rbeg + oo % rcnt;
+          const uint32_t off1 = (uint32_t)(tok * BM + rr) * 4u;
+          const uint32_t off2 = off1 + (uint32_t)(BM / 2) * 4u;  // dual: the up half of the tile
+          const int w_row = row0 + rr;
+          in_rows[u] = ok[u] && w_row < seg_rows;
+          dst[u] = g.out + (size_t)(tok_base + tok) * g.ld_out + col0 + w_row;
+          if (in_rows[u] && g.epi == EPI_RESIDUAL) old[u] = *dst[u];
+#pragma unroll
+          for (int sp = 0; sp < MAXS; ++sp) {
+            v[u][sp] = 0.f;
+            v2[u][sp] = 0.f;
+            if (ok[u] && sp < S) {
+              if (S > 1) {
+                asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v[u][sp]) : "r"(rb[sp] + off1) : "memory");
+                if (g.dual) asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v2[u][sp]) : "r"(rb[sp] + off2) : "memory");
+              } else {
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[u][sp]) : "r"(red + off1) : "memory");
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v2[u][sp]) : "r"(red + off2) : "memory");
+              }
+            }
           }
-        } else {
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(acc) : "r"(a1) : "memory");
-          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(acc2) : "r"(a2) : "memory");
         }
-        const int w_row = row0 + rr;
-        if (w_row < seg_rows) {
-          bf16* dst = g.out + (size_t)(tok_base + tok) * g.ld_out + col0 + w_row;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          if (!in_rows[u]) continue;
+          float acc = 0.f, acc2 = 0.f;
+#pragma unroll
+          for (int sp = 0; sp < MAXS; ++sp)
+            if (sp < S) {  // rank order, as before
+              acc += v[u][sp];
+              acc2 += v2[u][sp];
+            }
           if (g.epi == EPI_STORE) {
-            *dst = f2bf(acc);
+            *dst[u] = f2bf(acc);
           } else if (g.epi == EPI_RESIDUAL) {
-            *dst = f2bf(__fadd_rn(bf2f(*dst), bf2f(f2bf(acc))));
+            *dst[u] = f2bf(__fadd_rn(bf2f(old[u]), bf2f(f2bf(acc))));
           } else {
             const float gt = bf2f(f2bf(acc)), up = bf2f(f2bf(acc2));
-            *dst = f2bf(__fmul_rn(up, bf2f(f2bf(silu_ref_f(gt)))));
+            *dst[u] = f2bf(__fmul_rn(up, bf2f(f2bf(silu_ref_f(gt)))));
           }
         }
       }
