@@ -172,6 +172,15 @@ int qie_synth_checkpoint_write(const qie_config* cfg, uint64_t seed, const char*
 int qie_checkpoint_inspect(const char* meta_path, int head_dim_hint, qie_config* cfg_out, size_t* total_bytes,
                            int* n_tensors);
 
+/* HOST only: parsed_tensors(), src/tensor_parser.cpp:31-129 -- HF safetensors shards (in the order given)
+ * -> weights.bin + meta_data.txt exactly as the reference lays them out: keys starting "model." or "lm_",
+ * byte-lexicographic key order inside a shard, running [begin,end) offsets, every "lm_" tensor named
+ * "logits".  The bytes are copied tensor by tensor from each shard's data_offsets.  BF16 only.
+ * tie_lm_head != 0: a checkpoint without an lm_head tensor (tied embeddings) gets a second copy of
+ * model.embed_tokens.weight appended as "lm_head.weight"; with 0 such a checkpoint is refused (QIE_EIO). */
+int qie_convert_safetensors(const char* const* shard_paths, int n_shards, const char* meta_path, const char* weights_path,
+                            int tie_lm_head, size_t* total_bytes, int* n_tensors);
+
 /* build_indexed_tensors + load_all_weights_to_gpu_chunked + initialize_model_buffers,
  * tensor_parser.cpp:132-165, iengine.cu:117-223, utills.cu:4-129: parse meta_data.txt,
  * upload weights.bin as ONE device blob, derive the model shape from tensor shapes. */

@@ -80,6 +80,7 @@ def lib():
         "qie_attention_decode_fast": (i32, [C.POINTER(KvView), i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "qie_engine_opts_default": (None, [C.POINTER(EngineOpts)]),
         "qie_synth_checkpoint_write": (i32, [C.POINTER(Config), u64, C.c_char_p, C.c_char_p]),
+        "qie_convert_safetensors": (i32, [C.POINTER(C.c_char_p), i32, C.c_char_p, C.c_char_p, i32, C.POINTER(sz), C.POINTER(i32)]),
         "qie_checkpoint_inspect": (i32, [C.c_char_p, i32, C.POINTER(Config), C.POINTER(sz), C.POINTER(i32)]),
         "qie_engine_create": (i32, [C.c_char_p, C.c_char_p, C.POINTER(EngineOpts), C.POINTER(vp)]),
         "qie_engine_create_from_blob": (i32, [C.c_char_p, vp, C.POINTER(EngineOpts), C.POINTER(vp)]),

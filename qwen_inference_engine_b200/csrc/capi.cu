@@ -302,6 +302,19 @@ int qie_checkpoint_inspect(const char* meta_path, int head_dim_hint, qie_config*
   return QIE_OK;
 }
 
+int qie_convert_safetensors(const char* const* shard_paths, int n_shards, const char* meta_path, const char* weights_path,
+                            int tie_lm_head, size_t* total_bytes, int* n_tensors) {
+  if (!shard_paths || n_shards <= 0 || !meta_path || !weights_path) return fail(QIE_EINVAL, "convert_safetensors: null argument");
+  std::vector<std::string> shards;
+  for (int i = 0; i < n_shards; ++i) {
+    if (!shard_paths[i]) return fail(QIE_EINVAL, "convert_safetensors: null shard path");
+    shards.push_back(shard_paths[i]);
+  }
+  const std::string err = convert_safetensors(shards, meta_path, weights_path, tie_lm_head != 0, total_bytes, n_tensors);
+  if (!err.empty()) return fail(QIE_EIO, "%s", err.c_str());
+  return QIE_OK;
+}
+
 static void engine_free(qie_engine* e) {
   if (!e) return;
   cudaSetDevice(e->opts.device);

@@ -44,6 +44,10 @@ Checkpoint synth_layout(const qie_config& cfg);
 // model shape from tensor shapes (replaces the literals of src/utills.cu:8-16)
 bool derive_config(const Checkpoint& ck, int head_dim_hint, int context, qie_config* cfg, std::string* err);
 void write_meta(const Checkpoint& ck, FILE* f);
+// HF safetensors shards -> weights.bin + meta_data.txt in the reference's order (safetensors_convert.cpp);
+// returns "" or the error text
+std::string convert_safetensors(const std::vector<std::string>& shards, const std::string& meta_path,
+                                const std::string& weights_path, bool tie_lm_head, size_t* total_bytes, int* n_tensors);
 // host value of global element g (twin of synth_fill_kernel)
 uint16_t synth_value(uint64_t seed, uint64_t g, int kind);
 

@@ -7,6 +7,8 @@
 // errors are error codes rather than token 0.
 //   iengine --meta model_files/meta_data.txt --weights weights.bin --prompt 151643,785,4767 --n 128
 //   iengine --synthetic qwen2.5-0.5b --prompt 151643,785 --prompt 151643,3639 --n 32 --topk 50
+//   iengine --convert model-00001-of-00002.safetensors --convert model-00002-of-00002.safetensors
+//           --meta model_files/meta_data.txt --weights weights.bin [--tie-lm-head]     (host only, then exits)
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -38,6 +40,8 @@ static bool arch_config(const std::string& a, qie_config* c) {
 
 int main(int argc, char** argv) {
   std::string meta, weights, synthetic;
+  std::vector<const char*> shards;  // --convert: safetensors shards, in order (parsed_tensors(), tensor_parser.cpp:31-129)
+  int tie_lm_head = 0;
   std::vector<std::vector<int32_t>> prompts;
   int n_new = 32, topk = 1, device = 0, fast = 0;
   const int EOS = 151645;
@@ -51,6 +55,8 @@ int main(int argc, char** argv) {
     else if (a == "--topk") topk = atoi(next());
     else if (a == "--device") device = atoi(next());
     else if (a == "--fast") fast = 1;
+    else if (a == "--convert") shards.push_back(next());
+    else if (a == "--tie-lm-head") tie_lm_head = 1;
     else if (a == "--prompt") {
       std::vector<int32_t> p;
       for (char* tok = strtok(const_cast<char*>(next()), ","); tok; tok = strtok(nullptr, ",")) p.push_back(atoi(tok));
@@ -59,6 +65,17 @@ int main(int argc, char** argv) {
       fprintf(stderr, "unknown argument %s\n", a.c_str());
       return 2;
     }
+  }
+  if (!shards.empty()) {  // checkpoint conversion only: no GPU needed
+    if (meta.empty() || weights.empty()) {
+      fprintf(stderr, "iengine: --convert needs --meta and --weights (output paths)\n");
+      return 2;
+    }
+    size_t total = 0;
+    int n = 0;
+    if (qie_convert_safetensors(shards.data(), (int)shards.size(), meta.c_str(), weights.c_str(), tie_lm_head, &total, &n)) die("convert");
+    printf("iengine: %d tensors, %zu bytes -> %s + %s\n", n, total, weights.c_str(), meta.c_str());
+    return 0;
   }
   if (prompts.empty()) prompts.push_back({151643, 785, 4767, 315, 279, 3639, 4180, 374});  // iengine.cu:325
   qie_engine_opts o;

@@ -50,6 +50,16 @@ def write_synthetic_checkpoint(cfg, seed, meta_path, weights_path):
                                                 str(weights_path).encode()))
 
 
+def convert_safetensors(shard_paths, meta_path, weights_path, tie_lm_head=False):
+    """host-only: HF safetensors shards -> weights.bin + meta_data.txt in the reference's layout
+    (parsed_tensors(), tensor_parser.cpp:31-129).  Returns (total bytes, tensor count)."""
+    arr = (C.c_char_p * len(shard_paths))(*[str(p).encode() for p in shard_paths])
+    tot, n = C.c_size_t(), C.c_int()
+    check(_lib.lib().qie_convert_safetensors(arr, len(shard_paths), str(meta_path).encode(), str(weights_path).encode(),
+                                             int(tie_lm_head), C.byref(tot), C.byref(n)))
+    return tot.value, n.value
+
+
 def inspect_checkpoint(meta_path, head_dim_hint=0):
     """host-only: (Config, total weight bytes, tensor count) of a meta_data.txt"""
     cfg, tot, n = Config(), C.c_size_t(), C.c_int()
