@@ -249,6 +249,22 @@ int qie_decode_run(qie_engine* e, const int* h_seqs, const int32_t* h_tokens_in,
 int qie_decode_step_device(qie_engine* e, const int* h_seqs, int n);
 int qie_sync(qie_engine* e);
 
+/* Continuous batching (what iengine.cuh:23-37 `State`, the commented second sequence of iengine.cu:369-373 and
+ * the EOS test of qwen_main.cu:257 sketch).  Requests queue up; every qie_sched_step admits waiting requests
+ * FIFO while sequence slots and KV pages allow (pages for prompt + max_new_tokens are reserved at admission, so a
+ * decode step never runs out), then advances ALL running requests with one batched decode step; a request that
+ * samples `eos_token` (151645 in the reference; -1 = none) or reaches max_new_tokens leaves the batch and its pages
+ * are recycled.  In reference-order numerics a request's tokens do not depend on the batch it shares (tested).
+ * qie_sched_step returns the number of unfinished requests or a negative error; qie_sched_result copies the tokens
+ * generated so far (including the EOS token) and returns their count. */
+typedef struct qie_scheduler qie_scheduler;
+int qie_sched_create(qie_engine* e, int max_running, int eos_token, qie_scheduler** out);
+void qie_sched_destroy(qie_scheduler* s);
+int qie_sched_submit(qie_scheduler* s, const int32_t* ids, int n, int max_new_tokens, int* request_id);
+int qie_sched_step(qie_scheduler* s);
+int qie_sched_result(const qie_scheduler* s, int request_id, int32_t* out, int max_tokens, int* finished);
+int qie_sched_stats(const qie_scheduler* s, long* steps, long* decode_rows, long* prefills, int* running, int* waiting);
+
 /* Parity hooks (the reference's dump_device_bf16, qwen_main.cu:42-61). When capture is
  * on, every forward keeps per-layer activations; qie_capture_read copies one of them to
  * HOST memory. Tags: input_norm q k v attn x_attn mlp_h x_out (layer >= 0), logits

@@ -6,8 +6,8 @@ This package only binds it: `engine` mirrors the reference's host driver, `layer
 `launch_*` operator wrappers.  Importing the package never touches oracle/.
 """
 from ._lib import LIB_PATH, QieError, declared_symbols, lib  # noqa: F401
-from .engine import (ARCHS, REF_CONTEXT, Config, Engine, convert_safetensors, inspect_checkpoint, kv_bytes_per_pos,  # noqa: F401
+from .engine import (ARCHS, REF_CONTEXT, Config, Engine, Scheduler, convert_safetensors, inspect_checkpoint, kv_bytes_per_pos,  # noqa: F401
                      make_config, tp_plan, weight_bytes, write_synthetic_checkpoint)
 
-__all__ = ["Engine", "Config", "make_config", "ARCHS", "QieError", "lib", "LIB_PATH", "weight_bytes",
+__all__ = ["Engine", "Scheduler", "Config", "make_config", "ARCHS", "QieError", "lib", "LIB_PATH", "weight_bytes",
            "kv_bytes_per_pos", "tp_plan", "convert_safetensors", "inspect_checkpoint", "write_synthetic_checkpoint", "declared_symbols", "REF_CONTEXT"]

@@ -98,6 +98,12 @@ def lib():
         "qie_seq_free": (i32, [vp, i32]),
         "qie_seq_len": (i32, [vp, i32]),
         "qie_kv_pages_free": (i32, [vp]),
+        "qie_sched_create": (i32, [vp, i32, i32, C.POINTER(vp)]),
+        "qie_sched_destroy": (None, [vp]),
+        "qie_sched_submit": (i32, [vp, vp, i32, i32, ip]),
+        "qie_sched_step": (i32, [vp]),
+        "qie_sched_result": (i32, [vp, i32, vp, i32, ip]),
+        "qie_sched_stats": (i32, [vp, C.POINTER(C.c_long), C.POINTER(C.c_long), C.POINTER(C.c_long), ip, ip]),
         "qie_prefill": (i32, [vp, i32, vp, i32, vp]),
         "qie_decode_step": (i32, [vp, vp, vp, i32, vp]),
         "qie_decode_run": (i32, [vp, vp, vp, i32, i32, vp]),

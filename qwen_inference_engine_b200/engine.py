@@ -265,3 +265,52 @@ class Engine:
             return toks
         finally:
             self.free_sequence(s)
+
+
+class Scheduler:
+    """continuous batching over an Engine (qie_sched_* in include/qie_b200.h): submit() queues a request,
+    step() admits + runs one batched decode step, run() drains the queue."""
+
+    def __init__(self, engine, max_running=64, eos_token=151645):
+        self._L, self._eng = engine._L, engine
+        h = C.c_void_p()
+        check(self._L.qie_sched_create(engine._h, max_running, eos_token, C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.qie_sched_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def submit(self, ids, max_new_tokens):
+        ids = _i32(ids)
+        rid = C.c_int()
+        check(self._L.qie_sched_submit(self._h, ids.ctypes.data, len(ids), max_new_tokens, C.byref(rid)))
+        return rid.value
+
+    def step(self):
+        return check(self._L.qie_sched_step(self._h))
+
+    def result(self, rid, max_tokens=1 << 16):
+        out = np.zeros(max_tokens, np.int32)
+        fin = C.c_int()
+        n = check(self._L.qie_sched_result(self._h, rid, out.ctypes.data, max_tokens, C.byref(fin)))
+        return [int(t) for t in out[:min(n, max_tokens)]], bool(fin.value)
+
+    def stats(self):
+        st, rows, pf = C.c_long(), C.c_long(), C.c_long()
+        run, wait = C.c_int(), C.c_int()
+        check(self._L.qie_sched_stats(self._h, C.byref(st), C.byref(rows), C.byref(pf), C.byref(run), C.byref(wait)))
+        return dict(steps=st.value, decode_rows=rows.value, prefills=pf.value, running=run.value, waiting=wait.value)
+
+    def run(self, max_steps=1 << 20):
+        for _ in range(max_steps):
+            if self.step() == 0:
+                return
+        raise RuntimeError("scheduler did not drain")

@@ -1,0 +1,69 @@
+"""gpu: continuous batching (qie_sched_*).  Requests of different lengths share decode steps, join and leave the
+batch at different times, wait for KV pages; in reference-order numerics every request must get exactly the tokens
+it gets when it runs alone (llm() of the reference is per sequence: iengine.cu:327-421), EOS ends a request at once
+and all pages return to the pool."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+pytestmark = pytest.mark.gpu
+
+
+def _requests(vocab):
+    from util import prompt_ids
+    lens = [3, 40, 7, 19, 33, 5, 12, 27, 9, 16, 4]
+    news = [24, 5, 17, 9, 12, 30, 6, 14, 21, 8, 11]
+    return [(prompt_ids(n, vocab, seed=100 + i), m) for i, (n, m) in enumerate(zip(lens, news))]
+
+
+def test_continuous_batching_matches_solo_runs():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import qwen_inference_engine_b200 as q
+    # 16-position pages; 14 pages: at most ~3-4 requests (prompt + budget reserved) fit at once -> queueing
+    eng = q.Engine(synthetic="small", seed=5, context=256, max_seqs=5, max_pages=14, max_batch_tokens=64)
+    reqs = _requests(eng.config.vocab)
+    solo = [eng.generate(ids, m) for ids, m in reqs]
+    total_pages = eng.pages_free()
+    sch = q.Scheduler(eng, max_running=4, eos_token=-1)
+    rids = [sch.submit(ids, m) for ids, m in reqs]
+    seen_running = set()
+    for _ in range(10000):
+        left = sch.step()
+        st = sch.stats()
+        seen_running.add(st["running"])
+        assert st["running"] <= 4
+        if left == 0:
+            break
+    for rid, want in zip(rids, solo):
+        got, fin = sch.result(rid)
+        assert fin and got == want
+    st = sch.stats()
+    assert st["prefills"] == len(reqs) and st["decode_rows"] == sum(len(s) - 1 for s in solo)
+    assert max(seen_running) >= 3 and st["steps"] < sum(len(s) for s in solo)  # requests really shared steps
+    assert eng.pages_free() == total_pages  # every page came back
+    sch.close()
+
+    # EOS: a token that some request produces in mid-stream ends that request there (qwen_main.cu:257)
+    eos = solo[5][9]
+    sch = q.Scheduler(eng, max_running=3, eos_token=eos)
+    rids = [sch.submit(ids, m) for ids, m in reqs]
+    sch.run()
+    cut = 0
+    for rid, want in zip(rids, solo):
+        got, fin = sch.result(rid)
+        exp = want[:want.index(eos) + 1] if eos in want else want
+        cut += len(exp) < len(want)
+        assert fin and got == exp
+    assert cut >= 1 and eng.pages_free() == total_pages
+    # a request that can never fit is refused at submit
+    with pytest.raises(q.QieError):
+        sch.submit(np.arange(200, dtype=np.int32) % 100, 100)
+    sch.close()
+    eng.close()
