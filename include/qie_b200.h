@@ -230,6 +230,11 @@ int qie_seq_new(qie_engine* e, int* seq);
 /* free_page_list + destroy_model_buffers (iengine.cu:98-109, utills.cu:147-205). */
 int qie_seq_free(qie_engine* e, int seq);
 int qie_seq_len(const qie_engine* e, int seq);
+/* KV offload (the experiment commented out in iengine.cu:376-429): copy the sequence's pages to pinned host memory
+ * and return them to the pool / take fresh pages and copy the bytes back.  A swapped-out sequence keeps its length
+ * and step; prefill/decode on it return QIE_ESTATE until it is swapped in; generation then continues bit for bit. */
+int qie_seq_swap_out(qie_engine* e, int seq);
+int qie_seq_swap_in(qie_engine* e, int seq);
 int qie_kv_pages_free(const qie_engine* e);
 
 /* llm() with state == prefill, qwen_main.cu:74-247. h_ids: HOST int32[n]. The sampled

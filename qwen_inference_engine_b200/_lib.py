@@ -97,6 +97,8 @@ def lib():
         "qie_seq_new": (i32, [vp, ip]),
         "qie_seq_free": (i32, [vp, i32]),
         "qie_seq_len": (i32, [vp, i32]),
+        "qie_seq_swap_out": (i32, [vp, i32]),
+        "qie_seq_swap_in": (i32, [vp, i32]),
         "qie_kv_pages_free": (i32, [vp]),
         "qie_sched_create": (i32, [vp, i32, i32, C.POINTER(vp)]),
         "qie_sched_destroy": (None, [vp]),

@@ -844,6 +844,7 @@ int qie_seq_free(qie_engine* e, int seq) {
   if (rc) return rc;
   cudaStreamSynchronize(e->stream);
   for (int p : e->seqs[seq].pages) e->free_pages.push_back(p);
+  if (e->seqs[seq].host_copy) cudaFreeHost(e->seqs[seq].host_copy);
   e->seqs[seq] = Sequence();
   return QIE_OK;
 }
@@ -889,6 +890,7 @@ int qie_prefill(qie_engine* e, int seq, const int32_t* h_ids, int n, int32_t* h_
     if (h_ids[i] < 0 || h_ids[i] >= e->cfg.vocab) return fail(QIE_EINVAL, "prefill: token id %d out of range", h_ids[i]);
   CU(cudaSetDevice(e->opts.device));
   Sequence& s = e->seqs[seq];
+  if (s.host_copy) return fail(QIE_ESTATE, "sequence %d is swapped out (qie_seq_swap_in first)", seq);
   rc = ensure_pages(e, seq, s.len + n);
   if (rc < 0) return rc;
   if (rc) CU(push_block_row(e, seq));
@@ -967,6 +969,7 @@ static int decode_prepare(qie_engine* e, const int* h_seqs, int n, int* max_kv_l
     if (rc) return rc;
     Sequence& s = e->seqs[h_seqs[i]];
     if (s.len == 0) return fail(QIE_ESTATE, "sequence %d has not been prefilled", h_seqs[i]);
+    if (s.host_copy) return fail(QIE_ESTATE, "sequence %d is swapped out (qie_seq_swap_in first)", h_seqs[i]);
     rc = ensure_pages(e, h_seqs[i], s.len + 1);
     if (rc < 0) return rc;
     if (rc) CU(push_block_row(e, h_seqs[i]));
@@ -1086,6 +1089,52 @@ long qie_capture_read(qie_engine* e, const char* tag, int layer, qie_bf16* h_out
 }
 
 long qie_launch_count(const qie_engine* e) { return e ? e->launches : 0; }
+
+// KV offload (the experiment commented out in the reference's main(), iengine.cu:376-429): the pages of a
+// sequence are copied to pinned host memory and handed back to the pool; swap-in takes fresh pages (any ids) and
+// copies the bytes back.  A page holds all layers, so one copy per page moves page_stride() elements.
+int qie_seq_swap_out(qie_engine* e, int seq) {
+  int rc = check_seq(e, seq);
+  if (rc) return rc;
+  Sequence& s = e->seqs[seq];
+  if (s.host_copy) return fail(QIE_ESTATE, "sequence %d is already swapped out", seq);
+  if (s.pages.empty()) return QIE_OK;
+  CU(cudaSetDevice(e->opts.device));
+  const size_t pb = e->kv.page_stride() * sizeof(bf16);
+  CU(cudaMallocHost(&s.host_copy, s.pages.size() * pb));
+  for (size_t i = 0; i < s.pages.size(); ++i)
+    CU(cudaMemcpyAsync(static_cast<char*>(s.host_copy) + i * pb, reinterpret_cast<const char*>(e->kv.pool) + (size_t)s.pages[i] * pb, pb,
+                       cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  s.host_pages = (int)s.pages.size();
+  for (int p : s.pages) e->free_pages.push_back(p);
+  s.pages.clear();
+  return QIE_OK;
+}
+
+int qie_seq_swap_in(qie_engine* e, int seq) {
+  int rc = check_seq(e, seq);
+  if (rc) return rc;
+  Sequence& s = e->seqs[seq];
+  if (!s.host_copy) return fail(QIE_ESTATE, "sequence %d is not swapped out", seq);
+  if ((int)e->free_pages.size() < s.host_pages) return fail(QIE_ENOMEM, "swap_in: %d pages needed, %zu free", s.host_pages, e->free_pages.size());
+  CU(cudaSetDevice(e->opts.device));
+  const size_t pb = e->kv.page_stride() * sizeof(bf16);
+  for (int i = 0; i < s.host_pages; ++i) {
+    const int p = e->free_pages.back();
+    e->free_pages.pop_back();
+    e->block_table_h[(size_t)seq * e->max_pages_per_seq + i] = p;
+    s.pages.push_back(p);
+    CU(cudaMemcpyAsync(reinterpret_cast<char*>(e->kv.pool) + (size_t)p * pb, static_cast<const char*>(s.host_copy) + (size_t)i * pb, pb,
+                       cudaMemcpyHostToDevice, e->stream));
+  }
+  CU(push_block_row(e, seq));
+  CU(cudaStreamSynchronize(e->stream));
+  cudaFreeHost(s.host_copy);
+  s.host_copy = nullptr;
+  s.host_pages = 0;
+  return QIE_OK;
+}
 
 int qie_seq_fill_synthetic(qie_engine* e, int seq, int n_pos, uint64_t seed) {
   int rc = check_seq(e, seq);

@@ -27,6 +27,9 @@ struct Sequence {
   int len = 0;   // positions held in the KV cache (ModelBuffers::sequence_len)
   int step = 0;  // batch_metadata::step
   std::vector<int> pages;
+  // swapped out (qie_seq_swap_out): the pages' bytes live in pinned host memory, `pages` is empty
+  void* host_copy = nullptr;
+  int host_pages = 0;
 };
 
 struct CaptureBuf {

@@ -165,6 +165,12 @@ class Engine:
     def free_sequence(self, seq):
         check(self._L.qie_seq_free(self._h, seq))
 
+    def swap_out(self, seq):
+        check(self._L.qie_seq_swap_out(self._h, seq))
+
+    def swap_in(self, seq):
+        check(self._L.qie_seq_swap_in(self._h, seq))
+
     def seq_len(self, seq):
         return check(self._L.qie_seq_len(self._h, seq))
 

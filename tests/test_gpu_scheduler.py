@@ -67,3 +67,40 @@ def test_continuous_batching_matches_solo_runs():
         sch.submit(np.arange(200, dtype=np.int32) % 100, 100)
     sch.close()
     eng.close()
+
+
+def test_kv_swap_out_and_in_keeps_generation_bit_exact():
+    """KV offload (iengine.cu:376-429, commented out in the reference): a sequence's pages go to pinned host memory,
+    other sequences overwrite them, the sequence comes back on different pages and continues with the same tokens."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import qwen_inference_engine_b200 as q
+    from util import prompt_ids
+    eng = q.Engine(synthetic="small", seed=8, context=256, max_seqs=4, max_pages=8, max_batch_tokens=64)
+    ids = prompt_ids(37, eng.config.vocab, seed=3)
+    want = eng.generate(ids, 24)
+    total = eng.pages_free()
+    a = eng.new_sequence()
+    toks = [eng.prefill(a, ids)]
+    toks += [int(t) for t in eng.decode_run([a], [toks[0]], 7)[:, 0]]
+    used = total - eng.pages_free()
+    eng.swap_out(a)
+    assert eng.pages_free() == total and eng.seq_len(a) == 37 + 7
+    with pytest.raises(q.QieError):
+        eng.decode_step([a], [toks[-1]])  # swapped out
+    with pytest.raises(q.QieError):
+        eng.swap_out(a)
+    # other work takes (and dirties) the whole pool
+    others = [eng.generate(prompt_ids(50 + 9 * i, eng.config.vocab, seed=20 + i), 12) for i in range(2)]
+    b = eng.new_sequence()
+    eng.prefill(b, prompt_ids(100, eng.config.vocab, seed=40))  # 7 pages: A's old pages are in use again
+    with pytest.raises(q.QieError):
+        eng.swap_in(a)  # not enough free pages
+    eng.free_sequence(b)
+    eng.swap_in(a)
+    assert total - eng.pages_free() == used
+    toks += [int(t) for t in eng.decode_run([a], [toks[-1]], 16)[:, 0]]
+    assert toks == want and len(others) == 2
+    eng.free_sequence(a)
+    assert eng.pages_free() == total
+    eng.close()
