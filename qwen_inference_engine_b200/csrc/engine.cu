@@ -189,6 +189,8 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
       a.layer = l;
       const int tiles = (max_kv_len + 63) / 64;
       int ns = (4 * e->num_sms) / std::max(1, n * c.n_kv);
+      static const int ns_env = [] { const char* v = getenv("QIE_ATTN_SPLITS"); return v ? atoi(v) : 0; }();  // tuning knob
+      if (ns_env > 0) ns = ns_env;
       ns = std::max(1, std::min(ns, std::min(e->attn_max_splits, tiles)));
       a.n_splits = ns;
       a.scale_log2 = 1.4426950408889634f / sqrtf((float)hd);
