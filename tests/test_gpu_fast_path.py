@@ -157,6 +157,33 @@ def test_fast_prefill_persistent_gemm_whole_prompt():
     e_fast.close()
 
 
+def test_fast_prefill_chunking():
+    """the same 700-token prompt prefilled in one forward, in chunks of 256 and in chunks of 100 rows (different
+    GEMM variants: persistent / one tile per CTA / cluster split-K, attention with a cache prefix).  Rows are
+    independent, only the split-K summation order depends on the chunk size, so logits agree within the fast-path
+    tolerance and the reference-order engine -- where chunking must be invisible bit for bit -- is checked too."""
+    import qwen_inference_engine_b200 as q
+    cfg = q.make_config(dict(q.ARCHS["qwen2.5-0.5b"], layers=3, vocab=4096), context=2048)
+    ids = prompt_ids(700, cfg.vocab, seed=23)
+    for numerics, chunks in (("fast", (1024, 256, 100)), ("reference_order", (256, 64))):
+        outs, logits = [], []
+        for chunk in chunks:
+            eng = q.Engine(synthetic=cfg, seed=4, context=2048, max_batch_tokens=chunk, max_seqs=2, kv_bytes=128 << 20,
+                           numerics=numerics)
+            eng.capture(True)
+            s = eng.new_sequence()
+            t = eng.prefill(s, ids)
+            logits.append(eng.read_capture("logits", -1).copy())
+            eng.capture(False)
+            outs.append([t] + [int(x) for x in eng.decode_run([s], [t], 12)[:, 0]])
+            eng.close()
+        for lg, o in zip(logits[1:], outs[1:]):
+            if numerics == "fast":
+                assert close(lg, logits[0]), (rel_l2(lg, logits[0]), rel_err(lg, logits[0]))
+            else:
+                assert np.array_equal(lg, logits[0]) and o == outs[0]
+
+
 def test_fast_engine_vs_reference_order_engine():
     """whole forward, batch 16 decode: FAST numerics vs REFERENCE_ORDER numerics on the same
     weights: logits within tolerance at every step; token agreement reported."""
