@@ -64,7 +64,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "40"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -73,12 +73,16 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """clocks of the samples taken inside [t0, t1] (host wall clock around the timed region).  nvidia-smi is
+        started before the warm-up so that it is already streaming when the region begins; if the region is
+        shorter than the sampling interval, the samples of the whole loaded window (warm-up + timed steps) are
+        used and the JSON says so."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -86,7 +90,14 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        rows, window = self.rows, "all samples"
+        if t0 is not None and t1 is not None:
+            inside = [r for r in self.rows if t0 <= r[0] <= t1]
+            if inside:
+                rows, window = inside, "timed region"
+            else:
+                rows, window = [r for r in self.rows if r[0] <= t1 + 0.1], "warm-up + timed region (region shorter than the sampling interval)"
+        for r in (x[1:] for x in rows):
             try:
                 sm.append(float(r[1]))
                 mx.append(float(r[2]))
@@ -97,7 +108,7 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def dist_env():
@@ -243,14 +254,15 @@ def main():
             torch.cuda.synchronize()
 
     # ---------------- kernel-only leg (graph replay, ids resident on the device) ----------
+    sampler = ClockSampler(local)
+    sampler.start()  # streaming before the warm-up, so samples exist from the first timed step on
     cur = eng.decode_step(seqs, tokens)  # stages ids/pos on the device, first graph shape seen
     for _ in range(args.warmup):
         eng.decode_step_device(seqs)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
+    t_region0 = time.time()
     with torch.cuda.stream(ext):
         e0.record()
     for _ in range(args.steps):
@@ -260,7 +272,7 @@ def main():
         e1.record()
     eng.sync()
     ms_kernel = e0.elapsed_time(e1)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_region0, time.time())
     barrier()
 
     # ---------------- e2e leg (host buffers through the C ABI) ----------------------------
