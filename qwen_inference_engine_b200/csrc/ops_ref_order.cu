@@ -12,6 +12,11 @@
 #include <curand_kernel.h>
 #include <math_constants.h>
 
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 #include "kernels.h"
 #include "launch.h"
@@ -544,9 +549,110 @@ __global__ void __launch_bounds__(1024) sample_topk_kernel(const bf16* __restric
   }
 }
 
+// Greedy mode (k == 1, what the persistent kernel folds into its lm_head epilogue): the sampled token is the
+// arg-max in the reference's total order whatever the random draw, so the row can be scanned by several CTAs with
+// 16-byte loads -- the one-block-per-row scan above is latency bound (85 us for 152 k logits, 64 SMs busy at batch
+// 64).  Stage 1: CTA (slice, row) reduces its slice to one candidate; stage 2: one warp per row merges the slices.
+constexpr int GREEDY_SLICES = 8;
+__global__ void __launch_bounds__(256) greedy_slice_kernel(const bf16* __restrict__ logits, Cand* __restrict__ cands, size_t vocab) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ Cand s_c[8];
+  const int slice = blockIdx.x, rowi = blockIdx.y;
+  const bf16* row = logits + (size_t)rowi * vocab;
+  const size_t nvec = vocab >> 3;  // 8 logits per 16-byte load (rows are 16-byte aligned: vocab % 8 == 0, checked by the launcher)
+  const size_t per = (nvec + GREEDY_SLICES - 1) / GREEDY_SLICES;
+  const size_t v0 = (size_t)slice * per, v1 = min(nvec, v0 + per);
+  float bv = -CUDART_INF_F;
+  int bi = -1;
+  for (size_t v = v0 + threadIdx.x; v < v1; v += 256) {
+    const uint4 q = ld_nc_v4(reinterpret_cast<const uint4*>(row) + v);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float f0 = lo2f(w[e]), f1 = hi2f(w[e]);
+      const int i0 = (int)(v * 8) + 2 * e;
+      if (f0 > -CUDART_INF_F && cand_better(f0, i0, bv, bi)) {
+        bv = f0;
+        bi = i0;
+      }
+      if (f1 > -CUDART_INF_F && cand_better(f1, i0 + 1, bv, bi)) {
+        bv = f1;
+        bi = i0 + 1;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (cand_better(ov, oi, bv, bi)) {
+      bv = ov;
+      bi = oi;
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) s_c[warp] = Cand{bv, bi};
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w2 = 1; w2 < 8; ++w2)
+      if (cand_better(s_c[w2].val, s_c[w2].idx, bv, bi)) {
+        bv = s_c[w2].val;
+        bi = s_c[w2].idx;
+      }
+    cands[(size_t)rowi * GREEDY_SLICES + slice] = Cand{bv, bi};
+  }
+}
+__global__ void greedy_merge_kernel(const Cand* __restrict__ cands, int* __restrict__ out, int n_rows) {
+  pdl_wait();
+  pdl_trigger();
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows) return;
+  float bv = -CUDART_INF_F;
+  int bi = -1;
+  for (int s2 = 0; s2 < GREEDY_SLICES; ++s2) {
+    const Cand c = cands[(size_t)r * GREEDY_SLICES + s2];
+    if (cand_better(c.val, c.idx, bv, bi)) {
+      bv = c.val;
+      bi = c.idx;
+    }
+  }
+  out[r] = bi;  // -1 if the row holds no finite logit, like the scan above
+}
+
 cudaError_t launch_sample_topk(const bf16* logits, int* out_tokens, int n_rows, size_t vocab, float temperature,
                                int k, uint64_t seed, uint64_t seed_stride, const int* step_ptr, cudaStream_t st) {
   if (n_rows == 0) return cudaSuccess;
+  if (k == 1 && vocab % 8 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && vocab >= 4096) {
+    // candidate scratch per stream (engines of one process run on their own streams); buffers are never freed or
+    // moved once handed out, because captured CUDA graphs keep their address
+    struct Scratch {
+      Cand* p = nullptr;
+      int cap = 0;
+    };
+    static std::mutex mu;
+    static std::map<cudaStream_t, std::vector<Scratch>> pool;
+    Cand* cands = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      std::vector<Scratch>& v = pool[st];
+      for (const Scratch& sc : v)
+        if (sc.cap >= n_rows) cands = sc.p;
+      if (!cands) {
+        Scratch sc;
+        sc.cap = std::max(n_rows, 256);
+        cudaError_t e = cudaMalloc(&sc.p, (size_t)sc.cap * GREEDY_SLICES * sizeof(Cand));
+        if (e != cudaSuccess) return e;
+        v.push_back(sc);
+        cands = sc.p;
+      }
+    }
+    (void)launch_k(greedy_slice_kernel, dim3(GREEDY_SLICES, n_rows), dim3(256), 0, st, logits, cands, vocab);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    (void)launch_k(greedy_merge_kernel, dim3((n_rows + 63) / 64), dim3(64), 0, st, (const Cand*)cands, out_tokens, n_rows);
+    return cudaGetLastError();
+  }
   (void)launch_k(sample_topk_kernel, dim3(n_rows), dim3(1024), 0, st, logits, out_tokens, vocab, temperature, k, seed, seed_stride, step_ptr);
   return cudaGetLastError();
 }
