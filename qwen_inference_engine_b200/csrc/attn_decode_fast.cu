@@ -26,7 +26,10 @@
 namespace qie {
 
 static constexpr int TILE = 64;    // kv positions per pipeline stage
-static constexpr int STAGES = 3;   // 3 x 16 KiB (hd 64): 4 CTAs / SM
+#ifndef QIE_FD_STAGES
+#define QIE_FD_STAGES 3
+#endif
+static constexpr int STAGES = QIE_FD_STAGES;   // 3 x 16 KiB (hd 64): 4 CTAs / SM
 
 template <int HD>
 struct FastAttnSmem {

@@ -17,10 +17,11 @@ ap.add_argument("--steps", type=int, default=128)
 ap.add_argument("--mega", type=int, default=1)
 ap.add_argument("--graph", type=int, default=1)
 ap.add_argument("--fast", type=int, default=0)
+ap.add_argument("--page-size", type=int, default=16)
 a = ap.parse_args()
 cfg = q.make_config(a.arch)
 eng = q.Engine(synthetic=a.arch, kv_bytes=a.batch * (a.ctx + a.steps + 256) * q.kv_bytes_per_pos(cfg) + (64 << 20),
-               max_seqs=a.batch + 1, max_batch_tokens=max(a.batch, 64), use_graph=bool(a.graph),
+               max_seqs=a.batch + 1, max_batch_tokens=max(a.batch, 64), use_graph=bool(a.graph), page_size=a.page_size,
                numerics="fast" if a.fast else "reference_order")
 eng.set_int("mega", a.mega)
 seqs = []
