@@ -200,6 +200,38 @@ __device__ __forceinline__ void load_rows_tp(const MegaArgs& a, uint32_t act, in
   bar_consumers();
 }
 
+// One row (dist_norm: CTA b owns row b): the sum lands in row 0 of the activation region and in the other
+// residual buffer; nobody else computes this row.
+__device__ __forceinline__ void load_row_tp(const MegaArgs& a, uint32_t act, int b, int H, const bf16* x_cur, bf16* x_next, int xpar) {
+  const int hv = H >> 3;
+  const float* part = a.tp_part[a.tp_rank] + (size_t)xpar * a.tp_size * MEGA_TP_ROWS * H;
+  const size_t rstride = (size_t)MEGA_TP_ROWS * H;
+  for (int i = threadIdx.x; i < hv; i += NTC) {
+    const int n = i * 8;
+    const size_t e = (size_t)b * H + n;
+    const uint4 old = __ldcg(reinterpret_cast<const uint4*>(x_cur + e));
+    float4 s0 = __ldcg(reinterpret_cast<const float4*>(part + e));
+    float4 s1 = __ldcg(reinterpret_cast<const float4*>(part + e + 4));
+    for (int r = 1; r < a.tp_size; ++r) {
+      const float4 p0 = __ldcg(reinterpret_cast<const float4*>(part + r * rstride + e));
+      const float4 p1 = __ldcg(reinterpret_cast<const float4*>(part + r * rstride + e + 4));
+      s0.x = __fadd_rn(s0.x, p0.x); s0.y = __fadd_rn(s0.y, p0.y); s0.z = __fadd_rn(s0.z, p0.z); s0.w = __fadd_rn(s0.w, p0.w);
+      s1.x = __fadd_rn(s1.x, p1.x); s1.y = __fadd_rn(s1.y, p1.y); s1.z = __fadd_rn(s1.z, p1.z); s1.w = __fadd_rn(s1.w, p1.w);
+    }
+    auto add2 = [](uint32_t o, float y0, float y1) {
+      return pack2(f2bf(__fadd_rn(lo2f(o), bf2f(f2bf(y0)))), f2bf(__fadd_rn(hi2f(o), bf2f(f2bf(y1)))));
+    };
+    uint4 nw;
+    nw.x = add2(old.x, s0.x, s0.y);
+    nw.y = add2(old.y, s0.z, s0.w);
+    nw.z = add2(old.z, s1.x, s1.y);
+    nw.w = add2(old.w, s1.z, s1.w);
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(act + n * 2), "r"(nw.x), "r"(nw.y), "r"(nw.z), "r"(nw.w) : "memory");
+    *reinterpret_cast<uint4*>(x_next + e) = nw;
+  }
+  bar_consumers();
+}
+
 // The same sum for more than a few rows: every CTA reading every rank's fp32 partial sums of the whole batch
 // costs (2 + 4 tp) bytes per element and CTA of L2 traffic, so the rows are combined ONCE -- item i by CTA
 // i mod grid -- into the other residual buffer, followed by a grid barrier and a plain bf16 row load.
@@ -1386,11 +1418,19 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
         // CTA b normalises row b once, publishes it, and everybody copies the result
         const int b = blockIdx.x;
         if (b < a.B) {  // B <= gridDim.x (launcher)
-          load_rows(act, 1, H, [&](int) { return from_embed ? a.embed + (size_t)a.ids[b] * H : a.x + (size_t)b * H; });
+          if (tp && !from_embed)
+            load_row_tp(a, act, b, H, x_cur, x_next, (int)((xch - 1) & 1));
+          else
+            load_rows(act, 1, H, [&](int) { return from_embed ? a.embed + (size_t)a.ids[b] * H : a.x + (size_t)b * H; });
           rmsnorm_rows(a, smem, 1, H, which);
           const uint4* src = reinterpret_cast<const uint4*>(smem + a.off_act);
           uint4* dst = reinterpret_cast<uint4*>(a.xn + (size_t)b * H);
           for (int i = threadIdx.x; i < (H >> 3); i += NTC) dst[i] = src[i];
+        }
+        if (tp && !from_embed) {  // every row was rewritten by its CTA
+          const bf16* t = x_cur;
+          x_cur = x_next;
+          x_next = const_cast<bf16*>(t);
         }
         grid_sync(a.bar, epoch);
         stamp();

@@ -545,7 +545,7 @@ cudaError_t forward_decode_mega(qie_engine* e, int n, int max_kv_len, float temp
     for (int r = 0; r < e->tp.size; ++r) {
       char* base = reinterpret_cast<char*>(e->tp_peer_xbuf[r]);
       a.tp_flag[r] = reinterpret_cast<unsigned*>(base);
-      a.tp_cand[r] = reinterpret_cast<MegaCand*>(base + 256);
+      a.tp_cand[r] = reinterpret_cast<MegaCand*>(base + 256);  // [tp][MEGA_TP_ROWS] x 8 bytes <= 2 KiB < MEGA_TP_HEADER
       a.tp_part[r] = reinterpret_cast<float*>(base + MEGA_TP_HEADER);
     }
     a.tp_epoch = reinterpret_cast<unsigned*>(e->tp_xbuf) + 32;  // byte 128 of the header: local generation base

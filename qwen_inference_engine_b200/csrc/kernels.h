@@ -172,8 +172,8 @@ cudaError_t launch_advance(int* pos, int* ids, const int* sampled, int n, int* s
 // decode_mega.cu: ONE cooperative launch runs a whole decode step (all layers, lm_head,
 // greedy arg-max, bookkeeping) for up to 64 sequences in reference-order arithmetic.
 constexpr int MEGA_MAX_TP = 4;
-constexpr int MEGA_TP_ROWS = 16;
-constexpr int MEGA_TP_HEADER = 1024;  // bytes in front of the partial sums: flag words, generation word (byte 128), candidate table (byte 256)
+constexpr int MEGA_TP_ROWS = 64;
+constexpr int MEGA_TP_HEADER = 4096;  // bytes in front of the partial sums: flag words, generation word (byte 128), candidate table (byte 256)
 struct MegaLayer {
   const bf16 *in_ln, *q, *k, *v, *o, *q_norm, *k_norm, *post_ln, *gate, *up, *down;
 };
@@ -207,7 +207,7 @@ struct MegaArgs {
   int fast;                          // 1: fast (tolerance) numerics, <= 8 rows: split-K over the warps, parallel RMSNorm
   int kv_l2_prefetch;                // 1: request the next layer's cached K/V into L2 one phase group ahead of its attention
   int n_layers_run;                  // debug: stop after this many layers (0 = all, then lm_head)
-  // tensor parallel inside the kernel (tp_size > 1, <= 16 rows): n_q / n_kv / I / V and the weight maps describe
+  // tensor parallel inside the kernel (tp_size > 1, <= MEGA_TP_ROWS rows): n_q / n_kv / I / V and the weight maps describe
   // THIS rank's shard; o_proj / down_proj accumulators are written as fp32 partial sums into every rank's
   // exchange buffer over NVLink peer mappings, a cross-GPU flag barrier replaces the grid barrier behind those two
   // phases, and the next phase's row load adds the partial sums in rank order (one bf16 rounding, like tp_size 1)

@@ -29,7 +29,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("arch,batch", [("small", 3), ("qwen2.5-0.5b", 2)])
+@pytest.mark.parametrize("arch,batch", [("small", 3), ("qwen2.5-0.5b", 2), ("small", 20)])  # 20 rows: one CTA per row normalises
 def test_tp2_matches_single_gpu(arch, batch):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
