@@ -127,6 +127,12 @@ int qie_attention_prefill_fast(const qie_kv_view* kv, int layer, const qie_bf16*
                                const int* slot, const int* block_table, int max_pages, int n_tok, int n_q_heads,
                                qie_stream st);
 
+/* The same prefill attention on tcgen05 / TMEM (head_dim 128): S = QK^T and O_t = PV as tcgen05.mma with the
+ * accumulators in tensor memory, softmax by one thread per query row over tcgen05.ld.  variant = 0. */
+int qie_attention_prefill_tc(const qie_kv_view* kv, int layer, const qie_bf16* Q, qie_bf16* out, const int* pos,
+                             const int* slot, const int* block_table, int max_pages, int n_tok, int n_q_heads, int variant,
+                             qie_stream st);
+
 /* ------------------------------------------------------------------------------------
  * (2) driver level
  * ---------------------------------------------------------------------------------- */

@@ -76,6 +76,7 @@ def lib():
         "qie_attention": (i32, [C.POINTER(KvView), i32, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
         "qie_sample_topk": (i32, [vp, vp, i32, sz, f32, i32, u64, u64, vp]),
         "qie_matmul_fast": (i32, [vp, vp, vp, i32, i32, i32, vp]),
+        "qie_attention_prefill_tc": (i32, [C.POINTER(KvView), i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "qie_attention_prefill_fast": (i32, [C.POINTER(KvView), i32, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
         "qie_attention_decode_fast": (i32, [C.POINTER(KvView), i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "qie_engine_opts_default": (None, [C.POINTER(EngineOpts)]),

@@ -247,6 +247,28 @@ int qie_attention_prefill_fast(const qie_kv_view* kv, int layer, const qie_bf16*
   return QIE_OK;
 }
 
+int qie_attention_prefill_tc(const qie_kv_view* kv, int layer, const qie_bf16* Q, qie_bf16* out, const int* pos,
+                             const int* slot, const int* block_table, int max_pages, int n_tok, int n_q_heads, int variant,
+                             qie_stream st) {
+  if (!kv || layer < 0 || layer >= kv->n_layers) return fail(QIE_EINVAL, "attention_prefill_tc: bad layer");
+  if (n_q_heads % kv->n_kv_heads || kv->head_dim != 128) return fail(QIE_EINVAL, "attention_prefill_tc: head_dim must be 128");
+  FastAttnArgs a{};
+  a.q = (const bf16*)Q;
+  a.out = (bf16*)out;
+  a.pos = pos;
+  a.slot = slot;
+  a.block_table = block_table;
+  a.max_pages = max_pages;
+  a.n_tok = n_tok;
+  a.n_q = n_q_heads;
+  a.layer = layer;
+  a.n_splits = 1;
+  a.scale_log2 = 1.4426950408889634f / sqrtf((float)kv->head_dim);
+  a.kv = geom_of(kv);
+  CU(launch_attention_prefill_tc(a, variant, (cudaStream_t)st));
+  return QIE_OK;
+}
+
 // ---------------------------------------------------------------- driver level
 void qie_engine_opts_default(qie_engine_opts* o) {
   memset(o, 0, sizeof(*o));

@@ -213,7 +213,12 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
       a.n_splits = 1;
       a.scale_log2 = 1.4426950408889634f / sqrtf((float)hd);
       a.kv = e->kv;
-      QIE_TRY(KK_ATTN, launch_attention_prefill_fast(a, st));
+      // head_dim 128 and at least one full 128-row query tile: tcgen05 / TMEM kernel (QIE_ATTN_TC=0 keeps mma.sync)
+      static const bool tc_on = [] { const char* v = getenv("QIE_ATTN_TC"); return !(v && v[0] == '0'); }();
+      if (tc_on && hd == 128 && n >= 128)
+        QIE_TRY(KK_ATTN, launch_attention_prefill_tc(a, 0, st));
+      else
+        QIE_TRY(KK_ATTN, launch_attention_prefill_fast(a, st));
     } else {
       AttnArgs a{};
       a.q = e->q;

@@ -114,6 +114,8 @@ cudaError_t launch_attention_decode_fast(const FastAttnArgs& a, cudaStream_t st)
 // causal tiled attention for prefill rows (attn_prefill_fast.cu): rows are consecutive positions
 // pos[0]+t of one sequence (slot[0]); n_splits / ws_* unused
 cudaError_t launch_attention_prefill_fast(const FastAttnArgs& a, cudaStream_t st);
+// the same on tcgen05 / TMEM (attn_prefill_tc.cu), head_dim 128; lbo_sbo_swap: descriptor probe, 0 in production
+cudaError_t launch_attention_prefill_tc(const FastAttnArgs& a, int lbo_sbo_swap, cudaStream_t st);
 
 // tcgen05 GEMM (fast numerics, M > 8)
 struct TensorMap2D {

@@ -125,3 +125,10 @@ def launch_attn_prefill_fast(Q, out, pool, layer, pos, slot, n_q_heads):
     check(_lib.lib().qie_attention_prefill_fast(C.byref(pool.view), layer, _p(Q), _p(out), _p(pos), _p(slot),
                                                 _p(pool.block_table), pool.max_pages, pos.numel(), n_q_heads,
                                                 _st()))
+
+
+def launch_attn_prefill_tc(Q, out, pool, layer, pos, slot, n_q_heads, variant=0):
+    """the same on tcgen05 / TMEM (head_dim 128)."""
+    check(_lib.lib().qie_attention_prefill_tc(C.byref(pool.view), layer, _p(Q), _p(out), _p(pos), _p(slot),
+                                              _p(pool.block_table), pool.max_pages, pos.numel(), n_q_heads, variant,
+                                              _st()))

@@ -114,6 +114,35 @@ def test_prefill_attention_vs_reference_order_attention(layers, hd, n_q, n_kv, p
     assert rel_err(got, want) < TOL_BF16
 
 
+@pytest.mark.parametrize("n_q,n_kv,prefix,T", [(12, 2, 0, 257), (28, 4, 130, 70), (2, 1, 64, 128), (4, 2, 77, 1000),
+                                                (2, 2, 0, 1), (6, 1, 300, 129)])
+def test_prefill_attention_tcgen05_vs_reference_order_attention(layers, n_q, n_kv, prefix, T):
+    """the tcgen05 / TMEM prefill attention (head_dim 128: S and P V on the 5th-gen tensor cores, softmax over
+    tcgen05.ld) against the reference-order kernel: ragged last tile, cache prefix, GQA groups, one-row chunk."""
+    hd = 128
+    rng = np.random.default_rng(n_q * 31 + prefix + T)
+    Dq, Dkv = n_q * hd, n_kv * hd
+    n_layers, layer, ps = 2, 1, 16
+    total = prefix + T
+    pool = layers.KvPool(n_pages=2 * ((total + ps - 1) // ps + 1), page_size=ps, n_layers=n_layers, n_kv_heads=n_kv,
+                         head_dim=hd, max_seqs=2)
+    for b, n in ((0, 9), (1, total)):
+        K, V = rand_bf16(rng, (n, Dkv), 1.0), rand_bf16(rng, (n, Dkv), 1.0)
+        pos = torch.arange(n, dtype=torch.int32, device="cuda")
+        pool.store(layer, to_dev(K), to_dev(V), pos, torch.full((n,), b, dtype=torch.int32, device="cuda"))
+    Q = to_dev(rand_bf16(rng, (T, Dq), 1.0))
+    pos = torch.arange(prefix, total, dtype=torch.int32, device="cuda")
+    slot = torch.full((T,), 1, dtype=torch.int32, device="cuda")
+    o_ref = torch.zeros_like(Q)
+    o_new = torch.full_like(Q, float("nan"))
+    layers.launch_attn(Q, o_ref, pool, layer, pos, slot, n_q)
+    layers.launch_attn_prefill_tc(Q, o_new, pool, layer, pos, slot, n_q)
+    torch.cuda.synchronize()
+    got, want = to_host(o_new), to_host(o_ref)
+    assert not np.isnan(bf16_to_f32(got)).any()
+    assert rel_err(got, want) < TOL_BF16
+
+
 def test_fast_prefill_engine_long_prompt():
     """whole prefill, 300-token prompt in chunks of 128 rows (tcgen05 GEMMs + tiled causal attention):
     logits and per-layer activations of the last chunk within tolerance of the reference-order engine."""
