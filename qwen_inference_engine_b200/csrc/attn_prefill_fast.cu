@@ -59,8 +59,8 @@ __global__ void __launch_bounds__(128, 3) attn_prefill_fast_kernel(FastAttnArgs 
   constexpr int NT = HD / 8;   // n-tiles of P V
   constexpr int SN = PF_KT / 8;  // n-tiles of S per warp (8)
 
-  const int qt = gridDim.x - 1 - blockIdx.x;  // heavy tiles first
-  const int h = blockIdx.y;
+  const int qt = gridDim.y - 1 - blockIdx.y;  // heavy tiles first, all heads of a tile before the next tile
+  const int h = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, c = lane & 3;
   const int G = a.n_q / a.kv.n_kv;
@@ -271,7 +271,7 @@ static cudaError_t launch_pf_hd(const FastAttnArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     set = true;
   }
-  dim3 grid((a.n_tok + PF_QT - 1) / PF_QT, a.n_q);
+  dim3 grid(a.n_q, (a.n_tok + PF_QT - 1) / PF_QT);
   (void)launch_k(attn_prefill_fast_kernel<HD>, grid, dim3(128), smem, st, a);
   return cudaGetLastError();
 }

@@ -73,8 +73,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // K-major operand, SWIZZLE_128B, 8-row atoms 1024 bytes apart (same encoding as gemm_tcgen05.cu)
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -122,7 +122,9 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
   int* s_pages = reinterpret_cast<int*>(sg + SM_PAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = gridDim.x - 1 - blockIdx.x, h = blockIdx.y;
+  // CTAs are handed out x-fastest: all heads of the longest query tile first, then the next tile (longest-processing-
+  // time order over the SMs; tile-fastest order left a 32-tile CTA for the end: makespan 61 vs 48 tile units at T = 4096)
+  const int qt = gridDim.y - 1 - blockIdx.y, h = blockIdx.x;
   const int G = a.n_q / a.kv.n_kv, kvh = h / G;
   const int t0 = qt * TQ, n_rows = min(TQ, a.n_tok - t0);
   const int psz = a.kv.page_size;
@@ -227,11 +229,15 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
         mbar_wait_(bar_o, ph ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-        for (int c0 = 0; c0 < HDX; c0 += 32) {
-          uint32_t r[32];
+        for (int c0 = 0; c0 < HDX; c0 += 64) {  // two TMEM loads in flight per wait
+          uint32_t r[32], r2[32];
           tmem_ld32(lane_addr + 128 + c0, r);
+          tmem_ld32(lane_addr + 128 + c0 + 32, r2);
+          tmem_wait_ld();
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[c0 + j] = fmaf(o[c0 + j], corr, __uint_as_float(r[j]));
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[c0 + 32 + j] = fmaf(o[c0 + 32 + j], corr, __uint_as_float(r2[j]));
         }
       }
       mbar_wait_(bar_s, ph);
@@ -240,15 +246,19 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
       const bool need_mask = p0 + TK - 1 > my_pos;
       float mx = -INFINITY;
 #pragma unroll
-      for (int c0 = 0; c0 < TK; c0 += 32) {
-        uint32_t r[32];
+      for (int c0 = 0; c0 < TK; c0 += 64) {
+        uint32_t r[32], r2[32];
         tmem_ld32(lane_addr + c0, r);
+        tmem_ld32(lane_addr + c0 + 32, r2);
+        tmem_wait_ld();
         if (need_mask) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) mx = fmaxf(mx, p0 + c0 + j > my_pos ? -INFINITY : __uint_as_float(r[j]));
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, p0 + c0 + 32 + j > my_pos ? -INFINITY : __uint_as_float(r2[j]));
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r2[j])));
         }
       }
       const float m_new = fmaxf(m_run, mx);
@@ -260,6 +270,7 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
       for (int c0 = 0; c0 < TK; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(lane_addr + c0, r);
+        tmem_wait_ld();
         uint32_t pk[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
@@ -302,11 +313,15 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
     mbar_wait_(bar_o, (uint32_t)((n_tiles - 1) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-    for (int c0 = 0; c0 < HDX; c0 += 32) {
-      uint32_t r[32];
+    for (int c0 = 0; c0 < HDX; c0 += 64) {
+      uint32_t r[32], r2[32];
       tmem_ld32(lane_addr + 128 + c0, r);
+      tmem_ld32(lane_addr + 128 + c0 + 32, r2);
+      tmem_wait_ld();
 #pragma unroll
       for (int j = 0; j < 32; ++j) o[c0 + j] = fmaf(o[c0 + j], corr, __uint_as_float(r[j]));
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[c0 + 32 + j] = fmaf(o[c0 + 32 + j], corr, __uint_as_float(r2[j]));
     }
   }
   if (warp < 4 && row < n_rows) {
@@ -340,7 +355,7 @@ cudaError_t launch_attention_prefill_tc(const FastAttnArgs& a, int lbo_sbo_swap,
     if (e != cudaSuccess) return e;
     set = true;
   }
-  dim3 grid((a.n_tok + TQ - 1) / TQ, a.n_q);
+  dim3 grid(a.n_q, (a.n_tok + TQ - 1) / TQ);
   (void)launch_k(attn_prefill_tc_kernel, grid, dim3(NTHR), (size_t)SM_TOTAL, st, a, lbo_sbo_swap);
   return cudaGetLastError();
 }
