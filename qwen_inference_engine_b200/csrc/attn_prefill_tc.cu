@@ -30,14 +30,17 @@ constexpr int TILE_B = 2 * BLK;              // a 128 x 128 bf16 operand = 32 Ki
 constexpr int SM_Q = 0, SM_P = TILE_B, SM_K0 = 2 * TILE_B;  // Q | P | K[2] | V[2]
 constexpr int SM_V0 = SM_K0 + 2 * TILE_B;
 constexpr int SM_BAR = SM_V0 + 2 * TILE_B;   // mbarriers + tmem slot
-constexpr int SM_PAGES = SM_BAR + 64;
+constexpr int SM_X = SM_BAR + 64;          // float xmax[2][128], xsum[2][128]: exchange between the two threads of a row
+constexpr int SM_PAGES = SM_X + 2048;
 constexpr int MAXP = 2048;
 constexpr int SM_TOTAL = SM_PAGES + MAXP * 4 + 1024;
-constexpr int NTHR = 160;
+constexpr int NSOFT = 256;                  // 8 softmax warps: two threads per query row (keys / head-dim halves)
+constexpr int NTHR = NSOFT + 32;            // + the copy/MMA warp
 
 __device__ __forceinline__ void mbar_init_(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+// (pure polling with test_wait instead of try_wait was measured: no difference)
 __device__ __forceinline__ void mbar_wait_(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   const long long t0 = clock64();
@@ -120,8 +123,11 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
   unsigned char* sg = smem_raw + (s0 - smem_u32(smem_raw));
   const uint32_t bar_s = s0 + SM_BAR, bar_o = bar_s + 8, slot = bar_s + 16;
   int* s_pages = reinterpret_cast<int*>(sg + SM_PAGES);
+  float* xmax = reinterpret_cast<float*>(sg + SM_X);  // [2][128]
+  float* xsum = xmax + 256;                            // [2][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int MMA_WARP = NSOFT / 32;
   // CTAs are handed out x-fastest: all heads of the longest query tile first, then the next tile (longest-processing-
   // time order over the SMs; tile-fastest order left a 32-tile CTA for the end: makespan 61 vs 48 tile units at T = 4096)
   const int qt = gridDim.y - 1 - blockIdx.y, h = blockIdx.x;
@@ -139,20 +145,19 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
     mbar_init_(bar_o, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   const int n_pg = min(MAXP, (kv_len - 1) / psz + 1);
   for (int i = threadIdx.x; i < n_pg; i += NTHR) s_pages[i] = bt[i];
-  // Q tile
-  for (int i = threadIdx.x; i < TQ * 16; i += NTHR) {
+  for (int i = threadIdx.x; i < TQ * 16; i += NTHR) {  // Q tile
     const int r = i >> 4, ch = i & 15;
     const int t = t0 + min(r, n_rows - 1);
     cp_async16(s0 + SM_Q + tile_off(r, ch), a.q + (size_t)t * Dq + (size_t)h * HDX + ch * 8);
   }
   cp_async_commit();
-  cp_async_wait<0>();  // Q
+  cp_async_wait<0>();
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
 
   const size_t v_off = a.kv.kv_stride(), page_stride = a.kv.page_stride();
   const bf16* kv_base = a.kv.chunk(0, a.layer, 0, kvh);
-  // 160 threads = 10 rows x 16 chunk columns per pass: a thread always copies chunk column `lch` of rows lr0 + 10 k
+  // 288 threads = 18 rows x 16 chunk columns per pass: a thread always copies chunk column `lch` of rows lr0 + 18 k
   // (one warp doing all copies put ~3k instructions in front of every S product: measured 1.8x slower)
   const int lch = threadIdx.x & 15, lr0 = threadIdx.x >> 4;
   const int psz_shift = (psz & (psz - 1)) == 0 ? __ffs(psz) - 1 : -1;
@@ -171,7 +176,7 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
     const uint32_t kb = s0 + SM_K0 + buf * TILE_B, vb = s0 + SM_V0 + buf * TILE_B;
     const int p0 = tile * TK;
 #pragma unroll 4
-    for (int r = lr0; r < TK; r += 10) {
+    for (int r = lr0; r < TK; r += NTHR / 16) {
       const int p = min(p0 + r, kv_len - 1);
       const int pi = psz_shift >= 0 ? (p >> psz_shift) : p / psz;
       const int po = p - pi * psz;
@@ -185,18 +190,33 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
   };
   load_tile(0, 0);
 
-  const uint32_t lbo = lbo_sbo_swap ? 1024u : (uint32_t)BLK, sbo = lbo_sbo_swap ? (uint32_t)BLK : 1024u;
+  // Where the time goes (T = 4096, 12 heads, 171 us; probe builds that skip one part each): both MMA chains 35 us,
+  // the exp + bf16-pack pass 53 us (16 384 ex2 + 8 192 cvt per tile on the 16-lane XU pipe), everything else --
+  // tile copies, TMEM loads, row max, O fold, P stores, barriers, CTA prologue/epilogue -- 94 us.  An MN-major V
+  // descriptor costs the same as a K-major one.
+  const uint32_t lbo = (lbo_sbo_swap & 1) ? 1024u : (uint32_t)BLK, sbo = (lbo_sbo_swap & 1) ? (uint32_t)BLK : 1024u;
   constexpr uint32_t ID_S = idesc_(128, 128, false), ID_O = idesc_(128, 128, true);
   const float sl2 = a.scale_log2;
-  const int row = (warp & 3) * 32 + lane;           // softmax thread's query row (warps 0-3)
-  const int my_pos = pos_first + row;               // last visible key of this row
+  // softmax thread: query row `row` (= TMEM lane), half `hf`: keys [64 hf, 64 hf + 64) of every tile for the softmax,
+  // head-dim columns [64 hf, 64 hf + 64) of O.  Warps w and w + 4 share a TMEM lane quarter (warp % 4).
+  const bool soft = warp < MMA_WARP;
+  const int row = (warp & 3) * 32 + lane, hf = (warp >> 2) & 1;
+  const int my_pos = pos_first + row;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  float o[HDX];
+  float o[64];
   float m_run = -INFINITY, l_run = 0.f, corr = 1.f;
-  if (warp < 4) {
 #pragma unroll
-    for (int i = 0; i < HDX; ++i) o[i] = 0.f;
-  }
+  for (int i = 0; i < 64; ++i) o[i] = 0.f;
+  auto fold_o = [&]() {  // o = o * corr + (P V of the last tile), this thread's 64 head-dim columns
+    uint32_t r[32], r2[32];
+    tmem_ld32(lane_addr + 128 + 64 * hf, r);
+    tmem_ld32(lane_addr + 128 + 64 * hf + 32, r2);
+    tmem_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = fmaf(o[j], corr, __uint_as_float(r[j]));
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[32 + j] = fmaf(o[32 + j], corr, __uint_as_float(r2[j]));
+  };
 
   for (int it = 0; it < n_tiles; ++it) {
     const int buf = it & 1;
@@ -213,7 +233,7 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
     const uint32_t kb = s0 + SM_K0 + buf * TILE_B, vb = s0 + SM_V0 + buf * TILE_B;
     const uint32_t ph = it & 1;
     // ---- S = Q K^T
-    if (warp == 4 && lane == 0) {
+    if (warp == MMA_WARP && lane == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int kk = 0; kk < HDX / 16; ++kk) {
@@ -222,82 +242,58 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
       }
       umma_commit_(bar_s);
     }
-    const int p0 = it * TK;
-    if (warp < 4) {
-      if (it > 0) {
-        // fold the previous tile's P V product into the fp32 row while the tensor core works on this tile's S
-        mbar_wait_(bar_o, ph ^ 1);
+    const int p0 = it * TK + 64 * hf;  // first key of this thread's half
+    if (soft) {
+      if (it > 0) {  // fold the previous tile's P V product while the tensor core works on this tile's S
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-        for (int c0 = 0; c0 < HDX; c0 += 64) {  // two TMEM loads in flight per wait
-          uint32_t r[32], r2[32];
-          tmem_ld32(lane_addr + 128 + c0, r);
-          tmem_ld32(lane_addr + 128 + c0 + 32, r2);
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) o[c0 + j] = fmaf(o[c0 + j], corr, __uint_as_float(r[j]));
-#pragma unroll
-          for (int j = 0; j < 32; ++j) o[c0 + 32 + j] = fmaf(o[c0 + 32 + j], corr, __uint_as_float(r2[j]));
-        }
+        fold_o();
       }
       mbar_wait_(bar_s, ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // ---- softmax of this thread's row: pass 1 max, pass 2 exp + P
-      const bool need_mask = p0 + TK - 1 > my_pos;
+      // ---- this thread's 64 scores stay in registers between the max and the exp pass
+      uint32_t r[32], r2[32];
+      tmem_ld32(lane_addr + 64 * hf, r);
+      tmem_ld32(lane_addr + 64 * hf + 32, r2);
+      tmem_wait_ld();
+      const bool need_mask = p0 + 63 > my_pos;
       float mx = -INFINITY;
+      if (need_mask) {
 #pragma unroll
-      for (int c0 = 0; c0 < TK; c0 += 64) {
-        uint32_t r[32], r2[32];
-        tmem_ld32(lane_addr + c0, r);
-        tmem_ld32(lane_addr + c0 + 32, r2);
-        tmem_wait_ld();
-        if (need_mask) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, p0 + c0 + j > my_pos ? -INFINITY : __uint_as_float(r[j]));
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, p0 + c0 + 32 + j > my_pos ? -INFINITY : __uint_as_float(r2[j]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r2[j])));
+        for (int j = 0; j < 32; ++j) {
+          if (p0 + j > my_pos) r[j] = 0xff800000u;       // -inf
+          if (p0 + 32 + j > my_pos) r2[j] = 0xff800000u;
         }
       }
-      const float m_new = fmaxf(m_run, mx);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r2[j])));
+      xmax[hf * 128 + row] = mx;
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the two halves of every row meet
+      const float m_new = fmaxf(m_run, fmaxf(mx, xmax[(hf ^ 1) * 128 + row]));
       corr = ex2((m_run - m_new) * sl2);
       m_run = m_new;
       const float nms = -m_new * sl2;
       float rs = 0.f;
+      uint32_t pk[32];
 #pragma unroll
-      for (int c0 = 0; c0 < TK; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(lane_addr + c0, r);
-        tmem_wait_ld();
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float v0 = __uint_as_float(r[j]), v1 = __uint_as_float(r[j + 1]);
-          if (need_mask) {
-            if (p0 + c0 + j > my_pos) v0 = -INFINITY;
-            if (p0 + c0 + j + 1 > my_pos) v1 = -INFINITY;
-          }
-          const float e0 = ex2(fmaf(v0, sl2, nms)), e1 = ex2(fmaf(v1, sl2, nms));
-          rs += e0 + e1;
-          pk[j >> 1] = pack2(f2bf(e0), f2bf(e1));
-        }
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {  // 8 keys = one 16-byte chunk of the P row
-          const int ch = (c0 >> 3) + q4;
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s0 + SM_P + tile_off(row, ch)), "r"(pk[4 * q4]),
-                       "r"(pk[4 * q4 + 1]), "r"(pk[4 * q4 + 2]), "r"(pk[4 * q4 + 3])
-                       : "memory");
-        }
+      for (int j = 0; j < 32; j += 2) {
+        const float e0 = ex2(fmaf(__uint_as_float(r[j]), sl2, nms)), e1 = ex2(fmaf(__uint_as_float(r[j + 1]), sl2, nms));
+        const float e2 = ex2(fmaf(__uint_as_float(r2[j]), sl2, nms)), e3 = ex2(fmaf(__uint_as_float(r2[j + 1]), sl2, nms));
+        rs += (e0 + e1) + (e2 + e3);
+        pk[j >> 1] = pack2(f2bf(e0), f2bf(e1));
+        pk[16 + (j >> 1)] = pack2(f2bf(e2), f2bf(e3));
       }
-      l_run = l_run * corr + rs;
+#pragma unroll
+      for (int q8 = 0; q8 < 8; ++q8)  // 8 chunks of 8 keys = this half's column block of the P row
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s0 + SM_P + tile_off(row, 8 * hf + q8)), "r"(pk[4 * q8]),
+                     "r"(pk[4 * q8 + 1]), "r"(pk[4 * q8 + 2]), "r"(pk[4 * q8 + 3])
+                     : "memory");
+      l_run = l_run * corr + rs;  // partial sum of this half; the halves are added once at the end
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P (generic stores) -> tensor core
     }
     __syncthreads();
     // ---- O_t = P V
-    if (warp == 4 && lane == 0) {
+    if (warp == MMA_WARP && lane == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int kk = 0; kk < TK / 16; ++kk) {
@@ -307,39 +303,30 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
       }
       umma_commit_(bar_o);
     }
-    __syncthreads();  // K/V buffer and P are rewritten by the next iteration
   }
-  if (warp < 4) {
+  if (soft) {
     mbar_wait_(bar_o, (uint32_t)((n_tiles - 1) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    fold_o();
+    xsum[hf * 128 + row] = l_run;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (row < n_rows) {
+      const float inv = 1.f / (l_run + xsum[(hf ^ 1) * 128 + row]);
+      bf16* dst = a.out + (size_t)(t0 + row) * Dq + (size_t)h * HDX + 64 * hf;
 #pragma unroll
-    for (int c0 = 0; c0 < HDX; c0 += 64) {
-      uint32_t r[32], r2[32];
-      tmem_ld32(lane_addr + 128 + c0, r);
-      tmem_ld32(lane_addr + 128 + c0 + 32, r2);
-      tmem_wait_ld();
-#pragma unroll
-      for (int j = 0; j < 32; ++j) o[c0 + j] = fmaf(o[c0 + j], corr, __uint_as_float(r[j]));
-#pragma unroll
-      for (int j = 0; j < 32; ++j) o[c0 + 32 + j] = fmaf(o[c0 + 32 + j], corr, __uint_as_float(r2[j]));
-    }
-  }
-  if (warp < 4 && row < n_rows) {
-    const float inv = 1.f / l_run;
-    bf16* dst = a.out + (size_t)(t0 + row) * Dq + (size_t)h * HDX;
-#pragma unroll
-    for (int c = 0; c < HDX; c += 8) {
-      uint4 v;
-      v.x = pack2(f2bf(o[c] * inv), f2bf(o[c + 1] * inv));
-      v.y = pack2(f2bf(o[c + 2] * inv), f2bf(o[c + 3] * inv));
-      v.z = pack2(f2bf(o[c + 4] * inv), f2bf(o[c + 5] * inv));
-      v.w = pack2(f2bf(o[c + 6] * inv), f2bf(o[c + 7] * inv));
-      *reinterpret_cast<uint4*>(dst + c) = v;
+      for (int c = 0; c < 64; c += 8) {
+        uint4 v;
+        v.x = pack2(f2bf(o[c] * inv), f2bf(o[c + 1] * inv));
+        v.y = pack2(f2bf(o[c + 2] * inv), f2bf(o[c + 3] * inv));
+        v.z = pack2(f2bf(o[c + 4] * inv), f2bf(o[c + 5] * inv));
+        v.w = pack2(f2bf(o[c + 6] * inv), f2bf(o[c + 7] * inv));
+        *reinterpret_cast<uint4*>(dst + c) = v;
+      }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
   }

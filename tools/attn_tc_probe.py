@@ -56,3 +56,4 @@ if __name__ == "__main__":
     v = int(sys.argv[1]) if len(sys.argv) > 1 else 0
     run(1000, 77, 4, 2, v)
     run(4096, 0, 12, 2, v, time_it=True)
+    run(4096, 0, 28, 4, v, time_it=True)
