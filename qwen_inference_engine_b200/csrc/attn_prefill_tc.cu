@@ -220,14 +220,7 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
 
   for (int it = 0; it < n_tiles; ++it) {
     const int buf = it & 1;
-    // the buffer tile it+1 goes into was read by the P V product of tile it-1: wait for that MMA first
-    if (it > 0) mbar_wait_(bar_o, (uint32_t)((it - 1) & 1));
-    if (it + 1 < n_tiles) {
-      load_tile(it + 1, buf ^ 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
+    cp_async_wait<0>();  // tile it (requested one iteration ago)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async (generic proxy) data -> tensor core (async proxy)
     __syncthreads();
     const uint32_t kb = s0 + SM_K0 + buf * TILE_B, vb = s0 + SM_V0 + buf * TILE_B;
@@ -242,6 +235,10 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
       }
       umma_commit_(bar_s);
     }
+    // Behind the S product (queued right after the previous tile's P V in the tensor pipe): the buffer tile it+1 goes
+    // into was read by the P V product of tile it-1, so wait for that MMA, then request the copies.
+    if (it > 0) mbar_wait_(bar_o, (uint32_t)((it - 1) & 1));
+    if (it + 1 < n_tiles) load_tile(it + 1, buf ^ 1);
     const int p0 = it * TK + 64 * hf;  // first key of this thread's half
     if (soft) {
       if (it > 0) {  // fold the previous tile's P V product while the tensor core works on this tile's S
