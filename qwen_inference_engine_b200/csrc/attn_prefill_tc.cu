@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
 #pragma unroll
       for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r2[j])));
       xmax[hf * 128 + row] = mx;
-      asm volatile("bar.sync 1, 256;" ::: "memory");  // the two halves of every row meet
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");  // the two warps that share these 32 rows meet
       const float m_new = fmaxf(m_run, fmaxf(mx, xmax[(hf ^ 1) * 128 + row]));
       corr = ex2((m_run - m_new) * sl2);
       m_run = m_new;
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     fold_o();
     xsum[hf * 128 + row] = l_run;
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");
     if (row < n_rows) {
       const float inv = 1.f / (l_run + xsum[(hf ^ 1) * 128 + row]);
       bf16* dst = a.out + (size_t)(t0 + row) * Dq + (size_t)h * HDX + 64 * hf;
