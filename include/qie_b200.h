@@ -41,7 +41,7 @@ typedef uint16_t qie_bf16;     /* raw __nv_bfloat16 bits */
 
 const char* qie_last_error(void);
 /* ABI version; bumped on any signature change. */
-int qie_abi_version(void); /* currently 3 */
+int qie_abi_version(void); /* currently 4 */
 
 /* ------------------------------------------------------------------------------------
  * (1) operator level.  All pointers are DEVICE pointers unless named h_*.
@@ -109,6 +109,12 @@ int qie_attention(const qie_kv_view* kv, int layer, const qie_bf16* Q, qie_bf16*
  * out_tokens: device int[n_rows]. seeds: per-row seed = seed + row*seed_stride. */
 int qie_sample_topk(const qie_bf16* logits, int* out_tokens, int n_rows, size_t vocab, float temperature, int k,
                     uint64_t seed, uint64_t seed_stride, qie_stream st);
+
+/* The same with the reference's full RNG addressing: sample_topk_bf16's last argument is handed to the kernel as
+ * the cuRAND SUBSEQUENCE -- curand_init(seed, subsequence, 0) -- helpers.cuh:157-166, logit_decode.cu:256-257
+ * (llm() always passes 0 and folds the step into the seed, qwen_main.cu:241,388). */
+int qie_sample_topk_subseq(const qie_bf16* logits, int* out_tokens, int n_rows, size_t vocab, float temperature, int k,
+                           uint64_t seed, uint64_t seed_stride, uint64_t subsequence, qie_stream st);
 
 /* FAST-numerics operators (same contracts as qie_matmul / qie_attention, results within
  * the 1e-2 bf16 tolerance instead of bit-exact): tcgen05/TMEM/TMA GEMM with split-K, and
@@ -243,6 +249,14 @@ int qie_seq_swap_out(qie_engine* e, int seq);
 int qie_seq_swap_in(qie_engine* e, int seq);
 int qie_kv_pages_free(const qie_engine* e);
 
+/* Cache rows [pos0, pos0+n) of a sequence <-> HOST buffers in the REFERENCE's page layout
+ * [position][layer][n_kv*head_dim] (iengine.cu:352; include_cuda.cu:165-279 writes element
+ * ((pos % page_size)*L + layer)*Dkv of a page): a read with n = page_size is one reference page.
+ * Write grows the sequence (pages are taken from the pool) -- the host-side counterpart of
+ * kv_copy_layer_to_cache_prefill for callers that own K/V rows (page-list import, tests). */
+int qie_seq_kv_read(qie_engine* e, int seq, int pos0, int n, qie_bf16* h_K, qie_bf16* h_V);
+int qie_seq_kv_write(qie_engine* e, int seq, int pos0, int n, const qie_bf16* h_K, const qie_bf16* h_V);
+
 /* llm() with state == prefill, qwen_main.cu:74-247. h_ids: HOST int32[n]. The sampled
  * token is written to *h_token (HOST). */
 int qie_prefill(qie_engine* e, int seq, const int32_t* h_ids, int n, int32_t* h_token);
@@ -315,6 +329,11 @@ int qie_engine_set_int(qie_engine* e, const char* key, long value);
 int qie_decode_uses_mega(const qie_engine* e, int n_rows, int kv_len);
 long qie_mega_prof_read(qie_engine* e, uint64_t* h_out, size_t max_values);
 long qie_engine_read_activation(qie_engine* e, const char* name, void* h_out, size_t max_bytes);
+/* Layer-isolation parity hook of the per-operator forward: qie_engine_set_int keys "layer_first" / "layer_count"
+ * (run only these layers, no final norm / lm_head; 0 = the whole model) and "inject_x" (1: the residual stream is
+ * what qie_engine_write_activation(e, "x", rows, bytes) stored, the embedding gather is skipped).  Lets a test feed
+ * layer l of one numerics mode the layer input of another and compare ONE layer's output (north-star 1e-2 bar). */
+long qie_engine_write_activation(qie_engine* e, const char* name, const void* h_in, size_t bytes);
 
 #ifdef __cplusplus
 }

@@ -372,7 +372,9 @@ int ref_seq_fake_context(void* h, int n_ctx) {
   ref_seq* s = (ref_seq*)h;
   ModelBuffers* b = &s->buf;
   seq_alloc(s, 1);
-  int pages_required = ((n_ctx + s->page_size - 1) / s->page_size) + 1;
+  // room for 64 decoded tokens behind the context: kv_copy_layer_to_cache_decode's allocate-on-demand path
+  // (include_cuda.cu:248-261) works but prints "Error: Page N not allocated"; a timed run should not take it
+  int pages_required = ((n_ctx + 64 + s->page_size - 1) / s->page_size) + 1;
   size_t elems = (size_t)s->page_size * b->number_of_layers * b->hidden_dim_kv;
   s->pages = (page_table*)ref_pages_create(pages_required, elems);
   b->k_cache = s->pages->k_page_ptr;

@@ -75,6 +75,7 @@ def lib():
         "qie_kv_store": (i32, [C.POINTER(KvView), i32, vp, vp, vp, vp, vp, i32, i32, vp]),
         "qie_attention": (i32, [C.POINTER(KvView), i32, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
         "qie_sample_topk": (i32, [vp, vp, i32, sz, f32, i32, u64, u64, vp]),
+        "qie_sample_topk_subseq": (i32, [vp, vp, i32, sz, f32, i32, u64, u64, u64, vp]),
         "qie_matmul_fast": (i32, [vp, vp, vp, i32, i32, i32, vp]),
         "qie_attention_prefill_tc": (i32, [C.POINTER(KvView), i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "qie_attention_prefill_fast": (i32, [C.POINTER(KvView), i32, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
@@ -116,12 +117,15 @@ def lib():
         "qie_capture_read": (C.c_long, [vp, C.c_char_p, i32, vp, sz]),
         "qie_launch_count": (C.c_long, [vp]),
         "qie_seq_fill_synthetic": (i32, [vp, i32, i32, u64]),
+        "qie_seq_kv_read": (i32, [vp, i32, i32, i32, vp, vp]),
+        "qie_seq_kv_write": (i32, [vp, i32, i32, i32, vp, vp]),
         "qie_decode_step_profile": (i32, [vp, vp, vp, i32, vp, vp, i32]),
         "qie_kernel_kind_name": (C.c_char_p, [i32]),
         "qie_engine_set_int": (i32, [vp, C.c_char_p, C.c_long]),
         "qie_decode_uses_mega": (i32, [vp, i32, i32]),
         "qie_mega_prof_read": (C.c_long, [vp, vp, sz]),
         "qie_engine_read_activation": (C.c_long, [vp, C.c_char_p, vp, sz]),
+        "qie_engine_write_activation": (C.c_long, [vp, C.c_char_p, vp, sz]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)

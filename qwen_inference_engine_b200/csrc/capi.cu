@@ -32,7 +32,7 @@ static int cuda_fail(cudaError_t e, const char* what) {
 extern "C" {
 
 const char* qie_last_error(void) { return g_err; }
-int qie_abi_version(void) { return 3; }
+int qie_abi_version(void) { return 4; }
 
 // ---------------------------------------------------------------- operator level
 int qie_embedding(qie_bf16* out, const qie_bf16* table, const int* ids, size_t hidden, size_t n_tok, qie_stream st) {
@@ -141,6 +141,13 @@ int qie_sample_topk(const qie_bf16* logits, int* out_tokens, int n_rows, size_t 
                     uint64_t seed, uint64_t seed_stride, qie_stream st) {
   CU(launch_sample_topk((const bf16*)logits, out_tokens, n_rows, vocab, temperature, k, seed, seed_stride, nullptr,
                         (cudaStream_t)st));
+  return QIE_OK;
+}
+
+int qie_sample_topk_subseq(const qie_bf16* logits, int* out_tokens, int n_rows, size_t vocab, float temperature, int k,
+                           uint64_t seed, uint64_t seed_stride, uint64_t subsequence, qie_stream st) {
+  CU(launch_sample_topk((const bf16*)logits, out_tokens, n_rows, vocab, temperature, k, seed, seed_stride, nullptr,
+                        (cudaStream_t)st, subsequence));
   return QIE_OK;
 }
 
@@ -1158,6 +1165,60 @@ int qie_seq_swap_in(qie_engine* e, int seq) {
   return QIE_OK;
 }
 
+// Cache rows of one sequence <-> HOST memory in the REFERENCE's page layout [position][layer][kv_dim]
+// (iengine.cu:352, include_cuda.cu:165-279: element offset ((pos % page_size) * L + layer) * Dkv inside a page), so a
+// reference page of page_size positions starting at pos0 is exactly the buffer of a read with n = page_size.
+// Pages travel whole (page_stride elements, one copy each); the re-layout happens on the host.
+static int seq_kv_copy(qie_engine* e, int seq, int pos0, int n, qie_bf16* h_K, qie_bf16* h_V, bool write) {
+  int rc = check_seq(e, seq);
+  if (rc) return rc;
+  if (n <= 0 || pos0 < 0 || !h_K || !h_V) return fail(QIE_EINVAL, "seq_kv: bad range or null buffers");
+  Sequence& s = e->seqs[seq];
+  if (s.host_copy) return fail(QIE_ESTATE, "sequence %d is swapped out", seq);
+  CU(cudaSetDevice(e->opts.device));
+  if (write) {
+    rc = ensure_pages(e, seq, pos0 + n);
+    if (rc < 0) return rc;
+    if (rc) CU(push_block_row(e, seq));
+  } else if (pos0 + n > s.len) {
+    return fail(QIE_EINVAL, "seq_kv_read: rows [%d, %d) beyond the sequence length %d", pos0, pos0 + n, s.len);
+  }
+  const KvGeom& g = e->kv;
+  const int ps = g.page_size, L = g.n_layers, nkv = g.n_kv, hd = g.hd, Dkv = nkv * hd;
+  const size_t pe = g.page_stride();
+  std::vector<uint16_t> page(pe);
+  CU(cudaStreamSynchronize(e->stream));
+  for (int pi = pos0 / ps; pi <= (pos0 + n - 1) / ps; ++pi) {
+    uint16_t* dev = reinterpret_cast<uint16_t*>(g.pool) + (size_t)s.pages[pi] * pe;
+    const int lo = std::max(pos0, pi * ps), hi = std::min(pos0 + n, (pi + 1) * ps);
+    if (!write || lo != pi * ps || hi != (pi + 1) * ps) CU(cudaMemcpy(page.data(), dev, pe * 2, cudaMemcpyDeviceToHost));
+    for (int pos = lo; pos < hi; ++pos)
+      for (int l = 0; l < L; ++l)
+        for (int kv = 0; kv < 2; ++kv)
+          for (int h = 0; h < nkv; ++h) {
+            uint16_t* pool_row = page.data() + (size_t)l * g.layer_stride() + (size_t)kv * g.kv_stride() + (size_t)h * g.head_stride() +
+                                 (size_t)(pos - pi * ps) * hd;
+            uint16_t* host_row = (kv ? h_V : h_K) + ((size_t)(pos - pos0) * L + l) * Dkv + (size_t)h * hd;
+            if (write) memcpy(pool_row, host_row, hd * 2);
+            else memcpy(host_row, pool_row, hd * 2);
+          }
+    if (write) CU(cudaMemcpy(dev, page.data(), pe * 2, cudaMemcpyHostToDevice));
+  }
+  if (write && pos0 + n > s.len) {
+    s.len = pos0 + n;
+    if (s.step == 0) s.step = 1;
+  }
+  return QIE_OK;
+}
+
+int qie_seq_kv_read(qie_engine* e, int seq, int pos0, int n, qie_bf16* h_K, qie_bf16* h_V) {
+  return seq_kv_copy(e, seq, pos0, n, h_K, h_V, false);
+}
+
+int qie_seq_kv_write(qie_engine* e, int seq, int pos0, int n, const qie_bf16* h_K, const qie_bf16* h_V) {
+  return seq_kv_copy(e, seq, pos0, n, const_cast<qie_bf16*>(h_K), const_cast<qie_bf16*>(h_V), true);
+}
+
 int qie_seq_fill_synthetic(qie_engine* e, int seq, int n_pos, uint64_t seed) {
   int rc = check_seq(e, seq);
   if (rc) return rc;
@@ -1181,6 +1242,9 @@ int qie_engine_set_int(qie_engine* e, const char* key, long value) {
   if (k == "mega") e->use_mega = value != 0;
   else if (k == "mega_layers_run") e->mega_layers_run = (int)value;
   else if (k == "mega_prof") e->mega_prof_on = value != 0;
+  else if (k == "layer_first") e->layer_first = (int)std::max(0l, value);
+  else if (k == "layer_count") e->layer_count = (int)std::max(0l, value);
+  else if (k == "inject_x") e->inject_x = value != 0;
   else return fail(QIE_EINVAL, "unknown option %s", key);
   // captured graphs bake these choices in
   CU(cudaStreamSynchronize(e->stream));
@@ -1224,6 +1288,17 @@ long qie_engine_read_activation(qie_engine* e, const char* name, void* h_out, si
   bytes = std::min(bytes, max_bytes);
   CU(cudaStreamSynchronize(e->stream));
   CU(cudaMemcpy(h_out, src, bytes, cudaMemcpyDeviceToHost));
+  return (long)bytes;
+}
+
+long qie_engine_write_activation(qie_engine* e, const char* name, const void* h_in, size_t bytes) {
+  if (!e || !name || !h_in) return fail(QIE_EINVAL, "null argument");
+  if (std::string(name) != "x") return fail(QIE_EINVAL, "only the residual stream x can be written");
+  const size_t cap = (size_t)e->opts.max_batch_tokens * e->cfg.hidden * 2;
+  if (bytes > cap) return fail(QIE_EINVAL, "write_activation: %zu bytes > %zu", bytes, cap);
+  CU(cudaSetDevice(e->opts.device));
+  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaMemcpy(e->x, h_in, bytes, cudaMemcpyHostToDevice));
   return (long)bytes;
 }
 

@@ -179,7 +179,8 @@ int sample_topk_bf16(__nv_bfloat16* logits_d, int vocab, float temperature, int 
   int* d_tok = nullptr;
   int h_tok = -1;
   if (cudaMalloc(&d_tok, sizeof(int)) != cudaSuccess) return QIE_ECUDA;
-  int rc = qie_sample_topk(QB(logits_d), d_tok, 1, (size_t)vocab, temperature, topk, seed + (unsigned long long)step, 0, nullptr);
+  // `step` is the cuRAND subsequence in the reference (helpers.cuh:157-166 -> logit_decode.cu:256-257), not a seed offset
+  int rc = qie_sample_topk_subseq(QB(logits_d), d_tok, 1, (size_t)vocab, temperature, topk, seed, 0, (unsigned long long)step, nullptr);
   cudaMemcpy(&h_tok, d_tok, sizeof(int), cudaMemcpyDeviceToHost);
   cudaFree(d_tok);
   return rc == QIE_OK ? h_tok : rc;

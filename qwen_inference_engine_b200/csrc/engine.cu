@@ -122,8 +122,10 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
     return fast ? launch_rmsnorm_fast(x, w, y, H, rows, H, st) : launch_rmsnorm_ref(x, w, y, H, rows, H, st);
   };
 
-  QIE_TRY(KK_EMBED, launch_embedding(e->x, e->embed, e->ids_d, H, n, st));
-  for (int l = 0; l < c.layers; ++l) {
+  if (!e->inject_x) QIE_TRY(KK_EMBED, launch_embedding(e->x, e->embed, e->ids_d, H, n, st));
+  const int l_begin = e->layer_count > 0 ? std::min(e->layer_first, c.layers) : 0;
+  const int l_end = e->layer_count > 0 ? std::min(l_begin + e->layer_count, c.layers) : c.layers;
+  for (int l = l_begin; l < l_end; ++l) {
     const LayerWeights& w = e->L[l];
     QIE_TRY(KK_RMSNORM, rms(e->x, w.in_ln, e->xn, n));
     capture_copy(e, "input_norm", l, e->xn, (size_t)n * H);
@@ -288,7 +290,7 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
     }
     capture_copy(e, "x_out", l, e->x, (size_t)n * H);
   }
-  if (n_out == 0) return cudaSuccess;  // non-final prefill chunk: only the KV cache is needed
+  if (n_out == 0 || e->layer_count > 0) return cudaSuccess;  // non-final prefill chunk / layer-isolation hook: no logits
   // final norm only on the rows that feed lm_head (qwen_main.cu:227-236, :367-372)
   QIE_TRY(KK_RMSNORM, rms(e->x + (size_t)out_row0 * H, e->final_norm, e->xn, n_out));
   if (fast && n_out > 8) {
@@ -468,7 +470,7 @@ cudaError_t forward_rows_tp(qie_engine* e, int n, int max_kv_len, int out_row0, 
 }
 
 bool decode_uses_mega(const qie_engine* e, int n, int max_kv_len) {
-  if (!e->use_mega || e->capture || !e->mega_layers_d) return false;
+  if (!e->use_mega || e->capture || !e->mega_layers_d || e->layer_count > 0 || e->inject_x) return false;
   const qie_config& c = e->cfg;
   if (e->tp.size > 1) {
     // tensor parallel: the persistent kernel runs this rank's shard and exchanges partial sums over NVLink peer

@@ -96,6 +96,11 @@ struct qie_engine {
   unsigned long long* mega_prof_d = nullptr;  // phase timestamps of the last profiled step
   bool mega_prof_on = false;
   int mega_layers_run = 0;           // debug: run only this many layers (no lm_head)
+  // parity hooks of the per-operator forward (tests/test_gpu_layer_isolation.py): run layers [layer_first,
+  // layer_first + layer_count) only (0 = all, then final norm + lm_head) and/or take the residual stream x as
+  // written by qie_engine_write_activation instead of the embedding rows
+  int layer_first = 0, layer_count = 0;
+  bool inject_x = false;
 
   // tensor parallel (opts.tp_size > 1): heads / intermediate / vocabulary sharded, NCCL all-reduce
   qie::TpComm tp;

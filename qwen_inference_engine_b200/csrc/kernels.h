@@ -145,7 +145,8 @@ cudaError_t launch_rmsnorm_fast(const bf16* x, const bf16* w, bf16* y, size_t hi
 
 // sampling (reference tie-break + XORWOW)
 cudaError_t launch_sample_topk(const bf16* logits, int* out_tokens, int n_rows, size_t vocab, float temperature,
-                               int k, uint64_t seed, uint64_t seed_stride, const int* step_ptr, cudaStream_t st);
+                               int k, uint64_t seed, uint64_t seed_stride, const int* step_ptr, cudaStream_t st,
+                               uint64_t subsequence = 0);  // XORWOW subsequence (the reference's last sample_topk_bf16 argument)
 
 // synthetic weights on the device (twin of the host generator)
 cudaError_t launch_synth_fill(bf16* blob, size_t elem_begin, size_t n_elems, uint64_t seed, int kind,

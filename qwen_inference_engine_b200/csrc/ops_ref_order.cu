@@ -434,7 +434,8 @@ cudaError_t launch_attention_ref(const AttnArgs& a, cudaStream_t st) {
 // total order, so the scan can use any number of threads and still pick the same token.
 __global__ void __launch_bounds__(1024) sample_topk_kernel(const bf16* __restrict__ logits, int* __restrict__ out,
                                                             size_t vocab, float temperature, int k, uint64_t seed,
-                                                            uint64_t seed_stride, const int* __restrict__ step_ptr) {
+                                                            uint64_t seed_stride, const int* __restrict__ step_ptr,
+                                                            unsigned long long subsequence) {
   pdl_wait();
   pdl_trigger();
   __shared__ float topk_vals[256];
@@ -534,7 +535,7 @@ __global__ void __launch_bounds__(1024) sample_topk_kernel(const bf16* __restric
     }
     curandState rng;
     unsigned long long sd = seed + (unsigned long long)blockIdx.x * seed_stride + (step_ptr ? (unsigned)step_ptr[blockIdx.x] : 0u);
-    curand_init(sd, 0, 0, &rng);
+    curand_init(sd, subsequence, 0, &rng);  // logit_decode.cu:256-257: (seed, subsequence, offset 0)
     float u = __fmul_rn(curand_uniform(&rng), sum);
     float cum = 0.0f;
     int picked = topk_idxs[actual_k - 1];
@@ -621,7 +622,8 @@ __global__ void greedy_merge_kernel(const Cand* __restrict__ cands, int* __restr
 }
 
 cudaError_t launch_sample_topk(const bf16* logits, int* out_tokens, int n_rows, size_t vocab, float temperature,
-                               int k, uint64_t seed, uint64_t seed_stride, const int* step_ptr, cudaStream_t st) {
+                               int k, uint64_t seed, uint64_t seed_stride, const int* step_ptr, cudaStream_t st,
+                               uint64_t subsequence) {
   if (n_rows == 0) return cudaSuccess;
   if (k == 1 && vocab % 8 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && vocab >= 4096) {
     // candidate scratch per stream (engines of one process run on their own streams); buffers are never freed or
@@ -653,7 +655,8 @@ cudaError_t launch_sample_topk(const bf16* logits, int* out_tokens, int n_rows, 
     (void)launch_k(greedy_merge_kernel, dim3((n_rows + 63) / 64), dim3(64), 0, st, (const Cand*)cands, out_tokens, n_rows);
     return cudaGetLastError();
   }
-  (void)launch_k(sample_topk_kernel, dim3(n_rows), dim3(1024), 0, st, logits, out_tokens, vocab, temperature, k, seed, seed_stride, step_ptr);
+  (void)launch_k(sample_topk_kernel, dim3(n_rows), dim3(1024), 0, st, logits, out_tokens, vocab, temperature, k, seed, seed_stride, step_ptr,
+                 (unsigned long long)subsequence);
   return cudaGetLastError();
 }
 

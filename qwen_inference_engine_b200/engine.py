@@ -209,6 +209,19 @@ class Engine:
         """append n_pos positions of seeded random K/V without running the model (bench only)"""
         check(self._L.qie_seq_fill_synthetic(self._h, seq, n_pos, seed))
 
+    def kv_read(self, seq, pos0, n):
+        """cache rows [pos0, pos0+n) of a sequence as (K, V), each uint16 [n, layers, n_kv*head_dim]
+        -- the reference's page layout [position][layer][kv_dim]"""
+        c = self.config
+        K = np.zeros((n, c.layers, c.n_kv * c.head_dim), np.uint16)
+        V = np.zeros_like(K)
+        check(self._L.qie_seq_kv_read(self._h, seq, pos0, n, K.ctypes.data, V.ctypes.data))
+        return K, V
+
+    def kv_write(self, seq, pos0, K, V):
+        K, V = np.ascontiguousarray(K, np.uint16), np.ascontiguousarray(V, np.uint16)
+        check(self._L.qie_seq_kv_write(self._h, seq, pos0, K.shape[0], K.ctypes.data, V.ctypes.data))
+
     def decode_step_profile(self, seqs, tokens_in):
         """one eager decode step with an event pair around every launch ->
         {kernel class: (summed ms, launches)}"""
@@ -245,6 +258,10 @@ class Engine:
         out = np.zeros(n_elems, dtype)
         check(self._L.qie_engine_read_activation(self._h, name.encode(), out.ctypes.data, out.nbytes))
         return out
+
+    def write_activation(self, name, values):
+        values = np.ascontiguousarray(values)
+        check(self._L.qie_engine_write_activation(self._h, name.encode(), values.ctypes.data, values.nbytes))
 
     def launch_count(self):
         return self._L.qie_launch_count(self._h)

@@ -102,8 +102,9 @@ def sample_topk_bf16(logits_d, vocab, temperature, topk, seed, step=0):
     """helpers.cuh:157-166 -- returns the sampled token ids (one per row of logits)."""
     rows = logits_d.numel() // vocab
     out = torch.zeros(rows, dtype=torch.int32, device="cuda")
-    check(_lib.lib().qie_sample_topk(_p(logits_d), _p(out), rows, vocab, float(temperature), topk, seed + step, 0,
-                                     _st()))
+    # the reference hands `step` to the kernel as the cuRAND subsequence (helpers.cuh:157-166)
+    check(_lib.lib().qie_sample_topk_subseq(_p(logits_d), _p(out), rows, vocab, float(temperature), topk, seed, 0, step,
+                                            _st()))
     return out.cpu().numpy()
 
 

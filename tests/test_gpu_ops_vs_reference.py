@@ -142,6 +142,9 @@ def test_embedding_bit_exact(layers, ref, oracle):
     (128, 12, 2, 2, 19, 1, 0),     # 1.5B head geometry
     (128, 4, 4, 1, 9, 9, 1),       # MHA
     (64, 4, 1, 2, 160, 1, 0),      # config-1 final context length
+    (64, 14, 2, 1, 2048, 1, 0),    # BASELINE configs[1] context: 0.5B head geometry at t = 2048
+    (128, 12, 2, 1, 2049, 1, 0),   # 1.5B head geometry, odd length across the 2048 boundary
+    (64, 2, 1, 1, 700, 700, 1),    # causal prefill rows over many pages
 ])
 def test_attention_bit_exact(layers, ref, oracle, hd, n_q, n_kv, layers_n, t, mq, causal):
     """selfattention over a paged cache: reference page list (page_size 4, layout
@@ -170,7 +173,7 @@ def test_attention_bit_exact(layers, ref, oracle, hd, n_q, n_kv, layers_n, t, mq
     q_abs_base = 0 if causal else t - 1
     assert ref.L.ref_attn(p(Qd), p(o_ref), mq, t, hd, Dq, Dkv, causal, q_abs_base, layer, pages, ps_ref, layers_n) == 0
     # --- B200 pool
-    pool = layers.KvPool(n_pages=64, page_size=16, n_layers=layers_n, n_kv_heads=n_kv, head_dim=hd, max_seqs=4)
+    pool = layers.KvPool(n_pages=max(64, 4 * (t // 16 + 2)), page_size=16, n_layers=layers_n, n_kv_heads=n_kv, head_dim=hd, max_seqs=4)
     slot_id = 2
     pos_all = torch.arange(t, dtype=torch.int32, device="cuda")
     slot_all = torch.full((t,), slot_id, dtype=torch.int32, device="cuda")
@@ -217,6 +220,24 @@ def test_sampling_tiebreak_and_rng(layers, ref, oracle, vocab, levels, k, temp):
         assert oracle.sample_topk(lg, temp, k, seed) == want
         if k == 1:
             assert oracle.argmax_tiebreak(lg) == want
+
+
+@pytest.mark.parametrize("k,step", [(50, 1), (50, 7), (7, 123), (2, 65537)])
+def test_sampling_subsequence_argument(layers, ref, k, step):
+    """sample_topk_bf16's last argument is the cuRAND SUBSEQUENCE in the reference (helpers.cuh:157-166 ->
+    curand_init(seed, step, 0), logit_decode.cu:256-257), not a seed offset: nonzero values must pick the
+    reference's token, and must differ from seed + step for at least one draw."""
+    rng = np.random.default_rng(k * 1000 + step)
+    vocab, differs = 151936, 0
+    for trial in range(4):
+        lg = _tie_logits(rng, vocab, 4000)
+        ld = to_dev(lg)
+        seed = 1234 + trial
+        want = ref.L.ref_sample(p(ld), vocab, 0.7, k, seed, step)
+        got = int(layers.sample_topk_bf16(ld, vocab, 0.7, k, seed, step)[0])
+        assert got == want
+        differs += int(layers.sample_topk_bf16(ld, vocab, 0.7, k, seed + step, 0)[0]) != want
+    assert differs > 0 or k == 2
 
 
 def test_sampling_degenerate(layers, oracle):
