@@ -936,6 +936,32 @@ __device__ __forceinline__ float dot_tree_f(const float* __restrict__ q, const f
   return __fadd_rn(d[0].x, d[0].y);  // stride 1
 }
 
+// the same with the query operands travelling through a rolling register window: pair u of a head is the quads
+// q[4u..4u+3] and q[HD/2+4u..]; when pair u has been consumed its slot is refilled with pair u+4 (of the NEXT head
+// once this one runs out), so every broadcast LDS.128 is issued ~4 pairs (two dozen FP instructions) before its use.
+// With 7 warps per SM nothing else hides the shared-memory latency, and holding a whole head (64 registers) next to
+// the fp32 K row (64) spills.
+template <int HD>
+__device__ __forceinline__ float dot_tree_w(float4 (&wa)[4], float4 (&wb)[4], const float2 (&kf)[HD / 2], const float* __restrict__ q,
+                                            const float* __restrict__ qnext) {
+  constexpr int NPAIR = HD / 8;
+  float2 d[HD / 4];
+#pragma unroll
+  for (int u = 0; u < NPAIR; ++u) {
+    const float4 qa = wa[u & 3], qb = wb[u & 3];
+    const float* src = u + 4 < NPAIR ? q + 4 * (u + 4) : qnext + 4 * (u + 4 - NPAIR);
+    wa[u & 3] = *reinterpret_cast<const float4*>(src);
+    wb[u & 3] = *reinterpret_cast<const float4*>(src + HD / 2);
+    d[2 * u] = __fadd2_rn(__fmul2_rn(make_float2(qa.x, qa.y), kf[2 * u]), __fmul2_rn(make_float2(qb.x, qb.y), kf[2 * u + HD / 4]));
+    d[2 * u + 1] = __fadd2_rn(__fmul2_rn(make_float2(qa.z, qa.w), kf[2 * u + 1]), __fmul2_rn(make_float2(qb.z, qb.w), kf[2 * u + 1 + HD / 4]));
+  }
+#pragma unroll
+  for (int s = HD / 8; s >= 1; s >>= 1)
+#pragma unroll
+    for (int j = 0; j < s; ++j) d[j] = __fadd2_rn(d[j], d[j + s]);
+  return __fadd_rn(d[0].x, d[0].y);
+}
+
 template <int NP>
 __device__ __forceinline__ void head_load_cg(float (&x)[NP][2], const bf16* src, int lane) {
 #pragma unroll
@@ -1316,6 +1342,280 @@ __device__ __forceinline__ void attention_phase(const MegaArgs& a, int layer, un
   }
 }
 
+// ---------------------------------------------------------------- attention, query-group tasks (head_dim 64)
+// Many rows (B * n_q > grid): a task is (row, kv head) and the n_q / n_kv query heads of the group share ONE stream
+// of the cached K and V rows.  Both travel through shared memory in tiles of AT positions (one per consumer
+// thread), copied with coalesced 16-byte cp.async into 128-byte rows whose 16-byte chunk c sits at c ^ (row & 7)
+// (a thread reading ITS row with LDS.128 is conflict free), two buffers: K tile j+1 / V tile 0 are in flight while
+// tile j is used.  What the reference fixes is kept (self_attension.cu:47-137): products then the 2^k tree per
+// score, max, expf, the sequential sum, p = e / sum, the sequential fma chain over positions per output element.
+//  * scores: thread = cached position, the query group's heads in turn (q as fp32 in shared memory);
+//  * softmax: one warp per head; the sum chain runs in lane 0 with its operands requested 16 positions ahead;
+//  * PV: warps 0..3 own heads w, w+4, w+8, w+12 with lane l on output dims 2l, 2l+1: one LDS.32 of a V row feeds
+//    the fma chains of all heads of the warp (packed FFMA2: two IEEE fp32 fmas per instruction), the four
+//    probabilities of a head arrive with one broadcast LDS.128.  (r01: one warp per head re-read every V row
+//    7 times and the phase was bound by shared-memory wavefronts: 27 cycles per position, now ~8.)
+constexpr int AT = NTC;            // positions per K/V tile
+constexpr int AT_BYTES = AT * 128;  // head_dim 64, bf16
+__host__ __device__ inline int attn_score_pitch(int max_kv_len) { return ((max_kv_len + 1 + 31) & ~31) + 4; }  // pitch % 32 == 4
+
+// PV of one V tile (tn cached positions, rows of 128 bytes, lane l = output dims 2l, 2l+1) for the NH heads of a warp:
+// o[h] = fma(p[h][k], v[k], o[h]) for k ascending -- the reference's chain (self_attension.cu:112-137), two IEEE fmas
+// per packed FFMA2.  Groups of 4 positions in two operand sets; a set is reloaded (for 8 positions ahead) right
+// after it has been consumed, so every load has the other set's chains to land.
+template <int NH>
+__device__ __forceinline__ void pv_tile(const unsigned char* __restrict__ vl, const float* __restrict__ sb, int hstride, int tn,
+                                        float2 (&o)[2]) {
+  auto load4 = [&](uint32_t (&vv)[4], float4 (&pr)[NH], int kk) {
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) vv[jj] = *reinterpret_cast<const uint32_t*>(vl + (kk + jj) * 128);
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh) pr[hh] = *reinterpret_cast<const float4*>(sb + hh * hstride + kk);
+  };
+  auto fma4 = [&](const uint32_t (&vv)[4], const float4 (&pr)[NH]) {
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const float2 vf = make_float2(lo2f(vv[jj]), hi2f(vv[jj]));
+#pragma unroll
+      for (int hh = 0; hh < NH; ++hh) {
+        const float pj = jj == 0 ? pr[hh].x : (jj == 1 ? pr[hh].y : (jj == 2 ? pr[hh].z : pr[hh].w));
+        o[hh] = __ffma2_rn(make_float2(pj, pj), vf, o[hh]);
+      }
+    }
+  };
+  int k = 0;
+  const int n8 = tn & ~7;
+  if (n8) {
+    uint32_t va[4], vb[4];
+    float4 pa[NH], pb[NH];
+    load4(va, pa, 0);
+    load4(vb, pb, 4);
+#pragma unroll 1
+    for (; k < n8; k += 8) {
+      fma4(va, pa);
+      if (k + 8 < n8) load4(va, pa, k + 8);
+      fma4(vb, pb);
+      if (k + 12 < n8) load4(vb, pb, k + 12);
+    }
+  }
+  for (; k < tn; ++k) {
+    const uint32_t v1 = *reinterpret_cast<const uint32_t*>(vl + k * 128);
+    const float2 vf = make_float2(lo2f(v1), hi2f(v1));
+#pragma unroll
+    for (int hh = 0; hh < NH; ++hh) {
+      const float pj = sb[hh * hstride + k];
+      o[hh] = __ffma2_rn(make_float2(pj, pj), vf, o[hh]);
+    }
+  }
+}
+
+__device__ __noinline__ void attention_group_phase(const MegaArgs& a, int layer, unsigned char* smem) {
+  constexpr int HD = 64, NP = 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hs = a.n_q / a.n_kv;
+  const int Dq = a.n_q * HD, Dkv = a.n_kv * HD, QKV = Dq + 2 * Dkv;
+  const int ntask = a.B * a.n_kv;
+  const int SP = attn_score_pitch(a.max_kv_len);
+  const int psz = a.kv.page_size;             // a power of two on this path (mega_geometry)
+  const int psz_shift = __ffs(psz) - 1;
+  const uint32_t psz_mask = (uint32_t)psz - 1u;
+  const uint32_t pstride_b = (uint32_t)(a.kv.page_stride() * sizeof(bf16));
+  const MegaLayer& w = reinterpret_cast<const MegaLayer*>(smem + OFF_LAYERS)[layer];
+
+  float* q_s = reinterpret_cast<float*>(smem + a.off_act);   // [hs][HD] fp32
+  bf16* knew = reinterpret_cast<bf16*>(q_s + hs * HD);        // [HD]
+  bf16* vnew = knew + HD;
+  float* score = reinterpret_cast<float*>(vnew + HD);         // [hs][SP]
+  unsigned char* kvb = reinterpret_cast<unsigned char*>(score + hs * SP);  // [2][AT][128]
+  const uint32_t kvb_u32 = smem_u32(kvb);
+  int* pages = reinterpret_cast<int*>(kvb + 2 * AT_BYTES);    // [max_kv_len / page_size + 1]
+
+  unsigned long long* dbg = reinterpret_cast<unsigned long long*>(smem + OFF_DBG);
+  const bool timed = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  for (int task = blockIdx.x; task < ntask; task += gridDim.x) {
+    long long tq = timed ? clock64() : 0;
+    auto lap = [&](int slot) {
+      if (timed) {
+        const long long t = clock64();
+        dbg[slot] += (unsigned long long)(t - tq);
+        tq = t;
+      }
+    };
+    const int b = task / a.n_kv, kvh = task - b * a.n_kv, h0 = kvh * hs;
+    const int ps = a.pos[b];                      // cached positions 0..ps-1, the new one is ps
+    const int* bt = a.block_table + (size_t)a.slot[b] * a.max_pages;
+    const int ns = ps / AT + 1;                   // score tiles (the last one holds position ps)
+    const int nt = (ps + AT - 1) / AT;            // tiles with cached rows
+    // job j < ns: K tile j; job ns + i: V tile i.  Buffer j & 1.  K rows are stored with the chunk swizzle (a thread
+    // reads ITS row), V rows linearly (a warp reads ONE row, lane l its word l).  The 8 copies of a thread are
+    // independent (page ids come from shared memory), so they are issued back to back.
+    auto tile_load = [&](int j) {
+      const int kv = j >= ns ? 1 : 0, it = kv ? j - ns : j;
+      const int t0 = it * AT, tn = max(0, min(AT, ps - t0));
+      const uint32_t dst = kvb_u32 + (j & 1) * AT_BYTES + (threadIdx.x >> 3) * 128;
+      const uint32_t cc = threadIdx.x & 7;
+      // byte address of (page 0, this layer, K|V, this kv head, slot 0, chunk cc); a page id adds pstride_b, a slot 128
+      const unsigned char* base = reinterpret_cast<const unsigned char*>(a.kv.chunk(0, layer, kv, kvh)) + cc * 16;
+#pragma unroll
+      for (int i = 0; i < AT * 8 / NTC; ++i) {
+        const int r = (int)(threadIdx.x >> 3) + i * (NTC / 8);
+        if (r < tn) {
+          const uint32_t k = (uint32_t)(t0 + r);
+          const uint32_t col = kv ? cc : (cc ^ (uint32_t)(r & 7));
+          const size_t off = (size_t)(uint32_t)pages[k >> psz_shift] * pstride_b + (k & psz_mask) * 128u;  // one IMAD.WIDE
+          cp_async16(dst + i * (NTC / 8) * 128 + (col << 4), base + off);
+        }
+      }
+      cp_async_commit();
+    };
+    const int njobs = ns + nt;
+    for (int i = threadIdx.x; i <= ps / psz; i += NTC) pages[i] = bt[i];
+    bar_consumers();
+    tile_load(0);  // cached rows do not depend on this step's q/k/v: in flight during the set-up
+    // q/k-norm + RoPE of the group's query heads and of the new K row; KV store of the new position
+    {
+      const bf16* row = a.qkv + (size_t)b * QKV;
+      const float* cos_row = a.cos_t + (size_t)ps * 32 * NP;
+      const float* sin_row = a.sin_t + (size_t)ps * 32 * NP;
+      const int new_page = bt[ps / psz], new_off = ps % psz;
+      for (int r = warp; r < hs + 2; r += NW) {
+        float v[NP][2];
+        if (r < hs) {
+          head_load_cg<NP>(v, row + (size_t)(h0 + r) * HD, lane);
+          if (w.q_norm) head_norm<NP>(v, w.q_norm, lane);
+          head_rope<NP>(v, cos_row, sin_row, lane);
+          *reinterpret_cast<float2*>(q_s + r * HD + 2 * lane) = make_float2(v[0][0], v[0][1]);
+        } else if (r == hs) {
+          head_load_cg<NP>(v, row + Dq + (size_t)kvh * HD, lane);
+          if (w.k_norm) head_norm<NP>(v, w.k_norm, lane);
+          head_rope<NP>(v, cos_row, sin_row, lane);
+          head_store<NP>(v, knew, lane);
+          head_store<NP>(v, a.kv.chunk(new_page, layer, 0, kvh) + (size_t)new_off * HD, lane);
+        } else {
+          head_load_cg<NP>(v, row + Dq + Dkv + (size_t)kvh * HD, lane);
+          head_store<NP>(v, vnew, lane);
+          head_store<NP>(v, a.kv.chunk(new_page, layer, 1, kvh) + (size_t)new_off * HD, lane);
+        }
+      }
+    }
+    lap(10);
+
+    // ---- scores (self_attension.cu:47-74)
+    for (int j = 0; j < ns; ++j) {
+      const long long tw0 = timed ? clock64() : 0;
+      if (j + 1 < njobs) {
+        tile_load(j + 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      bar_consumers();  // tile j (and, at j = 0, q_s / knew) visible
+      if (timed) dbg[14] += (unsigned long long)(clock64() - tw0);
+      const int k = j * AT + threadIdx.x;
+      if (k <= ps) {
+        const unsigned char* base = k == ps ? reinterpret_cast<const unsigned char*>(knew) : kvb + (j & 1) * AT_BYTES + threadIdx.x * 128;
+        const int swz = k == ps ? 0 : (threadIdx.x & 7);
+        float2 kf[HD / 2];
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i) {
+          const uint4 t = *reinterpret_cast<const uint4*>(base + ((i ^ swz) << 4));
+          kf[4 * i] = make_float2(lo2f(t.x), hi2f(t.x));
+          kf[4 * i + 1] = make_float2(lo2f(t.y), hi2f(t.y));
+          kf[4 * i + 2] = make_float2(lo2f(t.z), hi2f(t.z));
+          kf[4 * i + 3] = make_float2(lo2f(t.w), hi2f(t.w));
+        }
+        // dot / sqrtf(64): the divisor is exactly 8, and x / 8 == x * 0.125 bit for bit
+        float4 wa[4], wb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          wa[u] = *reinterpret_cast<const float4*>(q_s + 4 * u);
+          wb[u] = *reinterpret_cast<const float4*>(q_s + HD / 2 + 4 * u);
+        }
+        for (int i = 0; i < hs; ++i)
+          score[i * SP + k] = __fmul_rn(dot_tree_w<HD>(wa, wb, kf, q_s + i * HD, q_s + (i + 1 < hs ? i + 1 : i) * HD), 0.125f);
+      }
+      bar_consumers();  // buffer j & 1 is refilled by job j + 2
+    }
+    lap(11);
+
+    // ---- softmax (self_attension.cu:94-107): one warp per head
+    for (int i = warp; i < hs; i += NW) {
+      float* s = score + i * SP;
+      const int n = ps + 1;
+      float m = -1e9f;
+      for (int k = lane; k < n; k += 32) m = fmaxf(m, s[k]);
+      m = warp_max(m);
+      for (int k = lane; k < n; k += 32) s[k] = expf(__fsub_rn(s[k], m));
+      __syncwarp();
+      float sum = 0.f;
+      if (lane == 0) {
+        // the reference's sequential sum: blocks of 16 values, the next block requested before the current FADD chain
+        const int n16 = n & ~15;
+        float4 c[4], nx[4];
+        if (n16) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) c[u] = *reinterpret_cast<const float4*>(s + 4 * u);
+        }
+        for (int k = 0; k < n16; k += 16) {
+          const int kn = k + 16 < n16 ? k + 16 : k;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) nx[u] = *reinterpret_cast<const float4*>(s + kn + 4 * u);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            sum = __fadd_rn(sum, c[u].x);
+            sum = __fadd_rn(sum, c[u].y);
+            sum = __fadd_rn(sum, c[u].z);
+            sum = __fadd_rn(sum, c[u].w);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) c[u] = nx[u];
+        }
+        for (int k = n16; k < n; ++k) sum = __fadd_rn(sum, s[k]);
+      }
+      sum = __shfl_sync(0xffffffffu, sum, 0);
+      for (int k = lane; k < n; k += 32) s[k] = __fdiv_rn(s[k], sum);
+    }
+    lap(12);
+
+    // ---- PV (self_attension.cu:112-137)
+    float2 o[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    const int nh = warp < hs ? (warp + NW < hs ? 2 : 1) : 0;  // heads warp and warp + NW
+    for (int it = 0; it < nt; ++it) {
+      const int j = ns + it;
+      const long long tw0 = timed ? clock64() : 0;
+      if (j + 1 < njobs) {
+        tile_load(j + 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      bar_consumers();  // V tile `it` visible (and, at it = 0, the probabilities)
+      if (timed) dbg[15] += (unsigned long long)(clock64() - tw0);
+      const unsigned char* vl = kvb + (j & 1) * AT_BYTES + 4 * lane;  // V rows are stored linearly: lane l reads word l of a row
+      const int t0 = it * AT, tn = min(AT, ps - t0);
+      if (nh == 1)
+        pv_tile<1>(vl, score + warp * SP + t0, NW * SP, tn, o);
+      else if (nh == 2)
+        pv_tile<2>(vl, score + warp * SP + t0, NW * SP, tn, o);
+      bar_consumers();  // the buffer is refilled two tiles later
+    }
+    if (nt == 0) bar_consumers();  // the probabilities of other warps are read below
+    {
+      const uint32_t v1 = *reinterpret_cast<const uint32_t*>(vnew + 2 * lane);  // the new position: V of this step's projection
+      const float2 vf = make_float2(lo2f(v1), hi2f(v1));
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh)
+        if (hh < nh) {
+          const float pj = score[(warp + NW * hh) * SP + ps];
+          o[hh] = __ffma2_rn(make_float2(pj, pj), vf, o[hh]);
+          *reinterpret_cast<uint32_t*>(a.att + (size_t)b * Dq + (size_t)(h0 + warp + NW * hh) * HD + 2 * lane) = pack2(f2bf(o[hh].x), f2bf(o[hh].y));
+        }
+    }
+    bar_consumers();  // shared memory is reused by the next task / phase
+    lap(13);
+  }
+}
+
 // ---------------------------------------------------------------- the kernel
 template <int NP, int MT, bool FAST>
 __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __grid_constant__ MegaArgs a) {
@@ -1391,7 +1691,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
     const bf16* a_src = nullptr;
     if (kind == PH_O) {
       // ---- attention, then O + residual
-      attention_phase<NP>(a, l, smem, 1);
+      if (NP == 1 && a.attn_group)
+        attention_group_phase(a, l, smem);
+      else
+        attention_phase<NP>(a, l, smem, 1);
       stamp();
       grid_sync(a.bar, epoch);
       stamp();
@@ -1592,7 +1895,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
 }
 
 struct Geom {
-  int KC, slot_bytes, act_bytes, n_slots, off_act, off_ring, mt, stream_down, kstg, attn_off, off_red;
+  int KC, slot_bytes, act_bytes, n_slots, off_act, off_ring, mt, stream_down, kstg, attn_off, off_red, group;
   size_t smem;
 };
 
@@ -1607,7 +1910,7 @@ int kc_for(int H, int big) {
   return KC;
 }
 
-bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int grid, int KC, int fast, Geom* g) {
+bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int grid, int KC, int fast, int psz, Geom* g) {
   const int Dq = n_q * hd;
   if ((H % 64) || (I % 64) || (Dq % 64) || (hd != 64 && hd != 128) || KC < 64 || (KC % 64)) return false;
   if (B < 1 || B > MAX_ROWS || n_q % n_kv || n_q / n_kv > 2 * NW || L > MAX_LAYERS) return false;
@@ -1621,6 +1924,7 @@ bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int ma
   const int stream_down = !fast && res_i > 48 * 1024;  // fast numerics keeps [B, I] resident (<= 8 rows)
   int act = std::max(res_h, stream_down ? strm : res_i);
   const int hs = (B * n_q <= grid) ? 1 : n_q / n_kv;
+  const int group = hs > 1 && hd == 64 && psz > 0 && (psz & (psz - 1)) == 0;  // query-group tasks with K and V tiles in shared memory (attention_group_phase)
   const int tmax = (max_kv_len + 3) & ~3;
   const int act_gemm = act;
   const int off_act = (OFF_WNORM + 2 * H * 2 + 127) & ~127;
@@ -1629,8 +1933,9 @@ bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int ma
   int kstg = hs == 1 ? std::min(256, (max_kv_len + 15) & ~15) : 0;  // K rows staged before the barrier
   int attn_off = 0, off_red = 0, off_ring = 0, S = 0;
   for (;;) {
-    const int attn = hs * hd * 4 + 2 * hd * 2 + hs * tmax * 4 + (max_kv_len + 32) * 4 /* pages: <= one per position */ +
-                     2 * VT * hd * 2 + kstg * (hd * 2 + 16) + 2 * hd * 2 + hd * 4 + 64;
+    const int attn = group ? hs * hd * 4 + 2 * hd * 2 + hs * attn_score_pitch(max_kv_len) * 4 + 2 * AT_BYTES + (max_kv_len / std::max(1, psz) + 2) * 4 + 64
+                           : hs * hd * 4 + 2 * hd * 2 + hs * tmax * 4 + (max_kv_len + 32) * 4 /* pages: <= one per position */ +
+                                 2 * VT * hd * 2 + kstg * (hd * 2 + 16) + 2 * hd * 2 + hd * 4 + 64;
     attn_off = kstg > 0 ? ((res_h + 127) & ~127) : 0;  // staged attention areas live behind the resident rows
     act = std::max(act_gemm, attn + attn_off);
     off_red = off_act + ((act + 127) & ~127);     // fast numerics: split-K partial sums [FAST_U][NW][32][8] fp32
@@ -1653,6 +1958,7 @@ bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int ma
   g->kstg = kstg;
   g->attn_off = attn_off;
   g->off_red = off_red;
+  g->group = group;
   g->smem = (size_t)off_ring + (size_t)S * slot;
   return true;
 }
@@ -1661,9 +1967,9 @@ bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int ma
 
 int decode_mega_kc(int H, int big) { return kc_for(H, big); }
 
-bool decode_mega_supports(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int num_sms, int KC, int fast) {
+bool decode_mega_supports(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int num_sms, int KC, int fast, int page_size) {
   Geom g;
-  return mega_geometry(H, I, L, n_q, n_kv, hd, B, max_kv_len, num_sms, KC, fast, &g);
+  return mega_geometry(H, I, L, n_q, n_kv, hd, B, max_kv_len, num_sms, KC, fast, page_size, &g);
 }
 
 int decode_mega_prof_slots(int L) { return 2 * (16 * L + 8) + 16; }
@@ -1681,7 +1987,7 @@ static void (*pick_kernel(int mt, bool fast))(MegaArgs) {
 
 cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st) {
   Geom g;
-  if (!mega_geometry(a.H, a.I, a.L, a.n_q, a.n_kv, a.hd, a.B, a.max_kv_len, num_sms, a.KC, a.fast, &g)) return cudaErrorInvalidValue;
+  if (!mega_geometry(a.H, a.I, a.L, a.n_q, a.n_kv, a.hd, a.B, a.max_kv_len, num_sms, a.KC, a.fast, a.kv.page_size, &g)) return cudaErrorInvalidValue;
   a.slot_bytes = g.slot_bytes;
   a.act_bytes = g.act_bytes;
   a.n_slots = g.n_slots;
@@ -1691,6 +1997,7 @@ cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st) {
   a.attn_kstg = g.kstg;
   a.attn_off = g.attn_off;
   a.off_red = g.off_red;
+  a.attn_group = g.group;
   a.dist_norm = a.B > 16 && a.B <= num_sms && a.xn != nullptr;
   {  // per phase kind: units of a CTA (q, +1 for the first r CTAs), chunks, and ring advances modulo the slot count
     const int Dq = a.n_q * a.hd, Dkv = a.n_kv * a.hd;

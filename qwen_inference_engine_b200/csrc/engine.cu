@@ -324,7 +324,7 @@ static int mega_tile_set(const qie_engine* e, int n, int max_kv_len) {
   const int fast = !tp && e->opts.numerics == QIE_NUMERICS_FAST;
   const int I = tp ? e->plan.inter : c.inter, nq = tp ? e->plan.n_q : c.n_q, nkv = tp ? e->plan.n_kv : c.n_kv;
   if (n <= 8 && e->mega_kc[1] > e->mega_kc[0] &&
-      decode_mega_supports(c.hidden, I, c.layers, nq, nkv, c.head_dim, n, max_kv_len, e->num_sms, e->mega_kc[1], fast))
+      decode_mega_supports(c.hidden, I, c.layers, nq, nkv, c.head_dim, n, max_kv_len, e->num_sms, e->mega_kc[1], fast, e->kv.page_size))
     return 1;
   return 0;
 }
@@ -478,11 +478,11 @@ bool decode_uses_mega(const qie_engine* e, int n, int max_kv_len) {
     if (!e->tp_mega_ready || n > MEGA_TP_ROWS || e->topk != 1) return false;
     const TpPlan& pl = e->plan;
     return decode_mega_supports(c.hidden, pl.inter, c.layers, pl.n_q, pl.n_kv, c.head_dim, n, max_kv_len, e->num_sms,
-                                e->mega_kc[mega_tile_set(e, n, max_kv_len)], 0);
+                                e->mega_kc[mega_tile_set(e, n, max_kv_len)], 0, e->kv.page_size);
   }
   const int fast = e->opts.numerics == QIE_NUMERICS_FAST;  // fast numerics: persistent kernel for <= 8 rows
   return decode_mega_supports(c.hidden, c.inter, c.layers, c.n_q, c.n_kv, c.head_dim, n, max_kv_len, e->num_sms,
-                              e->mega_kc[mega_tile_set(e, n, max_kv_len)], fast);
+                              e->mega_kc[mega_tile_set(e, n, max_kv_len)], fast, e->kv.page_size);
 }
 
 cudaError_t forward_decode_mega(qie_engine* e, int n, int max_kv_len, float temperature) {

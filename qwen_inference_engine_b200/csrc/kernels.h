@@ -225,11 +225,11 @@ struct MegaArgs {
   // geometry, filled by the launcher (ph_*: per GEMM phase kind qkv/o/gate+up/down/lm_head)
   int ph_nu[5];  // units per round (NW, or NW / token tiles when the tiles of a unit are spread over warps)
   int ph_q[5], ph_r[5], ph_nch[5], ph_adv_slot[5][2], ph_adv_par[5][2], ph_round_slot[5], ph_round_par[5];
-  int n_slots, slot_bytes, act_bytes, off_act, off_ring, stream_down, attn_kstg, attn_off, off_red;
+  int n_slots, slot_bytes, act_bytes, off_act, off_ring, stream_down, attn_kstg, attn_off, off_red, attn_group;
 };
 // max rows the persistent kernel accepts for this model shape (0 = shape unsupported)
 int decode_mega_kc(int H, int big);  // k elements per weight tile (box depth of the weight tensor maps); big: batches <= 8
-bool decode_mega_supports(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int num_sms, int KC, int fast);
+bool decode_mega_supports(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int num_sms, int KC, int fast, int page_size);
 int decode_mega_prof_slots(int L);
 cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st);
 

@@ -251,7 +251,7 @@ class Engine:
         out = np.zeros(2 * n + 16, np.uint64)
         check(self._L.qie_mega_prof_read(self._h, out.ctypes.data, len(out)))
         self.mega_gemm_cycles = out[2 * n:2 * n + 10]  # per GEMM phase kind: (cycles waiting for weights, cycles in the MMA loop)
-        self.mega_attn_cycles = out[2 * n + 10:2 * n + 14]  # attention of CTA 0: setup, scores, softmax, PV
+        self.mega_attn_cycles = out[2 * n + 10:2 * n + 16]  # attention of CTA 0: setup, scores, softmax, PV; [4], [5]: tile issue + wait inside scores / PV
         return out[:n - 2], out[n:2 * n - 2]  # (ns, SM cycles) at the 16*layers + 6 stamp points
 
     def read_activation(self, name, n_elems, dtype=np.uint16):
