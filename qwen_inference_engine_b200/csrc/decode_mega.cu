@@ -273,6 +273,9 @@ struct Phase {
   int n_c, nch, nu;  // units of THIS CTA, chunks per unit, units per round (host-precomputed tables)
   int upr, row2;     // weight rows per unit (8, or 16 for lm_head pairs), row offset of the second tile of a dual unit
   int xpar;          // tensor parallel: which half of the exchange buffer this phase's partial sums go to
+  // unit i of this CTA is ufirst + i * ustep.  Default: blockIdx.x + i * gridDim.x.  Tile-split phases (ts): the CTA
+  // owns ONE 16-row token tile (tile) and the units grp, grp + G, ... of ALL output rows, see gemm_ts
+  int ufirst, ustep, cls, ts, tile;
 };
 
 __device__ __forceinline__ void make_phase(const MegaArgs& a, int idx, Phase& p) {
@@ -320,7 +323,21 @@ __device__ __forceinline__ void make_phase(const MegaArgs& a, int idx, Phase& p)
   }
   p.ubeg[p.nseg] = u;
   p.units = u;
-  p.n_c = a.ph_q[p.kind] + ((int)blockIdx.x < a.ph_r[p.kind] ? 1 : 0);
+  p.ts = a.ph_ts[p.kind];
+  if (p.ts) {
+    const int G = a.ph_G[p.kind], grp = (int)blockIdx.x / a.mtt;
+    p.tile = (int)blockIdx.x - grp * a.mtt;
+    p.ufirst = grp;
+    p.ustep = G;
+    p.cls = grp < a.ph_r[p.kind] ? 1 : 0;
+    p.n_c = grp < G ? a.ph_q[p.kind] + p.cls : 0;  // CTAs beyond mtt * G (grid not a multiple of the tile count) sit the phase out
+  } else {
+    p.tile = 0;
+    p.ufirst = (int)blockIdx.x;
+    p.ustep = (int)gridDim.x;
+    p.cls = (int)blockIdx.x < a.ph_r[p.kind] ? 1 : 0;
+    p.n_c = a.ph_q[p.kind] + p.cls;
+  }
   p.nch = a.ph_nch[p.kind];
   p.nu = a.ph_nu[p.kind];
 }
@@ -368,7 +385,7 @@ __device__ __forceinline__ void producer_loop(const MegaArgs& a, uint32_t smem_b
       const int nact = min(p.nu, n_c - r0);
       for (int ch = 0; ch < nch; ++ch) {
         for (int s = 0; s < nact; ++s) {
-          const int u = blockIdx.x + (r0 + s) * gridDim.x;
+          const int u = p.ufirst + (r0 + s) * p.ustep;
           int seg = 0;
           while (seg + 1 < p.nseg && u >= p.ubeg[seg + 1]) ++seg;
           const int row0 = (u - p.ubeg[seg]) * p.upr;
@@ -429,36 +446,30 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[MT == 0 ? 1 : MT][4], flo
   const bool row_valid = (lane >> 2) < B;
   const uint32_t a0 = MT == 0 ? a_addr + (lane >> 2) * AS + (lane & 3) * 4
                               : a_addr + ((lane & 7) + ((lane >> 3) & 1) * 8) * AS + (lane >> 4) * 16;
-  auto load = [&](F& f, int j0) {
+  auto load_step = [&](F& f, int s, int j) {  // fragments of k-step j -> slot s of f
+    const uint32_t baddr = brow + (uint32_t)(j >> 2) * 1024u + boff[(GS == 4) ? s : (j & 3)];
+    if (DUAL)
+      ldmatrix_x4(f.b[s][0], f.b[s][1], f.b[s][2], f.b[s][3], baddr);
+    else
+      ldmatrix_x2(f.b[s][0], f.b[s][1], baddr);
 #pragma unroll
-    for (int s = 0; s < GS; ++s) {
-      const int j = j0 + s;
-      const uint32_t baddr = brow + (uint32_t)(j >> 2) * 1024u + boff[(GS == 4) ? s : (j & 3)];
-      if (DUAL)
-        ldmatrix_x4(f.b[s][0], f.b[s][1], f.b[s][2], f.b[s][3], baddr);
-      else
-        ldmatrix_x2(f.b[s][0], f.b[s][1], baddr);
-#pragma unroll
-      for (int m = 0; m < MTT; ++m) {
-        if (MT == 0) {
-          if (row_valid) {  // invalid token rows keep the zeros they were initialised with
-            f.a[s][m][0] = lds32(a0 + j * 32);
-            f.a[s][m][2] = lds32(a0 + j * 32 + 16);
-          }
-        } else {
-          ldmatrix_x4(f.a[s][m][0], f.a[s][m][1], f.a[s][m][2], f.a[s][m][3], a0 + m * 16 * AS + j * 32);
+    for (int m = 0; m < MTT; ++m) {
+      if (MT == 0) {
+        if (row_valid) {  // invalid token rows keep the zeros they were initialised with
+          f.a[s][m][0] = lds32(a0 + j * 32);
+          f.a[s][m][2] = lds32(a0 + j * 32 + 16);
         }
+      } else {
+        ldmatrix_x4(f.a[s][m][0], f.a[s][m][1], f.a[s][m][2], f.a[s][m][3], a0 + m * 16 * AS + j * 32);
       }
     }
   };
-  auto compute = [&](const F& f) {
+  auto compute_step = [&](const F& f, int s) {
 #pragma unroll
-    for (int s = 0; s < GS; ++s)
-#pragma unroll
-      for (int m = 0; m < MTT; ++m) {
-        mma_bf16_16816(acc[m], f.a[s][m], f.b[s][0], f.b[s][1]);
-        if (DUAL) mma_bf16_16816(acc2[m], f.a[s][m], f.b[s][2], f.b[s][3]);
-      }
+    for (int m = 0; m < MTT; ++m) {
+      mma_bf16_16816(acc[m], f.a[s][m], f.b[s][0], f.b[s][1]);
+      if (DUAL) mma_bf16_16816(acc2[m], f.a[s][m], f.b[s][2], f.b[s][3]);
+    }
   };
   F f0, f1;
   if (MT == 0) {
@@ -474,15 +485,38 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[MT == 0 ? 1 : MT][4], flo
         asm volatile("mov.u32 %0, 0;" : "=r"(f1.a[s][0][i]));
       }
   }
-  load(f0, 0);  // nk16 is a multiple of 4 (chunks are whole 64-wide k blocks), GS divides 4
-  for (int j0 = 0; j0 < nk16; j0 += 2 * GS) {
-    const bool more1 = j0 + GS < nk16;
-    if (more1) load(f1, j0 + GS);
-    compute(f0);
-    if (more1) {
-      if (j0 + 2 * GS < nk16) load(f0, j0 + 2 * GS);
-      compute(f1);
+  // nk16 is a multiple of 4 (chunks are whole 64-wide k blocks), GS divides 4.  The HMMAs of a chain are dependent
+  // (20.7 cycles apart) and a warp issues in order, so the fragment loads of the NEXT group are placed BETWEEN the
+  // HMMAs of the current one -- step s of the other set right behind step s -- where they issue in the latency
+  // shadow of the HMMA just issued.  (r01 issued a whole group of loads, then the group's HMMAs: both are asm
+  // volatile and keep their order, so ~36 load / address instructions sat on the chain: 59 cycles per k-step at one
+  // chain per warp.)
+#pragma unroll
+  for (int s = 0; s < GS; ++s) load_step(f0, s, s);
+  int j0 = 0;
+  for (; j0 + 2 * GS < nk16; j0 += 2 * GS) {  // at least three groups left: no per-step branches in the steady state
+#pragma unroll
+    for (int s = 0; s < GS; ++s) {
+      compute_step(f0, s);
+      load_step(f1, s, j0 + GS + s);
     }
+#pragma unroll
+    for (int s = 0; s < GS; ++s) {
+      compute_step(f1, s);
+      load_step(f0, s, j0 + 2 * GS + s);
+    }
+  }
+  if (j0 + GS < nk16) {  // two groups left (f0 is loaded)
+#pragma unroll
+    for (int s = 0; s < GS; ++s) {
+      compute_step(f0, s);
+      load_step(f1, s, j0 + GS + s);
+    }
+#pragma unroll
+    for (int s = 0; s < GS; ++s) compute_step(f1, s);
+  } else {  // one group left
+#pragma unroll
+    for (int s = 0; s < GS; ++s) compute_step(f0, s);
   }
 }
 
@@ -580,7 +614,7 @@ __device__ __forceinline__ void gemm_inner(const MegaArgs& a, const Phase& p, ui
     if (!stream && !has) break;  // resident A: idle warps need not take part
     int seg = 0, row0 = 0;
     if (has) {
-      const int u = blockIdx.x + (r0 + us) * gridDim.x;
+      const int u = p.ufirst + (r0 + us) * p.ustep;
       while (seg + 1 < p.nseg && u >= p.ubeg[seg + 1]) ++seg;
       row0 = (u - p.ubeg[seg]) * p.upr;
     }
@@ -665,15 +699,111 @@ __device__ __forceinline__ void gemm_inner(const MegaArgs& a, const Phase& p, ui
         }
       }
   }
-  const int cls = (int)blockIdx.x < a.ph_r[p.kind] ? 1 : 0;
-  base.advance((uint32_t)(n_c * nch), a.ph_adv_slot[p.kind][cls], a.ph_adv_par[p.kind][cls], S);
+  base.advance((uint32_t)(n_c * nch), a.ph_adv_slot[p.kind][p.cls], a.ph_adv_par[p.kind][p.cls], S);
+}
+
+// Tile-split GEMM phase (more than 16 rows, phases with at most one unit per CTA in the default mapping: QKV, O, DOWN of
+// the 0.5B shape).  The default mapping gives such a phase ONE unit per CTA and spreads its token tiles over warps, so
+// every CTA needs the activations of ALL rows: for down_proj that is the whole [64, I] operand (622 KB at I = 4864)
+// copied from L2 by each of the 148 CTAs, 92 MB of L2 traffic per layer and 29 us (r01).  Here CTA c owns token tile
+// c % T and the units c / T, c / T + G, ... (G = grid / T): warp w runs the HMMA chain of its unit for that ONE tile, the
+// A operand is 16 rows -- resident for K = H (29 KB instead of 115 KB), streamed in KC-wide chunks through a 4-stage
+// cp.async ring for down_proj (155 KB per CTA instead of 622 KB, one barrier per chunk) -- and the weights of a unit
+// are fetched by the T CTAs of its group from L2 (HBM still sees them once).  Same arithmetic: one dependent chain per
+// (unit, tile) with k ascending.
+constexpr int TS_STAGES = 4;
+template <int MT>
+__device__ __forceinline__ void gemm_ts(const MegaArgs& a, const Phase& p, uint32_t smem_base, RingPos& base, const bf16* a_src,
+                                        unsigned char* dbg_smem) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t S = a.n_slots;
+  const int KC = a.KC, RS = (KC + 8) * 2;
+  const uint32_t ring = smem_base + a.off_ring, act = smem_base + a.off_act;
+  const bool stream = a_src != nullptr;
+  const int AS = stream ? RS : (p.K + 8) * 2;
+  const int g = lane >> 2, c = lane & 3;
+  const int n_c = p.n_c, nch = p.nch;
+  const int tok0 = p.tile * 16, nrows = min(16, a.B - tok0);
+  RingPos rnd = base;
+  auto a_chunk_load = [&](int ch) {  // rows of this tile x [ch*KC, +klen) -> stage ch % TS_STAGES (an empty group past the end)
+    if (ch < nch) {
+      const int k0 = ch * KC, klen = min(KC, p.K - k0), per = klen >> 3;
+      const uint32_t dst = act + (ch % TS_STAGES) * (16 * RS);
+      for (int i = threadIdx.x; i < nrows * per; i += NTC) {
+        const int b = i / per, cc = i - b * per;
+        cp_async16(dst + b * RS + cc * 16, a_src + (size_t)(tok0 + b) * p.K + k0 + cc * 8);
+      }
+    }
+    cp_async_commit();
+  };
+  for (int r0 = 0; r0 < n_c; r0 += NW, rnd.advance(NW * nch, a.ph_round_slot[p.kind], a.ph_round_par[p.kind], S)) {
+    const int nact = min(NW, n_c - r0);
+    const bool has = warp < nact;
+    if (!stream && !has) break;
+    int seg = 0, row0 = 0;
+    if (has) {
+      const int u = p.ufirst + (r0 + warp) * p.ustep;
+      while (seg + 1 < p.nseg && u >= p.ubeg[seg + 1]) ++seg;
+      row0 = (u - p.ubeg[seg]) * p.upr;
+    }
+    float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}}, acc2[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+    if (stream)
+      for (int s = 0; s < TS_STAGES - 1; ++s) a_chunk_load(s);
+    RingPos me = rnd;
+    me.step(warp, S);
+    for (int ch = 0; ch < nch; ++ch) {
+      const int k0 = ch * KC, klen = min(KC, p.K - k0);
+      if (stream) {
+        cp_async_wait<TS_STAGES - 2>();  // this thread's part of chunk ch has landed
+        bar_consumers();                 // ... everybody's has, and everybody is done with chunk ch - 1
+        a_chunk_load(ch + TS_STAGES - 1);  // into the stage chunk ch - 1 used
+      }
+      if (has) {
+        const bool timed = a.prof != nullptr && threadIdx.x == 0 && blockIdx.x == 0;
+        const long long tw0 = timed ? clock64() : 0;
+        if (lds32_volatile(smem_base + OFF_ISSUED) <= me.job) {
+          const long long t0 = clock64();
+          while (lds32_volatile(smem_base + OFF_ISSUED) <= me.job)
+            if (clock64() - t0 > SPIN_LIMIT) __trap();
+        }
+        const uint32_t slot = me.slot;
+        mbar_wait(smem_base + OFF_FULL + slot * 8, me.par);
+        const long long tw1 = timed ? clock64() : 0;
+        const uint32_t a_addr = stream ? act + (ch % TS_STAGES) * (16 * RS) : act + k0 * 2;
+        mma_chunk<1, false>(acc, acc2, ring + slot * a.slot_bytes, a_addr, AS, 0, klen >> 4, a.B, lane);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_base + OFF_EMPTY + slot * 8);
+        if (timed) {
+          unsigned long long* dbg = reinterpret_cast<unsigned long long*>(dbg_smem);
+          dbg[p.kind * 2] += (unsigned long long)(tw1 - tw0);
+          dbg[p.kind * 2 + 1] += (unsigned long long)(clock64() - tw1);
+        }
+        me.step(nact, S);
+      }
+    }
+    if (stream) {
+      cp_async_wait<0>();
+      bar_consumers();  // the stages are refilled by the next round / the next phase's row load
+    }
+    if (!has) continue;
+    const int n = row0 + c * 2;
+    if (n >= p.rows[seg]) continue;
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int tok = tok0 + g + hr * 8;
+      if (tok < a.B) epilogue_store<MT>(a, p, seg, tok, n, acc[0][hr * 2], acc[0][hr * 2 + 1], 0.f, 0.f, 0u);
+    }
+  }
+  if (n_c > 0) base.advance((uint32_t)(n_c * nch), a.ph_adv_slot[p.kind][p.cls], a.ph_adv_par[p.kind][p.cls], S);
 }
 
 template <int MT>
 __device__ __forceinline__ void gemm_phase(const MegaArgs& a, const Phase& p, uint32_t smem_base, RingPos& base,
                                            const bf16* a_src, Best (&best)[MT == 0 ? 1 : MT][2],
                                            unsigned char* dbg_smem) {
-  if (MT >= 2 && p.nu != NW)
+  if (MT >= 2 && p.ts)
+    gemm_ts<MT>(a, p, smem_base, base, a_src, dbg_smem);  // one token tile per CTA
+  else if (MT >= 2 && p.nu != NW)
     gemm_inner<MT, 1>(a, p, smem_base, base, a_src, best, dbg_smem);  // one token tile per warp
   else
     gemm_inner<MT, MT>(a, p, smem_base, base, a_src, best, dbg_smem);
@@ -1698,12 +1828,17 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
       stamp();
       grid_sync(a.bar, epoch);
       stamp();
-      load_rows(act, a.B, Dq, [&](int b) { return a.att + (size_t)b * Dq; });
+      if (a.ph_ts[PH_O]) {  // tile-split: this CTA's 16-row token tile only
+        const int tok0 = ((int)blockIdx.x % a.mtt) * 16;
+        load_rows(act, min(16, a.B - tok0), Dq, [&](int b) { return a.att + (size_t)(tok0 + b) * Dq; });
+      } else {
+        load_rows(act, a.B, Dq, [&](int b) { return a.att + (size_t)b * Dq; });
+      }
       stamp();
     } else if (kind == PH_DOWN) {
       // ---- down + residual
       if (a.kv_l2_prefetch && l + 1 < L) attention_prefetch_l2<NP>(a, l + 1);
-      if (a.stream_down)
+      if (a.stream_down || a.ph_ts[PH_DOWN])
         a_src = a.h;
       else
         load_rows(act, a.B, a.I, [&](int b) { return a.h + (size_t)b * a.I; });
@@ -1737,7 +1872,12 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
         }
         grid_sync(a.bar, epoch);
         stamp();
-        load_rows(act, a.B, H, [&](int r) { return a.xn + (size_t)r * H; });
+        if (a.ph_ts[kind == PH_LMHEAD ? PH_LMHEAD : kind]) {  // tile-split (QKV): this CTA's token tile only
+          const int tok0 = ((int)blockIdx.x % a.mtt) * 16;
+          load_rows(act, min(16, a.B - tok0), H, [&](int r) { return a.xn + (size_t)(tok0 + r) * H; });
+        } else {
+          load_rows(act, a.B, H, [&](int r) { return a.xn + (size_t)r * H; });
+        }
         stamp();
       } else {
         if (tp && !from_embed) {
@@ -1999,6 +2139,11 @@ cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st) {
   a.off_red = g.off_red;
   a.attn_group = g.group;
   a.dist_norm = a.B > 16 && a.B <= num_sms && a.xn != nullptr;
+  a.mtt = g.mt == 0 ? 1 : g.mt;
+  // tile split needs the tiles to cover the rows it is given (mtt = 2: 17..32 rows, 4: 33..64) and no tensor parallel
+  // exchange in the epilogue (kept on the default mapping); QIE_MEGA_TS=0 switches it off (A/B knob)
+  static const bool ts_env = [] { const char* v = getenv("QIE_MEGA_TS"); return !(v && v[0] == '0'); }();
+  const bool ts_on = ts_env && a.tp_size <= 1 && !a.fast;
   {  // per phase kind: units of a CTA (q, +1 for the first r CTAs), chunks, and ring advances modulo the slot count
     const int Dq = a.n_q * a.hd, Dkv = a.n_kv * a.hd;
     const int units[5] = {(Dq + 7) / 8 + 2 * ((Dkv + 7) / 8), (a.H + 7) / 8, (a.I + 7) / 8, (a.H + 7) / 8, (a.V + 15) / 16};
@@ -2013,10 +2158,24 @@ cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st) {
         a.ph_adv_slot[k][cls] = jobs % S;
         a.ph_adv_par[k][cls] = (jobs / S) & 1;
       }
-      // phases with at most one unit per CTA spread the token tiles of that unit over MT warps
+      // phases with at most one unit per CTA spread the token tiles of that unit over MT warps -- or, where the
+      // normalised rows come from the row-per-CTA path (dist_norm) / plain buffers, over CTAs (tile split, gemm_ts)
       const int mtt = g.mt == 0 ? 1 : g.mt;
       const bool split = mtt >= 2 && units[k] <= num_sms && k != 4;
-      a.ph_nu[k] = split ? NW / mtt : NW;
+      const bool ts = split && ts_on && (k == PH_O || k == PH_DOWN || (k == PH_QKV && a.dist_norm));
+      a.ph_ts[k] = ts ? 1 : 0;
+      a.ph_G[k] = ts ? num_sms / mtt : 0;
+      if (ts) {
+        const int G = a.ph_G[k];
+        a.ph_q[k] = units[k] / G;
+        a.ph_r[k] = units[k] % G;
+        for (int cls = 0; cls < 2; ++cls) {
+          const int jobs = (a.ph_q[k] + cls) * a.ph_nch[k];
+          a.ph_adv_slot[k][cls] = jobs % S;
+          a.ph_adv_par[k][cls] = (jobs / S) & 1;
+        }
+      }
+      a.ph_nu[k] = ts ? NW : (split ? NW / mtt : NW);
       if (a.fast)  // split-K rounds of <= FAST_U units
         a.ph_nu[k] = std::max(1, std::min(FAST_U, (units[k] + num_sms - 1) / num_sms));
       const int rj = a.ph_nu[k] * a.ph_nch[k];

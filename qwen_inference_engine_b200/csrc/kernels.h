@@ -224,6 +224,7 @@ struct MegaArgs {
   int KC;  // k elements per weight tile = box depth of wmaps (decode_mega_kc at engine setup)
   // geometry, filled by the launcher (ph_*: per GEMM phase kind qkv/o/gate+up/down/lm_head)
   int ph_nu[5];  // units per round (NW, or NW / token tiles when the tiles of a unit are spread over warps)
+  int ph_ts[5], ph_G[5], mtt;  // tile-split phases: CTA c owns token tile c % mtt and the units c / mtt + i * G (gemm_ts)
   int ph_q[5], ph_r[5], ph_nch[5], ph_adv_slot[5][2], ph_adv_par[5][2], ph_round_slot[5], ph_round_par[5];
   int n_slots, slot_bytes, act_bytes, off_act, off_ring, stream_down, attn_kstg, attn_off, off_red, attn_group;
 };
