@@ -711,7 +711,7 @@ __device__ __forceinline__ void gemm_inner(const MegaArgs& a, const Phase& p, ui
 // cp.async ring for down_proj (155 KB per CTA instead of 622 KB, one barrier per chunk) -- and the weights of a unit
 // are fetched by the T CTAs of its group from L2 (HBM still sees them once).  Same arithmetic: one dependent chain per
 // (unit, tile) with k ascending.
-constexpr int TS_STAGES = 4;
+constexpr int TS_STAGES = 4;  // measured: 7 stages change nothing (the phase is not bound by the depth of the A stream)
 template <int MT>
 __device__ __forceinline__ void gemm_ts(const MegaArgs& a, const Phase& p, uint32_t smem_base, RingPos& base, const bf16* a_src,
                                         unsigned char* dbg_smem) {
@@ -725,13 +725,23 @@ __device__ __forceinline__ void gemm_ts(const MegaArgs& a, const Phase& p, uint3
   const int n_c = p.n_c, nch = p.nch;
   const int tok0 = p.tile * 16, nrows = min(16, a.B - tok0);
   RingPos rnd = base;
+  // A stream: piece i of a chunk is (row i / per, 16-byte column i % per); the threads from warp lw0 on walk their pieces
+  // incrementally (one division per chunk).  All consumer threads copy (lw0 = 0).
+  int lw0 = 0;  // first loader warp of the current round
   auto a_chunk_load = [&](int ch) {  // rows of this tile x [ch*KC, +klen) -> stage ch % TS_STAGES (an empty group past the end)
-    if (ch < nch) {
+    const int lj = (int)threadIdx.x - lw0 * 32;
+    if (ch < nch && lj >= 0) {
+      const int NL = NTC - lw0 * 32;
       const int k0 = ch * KC, klen = min(KC, p.K - k0), per = klen >> 3;
       const uint32_t dst = act + (ch % TS_STAGES) * (16 * RS);
-      for (int i = threadIdx.x; i < nrows * per; i += NTC) {
-        const int b = i / per, cc = i - b * per;
+      int b = lj / per, cc = lj - b * per;
+      while (b < nrows) {
         cp_async16(dst + b * RS + cc * 16, a_src + (size_t)(tok0 + b) * p.K + k0 + cc * 8);
+        cc += NL;
+        while (cc >= per) {
+          cc -= per;
+          ++b;
+        }
       }
     }
     cp_async_commit();
@@ -747,6 +757,7 @@ __device__ __forceinline__ void gemm_ts(const MegaArgs& a, const Phase& p, uint3
       row0 = (u - p.ubeg[seg]) * p.upr;
     }
     float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}}, acc2[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+    lw0 = 0;  // measured (B200, batch 64): leaving the copies to the warps without a unit is slower (20.0 vs 17.0 us per layer)
     if (stream)
       for (int s = 0; s < TS_STAGES - 1; ++s) a_chunk_load(s);
     RingPos me = rnd;
@@ -2063,6 +2074,7 @@ bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int ma
   if (fast && B > 8) return false;
   const int stream_down = !fast && res_i > 48 * 1024;  // fast numerics keeps [B, I] resident (<= 8 rows)
   int act = std::max(res_h, stream_down ? strm : res_i);
+  if (mt >= 2) act = std::max(act, TS_STAGES * 16 * (KC + 8) * 2);  // tile-split down_proj: stages of the 16-row A stream (gemm_ts)
   const int hs = (B * n_q <= grid) ? 1 : n_q / n_kv;
   const int group = hs > 1 && hd == 64 && psz > 0 && (psz & (psz - 1)) == 0;  // query-group tasks with K and V tiles in shared memory (attention_group_phase)
   const int tmax = (max_kv_len + 3) & ~3;
