@@ -1081,7 +1081,8 @@ __device__ __forceinline__ float dot_tree_f(const float* __restrict__ q, const f
 // q[4u..4u+3] and q[HD/2+4u..]; when pair u has been consumed its slot is refilled with pair u+4 (of the NEXT head
 // once this one runs out), so every broadcast LDS.128 is issued ~4 pairs (two dozen FP instructions) before its use.
 // With 7 warps per SM nothing else hides the shared-memory latency, and holding a whole head (64 registers) next to
-// the fp32 K row (64) spills.
+// the fp32 K row (64) spills.  (Measured dead end: the query head as packed bf16 -- half the shared-memory bytes, two
+// ALU instructions per pair to widen -- makes the loop 20 % SLOWER: it is bound by issue slots, not by the LSU.)
 template <int HD>
 __device__ __forceinline__ float dot_tree_w(float4 (&wa)[4], float4 (&wb)[4], const float2 (&kf)[HD / 2], const float* __restrict__ q,
                                             const float* __restrict__ qnext) {
@@ -1507,6 +1508,9 @@ __host__ __device__ inline int attn_score_pitch(int max_kv_len) { return ((max_k
 template <int NH>
 __device__ __forceinline__ void pv_tile(const unsigned char* __restrict__ vl, const float* __restrict__ sb, int hstride, int tn,
                                         float2 (&o)[2]) {
+  // bf16 pair -> two floats on the ALU pipe only (PRMT / LOP3): the shift form becomes IMAD.U32 every other time, which
+  // shares the FMA pipe with the FFMA2 chain (math-pipe throttle was 12 % of this loop's stall samples)
+  auto cvt2 = [](uint32_t v) { return make_float2(__uint_as_float(__byte_perm(v, 0u, 0x1044)), __uint_as_float(v & 0xffff0000u)); };
   auto load4 = [&](uint32_t (&vv)[4], float4 (&pr)[NH], int kk) {
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) vv[jj] = *reinterpret_cast<const uint32_t*>(vl + (kk + jj) * 128);
@@ -1516,7 +1520,7 @@ __device__ __forceinline__ void pv_tile(const unsigned char* __restrict__ vl, co
   auto fma4 = [&](const uint32_t (&vv)[4], const float4 (&pr)[NH]) {
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
-      const float2 vf = make_float2(lo2f(vv[jj]), hi2f(vv[jj]));
+      const float2 vf = cvt2(vv[jj]);
 #pragma unroll
       for (int hh = 0; hh < NH; ++hh) {
         const float pj = jj == 0 ? pr[hh].x : (jj == 1 ? pr[hh].y : (jj == 2 ? pr[hh].z : pr[hh].w));
@@ -1525,23 +1529,36 @@ __device__ __forceinline__ void pv_tile(const unsigned char* __restrict__ vl, co
     }
   };
   int k = 0;
-  const int n8 = tn & ~7;
-  if (n8) {
-    uint32_t va[4], vb[4];
-    float4 pa[NH], pb[NH];
+  // 16 positions per iteration in four operand sets of 4; a set is reloaded (16 positions ahead) right behind its use,
+  // so every load has the other three sets' chains (~50 cycles) to land and the loop overhead is paid once per 16
+  const int n16 = tn & ~15;
+  if (n16) {
+    uint32_t va[4], vb[4], vc[4], vd[4];
+    float4 pa[NH], pb[NH], pc[NH], pd[NH];
     load4(va, pa, 0);
     load4(vb, pb, 4);
+    load4(vc, pc, 8);
+    load4(vd, pd, 12);
 #pragma unroll 1
-    for (; k < n8; k += 8) {
+    for (; k + 16 < n16; k += 16) {
       fma4(va, pa);
-      if (k + 8 < n8) load4(va, pa, k + 8);
+      load4(va, pa, k + 16);
       fma4(vb, pb);
-      if (k + 12 < n8) load4(vb, pb, k + 12);
+      load4(vb, pb, k + 20);
+      fma4(vc, pc);
+      load4(vc, pc, k + 24);
+      fma4(vd, pd);
+      load4(vd, pd, k + 28);
     }
+    fma4(va, pa);
+    fma4(vb, pb);
+    fma4(vc, pc);
+    fma4(vd, pd);
+    k += 16;
   }
   for (; k < tn; ++k) {
     const uint32_t v1 = *reinterpret_cast<const uint32_t*>(vl + k * 128);
-    const float2 vf = make_float2(lo2f(v1), hi2f(v1));
+    const float2 vf = cvt2(v1);
 #pragma unroll
     for (int hh = 0; hh < NH; ++hh) {
       const float pj = sb[hh * hstride + k];
@@ -1553,9 +1570,12 @@ __device__ __forceinline__ void pv_tile(const unsigned char* __restrict__ vl, co
 __device__ __noinline__ void attention_group_phase(const MegaArgs& a, int layer, unsigned char* smem) {
   constexpr int HD = 64, NP = 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int hs = a.n_q / a.n_kv;
+  // a task is (row, kv head, part): the query group of a kv head (hsk heads) is cut into parts of hp heads while all
+  // tasks still fit one wave of CTAs (batch 64: one part of 7 heads, 128 tasks; batch 32: 4 + 3 heads, 128 tasks; batch
+  // 16: 2 + 2 + 2 + 1, 128 tasks) -- r02 first version: one task per (row, kv head) left most SMs idle below 64 rows
+  const int hsk = a.n_q / a.n_kv, hp = a.attn_hp, nparts = (hsk + hp - 1) / hp;
   const int Dq = a.n_q * HD, Dkv = a.n_kv * HD, QKV = Dq + 2 * Dkv;
-  const int ntask = a.B * a.n_kv;
+  const int ntask = a.B * a.n_kv * nparts;
   const int SP = attn_score_pitch(a.max_kv_len);
   const int psz = a.kv.page_size;             // a power of two on this path (mega_geometry)
   const int psz_shift = __ffs(psz) - 1;
@@ -1563,11 +1583,11 @@ __device__ __noinline__ void attention_group_phase(const MegaArgs& a, int layer,
   const uint32_t pstride_b = (uint32_t)(a.kv.page_stride() * sizeof(bf16));
   const MegaLayer& w = reinterpret_cast<const MegaLayer*>(smem + OFF_LAYERS)[layer];
 
-  float* q_s = reinterpret_cast<float*>(smem + a.off_act);   // [hs][HD] fp32
-  bf16* knew = reinterpret_cast<bf16*>(q_s + hs * HD);        // [HD]
+  float* q_s = reinterpret_cast<float*>(smem + a.off_act);   // [hp][HD] fp32
+  bf16* knew = reinterpret_cast<bf16*>(q_s + hp * HD);        // [HD]
   bf16* vnew = knew + HD;
   float* score = reinterpret_cast<float*>(vnew + HD);         // [hs][SP]
-  unsigned char* kvb = reinterpret_cast<unsigned char*>(score + hs * SP);  // [2][AT][128]
+  unsigned char* kvb = reinterpret_cast<unsigned char*>(score + hp * SP);  // [2][AT][128]
   const uint32_t kvb_u32 = smem_u32(kvb);
   int* pages = reinterpret_cast<int*>(kvb + 2 * AT_BYTES);    // [max_kv_len / page_size + 1]
 
@@ -1582,7 +1602,10 @@ __device__ __noinline__ void attention_group_phase(const MegaArgs& a, int layer,
         tq = t;
       }
     };
-    const int b = task / a.n_kv, kvh = task - b * a.n_kv, h0 = kvh * hs;
+    const int bk = task / nparts, part = task - bk * nparts;
+    const int b = bk / a.n_kv, kvh = bk - b * a.n_kv, h0 = kvh * hsk + part * hp;
+    const int hs = min(hp, hsk - part * hp);  // query heads of this task
+    const bool writer = part == 0;           // one task per (row, kv head) stores the new K / V row
     const int ps = a.pos[b];                      // cached positions 0..ps-1, the new one is ps
     const int* bt = a.block_table + (size_t)a.slot[b] * a.max_pages;
     const int ns = ps / AT + 1;                   // score tiles (the last one holds position ps)
@@ -1631,11 +1654,11 @@ __device__ __noinline__ void attention_group_phase(const MegaArgs& a, int layer,
           if (w.k_norm) head_norm<NP>(v, w.k_norm, lane);
           head_rope<NP>(v, cos_row, sin_row, lane);
           head_store<NP>(v, knew, lane);
-          head_store<NP>(v, a.kv.chunk(new_page, layer, 0, kvh) + (size_t)new_off * HD, lane);
+          if (writer) head_store<NP>(v, a.kv.chunk(new_page, layer, 0, kvh) + (size_t)new_off * HD, lane);
         } else {
           head_load_cg<NP>(v, row + Dq + Dkv + (size_t)kvh * HD, lane);
           head_store<NP>(v, vnew, lane);
-          head_store<NP>(v, a.kv.chunk(new_page, layer, 1, kvh) + (size_t)new_off * HD, lane);
+          if (writer) head_store<NP>(v, a.kv.chunk(new_page, layer, 1, kvh) + (size_t)new_off * HD, lane);
         }
       }
     }
@@ -2150,6 +2173,13 @@ cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st) {
   a.attn_off = g.attn_off;
   a.off_red = g.off_red;
   a.attn_group = g.group;
+  a.attn_hp = 1;
+  if (g.group) {  // heads per attention task: the smallest part size whose tasks fit one wave
+    const int hsk = a.n_q / a.n_kv;
+    int hp = 1;
+    while (hp < hsk && a.B * a.n_kv * ((hsk + hp - 1) / hp) > num_sms) ++hp;
+    a.attn_hp = hp;
+  }
   a.dist_norm = a.B > 16 && a.B <= num_sms && a.xn != nullptr;
   a.mtt = g.mt == 0 ? 1 : g.mt;
   // tile split needs the tiles to cover the rows it is given (mtt = 2: 17..32 rows, 4: 33..64) and no tensor parallel

@@ -226,7 +226,7 @@ struct MegaArgs {
   int ph_nu[5];  // units per round (NW, or NW / token tiles when the tiles of a unit are spread over warps)
   int ph_ts[5], ph_G[5], mtt;  // tile-split phases: CTA c owns token tile c % mtt and the units c / mtt + i * G (gemm_ts)
   int ph_q[5], ph_r[5], ph_nch[5], ph_adv_slot[5][2], ph_adv_par[5][2], ph_round_slot[5], ph_round_par[5];
-  int n_slots, slot_bytes, act_bytes, off_act, off_ring, stream_down, attn_kstg, attn_off, off_red, attn_group;
+  int n_slots, slot_bytes, act_bytes, off_act, off_ring, stream_down, attn_kstg, attn_off, off_red, attn_group, attn_hp;
 };
 // max rows the persistent kernel accepts for this model shape (0 = shape unsupported)
 int decode_mega_kc(int H, int big);  // k elements per weight tile (box depth of the weight tensor maps); big: batches <= 8
