@@ -103,6 +103,19 @@ int qie_attention(const qie_kv_view* kv, int layer, const qie_bf16* Q, qie_bf16*
                   const int* slot, const int* block_table, int max_pages, int n_tok, int n_q_heads,
                   qie_stream st);
 
+/* The same two operators over the REFERENCE's own cache: a list of pages, each a K and a V device buffer of
+ * page_size * n_layers * kv_dim bf16 laid out [slot][layer][kv_dim] (include/iengine.cuh:42-48, src/iengine.cu:89-96,
+ * element ((pos % page_size) * n_layers + layer) * kv_dim, src/include_cuda.cu:165-279).  d_k_pages / d_v_pages are
+ * DEVICE arrays of n_pages device pointers in list order -- what the reference's kernel finds by walking
+ * ptr_to_next_page (src/self_attension.cu:47-53,124-126).  All rows belong to that one sequence; row t attends to
+ * positions 0..pos[t].  These are what include/layers/iengine_compat.hh's launch_attn(..., page_table*, page_size) and
+ * kv_copy_layer_to_cache_{prefill,decode} call, so a caller that owns reference pages needs no engine. */
+int qie_attention_pagelist(const qie_bf16* const* d_k_pages, const qie_bf16* const* d_v_pages, int n_pages, int page_size,
+                           int n_layers, int layer, int n_kv_heads, int head_dim, const qie_bf16* Q, qie_bf16* out, const int* pos,
+                           int n_tok, int n_q_heads, qie_stream st);
+int qie_kv_store_pagelist(qie_bf16* const* d_k_pages, qie_bf16* const* d_v_pages, int n_pages, int page_size, int n_layers,
+                          int layer, int kv_dim, const qie_bf16* K, const qie_bf16* V, int pos0, int n_tok, qie_stream st);
+
 /* sample_topk_bf16 -> topk_temperature_softmax_sampling_kernel_bf16,
  * helpers.cuh:157-166 / src/logit_decode.cu:149-274. One row of `vocab` bf16 logits per
  * sequence; same arg-max tie-break and XORWOW stream (subsequence 0) as the reference.

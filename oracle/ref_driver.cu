@@ -23,12 +23,29 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <iostream>
 #include <vector>
 
+// The SAME driver compiles two ways (oracle/Makefile):
+//   default            against the reference's own helpers.cuh + kernels            -> _ref/libqie_ref.so
+//   -DQIE_COMPAT_REPLAY against include/layers/iengine_compat.hh + libqie_b200.so   -> _compat/libqie_compat_replay.so
+// The second build is the drop-in proof for the operator-level boundary: llm()'s call sequence, written
+// once against the reference's names (launch_rms, proj/launch_matmul, launch_qknorm, launch_rope[_single],
+// kv_copy_layer_to_cache_*, launch_attn over a page_table list, launch_act/elem/resadd, copy_*_vec, sample_topk_bf16,
+// create_page_list / allocate_page_buffers, ModelBuffers), links and runs against the B200 library unchanged; the two
+// .so files export the same ref_* entry points and tests compare their results bit for bit.  The only source-level
+// difference is the three direct <<<>>> launches of the reference (embedding x2, sampler), which cannot cross a
+// shared-library boundary and go through launch_embedding / sample_topk_bf16 in the compat build.
+#ifdef QIE_COMPAT_REPLAY
+#include "layers/iengine_compat.hh"
+static void qie_ref_set_attn_dims(int, int) {}  // the compat launch_attn derives both from its arguments
+#define QIE_EMBED(blocks, threads, out, table, ids, hidden, n) launch_embedding(out, table, ids, hidden, n)
+#else
 #include "helpers.cuh"  // reference: launch_* wrappers (non-inline: include from ONE TU only)
 
 void precompute_cos_sin(float* cos_values, float* sin_values, int seq_len, int head_dim);
 extern "C" void qie_ref_set_attn_dims(int group, int layers);  // appended to the patched attention TU
+#define QIE_EMBED(blocks, threads, out, table, ids, hidden, n) embedding_matrix_func<<<blocks, threads>>>(out, table, ids, hidden, n)
 
 // Referenced only by the reference's main() (src/iengine.cu:226, compiled with
 // -Dmain=qie_ref_unused_main to get create_page_list & co.); never called from here.
@@ -39,6 +56,7 @@ int llm(batch_metadata*, std::unordered_map<std::string, std::vector<tensor>>, s
         __nv_bfloat16*) {
   abort();
 }
+#endif
 
 namespace {
 struct Quiet {  // the reference prints from kv_copy_layer_to_cache_decode (include_cuda.cu:267) etc.
@@ -73,7 +91,7 @@ extern "C" {
 // ------------------------------------------------------------------ single operators
 int ref_embedding(__nv_bfloat16* out, __nv_bfloat16* table, int* ids, size_t hidden, size_t n_tok) {
   int threads = 256, blocks = (int)((n_tok + threads - 1) / threads);  // utills.cu:51-54
-  embedding_matrix_func<<<blocks, threads>>>(out, table, ids, hidden, n_tok);
+  QIE_EMBED(blocks, threads, out, table, ids, hidden, n_tok);
   return sync_check("embedding");
 }
 int ref_rmsnorm(__nv_bfloat16* x, __nv_bfloat16* w, __nv_bfloat16* y, size_t hidden, size_t seqlen) {
@@ -128,6 +146,10 @@ void* ref_pages_create(int n_pages, size_t elems_per_page) {
   return head;
 }
 void ref_pages_free(void* h) {  // free_page_list() std::free()s managed memory (iengine.cu:104); do it properly
+#ifdef QIE_COMPAT_REPLAY
+  free_page_list((page_table*)h);
+  return;
+#endif
   page_table* p = (page_table*)h;
   while (p) {
     page_table* nx = p->ptr_to_next_page;
@@ -354,8 +376,7 @@ int ref_forward_prefill(void* h, const int* ids, int n_tok, int topk, float temp
   b->k_cache = s->pages->k_page_ptr;  // iengine.cu:359-360
   b->v_cache = s->pages->v_page_ptr;
   int threads = 256, blocks = (n_tok + threads - 1) / threads;
-  embedding_matrix_func<<<blocks, threads>>>(b->embeddings_out, b->embeddings_d, b->d_token_ids, b->hidden_dim,
-                                             b->sequence_len);
+  QIE_EMBED(blocks, threads, b->embeddings_out, b->embeddings_d, b->d_token_ids, b->hidden_dim, b->sequence_len);
   for (int i = 0; i < (int)b->number_of_layers; ++i) layer_body(s, i, n_tok, false, false, tap, user);
   launch_rms(b->embeddings_out, s->m.norm, b->rms_out, b->hidden_dim, b->sequence_len);
   copy_last_vocab_vec(b->rms_out, b->last_x, (int)b->hidden_dim, (int)b->sequence_len);
@@ -395,13 +416,16 @@ int ref_forward_decode(void* h, int token, int topk, float temperature, unsigned
   cudaMemcpy(d_token_ids_decode, &token, sizeof(int), cudaMemcpyHostToDevice);
   if (with_syncs) cudaDeviceSynchronize();
   b->sequence_len = b->sequence_len + 1;
-  embedding_matrix_func<<<1, 1>>>(b->embeddings_out, b->embeddings_d, d_token_ids_decode, b->hidden_dim, 1);
+  QIE_EMBED(1, 1, b->embeddings_out, b->embeddings_d, d_token_ids_decode, b->hidden_dim, 1);
   if (with_syncs) cudaDeviceSynchronize();
   for (int i = 0; i < (int)b->number_of_layers; ++i) layer_body(s, i, 1, true, with_syncs != 0, tap, user);
   launch_rms(b->embeddings_out, s->m.norm, b->rms_out, b->hidden_dim, 1);
   copy_first_token(b->rms_out, b->last_x, (int)b->hidden_dim);
   launch_matmul(b->last_x, s->m.lm_head, b->prefill_output_d, 1, (int)b->hidden_dim, (int)b->vocab_size);
   if (sync_check("decode")) return -1000000;
+#ifdef QIE_COMPAT_REPLAY
+  int out = sample_topk_bf16(b->prefill_output_d, (int)b->vocab_size, temperature, topk, seed + s->step, 0);
+#else
   int* d_output_token;
   cudaMalloc(&d_output_token, sizeof(int));  // :383
   cudaDeviceSynchronize();
@@ -412,6 +436,7 @@ int ref_forward_decode(void* h, int token, int topk, float temperature, unsigned
   cudaMemcpy(&out, d_output_token, sizeof(int), cudaMemcpyDeviceToHost);
   cudaDeviceSynchronize();
   cudaFree(d_output_token);
+#endif
   cudaFree(d_token_ids_decode);
   s->step += 1;
   return out;

@@ -74,6 +74,8 @@ def lib():
         "qie_residual_add": (i32, [vp, vp, sz, vp]),
         "qie_kv_store": (i32, [C.POINTER(KvView), i32, vp, vp, vp, vp, vp, i32, i32, vp]),
         "qie_attention": (i32, [C.POINTER(KvView), i32, vp, vp, vp, vp, vp, i32, i32, i32, vp]),
+        "qie_attention_pagelist": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, i32, vp]),
+        "qie_kv_store_pagelist": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp]),
         "qie_sample_topk": (i32, [vp, vp, i32, sz, f32, i32, u64, u64, vp]),
         "qie_sample_topk_subseq": (i32, [vp, vp, i32, sz, f32, i32, u64, u64, u64, vp]),
         "qie_matmul_fast": (i32, [vp, vp, vp, i32, i32, i32, vp]),

@@ -137,6 +137,39 @@ int qie_attention(const qie_kv_view* kv, int layer, const qie_bf16* Q, qie_bf16*
   CU(launch_attention_ref(a, (cudaStream_t)st));
   return QIE_OK;
 }
+int qie_attention_pagelist(const qie_bf16* const* d_k_pages, const qie_bf16* const* d_v_pages, int n_pages, int page_size,
+                           int n_layers, int layer, int n_kv_heads, int head_dim, const qie_bf16* Q, qie_bf16* out, const int* pos,
+                           int n_tok, int n_q_heads, qie_stream st) {
+  if (!d_k_pages || !d_v_pages || n_pages <= 0 || page_size <= 0 || layer < 0 || layer >= n_layers || n_kv_heads <= 0 ||
+      n_q_heads % n_kv_heads)
+    return fail(QIE_EINVAL, "attention_pagelist: bad geometry");
+  AttnArgs a{};
+  a.q = (const bf16*)Q;
+  a.out = (bf16*)out;
+  a.pos = pos;
+  a.n_tok = n_tok;
+  a.n_q = n_q_heads;
+  a.layer = layer;
+  a.max_kv_len = n_pages * page_size;
+  a.kv.page_size = page_size;
+  a.kv.n_kv = n_kv_heads;
+  a.kv.hd = head_dim;
+  a.kv.n_layers = n_layers;
+  a.k_pages = reinterpret_cast<const bf16* const*>(d_k_pages);
+  a.v_pages = reinterpret_cast<const bf16* const*>(d_v_pages);
+  a.pl_layers = n_layers;
+  CU(launch_attention_ref(a, (cudaStream_t)st));
+  return QIE_OK;
+}
+int qie_kv_store_pagelist(qie_bf16* const* d_k_pages, qie_bf16* const* d_v_pages, int n_pages, int page_size, int n_layers,
+                          int layer, int kv_dim, const qie_bf16* K, const qie_bf16* V, int pos0, int n_tok, qie_stream st) {
+  if (!d_k_pages || !d_v_pages || page_size <= 0 || layer < 0 || layer >= n_layers || pos0 < 0 ||
+      (size_t)pos0 + n_tok > (size_t)n_pages * page_size)
+    return fail(QIE_EINVAL, "kv_store_pagelist: rows [%d, %d) do not fit %d pages of %d", pos0, pos0 + n_tok, n_pages, page_size);
+  CU(launch_kv_store_pagelist(reinterpret_cast<bf16* const*>(d_k_pages), reinterpret_cast<bf16* const*>(d_v_pages), page_size,
+                              n_layers, layer, kv_dim, (const bf16*)K, (const bf16*)V, pos0, n_tok, (cudaStream_t)st));
+  return QIE_OK;
+}
 int qie_sample_topk(const qie_bf16* logits, int* out_tokens, int n_rows, size_t vocab, float temperature, int k,
                     uint64_t seed, uint64_t seed_stride, qie_stream st) {
   CU(launch_sample_topk((const bf16*)logits, out_tokens, n_rows, vocab, temperature, k, seed, seed_stride, nullptr,

@@ -3,8 +3,10 @@
 // libqie_b200's kernels.
 #include "../../include/layers/iengine_compat.hh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <iostream>
 #include <map>
 #include <mutex>
@@ -60,7 +62,10 @@ TensorTable build_indexed_tensors() {  // tensor_parser.cpp:132-165
 
 void precompute_cos_sin(float* c, float* s, int seq_len, int head_dim) { qie_precompute_cos_sin(c, s, seq_len, head_dim); }
 
-// ---- page list: host bookkeeping only (KV memory is the engine's pool) -----------------
+// ---- page list (iengine.cu:72-109): host nodes, one device K / V buffer pair per page -----------------
+static std::mutex g_pg_mu;
+static std::map<page_table*, size_t> g_page_elems;  // node -> elems_per_page it was allocated with
+
 page_table* create_page_list(int pages_required) {
   page_table* head = nullptr;
   page_table** cur = &head;
@@ -74,15 +79,121 @@ page_table* create_page_list(int pages_required) {
   }
   return head;
 }
-void allocate_page_buffers(page_table* node, size_t) {
-  if (node) node->page_allocated = 1;  // pages are taken from the pool when positions are written
+void allocate_page_buffers(page_table* node, size_t elems_per_page) {
+  if (!node || node->k_page_ptr) return;
+  if (cudaMalloc(&node->k_page_ptr, elems_per_page * sizeof(__nv_bfloat16)) != cudaSuccess ||
+      cudaMalloc(&node->v_page_ptr, elems_per_page * sizeof(__nv_bfloat16)) != cudaSuccess) {
+    fprintf(stderr, "allocate_page_buffers: out of device memory\n");
+    abort();  // iengine.cu:51-70: the reference's allocator macros abort too
+  }
+  node->page_allocated = 1;
+  std::lock_guard<std::mutex> lk(g_pg_mu);
+  g_page_elems[node] = elems_per_page;
 }
 void free_page_list(page_table* head) {
+  cudaDeviceSynchronize();
+  std::lock_guard<std::mutex> lk(g_pg_mu);
   while (head) {
     page_table* next = head->ptr_to_next_page;
+    if (head->k_page_ptr) cudaFree(head->k_page_ptr);
+    if (head->v_page_ptr) cudaFree(head->v_page_ptr);
+    g_page_elems.erase(head);
     delete head;
     head = next;
   }
+}
+
+// device arrays of the list's K / V page pointers, in list order (what the reference's kernel finds by walking
+// ptr_to_next_page); rebuilt per call: the list may have grown (kv_copy_layer_to_cache_decode allocates on demand)
+struct PageArrays {
+  qie_bf16** d_k = nullptr;
+  qie_bf16** d_v = nullptr;
+  int n = 0;
+  size_t elems = 0;
+};
+static int gather_pages(page_table* head, PageArrays* out) {
+  std::vector<qie_bf16*> k, v;
+  size_t elems = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_pg_mu);
+    for (page_table* p = head; p && p->k_page_ptr; p = p->ptr_to_next_page) {
+      k.push_back(reinterpret_cast<qie_bf16*>(p->k_page_ptr));
+      v.push_back(reinterpret_cast<qie_bf16*>(p->v_page_ptr));
+      auto it = g_page_elems.find(p);
+      if (it != g_page_elems.end()) elems = it->second;
+    }
+  }
+  if (k.empty()) return QIE_EINVAL;
+  static thread_local qie_bf16** d_buf = nullptr;
+  static thread_local size_t d_cap = 0;
+  if (d_cap < 2 * k.size()) {
+    if (d_buf) cudaFree(d_buf);
+    d_cap = 2 * k.size() + 64;
+    if (cudaMalloc(&d_buf, d_cap * sizeof(void*)) != cudaSuccess) return QIE_ENOMEM;
+  }
+  cudaMemcpy(d_buf, k.data(), k.size() * sizeof(void*), cudaMemcpyHostToDevice);
+  cudaMemcpy(d_buf + k.size(), v.data(), v.size() * sizeof(void*), cudaMemcpyHostToDevice);
+  out->d_k = d_buf;
+  out->d_v = d_buf + k.size();
+  out->n = (int)k.size();
+  out->elems = elems;
+  return QIE_OK;
+}
+
+void kv_copy_layer_to_cache_prefill(ModelBuffers* b, int i, page_table* head, int page_size) {
+  PageArrays pa;
+  if (!b || gather_pages(head, &pa) != QIE_OK) return;
+  if (qie_kv_store_pagelist(pa.d_k, pa.d_v, pa.n, page_size, (int)b->number_of_layers, i, (int)b->hidden_dim_kv,
+                            reinterpret_cast<qie_bf16*>(b->K), reinterpret_cast<qie_bf16*>(b->V), 0, (int)b->sequence_len, nullptr) != QIE_OK)
+    fprintf(stderr, "kv_copy_layer_to_cache_prefill: %s\n", qie_last_error());
+  cudaStreamSynchronize(nullptr);  // the page-pointer scratch is reused by the next call
+}
+void kv_copy_layer_to_cache_decode(ModelBuffers* b, int i, page_table* head, int page_size) {
+  if (!b || !head) return;
+  const size_t pos = b->sequence_len - 1;
+  const int page_idx = (int)(pos / page_size);
+  // include_cuda.cu:248-261: a missing page is appended and allocated on the spot
+  page_table* p = head;
+  for (int n = 0; n < page_idx; ++n) {
+    if (!p->ptr_to_next_page) {
+      p->ptr_to_next_page = create_page_list(1);
+      allocate_page_buffers(p->ptr_to_next_page, (size_t)page_size * b->number_of_layers * b->hidden_dim_kv);
+    }
+    p = p->ptr_to_next_page;
+  }
+  PageArrays pa;
+  if (gather_pages(head, &pa) != QIE_OK) return;
+  if (qie_kv_store_pagelist(pa.d_k, pa.d_v, pa.n, page_size, (int)b->number_of_layers, i, (int)b->hidden_dim_kv,
+                            reinterpret_cast<qie_bf16*>(b->K), reinterpret_cast<qie_bf16*>(b->V), (int)pos, 1, nullptr) != QIE_OK)
+    fprintf(stderr, "kv_copy_layer_to_cache_decode: %s\n", qie_last_error());
+  cudaStreamSynchronize(nullptr);
+}
+
+void launch_attn(__nv_bfloat16* Q, __nv_bfloat16* out, size_t mq, size_t mkv, size_t head_dim, size_t hidden, size_t hidden_kv,
+                 int causal, size_t q_abs_base, int layer_id, page_table* head, int page_size) {
+  PageArrays pa;
+  if (gather_pages(head, &pa) != QIE_OK || !pa.elems || mq == 0 || mkv == 0) return;
+  const int n_layers = (int)(pa.elems / ((size_t)page_size * hidden_kv));  // the reference hard-codes 40 (self_attension.cu:35)
+  // row t sees positions 0 .. min(mkv - 1, q_abs_base + t) when causal, else 0 .. mkv - 1 (self_attension.cu:84-89)
+  std::vector<int> pos(mq);
+  for (size_t t = 0; t < mq; ++t) pos[t] = (int)(causal ? std::min(mkv - 1, q_abs_base + t) : mkv - 1);
+  static thread_local int* d_pos = nullptr;
+  static thread_local size_t d_pos_cap = 0;
+  if (d_pos_cap < mq) {
+    if (d_pos) cudaFree(d_pos);
+    d_pos_cap = mq + 256;
+    if (cudaMalloc(&d_pos, d_pos_cap * sizeof(int)) != cudaSuccess) return;
+  }
+  cudaMemcpy(d_pos, pos.data(), mq * sizeof(int), cudaMemcpyHostToDevice);
+  if (qie_attention_pagelist(pa.d_k, pa.d_v, pa.n, page_size, n_layers, layer_id, (int)(hidden_kv / head_dim), (int)head_dim,
+                             reinterpret_cast<qie_bf16*>(Q), reinterpret_cast<qie_bf16*>(out), d_pos, (int)mq, (int)(hidden / head_dim),
+                             nullptr) != QIE_OK)
+    fprintf(stderr, "launch_attn: %s\n", qie_last_error());
+  cudaStreamSynchronize(nullptr);  // helpers.cuh:128: the reference wrapper synchronises (d_pos / page arrays are reused)
+}
+
+void launch_embedding(__nv_bfloat16* out, __nv_bfloat16* table, int* d_token_ids, size_t hidden, size_t n_tok) {
+  qie_embedding(reinterpret_cast<qie_bf16*>(out), reinterpret_cast<qie_bf16*>(table), d_token_ids, hidden, n_tok, nullptr);
 }
 
 // ---- engine binding ---------------------------------------------------------------------
@@ -104,15 +215,26 @@ qie_engine* qie_compat_engine(__nv_bfloat16* blob) {
     fprintf(stderr, "qie compat: %s\n", qie_last_error());
     return nullptr;
   }
-  // the reference hard-codes top-k 50, T = 1.0 (prefill) / 0.7 (decode), seed 1234 + step
-  qie_engine_set_sampling(e, 50, 1.0f, 0.7f, 1234, 1);
+  // the reference hard-codes top-k 50, T = 1.0 (prefill) / 0.7 (decode), seed 1234 + step (qwen_main.cu:241,381-388);
+  // QIE_COMPAT_TOPK overrides k (1 = the greedy mode BASELINE configs[0] asks for)
+  int topk = 50;
+  if (const char* v = getenv("QIE_COMPAT_TOPK")) topk = std::max(1, atoi(v));
+  qie_engine_set_sampling(e, topk, 1.0f, 0.7f, 1234, 1);
   g_engines[blob] = e;
   return e;
 }
 
+// driver-level state that the reference keeps implicitly (the prompt lives in d_token_ids, the sequence in its page
+// list): the prompt ids on the host and the engine sequence slot, keyed by the ModelBuffers the caller owns
+struct CompatSeq {
+  std::vector<int> ids;
+  int seq = -1;
+};
+static std::map<ModelBuffers*, CompatSeq> g_seqs;
+
 void initialize_model_buffers(ModelBuffers& buf, int* h_token_ids, TensorTable& tensors, std::ifstream&, size_t n) {
+  memset(&buf, 0, sizeof(buf));
   buf.sequence_len = n;
-  buf.h_token_ids.assign(h_token_ids, h_token_ids + n);
   auto dim = [&](const char* name, int i) -> size_t {
     auto it = tensors.find(name);
     return it == tensors.end() || it->second.empty() || (int)it->second[0].shape.size() <= i ? 0 : it->second[0].shape[i];
@@ -126,21 +248,31 @@ void initialize_model_buffers(ModelBuffers& buf, int* h_token_ids, TensorTable& 
   buf.num_of_kvheads = buf.head_dim ? buf.hidden_dim_kv / buf.head_dim : 0;
   buf.number_of_layers = tensors.count("input_layernorm.weight") ? tensors["input_layernorm.weight"].size() : 0;
   buf.context_size = CONTEXT_SIZE;
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_seqs[&buf].ids.assign(h_token_ids, h_token_ids + n);
 }
-void destroy_model_buffers(ModelBuffers& buf) { buf.h_token_ids.clear(); }
+void destroy_model_buffers(ModelBuffers& buf) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_seqs.erase(&buf);
+}
 
 int llm(batch_metadata* seq, TensorTable, std::ifstream&, page_table*, int, __nv_bfloat16* blob) {
   qie_engine* e = qie_compat_engine(blob);
   if (!e || !seq || !seq->buffer) return QIE_EINVAL;
   ModelBuffers* b = seq->buffer;
-  if (b->qie_seq < 0 && qie_seq_new(e, &b->qie_seq) != QIE_OK) return QIE_ENOMEM;
+  CompatSeq* cs;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    cs = &g_seqs[b];
+  }
+  if (cs->seq < 0 && qie_seq_new(e, &cs->seq) != QIE_OK) return QIE_ENOMEM;
   int32_t tok = 0;
   int rc;
   if (seq->state == prefill) {
-    rc = qie_prefill(e, b->qie_seq, b->h_token_ids.data(), (int)b->h_token_ids.size(), &tok);
+    rc = qie_prefill(e, cs->seq, cs->ids.data(), (int)cs->ids.size(), &tok);
   } else {
     int32_t in = seq->generated_token;
-    rc = qie_decode_step(e, &b->qie_seq, &in, 1, &tok);
+    rc = qie_decode_step(e, &cs->seq, &in, 1, &tok);
     b->sequence_len += 1;  // qwen_main.cu:265
   }
   if (rc != QIE_OK) {

@@ -94,8 +94,18 @@ struct AttnArgs {
   int max_pages, n_tok, n_q, layer;
   int max_kv_len;  // upper bound on pos[t]+1 (sizes shared memory)
   KvGeom kv;
+  // page-list mode (the reference's own cache layout, include/iengine.cuh:42-48 + include_cuda.cu:165-279): when
+  // k_pages != nullptr, position p of the ONE sequence all rows belong to lives in page p / kv.page_size at element
+  // ((p % kv.page_size) * pl_layers + layer) * n_kv*hd of k_pages[..] / v_pages[..]; slot / block_table are unused and
+  // kv carries only page_size, n_kv, hd
+  const bf16* const* k_pages = nullptr;
+  const bf16* const* v_pages = nullptr;
+  int pl_layers = 0;
 };
 cudaError_t launch_attention_ref(const AttnArgs& a, cudaStream_t st);
+// K, V rows [n_tok, kv_dim] -> positions pos0 + t of a page list in the reference's layout (see AttnArgs)
+cudaError_t launch_kv_store_pagelist(bf16* const* k_pages, bf16* const* v_pages, int page_size, int n_layers, int layer, int kv_dim,
+                                     const bf16* K, const bf16* V, int pos0, int n_tok, cudaStream_t st);
 
 // split-KV flash-decoding (fast numerics): one query token per row, row b = sequence slot[b]
 struct FastAttnArgs {

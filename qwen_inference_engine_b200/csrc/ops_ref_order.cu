@@ -260,6 +260,29 @@ cudaError_t launch_kv_store(const KvGeom& kv, int layer, const bf16* K, const bf
   return cudaGetLastError();
 }
 
+// K/V rows -> a page list in the reference's layout (kv_copy_layer_to_cache_{prefill,decode}, include_cuda.cu:165-279:
+// one cudaMemcpy2D pair per page per layer there; one launch here)
+__global__ void kv_store_pagelist_kernel(bf16* const* __restrict__ k_pages, bf16* const* __restrict__ v_pages, int page_size,
+                                         int n_layers, int layer, int kv_dim, const bf16* __restrict__ K,
+                                         const bf16* __restrict__ V, int pos0, int n_tok) {
+  pdl_wait();
+  pdl_trigger();
+  const int tok = blockIdx.x, pos = pos0 + tok;
+  const size_t off = ((size_t)(pos % page_size) * n_layers + layer) * kv_dim;
+  bf16* kd = k_pages[pos / page_size] + off;
+  bf16* vd = v_pages[pos / page_size] + off;
+  for (int i = threadIdx.x; i < kv_dim; i += blockDim.x) {
+    kd[i] = K[(size_t)tok * kv_dim + i];
+    vd[i] = V[(size_t)tok * kv_dim + i];
+  }
+}
+cudaError_t launch_kv_store_pagelist(bf16* const* k_pages, bf16* const* v_pages, int page_size, int n_layers, int layer, int kv_dim,
+                                     const bf16* K, const bf16* V, int pos0, int n_tok, cudaStream_t st) {
+  if (n_tok == 0) return cudaSuccess;
+  (void)launch_k(kv_store_pagelist_kernel, dim3(n_tok), dim3(128), 0, st, k_pages, v_pages, page_size, n_layers, layer, kv_dim, K, V, pos0, n_tok);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ elementwise
 __global__ void silu_kernel(bf16* x, size_t n) {
   pdl_wait();
@@ -306,7 +329,7 @@ cudaError_t launch_residual_add(bf16* a, const bf16* b, size_t n, cudaStream_t s
 // out[d] = fma(p[k], v[k][d], out[d]) for k ascending (self_attension.cu:112-137).
 // Positions > pos[t] contribute exact zeros in the reference (mask -1e9 -> expf = 0 ->
 // fma(0, v, o) = o), so stopping at pos[t] is bit-identical.
-template <int NP>
+template <int NP, bool PL>  // PL: page-list addressing (the reference's cache layout)
 __global__ void __launch_bounds__(256) attention_ref_kernel(AttnArgs a) {
   pdl_wait();
   pdl_trigger();
@@ -324,8 +347,18 @@ __global__ void __launch_bounds__(256) attention_ref_kernel(AttnArgs a) {
   const int kvh = h / group;
   const int psz = a.kv.page_size;
   const int n_pages = (kv_len + psz - 1) / psz;
-  const int* bt = a.block_table + (size_t)a.slot[tok] * a.max_pages;
-  for (int i = threadIdx.x; i < n_pages; i += blockDim.x) pages[i] = bt[i];
+  if (!PL) {
+    const int* bt = a.block_table + (size_t)a.slot[tok] * a.max_pages;
+    for (int i = threadIdx.x; i < n_pages; i += blockDim.x) pages[i] = bt[i];
+  }
+  // row of cache position k: pool chunk [slot][hd], or the reference's page [slot][layer][kv_dim]
+  const size_t pl_row = (size_t)a.pl_layers * a.kv.n_kv * hd, pl_off = (size_t)a.layer * a.kv.n_kv * hd + (size_t)kvh * hd;
+  auto k_row = [&](int k) -> const bf16* {
+    return PL ? a.k_pages[k / psz] + (size_t)(k % psz) * pl_row + pl_off : a.kv.chunk(pages[k / psz], a.layer, 0, kvh) + (size_t)(k % psz) * hd;
+  };
+  auto v_row = [&](int k) -> const bf16* {
+    return PL ? a.v_pages[k / psz] + (size_t)(k % psz) * pl_row + pl_off : a.kv.chunk(pages[k / psz], a.layer, 1, kvh) + (size_t)(k % psz) * hd;
+  };
 
   float q[NP][2];
   head_load<NP>(q, a.q + (size_t)tok * a.n_q * hd + (size_t)h * hd, lane);
@@ -333,7 +366,7 @@ __global__ void __launch_bounds__(256) attention_ref_kernel(AttnArgs a) {
 
   const float inv_den = __fsqrt_rn((float)hd);
   for (int k = warp; k < kv_len; k += 8) {
-    const bf16* kp = a.kv.chunk(pages[k / psz], a.layer, 0, kvh) + (size_t)(k % psz) * hd;
+    const bf16* kp = k_row(k);
     float pr[NP][2];
     head_load<NP>(pr, kp, lane);
 #pragma unroll
@@ -385,17 +418,16 @@ __global__ void __launch_bounds__(256) attention_ref_kernel(AttnArgs a) {
     float o = 0.f;
     int k = 0;
     for (; k + 4 <= kv_len; k += 4) {
-      float v0 = bf2f(a.kv.chunk(pages[k / psz], a.layer, 1, kvh)[(size_t)(k % psz) * hd + d]);
-      float v1 = bf2f(a.kv.chunk(pages[(k + 1) / psz], a.layer, 1, kvh)[(size_t)((k + 1) % psz) * hd + d]);
-      float v2 = bf2f(a.kv.chunk(pages[(k + 2) / psz], a.layer, 1, kvh)[(size_t)((k + 2) % psz) * hd + d]);
-      float v3 = bf2f(a.kv.chunk(pages[(k + 3) / psz], a.layer, 1, kvh)[(size_t)((k + 3) % psz) * hd + d]);
+      float v0 = bf2f(v_row(k)[d]);
+      float v1 = bf2f(v_row(k + 1)[d]);
+      float v2 = bf2f(v_row(k + 2)[d]);
+      float v3 = bf2f(v_row(k + 3)[d]);
       o = __fmaf_rn(score[k], v0, o);
       o = __fmaf_rn(score[k + 1], v1, o);
       o = __fmaf_rn(score[k + 2], v2, o);
       o = __fmaf_rn(score[k + 3], v3, o);
     }
-    for (; k < kv_len; ++k)
-      o = __fmaf_rn(score[k], bf2f(a.kv.chunk(pages[k / psz], a.layer, 1, kvh)[(size_t)(k % psz) * hd + d]), o);
+    for (; k < kv_len; ++k) o = __fmaf_rn(score[k], bf2f(v_row(k)[d]), o);
     a.out[(size_t)tok * a.n_q * hd + (size_t)h * hd + d] = f2bf(o);
   }
 }
@@ -406,16 +438,18 @@ cudaError_t launch_attention_ref(const AttnArgs& a, cudaStream_t st) {
   size_t smem = (size_t)a.max_kv_len * sizeof(float) + (size_t)max_pages_used * sizeof(int);
   dim3 grid(a.n_q, a.n_tok);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
-#define QIE_ATTN(NPV)                                                                                         \
-  {                                                                                                           \
-    static bool set = false;                                                                                  \
-    if (!set) {                                                                                               \
-      cudaError_t e = cudaFuncSetAttribute(attention_ref_kernel<NPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                           200 * 1024);                                                       \
-      if (e != cudaSuccess) return e;                                                                         \
-      set = true;                                                                                             \
-    }                                                                                                         \
-    (void)launch_k(attention_ref_kernel<NPV>, dim3(grid), dim3(256), smem, st, a);                                                    \
+#define QIE_ATTN(NPV)                                                                                              \
+  {                                                                                                                \
+    /* per-device opt-in to > 48 KiB of dynamic shared memory: set on every launch (cheap), not once per process */ \
+    if (a.k_pages) {                                                                                               \
+      cudaError_t e = cudaFuncSetAttribute(attention_ref_kernel<NPV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+      if (e != cudaSuccess) return e;                                                                              \
+      (void)launch_k(attention_ref_kernel<NPV, true>, dim3(grid), dim3(256), smem, st, a);                          \
+    } else {                                                                                                       \
+      cudaError_t e = cudaFuncSetAttribute(attention_ref_kernel<NPV, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+      if (e != cudaSuccess) return e;                                                                              \
+      (void)launch_k(attention_ref_kernel<NPV, false>, dim3(grid), dim3(256), smem, st, a);                         \
+    }                                                                                                              \
   }
   switch (a.kv.hd) {
     case 64: QIE_ATTN(1); break;
