@@ -118,20 +118,18 @@ def dist_env():
     return rank, world, local
 
 
-def cpu_baseline_port(cfg_name, sample_tokens=3, prompt_len=8):
+def cpu_baseline_port(cfg_name, sample_tokens=3, prompt_len=8, cores=None):
     """plain-C oracle (scalar port, row-parallel over all host cores) on a bounded sample:
     one sequence, short prompt, `sample_tokens` decode tokens of the same architecture."""
     import numpy as np
 
-    import qwen_inference_engine_b200 as q
-    from oracle.oracle import Oracle, OracleModel
-    cores = os.cpu_count() or 1
+    from oracle.oracle import Oracle, OracleModel, OrcConfig
+    cores = cores or os.cpu_count() or 1
     o = Oracle()
     o.set_threads(cores)
-    cfg = q.make_config(cfg_name)
     d = tempfile.mkdtemp(prefix="qie_bench_")
     meta, wts = os.path.join(d, "meta_data.txt"), os.path.join(d, "weights.bin")
-    q.write_synthetic_checkpoint(cfg, 1234, meta, wts)
+    o.synth_write(OrcConfig(**ARCH_DIMS), 1234, meta, wts)
     om = OracleModel(o, meta, wts)
     s = om.new_seq()
     tok = om.prefill(s, np.arange(1, prompt_len + 1, dtype=np.int32))
@@ -149,7 +147,53 @@ def cpu_baseline_port(cfg_name, sample_tokens=3, prompt_len=8):
     return {"value": sample_tokens / dt, "unit": "tokens/s", "cores": cores, "kind": "port",
             "sample": f"oracle/qie_oracle.c: {sample_tokens} greedy decode tokens of ONE {cfg_name} sequence after a "
                       f"{prompt_len}-token prompt (context {prompt_len + 1}..{prompt_len + sample_tokens}), matmul rows over "
-                      f"{cores} pthreads; per-sequence rate (a batch of 64 is 64 such sequences one after another)"}
+                      f"{cores} pthread(s); per-sequence rate (a batch of 64 is 64 such sequences one after another)"}
+
+
+def _ref_model_on_device(arch_dims):
+    """random-init checkpoint written by the ORACLE's generator (oracle/qie_oracle.c, the same counter hash as the
+    product's), parsed by the oracle's loader and uploaded with torch: the reference arm never loads libqie_b200.so"""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+    from oracle.oracle import Oracle, OracleModel, OrcConfig, RefLayerW, RefModelDesc
+    o = Oracle()
+    d = tempfile.mkdtemp(prefix="qie_ref_")
+    meta, wts = os.path.join(d, "meta_data.txt"), os.path.join(d, "weights.bin")
+    cfg = OrcConfig(**arch_dims)
+    o.synth_write(cfg, 1234, meta, wts)
+    om = OracleModel(o, meta, wts)
+    keep = []
+
+    def up(name, layer=-1):
+        a = om.tensor(name, layer)
+        t = torch.from_numpy(np.ascontiguousarray(a).view(np.int16)).cuda()
+        keep.append(t)
+        return t.data_ptr()
+
+    layers = (RefLayerW * cfg.layers)()
+    names = dict(in_ln="input_layernorm.weight", q="self_attn.q_proj.weight", k="self_attn.k_proj.weight",
+                 v="self_attn.v_proj.weight", o="self_attn.o_proj.weight", q_norm="self_attn.q_norm.weight",
+                 k_norm="self_attn.k_norm.weight", post_ln="post_attention_layernorm.weight",
+                 up="mlp.up_proj.weight", gate="mlp.gate_proj.weight", down="mlp.down_proj.weight")
+    for l in range(cfg.layers):
+        for f, sn in names.items():
+            setattr(layers[l], f, up(sn, l))
+    desc = RefModelDesc(cfg.hidden, cfg.inter, cfg.layers, cfg.n_q, cfg.n_kv, cfg.head_dim, cfg.vocab, cfg.context,
+                        up("embed_tokens.weight"), up("norm.weight"), up("logits"), layers)
+    desc._keep = (layers, keep)
+    om.close()
+    for f in (wts, meta):
+        try:
+            os.remove(f)
+        except OSError:
+            pass
+    return desc
+
+
+ARCH_DIMS = dict(hidden=896, inter=4864, layers=24, n_q=14, n_kv=2, head_dim=64, vocab=151936, context=32786)
+PROMPT32 = [151643, 785, 50802, 1525, 3818] + list(range(100, 127))  # configs[0]: 32-token prompt
 
 
 def run_reference(args):
@@ -157,16 +201,14 @@ def run_reference(args):
     rank, world, local = dist_env()
     if rank != 0:
         return 0
+    import numpy as np
     import torch
-
-    import qwen_inference_engine_b200 as q
     from oracle.oracle import Ref, RefSeq
     torch.cuda.set_device(0)
     ref = Ref()
-    eng = q.Engine(synthetic=ARCH, seed=1234, kv_bytes=64 << 20, max_seqs=2, max_batch_tokens=16)  # weight blob only
-    desc = ref.model_desc(eng)
+    desc = _ref_model_on_device(ARCH_DIMS)
     rs = RefSeq(ref, desc, page_size=4)  # the reference's main() uses page_size 4 (iengine.cu:334)
-    rs.fake_context(CTX)
+    rs.fake_context(CTX)                 # pages for CTX + 64 positions: the timed tokens never take the allocate-on-demand path
     tok = 785
     for _ in range(args.warmup):
         tok = rs.decode(tok)
@@ -177,21 +219,189 @@ def run_reference(args):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     rs.close()
-    eng.close()
     val = args.steps / dt
+    # configs[0] on the reference's CUDA path: 32-token prompt through its prefill branch, then greedy decode
+    # (qwen_main.cu:74-247 / :250-404 with k = 1), llm()'s per-op device syncs kept
+    extra = {}
+    try:
+        r1 = RefSeq(ref, desc, page_size=4)
+        ids = np.asarray(PROMPT32, np.int32)
+        torch.cuda.synchronize()
+        tp0 = time.perf_counter()
+        t1 = r1.prefill(ids)
+        torch.cuda.synchronize()
+        tp1 = time.perf_counter()
+        n_dec = 64
+        for _ in range(n_dec):
+            t1 = r1.decode(t1)
+        torch.cuda.synchronize()
+        tp2 = time.perf_counter()
+        r1.close()
+        extra["config1_reference_cuda"] = {
+            "workload": "configs[0]: 0.5B-arch, batch 1, 32-token prompt, greedy decode (64 of the 128 tokens timed), the "
+                        "reference's kernels in llm()'s launch order with its per-op cudaDeviceSynchronize",
+            "prefill_ms": 1e3 * (tp1 - tp0), "decode_tokens_per_s": n_dec / (tp2 - tp1), "us_per_token": 1e6 * (tp2 - tp1) / n_dec}
+    except Exception as ex:
+        extra["config1_reference_cuda_error"] = str(ex)
     sample = (f"reference CUDA kernels (sm_100a build of /root/reference/layers/src, launch order + syncs of llm() "
               f"decode) on ONE sequence at context {CTX}.. (KV pages pre-allocated, zero-filled), {args.steps} tokens; "
               "the reference has no batching: a batch of 64 is 64 such calls, so tokens/s is the per-call rate")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic (seeded random-init weights; zero KV cache of the stated length)",
+            "data": "synthetic (seeded random-init weights from the oracle's generator; zero KV cache of the stated length)",
             "config": {"workload": f"{ARCH} decode, batch {BATCH} (processed one sequence at a time), ctx {CTX}",
-                       "note": "rank 0 only; the reference is single-GPU, single-sequence"},
+                       "note": "rank 0 only; the reference is single-GPU, single-sequence; libqie_b200.so is not loaded by this arm"},
             "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": 1, "kind": "reference", "sample": sample},
-            "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "extra": extra}
     print(json.dumps(line), flush=True)
     return 0
+
+
+def config4_leg(q, torch, np, rank, world, local, use_dist):
+    """BASELINE configs[3]: the configs[0] workload x 256 sequences (distinct seeded 32-token prompts, greedy decode),
+    256 / N sequences per GPU, full weight replica per GPU, no collective.  Total work is fixed -> strong scaling.
+    More than 64 rows run as consecutive persistent launches of <= 64 rows."""
+    n_seq = 256 // world
+    cfg = q.make_config(ARCH)
+    steps = 48
+    eng = q.Engine(synthetic=ARCH, seed=1234, device=local, max_seqs=n_seq + 1, max_batch_tokens=max(64, n_seq), page_size=16,
+                   kv_bytes=n_seq * 256 * q.kv_bytes_per_pos(cfg) + (64 << 20))
+    rng = np.random.default_rng(77 + rank)
+    seqs, first = [], []
+    for i in range(n_seq):
+        s_ = eng.new_sequence()
+        seqs.append(s_)
+        first.append(eng.prefill(s_, rng.integers(0, cfg.vocab, size=32, dtype=np.int32)))
+    eng.decode_run(seqs, np.asarray(first, np.int32), 8)  # warm-up: eager shape + graph capture
+    eng.sync()
+    if use_dist:
+        import torch.distributed as dist
+        dist.barrier()
+    ext = torch.cuda.ExternalStream(eng.stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(ext):
+        e0.record()
+    for _ in range(steps):
+        eng.decode_step_device(seqs)
+    with torch.cuda.stream(ext):
+        e1.record()
+    eng.sync()
+    ms = e0.elapsed_time(e1)
+    mega = bool(eng.uses_mega(n_seq, 32 + 8 + steps + 2))
+    eng.close()
+    if use_dist:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    return {"workload": f"256 sequences, 32-token prompts, greedy decode at context 41..{40 + steps}, {n_seq} per GPU on {world} GPU(s)",
+            "scaling": "strong", "sequences_per_gpu": n_seq, "persistent_kernel": mega, "steps": steps, "ms_per_step": ms / steps,
+            "tokens_per_s": 256 * steps / (ms / 1e3)}
+
+
+def tp_leg(q, torch, np, rank, world, local):
+    """BASELINE configs[4] inside the driver-visible run: Qwen2.5-7B-arch sharded over the N ranks of this torchrun
+    (heads / intermediate / vocabulary; o_proj and down_proj partial sums exchanged inside the persistent kernel over
+    NVLink peer memory, NCCL all-reduce on the per-operator path), batch 1 and 16; on rank 0 the same model on one GPU
+    for the speed-up; a parity run of a 3-layer model against tp_size 1; exchange latency from in-kernel timestamps."""
+    import torch.distributed as dist
+    out = {"tp_size": world}
+
+    def connect(eng):
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(q.Engine.tp_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(idt, 0)
+        eng.tp_connect(bytes(idt.cpu().numpy().tobytes()))
+
+    def timed_decode(eng, batch, steps, prompts):
+        seqs, first = [], []
+        for b in range(batch):
+            s_ = eng.new_sequence()
+            seqs.append(s_)
+            first.append(eng.prefill(s_, prompts[b]))
+        cur = np.asarray(first, np.int32)
+        for _ in range(6):
+            cur = eng.decode_step(seqs, cur)
+        st = torch.cuda.ExternalStream(eng.stream, device=local)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(st)
+        toks = eng.decode_run(seqs, cur, steps)
+        e1.record(st)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), np.asarray(toks), seqs
+
+    cfg7 = q.make_config("qwen2.5-7b", context=4096)
+    try:
+        q.tp_plan(cfg7, rank, world)
+    except Exception as ex:
+        return {"tp_size": world, "unsupported": str(ex)}
+    rng = np.random.default_rng(7)
+    # ---- parity: 3 layers of the 7B shape, one forward, tp_size N vs tp_size 1 (rank 0)
+    cfg3 = q.make_config("qwen2.5-7b", context=4096, layers=3)
+    p3 = rng.integers(0, cfg3.vocab, size=24, dtype=np.int32)
+    e3 = q.Engine(synthetic=cfg3, seed=1234, device=local, max_seqs=4, max_batch_tokens=64, kv_bytes=256 << 20, context=4096,
+                  use_graph=False, tp_rank=rank, tp_size=world)
+    connect(e3)
+    s3 = e3.new_sequence()
+    t3 = e3.prefill(s3, p3)
+    d3 = [int(t3)]
+    for _ in range(8):
+        d3.append(int(e3.decode_step([s3], [d3[-1]])[0]))
+    plan = q.tp_plan(cfg3, rank, world)
+    lg_tp = e3.read_activation("logits", plan["vocab"]).copy()
+    e3.close()
+    if rank == 0:
+        r3 = q.Engine(synthetic=cfg3, seed=1234, device=local, max_seqs=4, max_batch_tokens=64, kv_bytes=256 << 20, context=4096, use_graph=False)
+        sr = r3.new_sequence()
+        w3 = [int(r3.prefill(sr, p3))]
+        for _ in range(8):
+            w3.append(int(r3.decode_step([sr], [w3[-1]])[0]))
+        full = r3.read_activation("logits", cfg3.vocab)[plan["vocab0"]:plan["vocab0"] + plan["vocab"]]
+        a_ = (lg_tp.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+        b_ = (full.astype(np.uint32) << 16).view(np.float32).astype(np.float64)
+        out["parity_3layer"] = {"tokens_equal_tp1": d3 == w3, "logits_rel_l2_vs_tp1": float(np.linalg.norm(a_ - b_) / (np.linalg.norm(b_) + 1e-30)),
+                                "logits_bit_identical": bool(np.array_equal(lg_tp, full))}
+        r3.close()
+    dist.barrier()
+    # ---- speed: full 28-layer 7B shape
+    for batch in (1, 16):
+        prompts = rng.integers(0, cfg7.vocab, size=(batch, 32), dtype=np.int32)
+        eng = q.Engine(synthetic=cfg7, seed=1234, device=local, max_seqs=batch + 1, max_batch_tokens=64, kv_bytes=1 << 30,
+                       context=4096, tp_rank=rank, tp_size=world)
+        connect(eng)
+        steps = 48
+        ms, toks, seqs = timed_decode(eng, batch, steps, prompts)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        rec = {"ms_per_step": ms / steps, "tokens_per_s": batch * steps / (ms / 1e3),
+               "persistent_kernel": bool(eng.uses_mega(batch, 32 + 6 + steps + 2)),
+               "exchanges_per_token": 2 * cfg7.layers + 1,
+               "nvlink_bytes_sent_per_token_per_gpu": int((2 * cfg7.layers) * (world - 1) * batch * cfg7.hidden * 4)}
+        if rec["persistent_kernel"]:
+            try:  # exchange latency: the two cross-GPU barriers of a layer, from CTA 0's in-kernel timestamps
+                eng.set_int("mega_prof", 1)
+                eng.decode_step(seqs, toks[-1])
+                ts, _ = eng.mega_prof()
+                eng.set_int("mega_prof", 0)
+                d_ = np.diff(ts.astype(np.int64))[:16 * cfg7.layers].reshape(cfg7.layers, 16)
+                rec["exchange_wait_us"] = {"o_proj": float(d_[1:, 8].mean()) / 1e3, "down_proj": float(d_[1:, 15].mean()) / 1e3}
+            except Exception as ex:
+                rec["exchange_wait_error"] = str(ex)
+        eng.close()
+        dist.barrier()
+        if rank == 0:
+            e1_ = q.Engine(synthetic=cfg7, seed=1234, device=local, max_seqs=batch + 1, max_batch_tokens=64, kv_bytes=1 << 30, context=4096)
+            ms1, _, _ = timed_decode(e1_, batch, steps, prompts)
+            rec["one_gpu_tokens_per_s"] = batch * steps / (ms1 / 1e3)
+            rec["speedup_vs_one_gpu"] = rec["tokens_per_s"] / rec["one_gpu_tokens_per_s"]
+            e1_.close()
+        dist.barrier()
+        out[f"qwen2.5-7b_batch{batch}"] = rec
+    return out
 
 
 def main():
@@ -262,6 +472,7 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
+    ctx_leg0 = eng.seq_len(seqs[0])  # cached positions when the first timed step starts
     t_region0 = time.time()
     with torch.cuda.stream(ext):
         e0.record()
@@ -272,6 +483,7 @@ def main():
         e1.record()
     eng.sync()
     ms_kernel = e0.elapsed_time(e1)
+    ctx_leg_mean = 0.5 * (ctx_leg0 + eng.seq_len(seqs[0]) - 1)  # mean cached positions per sequence over the timed steps
     clocks = sampler.stop(t_region0, time.time())
     barrier()
 
@@ -338,7 +550,7 @@ def main():
         "gemm_down": 2 * H * I + B * 2 * (I + 2 * H),
         "lm_head": 2 * cfg.vocab * H + B * 2 * (H + cfg.vocab),
     }
-    step_bytes = q.weight_bytes(cfg) + B * ctx_now * kvpp + B * kvpp + B * 2 * H
+    step_bytes = int(q.weight_bytes(cfg) + B * ctx_leg_mean * kvpp + B * kvpp + B * 2 * H)  # SURVEY 8d, context of the TIMED leg
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if mega:
@@ -355,6 +567,7 @@ def main():
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "alg_bytes_per_launch": step_bytes, "avg_launch_us": dom_avg_s * 1e6, "share_of_step": 1.0,
+                    "context_of_timed_leg": [int(ctx_leg0), int(ctx_leg0 + args.steps - 1)],
                     "phases_us_per_step": mega_phase_us,
                     "attention_phase": {"alg_bytes": alg_bytes["attention"] * cfg.layers,
                                         "achieved_GBs": alg_bytes["attention"] * cfg.layers / (att_us * 1e-6) / 1e9 if att_us else None},
@@ -509,12 +722,29 @@ def main():
         except Exception as ex:
             line.setdefault("extra", {})["prefill_error"] = str(ex)
 
+    # ---------------- configs[3]: 256 sequences, 32-token prompts, sharded 256 / N per GPU (STRONG scaling) ----------
+    if not args.no_extra:
+        try:
+            line.setdefault("extra", {})["config4_256seq"] = config4_leg(q, torch, np, rank, world, local, use_dist)
+        except Exception as ex:
+            line.setdefault("extra", {})["config4_error"] = str(ex)
+    # ---------------- configs[4]: Qwen2.5-7B-arch tensor parallel over the N GPUs of this run ---------------------
+    if use_dist and not args.no_extra:
+        try:
+            line.setdefault("extra", {})["tp"] = tp_leg(q, torch, np, rank, world, local)
+        except Exception as ex:
+            line.setdefault("extra", {})["tp_error"] = str(ex)
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline_port(ARCH)
         except Exception as ex:
             line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": f"failed: {ex}"}
+        try:  # the north star's "scalar C++ CPU forward": the same port on ONE thread
+            line.setdefault("extra", {})["cpu_scalar_1thread"] = cpu_baseline_port(ARCH, sample_tokens=2, prompt_len=4, cores=1)
+        except Exception as ex:
+            line.setdefault("extra", {})["cpu_scalar_1thread_error"] = str(ex)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if use_dist:

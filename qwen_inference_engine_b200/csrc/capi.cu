@@ -986,7 +986,10 @@ int qie_prefill(qie_engine* e, int seq, const int32_t* h_ids, int n, int32_t* h_
 
 // one decode step for the batch already staged on the device (ids/pos/slot/rowstep)
 static cudaError_t decode_forward(qie_engine* e, int n, int bucket) {
-  if (decode_uses_mega(e, n, bucket)) return forward_decode_mega(e, n, bucket, e->temp_decode);
+  if (decode_uses_mega(e, n, bucket)) {
+    cudaError_t r = forward_decode_mega(e, n, bucket, e->temp_decode);
+    if (r != cudaErrorNotReady) return r;  // NotReady: the cooperative launch could not be placed, nothing ran yet
+  }
   return forward_rows(e, n, bucket, 0, n, e->temp_decode, true);
 }
 

@@ -481,11 +481,38 @@ bool decode_uses_mega(const qie_engine* e, int n, int max_kv_len) {
                                 e->mega_kc[mega_tile_set(e, n, max_kv_len)], 0, e->kv.page_size);
   }
   const int fast = e->opts.numerics == QIE_NUMERICS_FAST;  // fast numerics: persistent kernel for <= 8 rows
-  return decode_mega_supports(c.hidden, c.inter, c.layers, c.n_q, c.n_kv, c.head_dim, n, max_kv_len, e->num_sms,
-                              e->mega_kc[mega_tile_set(e, n, max_kv_len)], fast, e->kv.page_size);
+  // more rows than one launch takes (BASELINE configs[3]: 256 sequences on one GPU) run as consecutive launches of
+  // <= MEGA_ROWS_PER_LAUNCH rows: both block sizes must fit
+  const int nb = std::min(n, MEGA_ROWS_PER_LAUNCH), tail = n % MEGA_ROWS_PER_LAUNCH;
+  if (n > MEGA_ROWS_PER_LAUNCH && (fast || e->mega_layers_run > 0)) return false;
+  if (tail && n > MEGA_ROWS_PER_LAUNCH &&
+      !decode_mega_supports(c.hidden, c.inter, c.layers, c.n_q, c.n_kv, c.head_dim, tail, max_kv_len, e->num_sms,
+                            e->mega_kc[mega_tile_set(e, tail, max_kv_len)], fast, e->kv.page_size))
+    return false;
+  return decode_mega_supports(c.hidden, c.inter, c.layers, c.n_q, c.n_kv, c.head_dim, nb, max_kv_len, e->num_sms,
+                              e->mega_kc[mega_tile_set(e, nb, max_kv_len)], fast, e->kv.page_size);
 }
 
-cudaError_t forward_decode_mega(qie_engine* e, int n, int max_kv_len, float temperature) {
+static cudaError_t forward_decode_mega_rows(qie_engine* e, int row0, int n, int max_kv_len, float temperature);
+
+cudaError_t forward_decode_mega(qie_engine* e, int n_total, int max_kv_len, float temperature) {
+  // row blocks: every block is one cooperative launch over its own slice of the row metadata / logits / samples;
+  // the activation buffers are reused (the launches are stream-ordered)
+  for (int row0 = 0; row0 < n_total; row0 += MEGA_ROWS_PER_LAUNCH) {
+    cudaError_t r = forward_decode_mega_rows(e, row0, std::min(MEGA_ROWS_PER_LAUNCH, n_total - row0), max_kv_len, temperature);
+    if (r != cudaSuccess) return r;
+  }
+  const qie_config& c = e->cfg;
+  if (e->tp.size <= 1 && e->topk != 1 && e->mega_layers_run <= 0) {
+    // top-k > 1: the sampler is the reference's k-round scan + XORWOW draw (logit_decode.cu:149-274)
+    QIE_TRY(KK_SAMPLE, launch_sample_topk(e->logits, e->sampled_d, n_total, c.vocab, temperature, e->topk, e->seed, 0,
+                                          e->add_step ? e->rowstep_d : nullptr, e->stream));
+    QIE_TRY(KK_ADVANCE, launch_advance(e->pos_d, e->ids_d, e->sampled_d, n_total, e->rowstep_d, e->stream));
+  }
+  return cudaSuccess;
+}
+
+static cudaError_t forward_decode_mega_rows(qie_engine* e, int row0, int n, int max_kv_len, float temperature) {
   const qie_config& c = e->cfg;
   MegaArgs a{};
   a.H = c.hidden;
@@ -505,22 +532,22 @@ cudaError_t forward_decode_mega(qie_engine* e, int n, int max_kv_len, float temp
   a.cos_t = e->cos_d;
   a.sin_t = e->sin_d;
   a.B = n;
-  a.ids = e->ids_d;
-  a.pos = e->pos_d;
-  a.slot = e->slot_d;
+  a.ids = e->ids_d + row0;
+  a.pos = e->pos_d + row0;
+  a.slot = e->slot_d + row0;
   a.block_table = e->block_table_d;
   a.max_pages = e->max_pages_per_seq;
   a.max_kv_len = max_kv_len;
-  a.rowstep = e->rowstep_d;
+  a.rowstep = e->rowstep_d + row0;
   a.kv = e->kv;
   a.x = e->x;
   a.xn = e->xn;
   a.qkv = e->qkv;
   a.att = e->att;
   a.h = e->h;
-  a.logits = e->logits;
+  a.logits = e->logits + (size_t)row0 * c.vocab;
   a.cand = e->mega_cand_d;
-  a.sampled = e->sampled_d;
+  a.sampled = e->sampled_d + row0;
   a.bar = e->mega_bar_d;
   a.prof = e->mega_prof_on ? e->mega_prof_d : nullptr;
   a.prof_stride = 16 * c.layers + 8;
@@ -574,16 +601,12 @@ cudaError_t forward_decode_mega(qie_engine* e, int n, int max_kv_len, float temp
     cudaStreamIsCapturing(e->stream, &cs);
     if (cs != cudaStreamCaptureStatusNone) return r;
     (void)cudaGetLastError();
+    if (row0 > 0) return r;  // earlier row blocks of this step have already advanced: no consistent fallback
     e->use_mega = false;
-    return forward_rows(e, n, max_kv_len, 0, n, temperature, true);
+    return cudaErrorNotReady;  // the caller (decode_forward) re-runs the whole step through forward_rows
   }
   ++e->launches;
-  if (!a.greedy && e->mega_layers_run <= 0) {
-    // top-k > 1: the sampler is the reference's k-round scan + XORWOW draw (logit_decode.cu:149-274)
-    QIE_TRY(KK_SAMPLE, launch_sample_topk(e->logits, e->sampled_d, n, c.vocab, temperature, e->topk, e->seed, 0,
-                                          e->add_step ? e->rowstep_d : nullptr, e->stream));
-    QIE_TRY(KK_ADVANCE, launch_advance(e->pos_d, e->ids_d, e->sampled_d, n, e->rowstep_d, e->stream));
-  }
+  (void)temperature;
   return cudaSuccess;
 }
 

@@ -27,7 +27,8 @@ def _kv_snapshot(eng):
 
 
 def _run(qie, arch, n_seq, n_prompt, n_steps, use_mega):
-    eng = qie.Engine(synthetic=arch, seed=1234, context=512, max_batch_tokens=64, use_graph=False, kv_bytes=32 << 20)
+    eng = qie.Engine(synthetic=arch, seed=1234, context=512, max_batch_tokens=max(64, n_seq), max_seqs=max(64, n_seq + 1),
+                     use_graph=False, kv_bytes=(32 << 20) * max(1, n_seq // 32))
     assert eng.uses_mega(n_seq, n_prompt + n_seq + n_steps)
     eng.set_int("mega", int(use_mega))
     seqs, toks = [], []
@@ -49,6 +50,7 @@ def _run(qie, arch, n_seq, n_prompt, n_steps, use_mega):
 @pytest.mark.parametrize("arch,n_seq,n_prompt,n_steps", [
     ("tiny", 1, 3, 20), ("small", 1, 9, 40), ("small", 3, 5, 24), ("small128", 2, 7, 20), ("small", 8, 4, 12),
     ("small", 16, 4, 10), ("small", 40, 3, 8), ("small128", 33, 3, 6), ("tiny", 64, 2, 6),
+    ("small", 150, 2, 5),  # more rows than one launch takes: 64 + 64 + 22 (BASELINE configs[3]: 256 sequences per GPU at N = 1)
 ])
 def test_mega_equals_per_operator_path(qie, arch, n_seq, n_prompt, n_steps):
     want_t, want_l, want_kv = _run(qie, arch, n_seq, n_prompt, n_steps, use_mega=False)
