@@ -242,6 +242,9 @@ int qie_engine_get_config(const qie_engine* e, qie_config* out);
  * helpers.cuh:18-29; *n_elems receives the element count. NULL on miss. */
 const qie_bf16* qie_engine_weight(const qie_engine* e, const char* short_name, int layer, size_t* n_elems);
 int qie_engine_kv_view(const qie_engine* e, qie_kv_view* out);
+/* what a caller that batches requests has to respect: rows one decode step takes (min of max_batch_tokens and the
+ * logits rows), KV pages one sequence can hold, sequence slots */
+int qie_engine_limits(const qie_engine* e, int* max_decode_rows, int* max_pages_per_seq, int* max_seqs);
 qie_stream qie_engine_stream(const qie_engine* e);
 
 /* sampling parameters applied by prefill/decode (defaults: top-k 1 = greedy).
@@ -294,7 +297,10 @@ int qie_sync(qie_engine* e);
  * samples `eos_token` (151645 in the reference; -1 = none) or reaches max_new_tokens leaves the batch and its pages
  * are recycled.  In reference-order numerics a request's tokens do not depend on the batch it shares (tested).
  * qie_sched_step returns the number of unfinished requests or a negative error; qie_sched_result copies the tokens
- * generated so far (including the EOS token) and returns their count. */
+ * generated so far (including the EOS token) and returns their count; *finished is 0 (queued / running), 1 (done) or
+ * the negative QIE_E* code that failed THIS request.  qie_sched_submit refuses what could never run (prompt +
+ * max_new_tokens beyond the context or the per-sequence page table, token ids outside the vocabulary); a request whose
+ * prefill or decode fails later is finished as failed and its sequence and pages are released -- the others go on. */
 typedef struct qie_scheduler qie_scheduler;
 int qie_sched_create(qie_engine* e, int max_running, int eos_token, qie_scheduler** out);
 void qie_sched_destroy(qie_scheduler* s);

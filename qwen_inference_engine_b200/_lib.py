@@ -97,6 +97,7 @@ def lib():
         "qie_engine_weight": (vp, [vp, C.c_char_p, i32, C.POINTER(sz)]),
         "qie_engine_kv_view": (i32, [vp, C.POINTER(KvView)]),
         "qie_engine_stream": (vp, [vp]),
+        "qie_engine_limits": (i32, [vp, ip, ip, ip]),
         "qie_engine_set_sampling": (i32, [vp, i32, f32, f32, u64, i32]),
         "qie_seq_new": (i32, [vp, ip]),
         "qie_seq_free": (i32, [vp, i32]),

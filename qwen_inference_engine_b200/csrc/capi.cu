@@ -869,6 +869,14 @@ int qie_engine_kv_view(const qie_engine* e, qie_kv_view* out) {
 
 qie_stream qie_engine_stream(const qie_engine* e) { return e ? (qie_stream)e->stream : nullptr; }
 
+int qie_engine_limits(const qie_engine* e, int* max_decode_rows, int* max_pages_per_seq, int* max_seqs) {
+  if (!e) return fail(QIE_EINVAL, "null engine");
+  if (max_decode_rows) *max_decode_rows = std::min(e->opts.max_batch_tokens, e->logits_rows);
+  if (max_pages_per_seq) *max_pages_per_seq = e->max_pages_per_seq;
+  if (max_seqs) *max_seqs = (int)e->seqs.size();
+  return QIE_OK;
+}
+
 int qie_engine_set_sampling(qie_engine* e, int topk, float temperature_prefill, float temperature_decode,
                             uint64_t seed, int add_step) {
   if (!e || topk < 1 || topk > 256) return fail(QIE_EINVAL, "set_sampling: topk must be in [1,256]");
@@ -1039,6 +1047,8 @@ static int decode_prepare(qie_engine* e, const int* h_seqs, int n, int* max_kv_l
     if (rc < 0) return rc;
     if (rc) CU(push_block_row(e, h_seqs[i]));
     mk = std::max(mk, s.len + 1);
+    for (int j = 0; j < i; ++j)  // two rows of one sequence would write the same KV slot
+      if (h_seqs[j] == h_seqs[i]) return fail(QIE_EINVAL, "decode: sequence %d appears twice in the batch", h_seqs[i]);
   }
   *max_kv_len = mk;
   return QIE_OK;

@@ -1840,7 +1840,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
   prefetch_norm_w(a, smem_base, 0, layers[0].in_ln);
   // embedding rows (embedded_matrix.cu:5-17): x[b] = E[ids[b]]; layer 0 reads E directly
   for (int b = blockIdx.x; b < a.B; b += gridDim.x) {
-    const uint4* src = reinterpret_cast<const uint4*>(a.embed + (size_t)a.ids[b] * H);
+    const uint4* src = reinterpret_cast<const uint4*>(a.embed + (size_t)max(a.ids[b], 0) * H);
     uint4* dst = reinterpret_cast<uint4*>(a.x + (size_t)b * H);
     for (int i = threadIdx.x; i < (H >> 3); i += NTC) dst[i] = src[i];
   }
@@ -1893,7 +1893,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
           if (tp && !from_embed)
             load_row_tp(a, act, b, H, x_cur, x_next, (int)((xch - 1) & 1));
           else
-            load_rows(act, 1, H, [&](int) { return from_embed ? a.embed + (size_t)a.ids[b] * H : a.x + (size_t)b * H; });
+            load_rows(act, 1, H, [&](int) { return from_embed ? a.embed + (size_t)max(a.ids[b], 0) * H : a.x + (size_t)b * H; });
           rmsnorm_rows(a, smem, 1, H, which);
           const uint4* src = reinterpret_cast<const uint4*>(smem + a.off_act);
           uint4* dst = reinterpret_cast<uint4*>(a.xn + (size_t)b * H);
@@ -1927,7 +1927,7 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
           x_cur = x_next;
           x_next = const_cast<bf16*>(t);
         } else {
-          load_rows(act, a.B, H, [&](int b) { return from_embed ? a.embed + (size_t)a.ids[b] * H : a.x + (size_t)b * H; });
+          load_rows(act, a.B, H, [&](int b) { return from_embed ? a.embed + (size_t)max(a.ids[b], 0) * H : a.x + (size_t)b * H; });
         }
         stamp();
         if (FAST)

@@ -26,7 +26,11 @@ bool g_use_pdl = [] {
       cudaEventRecord(_r.a, e->stream);                        \
     }                                                          \
     cudaError_t _e = (expr);                                   \
-    if (_e != cudaSuccess) return _e;                          \
+    if (_e != cudaSuccess) {                                   \
+      if (_r.a) cudaEventDestroy(_r.a);                        \
+      if (_r.b) cudaEventDestroy(_r.b);                        \
+      return _e;                                               \
+    }                                                          \
     if (e->prof_on) {                                          \
       cudaEventRecord(_r.b, e->stream);                        \
       e->prof.push_back(_r);                                   \

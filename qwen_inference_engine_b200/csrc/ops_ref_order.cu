@@ -30,7 +30,8 @@ __global__ void embedding_kernel(bf16* __restrict__ out, const bf16* __restrict_
   pdl_wait();
   pdl_trigger();
   const size_t t = blockIdx.x;
-  const bf16* src = table + (size_t)ids[t] * hidden;
+  // a sampler that found no finite logit reports -1 (never a valid id); such a row reads row 0 instead of out of bounds
+  const bf16* src = table + (size_t)max(ids[t], 0) * hidden;
   bf16* dst = out + t * hidden;
   if ((hidden & 7) == 0) {
     const uint4* s4 = reinterpret_cast<const uint4*>(src);

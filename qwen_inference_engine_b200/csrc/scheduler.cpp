@@ -21,10 +21,12 @@ struct qie_scheduler {
   qie_engine* eng = nullptr;
   int max_running = 0, eos = -1;
   int page_size = 16, total_pages = 0;
+  int context = 0, vocab = 0, max_pages_per_seq = 0;  // engine limits a request is checked against when it is submitted
   struct Req {
     std::vector<int32_t> prompt, out;
     int max_new = 0, seq = -1, reserved = 0;
     bool running = false, done = false;
+    int error = 0;  // QIE_E* code of the call that failed this request (0 = none)
   };
   std::vector<Req> reqs;
   std::deque<int> waiting;
@@ -60,6 +62,18 @@ int qie_sched_create(qie_engine* e, int max_running, int eos_token, qie_schedule
   s->eos = eos_token;
   s->page_size = v.page_size;
   s->total_pages = v.n_pages;
+  qie_config cfg;
+  int max_rows = 0, max_pages_per_seq = 0, max_seqs = 0;
+  if ((rc = qie_engine_get_config(e, &cfg)) || (rc = qie_engine_limits(e, &max_rows, &max_pages_per_seq, &max_seqs))) {
+    delete s;
+    return rc;
+  }
+  s->context = cfg.context;
+  s->vocab = cfg.vocab;
+  s->max_pages_per_seq = max_pages_per_seq;
+  // never more rows in a decode step than the engine takes (max_batch_tokens / logits rows) or sequences it can hold
+  if (s->max_running > max_rows) s->max_running = max_rows;
+  if (s->max_running > max_seqs) s->max_running = max_seqs;
   *out = s;
   return QIE_OK;
 }
@@ -73,7 +87,12 @@ void qie_sched_destroy(qie_scheduler* s) {
 
 int qie_sched_submit(qie_scheduler* s, const int32_t* ids, int n, int max_new_tokens, int* request_id) {
   if (!s || !ids || n <= 0 || max_new_tokens <= 0 || !request_id) return QIE_EINVAL;
+  // a request that could never run is refused HERE: once queued it would sit at the head of the FIFO and starve
+  // everybody behind it (prefill / decode fail the same way every step)
   if (pages_for(s, n + max_new_tokens) > s->total_pages) return QIE_ENOMEM;  // could never be admitted
+  if (n + max_new_tokens > s->context || pages_for(s, n + max_new_tokens) > s->max_pages_per_seq) return QIE_EINVAL;
+  for (int i = 0; i < n; ++i)
+    if (ids[i] < 0 || ids[i] >= s->vocab) return QIE_EINVAL;
   qie_scheduler::Req r;
   r.prompt.assign(ids, ids + n);
   r.max_new = max_new_tokens;
@@ -101,8 +120,13 @@ int qie_sched_step(qie_scheduler* s) {
     int32_t tok = 0;
     rc = qie_prefill(s->eng, seq, r.prompt.data(), (int)r.prompt.size(), &tok);
     if (rc) {
+      // this request fails (and leaves the queue); the others go on.  Only a device failure stops the scheduler.
       qie_seq_free(s->eng, seq);
-      return rc;
+      s->waiting.pop_front();
+      r.error = rc;
+      r.done = true;
+      if (rc == QIE_ECUDA) return rc;
+      continue;
     }
     ++s->prefills;
     s->waiting.pop_front();
@@ -126,13 +150,27 @@ int qie_sched_step(qie_scheduler* s) {
       seqs[i] = r.seq;
       in[i] = r.out.back();
     }
+    std::vector<int> row_rc(n, 0);
     int rc = qie_decode_step(s->eng, seqs.data(), in.data(), n, out.data());
-    if (rc) return rc;
+    if (rc == QIE_ECUDA) return rc;
+    if (rc) {
+      // the batched call refused (no state was changed: arguments are checked before anything is launched): find
+      // the offending request(s) by stepping every row on its own; they are failed, the others advance as usual
+      for (int i = 0; i < n; ++i) {
+        row_rc[i] = qie_decode_step(s->eng, &seqs[i], &in[i], 1, &out[i]);
+        if (row_rc[i] == QIE_ECUDA) return row_rc[i];
+      }
+    }
     s->decode_rows += n;
     std::vector<int> still;
     for (int i = 0; i < n; ++i) {
       const int id = s->running[i];
       qie_scheduler::Req& r = s->reqs[id];
+      if (row_rc[i]) {
+        r.error = row_rc[i];
+        finish(s, id);
+        continue;
+      }
       r.out.push_back(out[i]);
       if (out[i] == s->eos || (int)r.out.size() >= r.max_new)
         finish(s, id);
@@ -150,7 +188,7 @@ int qie_sched_result(const qie_scheduler* s, int request_id, int32_t* out, int m
   const int n = (int)r.out.size();
   if (out)
     for (int i = 0; i < n && i < max_tokens; ++i) out[i] = r.out[i];
-  if (finished) *finished = r.done ? 1 : 0;
+  if (finished) *finished = r.error ? r.error : (r.done ? 1 : 0);  // negative: the QIE_E* code that failed the request
   return n;
 }
 

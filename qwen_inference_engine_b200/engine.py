@@ -324,6 +324,7 @@ class Scheduler:
         out = np.zeros(max_tokens, np.int32)
         fin = C.c_int()
         n = check(self._L.qie_sched_result(self._h, rid, out.ctypes.data, max_tokens, C.byref(fin)))
+        self.last_status = fin.value  # 0 queued / running, 1 done, negative: the QIE_E* code that failed the request
         return [int(t) for t in out[:min(n, max_tokens)]], bool(fin.value)
 
     def stats(self):
@@ -333,7 +334,8 @@ class Scheduler:
         return dict(steps=st.value, decode_rows=rows.value, prefills=pf.value, running=run.value, waiting=wait.value)
 
     def run(self, max_steps=1 << 20):
+        """step until every request has finished; returns the number left (0)"""
         for _ in range(max_steps):
             if self.step() == 0:
-                return
+                return 0
         raise RuntimeError("scheduler did not drain")

@@ -104,3 +104,39 @@ def test_kv_swap_out_and_in_keeps_generation_bit_exact():
     eng.free_sequence(a)
     assert eng.pages_free() == total
     eng.close()
+
+
+def test_bad_requests_are_refused_and_never_wedge_the_queue():
+    """a request that can never run (prompt + budget beyond the context, token id outside the vocabulary)
+    is refused at submit; max_running is clamped to what a decode step takes; the good requests around it finish."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import qwen_inference_engine_b200 as q
+    from util import prompt_ids
+    eng = q.Engine(synthetic="small", seed=5, context=64, max_seqs=4, max_pages=32, max_batch_tokens=8)
+    V = eng.config.vocab
+    sch = q.Scheduler(eng, max_running=1000, eos_token=-1)  # clamped to min(8 rows, 4 sequence slots)
+    good1 = sch.submit(prompt_ids(5, V, seed=1), 6)
+    for bad in (lambda: sch.submit(prompt_ids(40, V, seed=2), 30),            # 70 positions > context 64
+                lambda: sch.submit(np.array([1, 2, V + 3], np.int32), 4),     # id outside the vocabulary
+                lambda: sch.submit(np.array([1, -2, 3], np.int32), 4)):
+        with pytest.raises(q.QieError) as ei:
+            bad()
+        assert ei.value.code == -1  # QIE_EINVAL
+    more = [sch.submit(prompt_ids(4 + i, V, seed=10 + i), 5) for i in range(6)]  # more requests than sequence slots
+    left = sch.run()
+    assert left == 0
+    for rid in [good1] + more:
+        toks, fin = sch.result(rid)
+        assert fin and sch.last_status == 1 and len(toks) in (5, 6)
+    st = sch.stats()
+    assert st["running"] == 0 and st["waiting"] == 0
+    # solo run of one of them gives the same tokens (nothing was disturbed by the refused submissions)
+    assert eng.generate(prompt_ids(5, V, seed=1), 6) == sch.result(good1)[0]
+    # duplicate sequence ids in one decode batch are refused
+    s0 = eng.new_sequence()
+    t0 = eng.prefill(s0, prompt_ids(3, V))
+    with pytest.raises(q.QieError):
+        eng.decode_step([s0, s0], [t0, t0])
+    sch.close()
+    eng.close()
