@@ -110,7 +110,7 @@ struct qie_engine {
   // exchange buffer of the persistent kernel: [MEGA_TP_HEADER: flags, generation, candidates][2][tp][MEGA_TP_ROWS][hidden] fp32, exported
   // to the peers through CUDA IPC (handles travel over the NCCL communicator in qie_engine_tp_connect)
   void* tp_xbuf = nullptr;
-  void* tp_peer_xbuf[qie::MEGA_MAX_TP] = {nullptr, nullptr, nullptr, nullptr};  // [rank] mapped base (own entry = tp_xbuf)
+  void* tp_peer_xbuf[qie::MEGA_MAX_TP] = {};  // [rank] mapped base (own entry = tp_xbuf)
   bool tp_mega_ready = false;
   qie::bf16* x2 = nullptr;            // residual ping-pong partner of x
   qie::TensorMap2D* mega_wmaps_tp_d[2] = {nullptr, nullptr};  // weight views of this rank's shard

@@ -185,9 +185,9 @@ cudaError_t launch_advance(int* pos, int* ids, const int* sampled, int n, int* s
 // decode_mega.cu: ONE cooperative launch runs a whole decode step (all layers, lm_head,
 // greedy arg-max, bookkeeping) for up to 64 sequences in reference-order arithmetic.
 constexpr int MEGA_ROWS_PER_LAUNCH = 64;  // rows one persistent launch takes (decode_mega.cu MAX_ROWS); more rows = more launches
-constexpr int MEGA_MAX_TP = 4;
+constexpr int MEGA_MAX_TP = 8;
 constexpr int MEGA_TP_ROWS = 64;
-constexpr int MEGA_TP_HEADER = 4096;  // bytes in front of the partial sums: flag words, generation word (byte 128), candidate table (byte 256)
+constexpr int MEGA_TP_HEADER = 8192;  // bytes in front of the partial sums: flag words, generation word (byte 128), candidate table (byte 256, [8][64] x 8 bytes)
 struct MegaLayer {
   const bf16 *in_ln, *q, *k, *v, *o, *q_norm, *k_norm, *post_ln, *gate, *up, *down;
 };

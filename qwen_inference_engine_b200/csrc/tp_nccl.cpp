@@ -13,11 +13,29 @@ namespace qie {
 
 bool tp_plan(const qie_config& c, int rank, int size, TpPlan* out) {
   if (size < 1 || rank < 0 || rank >= size) return false;
-  if (c.n_q % size || c.n_kv % size || c.inter % size) return false;
-  if ((c.n_q / size) % (c.n_kv / size)) return false;
+  if (c.inter % size || c.n_q % c.n_kv) return false;
   TpPlan p;
-  p.n_q = c.n_q / size;
-  p.n_kv = c.n_kv / size;
+  const int group = c.n_q / c.n_kv;  // query heads per kv head
+  if (c.n_kv % size == 0) {
+    // whole kv heads (and their query groups) per rank
+    p.n_kv = c.n_kv / size;
+    p.n_q = p.n_kv * group;
+    p.kv_row0 = rank * p.n_kv * c.head_dim;
+    p.q_row0 = rank * p.n_q * c.head_dim;
+  } else if (size % c.n_kv == 0) {
+    // more ranks than kv heads (Qwen2.5-7B: 28 q / 4 kv heads over 8 GPUs, SURVEY 7 "hard parts"): `rep` ranks share one
+    // kv head -- each keeps its own copy of that head's K/V cache -- and split its query group between them as evenly
+    // as it goes (7 heads over 2 ranks: 4 + 3).  No padded heads: o_proj takes the columns of the heads a rank owns.
+    const int rep = size / c.n_kv, kvh = rank / rep, sub = rank % rep;
+    if (group < rep) return false;
+    const int base = group / rep, extra = group % rep;
+    p.n_kv = 1;
+    p.n_q = base + (sub < extra ? 1 : 0);
+    p.kv_row0 = kvh * c.head_dim;
+    p.q_row0 = (kvh * group + sub * base + std::min(sub, extra)) * c.head_dim;
+  } else {
+    return false;
+  }
   p.inter = c.inter / size;
   if (p.inter & 7) return false;
   // vocabulary shards start at multiples of 256 so that the low byte of a token index (the
@@ -26,8 +44,6 @@ bool tp_plan(const qie_config& c, int rank, int size, TpPlan* out) {
   p.vocab0 = std::min(c.vocab, rank * per * 256);
   p.vocab = std::min(c.vocab, (rank + 1) * per * 256) - p.vocab0;
   if (p.vocab <= 0 || (p.vocab & 1)) return false;
-  p.q_row0 = rank * p.n_q * c.head_dim;
-  p.kv_row0 = rank * p.n_kv * c.head_dim;
   p.inter0 = rank * p.inter;
   *out = p;
   return true;

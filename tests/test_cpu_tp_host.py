@@ -41,11 +41,33 @@ def test_plan_tiles_the_model(arch, tp):
 def test_plan_refuses_indivisible_shapes():
     cfg = q.make_config("qwen2.5-7b")
     with pytest.raises(q.QieError):
-        q.tp_plan(cfg, 0, 8)  # 28 q / 4 kv heads do not split 8 ways
-    with pytest.raises(q.QieError):
         q.tp_plan(cfg, 2, 2)
     with pytest.raises(q.QieError):
-        q.tp_plan(q.make_config("qwen2.5-0.5b"), 0, 4)  # 2 kv heads
+        q.tp_plan(cfg, 0, 3)  # neither the kv heads nor the ranks divide
+    with pytest.raises(q.QieError):
+        q.tp_plan(q.make_config("qwen2.5-0.5b"), 0, 3)
+
+
+@pytest.mark.parametrize("arch,tp", [("qwen2.5-7b", 8), ("qwen2.5-0.5b", 4), ("small128", 2), ("qwen2.5-1.5b", 4)])
+def test_plan_with_more_ranks_than_kv_heads(arch, tp):
+    """BASELINE configs[4] names 2/4/8 GPUs; Qwen2.5-7B has 28 q / 4 kv heads.  With more ranks than kv heads, `rep`
+    ranks share one kv head (each caches it) and split its query group: every q head is owned exactly once, a rank's
+    q heads all belong to its kv head, o_proj columns = the owned q rows, MLP and vocabulary tile as always."""
+    cfg = q.make_config(arch)
+    plans = [q.tp_plan(cfg, r, tp) for r in range(tp)]
+    group, rep, hd = cfg.n_q // cfg.n_kv, tp // cfg.n_kv, cfg.head_dim
+    owned = []
+    for r, p in enumerate(plans):
+        assert p["n_kv"] == 1 and p["kv_row0"] == (r // rep) * hd
+        heads = list(range(p["q_row0"] // hd, p["q_row0"] // hd + p["n_q"]))
+        assert heads and all(h // group == r // rep for h in heads)  # GQA: q head h reads kv head h // group
+        owned += heads
+        assert p["vocab0"] % 256 == 0 and p["inter"] % 8 == 0
+    assert sorted(owned) == list(range(cfg.n_q))
+    sizes = [p["n_q"] for p in plans]
+    assert max(sizes) - min(sizes) <= 1  # 7 heads over 2 ranks: 4 + 3
+    assert sum(p["inter"] for p in plans) == cfg.inter and sum(p["vocab"] for p in plans) == cfg.vocab
+    assert [p["inter0"] for p in plans] == list(np.cumsum([0] + [p["inter"] for p in plans[:-1]]))
 
 
 def _free_port():
