@@ -528,6 +528,30 @@ def main():
     else:
         prof = eng.decode_step_profile(seqs, cur)
     ctx_now = eng.seq_len(seqs[0])
+    topk_extra = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        # the reference's real sampling mode on the same batch: top-k 50, T 0.7, XORWOW (qwen_main.cu:381-388) -- the
+        # persistent kernel leaves the logits, one radix-select + draw kernel follows (the reference does k = 50 scans)
+        try:
+            eng.set_sampling(topk=50, temperature_prefill=1.0, temperature_decode=0.7, seed=1234, add_step=True)
+            cur = eng.decode_step(seqs, cur)
+            for _ in range(3):
+                eng.decode_step_device(seqs)
+            eng.sync()
+            with torch.cuda.stream(ext):
+                e0.record()
+            for _ in range(10):
+                eng.decode_step_device(seqs)
+            with torch.cuda.stream(ext):
+                e1.record()
+            eng.sync()
+            ms_k = e0.elapsed_time(e1) / 10
+            topk_extra = {"workload": "same batch / context, top-k 50 + temperature 0.7 + XORWOW draw per row (the reference's sampling mode)",
+                          "ms_per_step": ms_k, "tokens_per_s": B / (ms_k / 1e3), "launches_per_step": int(eng.launch_count()),
+                          "sampler_overhead_ms_vs_greedy": ms_k - ms_kernel / args.steps}
+            eng.set_sampling(topk=1)
+        except Exception as ex:
+            topk_extra = {"error": str(ex)}
 
     if use_dist:
         t = torch.tensor([ms_kernel, ms_e2e], device="cuda", dtype=torch.float64)
@@ -609,6 +633,8 @@ def main():
                     "ms_per_step": ms_e2e / args.steps,
                     "api": "qie_decode_step (HOST int32 tokens in/out, pinned staging, one H2D + one D2H + stream sync per step)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+    if topk_extra:
+        line.setdefault("extra", {})["topk50_batch64"] = topk_extra
 
     if rank == 0 and world == 1 and not args.no_fast_extra and args.numerics != "fast":
         # side measurement: the same workload through the fast-numerics per-operator path

@@ -149,6 +149,8 @@ void launch_qknorm(__nv_bfloat16* X, __nv_bfloat16* w, int head_dim, int seqlen,
 void proj(const tensor& t, std::ifstream& f, __nv_bfloat16* w_h, __nv_bfloat16* w_d, size_t w_elems, __nv_bfloat16* x,
           __nv_bfloat16* y, int m, int n, int k, __nv_bfloat16* g_gpu_weights_buffer);
 int sample_topk_bf16(__nv_bfloat16* logits_d, int vocab, float temperature, int topk, unsigned long long seed, int step);
+// layers_include.cuh:33 declares the kernel and nothing defines it; host wrapper with the declared argument list
+void apply_repetition_penalty(__nv_bfloat16* logits, const int* context_tokens, size_t context_len, int vocab_size, float penalty);
 static inline void copy_last_vocab_vec(__nv_bfloat16* seq, __nv_bfloat16* dst, int hidden, int seqlen) {
   cudaMemcpyAsync(dst, &seq[(size_t)(seqlen - 1) * hidden], hidden * sizeof(__nv_bfloat16), cudaMemcpyDeviceToDevice, 0);
 }

@@ -129,6 +129,13 @@ int qie_sample_topk(const qie_bf16* logits, int* out_tokens, int n_rows, size_t 
 int qie_sample_topk_subseq(const qie_bf16* logits, int* out_tokens, int n_rows, size_t vocab, float temperature, int k,
                            uint64_t seed, uint64_t seed_stride, uint64_t subsequence, qie_stream st);
 
+/* apply_repetition_penalty_kernel, include/layers_include.cuh:33 -- declared by the reference with exactly these
+ * arguments, never defined or launched.  Conventional semantics (CTRL / HF): every DISTINCT id in context_tokens
+ * (DEVICE int[context_len]) has its logit divided by `penalty` when positive and multiplied when not (fp32 IEEE, one
+ * bf16 rounding); ids outside [0, vocab_size) are ignored.  One row of logits, in place. */
+int qie_repetition_penalty(qie_bf16* logits, const int* context_tokens, size_t context_len, int vocab_size, float penalty,
+                           qie_stream st);
+
 /* FAST-numerics operators (same contracts as qie_matmul / qie_attention, results within
  * the 1e-2 bf16 tolerance instead of bit-exact): tcgen05/TMEM/TMA GEMM with split-K, and
  * split-KV flash-decoding (one query token per row; n_splits = 0 picks a default).
@@ -252,6 +259,12 @@ qie_stream qie_engine_stream(const qie_engine* e);
  * (qwen_main.cu:241,381-388). per-step seed = seed + step when add_step != 0. */
 int qie_engine_set_sampling(qie_engine* e, int topk, float temperature_prefill, float temperature_decode,
                             uint64_t seed, int add_step);
+
+/* Driver-level repetition penalty: with penalty != 1 the engine keeps every sequence's tokens (prompt + generated) on
+ * the device and applies qie_repetition_penalty over them to the logits of every sampled row before the sampler
+ * (greedy or top-k); 1 switches it off.  Positions filled by qie_seq_fill_synthetic / qie_seq_kv_write carry no token
+ * and are skipped.  Not available with tensor parallelism. */
+int qie_engine_set_repetition_penalty(qie_engine* e, float penalty);
 
 /* create_new_sequence + create_page_list (iengine.cu:25-47,73-87). Returns a slot id. */
 int qie_seq_new(qie_engine* e, int* seq);

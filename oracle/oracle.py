@@ -64,6 +64,7 @@ class Oracle:
         L.orc_sample_topk.argtypes = [vp, f32, i32, sz, u64, u64]
         L.orc_argmax_ref_tiebreak.restype = i32
         L.orc_argmax_ref_tiebreak.argtypes = [vp, sz]
+        L.orc_repetition_penalty.argtypes = [vp, vp, sz, i32, f32]
         L.orc_model_load.restype = vp
         L.orc_model_load.argtypes = [C.c_char_p, C.c_char_p, i32, i32]
         L.orc_model_free.argtypes = [vp]
@@ -168,6 +169,12 @@ class Oracle:
     def argmax_tiebreak(self, logits):
         logits = _u16(logits)
         return self.L.orc_argmax_ref_tiebreak(logits.ctypes.data, logits.size)
+
+    def repetition_penalty(self, logits, context_tokens, penalty):
+        lg = _u16(logits).copy()
+        ctx = np.ascontiguousarray(context_tokens, np.int32)
+        self.L.orc_repetition_penalty(lg.ctypes.data, ctx.ctypes.data, len(ctx), lg.size, penalty)
+        return lg
 
     def synth_value(self, seed, g, kind):
         return self.L.orc_synth_value(seed, g, kind)

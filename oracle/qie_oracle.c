@@ -448,6 +448,24 @@ int orc_argmax_ref_tiebreak(const orc_bf16* logits, size_t vocab) {
   return bi;
 }
 
+/* apply_repetition_penalty_kernel: DECLARED in the reference (include/layers_include.cuh:33: logits, context_tokens,
+ * context_len, vocab_size, penalty) but never defined or launched -- there is no reference behaviour to match, so this
+ * states the conventional one (CTRL / HF RepetitionPenaltyLogitsProcessor): every DISTINCT token id of the context has
+ * its logit divided by the penalty when positive, multiplied when not; fp32 IEEE arithmetic on the bf16 logit, one
+ * bf16 rounding.  Ids outside [0, vocab) are ignored. */
+void orc_repetition_penalty(orc_bf16* logits, const int* context_tokens, size_t context_len, int vocab, float penalty) {
+  for (size_t i = 0; i < context_len; i++) {
+    int t = context_tokens[i];
+    if (t < 0 || t >= vocab) continue;
+    int seen = 0;
+    for (size_t j = 0; j < i && !seen; j++) seen = context_tokens[j] == t;
+    if (seen) continue;
+    float v = orc_bf2f(logits[t]);
+    v = v > 0.0f ? v / penalty : v * penalty;
+    logits[t] = orc_f2bf(v);
+  }
+}
+
 /* ------------------------------------------------------------------ checkpoint */
 typedef struct {
   char name[160];

@@ -98,6 +98,7 @@ int orc_sample_topk(const orc_bf16* logits, float temperature, int k, size_t voc
                     uint64_t subseq);
 /* the k=1 special case, spelled out as the closed-form tie-break rule */
 int orc_argmax_ref_tiebreak(const orc_bf16* logits, size_t vocab);
+void orc_repetition_penalty(orc_bf16* logits, const int* context_tokens, size_t context_len, int vocab, float penalty);
 
 /* ---- checkpoint (model_files/meta_data.txt + weights.bin) ---- */
 typedef struct orc_model orc_model;

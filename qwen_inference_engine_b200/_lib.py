@@ -78,6 +78,8 @@ def lib():
         "qie_kv_store_pagelist": (i32, [vp, vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp]),
         "qie_sample_topk": (i32, [vp, vp, i32, sz, f32, i32, u64, u64, vp]),
         "qie_sample_topk_subseq": (i32, [vp, vp, i32, sz, f32, i32, u64, u64, u64, vp]),
+        "qie_repetition_penalty": (i32, [vp, vp, sz, i32, f32, vp]),
+        "qie_engine_set_repetition_penalty": (i32, [vp, f32]),
         "qie_matmul_fast": (i32, [vp, vp, vp, i32, i32, i32, vp]),
         "qie_attention_prefill_tc": (i32, [C.POINTER(KvView), i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]),
         "qie_attention_prefill_fast": (i32, [C.POINTER(KvView), i32, vp, vp, vp, vp, vp, i32, i32, i32, vp]),

@@ -184,6 +184,14 @@ int qie_sample_topk_subseq(const qie_bf16* logits, int* out_tokens, int n_rows, 
   return QIE_OK;
 }
 
+int qie_repetition_penalty(qie_bf16* logits, const int* context_tokens, size_t context_len, int vocab_size, float penalty,
+                           qie_stream st) {
+  if (!logits || (!context_tokens && context_len) || vocab_size <= 0 || !(penalty > 0.0f)) return fail(QIE_EINVAL, "repetition_penalty: bad argument");
+  CU(launch_repetition_penalty((bf16*)logits, context_tokens, nullptr, nullptr, 0, context_len, context_len, 0, 1, vocab_size, penalty,
+                               (cudaStream_t)st));
+  return QIE_OK;
+}
+
 static int scratch(void** p, size_t* cap, size_t need) {
   if (*cap >= need) return QIE_OK;
   if (*p) cudaFree(*p);
@@ -378,6 +386,7 @@ int qie_convert_safetensors(const char* const* shard_paths, int n_shards, const 
 }
 
 static void engine_free(qie_engine* e) {
+  if (e && e->hist_d) cudaFree(e->hist_d);
   if (!e) return;
   cudaSetDevice(e->opts.device);
   if (e->stream) cudaStreamSynchronize(e->stream);
@@ -889,6 +898,23 @@ int qie_engine_set_sampling(qie_engine* e, int topk, float temperature_prefill, 
   e->temp_decode = temperature_decode;
   e->seed = seed;
   e->add_step = add_step;
+  return QIE_OK;
+}
+
+int qie_engine_set_repetition_penalty(qie_engine* e, float penalty) {
+  if (!e || !(penalty > 0.0f)) return fail(QIE_EINVAL, "repetition penalty must be > 0");
+  if (e->opts.tp_size > 1 && penalty != 1.0f) return fail(QIE_EINVAL, "repetition penalty over a sharded vocabulary is not built");
+  CU(cudaSetDevice(e->opts.device));
+  CU(cudaStreamSynchronize(e->stream));
+  if (penalty != 1.0f && !e->hist_d) {
+    const size_t n = e->seqs.size() * (size_t)e->cfg.context;
+    CU(cudaMalloc(&e->hist_d, n * sizeof(int)));
+    CU(cudaMemset(e->hist_d, 0xff, n * sizeof(int)));  // -1: positions never written are ignored by the kernel
+  }
+  e->rep_penalty = penalty;
+  for (auto& kvp : e->graphs)  // captured graphs bake the launch sequence in
+    if (kvp.second.exec) cudaGraphExecDestroy(kvp.second.exec);
+  e->graphs.clear();
   return QIE_OK;
 }
 

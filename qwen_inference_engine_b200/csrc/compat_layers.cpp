@@ -307,6 +307,9 @@ void proj(const tensor& t, std::ifstream&, __nv_bfloat16*, __nv_bfloat16* w_d, s
   assign_weight_pointer(t, w_d, blob);
   launch_matmul(x, w_d, y, m, n, k);
 }
+void apply_repetition_penalty(__nv_bfloat16* logits, const int* context_tokens, size_t context_len, int vocab_size, float penalty) {
+  qie_repetition_penalty(QB(logits), context_tokens, context_len, vocab_size, penalty, nullptr);
+}
 int sample_topk_bf16(__nv_bfloat16* logits_d, int vocab, float temperature, int topk, unsigned long long seed, int step) {
   int* d_tok = nullptr;
   int h_tok = -1;

@@ -126,6 +126,7 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
     return fast ? launch_rmsnorm_fast(x, w, y, H, rows, H, st) : launch_rmsnorm_ref(x, w, y, H, rows, H, st);
   };
 
+  if (e->hist_d) QIE_TRY(KK_EMBED, launch_history_append(e->hist_d, (size_t)c.context, e->ids_d, e->pos_d, e->slot_d, n, st));
   if (!e->inject_x) QIE_TRY(KK_EMBED, launch_embedding(e->x, e->embed, e->ids_d, H, n, st));
   const int l_begin = e->layer_count > 0 ? std::min(e->layer_first, c.layers) : 0;
   const int l_end = e->layer_count > 0 ? std::min(l_begin + e->layer_count, c.layers) : c.layers;
@@ -314,6 +315,9 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
     if (r != cudaSuccess) return r;
   }
   capture_copy(e, "logits", -1, e->logits, (size_t)n_out * c.vocab);
+  if (e->hist_d && e->rep_penalty != 1.0f)  // the context of output row r: positions 0 .. pos[out_row0 + r] of its sequence
+    QIE_TRY(KK_SAMPLE, launch_repetition_penalty(e->logits, e->hist_d, e->slot_d + out_row0, e->pos_d + out_row0, 1, 0, (size_t)max_kv_len,
+                                                 (size_t)c.context, n_out, c.vocab, e->rep_penalty, st));
   QIE_TRY(KK_SAMPLE, launch_sample_topk(e->logits, e->sampled_d, n_out, c.vocab, temperature, e->topk, e->seed, 0,
                              e->add_step ? e->rowstep_d : nullptr, st));
   if (advance) QIE_TRY(KK_ADVANCE, launch_advance(e->pos_d, e->ids_d, e->sampled_d, n_out, e->rowstep_d, st));
@@ -507,8 +511,13 @@ cudaError_t forward_decode_mega(qie_engine* e, int n_total, int max_kv_len, floa
     if (r != cudaSuccess) return r;
   }
   const qie_config& c = e->cfg;
-  if (e->tp.size <= 1 && e->topk != 1 && e->mega_layers_run <= 0) {
-    // top-k > 1: the sampler is the reference's k-round scan + XORWOW draw (logit_decode.cu:149-274)
+  const bool penal = e->hist_d && e->rep_penalty != 1.0f;
+  if (e->tp.size <= 1 && (e->topk != 1 || penal) && e->mega_layers_run <= 0) {
+    // top-k > 1 / repetition penalty: the kernel left the logits; penalty, then the sampler (radix-select top-k +
+    // the reference's XORWOW draw, logit_decode.cu:149-274), then the step bookkeeping
+    if (penal)
+      QIE_TRY(KK_SAMPLE, launch_repetition_penalty(e->logits, e->hist_d, e->slot_d, e->pos_d, 1, 0, (size_t)max_kv_len, (size_t)c.context,
+                                                   n_total, c.vocab, e->rep_penalty, e->stream));
     QIE_TRY(KK_SAMPLE, launch_sample_topk(e->logits, e->sampled_d, n_total, c.vocab, temperature, e->topk, e->seed, 0,
                                           e->add_step ? e->rowstep_d : nullptr, e->stream));
     QIE_TRY(KK_ADVANCE, launch_advance(e->pos_d, e->ids_d, e->sampled_d, n_total, e->rowstep_d, e->stream));
@@ -518,6 +527,8 @@ cudaError_t forward_decode_mega(qie_engine* e, int n_total, int max_kv_len, floa
 
 static cudaError_t forward_decode_mega_rows(qie_engine* e, int row0, int n, int max_kv_len, float temperature) {
   const qie_config& c = e->cfg;
+  if (e->hist_d)
+    QIE_TRY(KK_EMBED, launch_history_append(e->hist_d, (size_t)c.context, e->ids_d + row0, e->pos_d + row0, e->slot_d + row0, n, e->stream));
   MegaArgs a{};
   a.H = c.hidden;
   a.I = c.inter;
@@ -555,7 +566,7 @@ static cudaError_t forward_decode_mega_rows(qie_engine* e, int row0, int n, int 
   a.bar = e->mega_bar_d;
   a.prof = e->mega_prof_on ? e->mega_prof_d : nullptr;
   a.prof_stride = 16 * c.layers + 8;
-  a.greedy = e->topk == 1;
+  a.greedy = e->topk == 1 && !(e->hist_d && e->rep_penalty != 1.0f);
   a.fast = e->opts.numerics == QIE_NUMERICS_FAST ? 1 : 0;
   {
     // measured on B200 (batch 64 / ctx 2048): no gain -- the attention phase is bound by shared-memory

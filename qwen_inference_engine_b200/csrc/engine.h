@@ -116,6 +116,8 @@ struct qie_engine {
   qie::TensorMap2D* mega_wmaps_tp_d[2] = {nullptr, nullptr};  // weight views of this rank's shard
 
   // sampling
+  float rep_penalty = 1.0f;  // != 1: token history kept per sequence, penalty applied to the logits before sampling
+  int* hist_d = nullptr;     // [max_seqs][cfg.context] input tokens by position (allocated when a penalty is first set)
   int topk = 1;
   float temp_prefill = 1.0f, temp_decode = 0.7f;
   uint64_t seed = 1234;

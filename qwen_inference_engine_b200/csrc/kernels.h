@@ -158,6 +158,11 @@ cudaError_t launch_sample_topk(const bf16* logits, int* out_tokens, int n_rows, 
                                int k, uint64_t seed, uint64_t seed_stride, const int* step_ptr, cudaStream_t st,
                                uint64_t subsequence = 0);  // XORWOW subsequence (the reference's last sample_topk_bf16 argument)
 
+// repetition penalty over each row's context tokens (ops_ref_order.cu) + the engine's token history
+cudaError_t launch_repetition_penalty(bf16* logits, const int* ctx, const int* ctx_row, const int* ctx_len, int len_bias, size_t fixed_len,
+                                      size_t max_len, size_t ctx_stride, int n_rows, int vocab, float penalty, cudaStream_t st);
+cudaError_t launch_history_append(int* hist, size_t stride, const int* ids, const int* pos, const int* slot, int n, cudaStream_t st);
+
 // synthetic weights on the device (twin of the host generator)
 cudaError_t launch_synth_fill(bf16* blob, size_t elem_begin, size_t n_elems, uint64_t seed, int kind,
                               cudaStream_t st);

@@ -656,6 +656,150 @@ __global__ void greedy_merge_kernel(const Cand* __restrict__ cands, int* __restr
   out[r] = bi;  // -1 if the row holds no finite logit, like the scan above
 }
 
+// Top-k (k > 1) without k scans.  The reference selects by k rounds of "arg-max over everything not chosen yet"
+// (logit_decode.cu:182-223), i.e. the k best elements of the row in its total order -- value, then the larger
+// bit-reversed low byte of the index, then the lower index (cand_better) -- best first.  That order is the numeric
+// order of a 48-bit key [16: order-preserving bf16][8: brev(idx & 255)][24: 0xFFFFFF - idx], all keys distinct, so the
+// k-th best key is found by a radix select: six 8-bit digits from the top, one 256-bin shared-memory histogram pass
+// over the row per digit (the row is 300 KB and stays in L2), then one pass collects the k keys >= the threshold, a
+// bitonic sort orders them, and thread 0 runs the reference's tail (temperature, softmax over k, XORWOW draw, CDF
+// scan) unchanged.  7 passes instead of k = 50 (x exclusion-list checks); one block of 1024 threads per row.
+__device__ __forceinline__ unsigned long long topk_key(uint16_t bits, int idx) {
+  if (bits == 0x8000u) bits = 0;  // -0.0 == +0.0 in the reference's float compares
+  const uint32_t v16 = (bits & 0x8000u) ? (uint32_t)(uint16_t)~bits : (uint32_t)(bits | 0x8000u);
+  const uint32_t rev = __brev((unsigned)idx << 24);  // brev of the low byte, in the low byte
+  return ((unsigned long long)v16 << 32) | ((unsigned long long)rev << 24) | (unsigned long long)(0xFFFFFFu - (unsigned)idx);
+}
+__global__ void __launch_bounds__(1024) sample_topk_select_kernel(const bf16* __restrict__ logits, int* __restrict__ out, size_t vocab,
+                                                                    float temperature, int k, uint64_t seed, uint64_t seed_stride,
+                                                                    const int* __restrict__ step_ptr, unsigned long long subsequence) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ unsigned hist[256];
+  __shared__ unsigned long long sel[256];  // the selected keys, then sorted best first
+  __shared__ float topk_vals[256];
+  __shared__ int topk_idxs[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_need, s_count;
+  const uint16_t* row = reinterpret_cast<const uint16_t*>(logits) + (size_t)blockIdx.x * vocab;
+  const int tid = threadIdx.x;
+  if (!(temperature > 0.0f)) temperature = 1.0f;
+  k = min(k, (int)min(vocab, (size_t)256));
+  auto valid = [](uint16_t b) {  // -inf and NaN are never selected (the reference's v > best fails for both)
+    const uint16_t a = b & 0x7fffu;
+    return !(a > 0x7f80u) && b != 0xff80u;
+  };
+  // how many candidates exist at all
+  unsigned mine = 0;
+  for (size_t i = tid; i < vocab; i += blockDim.x) mine += valid(row[i]) ? 1u : 0u;
+  if (tid == 0) s_count = 0;
+  __syncthreads();
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if ((tid & 31) == 0 && mine) atomicAdd(&s_count, (int)mine);
+  __syncthreads();
+  const int actual_k = min(k, s_count);
+  if (actual_k <= 0) {
+    if (tid == 0) out[blockIdx.x] = -1;
+    return;
+  }
+  if (tid == 0) {
+    s_prefix = 0ull;
+    s_need = actual_k;
+  }
+  // ---- radix select of the actual_k-th largest key
+  for (int d = 5; d >= 0; --d) {
+    if (tid < 256) hist[tid] = 0u;
+    __syncthreads();
+    const unsigned long long prefix = s_prefix;
+    const int shift = 8 * d;
+    for (size_t i = tid; i < vocab; i += blockDim.x) {
+      const uint16_t b = row[i];
+      if (!valid(b)) continue;
+      const unsigned long long key = topk_key(b, (int)i);
+      if (d == 5 || (key >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int need = s_need, dig = 255;
+      for (; dig > 0; --dig) {  // digits above the threshold digit are taken whole
+        if ((int)hist[dig] >= need) break;
+        need -= (int)hist[dig];
+      }
+      s_prefix = prefix | ((unsigned long long)dig << shift);
+      s_need = need;
+    }
+    __syncthreads();
+  }
+  // ---- collect the keys >= threshold (exactly actual_k: keys are distinct)
+  const unsigned long long thr = s_prefix;
+  if (tid == 0) s_count = 0;
+  if (tid < 256) sel[tid] = 0ull;
+  __syncthreads();
+  for (size_t i = tid; i < vocab; i += blockDim.x) {
+    const uint16_t b = row[i];
+    if (!valid(b)) continue;
+    const unsigned long long key = topk_key(b, (int)i);
+    if (key >= thr) {
+      const int slot = atomicAdd(&s_count, 1);
+      if (slot < 256) sel[slot] = key;
+    }
+  }
+  __syncthreads();
+  // ---- bitonic sort of 256 keys, descending (empty slots are 0 = below every real key)
+  for (int size = 2; size <= 256; size <<= 1)
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      if (tid < 128) {
+        const int lo = 2 * tid - (tid & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const unsigned long long a = sel[lo], b2 = sel[hi];
+        if ((a < b2) == desc) {
+          sel[lo] = b2;
+          sel[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  if (tid < actual_k) {
+    const int idx = (int)(0xFFFFFFu - (unsigned)(sel[tid] & 0xFFFFFFull));
+    topk_idxs[tid] = idx;
+    topk_vals[tid] = bf2f(logits[(size_t)blockIdx.x * vocab + idx]);
+  }
+  __syncthreads();
+  if (tid == 0) {  // the reference's tail, logit_decode.cu:225-273 (as in sample_topk_kernel)
+    if (actual_k == 1) {
+      out[blockIdx.x] = topk_idxs[0];
+      return;
+    }
+    float max_val = __fdiv_rn(topk_vals[0], temperature);
+    for (int i = 1; i < actual_k; ++i) {
+      float v = __fdiv_rn(topk_vals[i], temperature);
+      if (v > max_val) max_val = v;
+      topk_vals[i] = v;
+    }
+    topk_vals[0] = __fdiv_rn(topk_vals[0], temperature);
+    float sum = 0.0f;
+    for (int i = 0; i < actual_k; ++i) {
+      topk_vals[i] = expf(__fsub_rn(topk_vals[i], max_val));
+      sum = __fadd_rn(sum, topk_vals[i]);
+    }
+    curandState rng;
+    unsigned long long sd = seed + (unsigned long long)blockIdx.x * seed_stride + (step_ptr ? (unsigned)step_ptr[blockIdx.x] : 0u);
+    curand_init(sd, subsequence, 0, &rng);
+    float u = __fmul_rn(curand_uniform(&rng), sum);
+    float cum = 0.0f;
+    int picked = topk_idxs[actual_k - 1];
+    for (int i = 0; i < actual_k; ++i) {
+      cum = __fadd_rn(cum, topk_vals[i]);
+      if (u <= cum) {
+        picked = topk_idxs[i];
+        break;
+      }
+    }
+    out[blockIdx.x] = picked;
+  }
+}
+
 cudaError_t launch_sample_topk(const bf16* logits, int* out_tokens, int n_rows, size_t vocab, float temperature,
                                int k, uint64_t seed, uint64_t seed_stride, const int* step_ptr, cudaStream_t st,
                                uint64_t subsequence) {
@@ -690,8 +834,62 @@ cudaError_t launch_sample_topk(const bf16* logits, int* out_tokens, int n_rows, 
     (void)launch_k(greedy_merge_kernel, dim3((n_rows + 63) / 64), dim3(64), 0, st, (const Cand*)cands, out_tokens, n_rows);
     return cudaGetLastError();
   }
-  (void)launch_k(sample_topk_kernel, dim3(n_rows), dim3(1024), 0, st, logits, out_tokens, vocab, temperature, k, seed, seed_stride, step_ptr,
-                 (unsigned long long)subsequence);
+  // k > 1: radix-select kernel (7 passes over the row); QIE_TOPK_SCAN=1 keeps the k-round scan of the reference (A/B knob,
+  // and the only path for vocabularies beyond 2^24 entries, which the 24-bit index field of the key cannot hold)
+  static const bool scan_env = [] { const char* v = getenv("QIE_TOPK_SCAN"); return v && v[0] == '1'; }();
+  if (k > 1 && !scan_env && vocab < (1u << 24))
+    (void)launch_k(sample_topk_select_kernel, dim3(n_rows), dim3(1024), 0, st, logits, out_tokens, vocab, temperature, k, seed, seed_stride,
+                   step_ptr, (unsigned long long)subsequence);
+  else
+    (void)launch_k(sample_topk_kernel, dim3(n_rows), dim3(1024), 0, st, logits, out_tokens, vocab, temperature, k, seed, seed_stride, step_ptr,
+                   (unsigned long long)subsequence);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ repetition penalty
+// apply_repetition_penalty_kernel is declared by the reference (include/layers_include.cuh:33) and never defined; the
+// conventional semantics are implemented (see oracle/qie_oracle.c orc_repetition_penalty): every DISTINCT token id of
+// a row's context has its logit divided (positive) or multiplied (otherwise) by the penalty.  Row r's context is
+// ctx[ctx_row[r] * ctx_stride + 0 .. ctx_len[r]) (ctx_row == nullptr: row r, ctx_len == nullptr: fixed_len).
+// One thread per context position; only the first occurrence of a token applies, so no logit is written twice.
+__global__ void repetition_penalty_kernel(bf16* __restrict__ logits, const int* __restrict__ ctx, const int* __restrict__ ctx_row,
+                                          const int* __restrict__ ctx_len, int len_bias, size_t fixed_len, size_t ctx_stride, int vocab,
+                                          float penalty) {
+  pdl_wait();
+  pdl_trigger();
+  const int r = blockIdx.y;
+  const size_t n = ctx_len ? (size_t)(ctx_len[r] + len_bias) : fixed_len;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int* c = ctx + (size_t)(ctx_row ? ctx_row[r] : r) * ctx_stride;
+  const int t = c[i];
+  if (t < 0 || t >= vocab) return;
+  for (size_t j = 0; j < i; ++j)
+    if (c[j] == t) return;
+  bf16* p = logits + (size_t)r * vocab + t;
+  float v = bf2f(*p);
+  v = v > 0.0f ? __fdiv_rn(v, penalty) : __fmul_rn(v, penalty);
+  *p = f2bf(v);
+}
+cudaError_t launch_repetition_penalty(bf16* logits, const int* ctx, const int* ctx_row, const int* ctx_len, int len_bias, size_t fixed_len,
+                                      size_t max_len, size_t ctx_stride, int n_rows, int vocab, float penalty, cudaStream_t st) {
+  if (n_rows == 0 || max_len == 0) return cudaSuccess;
+  (void)launch_k(repetition_penalty_kernel, dim3((unsigned)((max_len + 255) / 256), n_rows), dim3(256), 0, st, logits, ctx, ctx_row, ctx_len,
+                 len_bias, fixed_len, ctx_stride, vocab, penalty);
+  return cudaGetLastError();
+}
+// token history of the engine's sequences (only kept while a repetition penalty is set): the input token of every row
+// of a forward goes to hist[slot[t]][pos[t]]
+__global__ void history_append_kernel(int* __restrict__ hist, size_t stride, const int* __restrict__ ids, const int* __restrict__ pos,
+                                      const int* __restrict__ slot, int n) {
+  pdl_wait();
+  pdl_trigger();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n && (size_t)pos[t] < stride) hist[(size_t)slot[t] * stride + pos[t]] = ids[t];
+}
+cudaError_t launch_history_append(int* hist, size_t stride, const int* ids, const int* pos, const int* slot, int n, cudaStream_t st) {
+  if (!n) return cudaSuccess;
+  (void)launch_k(history_append_kernel, dim3((n + 127) / 128), dim3(128), 0, st, hist, stride, ids, pos, slot, n);
   return cudaGetLastError();
 }
 

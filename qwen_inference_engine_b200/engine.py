@@ -142,6 +142,9 @@ class Engine:
         check(self._L.qie_engine_set_sampling(self._h, topk, temperature_prefill, temperature_decode, seed,
                                               int(add_step)))
 
+    def set_repetition_penalty(self, penalty):
+        check(self._L.qie_engine_set_repetition_penalty(self._h, float(penalty)))
+
     @property
     def stream(self):
         return self._L.qie_engine_stream(self._h)

@@ -108,6 +108,11 @@ def sample_topk_bf16(logits_d, vocab, temperature, topk, seed, step=0):
     return out.cpu().numpy()
 
 
+def apply_repetition_penalty(logits_d, context_tokens_d, vocab, penalty):
+    """layers_include.cuh:33 (declared, never defined in the reference): in place on one row of logits"""
+    check(_lib.lib().qie_repetition_penalty(_p(logits_d), _p(context_tokens_d), context_tokens_d.numel(), vocab, float(penalty), _st()))
+
+
 # ---- fast-numerics operators (tolerance parity, see include/qie_b200.h) ---------------------
 def launch_matmul_fast(A, B, Cout, M, N, K):
     """tcgen05/TMEM/TMA GEMM: same contract as launch_matmul, results within 1e-2 (bf16)."""
