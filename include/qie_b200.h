@@ -41,7 +41,7 @@ typedef uint16_t qie_bf16;     /* raw __nv_bfloat16 bits */
 
 const char* qie_last_error(void);
 /* ABI version; bumped on any signature change. */
-int qie_abi_version(void); /* currently 4 */
+int qie_abi_version(void); /* currently 5 */
 
 /* ------------------------------------------------------------------------------------
  * (1) operator level.  All pointers are DEVICE pointers unless named h_*.
@@ -179,7 +179,18 @@ typedef struct {
   int use_graph;         /* replay decode steps from a CUDA graph */
   int tp_rank, tp_size;  /* tensor-parallel shard (1 = off) */
   int numerics;          /* QIE_NUMERICS_REFERENCE_ORDER (default) or QIE_NUMERICS_FAST */
+  int semantics;         /* QIE_SEMANTICS_REFERENCE (default) or QIE_SEMANTICS_HF */
+  float rms_eps;         /* RMSNorm / q,k-norm epsilon; 0 = by semantics (1e-4 reference, 1e-6 HF) */
 } qie_engine_opts;
+
+/* Model semantics.  REFERENCE: what the reference's kernels compute -- interleaved-pair RoPE (src/RoPE.cu:6-22), eps 1e-4
+ * (src/normalization.cu:9, src/qk_norm.cu:46).  HF: what the published Qwen2.5 / Qwen3 checkpoints were trained with --
+ * half-rotation RoPE (transformers' rotate_half) and eps 1e-6.  Independently of this switch, and driven by the
+ * checkpoint's tensors only: per-head q/k-norm is applied iff self_attn.{q,k}_norm.weight exist (Qwen3: yes, Qwen2.5:
+ * no), projection biases are added iff self_attn.{q,k,v}_proj.bias exist (Qwen2.5: yes; y = bf16(bf16(acc) + bias)).
+ * HF semantics and biases run on the per-operator launch path (the persistent decode kernel keeps the reference's). */
+#define QIE_SEMANTICS_REFERENCE 0
+#define QIE_SEMANTICS_HF 1
 
 /* REFERENCE_ORDER: every kernel reproduces the reference's fp32 operation order; results
  * are bit-identical to the reference's kernels (greedy tokens, logits, activations).

@@ -68,6 +68,7 @@ class Oracle:
         L.orc_model_load.restype = vp
         L.orc_model_load.argtypes = [C.c_char_p, C.c_char_p, i32, i32]
         L.orc_model_free.argtypes = [vp]
+        L.orc_model_set_semantics.argtypes = [vp, i32, f32]
         L.orc_model_config.restype = C.POINTER(OrcConfig)
         L.orc_model_config.argtypes = [vp]
         L.orc_model_tensor.restype = vp
@@ -200,6 +201,11 @@ class OracleModel:
         self.cfg = oracle.L.orc_model_config(self.m).contents
         self.page_size = page_size
         self._seqs = []
+
+    def set_semantics(self, rope_half=False, eps=1e-4):
+        """HF / Qwen2.5-Qwen3 checkpoints: rope_half=True, eps=1e-6 (the reference: interleaved RoPE, 1e-4)"""
+        self.o.L.orc_model_set_semantics(self.m, int(rope_half), float(eps))
+        return self
 
     def tensor(self, short_name, layer=-1):
         n = C.c_size_t()

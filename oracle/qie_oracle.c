@@ -71,7 +71,9 @@ void orc_embedding(orc_bf16* out, const orc_bf16* table, const int* ids, size_t 
  * src/normalization.cu:5-26.  One thread per token; sum is a sequential fp32 chain,
  * contracted by nvcc to FFMA (sum = fma(x,x,sum)); eps 1e-4 (:9); (x/rms)*w (:23). */
 void orc_rmsnorm(const orc_bf16* x, const orc_bf16* w, orc_bf16* y, size_t hidden, size_t n_tok) {
-  const float e = 1e-04f;
+  orc_rmsnorm_eps(x, w, y, hidden, n_tok, 1e-04f);
+}
+void orc_rmsnorm_eps(const orc_bf16* x, const orc_bf16* w, orc_bf16* y, size_t hidden, size_t n_tok, float e) {
   for (size_t t = 0; t < n_tok; t++) {
     float sum = 0;
     for (size_t i = 0; i < hidden; i++) {
@@ -148,7 +150,9 @@ static float tree_sum(float* buf, int n) {
 }
 
 void orc_qknorm(orc_bf16* qk, const orc_bf16* w, int head_dim, int n_tok, int row_dim, int n_heads) {
-  const float eps = 1e-04f;
+  orc_qknorm_eps(qk, w, head_dim, n_tok, row_dim, n_heads, 1e-04f);
+}
+void orc_qknorm_eps(orc_bf16* qk, const orc_bf16* w, int head_dim, int n_tok, int row_dim, int n_heads, float eps) {
   float buf[256];
   for (int h = 0; h < n_heads; h++)
     for (int tok = 0; tok < n_tok; tok++) {
@@ -180,6 +184,31 @@ void orc_rope(const float* cos_values, const float* sin_values, orc_bf16* x, int
         x[base + i] = orc_f2bf(v1);
         x[base + i + 1] = orc_f2bf(v2);
       }
+}
+
+/* "HF-correct" RoPE (transformers' rotate_half): element j of a head pairs with j + hd/2,
+ *   out[j] = x[j]*c_j - x[j+hd/2]*s_j ;  out[j+hd/2] = x[j+hd/2]*c_j + x[j]*s_j,   c_j, s_j the same table rows.
+ * Not in the reference (its RoPE is the interleaved form above); fp32 math, one bf16 rounding, same fma placement. */
+void orc_rope_half(const float* cos_values, const float* sin_values, orc_bf16* x, int n_tok, int head_dim, int row_dim,
+                   int n_heads) {
+  int half = head_dim / 2;
+  for (int idx = 0; idx < n_tok; idx++)
+    for (int h = 0; h < n_heads; h++)
+      for (int j = 0; j < half; j++) {
+        size_t base = (size_t)idx * row_dim + (size_t)h * head_dim;
+        float x0 = orc_bf2f(x[base + j]), x1 = orc_bf2f(x[base + j + half]);
+        float c = cos_values[(size_t)idx * half + j], s = sin_values[(size_t)idx * half + j];
+        float v1 = fmaf(x0, c, -(x1 * s));
+        float v2 = fmaf(c, x1, x0 * s);
+        x[base + j] = orc_f2bf(v1);
+        x[base + j + half] = orc_f2bf(v2);
+      }
+}
+/* projection bias (Qwen2.5 q/k/v_proj.bias; the reference has none): y = bf16(float(y) + float(b)) on the already
+ * rounded projection output, per row */
+void orc_add_bias(orc_bf16* y, const orc_bf16* b, int n_tok, int dim) {
+  for (int t = 0; t < n_tok; t++)
+    for (int i = 0; i < dim; i++) y[(size_t)t * dim + i] = orc_f2bf(orc_bf2f(y[(size_t)t * dim + i]) + orc_bf2f(b[i]));
 }
 
 /* ------------------------------------------------------------------ SiLU, mul, add
@@ -484,6 +513,9 @@ struct orc_model {
   size_t blob_bytes;
   int fd;
   float *cos_t, *sin_t;
+  /* semantics switches (orc_model_set_semantics): the reference's are eps 1e-4 + interleaved RoPE */
+  float eps;
+  int rope_half;
 };
 
 static const orc_tensor* find_tensor(const orc_model* m, const char* short_name, int layer) {
@@ -501,6 +533,10 @@ const orc_bf16* orc_model_tensor(const orc_model* m, const char* short_name, int
 }
 
 const orc_config* orc_model_config(const orc_model* m) { return &m->cfg; }
+void orc_model_set_semantics(orc_model* m, int rope_half, float eps) {
+  m->rope_half = rope_half;
+  m->eps = eps > 0 ? eps : 1e-04f;
+}
 
 orc_model* orc_model_load(const char* meta_path, const char* weights_path, int head_dim_hint, int context) {
   FILE* f = fopen(meta_path, "r");
@@ -680,17 +716,29 @@ static void layer_stack(orc_seq* s, int n_tok, int pos0, int causal) {
   int H = c->hidden, hd = c->head_dim, Dq = c->n_q * hd, Dkv = c->n_kv * hd, I = c->inter;
   int half = hd / 2;
   for (int i = 0; i < c->layers; i++) {
-    orc_rmsnorm(s->x, orc_model_tensor(m, "input_layernorm.weight", i, NULL), s->rms_out, H, n_tok);
+    const float eps = m->eps > 0 ? m->eps : 1e-04f;
+    orc_rmsnorm_eps(s->x, orc_model_tensor(m, "input_layernorm.weight", i, NULL), s->rms_out, H, n_tok, eps);
     DUMP("input_norm", i, s->rms_out, (size_t)n_tok * H);
     orc_matmul(s->rms_out, orc_model_tensor(m, "self_attn.q_proj.weight", i, NULL), s->Q, n_tok, H, Dq);
     orc_matmul(s->rms_out, orc_model_tensor(m, "self_attn.k_proj.weight", i, NULL), s->K, n_tok, H, Dkv);
     orc_matmul(s->rms_out, orc_model_tensor(m, "self_attn.v_proj.weight", i, NULL), s->V, n_tok, H, Dkv);
     const orc_bf16* qn = orc_model_tensor(m, "self_attn.q_norm.weight", i, NULL);
     const orc_bf16* kn = orc_model_tensor(m, "self_attn.k_norm.weight", i, NULL);
-    if (qn) orc_qknorm(s->Q, qn, hd, n_tok, Dq, c->n_q);
-    if (kn) orc_qknorm(s->K, kn, hd, n_tok, Dkv, c->n_kv);
-    orc_rope(m->cos_t + (size_t)pos0 * half, m->sin_t + (size_t)pos0 * half, s->Q, n_tok, hd, Dq, c->n_q);
-    orc_rope(m->cos_t + (size_t)pos0 * half, m->sin_t + (size_t)pos0 * half, s->K, n_tok, hd, Dkv, c->n_kv);
+    const orc_bf16* qb = orc_model_tensor(m, "self_attn.q_proj.bias", i, NULL);
+    const orc_bf16* kb = orc_model_tensor(m, "self_attn.k_proj.bias", i, NULL);
+    const orc_bf16* vb = orc_model_tensor(m, "self_attn.v_proj.bias", i, NULL);
+    if (qb) orc_add_bias(s->Q, qb, n_tok, Dq);
+    if (kb) orc_add_bias(s->K, kb, n_tok, Dkv);
+    if (vb) orc_add_bias(s->V, vb, n_tok, Dkv);
+    if (qn) orc_qknorm_eps(s->Q, qn, hd, n_tok, Dq, c->n_q, eps);
+    if (kn) orc_qknorm_eps(s->K, kn, hd, n_tok, Dkv, c->n_kv, eps);
+    if (m->rope_half) {
+      orc_rope_half(m->cos_t + (size_t)pos0 * half, m->sin_t + (size_t)pos0 * half, s->Q, n_tok, hd, Dq, c->n_q);
+      orc_rope_half(m->cos_t + (size_t)pos0 * half, m->sin_t + (size_t)pos0 * half, s->K, n_tok, hd, Dkv, c->n_kv);
+    } else {
+      orc_rope(m->cos_t + (size_t)pos0 * half, m->sin_t + (size_t)pos0 * half, s->Q, n_tok, hd, Dq, c->n_q);
+      orc_rope(m->cos_t + (size_t)pos0 * half, m->sin_t + (size_t)pos0 * half, s->K, n_tok, hd, Dkv, c->n_kv);
+    }
     DUMP("q", i, s->Q, (size_t)n_tok * Dq);
     DUMP("k", i, s->K, (size_t)n_tok * Dkv);
     DUMP("v", i, s->V, (size_t)n_tok * Dkv);
@@ -700,7 +748,7 @@ static void layer_stack(orc_seq* s, int n_tok, int pos0, int causal) {
     orc_matmul(s->att, orc_model_tensor(m, "self_attn.o_proj.weight", i, NULL), s->o, n_tok, Dq, H);
     orc_residual_add(s->x, s->o, (size_t)n_tok * H);
     DUMP("x_attn", i, s->x, (size_t)n_tok * H);
-    orc_rmsnorm(s->x, orc_model_tensor(m, "post_attention_layernorm.weight", i, NULL), s->rms_out, H, n_tok);
+    orc_rmsnorm_eps(s->x, orc_model_tensor(m, "post_attention_layernorm.weight", i, NULL), s->rms_out, H, n_tok, eps);
     orc_matmul(s->rms_out, orc_model_tensor(m, "mlp.up_proj.weight", i, NULL), s->up, n_tok, H, I);
     orc_matmul(s->rms_out, orc_model_tensor(m, "mlp.gate_proj.weight", i, NULL), s->gate, n_tok, H, I);
     orc_silu(s->gate, (size_t)n_tok * I);
@@ -719,7 +767,7 @@ static int head_and_sample(orc_seq* s, int row, int topk, float temperature, uin
   int H = c->hidden;
   /* final norm is applied to every row in the reference (qwen_main.cu:227); only `row`
    * is consumed (:233 copy_last_vocab_vec / :368 copy_first_token). */
-  orc_rmsnorm(s->x + (size_t)row * H, orc_model_tensor(m, "norm.weight", 0, NULL), s->rms_out, H, 1);
+  orc_rmsnorm_eps(s->x + (size_t)row * H, orc_model_tensor(m, "norm.weight", 0, NULL), s->rms_out, H, 1, m->eps > 0 ? m->eps : 1e-04f);
   orc_matmul(s->rms_out, orc_model_tensor(m, "logits", 0, NULL), s->logits, 1, H, c->vocab);
   if (logits_out) memcpy(logits_out, s->logits, sizeof(orc_bf16) * (size_t)c->vocab);
   DUMP("logits", -1, s->logits, (size_t)c->vocab);

@@ -52,6 +52,7 @@ void orc_embedding(orc_bf16* out, const orc_bf16* table, const int* ids, size_t 
 
 /* src/normalization.cu:5-26 rmsNorm */
 void orc_rmsnorm(const orc_bf16* x, const orc_bf16* w, orc_bf16* y, size_t hidden, size_t n_tok);
+void orc_rmsnorm_eps(const orc_bf16* x, const orc_bf16* w, orc_bf16* y, size_t hidden, size_t n_tok, float eps);
 
 /* src/matrix_mul.cu:165-288 matrix_mul (via helpers.cuh:81 launch_matmul):
  * C[M,K] = A[M,N] * B[K,N]^T, fp32 accumulate over N in 16-wide chunks, bf16 store.
@@ -60,6 +61,10 @@ void orc_matmul(const orc_bf16* A, const orc_bf16* B, orc_bf16* C, int M, int N,
 
 /* src/qk_norm.cu:43-80 qkNorm (in place; one block per head, tree reduction) */
 void orc_qknorm(orc_bf16* qk, const orc_bf16* w, int head_dim, int n_tok, int row_dim, int n_heads);
+void orc_qknorm_eps(orc_bf16* qk, const orc_bf16* w, int head_dim, int n_tok, int row_dim, int n_heads, float eps);
+/* Qwen2.5 / HF semantics that the reference does not have */
+void orc_rope_half(const float* cos_values, const float* sin_values, orc_bf16* x, int n_tok, int head_dim, int row_dim, int n_heads);
+void orc_add_bias(orc_bf16* y, const orc_bf16* b, int n_tok, int dim);
 
 /* src/RoPE.cu:6-22 RoPE (in place, interleaved pairs). cos/sin point at the row of
  * the FIRST token (launch_rope_single pre-offsets them, helpers.cuh:143-147). */
@@ -108,6 +113,9 @@ orc_model* orc_model_load(const char* meta_path, const char* weights_path, int h
                           int context);
 void orc_model_free(orc_model* m);
 const orc_config* orc_model_config(const orc_model* m);
+/* rope_half != 0: HF rotate_half RoPE; eps: RMSNorm / q,k-norm epsilon (<= 0: the reference's 1e-4).  Projection biases are
+ * applied whenever the checkpoint holds self_attn.{q,k,v}_proj.bias. */
+void orc_model_set_semantics(orc_model* m, int rope_half, float eps);
 /* pointer to a tensor by short name / layer (layer ignored for globals); NULL if absent */
 const orc_bf16* orc_model_tensor(const orc_model* m, const char* short_name, int layer, size_t* n_elems);
 

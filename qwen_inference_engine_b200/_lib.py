@@ -31,7 +31,8 @@ class EngineOpts(C.Structure):
     _fields_ = [("device", C.c_int), ("page_size", C.c_int), ("max_pages", C.c_int),
                 ("kv_bytes", C.c_size_t), ("max_seqs", C.c_int), ("max_batch_tokens", C.c_int),
                 ("context", C.c_int), ("head_dim_hint", C.c_int), ("use_graph", C.c_int),
-                ("tp_rank", C.c_int), ("tp_size", C.c_int), ("numerics", C.c_int)]
+                ("tp_rank", C.c_int), ("tp_size", C.c_int), ("numerics", C.c_int),
+                ("semantics", C.c_int), ("rms_eps", C.c_float)]
 
 
 class KvView(C.Structure):

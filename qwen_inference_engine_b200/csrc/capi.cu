@@ -32,7 +32,7 @@ static int cuda_fail(cudaError_t e, const char* what) {
 extern "C" {
 
 const char* qie_last_error(void) { return g_err; }
-int qie_abi_version(void) { return 4; }
+int qie_abi_version(void) { return 5; }
 
 // ---------------------------------------------------------------- operator level
 int qie_embedding(qie_bf16* out, const qie_bf16* table, const int* ids, size_t hidden, size_t n_tok, qie_stream st) {
@@ -437,9 +437,24 @@ static int engine_finish_setup(qie_engine* e) {
     w.up = ptr("mlp.up_proj.weight", l);
     w.gate = ptr("mlp.gate_proj.weight", l);
     w.down = ptr("mlp.down_proj.weight", l);
+    w.q_bias = ptr("self_attn.q_proj.bias", l);  // data-driven: present in Qwen2.5 checkpoints
+    w.k_bias = ptr("self_attn.k_proj.bias", l);
+    w.v_bias = ptr("self_attn.v_proj.bias", l);
+    if (w.q_bias || w.k_bias || w.v_bias) e->has_bias = true;
     if (!w.in_ln || !w.q || !w.k || !w.v || !w.o || !w.post_ln || !w.up || !w.gate || !w.down)
       return fail(QIE_EIO, "layer %d: missing tensor in checkpoint", l);
   }
+  // biases the forward does not apply would give wrong logits without an error: refuse them
+  for (const TensorInfo& t : e->ck.tensors) {
+    const std::string& sn = t.short_name;
+    const bool is_bias = sn.size() > 5 && sn.compare(sn.size() - 5, 5, ".bias") == 0;
+    if (is_bias && sn != "self_attn.q_proj.bias" && sn != "self_attn.k_proj.bias" && sn != "self_attn.v_proj.bias")
+      return fail(QIE_EIO, "checkpoint tensor %s: this bias is not applied by the forward", t.name.c_str());
+  }
+  e->rope_half = e->opts.semantics == QIE_SEMANTICS_HF;
+  e->eps = e->opts.rms_eps > 0.0f ? e->opts.rms_eps : (e->opts.semantics == QIE_SEMANTICS_HF ? 1e-06f : 1e-04f);
+  if (e->opts.tp_size > 1 && (e->has_bias || e->rope_half || e->eps != 1e-04f))
+    return fail(QIE_EINVAL, "HF semantics / projection biases are not built for tensor parallelism");
   e->embed = ptr("embed_tokens.weight", -1);
   e->final_norm = ptr("norm.weight", -1);
   e->lm_head = ptr("logits", -1);

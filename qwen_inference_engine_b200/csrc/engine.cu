@@ -123,7 +123,7 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
   const bool fast_attn = fast && advance;         // decode rows: one token per sequence
   const bool fast_prefill = fast && !advance;     // prefill rows: consecutive positions of one sequence
   auto rms = [&](const bf16* x, const bf16* w, bf16* y, int rows) {
-    return fast ? launch_rmsnorm_fast(x, w, y, H, rows, H, st) : launch_rmsnorm_ref(x, w, y, H, rows, H, st);
+    return fast ? launch_rmsnorm_fast(x, w, y, H, rows, H, st, e->eps) : launch_rmsnorm_ref(x, w, y, H, rows, H, st, e->eps);
   };
 
   if (e->hist_d) QIE_TRY(KK_EMBED, launch_history_append(e->hist_d, (size_t)c.context, e->ids_d, e->pos_d, e->slot_d, n, st));
@@ -179,6 +179,11 @@ cudaError_t forward_rows(qie_engine* e, int n, int max_kv_len, int out_row0, int
       a.n_q = c.n_q;
       a.layer = l;
       a.kv = e->kv;
+      a.q_bias = w.q_bias;
+      a.k_bias = w.k_bias;
+      a.v_bias = w.v_bias;
+      a.eps = e->eps;
+      a.rope_half = e->rope_half ? 1 : 0;
       QIE_TRY(KK_QKV_POST, launch_qkv_post(a, st));
     }
     capture_copy(e, "q", l, e->q, (size_t)n * Dq);
@@ -479,6 +484,7 @@ cudaError_t forward_rows_tp(qie_engine* e, int n, int max_kv_len, int out_row0, 
 
 bool decode_uses_mega(const qie_engine* e, int n, int max_kv_len) {
   if (!e->use_mega || e->capture || !e->mega_layers_d || e->layer_count > 0 || e->inject_x) return false;
+  if (e->has_bias || e->rope_half || e->eps != 1e-04f) return false;  // the persistent kernel implements the reference's semantics only
   const qie_config& c = e->cfg;
   if (e->tp.size > 1) {
     // tensor parallel: the persistent kernel runs this rank's shard and exchanges partial sums over NVLink peer

@@ -20,6 +20,7 @@ namespace qie {
 struct LayerWeights {
   const bf16 *in_ln = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *o = nullptr, *q_norm = nullptr,
              *k_norm = nullptr, *post_ln = nullptr, *up = nullptr, *gate = nullptr, *down = nullptr;
+  const bf16 *q_bias = nullptr, *k_bias = nullptr, *v_bias = nullptr;  // Qwen2.5 checkpoints (the reference has none)
 };
 
 struct Sequence {
@@ -114,6 +115,10 @@ struct qie_engine {
   bool tp_mega_ready = false;
   qie::bf16* x2 = nullptr;            // residual ping-pong partner of x
   qie::TensorMap2D* mega_wmaps_tp_d[2] = {nullptr, nullptr};  // weight views of this rank's shard
+
+  // model semantics (opts.semantics / opts.rms_eps; include/qie_b200.h)
+  float eps = 1e-04f;
+  bool rope_half = false, has_bias = false;
 
   // sampling
   float rep_penalty = 1.0f;  // != 1: token history kept per sequence, penalty applied to the logits before sampling

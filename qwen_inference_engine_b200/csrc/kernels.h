@@ -52,7 +52,7 @@ cudaError_t launch_gemm_ref_order(const GemmArgs& args, int num_sms, cudaStream_
 cudaError_t launch_embedding(bf16* out, const bf16* table, const int* ids, size_t hidden, size_t n_tok,
                              cudaStream_t st);
 cudaError_t launch_rmsnorm_ref(const bf16* x, const bf16* w, bf16* y, size_t hidden, size_t n_tok,
-                               size_t x_stride, cudaStream_t st);
+                               size_t x_stride, cudaStream_t st, float eps = 1e-04f);
 cudaError_t launch_qknorm_ref(bf16* x, const bf16* w, int hd, int n_tok, int row_dim, int n_heads, cudaStream_t st);
 cudaError_t launch_rope_ref(const float* cos_t, const float* sin_t, bf16* x, int n_tok, const int* pos, int pos0,
                             int hd, int row_dim, int n_heads, cudaStream_t st);
@@ -78,6 +78,11 @@ struct QkvPostArgs {
   const int* block_table;  // [*, max_pages]
   int max_pages, n_tok, n_q, layer;
   KvGeom kv;
+  // model semantics beyond the reference's (data / option driven): projection biases (Qwen2.5),
+  // RMS epsilon (1e-4 in the reference, normalization.cu:9 / qk_norm.cu:46; 1e-6 in HF), half-rotation RoPE
+  const bf16 *q_bias = nullptr, *k_bias = nullptr, *v_bias = nullptr;
+  float eps = 1e-04f;
+  int rope_half = 0;
 };
 cudaError_t launch_qkv_post(const QkvPostArgs& a, cudaStream_t st);
 
@@ -151,7 +156,7 @@ struct TcGemm {
 cudaError_t launch_gemm_tcgen05(const TcGemm& t, int num_sms, cudaStream_t st, int* launches);
 
 cudaError_t launch_rmsnorm_fast(const bf16* x, const bf16* w, bf16* y, size_t hidden, size_t n_tok, size_t x_stride,
-                                cudaStream_t st);
+                                cudaStream_t st, float eps = 1e-04f);
 
 // sampling (reference tie-break + XORWOW)
 cudaError_t launch_sample_topk(const bf16* logits, int* out_tokens, int n_rows, size_t vocab, float temperature,

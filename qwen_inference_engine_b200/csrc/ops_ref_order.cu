@@ -55,7 +55,7 @@ cudaError_t launch_embedding(bf16* out, const bf16* table, const int* ids, size_
 // the chain order is part of the result.  Thread 0 walks the chain out of shared memory
 // (4-cycle dependent FFMA issue, loads hoisted), the block does the rest in parallel.
 __global__ void __launch_bounds__(128) rmsnorm_ref_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
-                                                           bf16* __restrict__ y, int hidden, size_t x_stride) {
+                                                           bf16* __restrict__ y, int hidden, size_t x_stride, float eps) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ float xs[];
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128) rmsnorm_ref_kernel(const bf16* __restrict
       sum = __fmaf_rn(v7, v7, sum);
     }
     for (; i < hidden; ++i) sum = __fmaf_rn(xs[i], xs[i], sum);
-    s_rms = __fsqrt_rn(__fadd_rn(__fdiv_rn(sum, (float)hidden), 1e-04f));
+    s_rms = __fsqrt_rn(__fadd_rn(__fdiv_rn(sum, (float)hidden), eps));  // eps 1e-4 in the reference (normalization.cu:9)
   }
   __syncthreads();
   const float rms = s_rms;
@@ -89,16 +89,16 @@ __global__ void __launch_bounds__(128) rmsnorm_ref_kernel(const bf16* __restrict
 }
 
 cudaError_t launch_rmsnorm_ref(const bf16* x, const bf16* w, bf16* y, size_t hidden, size_t n_tok, size_t x_stride,
-                               cudaStream_t st) {
+                               cudaStream_t st, float eps) {
   if (n_tok == 0) return cudaSuccess;
-  (void)launch_k(rmsnorm_ref_kernel, dim3((unsigned)n_tok), dim3(128), hidden * sizeof(float), st, x, w, y, (int)hidden, x_stride);
+  (void)launch_k(rmsnorm_ref_kernel, dim3((unsigned)n_tok), dim3(128), hidden * sizeof(float), st, x, w, y, (int)hidden, x_stride, eps);
   return cudaGetLastError();
 }
 
 // fast-numerics variant: the sum of squares is reduced in parallel (warp shuffles), so it
 // differs from the reference's sequential chain in the last fp32 bits.
 __global__ void __launch_bounds__(256) rmsnorm_fast_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
-                                                            bf16* __restrict__ y, int hidden, size_t x_stride) {
+                                                            bf16* __restrict__ y, int hidden, size_t x_stride, float eps) {
   pdl_wait();
   pdl_trigger();
   __shared__ float s_part[8];
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) rmsnorm_fast_kernel(const bf16* __restric
   float tot = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) tot += s_part[i];
-  const float rms = __fsqrt_rn(__fadd_rn(__fdiv_rn(tot, (float)hidden), 1e-04f));
+  const float rms = __fsqrt_rn(__fadd_rn(__fdiv_rn(tot, (float)hidden), eps));
   for (int i = threadIdx.x * 2; i < hidden; i += 512) {
     uint32_t v = *reinterpret_cast<const uint32_t*>(xr + i), wv = *reinterpret_cast<const uint32_t*>(w + i);
     *reinterpret_cast<uint32_t*>(yr + i) = pack2(f2bf(__fmul_rn(__fdiv_rn(lo2f(v), rms), lo2f(wv))),
@@ -124,10 +124,10 @@ __global__ void __launch_bounds__(256) rmsnorm_fast_kernel(const bf16* __restric
   }
 }
 cudaError_t launch_rmsnorm_fast(const bf16* x, const bf16* w, bf16* y, size_t hidden, size_t n_tok, size_t x_stride,
-                                cudaStream_t st) {
+                                cudaStream_t st, float eps) {
   if (n_tok == 0) return cudaSuccess;
   if (hidden & 1) return cudaErrorInvalidValue;
-  (void)launch_k(rmsnorm_fast_kernel, dim3((unsigned)n_tok), dim3(256), 0, st, x, w, y, (int)hidden, x_stride);
+  (void)launch_k(rmsnorm_fast_kernel, dim3((unsigned)n_tok), dim3(256), 0, st, x, w, y, (int)hidden, x_stride, eps);
   return cudaGetLastError();
 }
 
@@ -206,8 +206,12 @@ __global__ void qkv_post_kernel(QkvPostArgs a) {
   if (h < a.n_q) {
     bf16* p = a.q + (size_t)tok * a.n_q * hd + (size_t)h * hd;
     head_load<NP>(v, a.q_in + (size_t)tok * a.q_in_stride + (size_t)h * hd, lane);
-    if (a.q_norm_w) head_norm<NP>(v, a.q_norm_w, lane);
-    head_rope<NP>(v, a.cos_t + (size_t)ps * 32 * NP, a.sin_t + (size_t)ps * 32 * NP, lane);
+    if (a.q_bias) head_add_bias<NP>(v, a.q_bias + (size_t)h * hd, lane);
+    if (a.q_norm_w) head_norm<NP>(v, a.q_norm_w, lane, a.eps);
+    if (a.rope_half)
+      head_rope_half<NP>(v, a.cos_t + (size_t)ps * 32 * NP, a.sin_t + (size_t)ps * 32 * NP, lane);
+    else
+      head_rope<NP>(v, a.cos_t + (size_t)ps * 32 * NP, a.sin_t + (size_t)ps * 32 * NP, lane);
     head_store<NP>(v, p, lane);
     return;
   }
@@ -216,11 +220,21 @@ __global__ void qkv_post_kernel(QkvPostArgs a) {
   if (h < a.n_q + a.kv.n_kv) {
     int kh = h - a.n_q;
     head_load<NP>(v, a.k + (size_t)tok * a.kv_stride + (size_t)kh * hd, lane);
-    if (a.k_norm_w) head_norm<NP>(v, a.k_norm_w, lane);
-    head_rope<NP>(v, a.cos_t + (size_t)ps * 32 * NP, a.sin_t + (size_t)ps * 32 * NP, lane);
+    if (a.k_bias) head_add_bias<NP>(v, a.k_bias + (size_t)kh * hd, lane);
+    if (a.k_norm_w) head_norm<NP>(v, a.k_norm_w, lane, a.eps);
+    if (a.rope_half)
+      head_rope_half<NP>(v, a.cos_t + (size_t)ps * 32 * NP, a.sin_t + (size_t)ps * 32 * NP, lane);
+    else
+      head_rope<NP>(v, a.cos_t + (size_t)ps * 32 * NP, a.sin_t + (size_t)ps * 32 * NP, lane);
     head_store<NP>(v, a.kv.chunk(page, a.layer, 0, kh) + (size_t)off * hd, lane);
   } else {
     int vh = h - a.n_q - a.kv.n_kv;
+    if (a.v_bias) {
+      head_load<NP>(v, a.v + (size_t)tok * a.kv_stride + (size_t)vh * hd, lane);
+      head_add_bias<NP>(v, a.v_bias + (size_t)vh * hd, lane);
+      head_store<NP>(v, a.kv.chunk(page, a.layer, 1, vh) + (size_t)off * hd, lane);
+      return;
+    }
     const uint32_t* src = reinterpret_cast<const uint32_t*>(a.v + (size_t)tok * a.kv_stride + (size_t)vh * hd);
     uint32_t* dst = reinterpret_cast<uint32_t*>(a.kv.chunk(page, a.layer, 1, vh) + (size_t)off * hd);
 #pragma unroll

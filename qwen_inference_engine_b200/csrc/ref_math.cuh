@@ -36,7 +36,7 @@ __device__ __forceinline__ float head_tree_sum(float (&v)[NP][2]) {
 // q/k-norm of one head held in registers (in place, values become the bf16-rounded
 // results as floats): qk_norm.cu:46-78.
 template <int NP>
-__device__ __forceinline__ void head_norm(float (&x)[NP][2], const bf16* __restrict__ w, int lane) {
+__device__ __forceinline__ void head_norm(float (&x)[NP][2], const bf16* __restrict__ w, int lane, float eps = 1e-04f) {
   float sq[NP][2];
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
@@ -44,7 +44,7 @@ __device__ __forceinline__ void head_norm(float (&x)[NP][2], const bf16* __restr
     sq[p][1] = __fmul_rn(x[p][1], x[p][1]);
   }
   float tot = head_tree_sum<NP>(sq);
-  float rms = __fsqrt_rn(__fadd_rn(__fdiv_rn(tot, (float)(64 * NP)), 1e-04f));
+  float rms = __fsqrt_rn(__fadd_rn(__fdiv_rn(tot, (float)(64 * NP)), eps));
   rms = __shfl_sync(0xffffffffu, rms, 0);
 #pragma unroll
   for (int p = 0; p < NP; ++p) {
@@ -66,6 +66,47 @@ __device__ __forceinline__ void head_rope(float (&x)[NP][2], const float* __rest
     float v2 = __fmaf_rn(c, x1, __fmul_rn(x0, s));
     x[p][0] = bf2f(f2bf(v1));
     x[p][1] = bf2f(f2bf(v2));
+  }
+}
+
+// "HF-correct" RoPE (transformers' rotate_half; Qwen2.5 / Qwen3 checkpoints): element j of a head
+// pairs with j + hd/2 and both use table column j.  Lane l holds elements 64p + 2l, 64p + 2l + 1: for hd = 128 the
+// partner (+64) is the same lane's p = 1 value; for hd = 64 the partner (+32) lives in lane l ^ 16, same slot.
+template <int NP>
+__device__ __forceinline__ void head_rope_half(float (&x)[NP][2], const float* __restrict__ cos_row,
+                                               const float* __restrict__ sin_row, int lane) {
+  if (NP == 1) {
+    const bool hi = lane >= 16;  // this lane holds elements of the second half
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const int j = (2 * lane + s) & 31;  // table column of this element's pair
+      const float c = cos_row[j], sn = sin_row[j];
+      const float mine = x[0][s], other = __shfl_xor_sync(0xffffffffu, x[0][s], 16);
+      // first half: x0*c - x1*s ; second half: x1*c + x0*s  (x0 = first-half element, x1 = its partner)
+      const float v = hi ? __fmaf_rn(c, mine, __fmul_rn(other, sn)) : __fmaf_rn(mine, c, -__fmul_rn(other, sn));
+      x[0][s] = bf2f(f2bf(v));
+    }
+  } else {
+#pragma unroll
+    for (int p = 0; p < NP / 2; ++p)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int j = 64 * p + 2 * lane + s;
+        const float c = cos_row[j], sn = sin_row[j];
+        const float x0 = x[p][s], x1 = x[p + NP / 2][s];
+        x[p][s] = bf2f(f2bf(__fmaf_rn(x0, c, -__fmul_rn(x1, sn))));
+        x[p + NP / 2][s] = bf2f(f2bf(__fmaf_rn(c, x1, __fmul_rn(x0, sn))));
+      }
+  }
+}
+// projection bias (Qwen2.5): y = bf16(y + b) on the rounded projection output
+template <int NP>
+__device__ __forceinline__ void head_add_bias(float (&x)[NP][2], const bf16* __restrict__ b, int lane) {
+#pragma unroll
+  for (int p = 0; p < NP; ++p) {
+    const uint32_t bp = *reinterpret_cast<const uint32_t*>(b + 64 * p + 2 * lane);
+    x[p][0] = bf2f(f2bf(__fadd_rn(x[p][0], lo2f(bp))));
+    x[p][1] = bf2f(f2bf(__fadd_rn(x[p][1], hi2f(bp))));
   }
 }
 

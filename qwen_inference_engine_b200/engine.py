@@ -84,7 +84,7 @@ class Engine:
     def __init__(self, meta_path=None, weights_path=None, *, synthetic=None, seed=1234, device=0,
                  page_size=16, kv_bytes=0, max_pages=0, max_seqs=64, max_batch_tokens=256,
                  context=REF_CONTEXT, use_graph=True, head_dim_hint=0, numerics="reference_order",
-                 tp_rank=0, tp_size=1):
+                 tp_rank=0, tp_size=1, semantics="reference", rms_eps=0.0):
         L = _lib.lib()
         o = EngineOpts()
         L.qie_engine_opts_default(C.byref(o))
@@ -93,6 +93,7 @@ class Engine:
         o.use_graph, o.head_dim_hint = int(use_graph), head_dim_hint
         o.numerics = {"reference_order": 0, "fast": 1}[numerics]
         o.tp_rank, o.tp_size = tp_rank, tp_size
+        o.semantics, o.rms_eps = {"reference": 0, "hf": 1}[semantics], rms_eps
         self.numerics = numerics
         h = C.c_void_p()
         if synthetic is not None:

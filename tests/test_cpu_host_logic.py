@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     out = subprocess.check_output(["nm", "-D", "--defined-only", q.LIB_PATH], text=True)
     exported = set(re.findall(r" T (qie_\w+)", out))
     assert set(names) <= exported
-    assert lib.qie_abi_version() == 4
+    assert lib.qie_abi_version() == 5
 
 
 def test_header_cites_reference_interfaces():
