@@ -862,7 +862,7 @@ cudaError_t launch_sample_topk(const bf16* logits, int* out_tokens, int n_rows, 
 
 // ------------------------------------------------------------------ repetition penalty
 // apply_repetition_penalty_kernel is declared by the reference (include/layers_include.cuh:33) and never defined; the
-// conventional semantics are implemented (see oracle/qie_oracle.c orc_repetition_penalty): every DISTINCT token id of
+// conventional semantics (CTRL / HF RepetitionPenaltyLogitsProcessor) are implemented: every DISTINCT token id of
 // a row's context has its logit divided (positive) or multiplied (otherwise) by the penalty.  Row r's context is
 // ctx[ctx_row[r] * ctx_stride + 0 .. ctx_len[r]) (ctx_row == nullptr: row r, ctx_len == nullptr: fixed_len).
 // One thread per context position; only the first occurrence of a token applies, so no logit is written twice.
