@@ -684,6 +684,29 @@ __device__ __forceinline__ void gemm_inner(const MegaArgs& a, const Phase& p, ui
     // epilogue: c0,c1 -> (token 16m + g, n = row0 + 2c + {0,1}); c2,c3 -> token 16m + g + 8
     const int n = row0 + c * 2;
     if (n >= p.rows[seg]) continue;  // rows are even everywhere (checked by the launcher)
+    if (TWW >= 2 && p.kind != PH_LMHEAD) {
+      // The epilogue of a layer phase runs ONCE per layer per warp, i.e. always out of a cold instruction cache (the
+      // step walks ~8k instructions per layer), and cold straight-line code costs ~10 cycles per instruction: the
+      // 8-fold unrolled SiLU / residual epilogue (8 x ~150 instructions) took 6 us per layer at batch 64 -- longer
+      // than the phase's HMMAs.  The accumulators are parked in local memory (L1) and ONE copy of the epilogue code
+      // loops over the (tile, half) pairs.
+      float ev[TWW][8];
+#pragma unroll
+      for (int m = 0; m < TWW; ++m)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ev[m][i] = acc[m][i];
+          ev[m][4 + i] = acc2[m][i];
+        }
+#pragma unroll 1
+      for (int mm = 0; mm < 2 * TWW; ++mm) {
+        const int m = mm >> 1, hr = mm & 1;
+        const int tok = (m0 + m) * 16 + g + hr * 8;
+        if (tok >= a.B) continue;
+        epilogue_store<MT>(a, p, seg, tok, n, ev[m][hr * 2], ev[m][hr * 2 + 1], ev[m][4 + hr * 2], ev[m][4 + hr * 2 + 1], res_old);
+      }
+      continue;
+    }
 #pragma unroll
     for (int m = 0; m < TWW; ++m)
 #pragma unroll
