@@ -790,6 +790,8 @@ __device__ __forceinline__ void gemm_ts(const MegaArgs& a, const Phase& p, uint3
       if (stream) {
         cp_async_wait<TS_STAGES - 2>();  // this thread's part of chunk ch has landed
         bar_consumers();                 // ... everybody's has, and everybody is done with chunk ch - 1
+        // measured: issuing these ~4 cp.async per thread costs ~990 cycles per chunk (35 per LDGSTS) -- as much as the
+        // chunk's HMMAs; a TMA box per chunk (as the weights use) is the fix that is still open
         a_chunk_load(ch + TS_STAGES - 1);  // into the stage chunk ch - 1 used
       }
       if (has) {
