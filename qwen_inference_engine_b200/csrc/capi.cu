@@ -399,7 +399,7 @@ static void engine_free(qie_engine* e) {
                  e->sampled_d, e->rowstep_d, e->x, e->xn, e->q, e->k, e->v, e->att, e->h, e->logits, e->qkv,
                  e->gemm_ws, e->attn_ws_o, e->attn_ws_ml, e->gemm_counters, e->mega_layers_d, e->mega_cand_d,
                  e->mega_bar_d, e->mega_prof_d, e->mega_wmaps_d[0], e->mega_wmaps_d[1], e->tp_buf, e->tp_cand, e->tp_xbuf, e->x2,
-                 e->mega_wmaps_tp_d[0], e->mega_wmaps_tp_d[1]};
+                 e->mega_wmaps_tp_d[0], e->mega_wmaps_tp_d[1], e->mega_kvmap_d};
   for (int r = 0; r < MEGA_MAX_TP; ++r)
     if (e->tp_peer_xbuf[r] && e->tp_peer_xbuf[r] != e->tp_xbuf) cudaIpcCloseMemHandle(e->tp_peer_xbuf[r]);
   tp_comm_destroy(&e->tp);
@@ -599,6 +599,18 @@ static int engine_finish_setup(qie_engine* e) {
       CU(cudaMalloc(&e->mega_cand_d, (size_t)e->num_sms * 64 * sizeof(MegaCand)));
       CU(cudaMalloc(&e->mega_bar_d, 4096));  // grid-barrier counters (8 shards on separate lines)
       CU(cudaMalloc(&e->mega_prof_d, (size_t)decode_mega_prof_slots(c.layers) * sizeof(unsigned long long)));
+      {
+        // K/V rows for the attention phase's TMA stream (head_dim 64, pages of a power of two >= 8 slots; other
+        // geometries keep the cp.async tile loader)
+        const int psz = e->kv.page_size;
+        const unsigned long long rows = (unsigned long long)e->kv.n_pages * e->kv.n_layers * 2ull * e->kv.n_kv * psz;
+        TensorMap2D km;
+        if (c.head_dim == 64 && psz >= 8 && (psz & (psz - 1)) == 0 &&
+            make_tensor_map_kv(&km, e->kv.pool, rows, c.head_dim, std::min(psz, 64)) == cudaSuccess) {
+          CU(cudaMalloc(&e->mega_kvmap_d, sizeof(TensorMap2D)));
+          CU(cudaMemcpy(e->mega_kvmap_d, &km, sizeof(TensorMap2D), cudaMemcpyHostToDevice));
+        }
+      }
     }
   }
   if (o.numerics == QIE_NUMERICS_FAST) {

@@ -1805,6 +1805,465 @@ __device__ __noinline__ void attention_group_phase(const MegaArgs& a, int layer,
   }
 }
 
+// ---------------------------------------------------------------- attention: query-group tasks, K/V streamed by TMA
+// Same tasks and the same arithmetic as attention_group_phase (the reference's order, self_attension.cu:47-137), but
+// the cached rows arrive through the KV tensor map: one cp.async.bulk.tensor request per page chunk (16 positions =
+// 2 KB) instead of 128 cp.async instructions, written with the 128-byte swizzle that both readers want.
+//  * scores: groups of 64 positions; warp w owns ring slot w and the groups w, w + 7, ...: it waits for its slot,
+//    pulls TWO rows per lane (positions l and l + 32 of the group) into fp32 registers, re-arms the slot with its next
+//    group and evaluates the product tree of both rows for every head of the task.  One broadcast LDS.128 of q now
+//    feeds two positions (the loop was bound by those loads: 16 per head and position), the two trees give the
+//    scheduler independent work, and no CTA-wide barrier separates the groups.  q is stored in the order the tree
+//    consumes it: quad u = {q[2m], q[2m+1], q[2m+32], q[2m+33]}, m = bitrev4(u), so that partial sums meet as early as
+//    possible (depth-first, 4 live partial sums per row instead of 16).
+//    products of two bf16 values are exact in fp32, so  p[i] + p[i+32]  ==  fma(q[i+32], k[i+32], p[i])  bit for bit
+//    (one rounding of the same exact sum) unless a product underflows below 2^-126 -- |q k| < 1e-38 does not occur
+//    for normalised heads.
+//  * softmax: one warp per head; exponentials of block j + 2 are computed by all lanes while every lane walks the
+//    reference's sequential sum over block j (broadcast LDS.128, no divergence), so the FADD chain (4 cycles per
+//    position) is the only cost.
+//  * PV: 4 warps own heads w and w + 4 (two FFMA2 chains per lane, one LDS.32 + one widening per V row for both); a
+//    fifth warp keeps the V ring (7 slots of 64 positions) filled; mbarriers per slot, no CTA-wide barrier per tile.
+constexpr int AG = 64;              // cached positions per K slot (one slot per warp)
+constexpr int AG_BYTES = AG * 128;  // head_dim 64, bf16
+constexpr int AVG = 128;            // cached positions per V slot: the PV warps pay the slot hand-over half as often
+constexpr int AVG_BYTES = AVG * 128;
+constexpr int NVS = NW * AG / AVG;  // V slots in the same ring memory (3)
+constexpr int OFF_AKF = 656;        // NW mbarriers: K slot of warp w filled      (behind OFF_DBG)
+constexpr int OFF_AVF = 896;        // NW mbarriers: V slot s filled              (behind OFF_REL)
+constexpr int OFF_AVE = 952;        // NW mbarriers: V slot s read by all PV warps
+constexpr int PVW = 4;              // PV warps; warp PVW feeds the V ring
+constexpr int AQ = 20;              // q quads per head in shared memory: 8 (lanes with even pairs) + 1 pad + 8 (odd pairs) + 3 pad --
+                                    // the two quads a lane pair reads together are 144 bytes apart: different banks
+static_assert(OFF_DBG + 16 * 8 <= OFF_AKF && OFF_AKF + NW * 8 <= OFF_REL && OFF_REL + MAX_SLOTS * 4 <= OFF_AVF &&
+                  OFF_AVE + NW * 8 <= OFF_RMS,
+              "shared-memory header layout");
+
+// ring state kept across tasks and layers, in the shared-memory header (registers of the caller stay untouched):
+// u32 kuse[NW] fills of warp w's K slot so far | u32 vseq: V groups streamed so far (slot = vseq % NVS, fill number =
+// vseq / NVS) | u32 pre: the K groups of the CTA's first task were requested in front of the grid barrier
+constexpr int OFF_APIPE = OFF_AKF + NW * 8;
+static_assert(OFF_APIPE + (NW + 2) * 4 <= OFF_REL, "shared-memory header layout");
+
+struct AttnTmaLayout {
+  int q, knew, sums, score, ring, total;  // byte offsets from the activation area
+};
+__host__ __device__ inline AttnTmaLayout attn_tma_layout(int off_act, int hp, int max_kv_len) {
+  AttnTmaLayout l;
+  l.q = 0;
+  l.knew = hp * AQ * 16;
+  l.sums = l.knew + 2 * 64 * 2;
+  l.score = l.sums + 64;
+  l.ring = ((off_act + l.score + hp * attn_score_pitch(max_kv_len) * 4 + 1023) & ~1023) - off_act;
+  l.total = l.ring + NW * AG_BYTES;
+  return l;
+}
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* map, uint32_t mbar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(mbar), "r"(c0), "r"(c1)
+               : "memory");
+}
+
+// group g (cached positions GS g .. min(GS g + GS, ps) - 1) of (layer, K|V, kv head) -> ring slot at dst: lane i requests
+// box i (min(page, 64) slots of one page chunk); whole boxes are copied, rows behind ps are never read
+template <int GS>
+__device__ __forceinline__ void attn_issue_group(const MegaArgs& a, uint32_t dst, uint32_t mbar, const int* __restrict__ bt, int layer,
+                                                 int kv, int kvh, int g, int ps, int lane) {
+  const int psz = a.kv.page_size, sh = __ffs(psz) - 1;
+  const int br = min(psz, AG), bsh = min(sh, 6);  // rows per box (the tensor map's box: min(page, 64) slots)
+  const int nbox = (min(GS, ps - GS * g) + br - 1) >> bsh;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the slot was read / written through the generic proxy
+  if (lane == 0) mbar_expect_tx(mbar, (uint32_t)(nbox * br * 128));
+  if (lane < nbox) {
+    const int p0 = GS * g + lane * br;
+    const int page = __ldg(bt + (p0 >> sh));
+    const int row = (((page * a.kv.n_layers + layer) * 2 + kv) * a.kv.n_kv + kvh) * psz + (p0 & (psz - 1));
+    tma_load_2d(dst + (uint32_t)(lane * br * 128), a.kvmap, mbar, 0, row);
+  }
+}
+
+__host__ __device__ constexpr int trailing_ones(int u) { return (u & 1) ? ((u & 2) ? ((u & 4) ? ((u & 8) ? 4 : 3) : 2) : 1) : 0; }
+
+// Half of the product tree for TWO cached rows against one query head.  The last combine of the reference's tree
+// but one (stride 2 elements) adds the sums over the even and the odd element pairs, so a lane pair splits a row by
+// pair parity: lane `half` evaluates strides 32 ... 4 over its 16 pairs (8 q quads, tree order) for both rows and the
+// two lanes swap one partial sum each.  kw[c][0|1]: pairs 4c + half and 4c + 2 + half of the row, as fp32.
+// w: rolling window of four q quads, refilled four steps ahead (from the next head at the end).
+__device__ __forceinline__ void dot_half2(float4 (&w)[4], const float4* __restrict__ qc, const float4* __restrict__ qn,
+                                          const float2 (&ka)[8][2], const float2 (&kb)[8][2], float2& ya, float2& yb) {
+  float2 st0[3], st1[3], x0, x1;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int c = ((u & 1) << 1) | ((u & 2) >> 1), hl = u >> 2;  // pair bitrev4(u) + half and its partner 16 pairs on
+    const float4 q = w[u & 3];
+    w[u & 3] = u + 4 < 8 ? qc[u + 4] : qn[u + 4 - 8];
+    const float2 qa = make_float2(q.x, q.y), qb = make_float2(q.z, q.w);
+    x0 = __ffma2_rn(qb, ka[c + 4][hl], __fmul2_rn(qa, ka[c][hl]));  // stride 32 (exact products)
+    x1 = __ffma2_rn(qb, kb[c + 4][hl], __fmul2_rn(qa, kb[c][hl]));
+    const int t = trailing_ones(u);
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+      if (b < t) {  // strides 16, 8, 4 as soon as both operands exist
+        x0 = __fadd2_rn(st0[b], x0);
+        x1 = __fadd2_rn(st1[b], x1);
+      }
+    if (t < 3) {
+      st0[t] = x0;
+      st1[t] = x1;
+    }
+  }
+  ya = x0;
+  yb = x1;
+}
+
+__device__ __forceinline__ float2 bf2x_to_f2(uint32_t v) {  // ALU pipe only (PRMT / LOP3), see pv_tile
+  return make_float2(__uint_as_float(__byte_perm(v, 0u, 0x1044)), __uint_as_float(v & 0xffff0000u));
+}
+
+// PV over one whole ring slot (AVG = 128 cached rows of V, swizzled: word `lane` of row r sits at (lane << 2) ^ ((r & 7) << 4)) for
+// the NH heads of a warp: o[h] = fma(p[h][k], v[k], o[h]) for k ascending -- the reference's chain
+// (self_attension.cu:112-137), two IEEE fmas per packed FFMA2, lane l = output dims 2l, 2l + 1.  Fully unrolled: every
+// address is one of 8 row registers + an immediate, so a position costs one LDS.32, the widening (PRMT + LOP3) and NH
+// FFMA2 (+ a quarter of a broadcast LDS.128 per head); chunk c + 1 is loaded before the chains of chunk c.
+template <int NH>
+__device__ __forceinline__ void pv_group(const unsigned char* __restrict__ slot, const uint32_t (&xo)[8], const float* __restrict__ p0,
+                                         const float* __restrict__ p1, float2 (&o)[2]) {
+  const unsigned char* rowp[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) rowp[j] = slot + xo[j];
+  uint32_t v[2][8];
+  float4 pr[2][NH][2];
+  auto load = [&](int c) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[c & 1][j] = *reinterpret_cast<const uint32_t*>(rowp[j] + c * 1024 + j * 128);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      pr[c & 1][0][u] = *reinterpret_cast<const float4*>(p0 + 8 * c + 4 * u);
+      if (NH == 2) pr[c & 1][NH - 1][u] = *reinterpret_cast<const float4*>(p1 + 8 * c + 4 * u);
+    }
+  };
+  load(0);
+#pragma unroll
+  for (int c = 0; c < AVG / 8; ++c) {
+    if (c + 1 < AVG / 8) load(c + 1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float2 vf = bf2x_to_f2(v[c & 1][j]);
+#pragma unroll
+      for (int hh = 0; hh < NH; ++hh) {
+        const float4 p4 = pr[c & 1][hh][j >> 2];
+        const float pj = (j & 3) == 0 ? p4.x : ((j & 3) == 1 ? p4.y : ((j & 3) == 2 ? p4.z : p4.w));
+        o[hh] = __ffma2_rn(make_float2(pj, pj), vf, o[hh]);
+      }
+    }
+  }
+}
+// the rows of a partial last group, one at a time
+template <int NH>
+__device__ __forceinline__ void pv_tail(const unsigned char* __restrict__ slot, int lane, const float* __restrict__ p0,
+                                        const float* __restrict__ p1, int nrows, float2 (&o)[2]) {
+  for (int r = 0; r < nrows; ++r) {
+    const float2 vf = bf2x_to_f2(*reinterpret_cast<const uint32_t*>(slot + r * 128 + (uint32_t)((lane << 2) ^ ((r & 7) << 4))));
+    o[0] = __ffma2_rn(make_float2(p0[r], p0[r]), vf, o[0]);
+    if (NH == 2) o[1] = __ffma2_rn(make_float2(p1[r], p1[r]), vf, o[1]);
+  }
+}
+
+// requests for the K groups of the CTA's first attention task, issued behind the QKV GEMM and in front of the grid
+// barrier that publishes q/k/v (cached rows do not depend on this step)
+__device__ __noinline__ void attention_tma_prefetch(const MegaArgs& a, int layer, unsigned char* smem) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hsk = a.n_q / a.n_kv, hp = a.attn_hp, nparts = (hsk + hp - 1) / hp;
+  const int ntask = a.B * a.n_kv * nparts;
+  const int task = blockIdx.x;
+  if (task >= ntask) return;  // (pre stays 0: no task, nobody reads it)
+  const int bk = task / nparts, b = bk / a.n_kv, kvh = bk - b * a.n_kv;
+  const int ps = a.pos[b];
+  const AttnTmaLayout lay = attn_tma_layout(a.off_act, hp, a.max_kv_len);
+  const uint32_t ring = smem_u32(smem + a.off_act + lay.ring);
+  if (AG * warp < ps)
+    attn_issue_group<AG>(a, ring + warp * AG_BYTES, smem_u32(smem + OFF_AKF + warp * 8), a.block_table + (size_t)a.slot[b] * a.max_pages, layer,
+                     0, kvh, warp, ps, lane);
+  if (threadIdx.x == 0) reinterpret_cast<uint32_t*>(smem + OFF_APIPE)[NW + 1] = 1u;  // read behind the grid barrier's bar.sync
+}
+
+__device__ __noinline__ void attention_tma_phase(const MegaArgs& a, int layer, unsigned char* smem) {
+  constexpr int HD = 64, NP = 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hsk = a.n_q / a.n_kv, hp = a.attn_hp, nparts = (hsk + hp - 1) / hp;
+  const int Dq = a.n_q * HD, Dkv = a.n_kv * HD, QKV = Dq + 2 * Dkv;
+  const int ntask = a.B * a.n_kv * nparts;
+  const int SP = attn_score_pitch(a.max_kv_len);
+  const MegaLayer& w = reinterpret_cast<const MegaLayer*>(smem + OFF_LAYERS)[layer];
+  const AttnTmaLayout lay = attn_tma_layout(a.off_act, hp, a.max_kv_len);
+  unsigned char* area = smem + a.off_act;
+  float* q_s = reinterpret_cast<float*>(area + lay.q);  // [hp][AQ quads], tree order
+  bf16* knew = reinterpret_cast<bf16*>(area + lay.knew);
+  bf16* vnew = knew + HD;
+  float* score = reinterpret_cast<float*>(area + lay.score);  // [hp][SP]
+  unsigned char* ringp = area + lay.ring;
+  const uint32_t ring = smem_u32(ringp);
+  const uint32_t kfull = smem_u32(smem + OFF_AKF + warp * 8);
+  const uint32_t vfull = smem_u32(smem + OFF_AVF), vempty = smem_u32(smem + OFF_AVE);
+
+  volatile uint32_t* pipe = reinterpret_cast<volatile uint32_t*>(smem + OFF_APIPE);
+  uint32_t kuse = pipe[warp], vseq = pipe[NW];
+  bool pre = pipe[NW + 1] != 0u;
+
+  unsigned long long* dbg = reinterpret_cast<unsigned long long*>(smem + OFF_DBG);
+  const bool timed = a.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  for (int task = blockIdx.x; task < ntask; task += gridDim.x) {
+    long long tq = timed ? clock64() : 0;
+    auto lap = [&](int slot) {
+      if (timed) {
+        const long long t = clock64();
+        dbg[slot] += (unsigned long long)(t - tq);
+        tq = t;
+      }
+    };
+    const int bk = task / nparts, part = task - bk * nparts;
+    const int b = bk / a.n_kv, kvh = bk - b * a.n_kv, h0 = kvh * hsk + part * hp;
+    const int hs = min(hp, hsk - part * hp);  // query heads of this task
+    const bool writer = part == 0;           // one task per (row, kv head) stores the new K / V row
+    const int ps = a.pos[b];                 // cached positions 0..ps-1, the new one is ps
+    const int* bt = a.block_table + (size_t)a.slot[b] * a.max_pages;
+    const int ng = (ps + AG - 1) / AG;       // groups with cached rows
+    const int nsg = ps / AG + 1;             // score groups (the last one holds position ps)
+    if (!pre && AG * warp < ps) attn_issue_group<AG>(a, ring + warp * AG_BYTES, kfull, bt, layer, 0, kvh, warp, ps, lane);
+    pre = false;
+    // q/k-norm + RoPE of the group's query heads and of the new K row; KV store of the new position.  Rows
+    // warp and warp + NW: both loads are in flight before the first norm
+    {
+      const bf16* row = a.qkv + (size_t)b * QKV;
+      const float* cos_row = a.cos_t + (size_t)ps * 32 * NP;
+      const float* sin_row = a.sin_t + (size_t)ps * 32 * NP;
+      const int psz = a.kv.page_size;
+      const int new_page = bt[ps / psz], new_off = ps % psz;
+      float v[2][NP][2];
+      auto src_of = [&](int r) { return r < hs ? row + (size_t)(h0 + r) * HD : (r == hs ? row + Dq + (size_t)kvh * HD : row + Dq + Dkv + (size_t)kvh * HD); };
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+        if (warp + NW * t < hs + 2) head_load_cg<NP>(v[t], src_of(warp + NW * t), lane);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int r = warp + NW * t;
+        if (r < hs) {
+          if (w.q_norm) head_norm<NP>(v[t], w.q_norm, lane);
+          head_rope<NP>(v[t], cos_row, sin_row, lane);
+          // pair `lane` = elements 2 lane, 2 lane + 1: first (lane < 16) or second half of quad bitrev4(lane & 15)
+          const int u = (int)(__brev((unsigned)(lane & 15)) >> 28);
+          *reinterpret_cast<float2*>(q_s + r * (4 * AQ) + 4 * (u + (u >> 3)) + 2 * (lane >> 4)) = make_float2(v[t][0][0], v[t][0][1]);
+        } else if (r == hs) {
+          if (w.k_norm) head_norm<NP>(v[t], w.k_norm, lane);
+          head_rope<NP>(v[t], cos_row, sin_row, lane);
+          head_store<NP>(v[t], knew, lane);
+          if (writer) head_store<NP>(v[t], a.kv.chunk(new_page, layer, 0, kvh) + (size_t)new_off * HD, lane);
+        } else if (r == hs + 1) {
+          head_store<NP>(v[t], vnew, lane);
+          if (writer) head_store<NP>(v[t], a.kv.chunk(new_page, layer, 1, kvh) + (size_t)new_off * HD, lane);
+        }
+      }
+    }
+    bar_consumers();  // q_s / knew / vnew visible
+    lap(10);
+
+    // ---- scores (self_attension.cu:47-74)
+    {
+      const int half = lane & 1, tp = lane >> 1;
+      const float4* q4 = reinterpret_cast<const float4*>(q_s) + 9 * half;  // this lane's 8 quads of every head
+      // (measured dead end: dealing the groups 8 ways with a double share for warp 3, which has its scheduler almost
+      // to itself -- 33 k -> 38 k cycles: a single warp is bound by the latency of its own trees, not by the FP pipe)
+      constexpr int gstep = NW;
+      for (int g = warp; g < nsg; g += gstep) {
+        if (g < ng) {
+          const long long tw0 = timed ? clock64() : 0;
+          mbar_wait(kfull, kuse & 1u);
+          ++kuse;
+          if (timed) dbg[14] += (unsigned long long)(clock64() - tw0);
+        }
+#pragma unroll 1
+        for (int sp = 0; sp < 2; ++sp) {  // 32 positions per pass: lane pair tp owns rows 32 sp + tp and 32 sp + 16 + tp
+          float2 kw[2][8][2];
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            const int r = 32 * sp + 16 * p + tp, k = AG * g + r;
+            const bool cached = k < ps;  // k == ps: the new row; k > ps: nothing (any readable address)
+            const unsigned char* rowp = cached ? ringp + warp * AG_BYTES + r * 128 : reinterpret_cast<const unsigned char*>(knew);
+            const int swz = cached ? (r & 7) : 0;
+#pragma unroll
+            for (int c = 0; c < HD / 8; ++c) {
+              const uint4 t = *reinterpret_cast<const uint4*>(rowp + ((c ^ swz) << 4));
+              kw[p][c][0] = bf2x_to_f2(half ? t.y : t.x);
+              kw[p][c][1] = bf2x_to_f2(half ? t.w : t.z);
+            }
+          }
+          if (sp == 1) {  // the slot has been read: re-arm it with this warp's next group
+            __syncwarp();
+            if (g + gstep < ng) attn_issue_group<AG>(a, ring + warp * AG_BYTES, kfull, bt, layer, 0, kvh, g + gstep, ps, lane);
+          }
+          float4 wq[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) wq[u] = q4[u];
+          const int kmine = AG * g + 32 * sp + 16 * half + tp;  // the row this lane finishes
+          for (int i = 0; i < hs; ++i) {
+            float2 ya, yb;
+            dot_half2(wq, q4 + AQ * i, q4 + AQ * (i + 1 < hs ? i + 1 : i), kw[0], kw[1], ya, yb);
+            // stride 2: sum over the even pairs + sum over the odd pairs (the other lane's half), then stride 1
+            const float2 give = half ? ya : yb, keep = half ? yb : ya;
+            const float2 got = make_float2(__shfl_xor_sync(0xffffffffu, give.x, 1), __shfl_xor_sync(0xffffffffu, give.y, 1));
+            const float2 d = __fadd2_rn(keep, got);
+            // dot / sqrtf(64): the divisor is exactly 8, and x / 8 == x * 0.125 bit for bit
+            if (kmine <= ps) score[i * SP + kmine] = __fmul_rn(__fadd_rn(d.x, d.y), 0.125f);
+          }
+        }
+      }
+    }
+    bar_consumers();  // all scores visible, every K slot is free
+    lap(11);
+
+    // ---- V ring: the first NVS groups (the PV warps free a slot per group from then on)
+    const int nvg = (ps + AVG - 1) / AVG;  // V groups
+    const uint32_t vs0 = vseq % NVS, vpar0 = (vseq / NVS) & 1u;
+    if (warp == PVW) {
+      uint32_t s = vs0;
+      for (int j = 0; j < min(nvg, NVS); ++j) {
+        attn_issue_group<AVG>(a, ring + s * AVG_BYTES, vfull + s * 8, bt, layer, 1, kvh, j, ps, lane);
+        if (++s == NVS) s = 0;
+      }
+    }
+
+    // ---- softmax (self_attension.cu:94-107): one warp per head
+    for (int i = warp; i < hs; i += NW) {
+      float* s = score + i * SP;
+      const int n = ps + 1;
+      float m = -1e9f;
+      {
+        int k = 4 * lane;
+        for (; k + 3 < n; k += 128) {
+          const float4 t = *reinterpret_cast<const float4*>(s + k);
+          m = fmaxf(fmaxf(m, fmaxf(t.x, t.y)), fmaxf(t.z, t.w));
+        }
+        for (; k < n; ++k) m = fmaxf(m, s[k]);  // (at most one lane has a partial quad)
+      }
+      m = warp_max(m);
+      // exponentials two blocks of 32 ahead of the sequential sum; every lane walks the same sum
+      const int nfull = n >> 5;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int k = 32 * j + lane;
+        if (k < n) s[k] = expf(__fsub_rn(s[k], m));
+      }
+      __syncwarp();
+      float sum = 0.f;
+      float4 cur[4], nxt[4];
+      auto chain16 = [&](const float4 (&v)[4]) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          sum = __fadd_rn(sum, v[u].x);
+          sum = __fadd_rn(sum, v[u].y);
+          sum = __fadd_rn(sum, v[u].z);
+          sum = __fadd_rn(sum, v[u].w);
+        }
+      };
+#pragma unroll
+      for (int u = 0; u < 4; ++u) cur[u] = *reinterpret_cast<const float4*>(s + 4 * u);
+      for (int j = 0; j < nfull; ++j) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) nxt[u] = *reinterpret_cast<const float4*>(s + 32 * j + 16 + 4 * u);
+        // (no branch around the exponential: its dependent chain is scheduled between the FADDs of the sum)
+        const int kn = 32 * (j + 2) + lane;
+        float en = expf(__fsub_rn(s[min(kn, n - 1)], m));
+        asm volatile("" : "+f"(en));  // computed here, for every lane (the compiler would sink it into the conditional store)
+        chain16(cur);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) cur[u] = *reinterpret_cast<const float4*>(s + 32 * (j + 1) + 4 * u);  // (pitch covers one block behind n)
+        chain16(nxt);
+        if (kn < n) s[kn] = en;
+        __syncwarp();
+      }
+      for (int k = 32 * nfull; k < n; ++k) sum = __fadd_rn(sum, s[k]);
+      for (int k = lane; k < n; k += 32) s[k] = __fdiv_rn(s[k], sum);
+    }
+    bar_consumers();  // probabilities visible
+    lap(12);
+
+    // ---- PV (self_attension.cu:112-137)
+    if (warp < PVW) {
+      const int nh = warp < hs ? (warp + PVW < hs ? 2 : 1) : 0;  // heads warp and warp + PVW
+      float2 o[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      uint32_t ls = vs0, lpar = vpar0;  // slot / fill parity of the current group
+      uint32_t xo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xo[j] = (uint32_t)((lane << 2) ^ (j << 4));  // word `lane` of a swizzled row r: r & 7 == j
+      const float* sb = score + warp * SP;
+      const int hstride = PVW * SP;
+      // every PV warp walks all V groups (also a warp without a head: the "drained" barrier counts PVW arrivals)
+      const float* p0 = sb;
+      const float* p1 = sb + hstride;
+      for (int j = 0; j < nvg; ++j) {
+        {
+          const long long tw0 = timed ? clock64() : 0;
+          mbar_wait(vfull + ls * 8, lpar);
+          if (timed) dbg[15] += (unsigned long long)(clock64() - tw0);
+        }
+        const unsigned char* slot = ringp + ls * AVG_BYTES;
+        const int nrows = min(AVG, ps - AVG * j);
+        if (nrows == AVG) {
+          if (nh == 2)
+            pv_group<2>(slot, xo, p0, p1, o);
+          else if (nh == 1)
+            pv_group<1>(slot, xo, p0, p1, o);
+        } else {
+          if (nh == 2)
+            pv_tail<2>(slot, lane, p0, p1, nrows, o);
+          else if (nh == 1)
+            pv_tail<1>(slot, lane, p0, p1, nrows, o);
+        }
+        p0 += AVG;
+        p1 += AVG;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(vempty + ls * 8);
+        if (++ls == NVS) {
+          ls = 0;
+          lpar ^= 1u;
+        }
+      }
+      {
+        const uint32_t v1 = *reinterpret_cast<const uint32_t*>(vnew + 2 * lane);  // the new position: V of this step's projection
+        const float2 vf = make_float2(lo2f(v1), hi2f(v1));
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh)
+          if (hh < nh) {
+            const float pj = sb[hh * hstride + ps];
+            o[hh] = __ffma2_rn(make_float2(pj, pj), vf, o[hh]);
+            *reinterpret_cast<uint32_t*>(a.att + (size_t)b * Dq + (size_t)(h0 + warp + PVW * hh) * HD + 2 * lane) = pack2(f2bf(o[hh].x), f2bf(o[hh].y));
+          }
+      }
+    } else if (warp == PVW) {
+      // V groups NVS.. : a slot is refilled when the PV warps have read its previous group
+      // (fill number f of a slot waits for the phase f - 1 of its "drained" barrier: one phase per group read)
+      uint32_t s = vs0, fpar = vpar0 ^ 1u;  // group NVS: the slot of group 0, one fill later
+      for (int j = NVS; j < nvg; ++j) {
+        mbar_wait(vempty + s * 8, fpar ^ 1u);
+        attn_issue_group<AVG>(a, ring + s * AVG_BYTES, vfull + s * 8, bt, layer, 1, kvh, j, ps, lane);
+        if (++s == NVS) {
+          s = 0;
+          fpar ^= 1u;
+        }
+      }
+    }
+    vseq += (uint32_t)nvg;
+    bar_consumers();  // shared memory is reused by the next task / phase
+    lap(13);
+  }
+  if (lane == 0) pipe[warp] = kuse;
+  if (threadIdx.x == 0) {
+    pipe[NW] = vseq;
+    pipe[NW + 1] = 0u;
+  }
+}
+
 // ---------------------------------------------------------------- the kernel
 template <int NP, int MT, bool FAST>
 __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __grid_constant__ MegaArgs a) {
@@ -1820,9 +2279,15 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
       mbar_init(smem_base + OFF_FULL + s * 8, 1);
       mbar_init(smem_base + OFF_EMPTY + s * 8, 1);
     }
+    for (int s = 0; s < NW; ++s) {  // K/V rings of the attention phase (attention_tma_phase)
+      mbar_init(smem_base + OFF_AKF + s * 8, 1);
+      mbar_init(smem_base + OFF_AVF + s * 8, 1);
+      mbar_init(smem_base + OFF_AVE + s * 8, PVW);
+    }
     *reinterpret_cast<volatile uint32_t*>(smem + OFF_ISSUED) = 0u;
     for (int i = 0; i < 16; ++i) reinterpret_cast<unsigned long long*>(smem + OFF_DBG)[i] = 0ull;
     for (int i = 0; i < MAX_SLOTS; ++i) reinterpret_cast<uint32_t*>(smem + OFF_REL)[i] = 0u;
+    for (int i = 0; i < NW + 2; ++i) reinterpret_cast<uint32_t*>(smem + OFF_APIPE)[i] = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -1880,7 +2345,9 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
     const bf16* a_src = nullptr;
     if (kind == PH_O) {
       // ---- attention, then O + residual
-      if (NP == 1 && a.attn_group)
+      if (NP == 1 && a.attn_tma)
+        attention_tma_phase(a, l, smem);
+      else if (NP == 1 && a.attn_group)
         attention_group_phase(a, l, smem);
       else
         attention_phase<NP>(a, l, smem, 1);
@@ -1973,6 +2440,10 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
       done = true;
     }
     if (!done) gemm_phase<MT>(a, p, smem_base, ring_pos, a_src, best, smem + OFF_DBG);
+    if (NP == 1 && kind == PH_QKV && a.attn_tma) {
+      bar_consumers();  // the activation rows of the QKV GEMM are dead: the K ring takes their place
+      attention_tma_prefetch(a, l, smem);
+    }
     stamp();
     if (kind == PH_LMHEAD) {
       // candidates: lanes (g, c) of a warp hold tokens 16m + g (+8); reduce over c, then over warps
@@ -2138,6 +2609,7 @@ bool mega_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int ma
                                  2 * VT * hd * 2 + kstg * (hd * 2 + 16) + 2 * hd * 2 + hd * 4 + 64;
     attn_off = kstg > 0 ? ((res_h + 127) & ~127) : 0;  // staged attention areas live behind the resident rows
     act = std::max(act_gemm, attn + attn_off);
+    if (group) act = std::max(act, attn_tma_layout(off_act, hs, max_kv_len).total);  // K/V rings fed by TMA (attention_tma_phase)
     off_red = off_act + ((act + 127) & ~127);     // fast numerics: split-K partial sums [FAST_U][NW][32][8] fp32
     off_ring = (off_red + red + 1023) & ~1023;    // swizzled TMA tiles: 1024-byte aligned slots
     const int budget = 227 * 1024 - off_ring;
@@ -2199,11 +2671,16 @@ cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st) {
   a.off_red = g.off_red;
   a.attn_group = g.group;
   a.attn_hp = 1;
+  a.attn_tma = 0;
   if (g.group) {  // heads per attention task: the smallest part size whose tasks fit one wave
     const int hsk = a.n_q / a.n_kv;
     int hp = 1;
     while (hp < hsk && a.B * a.n_kv * ((hsk + hp - 1) / hp) > num_sms) ++hp;
     a.attn_hp = hp;
+    // K/V streamed by TMA: needs the pool's tensor map (head_dim 64, pages of >= 8 slots) and <= 2 heads per PV warp
+    a.attn_tma = a.kvmap != nullptr && a.kv.page_size >= 8 && hp <= 2 * PVW;
+    static const bool tma_env = [] { const char* v = getenv("QIE_MEGA_ATMA"); return !(v && v[0] == '0'); }();  // A/B knob
+    if (!tma_env) a.attn_tma = 0;
   }
   a.dist_norm = a.B > 16 && a.B <= num_sms && a.xn != nullptr;
   a.mtt = g.mt == 0 ? 1 : g.mt;

@@ -547,6 +547,7 @@ static cudaError_t forward_decode_mega_rows(qie_engine* e, int row0, int n, int 
   const int tset = mega_tile_set(e, n, max_kv_len);
   a.wmaps = e->mega_wmaps_d[tset];
   a.KC = e->mega_kc[tset];
+  a.kvmap = e->mega_kvmap_d;
   a.embed = e->embed;
   a.final_norm = e->final_norm;
   a.lm_head = e->lm_head;

@@ -753,6 +753,24 @@ cudaError_t make_tensor_map_w3d(TensorMap2D* out, const bf16* base, int rows, in
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// KV pool [page][layer][k|v][head][slot][64] bf16 viewed as rows of 128 bytes (one head of one cached position).
+// One TMA request moves box_rows consecutive slots of a (page, layer, K|V, head) chunk into shared memory; the
+// 128-byte swizzle puts 16-byte chunk c of row r at chunk c ^ (r & 7), so that threads reading one row each
+// (attention scores) and a warp reading one row together (PV) are both free of bank conflicts.
+cudaError_t make_tensor_map_kv(TensorMap2D* out, const bf16* pool, unsigned long long rows, int hd, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return cudaErrorNotSupported;
+  if (hd != 64 || box_rows < 1 || box_rows > 256 || rows == 0 || rows >= (1ull << 31)) return cudaErrorInvalidValue;
+  cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)pool, dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 template <int BN>
 static cudaError_t launch_bn(const TcGemm& t, const TcArgs& g, int token_tiles, cudaStream_t st) {
   constexpr int STAGE_BYTES = BM * BK * 2 + BN * BK * 2;

@@ -138,6 +138,8 @@ struct TensorMap2D {
 };
 cudaError_t make_tensor_map_2d(TensorMap2D* out, const bf16* base, int rows, int K, int box_rows);
 cudaError_t make_tensor_map_w3d(TensorMap2D* out, const bf16* base, int rows, int K, int kc, int ld = 0);  // ld: row stride in elements (0 = K)
+// KV pool as a 2-D tensor {head_dim 64, every (page, layer, K|V, head, slot) row}: box = box_rows slots x 128 bytes, 128-byte swizzle
+cudaError_t make_tensor_map_kv(TensorMap2D* out, const bf16* pool, unsigned long long rows, int hd, int box_rows);
 int tc_token_tile(int M);
 struct TcGemm {
   const TensorMap2D* w[3];  // weight maps, box rows = 128
@@ -209,6 +211,7 @@ struct MegaArgs {
   int H, I, L, n_q, n_kv, hd, V;
   const MegaLayer* layers;  // device array [L]
   const TensorMap2D* wmaps; // device array [7*L + 1]: q k v o gate up down per layer, then lm_head (make_tensor_map_w3d)
+  const TensorMap2D* kvmap; // device: the KV pool as rows of one head (make_tensor_map_kv), nullptr = no TMA streaming of K/V
   const bf16 *embed, *final_norm, *lm_head;
   const float *cos_t, *sin_t;
   int B;  // decode rows, one token per sequence
@@ -247,7 +250,7 @@ struct MegaArgs {
   int ph_nu[5];  // units per round (NW, or NW / token tiles when the tiles of a unit are spread over warps)
   int ph_ts[5], ph_G[5], mtt;  // tile-split phases: CTA c owns token tile c % mtt and the units c / mtt + i * G (gemm_ts)
   int ph_q[5], ph_r[5], ph_nch[5], ph_adv_slot[5][2], ph_adv_par[5][2], ph_round_slot[5], ph_round_par[5];
-  int n_slots, slot_bytes, act_bytes, off_act, off_ring, stream_down, attn_kstg, attn_off, off_red, attn_group, attn_hp;
+  int n_slots, slot_bytes, act_bytes, off_act, off_ring, stream_down, attn_kstg, attn_off, off_red, attn_group, attn_hp, attn_tma;
 };
 // max rows the persistent kernel accepts for this model shape (0 = shape unsupported)
 int decode_mega_kc(int H, int big);  // k elements per weight tile (box depth of the weight tensor maps); big: batches <= 8
