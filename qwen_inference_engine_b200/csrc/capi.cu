@@ -399,7 +399,7 @@ static void engine_free(qie_engine* e) {
                  e->sampled_d, e->rowstep_d, e->x, e->xn, e->q, e->k, e->v, e->att, e->h, e->logits, e->qkv,
                  e->gemm_ws, e->attn_ws_o, e->attn_ws_ml, e->gemm_counters, e->mega_layers_d, e->mega_cand_d,
                  e->mega_bar_d, e->mega_prof_d, e->mega_wmaps_d[0], e->mega_wmaps_d[1], e->tp_buf, e->tp_cand, e->tp_xbuf, e->x2,
-                 e->mega_wmaps_tp_d[0], e->mega_wmaps_tp_d[1], e->mega_kvmap_d};
+                 e->mega_wmaps_tp_d[0], e->mega_wmaps_tp_d[1], e->mega_kvmap_d, e->mega_hmap_d};
   for (int r = 0; r < MEGA_MAX_TP; ++r)
     if (e->tp_peer_xbuf[r] && e->tp_peer_xbuf[r] != e->tp_xbuf) cudaIpcCloseMemHandle(e->tp_peer_xbuf[r]);
   tp_comm_destroy(&e->tp);
@@ -599,6 +599,13 @@ static int engine_finish_setup(qie_engine* e) {
       CU(cudaMalloc(&e->mega_cand_d, (size_t)e->num_sms * 64 * sizeof(MegaCand)));
       CU(cudaMalloc(&e->mega_bar_d, 4096));  // grid-barrier counters (8 shards on separate lines)
       CU(cudaMalloc(&e->mega_prof_d, (size_t)decode_mega_prof_slots(c.layers) * sizeof(unsigned long long)));
+      if ((I % 64) == 0 && e->h) {  // down_proj operand rows for the tile-split phase (tile set 0: batches > 8)
+        TensorMap2D hm;
+        if (make_tensor_map_w3d(&hm, e->h, (int)R, (int)I, e->mega_kc[0], 0, 16) == cudaSuccess) {
+          CU(cudaMalloc(&e->mega_hmap_d, sizeof(TensorMap2D)));
+          CU(cudaMemcpy(e->mega_hmap_d, &hm, sizeof(TensorMap2D), cudaMemcpyHostToDevice));
+        }
+      }
       {
         // K/V rows for the attention phase's TMA stream (head_dim 64, pages of a power of two >= 8 slots; other
         // geometries keep the cp.async tile loader)

@@ -49,6 +49,9 @@ constexpr int MAX_LAYERS = 64;
 constexpr int OFF_FULL = 0, OFF_EMPTY = 256, OFF_ISSUED = 512, OFF_DBG = 528, OFF_REL = 768, OFF_RMS = 1024, OFF_CAND = 1280;  // OFF_DBG: 16 x u64 cycle counters; OFF_REL: u32 per slot
 constexpr int OFF_LAYERS = OFF_CAND + NW * MAX_ROWS * 8;                 // MegaLayer[MAX_LAYERS]
 constexpr int OFF_WNORM = OFF_LAYERS + MAX_LAYERS * (int)sizeof(MegaLayer);  // 2 x [H] bf16 norm weights
+constexpr int OFF_TSF = 944;    // 4 mbarriers: stage of the tile-split A stream filled (gemm_ts)
+constexpr int OFF_TSE = 976;    // 4 mbarriers: ... read by every warp that has a unit (count = units of this CTA, set at kernel start)
+constexpr int OFF_TSSEQ = 748;  // u32: chunks of that stream requested so far (stage = seq & 3, fill parity = (seq >> 2) & 1)
 static_assert(sizeof(MegaLayer) == 88, "MegaLayer layout");
 
 enum { PH_QKV = 0, PH_O = 1, PH_GATEUP = 2, PH_DOWN = 3, PH_LMHEAD = 4 };
@@ -430,12 +433,15 @@ struct Frags {
   uint32_t a[GS][MTT][4];  // MT == 0: [1] and [3] (token rows 8..15) stay zero
 };
 
-template <int MT, bool DUAL>
+// ASWZ (one 16-row token tile, GS == 4): the A operand is a TMA box [k-block of 64][16 rows][64] with the 128-byte
+// swizzle (the layout of the weight tiles) instead of padded rows.
+template <int MT, bool DUAL, bool ASWZ = false>
 __device__ __forceinline__ void mma_chunk(float (&acc)[MT == 0 ? 1 : MT][4], float (&acc2)[MT == 0 ? 1 : MT][4],
                                           uint32_t slot_addr, uint32_t a_addr, int AS, int up_off, int nk16, int B,
                                           int lane) {
   using F = Frags<MT, DUAL>;
   constexpr int MTT = F::MTT, GS = F::GS;
+  static_assert(!ASWZ || (MT == 1 && GS == 4), "swizzled A: one token tile per warp");
   // weight tile: [k-block of 64][row 0-7][64] bf16, 16-byte chunk c of row r stored at c ^ r;
   // ldmatrix lanes 0-7 -> rows @k, 8-15 -> rows @k+8 (x2); DUAL: lanes 16-31 -> the up tile
   const int br = lane & 7, bh = (lane >> 3) & 1;
@@ -444,8 +450,12 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[MT == 0 ? 1 : MT][4], flo
 #pragma unroll
   for (int s = 0; s < 4; ++s) boff[s] = (uint32_t)((((s << 1) + bh) ^ br) << 4);
   const bool row_valid = (lane >> 2) < B;
+  const int arow = (lane & 7) + ((lane >> 3) & 1) * 8;  // ldmatrix.x4: lanes 0-15 rows @k, 16-31 rows @k+8
   const uint32_t a0 = MT == 0 ? a_addr + (lane >> 2) * AS + (lane & 3) * 4
-                              : a_addr + ((lane & 7) + ((lane >> 3) & 1) * 8) * AS + (lane >> 4) * 16;
+                              : (ASWZ ? a_addr + arow * 128 : a_addr + arow * AS + (lane >> 4) * 16);
+  uint32_t aoff[4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s) aoff[s] = (uint32_t)((((s << 1) + (lane >> 4)) ^ (arow & 7)) << 4);
   auto load_step = [&](F& f, int s, int j) {  // fragments of k-step j -> slot s of f
     const uint32_t baddr = brow + (uint32_t)(j >> 2) * 1024u + boff[(GS == 4) ? s : (j & 3)];
     if (DUAL)
@@ -460,7 +470,10 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[MT == 0 ? 1 : MT][4], flo
           f.a[s][m][2] = lds32(a0 + j * 32 + 16);
         }
       } else {
-        ldmatrix_x4(f.a[s][m][0], f.a[s][m][1], f.a[s][m][2], f.a[s][m][3], a0 + m * 16 * AS + j * 32);
+        if (ASWZ)
+          ldmatrix_x4(f.a[s][m][0], f.a[s][m][1], f.a[s][m][2], f.a[s][m][3], a0 + (uint32_t)(j >> 2) * 2048u + aoff[s]);
+        else
+          ldmatrix_x4(f.a[s][m][0], f.a[s][m][1], f.a[s][m][2], f.a[s][m][3], a0 + m * 16 * AS + j * 32);
       }
     }
   };
@@ -748,7 +761,23 @@ __device__ __forceinline__ void gemm_ts(const MegaArgs& a, const Phase& p, uint3
   const int n_c = p.n_c, nch = p.nch;
   const int tok0 = p.tile * 16, nrows = min(16, a.B - tok0);
   RingPos rnd = base;
-  // A stream: piece i of a chunk is (row i / per, 16-byte column i % per); the threads from warp lw0 on walk their pieces
+  // A stream by TMA (a.hmap: h as {64, rows, K / 64} in boxes of 16 rows x KC, 128-byte swizzle): ONE request per chunk
+  // by one thread instead of ~4 cp.async per thread (measured: issuing those cost ~990 cycles per chunk, as much as
+  // the chunk's HMMAs); the stage is a [k-block][16 rows][64] tile like the weight tiles (mma_chunk ASWZ).
+  static_assert(TS_STAGES == 4, "stage = seq & 3");
+  const bool tma = stream && a.hmap != nullptr;
+  const uint32_t tsf = smem_base + OFF_TSF;
+  const uint32_t stage0 = (act + 1023u) & ~1023u, STB = 16u * (uint32_t)KC * 2u;
+  const bool issuer = threadIdx.x == (NW - 1) * 32;
+  uint32_t aseq = tma ? lds32_volatile(smem_base + OFF_TSSEQ) : 0u;  // written behind a barrier of the previous tile-split phase
+  auto a_issue = [&](int ch) {  // issuer thread: rows of this tile x [ch*KC, +KC) (zero-filled past K) -> stage (aseq + ch) & 3
+    if (ch < nch) {
+      const uint32_t st = (aseq + (uint32_t)ch) & 3u;
+      mbar_expect_tx(tsf + st * 8, STB);
+      tma_load_3d(stage0 + st * STB, a.hmap, tsf + st * 8, 0, tok0, ch * (KC / 64));
+    }
+  };
+  // A stream by cp.async: piece i of a chunk is (row i / per, 16-byte column i % per); the threads from warp lw0 on walk their pieces
   // incrementally (one division per chunk).  All consumer threads copy (lw0 = 0).
   int lw0 = 0;  // first loader warp of the current round
   auto a_chunk_load = [&](int ch) {  // rows of this tile x [ch*KC, +klen) -> stage ch % TS_STAGES (an empty group past the end)
@@ -780,14 +809,50 @@ __device__ __forceinline__ void gemm_ts(const MegaArgs& a, const Phase& p, uint3
       row0 = (u - p.ubeg[seg]) * p.upr;
     }
     float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}}, acc2[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+    // residual words of this lane's two outputs (O / down without tensor parallel): requested now, used in the epilogue
+    uint32_t res_old[2] = {0u, 0u};
+    const bool res_pre = has && a.tp_size <= 1 && (p.kind == PH_O || p.kind == PH_DOWN) && row0 + c * 2 < p.rows[seg];
+    if (res_pre) {
+#pragma unroll
+      for (int hr = 0; hr < 2; ++hr) {
+        const int tok = tok0 + g + hr * 8;
+        if (tok < a.B) res_old[hr] = __ldcg(reinterpret_cast<const uint32_t*>(a.x + (size_t)tok * a.H + row0 + c * 2));
+      }
+    }
     lw0 = 0;  // measured (B200, batch 64): leaving the copies to the warps without a unit is slower (20.0 vs 17.0 us per layer)
-    if (stream)
+    // ring mode (the CTA's units fit one round and leave the issuer's warp free -- the 0.5B / 1.5B shapes): no CTA
+    // barrier per chunk; the issuer runs ahead, a stage is re-armed when the nact warps with a unit have read it
+    // (fill f of a stage waits for phase f - 1 of its "read" barrier, whose count is nact: set at kernel start)
+    const bool ring_mode = tma && n_c <= NW - 1;
+    if (tma) {
+      if (issuer) {
+        // h was written by other SMs through the generic proxy (published by the grid barrier), the stages were
+        // read / written through the generic proxy: order both before the async-proxy copies
+        asm volatile("fence.proxy.async;" ::: "memory");
+        if (ring_mode) {
+          for (int ch = 0; ch < nch; ++ch) {
+            const uint32_t q = aseq + (uint32_t)ch;
+            if (q >= (uint32_t)TS_STAGES) mbar_wait(smem_base + OFF_TSE + (q & 3u) * 8, ((q >> 2) & 1u) ^ 1u);
+            a_issue(ch);
+          }
+        } else {
+          for (int s = 0; s < TS_STAGES - 1; ++s) a_issue(s);
+        }
+      }
+    } else if (stream) {
       for (int s = 0; s < TS_STAGES - 1; ++s) a_chunk_load(s);
+    }
     RingPos me = rnd;
     me.step(warp, S);
     for (int ch = 0; ch < nch; ++ch) {
       const int k0 = ch * KC, klen = min(KC, p.K - k0);
-      if (stream) {
+      if (tma) {
+        if (!ring_mode) {
+          if (ch > 0) bar_consumers();  // everybody is done with chunk ch - 1: its stage takes chunk ch + 3
+          if (issuer) a_issue(ch + TS_STAGES - 1);
+        }
+        if (has) mbar_wait(tsf + ((aseq + (uint32_t)ch) & 3u) * 8, ((aseq + (uint32_t)ch) >> 2) & 1u);
+      } else if (stream) {
         cp_async_wait<TS_STAGES - 2>();  // this thread's part of chunk ch has landed
         bar_consumers();                 // ... everybody's has, and everybody is done with chunk ch - 1
         // measured: issuing these ~4 cp.async per thread costs ~990 cycles per chunk (35 per LDGSTS) -- as much as the
@@ -806,9 +871,15 @@ __device__ __forceinline__ void gemm_ts(const MegaArgs& a, const Phase& p, uint3
         mbar_wait(smem_base + OFF_FULL + slot * 8, me.par);
         const long long tw1 = timed ? clock64() : 0;
         const uint32_t a_addr = stream ? act + (ch % TS_STAGES) * (16 * RS) : act + k0 * 2;
-        mma_chunk<1, false>(acc, acc2, ring + slot * a.slot_bytes, a_addr, AS, 0, klen >> 4, a.B, lane);
+        if (tma)
+          mma_chunk<1, false, true>(acc, acc2, ring + slot * a.slot_bytes, stage0 + ((aseq + (uint32_t)ch) & 3u) * STB, AS, 0, klen >> 4, a.B, lane);
+        else
+          mma_chunk<1, false>(acc, acc2, ring + slot * a.slot_bytes, a_addr, AS, 0, klen >> 4, a.B, lane);
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_base + OFF_EMPTY + slot * 8);
+        if (lane == 0) {
+          mbar_arrive(smem_base + OFF_EMPTY + slot * 8);
+          if (ring_mode) mbar_arrive(smem_base + OFF_TSE + ((aseq + (uint32_t)ch) & 3u) * 8);
+        }
         if (timed) {
           unsigned long long* dbg = reinterpret_cast<unsigned long long*>(dbg_smem);
           dbg[p.kind * 2] += (unsigned long long)(tw1 - tw0);
@@ -817,7 +888,10 @@ __device__ __forceinline__ void gemm_ts(const MegaArgs& a, const Phase& p, uint3
         me.step(nact, S);
       }
     }
-    if (stream) {
+    if (tma) {
+      aseq += (uint32_t)nch;
+      bar_consumers();  // the stages are refilled by the next round / the next phase's row load
+    } else if (stream) {
       cp_async_wait<0>();
       bar_consumers();  // the stages are refilled by the next round / the next phase's row load
     }
@@ -827,9 +901,15 @@ __device__ __forceinline__ void gemm_ts(const MegaArgs& a, const Phase& p, uint3
 #pragma unroll
     for (int hr = 0; hr < 2; ++hr) {
       const int tok = tok0 + g + hr * 8;
-      if (tok < a.B) epilogue_store<MT>(a, p, seg, tok, n, acc[0][hr * 2], acc[0][hr * 2 + 1], 0.f, 0.f, 0u);
+      if (tok < a.B) {
+        if (res_pre)
+          epilogue_store<0>(a, p, seg, tok, n, acc[0][hr * 2], acc[0][hr * 2 + 1], 0.f, 0.f, res_old[hr]);  // <0>: residual word passed in
+        else
+          epilogue_store<MT>(a, p, seg, tok, n, acc[0][hr * 2], acc[0][hr * 2 + 1], 0.f, 0.f, 0u);
+      }
     }
   }
+  if (tma && issuer) sts32_volatile(smem_base + OFF_TSSEQ, aseq);  // read by everybody behind the next grid barrier
   if (n_c > 0) base.advance((uint32_t)(n_c * nch), a.ph_adv_slot[p.kind][p.cls], a.ph_adv_par[p.kind][p.cls], S);
 }
 
@@ -1830,20 +1910,20 @@ constexpr int AVG = 128;            // cached positions per V slot: the PV warps
 constexpr int AVG_BYTES = AVG * 128;
 constexpr int NVS = NW * AG / AVG;  // V slots in the same ring memory (3)
 constexpr int OFF_AKF = 656;        // NW mbarriers: K slot of warp w filled      (behind OFF_DBG)
-constexpr int OFF_AVF = 896;        // NW mbarriers: V slot s filled              (behind OFF_REL)
-constexpr int OFF_AVE = 952;        // NW mbarriers: V slot s read by all PV warps
+constexpr int OFF_AVF = 896;        // 3 mbarriers: V slot s filled               (behind OFF_REL)
+constexpr int OFF_AVE = 920;        // 3 mbarriers: V slot s read by all PV warps
 constexpr int PVW = 4;              // PV warps; warp PVW feeds the V ring
 constexpr int AQ = 20;              // q quads per head in shared memory: 8 (lanes with even pairs) + 1 pad + 8 (odd pairs) + 3 pad --
                                     // the two quads a lane pair reads together are 144 bytes apart: different banks
 static_assert(OFF_DBG + 16 * 8 <= OFF_AKF && OFF_AKF + NW * 8 <= OFF_REL && OFF_REL + MAX_SLOTS * 4 <= OFF_AVF &&
-                  OFF_AVE + NW * 8 <= OFF_RMS,
+                  OFF_AVF + NVS * 8 <= OFF_AVE && OFF_AVE + NVS * 8 <= OFF_TSF && OFF_TSF + 4 * 8 <= OFF_TSE && OFF_TSE + 4 * 8 <= OFF_RMS,
               "shared-memory header layout");
 
 // ring state kept across tasks and layers, in the shared-memory header (registers of the caller stay untouched):
 // u32 kuse[NW] fills of warp w's K slot so far | u32 vseq: V groups streamed so far (slot = vseq % NVS, fill number =
 // vseq / NVS) | u32 pre: the K groups of the CTA's first task were requested in front of the grid barrier
 constexpr int OFF_APIPE = OFF_AKF + NW * 8;
-static_assert(OFF_APIPE + (NW + 2) * 4 <= OFF_REL, "shared-memory header layout");
+static_assert(OFF_APIPE + (NW + 2) * 4 <= OFF_TSSEQ && OFF_TSSEQ + 4 <= OFF_REL, "shared-memory header layout");
 
 struct AttnTmaLayout {
   int q, knew, sums, score, ring, total;  // byte offsets from the activation area
@@ -2281,15 +2361,24 @@ __global__ void __launch_bounds__(MEGA_THREADS, 1) decode_mega_kernel(const __gr
       mbar_init(smem_base + OFF_FULL + s * 8, 1);
       mbar_init(smem_base + OFF_EMPTY + s * 8, 1);
     }
-    for (int s = 0; s < NW; ++s) {  // K/V rings of the attention phase (attention_tma_phase)
-      mbar_init(smem_base + OFF_AKF + s * 8, 1);
+    for (int s = 0; s < NW; ++s) mbar_init(smem_base + OFF_AKF + s * 8, 1);  // K/V rings of the attention phase (attention_tma_phase)
+    for (int s = 0; s < NVS; ++s) {
       mbar_init(smem_base + OFF_AVF + s * 8, 1);
       mbar_init(smem_base + OFF_AVE + s * 8, PVW);
+    }
+    {  // A stream of the tile-split down_proj (gemm_ts): "read" barriers count the warps of this CTA that own a unit
+      const int G = a.ph_G[PH_DOWN];
+      const int n_c = G > 0 ? a.ph_q[PH_DOWN] + (((int)blockIdx.x / a.mtt) < a.ph_r[PH_DOWN] ? 1 : 0) : 0;
+      for (int s = 0; s < 4; ++s) {
+        mbar_init(smem_base + OFF_TSF + s * 8, 1);
+        mbar_init(smem_base + OFF_TSE + s * 8, (uint32_t)max(1, min(NW, n_c)));
+      }
     }
     *reinterpret_cast<volatile uint32_t*>(smem + OFF_ISSUED) = 0u;
     for (int i = 0; i < 16; ++i) reinterpret_cast<unsigned long long*>(smem + OFF_DBG)[i] = 0ull;
     for (int i = 0; i < MAX_SLOTS; ++i) reinterpret_cast<uint32_t*>(smem + OFF_REL)[i] = 0u;
     for (int i = 0; i < NW + 2; ++i) reinterpret_cast<uint32_t*>(smem + OFF_APIPE)[i] = 0u;
+    *reinterpret_cast<uint32_t*>(smem + OFF_TSSEQ) = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }

@@ -548,6 +548,7 @@ static cudaError_t forward_decode_mega_rows(qie_engine* e, int row0, int n, int 
   a.wmaps = e->mega_wmaps_d[tset];
   a.KC = e->mega_kc[tset];
   a.kvmap = e->mega_kvmap_d;
+  a.hmap = tset == 0 && !(e->tp.size > 1) ? e->mega_hmap_d : nullptr;  // boxes of KC = mega_kc[0] columns over the unsharded h
   a.embed = e->embed;
   a.final_norm = e->final_norm;
   a.lm_head = e->lm_head;

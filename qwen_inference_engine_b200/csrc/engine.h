@@ -94,6 +94,7 @@ struct qie_engine {
   int mega_kc[2] = {0, 0};
   qie::MegaCand* mega_cand_d = nullptr;
   unsigned* mega_bar_d = nullptr;
+  qie::TensorMap2D* mega_hmap_d = nullptr;   // h [rows, I] in boxes of 16 rows x KC (batches > 8): A stream of the tile-split down_proj
   qie::TensorMap2D* mega_kvmap_d = nullptr;  // KV pool rows for the TMA K/V stream of the persistent kernel's attention
   unsigned long long* mega_prof_d = nullptr;  // phase timestamps of the last profiled step
   bool mega_prof_on = false;

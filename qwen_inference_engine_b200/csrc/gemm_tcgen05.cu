@@ -738,14 +738,14 @@ cudaError_t make_tensor_map_2d(TensorMap2D* out, const bf16* base, int rows, int
 // Weight matrix [rows, K] viewed as a 3-D tensor {64 k-elements, rows, K/64 k-blocks} so that
 // ONE TMA request moves a box of 8 rows x kc k-elements (8 x kc x 2 bytes) into shared
 // memory as [k-block][row][64] with the 128-byte swizzle (decode_mega.cu weight ring).
-cudaError_t make_tensor_map_w3d(TensorMap2D* out, const bf16* base, int rows, int K, int kc, int ld) {
+cudaError_t make_tensor_map_w3d(TensorMap2D* out, const bf16* base, int rows, int K, int kc, int ld, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return cudaErrorNotSupported;
   if ((K % 64) || (kc % 64) || kc / 64 > 256) return cudaErrorInvalidValue;
   if (ld <= 0) ld = K;  // a column slice of a wider matrix (tensor parallel o_proj / down_proj) has ld > K
   cuuint64_t dims[3] = {64, (cuuint64_t)rows, (cuuint64_t)(K / 64)};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, 128};
-  cuuint32_t box[3] = {64, 8, (cuuint32_t)(kc / 64)};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, (cuuint32_t)(kc / 64)};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, dims,
                    strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

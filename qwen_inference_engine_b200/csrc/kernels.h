@@ -137,7 +137,7 @@ struct TensorMap2D {
   alignas(64) unsigned char opaque[128];  // CUtensorMap
 };
 cudaError_t make_tensor_map_2d(TensorMap2D* out, const bf16* base, int rows, int K, int box_rows);
-cudaError_t make_tensor_map_w3d(TensorMap2D* out, const bf16* base, int rows, int K, int kc, int ld = 0);  // ld: row stride in elements (0 = K)
+cudaError_t make_tensor_map_w3d(TensorMap2D* out, const bf16* base, int rows, int K, int kc, int ld = 0, int box_rows = 8);  // ld: row stride in elements (0 = K)
 // KV pool as a 2-D tensor {head_dim 64, every (page, layer, K|V, head, slot) row}: box = box_rows slots x 128 bytes, 128-byte swizzle
 cudaError_t make_tensor_map_kv(TensorMap2D* out, const bf16* pool, unsigned long long rows, int hd, int box_rows);
 int tc_token_tile(int M);
@@ -212,6 +212,7 @@ struct MegaArgs {
   const MegaLayer* layers;  // device array [L]
   const TensorMap2D* wmaps; // device array [7*L + 1]: q k v o gate up down per layer, then lm_head (make_tensor_map_w3d)
   const TensorMap2D* kvmap; // device: the KV pool as rows of one head (make_tensor_map_kv), nullptr = no TMA streaming of K/V
+  const TensorMap2D* hmap;  // device: h [rows, I] as {64, rows, I/64} with boxes of 16 rows x KC (the A stream of the tile-split down_proj), or nullptr
   const bf16 *embed, *final_norm, *lm_head;
   const float *cos_t, *sin_t;
   int B;  // decode rows, one token per sequence
