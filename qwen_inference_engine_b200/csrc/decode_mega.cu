@@ -2265,6 +2265,9 @@ __device__ __noinline__ void attention_tma_phase(const MegaArgs& a, int layer, u
         __syncwarp();
       }
       for (int k = 32 * nfull; k < n; ++k) sum = __fadd_rn(sum, s[k]);
+      // (measured dead end: leaving these divisions to the two warps that idle during PV, group by group behind the V
+      // ring's "filled" barriers -- softmax 22 k -> 17 k cycles, PV 33 k -> 47 k: the PV warps' schedulers are saturated,
+      // whatever else runs on them lengthens the chains)
       for (int k = lane; k < n; k += 32) s[k] = __fdiv_rn(s[k], sum);
     }
     bar_consumers();  // probabilities visible
