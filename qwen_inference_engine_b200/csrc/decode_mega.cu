@@ -541,11 +541,14 @@ __device__ __forceinline__ void lm_store(const MegaArgs& a, int tok, int n, floa
   const bf16 l0 = f2bf(v0), l1 = f2bf(v1);
   *reinterpret_cast<uint32_t*>(a.logits + (size_t)tok * a.V + n) = pack2(l0, l1);
   const float f0 = bf2f(l0), f1 = bf2f(l1);
-  if (f0 > -CUDART_INF_F && cand_better(f0, n, bb.v, bb.i)) {
+  // take a candidate when it is finite-or-+inf and better in the reference's total order (cand_better).  A larger
+  // value wins outright (also against the initial {-inf, -1}); only an exact tie needs the index comparison -- the
+  // full comparator on every logit cost as many issue slots as the phase's HMMAs.
+  if (f0 > bb.v || (f0 == bb.v && f0 > -CUDART_INF_F && cand_better(f0, n, bb.v, bb.i))) {
     bb.v = f0;
     bb.i = n;
   }
-  if (f1 > -CUDART_INF_F && cand_better(f1, n + 1, bb.v, bb.i)) {
+  if (f1 > bb.v || (f1 == bb.v && f1 > -CUDART_INF_F && cand_better(f1, n + 1, bb.v, bb.i))) {
     bb.v = f1;
     bb.i = n + 1;
   }

@@ -222,3 +222,33 @@ def test_mega_fast_numerics_tolerance(qie, arch, n_seq):
     # (every op rounds to bf16; a different fp32 sum order moves values that sit on a rounding
     # boundary), so its final logits are held to 5e-2 and the per-layer bar is carried by the small models.
     assert rel_l2(a, b) < (1e-2 if eng.config.layers <= 3 else 5e-2)
+
+
+@pytest.mark.parametrize("page_size", [8, 16, 32, 64])
+def test_mega_group_attention_tma_page_sizes_and_ragged_contexts(qie, page_size):
+    """Query-group attention tasks with K/V streamed by TMA over the KV-pool tensor map (head_dim 64, pages of >= 8
+    slots): page chunks of 8 / 16 / 32 / 64 positions, contexts on both sides of the K-group (64) and V-group (128)
+    boundaries, partial last groups -- tokens, logits and the whole pool equal the per-operator path."""
+    ctxs = [1, 7, 8, 15, 16, 17, 31, 63, 64, 65, 100, 127, 128, 129, 130, 191, 192, 193, 255, 256, 257, 300, 319, 320, 321, 383,
+            384, 385, 401, 447, 448, 449, 450, 460, 470, 480, 490, 500, 505, 37, 41, 59, 61, 67, 71, 73, 79, 83]
+    res = {}
+    for mode in (0, 1):
+        eng = qie.Engine(synthetic="small", seed=1234, context=1024, max_seqs=len(ctxs) + 1, max_batch_tokens=64, use_graph=False,
+                         page_size=page_size, kv_bytes=128 << 20)
+        eng.set_int("mega", mode)
+        seqs = []
+        for i, n in enumerate(ctxs):
+            s = eng.new_sequence()
+            eng.fill_synthetic(s, n, seed=100 + i)
+            seqs.append(s)
+        assert eng.uses_mega(len(ctxs), 520) == bool(mode)
+        tok = (np.arange(len(ctxs), dtype=np.int32) * 131 + 3) % eng.config.vocab
+        hist = []
+        for _ in range(3):
+            tok = eng.decode_step(seqs, tok)
+            hist.append(tok.copy())
+        res[mode] = (np.stack(hist), eng.read_activation("logits", len(ctxs) * eng.config.vocab), _kv_snapshot(eng))
+        eng.close()
+    assert np.array_equal(res[1][1], res[0][1])
+    assert np.array_equal(res[1][0], res[0][0])
+    assert np.array_equal(res[1][2], res[0][2])
