@@ -194,6 +194,10 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
   // the exp + bf16-pack pass 53 us (16 384 ex2 + 8 192 cvt per tile on the 16-lane XU pipe), everything else --
   // tile copies, TMEM loads, row max, O fold, P stores, barriers, CTA prologue/epilogue -- 94 us.  An MN-major V
   // descriptor costs the same as a K-major one.
+  // r02, measured dead end: S in two TMEM buffers with S(t+1) issued before the softmax of tile t and K / V tiles
+  // requested separately (K(t+2) behind S(t), V(t+1) behind P V(t-1)): 17.5 -> 18.5 ms for the 1.5B prefill -- the softmax
+  // warps are the critical path, and the second copy pass (page lookups twice) costs them more than the S latency it hides.
+  // The next step is to take the copies off those warps altogether (K/V by TMA: two 64-column boxes per page chunk).
   const uint32_t lbo = (lbo_sbo_swap & 1) ? 1024u : (uint32_t)BLK, sbo = (lbo_sbo_swap & 1) ? (uint32_t)BLK : 1024u;
   constexpr uint32_t ID_S = idesc_(128, 128, false), ID_O = idesc_(128, 128, true);
   const float sl2 = a.scale_log2;
