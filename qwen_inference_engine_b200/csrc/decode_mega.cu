@@ -2005,43 +2005,52 @@ __device__ __forceinline__ float2 bf2x_to_f2(uint32_t v) {  // ALU pipe only (PR
 }
 
 // PV over one whole ring slot (AVG = 128 cached rows of V, swizzled: word `lane` of row r sits at (lane << 2) ^ ((r & 7) << 4)) for
-// the NH heads of a warp: o[h] = fma(p[h][k], v[k], o[h]) for k ascending -- the reference's chain
-// (self_attension.cu:112-137), two IEEE fmas per packed FFMA2, lane l = output dims 2l, 2l + 1.  Fully unrolled: every
-// address is one of 8 row registers + an immediate, so a position costs one LDS.32, the widening (PRMT + LOP3) and NH
-// FFMA2 (+ a quarter of a broadcast LDS.128 per head); chunk c + 1 is loaded before the chains of chunk c.
-template <int NH>
+// the two heads of a warp: o[h] = fma(p[h][k], v[k], o[h]) for k ascending -- the reference's chain
+// (self_attension.cu:112-137), two IEEE fmas per packed FFMA2, lane l = output dims 2l, 2l + 1.  The body is PVU rows
+// unrolled (every address is one of 8 row registers + an immediate: a position costs one LDS.32, the widening and two
+// FFMA2, + a quarter of a broadcast LDS.128 per head); chunk c + 1 is loaded before the chains of chunk c.
+// ONE copy of the body serves every PV warp: a warp with a single head runs the second chain on a dummy probability
+// row (its scheduler has the slots to spare) -- the step executes ~120 KB of code per layer, right at the size of the
+// instruction cache, and every KB less shows up in ALL phases (cold code costs ~10 cycles per instruction).
+constexpr int PVU = 64;
 __device__ __forceinline__ void pv_group(const unsigned char* __restrict__ slot, const uint32_t (&xo)[8], const float* __restrict__ p0,
                                          const float* __restrict__ p1, float2 (&o)[2]) {
   const unsigned char* rowp[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) rowp[j] = slot + xo[j];
   uint32_t v[2][8];
-  float4 pr[2][NH][2];
-  auto load = [&](int c) {
+  float4 pr[2][2][2];
+  auto load = [&](int c) {  // c: chunk of 8 rows within the current block of PVU (c = PVU / 8: first chunk of the next block)
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[c & 1][j] = *reinterpret_cast<const uint32_t*>(rowp[j] + c * 1024 + j * 128);
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       pr[c & 1][0][u] = *reinterpret_cast<const float4*>(p0 + 8 * c + 4 * u);
-      if (NH == 2) pr[c & 1][NH - 1][u] = *reinterpret_cast<const float4*>(p1 + 8 * c + 4 * u);
+      pr[c & 1][1][u] = *reinterpret_cast<const float4*>(p1 + 8 * c + 4 * u);
     }
   };
   load(0);
+#pragma unroll 1
+  for (int blk = 0; blk < AVG / PVU; ++blk) {
 #pragma unroll
-  for (int c = 0; c < AVG / 8; ++c) {
-    if (c + 1 < AVG / 8) load(c + 1);
+    for (int c = 0; c < PVU / 8; ++c) {
+      if (c + 1 < PVU / 8 || blk + 1 < AVG / PVU) load(c + 1);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      // low half through the FMA pipe (IMAD.SHL), high half through the ALU pipe (LOP3).  (Measured: a body of 32 rows
-      // looped four times instead of 128 rows unrolled -- 20 % of the issue slots wait for instructions here -- is 8 % slower.)
-      const float2 vf = make_float2(__uint_as_float(v[c & 1][j] * 65536u), __uint_as_float(v[c & 1][j] & 0xffff0000u));
+      for (int j = 0; j < 8; ++j) {
+        // low half through the FMA pipe (IMAD.SHL), high half through the ALU pipe (LOP3)
+        const float2 vf = make_float2(__uint_as_float(v[c & 1][j] * 65536u), __uint_as_float(v[c & 1][j] & 0xffff0000u));
 #pragma unroll
-      for (int hh = 0; hh < NH; ++hh) {
-        const float4 p4 = pr[c & 1][hh][j >> 2];
-        const float pj = (j & 3) == 0 ? p4.x : ((j & 3) == 1 ? p4.y : ((j & 3) == 2 ? p4.z : p4.w));
-        o[hh] = __ffma2_rn(make_float2(pj, pj), vf, o[hh]);
+        for (int hh = 0; hh < 2; ++hh) {
+          const float4 p4 = pr[c & 1][hh][j >> 2];
+          const float pj = (j & 3) == 0 ? p4.x : ((j & 3) == 1 ? p4.y : ((j & 3) == 2 ? p4.z : p4.w));
+          o[hh] = __ffma2_rn(make_float2(pj, pj), vf, o[hh]);
+        }
       }
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rowp[j] += PVU * 128;
+    p0 += PVU;
+    p1 += PVU;
   }
 }
 // the rows of a partial last group, one at a time
@@ -2288,7 +2297,7 @@ __device__ __noinline__ void attention_tma_phase(const MegaArgs& a, int layer, u
       const int hstride = PVW * SP;
       // every PV warp walks all V groups (also a warp without a head: the "drained" barrier counts PVW arrivals)
       const float* p0 = sb;
-      const float* p1 = sb + hstride;
+      const float* p1 = nh == 2 ? sb + hstride : sb;  // one head: the second chain repeats the first (never stored)
       for (int j = 0; j < nvg; ++j) {
         {
           const long long tw0 = timed ? clock64() : 0;
@@ -2298,10 +2307,7 @@ __device__ __noinline__ void attention_tma_phase(const MegaArgs& a, int layer, u
         const unsigned char* slot = ringp + ls * AVG_BYTES;
         const int nrows = min(AVG, ps - AVG * j);
         if (nrows == AVG) {
-          if (nh == 2)
-            pv_group<2>(slot, xo, p0, p1, o);
-          else if (nh == 1)
-            pv_group<1>(slot, xo, p0, p1, o);
+          if (nh >= 1) pv_group(slot, xo, p0, p1, o);
         } else {
           if (nh == 2)
             pv_tail<2>(slot, lane, p0, p1, nrows, o);
