@@ -290,13 +290,13 @@ __global__ void attn_combine_kernel(FastAttnArgs a, int hd) {
 
 template <int HD>
 static cudaError_t launch_hd(const FastAttnArgs& a, cudaStream_t st) {
-  static bool set = false;
+  static PerDeviceOnce set;
   constexpr int smem = FastAttnSmem<HD>::TOTAL;
   static_assert(FastAttnSmem<HD>::RING >= 4 * 16 * HD * 4 + 4 * 16 * 2 * 4, "merge scratch must fit in the KV ring");
-  if (!set) {
+  if (set.need()) {
     cudaError_t e = cudaFuncSetAttribute(attn_decode_fast_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    set = true;
+    set.done();
   }
   dim3 grid(a.n_splits, a.kv.n_kv, a.n_tok);
   (void)launch_k(attn_decode_fast_kernel<HD>, dim3(grid), dim3(128), smem, st, a);

@@ -264,12 +264,12 @@ __global__ void __launch_bounds__(128, 3) attn_prefill_fast_kernel(FastAttnArgs 
 
 template <int HD>
 static cudaError_t launch_pf_hd(const FastAttnArgs& a, cudaStream_t st) {
-  static bool set = false;
+  static PerDeviceOnce set;
   constexpr int smem = PrefillAttnSmem<HD>::TOTAL;
-  if (!set) {
+  if (set.need()) {
     cudaError_t e = cudaFuncSetAttribute(attn_prefill_fast_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
-    set = true;
+    set.done();
   }
   dim3 grid(a.n_q, (a.n_tok + PF_QT - 1) / PF_QT);
   (void)launch_k(attn_prefill_fast_kernel<HD>, grid, dim3(128), smem, st, a);

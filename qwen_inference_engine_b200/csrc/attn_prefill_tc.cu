@@ -337,11 +337,11 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
 cudaError_t launch_attention_prefill_tc(const FastAttnArgs& a, int lbo_sbo_swap, cudaStream_t st) {
   if (a.n_tok == 0) return cudaSuccess;
   if (a.kv.hd != HDX || a.n_q % a.kv.n_kv) return cudaErrorInvalidValue;
-  static bool set = false;
-  if (!set) {
+  static PerDeviceOnce set;
+  if (set.need()) {
     cudaError_t e = cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
     if (e != cudaSuccess) return e;
-    set = true;
+    set.done();
   }
   dim3 grid(a.n_q, (a.n_tok + TQ - 1) / TQ);
   (void)launch_k(attn_prefill_tc_kernel, grid, dim3(NTHR), (size_t)SM_TOTAL, st, a, lbo_sbo_swap);

@@ -214,12 +214,12 @@ __global__ void __launch_bounds__(256) gemm_ref_order_kernel(GemmArgs g) {
 
 template <int MT>
 static cudaError_t launch_mt(const GemmArgs& g, int nw, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_set;
+  if (attr_set.need()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_ref_order_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          200 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set.done();
   }
   int grid = (g.total_units + nw - 1) / nw;
   (void)launch_k(gemm_ref_order_kernel<MT>, dim3(grid), dim3(nw * 32), smem, st, g);

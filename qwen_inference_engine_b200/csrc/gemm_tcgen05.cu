@@ -775,13 +775,13 @@ template <int BN>
 static cudaError_t launch_bn(const TcGemm& t, const TcArgs& g, int token_tiles, cudaStream_t st) {
   constexpr int STAGE_BYTES = BM * BK * 2 + BN * BK * 2;
   constexpr size_t smem = (size_t)TcCfg<BN>::STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static bool set = false;
-  if (!set) {
+  static PerDeviceOnce set;
+  if (set.need()) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (e != cudaSuccess) return e;
-    set = true;
+    set.done();
   }
   const CUtensorMap* w0 = reinterpret_cast<const CUtensorMap*>(t.w[0]);
   const CUtensorMap* w1 = reinterpret_cast<const CUtensorMap*>(t.w[t.nseg > 1 ? 1 : 0]);
@@ -869,11 +869,11 @@ cudaError_t launch_gemm_tcgen05(const TcGemm& t, int num_sms, cudaStream_t st, i
   if (persist_on && g.staged && BN == PBN && tiles * token_tiles > num_sms / 2) {
     // prefill-sized launches: persistent tile loop, epilogue overlapped with the next tile's mainloop
     constexpr size_t smem = (size_t)P_STAGES * P_STAGE_BYTES + P_STAGING + 1024 /*align*/ + 256 /*barriers*/;
-    static bool set = false;
-    if (!set) {
+    static PerDeviceOnce set;
+    if (set.need()) {
       e = cudaFuncSetAttribute(gemm_tcgen05_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      set = true;
+      set.done();
     }
     const CUtensorMap* w0 = reinterpret_cast<const CUtensorMap*>(t.w[0]);
     const CUtensorMap* w1 = reinterpret_cast<const CUtensorMap*>(t.w[t.nseg > 1 ? 1 : 0]);

@@ -19,6 +19,21 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 
 extern bool g_use_pdl;  // engine.cu; set per process from QIE_PDL (default on)
 
+// Function attributes (opt-in dynamic shared memory, cluster size) are per DEVICE: a process that creates engines on
+// several devices must set them on each.  One flag per device ordinal instead of a process-wide `static bool`.
+struct PerDeviceOnce {
+  unsigned long long mask[4] = {0ull, 0ull, 0ull, 0ull};
+  bool need() const {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 256) return true;
+    return ((mask[d >> 6] >> (d & 63)) & 1ull) == 0ull;
+  }
+  void done() {
+    int d = 0;
+    if (cudaGetDevice(&d) == cudaSuccess && d >= 0 && d < 256) mask[d >> 6] |= 1ull << (d & 63);
+  }
+};
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                             Args&&... args) {

@@ -826,11 +826,14 @@ cudaError_t launch_sample_topk(const bf16* logits, int* out_tokens, int n_rows, 
       int cap = 0;
     };
     static std::mutex mu;
-    static std::map<cudaStream_t, std::vector<Scratch>> pool;
+    static std::map<std::pair<int, cudaStream_t>, std::vector<Scratch>> pool;  // keyed by (device, stream): a stream handle
+                                                                               // value can come back on another device
     Cand* cands = nullptr;
     {
+      int dev = 0;
+      (void)cudaGetDevice(&dev);
       std::lock_guard<std::mutex> lk(mu);
-      std::vector<Scratch>& v = pool[st];
+      std::vector<Scratch>& v = pool[std::make_pair(dev, st)];
       for (const Scratch& sc : v)
         if (sc.cap >= n_rows) cands = sc.p;
       if (!cands) {

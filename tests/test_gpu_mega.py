@@ -252,3 +252,34 @@ def test_mega_group_attention_tma_page_sizes_and_ragged_contexts(qie, page_size)
     assert np.array_equal(res[1][1], res[0][1])
     assert np.array_equal(res[1][0], res[0][0])
     assert np.array_equal(res[1][2], res[0][2])
+
+
+@pytest.mark.parametrize("n_seq,ctx", [(1, 12600), (40, 13000)])
+def test_reference_order_decode_above_12k_context(qie, n_seq, ctx):
+    """reference-order decode with more than 12 k cached positions (the reference's practical limit):
+    the persistent kernel where the score rows fit its shared memory, the per-operator kernels otherwise -- both give
+    the same tokens, logits and cache."""
+    res = {}
+    used = {}
+    for mode in (0, 1):
+        eng = qie.Engine(synthetic="tiny", seed=1234, context=16384, max_seqs=n_seq + 1, max_batch_tokens=64, use_graph=False,
+                         kv_bytes=n_seq * (ctx + 64) * 2 * 2 * 2 * 64 * 2 + (64 << 20))
+        eng.set_int("mega", mode)
+        seqs = []
+        for i in range(n_seq):
+            s = eng.new_sequence()
+            eng.fill_synthetic(s, ctx + 3 * i, seed=7 + i)
+            seqs.append(s)
+        used[mode] = eng.uses_mega(n_seq, ctx + 3 * n_seq + 4)
+        tok = (np.arange(n_seq, dtype=np.int32) * 17 + 1) % eng.config.vocab
+        hist = []
+        for _ in range(2):
+            tok = eng.decode_step(seqs, tok)
+            hist.append(tok.copy())
+        res[mode] = (np.stack(hist), eng.read_activation("logits", n_seq * eng.config.vocab), _kv_snapshot(eng))
+        eng.close()
+    print(f"n_seq {n_seq} ctx {ctx}: persistent kernel used: {used[1]}")
+    assert not used[0]
+    assert np.array_equal(res[1][1], res[0][1])
+    assert np.array_equal(res[1][0], res[0][0])
+    assert np.array_equal(res[1][2], res[0][2])
