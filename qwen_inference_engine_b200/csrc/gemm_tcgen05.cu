@@ -501,9 +501,13 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_kernel(const __grid_constant
 // one-tile-per-CTA kernel showed the tensor pipe 32-47 % active at K = 1536: per tile ~2.5 us of prologue and
 // ~8 us of epilogue sat next to a ~7-9 us mainloop (profiles/r01c_ncu_full_prefill_kernels.csv).
 static constexpr int PBN = 256;
-static constexpr int P_STAGES = 3;
+// r02: four operand stages instead of three (ncu: tensor pipe 37-61 % active with L2 at 15-32 % of its peak -- the mainloop
+// waited for TMA, 3 x 512 MMA cycles of lookahead do not cover the load latency); the room comes from a half-size
+// staging tile: the epilogue drains and stores the accumulator in two halves of 128 tokens.
+static constexpr int P_STAGES = 4;
 static constexpr int P_STAGE_BYTES = BM * BK * 2 + PBN * BK * 2;  // 48 KiB
-static constexpr int P_STAGING = PBN * BM * 2;                      // bf16 [256 tokens][128 rows] = 64 KiB
+static constexpr int P_HALF = PBN / 2;
+static constexpr int P_STAGING = P_HALF * BM * 2;                   // bf16 [128 tokens][128 rows] = 32 KiB
 
 __global__ void __launch_bounds__(192) gemm_tcgen05_persist_kernel(const __grid_constant__ CUtensorMap map_w0,
                                                                    const __grid_constant__ CUtensorMap map_w1,
@@ -628,10 +632,14 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_persist_kernel(const __grid_
       mbar_wait(tfull_bar(buf), ((uint32_t)j >> 1) & 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + (uint32_t)buf * PBN + ((uint32_t)(qd * 32) << 16);
+      const int n_tok_all = min(PBN, g.M - tok_base);
+#pragma unroll 1
+      for (int hf = 0; hf < 2; ++hf) {  // tokens [128 hf, 128 hf + 128) of the tile through the 32 KiB staging tile
+      const int h0 = hf * P_HALF;
 #pragma unroll 4
-      for (int c0 = 0; c0 < PBN; c0 += 16) {
+      for (int c0 = 0; c0 < P_HALF; c0 += 16) {
         uint32_t r[16];
-        tmem_ld16(acc + c0, r);
+        tmem_ld16(acc + h0 + c0, r);
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
           const unsigned short hb = __bfloat16_as_ushort(f2bf(__uint_as_float(r[q])));
@@ -640,8 +648,8 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_persist_kernel(const __grid_
       }
       tc_fence_before();
       asm volatile("bar.sync 2, 128;" ::: "memory");
-      if (tq == 0) mbar_arrive_local(tempty_bar(buf));  // the MMA warp may overwrite this accumulator (tile j+2)
-      const int n_tok = min(PBN, g.M - tok_base);
+      if (hf == 1 && tq == 0) mbar_arrive_local(tempty_bar(buf));  // the MMA warp may overwrite this accumulator (tile j+2)
+      const int n_tok = max(0, min(P_HALF, n_tok_all - h0));
       if (!g.dual) {
         const int totalc = n_tok * (BM / 8);
         for (int c = tq; c < totalc; c += 8 * 128) {
@@ -654,7 +662,7 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_persist_kernel(const __grid_
             const int tok = cc >> 4, part = cc & 15;
             const int w_row = row0 + part * 8;
             ok[u] = cc < totalc && w_row < seg_rows;
-            dst[u] = g.out + (size_t)(tok_base + tok) * g.ld_out + col0 + w_row;
+            dst[u] = g.out + (size_t)(tok_base + h0 + tok) * g.ld_out + col0 + w_row;
             if (ok[u]) {
               if (g.epi == EPI_RESIDUAL) x[u] = *reinterpret_cast<const uint4*>(dst[u]);
               y[u] = lds128(stg + (uint32_t)tok * PITCH + (uint32_t)part * 16u);
@@ -691,8 +699,10 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_persist_kernel(const __grid_
             const float a1 = __fmul_rn(hi2f(us[e]), bf2f(f2bf(silu_ref_f(hi2f(gs[e])))));
             o4[e] = pack2(f2bf(a0), f2bf(a1));
           }
-          *reinterpret_cast<uint4*>(g.out + (size_t)(tok_base + tok) * g.ld_out + w_row) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+          *reinterpret_cast<uint4*>(g.out + (size_t)(tok_base + h0 + tok) * g.ld_out + w_row) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
         }
+      }
+      if (hf == 0) asm volatile("bar.sync 2, 128;" ::: "memory");  // the staging tile is rewritten by the second half
       }
       asm volatile("bar.sync 2, 128;" ::: "memory");  // the staging tile is rewritten by the next tile
     }
