@@ -507,9 +507,11 @@ static constexpr int PBN = 256;
 static constexpr int P_STAGES = 4;
 static constexpr int P_STAGE_BYTES = BM * BK * 2 + PBN * BK * 2;  // 48 KiB
 static constexpr int P_HALF = PBN / 2;
+static constexpr int P_EPI = 256;                 // epilogue threads (8 warps)
+static constexpr int P_THREADS = 64 + P_EPI;      // + TMA warp + MMA warp
 static constexpr int P_STAGING = P_HALF * BM * 2;                   // bf16 [128 tokens][128 rows] = 32 KiB
 
-__global__ void __launch_bounds__(192) gemm_tcgen05_persist_kernel(const __grid_constant__ CUtensorMap map_w0,
+__global__ void __launch_bounds__(P_THREADS) gemm_tcgen05_persist_kernel(const __grid_constant__ CUtensorMap map_w0,
                                                                    const __grid_constant__ CUtensorMap map_w1,
                                                                    const __grid_constant__ CUtensorMap map_w2,
                                                                    const __grid_constant__ CUtensorMap map_x, TcArgs g,
@@ -610,7 +612,8 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_persist_kernel(const __grid_
       }
     }
   } else {
-    // ---- epilogue warps 2-5
+    // ---- epilogue warps 2-9: two warps per TMEM lane quarter, each draining half of the columns (r02: with four warps the
+    // epilogue of a K = 1536 tile -- drain, SiLU * up, 64 KiB of stores -- took longer than the tile's mainloop)
     constexpr uint32_t PITCH = BM * 2;
     const int qd = warp & 3;
     const int lane_row = qd * 32 + lane;
@@ -636,8 +639,9 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_persist_kernel(const __grid_
 #pragma unroll 1
       for (int hf = 0; hf < 2; ++hf) {  // tokens [128 hf, 128 hf + 128) of the tile through the 32 KiB staging tile
       const int h0 = hf * P_HALF;
+      const int cw = ((warp - 2) >> 2) * (P_HALF / 2);  // this warp's columns of the half: [cw, cw + 64)
 #pragma unroll 4
-      for (int c0 = 0; c0 < P_HALF; c0 += 16) {
+      for (int c0 = cw; c0 < cw + P_HALF / 2; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(acc + h0 + c0, r);
 #pragma unroll
@@ -647,18 +651,18 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_persist_kernel(const __grid_
         }
       }
       tc_fence_before();
-      asm volatile("bar.sync 2, 128;" ::: "memory");
+      asm volatile("bar.sync 2, 256;" ::: "memory");
       if (hf == 1 && tq == 0) mbar_arrive_local(tempty_bar(buf));  // the MMA warp may overwrite this accumulator (tile j+2)
       const int n_tok = max(0, min(P_HALF, n_tok_all - h0));
       if (!g.dual) {
         const int totalc = n_tok * (BM / 8);
-        for (int c = tq; c < totalc; c += 8 * 128) {
+        for (int c = tq; c < totalc; c += 8 * P_EPI) {
           uint4 y[8], x[8];
           bf16* dst[8];
           bool ok[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
-            const int cc = c + u * 128;
+            const int cc = c + u * P_EPI;
             const int tok = cc >> 4, part = cc & 15;
             const int w_row = row0 + part * 8;
             ok[u] = cc < totalc && w_row < seg_rows;
@@ -685,7 +689,7 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_persist_kernel(const __grid_
         }
       } else {
         const int totalc = n_tok * (BM / 16);
-        for (int c = tq; c < totalc; c += 128) {
+        for (int c = tq; c < totalc; c += P_EPI) {
           const int tok = c >> 3, part = c & 7;
           const int w_row = row0 + part * 8;
           if (w_row >= seg_rows) continue;
@@ -702,9 +706,9 @@ __global__ void __launch_bounds__(192) gemm_tcgen05_persist_kernel(const __grid_
           *reinterpret_cast<uint4*>(g.out + (size_t)(tok_base + h0 + tok) * g.ld_out + w_row) = make_uint4(o4[0], o4[1], o4[2], o4[3]);
         }
       }
-      if (hf == 0) asm volatile("bar.sync 2, 128;" ::: "memory");  // the staging tile is rewritten by the second half
+      if (hf == 0) asm volatile("bar.sync 2, 256;" ::: "memory");  // the staging tile is rewritten by the second half
       }
-      asm volatile("bar.sync 2, 128;" ::: "memory");  // the staging tile is rewritten by the next tile
+      asm volatile("bar.sync 2, 256;" ::: "memory");  // the staging tile is rewritten by the next tile
     }
   }
   __syncthreads();
@@ -890,7 +894,7 @@ cudaError_t launch_gemm_tcgen05(const TcGemm& t, int num_sms, cudaStream_t st, i
     const CUtensorMap* w2 = reinterpret_cast<const CUtensorMap*>(t.w[t.nseg > 2 ? 2 : 0]);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(std::min(num_sms, tiles * token_tiles));
-    cfg.blockDim = dim3(192);
+    cfg.blockDim = dim3(P_THREADS);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
