@@ -511,6 +511,9 @@ static constexpr int PBN = 256;
 // r02: four operand stages instead of three (ncu: tensor pipe 37-61 % active with L2 at 15-32 % of its peak -- the mainloop
 // waited for TMA, 3 x 512 MMA cycles of lookahead do not cover the load latency); the room comes from a half-size
 // staging tile: the epilogue drains and stores the accumulator in two halves of 128 tokens.
+// (measured dead end: a 128-token tile variant -- 6 stages of 32 KiB -- for the launches whose 256-token tiles quantise badly
+// over the SMs, e.g. o_proj / down_proj of the 1.5B shape, 192 tiles = 65 % of two waves: 15.5 -> 16.3 ms, 7B 62.8 -> 70.9 ms;
+// the half-size tiles lose more per flop than the fuller waves give back.  Only the 0.5B shape gained, 8.5 -> 8.1 ms.)
 static constexpr int P_STAGES = 4;
 static constexpr int P_STAGE_BYTES = BM * BK * 2 + PBN * BK * 2;  // 48 KiB
 static constexpr int P_HALF = PBN / 2;
