@@ -115,13 +115,14 @@ __device__ __forceinline__ uint32_t tile_off(int r, int ch) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a, int lbo_sbo_swap) {
+__global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a, int lbo_sbo_swap,
+                                                                  const __grid_constant__ CUtensorMap kvm, int use_tma) {
   pdl_wait();
   pdl_trigger();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t s0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* sg = smem_raw + (s0 - smem_u32(smem_raw));
-  const uint32_t bar_s = s0 + SM_BAR, bar_o = bar_s + 8, slot = bar_s + 16;
+  const uint32_t bar_s = s0 + SM_BAR, bar_o = bar_s + 8, slot = bar_s + 16, bar_kv = bar_s + 24;  // bar_kv: two (K/V buffer)
   int* s_pages = reinterpret_cast<int*>(sg + SM_PAGES);
   float* xmax = reinterpret_cast<float*>(sg + SM_X);  // [2][128]
   float* xsum = xmax + 256;                            // [2][128]
@@ -143,6 +144,8 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
   if (threadIdx.x == 0) {
     mbar_init_(bar_s, 1);
     mbar_init_(bar_o, 1);
+    mbar_init_(bar_kv, 1);
+    mbar_init_(bar_kv + 8, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
@@ -188,7 +191,29 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
     }
     cp_async_commit();
   };
-  load_tile(0, 0);
+  // K/V tiles by TMA (r02; pages of 16 positions): the 32 lanes of the MMA warp request the 2 x 8 x 2 boxes of a tile --
+  // (K | V) x 8 page chunks x 2 column halves of 64, 2 KiB each, written with the 128-byte swizzle to exactly the place
+  // tile_off() puts them -- so the eight softmax warps issue no copy instructions at all.  Chunks behind the last
+  // page of the sequence repeat that page (finite values; their keys are masked).
+  const int n_kv_pages = (kv_len - 1) / psz + 1;
+  auto tma_tile = [&](int tile, int buf) {  // MMA warp, all lanes
+    const int is_v = lane >> 4, pg = (lane >> 1) & 7, half = lane & 1;
+    const int pi = min(tile * (TK / 16) + pg, n_kv_pages - 1);
+    const int page = pi < MAXP ? s_pages[pi] : bt[pi];
+    const int row = (((page * a.kv.n_layers + a.layer) * 2 + is_v) * a.kv.n_kv + kvh) * psz;
+    const uint32_t dst = s0 + (is_v ? SM_V0 : SM_K0) + buf * TILE_B + half * BLK + pg * 16 * 128;
+    const uint32_t bar = bar_kv + 8u * (uint32_t)buf;
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * TILE_B) : "memory");
+    __syncwarp();
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(&kvm), "r"(bar), "r"(half * 64), "r"(row)
+                 : "memory");
+  };
+  if (use_tma) {
+    if (warp == MMA_WARP) tma_tile(0, 0);
+  } else {
+    load_tile(0, 0);
+  }
 
   // Where the time goes (T = 4096, 12 heads, 171 us; probe builds that skip one part each): both MMA chains 35 us,
   // the exp + bf16-pack pass 53 us (16 384 ex2 + 8 192 cvt per tile on the 16-lane XU pipe), everything else --
@@ -224,13 +249,16 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
 
   for (int it = 0; it < n_tiles; ++it) {
     const int buf = it & 1;
-    cp_async_wait<0>();  // tile it (requested one iteration ago)
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async (generic proxy) data -> tensor core (async proxy)
-    __syncthreads();
+    if (!use_tma) {
+      cp_async_wait<0>();  // tile it (requested one iteration ago)
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async (generic proxy) data -> tensor core (async proxy)
+      __syncthreads();
+    }
     const uint32_t kb = s0 + SM_K0 + buf * TILE_B, vb = s0 + SM_V0 + buf * TILE_B;
     const uint32_t ph = it & 1;
     // ---- S = Q K^T
     if (warp == MMA_WARP && lane == 0) {
+      if (use_tma) mbar_wait_(bar_kv + 8u * (uint32_t)buf, (uint32_t)((it >> 1) & 1));  // tile it has landed (async proxy: no fence)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
       for (int kk = 0; kk < HDX / 16; ++kk) {
@@ -241,11 +269,20 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
     }
     // Behind the S product (queued right after the previous tile's P V in the tensor pipe): the buffer tile it+1 goes
     // into was read by the P V product of tile it-1, so wait for that MMA, then request the copies.
-    if (it > 0) mbar_wait_(bar_o, (uint32_t)((it - 1) & 1));
-    if (it + 1 < n_tiles) load_tile(it + 1, buf ^ 1);
+    if (use_tma) {
+      if (warp == MMA_WARP) {
+        __syncwarp();
+        if (it > 0) mbar_wait_(bar_o, (uint32_t)((it - 1) & 1));
+        if (it + 1 < n_tiles) tma_tile(it + 1, buf ^ 1);
+      }
+    } else {
+      if (it > 0) mbar_wait_(bar_o, (uint32_t)((it - 1) & 1));
+      if (it + 1 < n_tiles) load_tile(it + 1, buf ^ 1);
+    }
     const int p0 = it * TK + 64 * hf;  // first key of this thread's half
     if (soft) {
       if (it > 0) {  // fold the previous tile's P V product while the tensor core works on this tile's S
+        if (use_tma) mbar_wait_(bar_o, (uint32_t)((it - 1) & 1));  // (the copy path waited for it in front of its copies)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         fold_o();
       }
@@ -343,8 +380,14 @@ cudaError_t launch_attention_prefill_tc(const FastAttnArgs& a, int lbo_sbo_swap,
     if (e != cudaSuccess) return e;
     set.done();
   }
+  // K/V by TMA: the pool as rows of one head (256 bytes), boxes of 16 slots x 64 columns; pages of 16 positions only
+  // (QIE_ATTN_TC_TMA=0 keeps the cp.async copies: A/B knob)
+  static const bool tma_env = [] { const char* v = getenv("QIE_ATTN_TC_TMA"); return !(v && v[0] == '0'); }();
+  TensorMap2D tm{};
+  const unsigned long long rows = (unsigned long long)a.kv.n_pages * a.kv.n_layers * 2ull * a.kv.n_kv * a.kv.page_size;
+  const int use_tma = tma_env && a.kv.page_size == 16 && make_tensor_map_kv(&tm, a.kv.pool, rows, HDX, 16) == cudaSuccess;
   dim3 grid(a.n_q, (a.n_tok + TQ - 1) / TQ);
-  (void)launch_k(attn_prefill_tc_kernel, grid, dim3(NTHR), (size_t)SM_TOTAL, st, a, lbo_sbo_swap);
+  (void)launch_k(attn_prefill_tc_kernel, grid, dim3(NTHR), (size_t)SM_TOTAL, st, a, lbo_sbo_swap, *reinterpret_cast<const CUtensorMap*>(&tm), use_tma);
   return cudaGetLastError();
 }
 

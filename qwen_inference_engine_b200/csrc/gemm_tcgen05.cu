@@ -784,9 +784,9 @@ cudaError_t make_tensor_map_w3d(TensorMap2D* out, const bf16* base, int rows, in
 cudaError_t make_tensor_map_kv(TensorMap2D* out, const bf16* pool, unsigned long long rows, int hd, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return cudaErrorNotSupported;
-  if (hd != 64 || box_rows < 1 || box_rows > 256 || rows == 0 || rows >= (1ull << 31)) return cudaErrorInvalidValue;
-  cuuint64_t dims[2] = {64, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {128};
+  if ((hd != 64 && hd != 128) || box_rows < 1 || box_rows > 256 || rows == 0 || rows >= (1ull << 31)) return cudaErrorInvalidValue;
+  cuuint64_t dims[2] = {(cuuint64_t)hd, (cuuint64_t)rows};  // head_dim 128: two 64-column boxes per row (the swizzle spans 128 bytes)
+  cuuint64_t strides[1] = {(cuuint64_t)hd * 2};
   cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(reinterpret_cast<CUtensorMap*>(out), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)pool, dims, strides,
