@@ -122,7 +122,9 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const uint32_t s0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   unsigned char* sg = smem_raw + (s0 - smem_u32(smem_raw));
-  const uint32_t bar_s = s0 + SM_BAR, bar_o = bar_s + 8, slot = bar_s + 16, bar_kv = bar_s + 24;  // bar_kv: two (K/V buffer)
+  // mbarriers: S product done (two: TMEM buffer t & 1; the copy path uses the first), P V done, K tile landed (two
+  // buffers), V tile landed (two)
+  const uint32_t bar_s = s0 + SM_BAR, bar_o = bar_s + 16, slot = bar_s + 24, bar_k = bar_s + 32, bar_v = bar_s + 48;
   int* s_pages = reinterpret_cast<int*>(sg + SM_PAGES);
   float* xmax = reinterpret_cast<float*>(sg + SM_X);  // [2][128]
   float* xsum = xmax + 256;                            // [2][128]
@@ -143,13 +145,16 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
 
   if (threadIdx.x == 0) {
     mbar_init_(bar_s, 1);
+    mbar_init_(bar_s + 8, 1);
     mbar_init_(bar_o, 1);
-    mbar_init_(bar_kv, 1);
-    mbar_init_(bar_kv + 8, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init_(bar_k + 8 * i, 1);
+      mbar_init_(bar_v + 8 * i, 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == MMA_WARP) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(256u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot), "r"(512u) : "memory");  // S[2] (2 x 128 columns) + O (128): the next power of two
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   const int n_pg = min(MAXP, (kv_len - 1) / psz + 1);
@@ -196,21 +201,26 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
   // tile_off() puts them -- so the eight softmax warps issue no copy instructions at all.  Chunks behind the last
   // page of the sequence repeat that page (finite values; their keys are masked).
   const int n_kv_pages = (kv_len - 1) / psz + 1;
-  auto tma_tile = [&](int tile, int buf) {  // MMA warp, all lanes
-    const int is_v = lane >> 4, pg = (lane >> 1) & 7, half = lane & 1;
+  auto tma_kv = [&](int tile, int buf, int is_v) {  // MMA warp: lanes 0-15 request the 8 page chunks x 2 column halves of K or V
+    const int pg = (lane >> 1) & 7, half = lane & 1;
     const int pi = min(tile * (TK / 16) + pg, n_kv_pages - 1);
     const int page = pi < MAXP ? s_pages[pi] : bt[pi];
     const int row = (((page * a.kv.n_layers + a.layer) * 2 + is_v) * a.kv.n_kv + kvh) * psz;
     const uint32_t dst = s0 + (is_v ? SM_V0 : SM_K0) + buf * TILE_B + half * BLK + pg * 16 * 128;
-    const uint32_t bar = bar_kv + 8u * (uint32_t)buf;
-    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * TILE_B) : "memory");
+    const uint32_t bar = (is_v ? bar_v : bar_k) + 8u * (uint32_t)buf;
+    if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)TILE_B) : "memory");
     __syncwarp();
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(dst), "l"(&kvm), "r"(bar), "r"(half * 64), "r"(row)
-                 : "memory");
+    if (lane < 16)
+      asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                   ::"r"(dst), "l"(&kvm), "r"(bar), "r"(half * 64), "r"(row)
+                   : "memory");
   };
   if (use_tma) {
-    if (warp == MMA_WARP) tma_tile(0, 0);
+    if (warp == MMA_WARP) {
+      tma_kv(0, 0, 0);
+      tma_kv(0, 0, 1);
+      if (n_tiles > 1) tma_kv(1, 1, 0);
+    }
   } else {
     load_tile(0, 0);
   }
@@ -219,10 +229,9 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
   // the exp + bf16-pack pass 53 us (16 384 ex2 + 8 192 cvt per tile on the 16-lane XU pipe), everything else --
   // tile copies, TMEM loads, row max, O fold, P stores, barriers, CTA prologue/epilogue -- 94 us.  An MN-major V
   // descriptor costs the same as a K-major one.
-  // r02, measured dead end: S in two TMEM buffers with S(t+1) issued before the softmax of tile t and K / V tiles
-  // requested separately (K(t+2) behind S(t), V(t+1) behind P V(t-1)): 17.5 -> 18.5 ms for the 1.5B prefill -- the softmax
-  // warps are the critical path, and the second copy pass (page lookups twice) costs them more than the S latency it hides.
-  // The next step is to take the copies off those warps altogether (K/V by TMA: two 64-column boxes per page chunk).
+  // r02: with the cp.async copies, S in two TMEM buffers / S(t+1) issued before the softmax of tile t was a dead end (17.5 ->
+  // 18.5 ms: the softmax warps are the critical path and a second copy pass cost them more than the S latency it hid);
+  // with K/V by TMA the same schedule is free for them (the TMA path below).
   const uint32_t lbo = (lbo_sbo_swap & 1) ? 1024u : (uint32_t)BLK, sbo = (lbo_sbo_swap & 1) ? (uint32_t)BLK : 1024u;
   constexpr uint32_t ID_S = idesc_(128, 128, false), ID_O = idesc_(128, 128, true);
   const float sl2 = a.scale_log2;
@@ -238,8 +247,8 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
   for (int i = 0; i < 64; ++i) o[i] = 0.f;
   auto fold_o = [&]() {  // o = o * corr + (P V of the last tile), this thread's 64 head-dim columns
     uint32_t r[32], r2[32];
-    tmem_ld32(lane_addr + 128 + 64 * hf, r);
-    tmem_ld32(lane_addr + 128 + 64 * hf + 32, r2);
+    tmem_ld32(lane_addr + 256 + 64 * hf, r);
+    tmem_ld32(lane_addr + 256 + 64 * hf + 32, r2);
     tmem_wait_ld();
 #pragma unroll
     for (int j = 0; j < 32; ++j) o[j] = fmaf(o[j], corr, __uint_as_float(r[j]));
@@ -247,100 +256,137 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
     for (int j = 0; j < 32; ++j) o[32 + j] = fmaf(o[32 + j], corr, __uint_as_float(r2[j]));
   };
 
+  // softmax of tile `it` for this thread's query row / key half: S from TMEM buffer sbuf, P (bf16) -> shared memory
+  auto softmax_tile = [&](int it, int sbuf) {
+    const int p0 = it * TK + 64 * hf;  // first key of this thread's half
+    // ---- this thread's 64 scores stay in registers between the max and the exp pass
+    uint32_t r[32], r2[32];
+    tmem_ld32(lane_addr + (uint32_t)sbuf * 128u + 64 * hf, r);
+    tmem_ld32(lane_addr + (uint32_t)sbuf * 128u + 64 * hf + 32, r2);
+    tmem_wait_ld();
+    const bool need_mask = p0 + 63 > my_pos;
+    float mx = -INFINITY;
+    if (need_mask) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (p0 + j > my_pos) r[j] = 0xff800000u;       // -inf
+        if (p0 + 32 + j > my_pos) r2[j] = 0xff800000u;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r2[j])));
+    xmax[hf * 128 + row] = mx;
+    asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");  // the two warps that share these 32 rows meet
+    const float m_new = fmaxf(m_run, fmaxf(mx, xmax[(hf ^ 1) * 128 + row]));
+    corr = ex2((m_run - m_new) * sl2);
+    m_run = m_new;
+    const float nms = -m_new * sl2;
+    float rs = 0.f;
+    uint32_t pk[32];
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+      const float e0 = ex2(fmaf(__uint_as_float(r[j]), sl2, nms)), e1 = ex2(fmaf(__uint_as_float(r[j + 1]), sl2, nms));
+      const float e2 = ex2(fmaf(__uint_as_float(r2[j]), sl2, nms)), e3 = ex2(fmaf(__uint_as_float(r2[j + 1]), sl2, nms));
+      rs += (e0 + e1) + (e2 + e3);
+      pk[j >> 1] = pack2(f2bf(e0), f2bf(e1));
+      pk[16 + (j >> 1)] = pack2(f2bf(e2), f2bf(e3));
+    }
+#pragma unroll
+    for (int q8 = 0; q8 < 8; ++q8)  // 8 chunks of 8 keys = this half's column block of the P row
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s0 + SM_P + tile_off(row, 8 * hf + q8)), "r"(pk[4 * q8]),
+                   "r"(pk[4 * q8 + 1]), "r"(pk[4 * q8 + 2]), "r"(pk[4 * q8 + 3])
+                   : "memory");
+    l_run = l_run * corr + rs;  // partial sum of this half; the halves are added once at the end
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P (generic stores) -> tensor core
+  };
+  auto issue_s = [&](int t, int sbuf) {  // MMA thread: S(t) = Q K(t)^T into TMEM buffer sbuf
+    const uint32_t kb = s0 + SM_K0 + (t & 1) * TILE_B;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int kk = 0; kk < HDX / 16; ++kk) {
+      const uint32_t ko = (uint32_t)((kk >> 2) * BLK + (kk & 3) * 32);
+      umma_(tmem + (uint32_t)sbuf * 128u, desc_kmajor(s0 + SM_Q + ko), desc_kmajor(kb + ko), ID_S, kk != 0);
+    }
+    umma_commit_(bar_s + 8u * (uint32_t)sbuf);
+  };
+  auto issue_pv = [&](int t) {  // MMA thread: O_t = P V(t)
+    const uint32_t vb = s0 + SM_V0 + (t & 1) * TILE_B;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+    for (int kk = 0; kk < TK / 16; ++kk) {
+      const uint32_t po = (uint32_t)((kk >> 2) * BLK + (kk & 3) * 32);   // P: K-major, K = keys
+      const uint32_t vo = (uint32_t)(kk * 16 * 128);                     // V: 16 keys further down = 2 atoms of 8 rows
+      umma_(tmem + 256, desc_kmajor(s0 + SM_P + po), desc_mnmajor(vb + vo, lbo, sbo), ID_O, kk != 0);
+    }
+    umma_commit_(bar_o);
+  };
+
+  if (use_tma) {
+    // ---- TMA path, software pipeline: S(t+1) goes to the tensor pipe in front of the softmax of tile t (two S buffers in
+    // TMEM); K(t+2) is requested as soon as S(t) is done, V(t+1) as soon as P V(t-1) is done.  The MMA warp does all of
+    // that; the softmax warps only wait for mbarriers.
+    if (warp == MMA_WARP && lane == 0) {
+      mbar_wait_(bar_k, 0);
+      issue_s(0, 0);
+    }
+    for (int it = 0; it < n_tiles; ++it) {
+      const int buf = it & 1;
+      if (warp == MMA_WARP) {
+        if (lane == 0 && it + 1 < n_tiles) {
+          mbar_wait_(bar_k + 8u * (uint32_t)(buf ^ 1), (uint32_t)(((it + 1) >> 1) & 1));  // K(it+1) has landed
+          issue_s(it + 1, buf ^ 1);  // (everybody read S(it-1) out of that buffer in front of the last __syncthreads)
+        }
+        __syncwarp();
+        if (it + 1 < n_tiles) {  // V(it+1) takes the place of V(it-1)
+          if (it > 0) mbar_wait_(bar_o, (uint32_t)((it - 1) & 1));
+          tma_kv(it + 1, buf ^ 1, 1);
+        }
+        if (it + 2 < n_tiles) {  // K(it+2) takes the place of K(it)
+          mbar_wait_(bar_s + 8u * (uint32_t)buf, (uint32_t)((it >> 1) & 1));
+          tma_kv(it + 2, buf, 0);
+        }
+      } else {
+        if (it > 0) {  // fold the previous tile's P V product
+          mbar_wait_(bar_o, (uint32_t)((it - 1) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          fold_o();
+        }
+        mbar_wait_(bar_s + 8u * (uint32_t)buf, (uint32_t)((it >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        softmax_tile(it, buf);
+      }
+      __syncthreads();
+      if (warp == MMA_WARP && lane == 0) {
+        mbar_wait_(bar_v + 8u * (uint32_t)buf, (uint32_t)((it >> 1) & 1));  // V(it) has landed
+        issue_pv(it);
+      }
+    }
+  } else {
   for (int it = 0; it < n_tiles; ++it) {
     const int buf = it & 1;
-    if (!use_tma) {
-      cp_async_wait<0>();  // tile it (requested one iteration ago)
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async (generic proxy) data -> tensor core (async proxy)
-      __syncthreads();
-    }
-    const uint32_t kb = s0 + SM_K0 + buf * TILE_B, vb = s0 + SM_V0 + buf * TILE_B;
-    const uint32_t ph = it & 1;
+    cp_async_wait<0>();  // tile it (requested one iteration ago)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // cp.async (generic proxy) data -> tensor core (async proxy)
+    __syncthreads();
     // ---- S = Q K^T
-    if (warp == MMA_WARP && lane == 0) {
-      if (use_tma) mbar_wait_(bar_kv + 8u * (uint32_t)buf, (uint32_t)((it >> 1) & 1));  // tile it has landed (async proxy: no fence)
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-      for (int kk = 0; kk < HDX / 16; ++kk) {
-        const uint32_t ko = (uint32_t)((kk >> 2) * BLK + (kk & 3) * 32);
-        umma_(tmem, desc_kmajor(s0 + SM_Q + ko), desc_kmajor(kb + ko), ID_S, kk != 0);
-      }
-      umma_commit_(bar_s);
-    }
+    if (warp == MMA_WARP && lane == 0) issue_s(it, 0);
     // Behind the S product (queued right after the previous tile's P V in the tensor pipe): the buffer tile it+1 goes
     // into was read by the P V product of tile it-1, so wait for that MMA, then request the copies.
-    if (use_tma) {
-      if (warp == MMA_WARP) {
-        __syncwarp();
-        if (it > 0) mbar_wait_(bar_o, (uint32_t)((it - 1) & 1));
-        if (it + 1 < n_tiles) tma_tile(it + 1, buf ^ 1);
-      }
-    } else {
-      if (it > 0) mbar_wait_(bar_o, (uint32_t)((it - 1) & 1));
-      if (it + 1 < n_tiles) load_tile(it + 1, buf ^ 1);
-    }
-    const int p0 = it * TK + 64 * hf;  // first key of this thread's half
+    if (it > 0) mbar_wait_(bar_o, (uint32_t)((it - 1) & 1));
+    if (it + 1 < n_tiles) load_tile(it + 1, buf ^ 1);
     if (soft) {
       if (it > 0) {  // fold the previous tile's P V product while the tensor core works on this tile's S
-        if (use_tma) mbar_wait_(bar_o, (uint32_t)((it - 1) & 1));  // (the copy path waited for it in front of its copies)
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         fold_o();
       }
-      mbar_wait_(bar_s, ph);
+      mbar_wait_(bar_s, (uint32_t)(it & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // ---- this thread's 64 scores stay in registers between the max and the exp pass
-      uint32_t r[32], r2[32];
-      tmem_ld32(lane_addr + 64 * hf, r);
-      tmem_ld32(lane_addr + 64 * hf + 32, r2);
-      tmem_wait_ld();
-      const bool need_mask = p0 + 63 > my_pos;
-      float mx = -INFINITY;
-      if (need_mask) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (p0 + j > my_pos) r[j] = 0xff800000u;       // -inf
-          if (p0 + 32 + j > my_pos) r2[j] = 0xff800000u;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fmaxf(__uint_as_float(r[j]), __uint_as_float(r2[j])));
-      xmax[hf * 128 + row] = mx;
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + (warp & 3)) : "memory");  // the two warps that share these 32 rows meet
-      const float m_new = fmaxf(m_run, fmaxf(mx, xmax[(hf ^ 1) * 128 + row]));
-      corr = ex2((m_run - m_new) * sl2);
-      m_run = m_new;
-      const float nms = -m_new * sl2;
-      float rs = 0.f;
-      uint32_t pk[32];
-#pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        const float e0 = ex2(fmaf(__uint_as_float(r[j]), sl2, nms)), e1 = ex2(fmaf(__uint_as_float(r[j + 1]), sl2, nms));
-        const float e2 = ex2(fmaf(__uint_as_float(r2[j]), sl2, nms)), e3 = ex2(fmaf(__uint_as_float(r2[j + 1]), sl2, nms));
-        rs += (e0 + e1) + (e2 + e3);
-        pk[j >> 1] = pack2(f2bf(e0), f2bf(e1));
-        pk[16 + (j >> 1)] = pack2(f2bf(e2), f2bf(e3));
-      }
-#pragma unroll
-      for (int q8 = 0; q8 < 8; ++q8)  // 8 chunks of 8 keys = this half's column block of the P row
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(s0 + SM_P + tile_off(row, 8 * hf + q8)), "r"(pk[4 * q8]),
-                     "r"(pk[4 * q8 + 1]), "r"(pk[4 * q8 + 2]), "r"(pk[4 * q8 + 3])
-                     : "memory");
-      l_run = l_run * corr + rs;  // partial sum of this half; the halves are added once at the end
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // P (generic stores) -> tensor core
+      softmax_tile(it, 0);
     }
     __syncthreads();
     // ---- O_t = P V
-    if (warp == MMA_WARP && lane == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-      for (int kk = 0; kk < TK / 16; ++kk) {
-        const uint32_t po = (uint32_t)((kk >> 2) * BLK + (kk & 3) * 32);   // P: K-major, K = keys
-        const uint32_t vo = (uint32_t)(kk * 16 * 128);                     // V: 16 keys further down = 2 atoms of 8 rows
-        umma_(tmem + 128, desc_kmajor(s0 + SM_P + po), desc_mnmajor(vb + vo, lbo, sbo), ID_O, kk != 0);
-      }
-      umma_commit_(bar_o);
-    }
+    if (warp == MMA_WARP && lane == 0) issue_pv(it);
+  }
   }
   if (soft) {
     mbar_wait_(bar_o, (uint32_t)((n_tiles - 1) & 1));
@@ -366,7 +412,7 @@ __global__ void __launch_bounds__(NTHR, 1) attn_prefill_tc_kernel(FastAttnArgs a
   __syncthreads();
   if (warp == MMA_WARP) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 }
 
