@@ -399,7 +399,7 @@ static void engine_free(qie_engine* e) {
                  e->sampled_d, e->rowstep_d, e->x, e->xn, e->q, e->k, e->v, e->att, e->h, e->logits, e->qkv,
                  e->gemm_ws, e->attn_ws_o, e->attn_ws_ml, e->gemm_counters, e->mega_layers_d, e->mega_cand_d,
                  e->mega_bar_d, e->mega_prof_d, e->mega_wmaps_d[0], e->mega_wmaps_d[1], e->tp_buf, e->tp_cand, e->tp_xbuf, e->x2,
-                 e->mega_wmaps_tp_d[0], e->mega_wmaps_tp_d[1], e->mega_kvmap_d, e->mega_hmap_d};
+                 e->mega_wmaps_tp_d[0], e->mega_wmaps_tp_d[1], e->mega_kvmap_d, e->mega_hmap_d, e->gemv_part_d};
   for (int r = 0; r < MEGA_MAX_TP; ++r)
     if (e->tp_peer_xbuf[r] && e->tp_peer_xbuf[r] != e->tp_xbuf) cudaIpcCloseMemHandle(e->tp_peer_xbuf[r]);
   tp_comm_destroy(&e->tp);
@@ -599,6 +599,11 @@ static int engine_finish_setup(qie_engine* e) {
       CU(cudaMalloc(&e->mega_cand_d, (size_t)e->num_sms * 64 * sizeof(MegaCand)));
       CU(cudaMalloc(&e->mega_bar_d, 4096));  // grid-barrier counters (8 shards on separate lines)
       CU(cudaMalloc(&e->mega_prof_d, (size_t)decode_mega_prof_slots(c.layers) * sizeof(unsigned long long)));
+      CU(cudaMalloc(&e->gemv_part_d, decode_gemv_part_floats(c.n_q, c.head_dim, e->num_sms) * sizeof(float)));
+      {
+        const char* gv = getenv("QIE_GEMV");
+        e->use_gemv = !(gv && gv[0] == '0');
+      }
       if ((I % 64) == 0 && e->h) {  // down_proj operand rows for the tile-split phase (tile set 0: batches > 8)
         TensorMap2D hm;
         if (make_tensor_map_w3d(&hm, e->h, (int)R, (int)I, e->mega_kc[0], 0, 16) == cudaSuccess) {
@@ -1346,6 +1351,7 @@ int qie_engine_set_int(qie_engine* e, const char* key, long value) {
   if (!e || !key) return fail(QIE_EINVAL, "null argument");
   std::string k(key);
   if (k == "mega") e->use_mega = value != 0;
+  else if (k == "gemv") e->use_gemv = value != 0;
   else if (k == "mega_layers_run") e->mega_layers_run = (int)value;
   else if (k == "mega_prof") e->mega_prof_on = value != 0;
   else if (k == "layer_first") e->layer_first = (int)std::max(0l, value);
