@@ -44,17 +44,19 @@ constexpr int GV_NPJ = 7;               // bf16 pairs of a residual row per thre
 constexpr int GV_SMEM_MAX = 227 * 1024;
 
 struct GemvArgs {
-  int n_slots, slot_bytes, off_act, off_ring;
+  int n_slots, slot_bytes, off_act, off_pf, off_ring;
   int n_split;   // KV splits per (row, q head)
   float* part;   // [tasks][hd + 2] partial attention results: max, sum, o[hd]
 };
 
 // shared-memory header
-constexpr int GO_FULL = 0, GO_EMPTY = 128, GO_RED = 256, GO_CAND = 512, GO_LAYERS = 1024;
+constexpr int GO_FULL = 0, GO_EMPTY = 128, GO_RED = 256, GO_DBG = 512, GO_CAND = 640, GO_RANGE = 1152, GO_ZERO = 1248, GO_LAYERS = 1280;  // GO_DBG: 16 x u64 cycle counters (profiled launches)
 constexpr int GO_XS = GO_LAYERS + GV_MAX_LAYERS * (int)sizeof(MegaLayer);  // residual rows [B][H] bf16
 // attention scratch inside the activation area
-constexpr int GA_Q = 0, GA_K = 256, GA_V = 512, GA_SCORE = 768, GA_PAGES = GA_SCORE + GV_PT * 4,
-              GA_PV = GA_PAGES + (GV_PT + 16) * 4, GA_END = GA_PV + GV_CW * 128 * 4;
+constexpr int GA_Q = 0, GA_K = 256, GA_V = 512, GA_SCORE = 768, GA_PV = GA_SCORE + GV_PT * 4, GA_END = GA_PV + GV_CW * 128 * 4;
+// staged in front of the QKV phase (outside the activation area): cos + sin row, q/k-norm weights, the task's page list
+constexpr int GP_COS = 0, GP_NW = 512, GP_PAGES = 1024, GP_END = GP_PAGES + (GV_PT + 16) * 4;
+constexpr int GV_MAX_SPLIT = 12;
 
 __device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
@@ -98,6 +100,26 @@ __device__ __forceinline__ unsigned long long globaltimer() {
   return t;
 }
 // grid barrier of the consumer warps (see decode_mega.cu grid_sync: release add + acquire poll)
+// split in two: loads that the next phases need and that do not depend on other CTAs are issued BETWEEN the arrival and
+// the wait -- in front of the arrival they would sit in front of the release fence (measured: +1 us per barrier)
+__device__ __forceinline__ void grid_arrive(unsigned* ctr, unsigned& epoch) {
+  bar_consumers();
+  if (threadIdx.x == 0) {
+    epoch += gridDim.x;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+  }
+}
+__device__ __forceinline__ void grid_wait(unsigned* ctr, unsigned epoch) {
+  if (threadIdx.x == 0) {
+    unsigned v;
+    const long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+      if (clock64() - t0 > GV_SPIN_LIMIT) __trap();
+    } while (v < epoch);
+  }
+  bar_consumers();
+}
 __device__ __forceinline__ void grid_sync(unsigned* ctr, unsigned& epoch) {
   bar_consumers();
   if (threadIdx.x == 0) {
@@ -140,7 +162,7 @@ struct GPhase {
   const bf16* w2;  // up_proj rows travel with the gate_proj rows of the same index
   int K, rows, ch; // ch: rows (row pairs) per ring slot
 };
-__device__ __forceinline__ void gv_phase(const MegaArgs& a, const GemvArgs& g, const MegaLayer* layers, int kind, int l, GPhase& p) {
+__device__ __forceinline__ void gv_phase(const MegaArgs& a, const unsigned char* smem, const MegaLayer* layers, int kind, int l, GPhase& p) {
   const int Dq = a.n_q * a.hd, Dkv = a.n_kv * a.hd;
   p.w2 = nullptr;
   p.nseg = 1;
@@ -180,25 +202,40 @@ __device__ __forceinline__ void gv_phase(const MegaArgs& a, const GemvArgs& g, c
       break;
   }
   if (p.nseg == 1) p.seg_rows[0] = p.rows;
-  p.ch = max(1, g.slot_bytes / (p.K * 2 * (p.w2 ? 2 : 1)));
+  p.ch = reinterpret_cast<const int*>(smem + GO_RANGE)[10 + kind];
 }
-// rows [r0, r1) of a phase that CTA c owns (contiguous, sizes differ by at most one)
-__device__ __forceinline__ void gv_range(int rows, int& r0, int& r1) {
-  r0 = (int)((long long)blockIdx.x * rows / gridDim.x);
-  r1 = (int)((long long)(blockIdx.x + 1) * rows / gridDim.x);
+// rows [r0, r1) of a phase kind that CTA c owns (contiguous, sizes differ by at most one).  The same for every layer:
+// computed once at kernel start (two 64-bit divisions per call cost ~1 us per phase on the token's critical path).
+__device__ __forceinline__ void gv_range_init(const MegaArgs& a, const GemvArgs& g, unsigned char* smem) {
+  if (threadIdx.x < 5) {
+    const int Dq = a.n_q * a.hd, Dkv = a.n_kv * a.hd;
+    const int k = threadIdx.x;
+    const long long rows = k == PH_QKV ? Dq + 2 * Dkv : (k == PH_O || k == PH_DOWN ? a.H : (k == PH_GATEUP ? a.I : a.V));
+    int* rg = reinterpret_cast<int*>(smem + GO_RANGE);
+    rg[2 * k] = (int)((long long)blockIdx.x * rows / gridDim.x);
+    rg[2 * k + 1] = (int)((long long)(blockIdx.x + 1) * rows / gridDim.x);
+    const int K = k == PH_O ? Dq : (k == PH_DOWN ? a.I : a.H);
+    rg[10 + k] = max(1, g.slot_bytes / (K * 2 * (k == PH_GATEUP ? 2 : 1)));  // rows (row pairs) per ring slot
+  }
+}
+__device__ __forceinline__ void gv_range(const unsigned char* smem, int kind, int& r0, int& r1) {
+  const int* rg = reinterpret_cast<const int*>(smem + GO_RANGE);
+  r0 = rg[2 * kind];
+  r1 = rg[2 * kind + 1];
 }
 
 // ---------------------------------------------------------------- producer: the weight stream of this CTA
-__device__ __forceinline__ void gv_producer(const MegaArgs& a, const GemvArgs& g, uint32_t smem_base, const MegaLayer* layers) {
+__device__ __forceinline__ void gv_producer(const MegaArgs& a, const GemvArgs& g, const unsigned char* smem, uint32_t smem_base,
+                                            const MegaLayer* layers) {
   if ((threadIdx.x & 31) != 0) return;
   uint32_t slot = 0, round = 0;
   const int nph = 4 * a.L + 1;
   for (int idx = 0; idx < nph; ++idx) {
     const int kind = idx < 4 * a.L ? (idx & 3) : PH_LMHEAD;
     GPhase p;
-    gv_phase(a, g, layers, kind, idx >> 2, p);
+    gv_phase(a, smem, layers, kind, idx >> 2, p);
     int r0, r1;
-    gv_range(p.rows, r0, r1);
+    gv_range(smem, kind, r0, r1);
     const uint32_t row_bytes = (uint32_t)p.K * 2u;
     for (int r = r0; r < r1; r += p.ch) {
       const int n = min(p.ch, r1 - r);
@@ -233,74 +270,121 @@ struct GvBest {
 };
 struct GvRing {
   uint32_t slot, round;
-  int rot;  // rows dealt so far modulo the half-warps: row i of a chunk goes to half-warp (rot + i) % GV_HW
+  int rot;  // items dealt so far modulo the consumer warps: item i of a chunk goes to warp (rot + i) % GV_CW
 };
 
 // ---------------------------------------------------------------- consumers: one GEMV phase
 // act: [NB][K] bf16 in shared memory.  KIND selects the epilogue.
+// A warp owns an ITEM = R weight rows that share the activation loads (gate/up: two gate rows and their two up rows;
+// lm_head: four neighbouring rows; else two): 32 lanes x 16 bytes per step, the loads of G steps issued in one batch
+// in front of their FMAs.  The step is bound by the length of a warp's dependent instruction stream, not by issue
+// slots or shared-memory bandwidth, so the per-row overhead is what counts: lanes beyond the row read the
+// weights of step 0 against a block of zeros instead of being predicated (no register clearing), and the R sums of a
+// lane are reduced together -- every exchange halves the values a lane carries; in the end lanes 8 g + i hold row g.
 template <int NB, int KIND>
 __device__ __forceinline__ void gv_gemv(const MegaArgs& a, const GemvArgs& g, const GPhase& p, unsigned char* smem, uint32_t smem_base,
                                         GvRing& ring, const unsigned char* act, GvBest& best) {
   constexpr bool PAIR = KIND == PH_GATEUP;
+  constexpr int R = (PAIR || KIND == PH_LMHEAD) ? 4 : 2;  // weight rows per item
+  constexpr int RI = PAIR ? 2 : R;                         // output rows (row pairs) per item
+  constexpr int G = R * NB > 4 ? 2 : 4;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int hw = warp * 2 + (lane >> 4), l16 = lane & 15;
-  const unsigned hmask = 0xffffu << (lane & 16);
   const int K = p.K, nv = K >> 3;
   const uint32_t row_bytes = (uint32_t)K * 2u;
   const bf16* xs = reinterpret_cast<const bf16*>(smem + GO_XS);
+  const uint4* zero4 = reinterpret_cast<const uint4*>(smem + GO_ZERO);
   int r0, r1;
-  gv_range(p.rows, r0, r1);
+  gv_range(smem, KIND, r0, r1);
+  const bool dbg_on = a.prof && blockIdx.x == 0 && threadIdx.x == 0;
+  long long t_in = 0, t_wait = 0;
+  if (dbg_on) t_in = clock64();
   for (int r = r0; r < r1; r += p.ch) {
     const int n = min(p.ch, r1 - r);
-    mbar_wait(smem_base + GO_FULL + ring.slot * 8, ring.round & 1);
+    if (a.prof) {  // warp-uniform: a lane on its own path would be measured apart from the lanes that really wait
+      const long long t0 = clock64();
+      mbar_wait(smem_base + GO_FULL + ring.slot * 8, ring.round & 1);
+      t_wait += clock64() - t0;
+    } else {
+      mbar_wait(smem_base + GO_FULL + ring.slot * 8, ring.round & 1);
+    }
     const unsigned char* base = smem + g.off_ring + ring.slot * g.slot_bytes;
-    int i = hw - ring.rot;
-    if (i < 0) i += GV_HW;
-    for (; i < n; i += GV_HW) {
-      const uint4* wr = reinterpret_cast<const uint4*>(base + (size_t)i * row_bytes);
-      const uint4* wr2 = reinterpret_cast<const uint4*>(base + (size_t)(n + i) * row_bytes);
-      float c[NB][4], c2[PAIR ? NB : 1][4];
+    const int items = (n + RI - 1) / RI;
+    int it = warp - ring.rot;
+    if (it < 0) it += GV_CW;
+#ifdef GV_EXP_SKIP
+    if (KIND == PH_GATEUP) it = items;
+#endif
+    for (; it < items; it += GV_CW) {
+      // rows of the item inside the chunk (a short tail repeats the last row, results dropped)
+      const uint4* wr[R];
 #pragma unroll
-      for (int b = 0; b < NB; ++b)
+      for (int q = 0; q < R; ++q) {
+        const int row = PAIR ? ((q & 1) ? n : 0) + min(RI * it + (q >> 1), n - 1) : min(R * it + q, n - 1);
+        wr[q] = reinterpret_cast<const uint4*>(base + (size_t)row * row_bytes);
+      }
+      float c[R][NB][4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) c[b][k] = 0.f;
+      for (int q = 0; q < R; ++q)
 #pragma unroll
-      for (int b = 0; b < (PAIR ? NB : 1); ++b)
+        for (int b = 0; b < NB; ++b)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) c2[b][k] = 0.f;
-#pragma unroll 4
-      for (int v = l16; v < nv; v += 16) {
-        const uint4 w = wr[v];
-        uint4 w2 = make_uint4(0u, 0u, 0u, 0u);
-        if (PAIR) w2 = wr2[v];
+          for (int k = 0; k < 4; ++k) c[q][b][k] = 0.f;
+      for (int v0 = lane; v0 < nv; v0 += 32 * G) {
+        uint4 w[R][G];
+        int vv[G];
+        bool ok[G];
+#pragma unroll
+        for (int u = 0; u < G; ++u) {
+          ok[u] = v0 + 32 * u < nv;
+          vv[u] = ok[u] ? v0 + 32 * u : lane;
+#pragma unroll
+          for (int q = 0; q < R; ++q) w[q][u] = wr[q][vv[u]];
+        }
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-          const uint4 x = reinterpret_cast<const uint4*>(act + (size_t)b * row_bytes)[v];
-          dot8(c[b], w, x);
-          if (PAIR) dot8(c2[b], w2, x);
+          uint4 x[G];
+#pragma unroll
+          for (int u = 0; u < G; ++u) x[u] = *(ok[u] ? reinterpret_cast<const uint4*>(act + (size_t)b * row_bytes) + vv[u] : zero4);
+#pragma unroll
+          for (int u = 0; u < G; ++u)
+#pragma unroll
+            for (int q = 0; q < R; ++q) dot8(c[q][b], w[q][u], x[u]);
         }
       }
-      float s[NB], s2[NB];
+      // reduce R sums per lane: exchanges at distance 16 (and 8 for R = 4) halve the values carried, then a butterfly
+      float s[NB];
 #pragma unroll
       for (int b = 0; b < NB; ++b) {
-        s[b] = (c[b][0] + c[b][1]) + (c[b][2] + c[b][3]);
-        s2[b] = PAIR ? (c2[b][0] + c2[b][1]) + (c2[b][2] + c2[b][3]) : 0.f;
+        float t[R];
 #pragma unroll
-        for (int o = 8; o > 0; o >>= 1) {
-          s[b] += __shfl_xor_sync(hmask, s[b], o);
-          if (PAIR) s2[b] += __shfl_xor_sync(hmask, s2[b], o);
+        for (int q = 0; q < R; ++q) t[q] = (c[q][b][0] + c[q][b][1]) + (c[q][b][2] + c[q][b][3]);
+        const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0;
+        if (R == 4) {
+          const float k0 = h16 ? t[2] : t[0], k1 = h16 ? t[3] : t[1];
+          const float g0 = h16 ? t[0] : t[2], g1 = h16 ? t[1] : t[3];
+          const float u0 = k0 + __shfl_xor_sync(0xffffffffu, g0, 16), u1 = k1 + __shfl_xor_sync(0xffffffffu, g1, 16);
+          s[b] = (h8 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, h8 ? u0 : u1, 8);
+        } else {
+          const float u0 = (h16 ? t[1] : t[0]) + __shfl_xor_sync(0xffffffffu, h16 ? t[0] : t[1], 16);
+          s[b] = u0 + __shfl_xor_sync(0xffffffffu, u0, 8);
         }
       }
-      // lane b of the half-warp finishes row b of the batch
-      float v1 = 0.f, v2 = 0.f;
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) s[b] += __shfl_xor_sync(0xffffffffu, s[b], o);
+      // R = 4: lanes 8 q + i hold weight row q; R = 2: lanes 16 q + i.  Lane i < B of a group finishes batch row i.
+      float v1 = 0.f;
 #pragma unroll
       for (int b = 0; b < NB; ++b)
-        if (l16 == b) {
-          v1 = s[b];
-          v2 = s2[b];
-        }
-      if (l16 < a.B) {
-        const int b = l16, gr = r + i;
+        if ((lane & 7) == b) v1 = s[b];
+      float v2 = 0.f;
+      if (PAIR) v2 = __shfl_xor_sync(0xffffffffu, v1, 8);  // the up_proj sum next to the gate_proj sum
+      const int q = R == 4 ? lane >> 3 : lane >> 4;          // weight row of the item this lane finishes
+      const int orow = PAIR ? RI * it + (q >> 1) : R * it + q;  // output row (pair) inside the chunk
+      const bool mine = (lane & (R == 4 ? 7 : 15)) < a.B && orow < n && (!PAIR || (q & 1) == 0);
+      if (mine) {
+        const int b = lane & 7, gr = r + orow;
         const float y = bf2f(f2bf(v1));  // the projection output as the reference stores it (matrix_mul.cu: bf16)
         if (KIND == PH_QKV) {
           a.qkv[(size_t)b * p.rows + gr] = f2bf(v1);
@@ -320,11 +404,16 @@ __device__ __forceinline__ void gv_gemv(const MegaArgs& a, const GemvArgs& g, co
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_base + GO_EMPTY + ring.slot * 8);
-    ring.rot = (ring.rot + n) % GV_HW;
+    ring.rot = (ring.rot + items) % GV_CW;
     if (++ring.slot == (uint32_t)g.n_slots) {
       ring.slot = 0;
       ++ring.round;
     }
+  }
+  if (dbg_on) {
+    unsigned long long* dbg = reinterpret_cast<unsigned long long*>(smem + GO_DBG);
+    dbg[2 * KIND] += (unsigned long long)t_wait;
+    dbg[2 * KIND + 1] += (unsigned long long)(clock64() - t_in);
   }
 }
 
@@ -393,8 +482,109 @@ __device__ __forceinline__ void gv_load_norm(const MegaArgs& a, unsigned char* s
 }
 
 // ---------------------------------------------------------------- attention: split-KV flash decoding
+struct GvTask {
+  int b, h, sp, kvh, ps, p0, p1, pc1, pg0;
+  bool has_new;
+};
 template <int NP>
-__device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& g, int layer, unsigned char* smem, const MegaLayer& w) {
+__device__ __forceinline__ bool gv_task(const MegaArgs& a, const GemvArgs& g, int task, int psh, GvTask& t) {
+  const int S = g.n_split, Gq = a.n_q / a.n_kv, psz = a.kv.page_size;
+  t.b = task / (a.n_q * S);
+  const int rem = task - t.b * a.n_q * S;
+  t.h = rem / S;
+  t.sp = rem - t.h * S;
+  t.kvh = t.h / Gq;
+  t.ps = a.pos[t.b];
+  const int npos = t.ps + 1, len = (npos + S - 1) / S;
+  t.p0 = min(npos, t.sp * len);
+  t.p1 = min(npos, t.p0 + len);
+  t.has_new = t.p1 == npos;               // the split holds the position this step appends
+  t.pc1 = t.has_new ? t.p1 - 1 : t.p1;    // cached positions [p0, pc1)
+  t.pg0 = psh >= 0 ? (t.p0 >> psh) : t.p0 / psz;
+  return t.p0 < t.p1;
+}
+// Everything of a task that does not depend on this step's q / k / v, staged outside the activation area:
+//   ST_STEP  (once per kernel for the CTA's task when every CTA has at most one): page list, cos / sin row
+//   ST_LAYER (in front of the QKV phase of every layer): q/k-norm weights, and the cached K / V rows requested into L2 --
+//            they were written a token ago and ~1 GB of weights has passed through L2 since: a plain load behind the
+//            grid barrier would be a DRAM + TLB miss on the token's critical path
+enum { ST_STEP = 1, ST_LAYER = 2, ST_PREFETCH = 4 };
+template <int NP>
+__device__ __forceinline__ void gv_attn_stage(const MegaArgs& a, const GemvArgs& g, int layer, unsigned char* smem, const MegaLayer& w,
+                                              const GvTask& t, int psh, int what) {
+  constexpr int HD = 64 * NP;
+  const int psz = a.kv.page_size;
+  unsigned char* pf = smem + g.off_pf;
+  float* cs = reinterpret_cast<float*>(pf + GP_COS);
+  uint32_t* nw = reinterpret_cast<uint32_t*>(pf + GP_NW);
+  int* pages = reinterpret_cast<int*>(pf + GP_PAGES);
+  const int tid = threadIdx.x;
+  const int pgn = t.pc1 > t.p0 ? (psh >= 0 ? ((t.pc1 - 1) >> psh) : (t.pc1 - 1) / psz) - t.pg0 + 1 : 0;
+  if (what & ST_STEP) {
+    if (tid < 64 * NP) {  // cos row then sin row: 32 * NP floats each
+      const int k = tid < 32 * NP ? tid : tid - 32 * NP;
+      cs[tid] = __ldg((tid < 32 * NP ? a.cos_t : a.sin_t) + (size_t)t.ps * 32 * NP + k);
+    }
+    const int* bt = a.block_table + (size_t)a.slot[t.b] * a.max_pages;
+    for (int i = tid; i < pgn; i += GV_CT) pages[i] = bt[t.pg0 + i];
+  }
+  if (what & ST_LAYER) {
+    if (tid >= 128 && tid < 128 + 64 * NP) {  // q_norm then k_norm weights as bf16 pairs: 32 * NP words each
+      const int k = tid - 128, kk = k < 32 * NP ? k : k - 32 * NP;
+      const bf16* src = k < 32 * NP ? w.q_norm : w.k_norm;
+      nw[k] = src ? __ldg(reinterpret_cast<const uint32_t*>(src) + kk) : 0u;
+    }
+  }
+  if (what & ST_PREFETCH) {  // needs the page list in shared memory (ST_STEP + a barrier before)
+    const int rows = t.pc1 - t.p0, per = HD / 64;  // 128-byte lines per row
+    for (int i = tid; i < rows * per * 2; i += GV_CT) {
+      const int kv = i & 1, j = i >> 1, rr = j / per, ln = j - rr * per, pp = t.p0 + rr;
+      const int pi = psh >= 0 ? (pp >> psh) : pp / psz;
+      const bf16* src = a.kv.chunk(pages[pi - t.pg0], layer, kv, t.kvh) + (size_t)(pp - pi * psz) * HD + ln * 64;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+    }
+  }
+}
+
+// the first 4 * NG cached positions of a task's K and V rows, 16 bytes per lane and position: element offsets inside
+// (layer 0, K) computed once per step, one 64-bit add per load afterwards
+template <int NP>
+struct GvPre {
+  size_t off[4];   // element offset of this lane's piece of position base + u * NG + grp; ~0 = beyond the task
+  uint4 k[4], v[4];
+};
+template <int NP>
+__device__ __forceinline__ void gv_pre_offsets(const MegaArgs& a, const int* pages, const GvTask& t, int psh, GvPre<NP>& pre) {
+  constexpr int HD = 64 * NP, LPP = HD / 8, GPW = 32 / LPP, NG = GV_CW * GPW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = warp * GPW + lane / LPP, j = lane % LPP, psz = a.kv.page_size;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int p = t.p0 + u * NG + grp;
+    pre.off[u] = ~(size_t)0;
+    if (p < t.pc1) {
+      const int pi = psh >= 0 ? (p >> psh) : p / psz;
+      pre.off[u] = (size_t)(a.kv.chunk(pages[pi - t.pg0], 0, 0, t.kvh) - a.kv.pool) + (size_t)(p - pi * psz) * HD + j * 8;
+    }
+  }
+}
+template <int NP>
+__device__ __forceinline__ void gv_pre_load(const MegaArgs& a, int layer, GvPre<NP>& pre) {
+  const bf16* kb = a.kv.pool + (size_t)layer * a.kv.layer_stride();
+  const bf16* vb = kb + a.kv.kv_stride();
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    pre.k[u] = pre.v[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (pre.off[u] != ~(size_t)0) {
+      pre.k[u] = ld_nc_v4(kb + pre.off[u]);
+      pre.v[u] = ld_nc_v4(vb + pre.off[u]);
+    }
+  }
+}
+
+template <int NP>
+__device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& g, int layer, unsigned char* smem, const MegaLayer& w,
+                                             GvPre<NP>& pre, bool preloaded) {
   constexpr int HD = 64 * NP, LPP = HD / 8, GPW = 32 / LPP, NG = GV_CW * GPW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = warp * GPW + lane / LPP, j = lane % LPP;
@@ -409,17 +599,21 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
   bf16* knew = reinterpret_cast<bf16*>(sc + GA_K);
   bf16* vnew = reinterpret_cast<bf16*>(sc + GA_V);
   float* score = reinterpret_cast<float*>(sc + GA_SCORE);
-  int* pages = reinterpret_cast<int*>(sc + GA_PAGES);
   float* pv = reinterpret_cast<float*>(sc + GA_PV);
   float* red = reinterpret_cast<float*>(smem + GO_RED);
+  unsigned char* pf = smem + g.off_pf;
+  const float* cos_s = reinterpret_cast<const float*>(pf + GP_COS);
+  const float* sin_s = cos_s + 32 * NP;
+  const bf16* qnw = reinterpret_cast<const bf16*>(pf + GP_NW);
+  const bf16* knw = qnw + 64 * NP;
+  const int* pages = reinterpret_cast<const int*>(pf + GP_PAGES);
   const float rs = 1.0f / sqrtf((float)HD);
   for (int task = blockIdx.x; task < ntask; task += gridDim.x) {
-    const int b = task / (a.n_q * S), rem = task - b * a.n_q * S, h = rem / S, sp = rem - h * S, kvh = h / Gq;
-    const int ps = a.pos[b], npos = ps + 1;
-    const int len = (npos + S - 1) / S;
-    const int p0 = min(npos, sp * len), p1 = min(npos, p0 + len);
-    float* part = g.part + (size_t)((b * a.n_q + h) * S + sp) * (HD + 2);
-    if (p0 >= p1) {  // empty split
+    GvTask t;
+    const bool any = gv_task<NP>(a, g, task, psh, t);
+    const int b = t.b, h = t.h, kvh = t.kvh, ps = t.ps, p0 = t.p0, p1 = t.p1, pc1 = t.pc1, pg0 = t.pg0;
+    float* part = g.part + (size_t)((b * a.n_q + h) * S + t.sp) * (HD + 2);
+    if (!any) {  // empty split (S > 1 only)
       if (threadIdx.x < HD) part[2 + threadIdx.x] = 0.f;
       if (threadIdx.x == 0) {
         part[0] = -CUDART_INF_F;
@@ -427,14 +621,49 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
       }
       continue;
     }
-    const bool has_new = p1 == npos;  // the split holds the position this step appends
+    const bool dbg_on = a.prof && blockIdx.x == 0 && threadIdx.x == 0;
+    unsigned long long* dbg = reinterpret_cast<unsigned long long*>(smem + GO_DBG);
+    long long tq = 0;
+    if (dbg_on) tq = clock64();
+    auto lap = [&](int k) {
+      if (dbg_on) {
+        const long long tt = clock64();
+        dbg[10 + k] += (unsigned long long)(tt - tq);
+        tq = tt;
+      }
+    };
+    if (ntask > (int)gridDim.x) {  // several tasks per CTA: nothing was staged ahead
+      gv_attn_stage<NP>(a, g, layer, smem, w, t, psh, ST_STEP | ST_LAYER);
+      bar_consumers();
+    }
+    const bool has_new = t.has_new;
     const bool writer = has_new && h == kvh * Gq;
-    const int pc1 = has_new ? p1 - 1 : p1;  // cached positions [p0, pc1)
     const int* bt = a.block_table + (size_t)a.slot[b] * a.max_pages;
-    const int pg0 = psh >= 0 ? (p0 >> psh) : p0 / psz;
     const bf16* row = a.qkv + (size_t)b * QKV;
-    const float* cos_row = a.cos_t + (size_t)ps * 32 * NP;
-    const float* sin_row = a.sin_t + (size_t)ps * 32 * NP;
+    // the first 4 * NG cached positions of K and V: requested before anything that depends on this step's q
+    auto load4 = [&](int base, int kv, uint4 (&r4)[4]) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int p = base + u * NG + grp;
+        r4[u] = make_uint4(0u, 0u, 0u, 0u);
+        if (p < pc1) {
+          const int pi = psh >= 0 ? (p >> psh) : p / psz;
+          r4[u] = ld_nc_v4(a.kv.chunk(pages[pi - pg0], layer, kv, kvh) + (size_t)(p - pi * psz) * HD + j * 8);
+        }
+      }
+    };
+    uint4 kr[4], vr[4];
+    if (preloaded) {  // requested in the shadow of the grid barrier in front of this phase
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        kr[u] = pre.k[u];
+        vr[u] = pre.v[u];
+      }
+    } else {
+      load4(p0, 0, kr);
+      load4(p0, 1, vr);
+    }
+    lap(4);
     if (warp == 0) {
       float v[NP][2];
 #pragma unroll
@@ -443,8 +672,8 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
         v[p][0] = lo2f(u);
         v[p][1] = hi2f(u);
       }
-      if (w.q_norm) head_norm<NP>(v, w.q_norm, lane);
-      head_rope<NP>(v, cos_row, sin_row, lane);
+      if (w.q_norm) head_norm<NP>(v, qnw, lane);
+      head_rope<NP>(v, cos_s, sin_s, lane);
       head_store<NP>(v, q_s, lane);
     } else if (warp == 1) {
       if (has_new) {
@@ -455,8 +684,8 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
           v[p][0] = lo2f(u);
           v[p][1] = hi2f(u);
         }
-        if (w.k_norm) head_norm<NP>(v, w.k_norm, lane);
-        head_rope<NP>(v, cos_row, sin_row, lane);
+        if (w.k_norm) head_norm<NP>(v, knw, lane);
+        head_rope<NP>(v, cos_s, sin_s, lane);
         head_store<NP>(v, knew, lane);
         if (writer) head_store<NP>(v, a.kv.chunk(bt[ps / psz], layer, 0, kvh) + (size_t)(ps % psz) * HD, lane);
       }
@@ -470,25 +699,15 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
             reinterpret_cast<uint32_t*>(a.kv.chunk(bt[ps / psz], layer, 1, kvh) + (size_t)(ps % psz) * HD)[32 * p + lane] = u;
         }
       }
-    } else if (pc1 > p0) {
-      const int pgn = (psh >= 0 ? ((pc1 - 1) >> psh) : (pc1 - 1) / psz) - pg0 + 1;
-      for (int i = threadIdx.x - 96; i < pgn; i += GV_CT - 96) pages[i] = bt[pg0 + i];
     }
+    lap(5);
     bar_consumers();
+    lap(0);
     // ---- scores: LPP lanes per cached position, 16 bytes of the row each
     const uint4 qv = reinterpret_cast<const uint4*>(q_s)[j];
     float mx = -CUDART_INF_F;
     for (int base = p0; base < pc1; base += 4 * NG) {
-      uint4 kr[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int p = base + u * NG + grp;
-        kr[u] = make_uint4(0u, 0u, 0u, 0u);
-        if (p < pc1) {
-          const int pi = psh >= 0 ? (p >> psh) : p / psz;
-          kr[u] = ld_nc_v4(a.kv.chunk(pages[pi - pg0], layer, 0, kvh) + (size_t)(p - pi * psz) * HD + j * 8);
-        }
-      }
+      if (base > p0) load4(base, 0, kr);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int p = base + u * NG + grp;
@@ -517,6 +736,7 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
     mx = warp_max(mx);
     if (lane == 0) red[warp] = mx;
     bar_consumers();
+    lap(1);
     float M = red[0];
 #pragma unroll
     for (int w8 = 1; w8 < GV_CW; ++w8) M = fmaxf(M, red[w8]);
@@ -531,36 +751,28 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
     ls = warp_sum(ls);
     if (lane == 0) red[GV_CW + warp] = ls;
     bar_consumers();
+    lap(2);
     // ---- PV: the same position groups, 8 output columns per lane
     float o8[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) o8[k] = 0.f;
-    auto fold = [&](const uint4& vr, float e) {
-      o8[0] = fmaf(e, lo2f(vr.x), o8[0]);
-      o8[1] = fmaf(e, hi2f(vr.x), o8[1]);
-      o8[2] = fmaf(e, lo2f(vr.y), o8[2]);
-      o8[3] = fmaf(e, hi2f(vr.y), o8[3]);
-      o8[4] = fmaf(e, lo2f(vr.z), o8[4]);
-      o8[5] = fmaf(e, hi2f(vr.z), o8[5]);
-      o8[6] = fmaf(e, lo2f(vr.w), o8[6]);
-      o8[7] = fmaf(e, hi2f(vr.w), o8[7]);
+    auto fold = [&](const uint4& vv, float e) {
+      o8[0] = fmaf(e, lo2f(vv.x), o8[0]);
+      o8[1] = fmaf(e, hi2f(vv.x), o8[1]);
+      o8[2] = fmaf(e, lo2f(vv.y), o8[2]);
+      o8[3] = fmaf(e, hi2f(vv.y), o8[3]);
+      o8[4] = fmaf(e, lo2f(vv.z), o8[4]);
+      o8[5] = fmaf(e, hi2f(vv.z), o8[5]);
+      o8[6] = fmaf(e, lo2f(vv.w), o8[6]);
+      o8[7] = fmaf(e, hi2f(vv.w), o8[7]);
     };
     for (int base = p0; base < pc1; base += 4 * NG) {
-      uint4 vr[4];
-      float e4[4];
+      if (base > p0) load4(base, 1, vr);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int p = base + u * NG + grp;
-        vr[u] = make_uint4(0u, 0u, 0u, 0u);
-        e4[u] = 0.f;
-        if (p < pc1) {
-          const int pi = psh >= 0 ? (p >> psh) : p / psz;
-          vr[u] = ld_nc_v4(a.kv.chunk(pages[pi - pg0], layer, 1, kvh) + (size_t)(p - pi * psz) * HD + j * 8);
-          e4[u] = score[p - p0];
-        }
+        fold(vr[u], p < pc1 ? score[p - p0] : 0.f);
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) fold(vr[u], e4[u]);
     }
     if (has_new && grp == 0) fold(reinterpret_cast<const uint4*>(vnew)[j], score[ps - p0]);
 #pragma unroll
@@ -573,46 +785,68 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
     }
     bar_consumers();
     if (threadIdx.x < HD) {
-      float t = 0.f;
+      float tt = 0.f, l = 0.f;
 #pragma unroll
-      for (int w8 = 0; w8 < GV_CW; ++w8) t += pv[w8 * HD + threadIdx.x];
-      part[2 + threadIdx.x] = t;
-    }
-    if (threadIdx.x == 0) {
-      float l = 0.f;
-#pragma unroll
-      for (int w8 = 0; w8 < GV_CW; ++w8) l += red[GV_CW + w8];
-      part[0] = M;
-      part[1] = l;
+      for (int w8 = 0; w8 < GV_CW; ++w8) {
+        tt += pv[w8 * HD + threadIdx.x];
+        l += red[GV_CW + w8];
+      }
+      if (S == 1) {
+        a.att[(size_t)b * Dq + (size_t)h * HD + threadIdx.x] = f2bf(tt / l);  // self_attension.cu:137: rounded once
+      } else {
+        part[2 + threadIdx.x] = tt;
+        if (threadIdx.x == 0) {
+          part[0] = M;
+          part[1] = l;
+        }
+      }
     }
     bar_consumers();  // the scratch is reused by the next task
+    lap(3);
   }
 }
 
-// attention output rows [B][Dq] bf16 (self_attension.cu:137: rounded once) from the tasks' partial results
+// attention output rows [B][Dq] bf16 (self_attension.cu:137: rounded once) from the tasks' partial results (S > 1):
+// all S loads of two outputs are in flight together (one L2 round trip per pair instead of 2 S dependent ones)
 __device__ __forceinline__ void gv_load_att(const MegaArgs& a, const GemvArgs& g, unsigned char* smem) {
-  const int HD = a.hd, Dq = a.n_q * HD, S = g.n_split;
+  const int HD = a.hd, Dq = a.n_q * HD, S = g.n_split, stride = HD + 2;
   bf16* att = reinterpret_cast<bf16*>(smem + g.off_act);
-  for (int e = threadIdx.x; e < a.B * Dq; e += GV_CT) {
-    const int b = e / Dq, r = e - b * Dq, h = r / HD, d = r - h * HD;
-    const float* pp = g.part + (size_t)((b * a.n_q + h) * S) * (HD + 2);
-    float o;
-    if (S == 1) {
-      o = __ldcg(pp + 2 + d) / __ldcg(pp + 1);
-    } else {
-      float M = -CUDART_INF_F;
-      for (int s = 0; s < S; ++s) M = fmaxf(M, __ldcg(pp + s * (HD + 2)));
-      float L = 0.f;
-      o = 0.f;
-      for (int s = 0; s < S; ++s) {
-        const float m = __ldcg(pp + s * (HD + 2));
-        const float wgt = m == -CUDART_INF_F ? 0.f : __expf(m - M);
-        L += __ldcg(pp + s * (HD + 2) + 1) * wgt;
-        o += __ldcg(pp + s * (HD + 2) + 2 + d) * wgt;
+  for (int e0 = threadIdx.x; e0 < a.B * Dq; e0 += 2 * GV_CT) {
+    float m[2][GV_MAX_SPLIT], l[2][GV_MAX_SPLIT], o[2][GV_MAX_SPLIT];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = e0 + q * GV_CT;
+      const bool ok = e < a.B * Dq;
+      const int ee = ok ? e : e0;
+      const int b = ee / Dq, r = ee - b * Dq, h = r / HD, d = r - h * HD;
+      const float* pp = g.part + (size_t)((b * a.n_q + h) * S) * stride;
+#pragma unroll
+      for (int s = 0; s < GV_MAX_SPLIT; ++s) {
+        m[q][s] = -CUDART_INF_F;
+        l[q][s] = 0.f;
+        o[q][s] = 0.f;
+        if (s < S) {
+          m[q][s] = __ldcg(pp + s * stride);
+          l[q][s] = __ldcg(pp + s * stride + 1);
+          o[q][s] = __ldcg(pp + s * stride + 2 + d);
+        }
       }
-      o /= L;
     }
-    att[e] = f2bf(o);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = e0 + q * GV_CT;
+      float M = -CUDART_INF_F;
+#pragma unroll
+      for (int s = 0; s < GV_MAX_SPLIT; ++s) M = fmaxf(M, m[q][s]);
+      float L = 0.f, acc = 0.f;
+#pragma unroll
+      for (int s = 0; s < GV_MAX_SPLIT; ++s) {
+        const float wgt = m[q][s] == -CUDART_INF_F ? 0.f : __expf(m[q][s] - M);
+        L += l[q][s] * wgt;
+        acc += o[q][s] * wgt;
+      }
+      if (e < a.B * Dq) att[e] = f2bf(acc / L);
+    }
   }
   bar_consumers();
 }
@@ -643,8 +877,12 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_gemv_kernel(const __grid
   }
   __syncthreads();
   const MegaLayer* layers = reinterpret_cast<const MegaLayer*>(smem + GO_LAYERS);
+  if (threadIdx.x < 16) reinterpret_cast<unsigned long long*>(smem + GO_DBG)[threadIdx.x] = 0ull;
+  if (threadIdx.x < 4) reinterpret_cast<uint32_t*>(smem + GO_ZERO)[threadIdx.x] = 0u;
+  gv_range_init(a, g, smem);
+  __syncthreads();
   if (warp == GV_CW) {
-    gv_producer(a, g, smem_base, layers);
+    gv_producer(a, g, smem, smem_base, layers);
     return;
   }
   unsigned epoch = 0;
@@ -653,7 +891,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_gemv_kernel(const __grid
   auto stamp = [&]() {
     if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {
       a.prof[prof_i] = globaltimer();
-      a.prof[a.prof_stride + prof_i] = (unsigned long long)clock64();
+      if (prof_i < 8 || prof_i >= 8 + 2 * 148) a.prof[a.prof_stride + prof_i] = (unsigned long long)clock64();  // (the gap: per-CTA stamps)
     }
     ++prof_i;
   };
@@ -661,6 +899,20 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_gemv_kernel(const __grid
   GvBest best{-CUDART_INF_F, -1};
   uint32_t wr[GV_NPJ];
   gv_norm_w(layers[0].in_ln, a.H, wr);
+  // this CTA's attention task (the same in every layer) when every CTA has at most one: page list + cos / sin row now
+  const int psz = a.kv.page_size;
+  const int psh = (psz & (psz - 1)) == 0 ? __ffs(psz) - 1 : -1;
+  const int ntask = a.B * a.n_q * g.n_split;
+  GvTask task0;
+  GvPre<NP> pre;
+  bool my_task = ntask <= (int)gridDim.x && (int)blockIdx.x < ntask;
+  if (my_task) my_task = gv_task<NP>(a, g, blockIdx.x, psh, task0);
+  if (my_task) gv_attn_stage<NP>(a, g, 0, smem, layers[0], task0, psh, ST_STEP | ST_LAYER);
+  bar_consumers();
+  if (my_task) {
+    gv_pre_offsets<NP>(a, reinterpret_cast<const int*>(smem + g.off_pf + GP_PAGES), task0, psh, pre);
+    gv_attn_stage<NP>(a, g, 0, smem, layers[0], task0, psh, ST_PREFETCH);
+  }
   stamp();
   GPhase p;
   for (int l = 0; l < a.L; ++l) {
@@ -668,21 +920,26 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_gemv_kernel(const __grid
     stamp();  // (qkv.load: the row load is part of the norm here)
     gv_load_norm<NB>(a, smem, g, l == 0, wr);
     stamp();
-    gv_phase(a, g, layers, PH_QKV, l, p);
+    gv_phase(a, smem, layers, PH_QKV, l, p);
     gv_gemv<NB, PH_QKV>(a, g, p, smem, smem_base, ring, act, best);
-    gv_norm_w(layers[l].post_ln, a.H, wr);
     stamp();
-    grid_sync(a.bar, epoch);
+    grid_arrive(a.bar, epoch);
+    gv_norm_w(layers[l].post_ln, a.H, wr);
+    if (my_task) gv_pre_load<NP>(a, l, pre);  // the cached K / V rows of this CTA's task: independent of this step's q
+    grid_wait(a.bar, epoch);
     stamp();
     // ---- q/k-norm + RoPE + KV store + attention
-    gv_attention<NP>(a, g, l, smem, layers[l]);
+    gv_attention<NP>(a, g, l, smem, layers[l], pre, my_task);
     stamp();
     grid_sync(a.bar, epoch);
     stamp();
     // ---- O + residual
-    gv_load_att(a, g, smem);
+    if (g.n_split == 1)
+      gv_load_rows(smem + g.off_act, a.att, a.B * a.n_q * a.hd);
+    else
+      gv_load_att(a, g, smem);
     stamp();
-    gv_phase(a, g, layers, PH_O, l, p);
+    gv_phase(a, smem, layers, PH_O, l, p);
     gv_gemv<NB, PH_O>(a, g, p, smem, smem_base, ring, act, best);
     stamp();
     grid_sync(a.bar, epoch);
@@ -691,37 +948,55 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_gemv_kernel(const __grid
     stamp();
     gv_load_norm<NB>(a, smem, g, false, wr);
     stamp();
-    gv_phase(a, g, layers, PH_GATEUP, l, p);
+    gv_phase(a, smem, layers, PH_GATEUP, l, p);
+    long long xt0 = 0;
+    if (a.prof && l == 5) xt0 = (long long)globaltimer();
     gv_gemv<NB, PH_GATEUP>(a, g, p, smem, smem_base, ring, act, best);
-    gv_norm_w(l + 1 < a.L ? layers[l + 1].in_ln : a.final_norm, a.H, wr);
+    if (a.prof && l == 5 && threadIdx.x == 0 && gridDim.x <= 148) {
+      a.prof[a.prof_stride + 8 + blockIdx.x] = globaltimer();
+      a.prof[a.prof_stride + 8 + 148 + blockIdx.x] = (unsigned long long)xt0;
+    }
     stamp();
-    grid_sync(a.bar, epoch);
+    grid_arrive(a.bar, epoch);
+    gv_norm_w(l + 1 < a.L ? layers[l + 1].in_ln : a.final_norm, a.H, wr);
+    grid_wait(a.bar, epoch);
     stamp();
     // ---- down + residual
     gv_load_rows(smem + g.off_act, a.h, a.B * a.I);
     stamp();
-    gv_phase(a, g, layers, PH_DOWN, l, p);
+    gv_phase(a, smem, layers, PH_DOWN, l, p);
     gv_gemv<NB, PH_DOWN>(a, g, p, smem, smem_base, ring, act, best);
     stamp();
-    grid_sync(a.bar, epoch);
+    grid_arrive(a.bar, epoch);
+    // the next layer's attention task: q/k-norm weights into shared memory, its cached K / V rows requested into L2
+    if (my_task && l + 1 < a.L) gv_attn_stage<NP>(a, g, l + 1, smem, layers[l + 1], task0, psh, ST_LAYER | ST_PREFETCH);
+    grid_wait(a.bar, epoch);
     stamp();
   }
   // ---- final norm + lm_head + arg-max candidates
   stamp();
   gv_load_norm<NB>(a, smem, g, false, wr);
   stamp();
-  gv_phase(a, g, layers, PH_LMHEAD, 0, p);
+  gv_phase(a, smem, layers, PH_LMHEAD, 0, p);
   gv_gemv<NB, PH_LMHEAD>(a, g, p, smem, smem_base, ring, act, best);
   stamp();
   {
-    MegaCand* cs = reinterpret_cast<MegaCand*>(smem + GO_CAND);  // [GV_HW][4]
-    const int hw = warp * 2 + (lane >> 4), l16 = lane & 15;
-    if (l16 < 4) cs[hw * 4 + l16] = MegaCand{best.v, best.i};
+    MegaCand* cs = reinterpret_cast<MegaCand*>(smem + GO_CAND);  // [GV_CW][4]
+#pragma unroll
+    for (int o = 16; o >= 8; o >>= 1) {  // lanes 8 q + b of a warp carry candidates of batch row b (weight row q of their items)
+      const float ov = __shfl_xor_sync(0xffffffffu, best.v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best.i, o);
+      if (cand_better(ov, oi, best.v, best.i)) {
+        best.v = ov;
+        best.i = oi;
+      }
+    }
+    if (lane < 4) cs[warp * 4 + lane] = MegaCand{best.v, best.i};
     bar_consumers();
     if (threadIdx.x < a.B) {
       float bv = cs[threadIdx.x].val;
       int bi = cs[threadIdx.x].idx;
-      for (int k = 1; k < GV_HW; ++k) {
+      for (int k = 1; k < GV_CW; ++k) {
         const MegaCand o = cs[k * 4 + threadIdx.x];
         if (cand_better(o.val, o.idx, bv, bi)) {
           bv = o.val;
@@ -766,6 +1041,8 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_gemv_kernel(const __grid
     }
   }
   stamp();
+  if (a.prof && blockIdx.x == 0 && threadIdx.x == 0)
+    for (int i = 0; i < 16; ++i) a.prof[2 * a.prof_stride + i] = reinterpret_cast<unsigned long long*>(smem + GO_DBG)[i];
 }
 
 struct GvGeom {
@@ -783,7 +1060,8 @@ bool gv_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_
   const int act_bytes = std::max(GA_END, nb * maxk * 2);
   GemvArgs g{};
   g.off_act = (GO_XS + nb * H * 2 + 127) & ~127;
-  g.off_ring = (g.off_act + act_bytes + 127) & ~127;
+  g.off_pf = (g.off_act + act_bytes + 127) & ~127;
+  g.off_ring = (g.off_pf + GP_END + 127) & ~127;
   int rd = std::max(1, 20480 / (I * 2));
   int slot = rd * I * 2;
   slot = std::max(slot, std::max(4 * H, 2 * Dq));
@@ -791,8 +1069,8 @@ bool gv_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_
   g.slot_bytes = slot;
   g.n_slots = std::min(GV_MAX_SLOTS, (GV_SMEM_MAX - g.off_ring) / slot);
   if (g.n_slots < 3) return false;
-  // KV splits: ~256 positions per task while the tasks fit one wave
-  int S = std::max(1, std::min((max_kv_len + 255) / 256, grid / std::max(1, B * n_q)));
+  // KV splits: ~256 positions per task while the tasks fit one wave (kv buckets are multiples of 128: one task up to 256)
+  int S = std::max(1, std::min(std::min((max_kv_len + 255) / 256, GV_MAX_SPLIT), grid / std::max(1, B * n_q)));
   if ((max_kv_len + 1 + S - 1) / S + 1 > GV_PT) return false;
   g.n_split = S;
   out->g = g;

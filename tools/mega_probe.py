@@ -51,6 +51,13 @@ if a.mega and eng.uses_mega(a.batch, a.ctx + a.steps + 16):
     gc = eng.mega_gemm_cycles.astype(np.int64).reshape(5, 2)
     print("CTA0 warp0 cycles (wait for weights, MMA loop) per step:", {k: (int(gc[i, 0]), int(gc[i, 1])) for i, k in enumerate(["qkv", "o", "gateup", "down", "lm_head"])})
     print("CTA0 attention cycles per step (setup, scores, softmax, PV):", [int(x) for x in eng.mega_attn_cycles])
+    if a.fast and a.batch <= 4 and cfg.layers > 5:
+        g_end, g_start = cyc[8:8 + 148], cyc[156:156 + 148]
+        t0 = g_start.min()
+        print("gate/up of layer 5 over the CTAs (us after the first start): start p50 %.2f max %.2f | end min %.2f p50 %.2f p90 %.2f max %.2f (CTA %d)" % (
+            np.median(g_start - t0) / 1e3, (g_start - t0).max() / 1e3, (g_end - t0).min() / 1e3, np.median(g_end - t0) / 1e3,
+            np.percentile(g_end - t0, 90) / 1e3, (g_end - t0).max() / 1e3, int(np.argmax(g_end))))
+        print("  end per CTA (us):", np.round((g_end - t0) / 1e3, 2).tolist())
     d = np.diff(ts)
     per = d[:16 * L].reshape(L, 16)
     names = ["qkv.load", "qkv.norm", "qkv.gemm", "qkv.bar", "att.run", "att.bar", "o.load", "o.gemm", "o.bar",
