@@ -699,8 +699,10 @@ def main():
                 eng.decode_run([s1], [int(t_first)], 120)
                 dtf = time.perf_counter() - t0
                 line["extra"]["batch1_fast_numerics"] = {
-                    "workload": "configs[0] batch 1, persistent kernel with K split over the warps + parallel RMSNorm "
-                                "(1e-2 tolerance per layer, tokens not bit-exact)",
+                    "workload": "configs[0] batch 1, fast numerics: the GEMV decode kernel (decode_gemv.cu: one persistent launch "
+                                "per token, weight rows streamed by bulk copies, warp-per-row-group FHFMA dot products, "
+                                "split-KV flash decoding, no grid barrier between the phases -- consumers poll per-layer "
+                                "activation buffers; 1e-2 tolerance per layer, tokens not bit-exact)",
                     "persistent_kernel": bool(eng.uses_mega(1, 200)),
                     "tokens_per_s": 120 / dtf, "us_per_token": 1e6 * dtf / 120,
                     "frac_of_hbm_peak": (b1_bytes * 120 / dtf / 1e9) / peak}

@@ -599,7 +599,11 @@ static int engine_finish_setup(qie_engine* e) {
       CU(cudaMalloc(&e->mega_cand_d, (size_t)e->num_sms * 64 * sizeof(MegaCand)));
       CU(cudaMalloc(&e->mega_bar_d, 4096));  // grid-barrier counters (8 shards on separate lines)
       CU(cudaMalloc(&e->mega_prof_d, (size_t)decode_mega_prof_slots(c.layers) * sizeof(unsigned long long)));
-      CU(cudaMalloc(&e->gemv_part_d, decode_gemv_part_floats(c.n_q, c.head_dim, e->num_sms) * sizeof(float)));
+      {
+        const size_t gb = decode_gemv_scratch_bytes(c.hidden, (int)I, c.layers, c.n_q, c.n_kv, c.head_dim, e->num_sms);
+        CU(cudaMalloc(&e->gemv_part_d, gb));
+        CU(cudaMemset(e->gemv_part_d, 0xFF, gb));  // "not stored yet" pattern of the GEMV kernel's per-layer buffers
+      }
       {
         const char* gv = getenv("QIE_GEMV");
         e->use_gemv = !(gv && gv[0] == '0');

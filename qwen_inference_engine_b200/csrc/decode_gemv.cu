@@ -36,18 +36,79 @@ enum { PH_QKV = 0, PH_O = 1, PH_GATEUP = 2, PH_DOWN = 3, PH_LMHEAD = 4 };
 constexpr int GV_CW = 8;                // consumer warps
 constexpr int GV_CT = GV_CW * 32;       // consumer threads
 constexpr int GV_THREADS = GV_CT + 32;  // + the producer warp
-constexpr int GV_HW = GV_CW * 2;        // half-warps
 constexpr int GV_MAX_SLOTS = 16;
 constexpr int GV_PT = 2048;             // cached positions one attention task takes
 constexpr int GV_MAX_LAYERS = 64;
 constexpr int GV_NPJ = 7;               // bf16 pairs of a residual row per thread: H <= 2 * 256 * 7
 constexpr int GV_SMEM_MAX = 227 * 1024;
+constexpr long long GV_SPIN_LIMIT = 4000000000ll;  // ~2 s of SM clocks: trap instead of hanging the GPU
 
 struct GemvArgs {
   int n_slots, slot_bytes, off_act, off_pf, off_ring;
   int n_split;   // KV splits per (row, q head)
-  float* part;   // [tasks][hd + 2] partial attention results: max, sum, o[hd]
+  int dataflow;  // 1 (default): no grid barrier between the phases, consumers poll the per-layer buffers (batch 1: 1780 ->
+                 // 2150 tok/s); 0 (QIE_GEMV_DATAFLOW=0): grid barriers between the phases, every layer reuses one block
+  bf16* act;     // per-layer activation buffers, every element 0xFFFF until its value is stored (GvAct)
 };
+
+// ---------------------------------------------------------------- data-flow synchronisation
+// The layers are NOT separated by grid barriers.  Every activation a phase hands to the next one has its own buffer PER
+// LAYER (x_in, qkv, attention output / split partials, x_mid, h: ~0.4 MB per sequence for the 0.5B shape), filled
+// with the bf16 pattern 0xFFFF (a NaN no operator stores) before the kernel starts.  A consumer polls exactly the
+// elements it needs until they stop being 0xFFFF: one L2 round trip behind the producer's store instead of
+// store -> fence -> atomic -> poll -> CTA barrier (measured ~1.9 us per grid barrier, 5 per layer, with every CTA
+// waiting for the slowest).  One real grid barrier remains (arg-max candidates), then all CTAs put the pattern back.
+struct GvAct {
+  bf16* base;
+  size_t ls;          // elements per layer
+  int oq, oa, om, oh, op;
+  __device__ __forceinline__ bf16* xi(int l) const { return base + (size_t)l * ls; }           // [B][H] input of layer l (l = L: final)
+  __device__ __forceinline__ bf16* qkv(int l) const { return xi(l) + oq; }                       // [B][Dq + 2 Dkv]
+  __device__ __forceinline__ bf16* att(int l) const { return xi(l) + oa; }                       // [B][Dq]
+  __device__ __forceinline__ bf16* xm(int l) const { return xi(l) + om; }                        // [B][H] behind o_proj
+  __device__ __forceinline__ bf16* hh(int l) const { return xi(l) + oh; }                        // [B][I]
+  __device__ __forceinline__ float* part(int l) const { return reinterpret_cast<float*>(xi(l) + op); }  // [tasks][hd + 2]
+};
+__host__ __device__ inline size_t gv_act_layer_elems(int B, int H, int I, int Dq, int Dkv, int hd, int ntask_part) {
+  return (size_t)B * (2 * H + (Dq + 2 * Dkv) + Dq + I) + (((size_t)ntask_part * (hd + 2) * 2 + 7) & ~(size_t)7);
+}
+__device__ __forceinline__ GvAct gv_act(const MegaArgs& a, const GemvArgs& g) {
+  const int Dq = a.n_q * a.hd, Dkv = a.n_kv * a.hd;
+  GvAct A;
+  A.base = g.act;
+  A.oq = a.B * a.H;
+  A.oa = A.oq + a.B * (Dq + 2 * Dkv);
+  A.om = A.oa + a.B * Dq;
+  A.oh = A.om + a.B * a.H;
+  A.op = A.oh + a.B * a.I;
+  // with grid barriers every layer reuses the first block (hot in L2; a store into a line that L2 no longer holds costs a
+  // DRAM fill in front of the reader); the pattern is not needed then, the polls succeed on the first request
+  A.ls = g.dataflow ? gv_act_layer_elems(a.B, a.H, a.I, Dq, Dkv, a.hd, g.n_split > 1 ? a.B * a.n_q * g.n_split : 0) : 0;
+  return A;
+}
+__device__ __forceinline__ bool gv_word_ready(uint32_t w) { return (w & 0xffffu) != 0xffffu && (w >> 16) != 0xffffu; }
+__device__ __forceinline__ uint32_t gv_ld_relaxed(const void* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 gv_ld_relaxed_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+// wait until both bf16 halves of a word have been stored
+__device__ __forceinline__ uint32_t gv_poll_u32(const void* p) {
+  uint32_t v = gv_ld_relaxed(p);
+  if (gv_word_ready(v)) return v;
+  const long long t0 = clock64();
+  do {
+    // (no pause: __nanosleep costs ~1 us per call here)
+    v = gv_ld_relaxed(p);
+    if (clock64() - t0 > GV_SPIN_LIMIT) __trap();
+  } while (!gv_word_ready(v));
+  return v;
+}
 
 // shared-memory header
 constexpr int GO_FULL = 0, GO_EMPTY = 128, GO_RED = 256, GO_DBG = 512, GO_CAND = 640, GO_RANGE = 1152, GO_ZERO = 1248, GO_LAYERS = 1280;  // GO_DBG: 16 x u64 cycle counters (profiled launches)
@@ -67,7 +128,6 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t addr, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t addr) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
 }
-constexpr long long GV_SPIN_LIMIT = 4000000000ll;  // ~2 s of SM clocks: trap instead of hanging the GPU
 __device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -88,10 +148,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t addr, uint32_t parity) {
     if (clock64() - t0 > GV_SPIN_LIMIT) __trap();
 }
 // 1-D bulk copy global -> shared memory of this CTA, completion counted on an mbarrier
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(mbar)
+// The weights are read exactly once per step: marked evict-first in L2, so that the ~1 GB stream does not push out what
+// IS re-read (activation buffers, norm weights, block tables, the KV rows of the previous tokens).
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(mbar), "l"(policy)
                : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
 __device__ __forceinline__ void bar_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(GV_CT) : "memory"); }
 __device__ __forceinline__ unsigned long long globaltimer() {
@@ -229,6 +296,7 @@ __device__ __forceinline__ void gv_producer(const MegaArgs& a, const GemvArgs& g
                                             const MegaLayer* layers) {
   if ((threadIdx.x & 31) != 0) return;
   uint32_t slot = 0, round = 0;
+  const uint64_t pol = l2_policy_evict_first();
   const int nph = 4 * a.L + 1;
   for (int idx = 0; idx < nph; ++idx) {
     const int kind = idx < 4 * a.L ? (idx & 3) : PH_LMHEAD;
@@ -244,15 +312,15 @@ __device__ __forceinline__ void gv_producer(const MegaArgs& a, const GemvArgs& g
       const uint32_t full = smem_base + GO_FULL + slot * 8;
       mbar_expect_tx(full, (uint32_t)n * row_bytes * (p.w2 ? 2u : 1u));
       if (p.w2) {
-        bulk_g2s(dst, p.seg[0] + (size_t)r * p.K, (uint32_t)n * row_bytes, full);
-        bulk_g2s(dst + (uint32_t)n * row_bytes, p.w2 + (size_t)r * p.K, (uint32_t)n * row_bytes, full);
+        bulk_g2s(dst, p.seg[0] + (size_t)r * p.K, (uint32_t)n * row_bytes, full, pol);
+        bulk_g2s(dst + (uint32_t)n * row_bytes, p.w2 + (size_t)r * p.K, (uint32_t)n * row_bytes, full, pol);
       } else {
         int s0 = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const int s1 = s0 + p.seg_rows[s];
           const int lo = max(r, s0), hi = min(r + n, s1);
           if (lo < hi)
-            bulk_g2s(dst + (uint32_t)(lo - r) * row_bytes, p.seg[s] + (size_t)(lo - s0) * p.K, (uint32_t)(hi - lo) * row_bytes, full);
+            bulk_g2s(dst + (uint32_t)(lo - r) * row_bytes, p.seg[s] + (size_t)(lo - s0) * p.K, (uint32_t)(hi - lo) * row_bytes, full, pol);
           s0 = s1;
         }
       }
@@ -283,7 +351,7 @@ struct GvRing {
 // lane are reduced together -- every exchange halves the values a lane carries; in the end lanes 8 g + i hold row g.
 template <int NB, int KIND>
 __device__ __forceinline__ void gv_gemv(const MegaArgs& a, const GemvArgs& g, const GPhase& p, unsigned char* smem, uint32_t smem_base,
-                                        GvRing& ring, const unsigned char* act, GvBest& best) {
+                                        GvRing& ring, const unsigned char* act, GvBest& best, bf16* out) {
   constexpr bool PAIR = KIND == PH_GATEUP;
   constexpr int R = (PAIR || KIND == PH_LMHEAD) ? 4 : 2;  // weight rows per item
   constexpr int RI = PAIR ? 2 : R;                         // output rows (row pairs) per item
@@ -387,12 +455,12 @@ __device__ __forceinline__ void gv_gemv(const MegaArgs& a, const GemvArgs& g, co
         const int b = lane & 7, gr = r + orow;
         const float y = bf2f(f2bf(v1));  // the projection output as the reference stores it (matrix_mul.cu: bf16)
         if (KIND == PH_QKV) {
-          a.qkv[(size_t)b * p.rows + gr] = f2bf(v1);
+          out[(size_t)b * p.rows + gr] = f2bf(v1);
         } else if (KIND == PH_O || KIND == PH_DOWN) {
-          a.x[(size_t)b * a.H + gr] = f2bf(bf2f(xs[b * a.H + gr]) + y);  // residual_add.cu:7
+          out[(size_t)b * a.H + gr] = f2bf(bf2f(xs[b * a.H + gr]) + y);  // residual_add.cu:7
         } else if (KIND == PH_GATEUP) {
           const float sg = bf2f(f2bf(y * (1.0f / (1.0f + expf(-y)))));     // SiLU.cu:6-8, stored as bf16
-          a.h[(size_t)b * a.I + gr] = f2bf(sg * bf2f(f2bf(v2)));            // element_add.cu (element-wise product)
+          out[(size_t)b * a.I + gr] = f2bf(sg * bf2f(f2bf(v2)));            // element_add.cu (element-wise product)
         } else {
           a.logits[(size_t)b * a.V + gr] = f2bf(v1);
           if (cand_better(y, gr, best.v, best.i)) {
@@ -429,23 +497,43 @@ __device__ __forceinline__ void gv_norm_w(const bf16* w, int H, uint32_t (&wr)[G
 // residual rows -> shared memory (raw, for the residual epilogues) + their RMSNorm (normalization.cu:9-21 rounding:
 // bf16((x / rms) * w)) into the activation area; the sum of squares is a tree, not the reference's chain
 template <int NB>
-__device__ __forceinline__ void gv_load_norm(const MegaArgs& a, unsigned char* smem, const GemvArgs& g, bool from_embed,
-                                             const uint32_t (&wr)[GV_NPJ]) {
+__device__ __forceinline__ void gv_load_norm(const MegaArgs& a, unsigned char* smem, const GemvArgs& g, const bf16* rows,
+                                             const uint32_t (&wr)[GV_NPJ]) {  // rows == nullptr: the embedding rows of a.ids
   const int H = a.H, hp = H >> 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t xv[NB][GV_NPJ];
   float ss[NB];
+  // Polling discipline: every word of a thread is requested in one round (the checks sit behind ALL requests: a check
+  // next to its load serialises the round trips) and the round is repeated while a word still shows the pattern.
+  // Measured alternatives: every word polled in turn (a round trip per word: 4 rows cost 7 us), one lane per warp
+  // polling a representative word first (+1 round trip, no gain), a pause between rounds (__nanosleep costs ~1 us).
+  {
+    const long long t0 = clock64();
+    bool ok;
+    do {
+      ok = true;
 #pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    ss[b] = 0.f;
-    const bool live = b < a.B;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(
-        live ? (from_embed ? a.embed + (size_t)max(a.ids[b], 0) * H : a.x + (size_t)b * H) : a.x);
+      for (int b = 0; b < NB; ++b) {
+        ss[b] = 0.f;
+        const bool live = b < a.B;
+        const uint32_t* src =
+            reinterpret_cast<const uint32_t*>(rows ? rows + (size_t)(live ? b : 0) * H : a.embed + (size_t)(live ? max(a.ids[b], 0) : 0) * H);
 #pragma unroll
-    for (int j = 0; j < GV_NPJ; ++j) {
-      const int idx = threadIdx.x + j * GV_CT;
-      xv[b][j] = (live && idx < hp) ? __ldcg(src + idx) : 0u;
-    }
+        for (int j = 0; j < GV_NPJ; ++j) {
+          const int idx = threadIdx.x + j * GV_CT;
+          xv[b][j] = 0u;
+          if (live && idx < hp) xv[b][j] = rows ? gv_ld_relaxed(src + idx) : __ldcg(src + idx);
+        }
+      }
+      if (rows) {  // checked behind ALL requests of the round (a check next to its load would serialise the round trips)
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+          for (int j = 0; j < GV_NPJ; ++j)
+            if (b < a.B && threadIdx.x + j * GV_CT < hp) ok = ok && gv_word_ready(xv[b][j]);
+      }
+      if (!ok && clock64() - t0 > GV_SPIN_LIMIT) __trap();
+    } while (!ok);
   }
   uint32_t* xs = reinterpret_cast<uint32_t*>(smem + GO_XS);
   float* red = reinterpret_cast<float*>(smem + GO_RED);
@@ -529,10 +617,21 @@ __device__ __forceinline__ void gv_attn_stage(const MegaArgs& a, const GemvArgs&
     for (int i = tid; i < pgn; i += GV_CT) pages[i] = bt[t.pg0 + i];
   }
   if (what & ST_LAYER) {
-    if (tid >= 128 && tid < 128 + 64 * NP) {  // q_norm then k_norm weights as bf16 pairs: 32 * NP words each
-      const int k = tid - 128, kk = k < 32 * NP ? k : k - 32 * NP;
-      const bf16* src = k < 32 * NP ? w.q_norm : w.k_norm;
-      nw[k] = src ? __ldg(reinterpret_cast<const uint32_t*>(src) + kk) : 0u;
+    // q_norm (warp 0) / k_norm (warp 1) weights as bf16 pairs, 32 * NP words each: asynchronous copies (a register
+    // round trip would stall this thread for a DRAM latency in front of the CTA barrier that follows); lane i copies
+    // exactly the words lane i reads in head_norm, so a cp.async.wait_all of the reader is all the ordering needed
+    if (tid < 64) {
+      const int wq = tid >> 5, ln = tid & 31;
+      const bf16* src = wq == 0 ? w.q_norm : w.k_norm;
+#pragma unroll
+      for (int p = 0; p < NP; ++p) {
+        uint32_t* dst = nw + wq * 32 * NP + 32 * p + ln;
+        if (src)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(reinterpret_cast<const uint32_t*>(src) + 32 * p + ln) : "memory");
+        else
+          *dst = 0u;
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     }
   }
   if (what & ST_PREFETCH) {  // needs the page list in shared memory (ST_STEP + a barrier before)
@@ -583,8 +682,8 @@ __device__ __forceinline__ void gv_pre_load(const MegaArgs& a, int layer, GvPre<
 }
 
 template <int NP>
-__device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& g, int layer, unsigned char* smem, const MegaLayer& w,
-                                             GvPre<NP>& pre, bool preloaded) {
+__device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& g, const GvAct& A, int layer, unsigned char* smem,
+                                             const MegaLayer& w, GvPre<NP>& pre, bool preloaded) {
   constexpr int HD = 64 * NP, LPP = HD / 8, GPW = 32 / LPP, NG = GV_CW * GPW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = warp * GPW + lane / LPP, j = lane % LPP;
@@ -612,7 +711,7 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
     GvTask t;
     const bool any = gv_task<NP>(a, g, task, psh, t);
     const int b = t.b, h = t.h, kvh = t.kvh, ps = t.ps, p0 = t.p0, p1 = t.p1, pc1 = t.pc1, pg0 = t.pg0;
-    float* part = g.part + (size_t)((b * a.n_q + h) * S + t.sp) * (HD + 2);
+    float* part = A.part(layer) + (size_t)((b * a.n_q + h) * S + t.sp) * (HD + 2);
     if (!any) {  // empty split (S > 1 only)
       if (threadIdx.x < HD) part[2 + threadIdx.x] = 0.f;
       if (threadIdx.x == 0) {
@@ -639,7 +738,7 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
     const bool has_new = t.has_new;
     const bool writer = has_new && h == kvh * Gq;
     const int* bt = a.block_table + (size_t)a.slot[b] * a.max_pages;
-    const bf16* row = a.qkv + (size_t)b * QKV;
+    const bf16* row = A.qkv(layer) + (size_t)b * QKV;  // polled: the QKV phase of this layer stores it
     // the first 4 * NG cached positions of K and V: requested before anything that depends on this step's q
     auto load4 = [&](int base, int kv, uint4 (&r4)[4]) {
 #pragma unroll
@@ -668,10 +767,11 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
       float v[NP][2];
 #pragma unroll
       for (int p = 0; p < NP; ++p) {
-        const uint32_t u = __ldcg(reinterpret_cast<const uint32_t*>(row + (size_t)h * HD + 64 * p + 2 * lane));
+        const uint32_t u = gv_poll_u32(row + (size_t)h * HD + 64 * p + 2 * lane);
         v[p][0] = lo2f(u);
         v[p][1] = hi2f(u);
       }
+      asm volatile("cp.async.wait_all;" ::: "memory");  // this lane's q_norm words (gv_attn_stage)
       if (w.q_norm) head_norm<NP>(v, qnw, lane);
       head_rope<NP>(v, cos_s, sin_s, lane);
       head_store<NP>(v, q_s, lane);
@@ -680,10 +780,11 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
         float v[NP][2];
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
-          const uint32_t u = __ldcg(reinterpret_cast<const uint32_t*>(row + Dq + (size_t)kvh * HD + 64 * p + 2 * lane));
+          const uint32_t u = gv_poll_u32(row + Dq + (size_t)kvh * HD + 64 * p + 2 * lane);
           v[p][0] = lo2f(u);
           v[p][1] = hi2f(u);
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");  // this lane's k_norm words (gv_attn_stage)
         if (w.k_norm) head_norm<NP>(v, knw, lane);
         head_rope<NP>(v, cos_s, sin_s, lane);
         head_store<NP>(v, knew, lane);
@@ -693,7 +794,7 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
       if (has_new) {
 #pragma unroll
         for (int p = 0; p < NP; ++p) {
-          const uint32_t u = __ldcg(reinterpret_cast<const uint32_t*>(row + Dq + Dkv + (size_t)kvh * HD + 64 * p + 2 * lane));
+          const uint32_t u = gv_poll_u32(row + Dq + Dkv + (size_t)kvh * HD + 64 * p + 2 * lane);
           reinterpret_cast<uint32_t*>(vnew)[32 * p + lane] = u;
           if (writer)
             reinterpret_cast<uint32_t*>(a.kv.chunk(bt[ps / psz], layer, 1, kvh) + (size_t)(ps % psz) * HD)[32 * p + lane] = u;
@@ -792,7 +893,7 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
         l += red[GV_CW + w8];
       }
       if (S == 1) {
-        a.att[(size_t)b * Dq + (size_t)h * HD + threadIdx.x] = f2bf(tt / l);  // self_attension.cu:137: rounded once
+        A.att(layer)[(size_t)b * Dq + (size_t)h * HD + threadIdx.x] = f2bf(tt / l);  // self_attension.cu:137: rounded once
       } else {
         part[2 + threadIdx.x] = tt;
         if (threadIdx.x == 0) {
@@ -808,29 +909,44 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
 
 // attention output rows [B][Dq] bf16 (self_attension.cu:137: rounded once) from the tasks' partial results (S > 1):
 // all S loads of two outputs are in flight together (one L2 round trip per pair instead of 2 S dependent ones)
-__device__ __forceinline__ void gv_load_att(const MegaArgs& a, const GemvArgs& g, unsigned char* smem) {
+__device__ __forceinline__ void gv_load_att(const MegaArgs& a, const GemvArgs& g, unsigned char* smem, const float* part) {
   const int HD = a.hd, Dq = a.n_q * HD, S = g.n_split, stride = HD + 2;
   bf16* att = reinterpret_cast<bf16*>(smem + g.off_act);
   for (int e0 = threadIdx.x; e0 < a.B * Dq; e0 += 2 * GV_CT) {
     float m[2][GV_MAX_SPLIT], l[2][GV_MAX_SPLIT], o[2][GV_MAX_SPLIT];
+    {  // every partial of the two outputs requested together, repeated until none shows the pattern
+      const long long t0 = clock64();
+      bool ready;
+      do {
+        ready = true;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int e = e0 + q * GV_CT;
-      const bool ok = e < a.B * Dq;
-      const int ee = ok ? e : e0;
-      const int b = ee / Dq, r = ee - b * Dq, h = r / HD, d = r - h * HD;
-      const float* pp = g.part + (size_t)((b * a.n_q + h) * S) * stride;
+        for (int q = 0; q < 2; ++q) {
+          const int e = e0 + q * GV_CT;
+          const bool ok = e < a.B * Dq;
+          const int ee = ok ? e : e0;
+          const int b = ee / Dq, r = ee - b * Dq, h = r / HD, d = r - h * HD;
+          const float* pp = part + (size_t)((b * a.n_q + h) * S) * stride;
 #pragma unroll
-      for (int s = 0; s < GV_MAX_SPLIT; ++s) {
-        m[q][s] = -CUDART_INF_F;
-        l[q][s] = 0.f;
-        o[q][s] = 0.f;
-        if (s < S) {
-          m[q][s] = __ldcg(pp + s * stride);
-          l[q][s] = __ldcg(pp + s * stride + 1);
-          o[q][s] = __ldcg(pp + s * stride + 2 + d);
+          for (int s = 0; s < GV_MAX_SPLIT; ++s) {
+            m[q][s] = -CUDART_INF_F;
+            l[q][s] = 0.f;
+            o[q][s] = 0.f;
+            if (s < S) {
+              m[q][s] = __uint_as_float(gv_ld_relaxed(pp + s * stride));
+              l[q][s] = __uint_as_float(gv_ld_relaxed(pp + s * stride + 1));
+              o[q][s] = __uint_as_float(gv_ld_relaxed(pp + s * stride + 2 + d));
+            }
+          }
         }
-      }
+#pragma unroll
+        for (int q = 0; q < 2; ++q)
+#pragma unroll
+          for (int s = 0; s < GV_MAX_SPLIT; ++s)
+            if (s < S)
+              ready = ready && __float_as_uint(m[q][s]) != 0xffffffffu && __float_as_uint(l[q][s]) != 0xffffffffu &&
+                      __float_as_uint(o[q][s]) != 0xffffffffu;
+        if (!ready && clock64() - t0 > GV_SPIN_LIMIT) __trap();
+      } while (!ready);
     }
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
@@ -853,7 +969,30 @@ __device__ __forceinline__ void gv_load_att(const MegaArgs& a, const GemvArgs& g
 __device__ __forceinline__ void gv_load_rows(unsigned char* dst, const bf16* src, int n_elems) {
   const uint4* s4 = reinterpret_cast<const uint4*>(src);
   uint4* d4 = reinterpret_cast<uint4*>(dst);
-  for (int i = threadIdx.x; i < (n_elems >> 3); i += GV_CT) d4[i] = __ldcg(s4 + i);
+  const int n4 = n_elems >> 3;
+  // polling discipline as in gv_load_norm: four requests in flight per lane, the round repeated for stragglers
+  for (int i0 = threadIdx.x; i0 < n4; i0 += 4 * GV_CT) {
+    uint4 v[4];
+    const long long t0 = clock64();
+    bool ok;
+    do {
+      ok = true;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * GV_CT;
+        if (i < n4) v[u] = gv_ld_relaxed_v4(s4 + i);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i0 + u * GV_CT < n4) ok = ok && gv_word_ready(v[u].x) && gv_word_ready(v[u].y) && gv_word_ready(v[u].z) && gv_word_ready(v[u].w);
+      if (!ok && clock64() - t0 > GV_SPIN_LIMIT) __trap();
+    } while (!ok);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * GV_CT;
+      if (i < n4) d4[i] = v[u];
+    }
+  }
   bar_consumers();
 }
 
@@ -915,70 +1054,73 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_gemv_kernel(const __grid
   }
   stamp();
   GPhase p;
+  const GvAct A = gv_act(a, g);
+  // No grid barrier inside the loop: every load of another CTA's result polls the per-layer buffer (GvAct).  The
+  // bar_consumers() behind a GEMV phase only protects the shared-memory activation area / residual rows of this CTA.
   for (int l = 0; l < a.L; ++l) {
     // ---- RMSNorm + QKV
     stamp();  // (qkv.load: the row load is part of the norm here)
-    gv_load_norm<NB>(a, smem, g, l == 0, wr);
+    gv_load_norm<NB>(a, smem, g, l == 0 ? nullptr : A.xi(l), wr);
     stamp();
     gv_phase(a, smem, layers, PH_QKV, l, p);
-    gv_gemv<NB, PH_QKV>(a, g, p, smem, smem_base, ring, act, best);
+    gv_gemv<NB, PH_QKV>(a, g, p, smem, smem_base, ring, act, best, A.qkv(l));
     stamp();
-    grid_arrive(a.bar, epoch);
+    if (!g.dataflow) grid_arrive(a.bar, epoch);
     gv_norm_w(layers[l].post_ln, a.H, wr);
     if (my_task) gv_pre_load<NP>(a, l, pre);  // the cached K / V rows of this CTA's task: independent of this step's q
-    grid_wait(a.bar, epoch);
+    if (!g.dataflow) grid_wait(a.bar, epoch); else bar_consumers();
     stamp();
     // ---- q/k-norm + RoPE + KV store + attention
-    gv_attention<NP>(a, g, l, smem, layers[l], pre, my_task);
+    gv_attention<NP>(a, g, A, l, smem, layers[l], pre, my_task);
     stamp();
-    grid_sync(a.bar, epoch);
+    if (!g.dataflow) grid_sync(a.bar, epoch);
     stamp();
     // ---- O + residual
     if (g.n_split == 1)
-      gv_load_rows(smem + g.off_act, a.att, a.B * a.n_q * a.hd);
+      gv_load_rows(smem + g.off_act, A.att(l), a.B * a.n_q * a.hd);
     else
-      gv_load_att(a, g, smem);
+      gv_load_att(a, g, smem, A.part(l));
     stamp();
     gv_phase(a, smem, layers, PH_O, l, p);
-    gv_gemv<NB, PH_O>(a, g, p, smem, smem_base, ring, act, best);
+    gv_gemv<NB, PH_O>(a, g, p, smem, smem_base, ring, act, best, A.xm(l));
     stamp();
-    grid_sync(a.bar, epoch);
+    if (!g.dataflow) grid_sync(a.bar, epoch); else bar_consumers();
     stamp();
     // ---- RMSNorm + gate/up + SiLU * up
     stamp();
-    gv_load_norm<NB>(a, smem, g, false, wr);
+    gv_load_norm<NB>(a, smem, g, A.xm(l), wr);
     stamp();
     gv_phase(a, smem, layers, PH_GATEUP, l, p);
     long long xt0 = 0;
     if (a.prof && l == 5) xt0 = (long long)globaltimer();
-    gv_gemv<NB, PH_GATEUP>(a, g, p, smem, smem_base, ring, act, best);
+    gv_gemv<NB, PH_GATEUP>(a, g, p, smem, smem_base, ring, act, best, A.hh(l));
     if (a.prof && l == 5 && threadIdx.x == 0 && gridDim.x <= 148) {
       a.prof[a.prof_stride + 8 + blockIdx.x] = globaltimer();
       a.prof[a.prof_stride + 8 + 148 + blockIdx.x] = (unsigned long long)xt0;
     }
     stamp();
-    grid_arrive(a.bar, epoch);
+    if (!g.dataflow) grid_arrive(a.bar, epoch);
     gv_norm_w(l + 1 < a.L ? layers[l + 1].in_ln : a.final_norm, a.H, wr);
-    grid_wait(a.bar, epoch);
+    if (!g.dataflow) grid_wait(a.bar, epoch); else bar_consumers();
     stamp();
     // ---- down + residual
-    gv_load_rows(smem + g.off_act, a.h, a.B * a.I);
+    gv_load_rows(smem + g.off_act, A.hh(l), a.B * a.I);
     stamp();
     gv_phase(a, smem, layers, PH_DOWN, l, p);
-    gv_gemv<NB, PH_DOWN>(a, g, p, smem, smem_base, ring, act, best);
+    gv_gemv<NB, PH_DOWN>(a, g, p, smem, smem_base, ring, act, best, A.xi(l + 1));
     stamp();
-    grid_arrive(a.bar, epoch);
+    if (!g.dataflow) grid_arrive(a.bar, epoch);
     // the next layer's attention task: q/k-norm weights into shared memory, its cached K / V rows requested into L2
     if (my_task && l + 1 < a.L) gv_attn_stage<NP>(a, g, l + 1, smem, layers[l + 1], task0, psh, ST_LAYER | ST_PREFETCH);
-    grid_wait(a.bar, epoch);
+    if (!g.dataflow) grid_wait(a.bar, epoch); else bar_consumers();
     stamp();
   }
   // ---- final norm + lm_head + arg-max candidates
   stamp();
-  gv_load_norm<NB>(a, smem, g, false, wr);
+  gv_load_norm<NB>(a, smem, g, A.xi(a.L), wr);
   stamp();
   gv_phase(a, smem, layers, PH_LMHEAD, 0, p);
-  gv_gemv<NB, PH_LMHEAD>(a, g, p, smem, smem_base, ring, act, best);
+  gv_gemv<NB, PH_LMHEAD>(a, g, p, smem, smem_base, ring, act, best, nullptr);
   stamp();
   {
     MegaCand* cs = reinterpret_cast<MegaCand*>(smem + GO_CAND);  // [GV_CW][4]
@@ -1041,6 +1183,15 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_gemv_kernel(const __grid
     }
   }
   stamp();
+  {  // every CTA is behind the grid barrier above, i.e. done with all layer buffers: put the "not stored yet" pattern back
+    const size_t one = gv_act_layer_elems(a.B, a.H, a.I, a.n_q * a.hd, a.n_kv * a.hd, a.hd, g.n_split > 1 ? a.B * a.n_q * g.n_split : 0);
+    const size_t n16 = ((g.dataflow ? one * (size_t)a.L : one) + (size_t)a.B * a.H + 7) >> 3;
+    uint4* dst = reinterpret_cast<uint4*>(A.base);
+    uint64_t keep;  // these lines are stored to and read again during the next step: keep them in L2 across the weight stream
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+    for (size_t i = (size_t)blockIdx.x * GV_CT + threadIdx.x; i < n16; i += (size_t)gridDim.x * GV_CT)
+      asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %1, %1, %1}, %2;" ::"l"(dst + i), "r"(0xffffffffu), "l"(keep) : "memory");
+  }
   if (a.prof && blockIdx.x == 0 && threadIdx.x == 0)
     for (int i = 0; i < 16; ++i) a.prof[2 * a.prof_stride + i] = reinterpret_cast<unsigned long long*>(smem + GO_DBG)[i];
 }
@@ -1084,15 +1235,21 @@ bool decode_gemv_supports(int H, int I, int L, int n_q, int n_kv, int hd, int B,
   GvGeom gg;
   return gv_geometry(H, I, L, n_q, n_kv, hd, B, max_kv_len, num_sms, &gg);
 }
-size_t decode_gemv_part_floats(int n_q, int hd, int num_sms) {
-  // partial attention results: (max, sum, o[hd]) per task, tasks <= max(rows * heads, SMs) splits included
-  return (size_t)(DECODE_GEMV_MAX_ROWS * n_q + num_sms) * (size_t)(hd + 2);
+size_t decode_gemv_scratch_bytes(int H, int I, int L, int n_q, int n_kv, int hd, int num_sms) {
+  // per-layer activation buffers of the data-flow synchronisation (GvAct): the largest layout over the row counts,
+  // split partials for at most one task per SM.  The caller fills it with 0xFF bytes once.
+  const size_t ls = gv_act_layer_elems(DECODE_GEMV_MAX_ROWS, H, I, n_q * hd, n_kv * hd, hd, num_sms);
+  return (ls * (size_t)L + (size_t)DECODE_GEMV_MAX_ROWS * H + 64) * sizeof(bf16);
 }
 
-cudaError_t launch_decode_gemv(MegaArgs a, float* part, int num_sms, cudaStream_t st) {
+cudaError_t launch_decode_gemv(MegaArgs a, void* scratch, int num_sms, cudaStream_t st) {
   GvGeom gg;
   if (!gv_geometry(a.H, a.I, a.L, a.n_q, a.n_kv, a.hd, a.B, a.max_kv_len, num_sms, &gg)) return cudaErrorInvalidValue;
-  gg.g.part = part;
+  gg.g.act = reinterpret_cast<bf16*>(scratch);
+  {
+    static const int df = [] { const char* v = getenv("QIE_GEMV_DATAFLOW"); return v ? atoi(v) : -1; }();
+    gg.g.dataflow = df >= 0 ? df : 1;
+  }
   const int nb = a.B <= 1 ? 1 : (a.B <= 2 ? 2 : 4);
   void (*kern)(MegaArgs, GemvArgs);
   if (a.hd == 64)

@@ -101,7 +101,7 @@ struct qie_engine {
   int mega_layers_run = 0;           // debug: run only this many layers (no lm_head)
   // GEMV decode kernel (decode_gemv.cu): fast-numerics steps of <= DECODE_GEMV_MAX_ROWS rows
   bool use_gemv = true;              // QIE_GEMV=0 / set_int("gemv", 0): the split-K variant of decode_mega.cu instead
-  float* gemv_part_d = nullptr;      // partial attention results of the split-KV tasks
+  float* gemv_part_d = nullptr;      // GEMV decode kernel: per-layer activation buffers + split-KV partials (0xFF = not stored yet)
   // parity hooks of the per-operator forward (tests/test_gpu_layer_isolation.py): run layers [layer_first,
   // layer_first + layer_count) only (0 = all, then final norm + lm_head) and/or take the residual stream x as
   // written by qie_engine_write_activation instead of the embedding rows

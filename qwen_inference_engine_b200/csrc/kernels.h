@@ -261,11 +261,12 @@ cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st);
 
 // decode_gemv.cu: the fast-numerics decode step of <= DECODE_GEMV_MAX_ROWS sequences as one persistent kernel of
 // memory-bound GEMVs (contiguous row ranges per CTA streamed by 1-D bulk copies, half-warp per weight row,
-// split-KV flash decoding).  Takes the MegaArgs of the step (tensor maps / ring geometry unused) + a scratch buffer
-// of decode_gemv_part_floats() floats for the partial attention results.
+// split-KV flash decoding, no grid barrier between the phases: consumers poll per-layer activation buffers).  Takes the
+// MegaArgs of the step (tensor maps / ring geometry unused) + a scratch buffer of decode_gemv_scratch_bytes() bytes that
+// the caller filled with 0xFF bytes ONCE (the kernel leaves it in that state).
 constexpr int DECODE_GEMV_MAX_ROWS = 4;
 bool decode_gemv_supports(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int num_sms);
-size_t decode_gemv_part_floats(int n_q, int hd, int num_sms);
-cudaError_t launch_decode_gemv(MegaArgs a, float* part, int num_sms, cudaStream_t st);
+size_t decode_gemv_scratch_bytes(int H, int I, int L, int n_q, int n_kv, int hd, int num_sms);
+cudaError_t launch_decode_gemv(MegaArgs a, void* scratch, int num_sms, cudaStream_t st);
 
 }  // namespace qie
