@@ -1356,6 +1356,7 @@ int qie_engine_set_int(qie_engine* e, const char* key, long value) {
   std::string k(key);
   if (k == "mega") e->use_mega = value != 0;
   else if (k == "gemv") e->use_gemv = value != 0;
+  else if (k == "gemv_dataflow") e->gemv_dataflow = value;
   else if (k == "mega_layers_run") e->mega_layers_run = (int)value;
   else if (k == "mega_prof") e->mega_prof_on = value != 0;
   else if (k == "layer_first") e->layer_first = (int)std::max(0l, value);

@@ -363,18 +363,21 @@ __device__ __forceinline__ void gv_gemv(const MegaArgs& a, const GemvArgs& g, co
   const uint4* zero4 = reinterpret_cast<const uint4*>(smem + GO_ZERO);
   int r0, r1;
   gv_range(smem, KIND, r0, r1);
+#ifdef GV_PROFILE_DETAIL  // cycles a warp waits for weights / spends in the phase (CTA 0): costs code on the hot path
   const bool dbg_on = a.prof && blockIdx.x == 0 && threadIdx.x == 0;
   long long t_in = 0, t_wait = 0;
   if (dbg_on) t_in = clock64();
+#endif
   for (int r = r0; r < r1; r += p.ch) {
     const int n = min(p.ch, r1 - r);
+#ifdef GV_PROFILE_DETAIL
     if (a.prof) {  // warp-uniform: a lane on its own path would be measured apart from the lanes that really wait
       const long long t0 = clock64();
       mbar_wait(smem_base + GO_FULL + ring.slot * 8, ring.round & 1);
       t_wait += clock64() - t0;
-    } else {
+    } else
+#endif
       mbar_wait(smem_base + GO_FULL + ring.slot * 8, ring.round & 1);
-    }
     const unsigned char* base = smem + g.off_ring + ring.slot * g.slot_bytes;
     const int items = (n + RI - 1) / RI;
     int it = warp - ring.rot;
@@ -478,11 +481,13 @@ __device__ __forceinline__ void gv_gemv(const MegaArgs& a, const GemvArgs& g, co
       ++ring.round;
     }
   }
+#ifdef GV_PROFILE_DETAIL
   if (dbg_on) {
     unsigned long long* dbg = reinterpret_cast<unsigned long long*>(smem + GO_DBG);
     dbg[2 * KIND] += (unsigned long long)t_wait;
     dbg[2 * KIND + 1] += (unsigned long long)(clock64() - t_in);
   }
+#endif
 }
 
 // norm weights of the next RMSNorm into registers (requested in front of the grid barrier that precedes their use)
@@ -720,6 +725,7 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
       }
       continue;
     }
+#ifdef GV_PROFILE_DETAIL
     const bool dbg_on = a.prof && blockIdx.x == 0 && threadIdx.x == 0;
     unsigned long long* dbg = reinterpret_cast<unsigned long long*>(smem + GO_DBG);
     long long tq = 0;
@@ -731,6 +737,9 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
         tq = tt;
       }
     };
+#else
+    auto lap = [](int) {};
+#endif
     if (ntask > (int)gridDim.x) {  // several tasks per CTA: nothing was staged ahead
       gv_attn_stage<NP>(a, g, layer, smem, w, t, psh, ST_STEP | ST_LAYER);
       bar_consumers();
@@ -996,7 +1005,16 @@ __device__ __forceinline__ void gv_load_rows(unsigned char* dst, const bf16* src
   bar_consumers();
 }
 
-template <int NP, int NB>
+// phase stamp of a profiled launch (CTA 0, thread 0).  One out-of-line copy: the kernel's straight-line code is several
+// times the 32 KB instruction cache, so everything that is not on the hot path is kept out of it.
+__device__ __noinline__ void gv_stamp(const MegaArgs& a, int prof_i) {
+  if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {
+    a.prof[prof_i] = globaltimer();
+    if (prof_i < 8 || prof_i >= 8 + 2 * 148) a.prof[a.prof_stride + prof_i] = (unsigned long long)clock64();  // (the gap: per-CTA stamps)
+  }
+}
+
+template <int NP, int NB, bool DF>
 __global__ void __launch_bounds__(GV_THREADS, 1) decode_gemv_kernel(const __grid_constant__ MegaArgs a, const __grid_constant__ GemvArgs g) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t smem_base = smem_u32(smem);
@@ -1028,10 +1046,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_gemv_kernel(const __grid
   GvRing ring{0u, 0u, 0};
   int prof_i = 0;
   auto stamp = [&]() {
-    if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) {
-      a.prof[prof_i] = globaltimer();
-      if (prof_i < 8 || prof_i >= 8 + 2 * 148) a.prof[a.prof_stride + prof_i] = (unsigned long long)clock64();  // (the gap: per-CTA stamps)
-    }
+    if (a.prof) gv_stamp(a, prof_i);
     ++prof_i;
   };
   const unsigned char* act = smem + g.off_act;
@@ -1065,15 +1080,15 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_gemv_kernel(const __grid
     gv_phase(a, smem, layers, PH_QKV, l, p);
     gv_gemv<NB, PH_QKV>(a, g, p, smem, smem_base, ring, act, best, A.qkv(l));
     stamp();
-    if (!g.dataflow) grid_arrive(a.bar, epoch);
+    if (!DF) grid_arrive(a.bar, epoch);
     gv_norm_w(layers[l].post_ln, a.H, wr);
     if (my_task) gv_pre_load<NP>(a, l, pre);  // the cached K / V rows of this CTA's task: independent of this step's q
-    if (!g.dataflow) grid_wait(a.bar, epoch); else bar_consumers();
+    if (!DF) grid_wait(a.bar, epoch); else bar_consumers();
     stamp();
     // ---- q/k-norm + RoPE + KV store + attention
     gv_attention<NP>(a, g, A, l, smem, layers[l], pre, my_task);
     stamp();
-    if (!g.dataflow) grid_sync(a.bar, epoch);
+    if (!DF) grid_sync(a.bar, epoch);
     stamp();
     // ---- O + residual
     if (g.n_split == 1)
@@ -1084,24 +1099,28 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_gemv_kernel(const __grid
     gv_phase(a, smem, layers, PH_O, l, p);
     gv_gemv<NB, PH_O>(a, g, p, smem, smem_base, ring, act, best, A.xm(l));
     stamp();
-    if (!g.dataflow) grid_sync(a.bar, epoch); else bar_consumers();
+    if (!DF) grid_sync(a.bar, epoch); else bar_consumers();
     stamp();
     // ---- RMSNorm + gate/up + SiLU * up
     stamp();
     gv_load_norm<NB>(a, smem, g, A.xm(l), wr);
     stamp();
     gv_phase(a, smem, layers, PH_GATEUP, l, p);
+#ifdef GV_PROFILE_DETAIL
     long long xt0 = 0;
     if (a.prof && l == 5) xt0 = (long long)globaltimer();
+#endif
     gv_gemv<NB, PH_GATEUP>(a, g, p, smem, smem_base, ring, act, best, A.hh(l));
+#ifdef GV_PROFILE_DETAIL  // start / end of this phase on every CTA (tools/mega_probe.py)
     if (a.prof && l == 5 && threadIdx.x == 0 && gridDim.x <= 148) {
       a.prof[a.prof_stride + 8 + blockIdx.x] = globaltimer();
       a.prof[a.prof_stride + 8 + 148 + blockIdx.x] = (unsigned long long)xt0;
     }
+#endif
     stamp();
-    if (!g.dataflow) grid_arrive(a.bar, epoch);
+    if (!DF) grid_arrive(a.bar, epoch);
     gv_norm_w(l + 1 < a.L ? layers[l + 1].in_ln : a.final_norm, a.H, wr);
-    if (!g.dataflow) grid_wait(a.bar, epoch); else bar_consumers();
+    if (!DF) grid_wait(a.bar, epoch); else bar_consumers();
     stamp();
     // ---- down + residual
     gv_load_rows(smem + g.off_act, A.hh(l), a.B * a.I);
@@ -1109,10 +1128,10 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_gemv_kernel(const __grid
     gv_phase(a, smem, layers, PH_DOWN, l, p);
     gv_gemv<NB, PH_DOWN>(a, g, p, smem, smem_base, ring, act, best, A.xi(l + 1));
     stamp();
-    if (!g.dataflow) grid_arrive(a.bar, epoch);
+    if (!DF) grid_arrive(a.bar, epoch);
     // the next layer's attention task: q/k-norm weights into shared memory, its cached K / V rows requested into L2
     if (my_task && l + 1 < a.L) gv_attn_stage<NP>(a, g, l + 1, smem, layers[l + 1], task0, psh, ST_LAYER | ST_PREFETCH);
-    if (!g.dataflow) grid_wait(a.bar, epoch); else bar_consumers();
+    if (!DF) grid_wait(a.bar, epoch); else bar_consumers();
     stamp();
   }
   // ---- final norm + lm_head + arg-max candidates
@@ -1242,20 +1261,27 @@ size_t decode_gemv_scratch_bytes(int H, int I, int L, int n_q, int n_kv, int hd,
   return (ls * (size_t)L + (size_t)DECODE_GEMV_MAX_ROWS * H + 64) * sizeof(bf16);
 }
 
-cudaError_t launch_decode_gemv(MegaArgs a, void* scratch, int num_sms, cudaStream_t st) {
+cudaError_t launch_decode_gemv(MegaArgs a, void* scratch, int num_sms, cudaStream_t st, int dataflow) {
   GvGeom gg;
   if (!gv_geometry(a.H, a.I, a.L, a.n_q, a.n_kv, a.hd, a.B, a.max_kv_len, num_sms, &gg)) return cudaErrorInvalidValue;
   gg.g.act = reinterpret_cast<bf16*>(scratch);
   {
     static const int df = [] { const char* v = getenv("QIE_GEMV_DATAFLOW"); return v ? atoi(v) : -1; }();
-    gg.g.dataflow = df >= 0 ? df : 1;
+    gg.g.dataflow = dataflow >= 0 ? (dataflow != 0) : (df >= 0 ? (df != 0) : 1);
   }
   const int nb = a.B <= 1 ? 1 : (a.B <= 2 ? 2 : 4);
   void (*kern)(MegaArgs, GemvArgs);
-  if (a.hd == 64)
-    kern = nb == 1 ? decode_gemv_kernel<1, 1> : (nb == 2 ? decode_gemv_kernel<1, 2> : decode_gemv_kernel<1, 4>);
-  else
-    kern = nb == 1 ? decode_gemv_kernel<2, 1> : (nb == 2 ? decode_gemv_kernel<2, 2> : decode_gemv_kernel<2, 4>);
+  if (gg.g.dataflow) {
+    if (a.hd == 64)
+      kern = nb == 1 ? decode_gemv_kernel<1, 1, true> : (nb == 2 ? decode_gemv_kernel<1, 2, true> : decode_gemv_kernel<1, 4, true>);
+    else
+      kern = nb == 1 ? decode_gemv_kernel<2, 1, true> : (nb == 2 ? decode_gemv_kernel<2, 2, true> : decode_gemv_kernel<2, 4, true>);
+  } else {
+    if (a.hd == 64)
+      kern = nb == 1 ? decode_gemv_kernel<1, 1, false> : (nb == 2 ? decode_gemv_kernel<1, 2, false> : decode_gemv_kernel<1, 4, false>);
+    else
+      kern = nb == 1 ? decode_gemv_kernel<2, 1, false> : (nb == 2 ? decode_gemv_kernel<2, 2, false> : decode_gemv_kernel<2, 4, false>);
+  }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gg.smem);
   if (e != cudaSuccess) return e;
   e = cudaMemsetAsync(a.bar, 0, sizeof(unsigned), st);

@@ -609,10 +609,11 @@ static cudaError_t forward_decode_mega_rows(qie_engine* e, int row0, int n, int 
     a.x2 = e->x2;
   }
   // fast numerics, <= DECODE_GEMV_MAX_ROWS rows: the GEMV kernel (decode_gemv.cu) -- contiguous row ranges per CTA,
-  // half-warp per weight row, split-KV flash decoding; same step semantics (logits, arg-max, bookkeeping)
+  // warp per group of weight rows, split-KV flash decoding, phases chained through polled per-layer buffers instead of
+  // grid barriers; same step semantics (logits, arg-max, bookkeeping)
   const bool gemv = a.fast && !tp && e->use_gemv && e->gemv_part_d && e->mega_layers_run <= 0 &&
                     decode_gemv_supports(a.H, a.I, a.L, a.n_q, a.n_kv, a.hd, n, max_kv_len, e->num_sms);
-  cudaError_t r = gemv ? launch_decode_gemv(a, e->gemv_part_d, e->num_sms, e->stream) : launch_decode_mega(a, e->num_sms, e->stream);
+  cudaError_t r = gemv ? launch_decode_gemv(a, e->gemv_part_d, e->num_sms, e->stream, e->gemv_dataflow) : launch_decode_mega(a, e->num_sms, e->stream);
   if (tp) {
     // the ranks must stay on the same path: no silent fallback here.  The step is ONE launch per rank: the
     // arg-max over the ranks' vocabulary ranges and the step bookkeeping happen inside the kernel.

@@ -100,6 +100,7 @@ struct qie_engine {
   bool mega_prof_on = false;
   int mega_layers_run = 0;           // debug: run only this many layers (no lm_head)
   // GEMV decode kernel (decode_gemv.cu): fast-numerics steps of <= DECODE_GEMV_MAX_ROWS rows
+  int gemv_dataflow = -1;            // set_int("gemv_dataflow", 0/1): grid barriers / polled per-layer buffers in decode_gemv.cu (-1: default)
   bool use_gemv = true;              // QIE_GEMV=0 / set_int("gemv", 0): the split-K variant of decode_mega.cu instead
   float* gemv_part_d = nullptr;      // GEMV decode kernel: per-layer activation buffers + split-KV partials (0xFF = not stored yet)
   // parity hooks of the per-operator forward (tests/test_gpu_layer_isolation.py): run layers [layer_first,

@@ -267,6 +267,6 @@ cudaError_t launch_decode_mega(MegaArgs a, int num_sms, cudaStream_t st);
 constexpr int DECODE_GEMV_MAX_ROWS = 4;
 bool decode_gemv_supports(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_kv_len, int num_sms);
 size_t decode_gemv_scratch_bytes(int H, int I, int L, int n_q, int n_kv, int hd, int num_sms);
-cudaError_t launch_decode_gemv(MegaArgs a, void* scratch, int num_sms, cudaStream_t st);
+cudaError_t launch_decode_gemv(MegaArgs a, void* scratch, int num_sms, cudaStream_t st, int dataflow = -1);  // dataflow: -1 default (1, or QIE_GEMV_DATAFLOW), 0 grid barriers, 1 polled buffers
 
 }  // namespace qie

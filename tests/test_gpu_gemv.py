@@ -108,3 +108,31 @@ def test_gemv_equals_itself_under_graph_replay_and_decode_run(qie):
         outs.append(eng.decode_run(seqs, np.asarray([5, 6], np.int32), 24))
         eng.close()
     assert np.array_equal(outs[0], outs[1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("arch,n_seq,ctx", [("small", 1, 40), ("small", 3, 300), ("qwen2.5-0.5b", 1, 33), ("qwen2.5-0.5b", 2, 700)])
+def test_gemv_polled_buffers_equal_grid_barriers(qie, arch, n_seq, ctx):
+    """the phases of the GEMV kernel are chained through polled per-layer buffers (no grid barrier); the same kernel with
+    grid barriers between the phases does the same arithmetic, so tokens AND logits must be bit-identical -- over several
+    steps (the kernel has to leave the not-stored-yet pattern behind for the next launch) and with split KV partials"""
+    res = []
+    for dataflow in (1, 0):
+        eng = qie.Engine(synthetic=arch, seed=77, context=1024, max_batch_tokens=64, max_seqs=8, use_graph=False,
+                         kv_bytes=256 << 20, numerics="fast")
+        eng.set_int("gemv_dataflow", dataflow)
+        seqs = []
+        for i in range(n_seq):
+            s = eng.new_sequence()
+            eng.fill_synthetic(s, ctx + 5 * i, seed=10 + i)
+            seqs.append(s)
+        tok = np.arange(n_seq, dtype=np.int32) + 11
+        toks, logits = [], []
+        for _ in range(6):
+            tok = eng.decode_step(seqs, tok)
+            toks.append(np.array(tok))
+            logits.append(eng.read_activation("logits", n_seq * eng.config.vocab).copy())
+        res.append((np.stack(toks), np.stack(logits)))
+        eng.close()
+    assert np.array_equal(res[0][0], res[1][0])
+    assert np.array_equal(res[0][1], res[1][1])

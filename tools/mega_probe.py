@@ -49,9 +49,10 @@ if a.mega and eng.uses_mega(a.batch, a.ctx + a.steps + 16):
     print("SM clock during the step: %.0f MHz" % ((cyc[-1] - cyc[0]) / max(1, ts[-1] - ts[0]) * 1e3))
     L = cfg.layers
     gc = eng.mega_gemm_cycles.astype(np.int64).reshape(5, 2)
+    # (the GEMV kernel of fast numerics at <= 4 rows fills the two cycle tables only when built with make GVX=-DGV_PROFILE_DETAIL)
     print("CTA0 warp0 cycles (wait for weights, MMA loop) per step:", {k: (int(gc[i, 0]), int(gc[i, 1])) for i, k in enumerate(["qkv", "o", "gateup", "down", "lm_head"])})
     print("CTA0 attention cycles per step (setup, scores, softmax, PV):", [int(x) for x in eng.mega_attn_cycles])
-    if a.fast and a.batch <= 4 and cfg.layers > 5:
+    if a.fast and a.batch <= 4 and cfg.layers > 5 and cyc[8:8 + 148].any():  # only a -DGV_PROFILE_DETAIL build of decode_gemv.cu stamps these
         g_end, g_start = cyc[8:8 + 148], cyc[156:156 + 148]
         t0 = g_start.min()
         print("gate/up of layer 5 over the CTAs (us after the first start): start p50 %.2f max %.2f | end min %.2f p50 %.2f p90 %.2f max %.2f (CTA %d)" % (
