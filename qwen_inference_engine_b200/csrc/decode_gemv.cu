@@ -37,6 +37,9 @@ constexpr int GV_CW = 8;                // consumer warps
 constexpr int GV_CT = GV_CW * 32;       // consumer threads
 constexpr int GV_THREADS = GV_CT + 32;  // + the producer warp
 constexpr int GV_MAX_SLOTS = 16;
+#ifndef GV_R_SMALL
+#define GV_R_SMALL 2  // weight rows per item in the QKV / o / down phases (measured: 1 = more warps busy but ctx 2048 15 % slower)
+#endif
 constexpr int GV_PT = 2048;             // cached positions one attention task takes
 constexpr int GV_MAX_LAYERS = 64;
 constexpr int GV_NPJ = 7;               // bf16 pairs of a residual row per thread: H <= 2 * 256 * 7
@@ -353,9 +356,10 @@ template <int NB, int KIND>
 __device__ __forceinline__ void gv_gemv(const MegaArgs& a, const GemvArgs& g, const GPhase& p, unsigned char* smem, uint32_t smem_base,
                                         GvRing& ring, const unsigned char* act, GvBest& best, bf16* out) {
   constexpr bool PAIR = KIND == PH_GATEUP;
-  constexpr int R = (PAIR || KIND == PH_LMHEAD) ? 4 : 2;  // weight rows per item
+  constexpr int R = (PAIR || KIND == PH_LMHEAD) ? 4 : GV_R_SMALL;  // weight rows per item
   constexpr int RI = PAIR ? 2 : R;                         // output rows (row pairs) per item
   constexpr int G = R * NB > 4 ? 2 : 4;
+  static_assert(R == 1 || R == 2 || R == 4, "reduction below is written for 1, 2 or 4 rows per item");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = p.K, nv = K >> 3;
   const uint32_t row_bytes = (uint32_t)K * 2u;
@@ -435,8 +439,11 @@ __device__ __forceinline__ void gv_gemv(const MegaArgs& a, const GemvArgs& g, co
           const float g0 = h16 ? t[0] : t[2], g1 = h16 ? t[1] : t[3];
           const float u0 = k0 + __shfl_xor_sync(0xffffffffu, g0, 16), u1 = k1 + __shfl_xor_sync(0xffffffffu, g1, 16);
           s[b] = (h8 ? u1 : u0) + __shfl_xor_sync(0xffffffffu, h8 ? u0 : u1, 8);
+        } else if (R == 2) {
+          const float u0 = (h16 ? t[R - 1] : t[0]) + __shfl_xor_sync(0xffffffffu, h16 ? t[0] : t[R - 1], 16);
+          s[b] = u0 + __shfl_xor_sync(0xffffffffu, u0, 8);
         } else {
-          const float u0 = (h16 ? t[1] : t[0]) + __shfl_xor_sync(0xffffffffu, h16 ? t[0] : t[1], 16);
+          const float u0 = t[0] + __shfl_xor_sync(0xffffffffu, t[0], 16);
           s[b] = u0 + __shfl_xor_sync(0xffffffffu, u0, 8);
         }
       }
@@ -444,16 +451,16 @@ __device__ __forceinline__ void gv_gemv(const MegaArgs& a, const GemvArgs& g, co
       for (int o = 4; o > 0; o >>= 1)
 #pragma unroll
         for (int b = 0; b < NB; ++b) s[b] += __shfl_xor_sync(0xffffffffu, s[b], o);
-      // R = 4: lanes 8 q + i hold weight row q; R = 2: lanes 16 q + i.  Lane i < B of a group finishes batch row i.
+      // R = 4: lanes 8 q + i hold weight row q; R = 1: every lane holds the sum.  Lane i < B of a group finishes batch row i.
       float v1 = 0.f;
 #pragma unroll
       for (int b = 0; b < NB; ++b)
         if ((lane & 7) == b) v1 = s[b];
       float v2 = 0.f;
       if (PAIR) v2 = __shfl_xor_sync(0xffffffffu, v1, 8);  // the up_proj sum next to the gate_proj sum
-      const int q = R == 4 ? lane >> 3 : lane >> 4;          // weight row of the item this lane finishes
+      const int q = R == 4 ? lane >> 3 : (R == 2 ? lane >> 4 : 0);  // weight row of the item this lane finishes
       const int orow = PAIR ? RI * it + (q >> 1) : R * it + q;  // output row (pair) inside the chunk
-      const bool mine = (lane & (R == 4 ? 7 : 15)) < a.B && orow < n && (!PAIR || (q & 1) == 0);
+      const bool mine = (R == 4 ? (lane & 7) : (R == 2 ? (lane & 15) : lane)) < a.B && orow < n && (!PAIR || (q & 1) == 0);
       if (mine) {
         const int b = lane & 7, gr = r + orow;
         const float y = bf2f(f2bf(v1));  // the projection output as the reference stores it (matrix_mul.cu: bf16)
@@ -761,7 +768,10 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
       }
     };
     uint4 kr[4], vr[4];
-    if (preloaded) {  // requested in the shadow of the grid barrier in front of this phase
+    if (preloaded) {  // element offsets from the start of the step; the rows were requested into L2 a phase ago, so these
+                      // loads are back while q is polled, normed and rotated.  (Requested earlier -- behind the QKV phase --
+                      // the values were spilled across the CTA barrier: +1.2 us per layer.)
+      if (S == 1) gv_pre_load<NP>(a, layer, pre);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         kr[u] = pre.k[u];
@@ -1082,7 +1092,9 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_gemv_kernel(const __grid
     stamp();
     if (!DF) grid_arrive(a.bar, epoch);
     gv_norm_w(layers[l].post_ln, a.H, wr);
-    if (my_task) gv_pre_load<NP>(a, l, pre);  // the cached K / V rows of this CTA's task: independent of this step's q
+    // split KV (long contexts): the task's first K / V rows are requested here, in front of the CTA barrier (their latency
+    // is the longer one); one split: at the start of the attention task (see gv_attention)
+    if (my_task && g.n_split > 1) gv_pre_load<NP>(a, l, pre);
     if (!DF) grid_wait(a.bar, epoch); else bar_consumers();
     stamp();
     // ---- q/k-norm + RoPE + KV store + attention
