@@ -42,7 +42,8 @@ constexpr int GV_MAX_SLOTS = 16;
 #endif
 constexpr int GV_PT = 2048;             // cached positions one attention task takes
 constexpr int GV_MAX_LAYERS = 64;
-constexpr int GV_NPJ = 7;               // bf16 pairs of a residual row per thread: H <= 2 * 256 * 7
+constexpr int GV_NVJ = 2;               // 16-byte vectors of a residual row per thread: H <= 8 * 256 * 2
+constexpr int GV_NPJ = 4 * GV_NVJ;      // = bf16 pairs per thread (words 4 v .. 4 v + 3 of vector v = thread + 256 jv)
 constexpr int GV_SMEM_MAX = 227 * 1024;
 constexpr long long GV_SPIN_LIMIT = 4000000000ll;  // ~2 s of SM clocks: trap instead of hanging the GPU
 
@@ -505,11 +506,12 @@ __device__ __forceinline__ void gv_gemv(const MegaArgs& a, const GemvArgs& g, co
 
 // norm weights of the next RMSNorm into registers (requested in front of the grid barrier that precedes their use)
 __device__ __forceinline__ void gv_norm_w(const bf16* w, int H, uint32_t (&wr)[GV_NPJ]) {
-  const uint32_t* wp = reinterpret_cast<const uint32_t*>(w);
+  const uint4* wp = reinterpret_cast<const uint4*>(w);
 #pragma unroll
-  for (int j = 0; j < GV_NPJ; ++j) {
-    const int idx = threadIdx.x + j * GV_CT;
-    wr[j] = idx < (H >> 1) ? __ldg(wp + idx) : 0u;
+  for (int jv = 0; jv < GV_NVJ; ++jv) {
+    const int v = threadIdx.x + jv * GV_CT;
+    const uint4 t = v < (H >> 3) ? __ldg(wp + v) : make_uint4(0u, 0u, 0u, 0u);
+    wr[4 * jv] = t.x, wr[4 * jv + 1] = t.y, wr[4 * jv + 2] = t.z, wr[4 * jv + 3] = t.w;
   }
 }
 // residual rows -> shared memory (raw, for the residual epilogues) + their RMSNorm (normalization.cu:9-21 rounding:
@@ -517,12 +519,14 @@ __device__ __forceinline__ void gv_norm_w(const bf16* w, int H, uint32_t (&wr)[G
 template <int NB>
 __device__ __forceinline__ void gv_load_norm(const MegaArgs& a, unsigned char* smem, const GemvArgs& g, const bf16* rows,
                                              const uint32_t (&wr)[GV_NPJ]) {  // rows == nullptr: the embedding rows of a.ids
-  const int H = a.H, hp = H >> 1;
+  const int H = a.H, hv = H >> 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t xv[NB][GV_NPJ];
+  uint4 xv[NB][GV_NVJ];
   float ss[NB];
-  // Polling discipline: every word of a thread is requested in one round (the checks sit behind ALL requests: a check
-  // next to its load serialises the round trips) and the round is repeated while a word still shows the pattern.
+  // Polling discipline: a thread owns 16-byte vectors of a row (every CTA polls every row: with 4-byte polls the 148 x
+  // B x H / 2 requests on the row's few L2 lines were served one after the other -- the wait grew with the row count);
+  // every vector of a thread is requested in one round (the checks sit behind ALL requests: a check next to its load
+  // serialises the round trips) and the round is repeated while a word still shows the pattern.
   // Measured alternatives: every word polled in turn (a round trip per word: 4 rows cost 7 us), one lane per warp
   // polling a representative word first (+1 round trip, no gain), a pause between rounds (__nanosleep costs ~1 us).
   {
@@ -534,43 +538,48 @@ __device__ __forceinline__ void gv_load_norm(const MegaArgs& a, unsigned char* s
       for (int b = 0; b < NB; ++b) {
         ss[b] = 0.f;
         const bool live = b < a.B;
-        const uint32_t* src =
-            reinterpret_cast<const uint32_t*>(rows ? rows + (size_t)(live ? b : 0) * H : a.embed + (size_t)(live ? max(a.ids[b], 0) : 0) * H);
+        const uint4* src =
+            reinterpret_cast<const uint4*>(rows ? rows + (size_t)(live ? b : 0) * H : a.embed + (size_t)(live ? max(a.ids[b], 0) : 0) * H);
 #pragma unroll
-        for (int j = 0; j < GV_NPJ; ++j) {
-          const int idx = threadIdx.x + j * GV_CT;
-          xv[b][j] = 0u;
-          if (live && idx < hp) xv[b][j] = rows ? gv_ld_relaxed(src + idx) : __ldcg(src + idx);
+        for (int jv = 0; jv < GV_NVJ; ++jv) {
+          const int v = threadIdx.x + jv * GV_CT;
+          xv[b][jv] = make_uint4(0u, 0u, 0u, 0u);
+          if (live && v < hv) xv[b][jv] = rows ? gv_ld_relaxed_v4(src + v) : __ldcg(src + v);
         }
       }
-      if (rows) {  // checked behind ALL requests of the round (a check next to its load would serialise the round trips)
+      if (rows) {  // checked behind ALL requests of the round
 #pragma unroll
         for (int b = 0; b < NB; ++b)
 #pragma unroll
-          for (int j = 0; j < GV_NPJ; ++j)
-            if (b < a.B && threadIdx.x + j * GV_CT < hp) ok = ok && gv_word_ready(xv[b][j]);
+          for (int jv = 0; jv < GV_NVJ; ++jv)
+            if (b < a.B && threadIdx.x + jv * GV_CT < hv)
+              ok = ok && gv_word_ready(xv[b][jv].x) && gv_word_ready(xv[b][jv].y) && gv_word_ready(xv[b][jv].z) && gv_word_ready(xv[b][jv].w);
       }
       if (!ok && clock64() - t0 > GV_SPIN_LIMIT) __trap();
     } while (!ok);
   }
-  uint32_t* xs = reinterpret_cast<uint32_t*>(smem + GO_XS);
+  uint4* xs = reinterpret_cast<uint4*>(smem + GO_XS);
   float* red = reinterpret_cast<float*>(smem + GO_RED);
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
 #pragma unroll
-    for (int j = 0; j < GV_NPJ; ++j) {
-      const int idx = threadIdx.x + j * GV_CT;
-      if (idx < hp) {
-        xs[b * hp + idx] = xv[b][j];
-        const float lo = lo2f(xv[b][j]), hi = hi2f(xv[b][j]);
-        ss[b] += lo * lo + hi * hi;
+    for (int jv = 0; jv < GV_NVJ; ++jv) {
+      const int v = threadIdx.x + jv * GV_CT;
+      if (v < hv) {
+        xs[b * hv + v] = xv[b][jv];
+        const uint32_t w4[4] = {xv[b][jv].x, xv[b][jv].y, xv[b][jv].z, xv[b][jv].w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float lo = lo2f(w4[c]), hi = hi2f(w4[c]);
+          ss[b] += lo * lo + hi * hi;
+        }
       }
     }
     ss[b] = warp_sum(ss[b]);
     if (lane == 0) red[b * GV_CW + warp] = ss[b];
   }
   bar_consumers();
-  uint32_t* xn = reinterpret_cast<uint32_t*>(smem + g.off_act);
+  uint4* xn = reinterpret_cast<uint4*>(smem + g.off_act);
 #pragma unroll
   for (int b = 0; b < NB; ++b) {
     float tot = 0.f;
@@ -578,10 +587,16 @@ __device__ __forceinline__ void gv_load_norm(const MegaArgs& a, unsigned char* s
     for (int w8 = 0; w8 < GV_CW; ++w8) tot += red[b * GV_CW + w8];
     const float rms = sqrtf(tot / (float)H + 1e-04f);
 #pragma unroll
-    for (int j = 0; j < GV_NPJ; ++j) {
-      const int idx = threadIdx.x + j * GV_CT;
-      if (idx < hp)
-        xn[b * hp + idx] = pack2(f2bf(__fdividef(lo2f(xv[b][j]), rms) * lo2f(wr[j])), f2bf(__fdividef(hi2f(xv[b][j]), rms) * hi2f(wr[j])));
+    for (int jv = 0; jv < GV_NVJ; ++jv) {
+      const int v = threadIdx.x + jv * GV_CT;
+      if (v < hv) {
+        const uint32_t w4[4] = {xv[b][jv].x, xv[b][jv].y, xv[b][jv].z, xv[b][jv].w};
+        uint32_t o4[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          o4[c] = pack2(f2bf(__fdividef(lo2f(w4[c]), rms) * lo2f(wr[4 * jv + c])), f2bf(__fdividef(hi2f(w4[c]), rms) * hi2f(wr[4 * jv + c])));
+        xn[b * hv + v] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+      }
     }
   }
   bar_consumers();
@@ -1276,7 +1291,7 @@ bool gv_geometry(int H, int I, int L, int n_q, int n_kv, int hd, int B, int max_
   if (B < 1 || B > DECODE_GEMV_MAX_ROWS || L < 1 || L > GV_MAX_LAYERS) return false;
   if (hd != 64 && hd != 128) return false;
   if (n_kv < 1 || n_q % n_kv != 0) return false;
-  if (H % 128 || I % 128 || Dq % 128 || H > 2 * GV_CT * GV_NPJ) return false;
+  if (H % 128 || I % 128 || Dq % 128 || H > 8 * GV_CT * GV_NVJ) return false;
   const int nb = B <= 1 ? 1 : (B <= 2 ? 2 : 4);
   const int maxk = std::max(std::max(H, I), Dq);
   const int act_bytes = std::max(GA_END, nb * maxk * 2);
