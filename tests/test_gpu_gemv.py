@@ -76,6 +76,27 @@ def test_gemv_decode_steps_vs_reference_order(qie, arch, n_seq, page_size):
     assert agree > 0.8
 
 
+@pytest.mark.parametrize("arch,ctxs,page_size", [("small", [122], 16), ("small", [250, 60], 16), ("small128", [60, 125, 251], 8),
+                                                 ("small128", [254], 1), ("small", [383, 2], 4)])
+def test_gemv_staged_kv_rows_and_bucket_boundaries(qie, arch, ctxs, page_size):
+    """contexts up to a KV bucket of 256 run the kernel build that stages the task's first 128 (head_dim 128: 64) cached K / V
+    rows in shared memory a phase ahead; the steps below cross the end of the staged rows (the rest is loaded in the
+    task), the bucket boundaries 128 -> 256 -> 384 (switch to the build without staging, then to split KV) and ragged rows
+    with fewer positions than lanes -- logits of every step against the reference-order kernel"""
+    n_seq, n_steps = len(ctxs), 10
+    ref = _engine(qie, arch, "reference_order", 0, page_size=page_size)
+    want_t, want_l, want_kv = _run(ref, n_seq, ctxs, n_steps)
+    ref.close()
+    eng = _engine(qie, arch, "fast", 1, page_size=page_size)
+    assert eng.uses_mega(n_seq, 64)
+    got_t, got_l, got_kv = _run(eng, n_seq, ctxs, n_steps, feed=want_t)
+    eng.close()
+    for i in range(n_steps):
+        assert rel_l2(got_l[i], want_l[i]) < 1e-2, f"logits step {i}"
+    for s in range(n_seq):
+        assert rel_l2(got_kv[s][0], want_kv[s][0]) < 1e-2 and rel_l2(got_kv[s][1], want_kv[s][1]) < 1e-2
+
+
 @pytest.mark.parametrize("arch,ctxs", [("small", [700]), ("small", [1500, 33]), ("small128", [2000, 1, 513, 300]),
                                        ("qwen2.5-0.5b", [2048])])
 def test_gemv_split_kv_long_context(qie, arch, ctxs):
