@@ -33,7 +33,10 @@ namespace {
 
 enum { PH_QKV = 0, PH_O = 1, PH_GATEUP = 2, PH_DOWN = 3, PH_LMHEAD = 4 };
 
-constexpr int GV_CW = 8;                // consumer warps
+// consumer warps.  7 + the producer = 8 warps = two per SM sub-partition: 255 registers per thread are available and
+// ptxas uses 242 without spills.  With 8 + 1 one sub-partition hosts three warps, which caps EVERY thread at 168
+// registers (256-512 bytes of spills in the GEMV loops): batch 1 2248 -> 2332 tok/s, batch 4 / ctx 1000 3748 -> 3952.
+constexpr int GV_CW = 7;
 constexpr int GV_CT = GV_CW * 32;       // consumer threads
 constexpr int GV_THREADS = GV_CT + 32;  // + the producer warp
 constexpr int GV_MAX_SLOTS = 16;
@@ -127,7 +130,7 @@ constexpr int GV_PART = 4;  // floats in front of a split's partial output row: 
 #define GV_STAGE_MAX_KV_ 256
 #endif
 constexpr int GV_STAGE_MAX_KV = GV_STAGE_MAX_KV_;  // contexts (kv bucket) up to which the first K / V rows are staged in shared memory
-constexpr int GV_KVS = 16384;  // bytes of staged K (and of V) rows per task: 4 * NG positions = 128 at head_dim 64, 64 at 128
+constexpr int GV_KVS = 4 * GV_CW * 4 * 64 * 2;  // bytes of staged K (and of V) rows per task: 4 * NG positions = 112 at head_dim 64, 56 at 128
 
 __device__ __forceinline__ void mbar_init(uint32_t addr, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
