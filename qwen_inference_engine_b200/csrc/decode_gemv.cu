@@ -608,6 +608,7 @@ __device__ __forceinline__ void gv_load_norm(const MegaArgs& a, unsigned char* s
 // ---------------------------------------------------------------- attention: split-KV flash decoding
 struct GvTask {
   int b, h, sp, kvh, ps, p0, p1, pc1, pg0;
+  int page_new;  // pool page of the position this step appends (set for the CTA's staged task at the start of the step)
   bool has_new;
 };
 template <int NP>
@@ -742,7 +743,7 @@ __device__ __forceinline__ void gv_pre_stage(const MegaArgs& a, const GemvArgs& 
 
 template <int NP, bool KS>
 __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& g, const GvAct& A, int layer, unsigned char* smem,
-                                             const MegaLayer& w, GvPre<NP>& pre, bool preloaded) {
+                                             const MegaLayer& w, GvPre<NP>& pre, bool preloaded, const GvTask& task0) {
   constexpr int HD = 64 * NP, LPP = HD / 8, GPW = 32 / LPP, NG = GV_CW * GPW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = warp * GPW + lane / LPP, j = lane % LPP;
@@ -767,8 +768,16 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
   const int* pages = reinterpret_cast<const int*>(pf + GP_PAGES);
   const float rs = 1.0f / sqrtf((float)HD);
   for (int task = blockIdx.x; task < ntask; task += gridDim.x) {
+    // the CTA's staged task was worked out at the start of the step: a.pos / a.slot / block-table loads here would be
+    // two to three dependent L2 round trips in front of everything else, once per layer
     GvTask t;
-    const bool any = gv_task<NP>(a, g, task, psh, t);
+    bool any = true;
+    if (preloaded) {
+      t = task0;
+    } else {
+      any = gv_task<NP>(a, g, task, psh, t);
+      t.page_new = -1;
+    }
     const int b = t.b, h = t.h, kvh = t.kvh, ps = t.ps, p0 = t.p0, p1 = t.p1, pc1 = t.pc1, pg0 = t.pg0;
     float* part = A.part(layer) + (size_t)((b * a.n_q + h) * S + t.sp) * (HD + GV_PART);
     if (!any) {  // empty split (S > 1 only)
@@ -800,7 +809,8 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
     }
     const bool has_new = t.has_new;
     const bool writer = has_new && h == kvh * Gq;
-    const int* bt = a.block_table + (size_t)a.slot[b] * a.max_pages;
+    int page_new = t.page_new;
+    if (!preloaded && writer) page_new = a.block_table[(size_t)a.slot[b] * a.max_pages + ps / psz];
     const bf16* row = A.qkv(layer) + (size_t)b * QKV;  // polled: the QKV phase of this layer stores it
     // the first 4 * NG cached positions of K and V: requested before anything that depends on this step's q
     auto load4 = [&](int base, int kv, uint4 (&r4)[4]) {
@@ -855,7 +865,7 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
         if (w.k_norm) head_norm<NP>(v, knw, lane);
         head_rope<NP>(v, cos_s, sin_s, lane);
         head_store<NP>(v, knew, lane);
-        if (writer) head_store<NP>(v, a.kv.chunk(bt[ps / psz], layer, 0, kvh) + (size_t)(ps % psz) * HD, lane);
+        if (writer) head_store<NP>(v, a.kv.chunk(page_new, layer, 0, kvh) + (size_t)(ps % psz) * HD, lane);
       }
     } else if (warp == 2) {
       if (has_new) {
@@ -864,7 +874,7 @@ __device__ __forceinline__ void gv_attention(const MegaArgs& a, const GemvArgs& 
           const uint32_t u = gv_poll_u32(row + Dq + Dkv + (size_t)kvh * HD + 64 * p + 2 * lane);
           reinterpret_cast<uint32_t*>(vnew)[32 * p + lane] = u;
           if (writer)
-            reinterpret_cast<uint32_t*>(a.kv.chunk(bt[ps / psz], layer, 1, kvh) + (size_t)(ps % psz) * HD)[32 * p + lane] = u;
+            reinterpret_cast<uint32_t*>(a.kv.chunk(page_new, layer, 1, kvh) + (size_t)(ps % psz) * HD)[32 * p + lane] = u;
         }
       }
     }
@@ -1124,10 +1134,11 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_gemv_kernel(const __grid
   const int psz = a.kv.page_size;
   const int psh = (psz & (psz - 1)) == 0 ? __ffs(psz) - 1 : -1;
   const int ntask = a.B * a.n_q * g.n_split;
-  GvTask task0;
+  GvTask task0{};
   GvPre<NP> pre;
   bool my_task = ntask <= (int)gridDim.x && (int)blockIdx.x < ntask;
   if (my_task) my_task = gv_task<NP>(a, g, blockIdx.x, psh, task0);
+  task0.page_new = my_task ? a.block_table[(size_t)a.slot[task0.b] * a.max_pages + task0.ps / psz] : -1;
   if (my_task) gv_attn_stage<NP, KS>(a, g, 0, smem, layers[0], task0, psh, ST_STEP | ST_LAYER);
   bar_consumers();
   if (my_task) {
@@ -1153,7 +1164,7 @@ __global__ void __launch_bounds__(GV_THREADS, 1) decode_gemv_kernel(const __grid
     if (!DF) grid_wait(a.bar, epoch); else bar_consumers();
     stamp();
     // ---- q/k-norm + RoPE + KV store + attention
-    gv_attention<NP, KS>(a, g, A, l, smem, layers[l], pre, my_task);
+    gv_attention<NP, KS>(a, g, A, l, smem, layers[l], pre, my_task, task0);
     stamp();
     if (!DF) grid_sync(a.bar, epoch);
     stamp();
